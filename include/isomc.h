@@ -1,0 +1,167 @@
+/*
+ * isomc.h -- C ABI of libisomc_b200.so: B200-native (sm_100a) MarchingCubes extraction.
+ *
+ * Drop-in boundary for the hot path of the Rust crate swiftcoder/isosurface:
+ *
+ *     MarchingCubes::<Signed>::new(size).extract(&source, &mut extractor)
+ *         (reference src/marching_cubes.rs:46-50,59-82)
+ *
+ * The reference has no FFI of its own; these are the entry points a `build.rs + extern "C"`
+ * shim inside the crate binds (INTEGRATION.md shows that shim).  Conventions:
+ *   - plain pointers and sizes only; every call returns an isomc_status (0 = OK, < 0 = error);
+ *     nothing unwinds across the boundary; isomc_last_error() gives the message;
+ *   - a handle mirrors `&mut self` of MarchingCubes: NOT thread-safe, one extract at a time,
+ *     distinct handles are independent (one CUDA stream each);
+ *   - result buffers are owned by the handle and stay valid until the next extract/destroy on
+ *     it (mirrors the borrow of the reference's builder state); copy-out fills caller memory;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     ISOMC_ERR_CUDA.
+ *
+ * Lattice contract (reference src/traversal/primal_grid.rs:44-45,59,63-67): for `size` = N the
+ * field is sampled on N x N x (N+1) lattice points, coordinate(i) = (i as f32) * (1.0f/(N-1)),
+ * and (N-1) x (N-1) x N cells are visited in (z, y, x) order.  Dense grids therefore carry
+ * N*N*(N+1) f32 values, x fastest, then y, then z.
+ *
+ * Output contract (reference src/extractor.rs:72-93, src/mesh.rs:91-100,240-251): vertices as
+ * packed xyz f32 in the reference's emission order (first reference while walking triangles in
+ * cell order), then 3 u32 indices per triangle in the reference's triangle order.
+ */
+#ifndef ISOMC_H
+#define ISOMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct isomc isomc_t;
+
+typedef enum isomc_status {
+    ISOMC_OK = 0,
+    ISOMC_ERR_BAD_ARG = -1,
+    ISOMC_ERR_CUDA = -2,            /* no device / driver / kernel failure */
+    ISOMC_ERR_OOM = -3,
+    ISOMC_ERR_INDEX_OVERFLOW = -4,  /* >= 2^32 vertices or triangles: the u32 index mesh cannot hold it
+                                       (the reference silently truncates, src/extractor.rs:90-92) */
+    ISOMC_ERR_UNSUPPORTED_SOURCE = -5,
+    ISOMC_ERR_NO_RESULT = -6,       /* counts/copy-out before any successful extract */
+    ISOMC_ERR_NCCL = -7
+} isomc_status;
+
+/* ---- implicit sources: a postfix program over the crate's shapes -------------------------
+ * Encodes `Sampler::new(&tree)` for trees built from reference src/implicit/ (scalar side):
+ *   SPHERE    a = radius                           sphere.rs:35-39
+ *   TORUS     a = radius, b = tube_radius          torus.rs:40-46
+ *   CYLINDER  a = radius, b = half_length          cylinder.rs:41-48
+ *   PRISM     a,b,c = half_extent                  rectangular_prism.rs:36-41
+ *   UNION / INTERSECTION / DIFFERENCE              csg.rs:35-39,68-72,96-100
+ *       pop two values (first-pushed = field `a`, second = field `b`):
+ *       min(a,b) / max(a,b) / max(b,-a)
+ *   TRANSLATE_PUSH a,b,c ... TRANSLATE_POP         examples/common/sources.rs:38-43
+ *       the nodes in between are sampled at q = p - (a,b,c)
+ * Evaluation is IEEE binary32, no FMA contraction, same operation order as the reference.    */
+enum {
+    ISOMC_SDF_SPHERE = 1,
+    ISOMC_SDF_TORUS = 2,
+    ISOMC_SDF_CYLINDER = 3,
+    ISOMC_SDF_PRISM = 4,
+    ISOMC_SDF_UNION = 16,
+    ISOMC_SDF_INTERSECTION = 17,
+    ISOMC_SDF_DIFFERENCE = 18,
+    ISOMC_SDF_TRANSLATE_PUSH = 32,
+    ISOMC_SDF_TRANSLATE_POP = 33
+};
+#define ISOMC_SDF_MAX_NODES 48
+#define ISOMC_SDF_MAX_STACK 8      /* values live at once (CSG nesting depth) */
+#define ISOMC_SDF_MAX_TRANSLATE 4  /* nested TRANSLATE_PUSH */
+
+typedef struct isomc_sdf_node {
+    uint32_t op;
+    float a, b, c;
+} isomc_sdf_node;
+
+/* per-extract statistics (new; the reference has none) */
+typedef struct isomc_stats {
+    uint64_t n_vertices, n_triangles, n_active_cells;
+    uint64_t n_samples, n_cells;
+    uint64_t algorithmic_bytes;   /* 4*S + 12*V + 12*T (grid sources) */
+    float ms_sign, ms_count, ms_scan, ms_emit, ms_total; /* CUDA-event times of the last timed extract */
+    uint32_t kernel_launches;     /* kernels launched by the last extract */
+    uint32_t emit_reruns;         /* 1 if the output buffers had to grow and emission re-ran */
+} isomc_stats;
+
+/* ---- lifecycle:  MarchingCubes::new(size) / Drop ---------------------------------------- */
+int32_t isomc_create(uint32_t size, int32_t device, isomc_t **out);
+int32_t isomc_destroy(isomc_t *h);
+const char *isomc_last_error(const isomc_t *h);      /* h may be NULL: last create() error */
+const char *isomc_version(void);
+
+/* ---- extract(&source, ...) --------------------------------------------------------------- */
+/* source = implicit tree (evaluated on device; no grid is materialised) */
+int32_t isomc_extract_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes);
+/* source = dense lattice already resident on the handle's device: N*N*(N+1) f32 */
+int32_t isomc_extract_grid_device(isomc_t *h, const float *d_grid);
+/* source = dense lattice in host memory (H2D copy, then as above) */
+int32_t isomc_extract_grid_host(isomc_t *h, const float *h_grid);
+
+/* ---- results:  the two Vecs behind extractor::IndexedVertices --------------------------- */
+int32_t isomc_counts(isomc_t *h, uint64_t *n_vertices, uint64_t *n_triangles, uint64_t *n_active_cells);
+int32_t isomc_device_buffers(isomc_t *h, const float **d_xyz, const uint32_t **d_idx);
+int32_t isomc_copy_out(isomc_t *h, float *xyz /* 3*V */, uint32_t *idx /* 3*T */);
+int32_t isomc_stats_get(isomc_t *h, isomc_stats *out);
+
+/* ---- stream control (benchmarks time with CUDA events on the launching stream) ---------- */
+int32_t isomc_get_stream(isomc_t *h, void **cuda_stream);
+/* adopt a caller-owned cudaStream_t (e.g. the framework's current stream); NULL = back to the handle's own */
+int32_t isomc_set_stream(isomc_t *h, void *cuda_stream);
+/* enqueue the whole extract without synchronising; finish with isomc_finish() */
+int32_t isomc_enqueue_grid_device(isomc_t *h, const float *d_grid);
+int32_t isomc_enqueue_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes);
+int32_t isomc_finish(isomc_t *h);
+/* pre-size the output buffers so steady-state extracts never re-run emission */
+int32_t isomc_reserve(isomc_t *h, uint64_t n_vertices, uint64_t n_triangles);
+/* collect per-kernel CUDA-event timings into isomc_stats on subsequent extracts (0/1) */
+int32_t isomc_set_profiling(isomc_t *h, int32_t on);
+
+/* ---- z-slab sharding across GPUs (new) -------------------------------------
+ * Rank g of G owns cell layers [z_begin, z_end) of the N cell layers.  It is given sample
+ * layers [z_begin - (z_begin > 0), z_end] (one halo layer on the high side, and one extra on the
+ * low side so that it can re-derive the ids of the boundary vertices the previous rank owns).
+ * Protocol:  slab_count -> exchange totals (NCCL all-gather, 3 x u64 per rank) -> slab_emit.
+ * Concatenating the ranks' vertex and index arrays in rank order gives exactly the single-GPU
+ * (= reference) mesh.                                                                         */
+int32_t isomc_slab_create(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t device, isomc_t **out);
+/* phase 1: classify + count.  d_slab = first sample layer of the slab, (layers)*N*N f32 */
+int32_t isomc_slab_count_grid_device(isomc_t *h, const float *d_slab);
+int32_t isomc_slab_count_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes);
+/* totals[0] = vertices owned by this slab, [1] = of those, vertices created before the slab's
+ * last cell layer, [2] = triangles owned by this slab.  Synchronises the stream. */
+int32_t isomc_slab_totals(isomc_t *h, uint64_t totals[3]);
+/* device pointer to the same three u64 (valid after slab_count is enqueued; for on-stream NCCL) */
+int32_t isomc_slab_totals_device(isomc_t *h, const uint64_t **d_totals);
+/* phase 2: emit with global numbering.  vertex_base = sum of totals[0] of lower ranks;
+ * boundary_base = vertex_base[g-1] + totals[1][g-1] (ignored for z_begin == 0). */
+int32_t isomc_slab_emit(isomc_t *h, uint64_t vertex_base, uint64_t boundary_base);
+/* phase 2, fully on-stream: d_gathered = all-gathered totals, 3 x u64 per rank, rank-major;
+ * the bases are derived on the device, no host round trip between count and emit. */
+int32_t isomc_slab_emit_gathered(isomc_t *h, const uint64_t *d_gathered, uint32_t rank, uint32_t n_ranks);
+
+/* ---- debug / parity helpers -------------------------------------------------------------- */
+/* per-cell cube_index in the reference's corner order (marching_cubes_impl.rs:26-37) for the
+ * last extract: (N-1)*(N-1)*N bytes to host memory, x fastest */
+int32_t isomc_debug_cube_indices(isomc_t *h, uint8_t *host_out);
+/* evaluate an SDF program on the device at n points (xyz packed) -> host values */
+int32_t isomc_debug_sample_sdf(int32_t device, const isomc_sdf_node *prog, uint32_t n_nodes,
+                               const float *h_xyz, uint64_t n_points, float *h_out);
+
+/* ---- synthetic fields used by bench.py and the tests ---------------------- */
+enum { ISOMC_FIELD_FBM = 1, ISOMC_FIELD_GYROID = 2, ISOMC_FIELD_SPHERE_UNION = 3 };
+/* fills sample layers [z_first, z_first + n_layers) of the size*size*(size+1) lattice into d_out */
+int32_t isomc_synth_field(int32_t device, int32_t kind, uint32_t size, uint64_t seed,
+                          uint32_t z_first, uint32_t n_layers, float *d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISOMC_H */

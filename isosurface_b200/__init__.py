@@ -1,0 +1,16 @@
+"""isosurface_b200 -- B200-native (sm_100a) MarchingCubes extraction behind the API of the Rust
+crate swiftcoder/isosurface.  The product is `libisomc_b200.so` (C ABI: include/isomc.h); this
+package is the Python host-side mirror of the crate's interface for that one path:
+
+    MarchingCubes(size).extract(Sampler(source), IndexedVertices(vertices, indices))
+
+See DESIGN.md for the path, INTEGRATION.md for the Rust-side binding.
+"""
+from .extractor import ArrayMesh, Extractor, IndexedVertices, OnlyVertices
+from .marching_cubes import MarchingCubes
+from .source import (Cylinder, DenseGrid, DeviceSource, Difference, Intersection, RectangularPrism, Sampler,
+                     Sphere, Torus, Translate, Union)
+
+__all__ = ["MarchingCubes", "Sampler", "DenseGrid", "DeviceSource", "Sphere", "Torus", "Cylinder",
+           "RectangularPrism", "Union", "Intersection", "Difference", "Translate", "Extractor",
+           "IndexedVertices", "OnlyVertices", "ArrayMesh"]

@@ -1,0 +1,594 @@
+/*
+ * isomc_api.cu -- the C ABI of include/isomc.h: handle management, stream-ordered pipeline,
+ * result delivery.  Mirrors `MarchingCubes::new(size)` / `.extract(&source, &mut extractor)`
+ * (reference src/marching_cubes.rs:46-50,59-82) and the IndexedVertices sink
+ * (src/extractor.rs:72-93).  No CPU fallback: every compute entry point needs a CUDA device.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/isomc.h"
+#include "isomc_device.cuh"
+#include "isomc_kernels.h"
+#include "isomc_tables.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum SrcKind { SRC_NONE = 0, SRC_GRID = 1, SRC_SDF = 2 };
+
+}  // namespace
+
+struct isomc {
+    uint32_t size = 0, z_begin = 0, z_end = 0;
+    int device = 0, sms = 148;
+    Geo g{};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    /* scratch */
+    uint32_t *signs = nullptr, *segpre = nullptr, *rowV = nullptr, *rowT = nullptr, *rowA = nullptr;
+    unsigned long long *layerTot = nullptr, *totals = nullptr; /* totals: 12 u64 */
+    uint32_t *vofs = nullptr, *ticket = nullptr;
+    McTables *tabs = nullptr;
+    unsigned long long *h_totals = nullptr; /* pinned */
+    float *stage_grid = nullptr;            /* device copy of a host grid */
+    /* results */
+    float *xyz = nullptr;
+    uint32_t *idx = nullptr;
+    uint64_t cap_v = 0, cap_t = 0;
+    uint64_t n_v = 0, n_t = 0, n_a = 0;
+    bool have_result = false, counted = false, emitted = false, totals_valid = false;
+    /* source of the extract in flight (needed to re-run emission after a buffer grow) */
+    SrcKind kind = SRC_NONE;
+    const float *d_grid = nullptr;
+    SdfProgram prog{};
+    /* profiling */
+    bool profiling = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    isomc_stats stats{};
+    std::string err;
+};
+
+namespace {
+
+int32_t fail(isomc *h, int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(h, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail((h), e_ == cudaErrorMemoryAllocation ? ISOMC_ERR_OOM : ISOMC_ERR_CUDA,       \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int32_t validate_program(isomc *h, const isomc_sdf_node *prog, uint32_t n, SdfProgram *out) {
+    if (!prog || n == 0) return fail(h, ISOMC_ERR_BAD_ARG, "empty SDF program");
+    if (n > ISOMC_SDF_MAX_NODES)
+        return fail(h, ISOMC_ERR_UNSUPPORTED_SOURCE, "SDF program has %u nodes (max %d)", n, ISOMC_SDF_MAX_NODES);
+    int depth = 0, tdepth = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        switch (prog[i].op) {
+        case ISOMC_SDF_SPHERE: case ISOMC_SDF_TORUS: case ISOMC_SDF_CYLINDER: case ISOMC_SDF_PRISM:
+            if (++depth > ISOMC_SDF_MAX_STACK)
+                return fail(h, ISOMC_ERR_UNSUPPORTED_SOURCE, "SDF program needs more than %d live values", ISOMC_SDF_MAX_STACK);
+            break;
+        case ISOMC_SDF_UNION: case ISOMC_SDF_INTERSECTION: case ISOMC_SDF_DIFFERENCE:
+            if (depth < 2) return fail(h, ISOMC_ERR_BAD_ARG, "SDF node %u: binary op with < 2 operands", i);
+            --depth;
+            break;
+        case ISOMC_SDF_TRANSLATE_PUSH:
+            if (++tdepth > ISOMC_SDF_MAX_TRANSLATE)
+                return fail(h, ISOMC_ERR_UNSUPPORTED_SOURCE, "more than %d nested translations", ISOMC_SDF_MAX_TRANSLATE);
+            break;
+        case ISOMC_SDF_TRANSLATE_POP:
+            if (--tdepth < 0) return fail(h, ISOMC_ERR_BAD_ARG, "SDF node %u: TRANSLATE_POP without PUSH", i);
+            break;
+        default:
+            return fail(h, ISOMC_ERR_UNSUPPORTED_SOURCE, "SDF node %u: unknown op %u (arbitrary closures are not a device path)", i, prog[i].op);
+        }
+    }
+    if (depth != 1 || tdepth != 0) return fail(h, ISOMC_ERR_BAD_ARG, "SDF program does not reduce to one value");
+    memset(out, 0, sizeof *out);
+    memcpy(out->nodes, prog, n * sizeof(isomc_sdf_node));
+    out->n = n;
+    return ISOMC_OK;
+}
+
+int32_t bind_device(isomc *h) {
+    CU(h, cudaSetDevice(h->device));
+    return ISOMC_OK;
+}
+
+int32_t ensure_capacity(isomc *h, uint64_t nv, uint64_t nt) {
+    if (nv > h->cap_v) {
+        uint64_t want = nv + nv / 16 + 1024;
+        if (h->xyz) CU(h, cudaFree(h->xyz));
+        h->xyz = nullptr; h->cap_v = 0;
+        CU(h, cudaMalloc(&h->xyz, want * 12));
+        h->cap_v = want;
+    }
+    if (nt > h->cap_t) {
+        uint64_t want = nt + nt / 16 + 1024;
+        if (h->idx) CU(h, cudaFree(h->idx));
+        h->idx = nullptr; h->cap_t = 0;
+        CU(h, cudaMalloc(&h->idx, want * 12));
+        h->cap_t = want;
+    }
+    return ISOMC_OK;
+}
+
+/* phase 1: sign bits, counts, scans.  Everything stream-ordered, nothing synchronises. */
+int32_t enqueue_count(isomc *h) {
+    const Geo &g = h->g;
+    h->have_result = false; h->counted = false; h->emitted = false; h->totals_valid = false;
+    h->stats.kernel_launches = 0; h->stats.emit_reruns = 0;
+    if (g.ncl == 0 || g.ncx == 0) { /* size == 1: the reference visits no cells */
+        CU(h, cudaMemsetAsync(h->totals, 0, 12 * sizeof(unsigned long long), h->stream));
+        h->counted = true;
+        return ISOMC_OK;
+    }
+    if (h->profiling) CU(h, cudaEventRecord(h->ev[0], h->stream));
+    CU(h, cudaMemsetAsync(h->layerTot, 0, (size_t)g.ncl * 3 * sizeof(unsigned long long), h->stream));
+    if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, h->sms, h->stream));
+    else CU(h, isomc_launch_sign_sdf(g, h->prog, h->signs, h->sms, h->stream));
+    if (h->profiling) CU(h, cudaEventRecord(h->ev[1], h->stream));
+    CU(h, isomc_launch_count(g, h->signs, h->tabs, h->segpre, h->rowV, h->rowT, h->rowA, h->layerTot, h->sms, h->stream));
+    if (h->profiling) CU(h, cudaEventRecord(h->ev[2], h->stream));
+    CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, h->stream));
+    if (h->profiling) CU(h, cudaEventRecord(h->ev[3], h->stream));
+    h->stats.kernel_launches += 3;
+    h->counted = true;
+    return ISOMC_OK;
+}
+
+int32_t enqueue_emit(isomc *h) {
+    const Geo &g = h->g;
+    if (g.ncl == 0 || g.ncx == 0) { h->emitted = true; return ISOMC_OK; }
+    CU(h, cudaMemsetAsync(h->ticket, 0, sizeof(uint32_t), h->stream));
+    if (h->kind == SRC_GRID)
+        CU(h, isomc_launch_emit_grid(g, h->d_grid, h->signs, h->segpre, h->rowV, h->rowT, h->tabs, h->totals, h->vofs,
+                                     h->ticket, h->xyz, h->idx, h->cap_v, h->cap_t, h->sms, h->stream));
+    else
+        CU(h, isomc_launch_emit_sdf(g, h->prog, h->signs, h->segpre, h->rowV, h->rowT, h->tabs, h->totals, h->vofs,
+                                    h->ticket, h->xyz, h->idx, h->cap_v, h->cap_t, h->sms, h->stream));
+    h->stats.kernel_launches += 1;
+    h->emitted = true;
+    return ISOMC_OK;
+}
+
+/* bring the totals to the host (synchronises) */
+int32_t fetch_totals(isomc *h) {
+    if (h->totals_valid) return ISOMC_OK;
+    CU(h, cudaMemcpyAsync(h->h_totals, h->totals, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->totals_valid = true;
+    return ISOMC_OK;
+}
+
+int32_t finish_impl(isomc *h) {
+    if (!h->counted) return fail(h, ISOMC_ERR_NO_RESULT, "finish() without an extract in flight");
+    int32_t rc = fetch_totals(h);
+    if (rc) return rc;
+    const uint64_t nv = h->h_totals[8], nt = h->h_totals[10];
+    /* ids are u32 and the whole numbering (incl. a slab's ghost layer) must fit */
+    if (h->h_totals[0] >= (1ull << 32) || h->h_totals[1] >= (1ull << 32))
+        return fail(h, ISOMC_ERR_INDEX_OVERFLOW, "mesh has %llu vertices / %llu triangles: does not fit u32 indices",
+                    (unsigned long long)h->h_totals[0], (unsigned long long)h->h_totals[1]);
+    const bool must_rerun = !h->emitted || nv > h->cap_v || nt > h->cap_t;
+    if (must_rerun) {
+        if (h->emitted) h->stats.emit_reruns = 1;
+        rc = ensure_capacity(h, nv, nt);
+        if (rc) return rc;
+        rc = enqueue_emit(h);
+        if (rc) return rc;
+    }
+    if (h->profiling) CU(h, cudaEventRecord(h->ev[4], h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->n_v = nv; h->n_t = nt; h->n_a = h->h_totals[11];
+    h->have_result = true;
+    isomc_stats &s = h->stats;
+    s.n_vertices = nv; s.n_triangles = nt; s.n_active_cells = h->n_a;
+    s.n_samples = (uint64_t)h->g.N * h->g.N * h->g.nsl;
+    s.n_cells = (uint64_t)h->g.ncx * h->g.ncx * (h->g.ncl - h->g.ghost);
+    s.algorithmic_bytes = 4 * s.n_samples + 12 * nv + 12 * nt;
+    if (h->profiling && h->g.ncl && !must_rerun) {
+        cudaEventElapsedTime(&s.ms_sign, h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&s.ms_count, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&s.ms_scan, h->ev[2], h->ev[3]);
+        cudaEventElapsedTime(&s.ms_emit, h->ev[3], h->ev[4]);
+        cudaEventElapsedTime(&s.ms_total, h->ev[0], h->ev[4]);
+    }
+    return ISOMC_OK;
+}
+
+int32_t set_vofs(isomc *h, uint32_t v) {
+    CU(h, cudaMemcpyAsync(h->vofs, &v, sizeof v, cudaMemcpyHostToDevice, h->stream));
+    return ISOMC_OK;
+}
+
+int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t device, isomc_t **out) {
+    if (!out) return fail(nullptr, ISOMC_ERR_BAD_ARG, "out == NULL");
+    *out = nullptr;
+    /* size == 0 underflows in the reference (primal_grid.rs:44); size > 8192 overflows the packed row prefixes */
+    if (size < 1 || size > 8192) return fail(nullptr, ISOMC_ERR_BAD_ARG, "size %u out of range [1, 8192]", size);
+    if (z_begin >= z_end || z_end > size) return fail(nullptr, ISOMC_ERR_BAD_ARG, "bad slab [%u, %u) of %u", z_begin, z_end, size);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, ISOMC_ERR_CUDA, "no CUDA device: %s (libisomc_b200 has no CPU fallback)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, ISOMC_ERR_BAD_ARG, "device %d out of range (%d devices)", device, ndev);
+    isomc *h = new (std::nothrow) isomc();
+    if (!h) return fail(nullptr, ISOMC_ERR_OOM, "host allocation failed");
+    h->size = size; h->z_begin = z_begin; h->z_end = z_end; h->device = device;
+    Geo &g = h->g;
+    g.N = size; g.ncx = size - 1;
+    g.nsegx = (g.ncx + 31) / 32; g.nws = g.nsegx + 1;
+    g.ghost = z_begin > 0 ? 1u : 0u;
+    g.gz0 = z_begin - g.ghost;
+    g.ncl = (g.ncx == 0) ? 0 : (z_end - z_begin + g.ghost);
+    g.nsl = g.ncl + 1;
+    g.inv = 1.0f / (float)(size - 1);
+    int32_t rc = ISOMC_OK;
+    auto body = [&]() -> int32_t {
+        CU(h, cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU(h, cudaGetDeviceProperties(&prop, device));
+        h->sms = prop.multiProcessorCount;
+        CU(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
+        for (auto &ev : h->ev) CU(h, cudaEventCreate(&ev));
+        McTables host_tabs;
+        if (isomc_build_tables(&host_tabs)) return fail(h, ISOMC_ERR_BAD_ARG, "case table is inconsistent");
+        CU(h, cudaMalloc(&h->tabs, sizeof(McTables)));
+        CU(h, cudaMemcpy(h->tabs, &host_tabs, sizeof(McTables), cudaMemcpyHostToDevice));
+        const uint64_t nrows_s = (uint64_t)g.nsl * g.N, nrows_c = (uint64_t)g.ncl * g.ncx;
+        CU(h, cudaMalloc(&h->signs, (nrows_s * g.nws + 4) * sizeof(uint32_t)));
+        CU(h, cudaMalloc(&h->segpre, (nrows_c * g.nsegx + 4) * sizeof(uint32_t)));
+        CU(h, cudaMalloc(&h->rowV, (nrows_c + 4) * sizeof(uint32_t)));
+        CU(h, cudaMalloc(&h->rowT, (nrows_c + 4) * sizeof(uint32_t)));
+        CU(h, cudaMalloc(&h->rowA, (nrows_c + 4) * sizeof(uint32_t)));
+        CU(h, cudaMalloc(&h->layerTot, ((size_t)g.ncl * 3 + 3) * sizeof(unsigned long long)));
+        CU(h, cudaMalloc(&h->totals, 12 * sizeof(unsigned long long)));
+        CU(h, cudaMemset(h->totals, 0, 12 * sizeof(unsigned long long)));
+        CU(h, cudaMalloc(&h->vofs, sizeof(uint32_t)));
+        CU(h, cudaMemset(h->vofs, 0, sizeof(uint32_t)));
+        CU(h, cudaMalloc(&h->ticket, sizeof(uint32_t)));
+        CU(h, cudaMallocHost(&h->h_totals, 12 * sizeof(unsigned long long)));
+        return ISOMC_OK;
+    };
+    rc = body();
+    if (rc) {
+        g_create_error = h->err;
+        isomc_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return ISOMC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *isomc_version(void) { return "isomc_b200 0.1.0 (sm_100a)"; }
+
+int32_t isomc_create(uint32_t size, int32_t device, isomc_t **out) { return create_impl(size, 0, size, device, out); }
+
+int32_t isomc_slab_create(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t device, isomc_t **out) {
+    return create_impl(size, z_begin, z_end, device, out);
+}
+
+int32_t isomc_destroy(isomc_t *h) {
+    if (!h) return ISOMC_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->signs); cudaFree(h->segpre); cudaFree(h->rowV); cudaFree(h->rowT); cudaFree(h->rowA);
+    cudaFree(h->layerTot); cudaFree(h->totals); cudaFree(h->vofs); cudaFree(h->ticket); cudaFree(h->tabs);
+    cudaFree(h->xyz); cudaFree(h->idx); cudaFree(h->stage_grid);
+    if (h->h_totals) cudaFreeHost(h->h_totals);
+    for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return ISOMC_OK;
+}
+
+const char *isomc_last_error(const isomc_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int32_t isomc_get_stream(isomc_t *h, void **cuda_stream) {
+    if (!h || !cuda_stream) return ISOMC_ERR_BAD_ARG;
+    *cuda_stream = (void *)h->stream;
+    return ISOMC_OK;
+}
+
+int32_t isomc_set_stream(isomc_t *h, void *cuda_stream) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return ISOMC_OK;
+}
+
+int32_t isomc_set_profiling(isomc_t *h, int32_t on) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    h->profiling = on != 0;
+    return ISOMC_OK;
+}
+
+int32_t isomc_reserve(isomc_t *h, uint64_t n_vertices, uint64_t n_triangles) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return ensure_capacity(h, n_vertices, n_triangles);
+}
+
+/* ---- full extracts ------------------------------------------------------------------------ */
+
+static int32_t enqueue_full(isomc_t *h) {
+    if (h->z_begin != 0 || h->z_end != h->size)
+        return fail(h, ISOMC_ERR_BAD_ARG, "this handle is a slab [%u, %u): use the isomc_slab_* calls", h->z_begin, h->z_end);
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    rc = set_vofs(h, 0);
+    if (rc) return rc;
+    rc = enqueue_count(h);
+    if (rc) return rc;
+    /* optimistic emission into the buffers of the previous extract; finish() re-runs it if they are too small */
+    if (h->cap_v > 0 || h->cap_t > 0) rc = enqueue_emit(h);
+    return rc;
+}
+
+int32_t isomc_enqueue_grid_device(isomc_t *h, const float *d_grid) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!d_grid) return fail(h, ISOMC_ERR_BAD_ARG, "d_grid == NULL");
+    h->kind = SRC_GRID; h->d_grid = d_grid;
+    return enqueue_full(h);
+}
+
+int32_t isomc_enqueue_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    int32_t rc = validate_program(h, prog, n_nodes, &h->prog);
+    if (rc) return rc;
+    h->kind = SRC_SDF; h->d_grid = nullptr;
+    return enqueue_full(h);
+}
+
+int32_t isomc_finish(isomc_t *h) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    return finish_impl(h);
+}
+
+int32_t isomc_extract_grid_device(isomc_t *h, const float *d_grid) {
+    int32_t rc = isomc_enqueue_grid_device(h, d_grid);
+    return rc ? rc : isomc_finish(h);
+}
+
+int32_t isomc_extract_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes) {
+    int32_t rc = isomc_enqueue_sdf(h, prog, n_nodes);
+    return rc ? rc : isomc_finish(h);
+}
+
+int32_t isomc_extract_grid_host(isomc_t *h, const float *h_grid) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h_grid) return fail(h, ISOMC_ERR_BAD_ARG, "h_grid == NULL");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    const size_t bytes = (size_t)h->g.N * h->g.N * h->g.nsl * sizeof(float);
+    if (!h->stage_grid) CU(h, cudaMalloc(&h->stage_grid, bytes > 0 ? bytes : 4));
+    CU(h, cudaMemcpyAsync(h->stage_grid, h_grid, bytes, cudaMemcpyHostToDevice, h->stream));
+    return isomc_extract_grid_device(h, h->stage_grid);
+}
+
+/* ---- results ------------------------------------------------------------------------------ */
+
+int32_t isomc_counts(isomc_t *h, uint64_t *n_vertices, uint64_t *n_triangles, uint64_t *n_active_cells) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h->have_result) return fail(h, ISOMC_ERR_NO_RESULT, "no extract has completed on this handle");
+    if (n_vertices) *n_vertices = h->n_v;
+    if (n_triangles) *n_triangles = h->n_t;
+    if (n_active_cells) *n_active_cells = h->n_a;
+    return ISOMC_OK;
+}
+
+int32_t isomc_device_buffers(isomc_t *h, const float **d_xyz, const uint32_t **d_idx) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h->have_result) return fail(h, ISOMC_ERR_NO_RESULT, "no extract has completed on this handle");
+    if (d_xyz) *d_xyz = h->xyz;
+    if (d_idx) *d_idx = h->idx;
+    return ISOMC_OK;
+}
+
+int32_t isomc_copy_out(isomc_t *h, float *xyz, uint32_t *idx) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h->have_result) return fail(h, ISOMC_ERR_NO_RESULT, "no extract has completed on this handle");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    if (xyz && h->n_v) CU(h, cudaMemcpyAsync(xyz, h->xyz, h->n_v * 12, cudaMemcpyDeviceToHost, h->stream));
+    if (idx && h->n_t) CU(h, cudaMemcpyAsync(idx, h->idx, h->n_t * 12, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return ISOMC_OK;
+}
+
+int32_t isomc_stats_get(isomc_t *h, isomc_stats *out) {
+    if (!h || !out) return ISOMC_ERR_BAD_ARG;
+    if (!h->have_result) return fail(h, ISOMC_ERR_NO_RESULT, "no extract has completed on this handle");
+    *out = h->stats;
+    return ISOMC_OK;
+}
+
+/* ---- slabs -------------------------------------------------------------------------------- */
+
+int32_t isomc_slab_count_grid_device(isomc_t *h, const float *d_slab) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!d_slab) return fail(h, ISOMC_ERR_BAD_ARG, "d_slab == NULL");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    h->kind = SRC_GRID; h->d_grid = d_slab;
+    return enqueue_count(h);
+}
+
+int32_t isomc_slab_count_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    rc = validate_program(h, prog, n_nodes, &h->prog);
+    if (rc) return rc;
+    h->kind = SRC_SDF; h->d_grid = nullptr;
+    return enqueue_count(h);
+}
+
+int32_t isomc_slab_totals(isomc_t *h, uint64_t totals[3]) {
+    if (!h || !totals) return ISOMC_ERR_BAD_ARG;
+    if (!h->counted) return fail(h, ISOMC_ERR_NO_RESULT, "slab_totals before slab_count");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    rc = fetch_totals(h);
+    if (rc) return rc;
+    totals[0] = h->h_totals[8]; totals[1] = h->h_totals[9]; totals[2] = h->h_totals[10];
+    return ISOMC_OK;
+}
+
+int32_t isomc_slab_totals_device(isomc_t *h, const uint64_t **d_totals) {
+    if (!h || !d_totals) return ISOMC_ERR_BAD_ARG;
+    *d_totals = (const uint64_t *)(h->totals + 8);
+    return ISOMC_OK;
+}
+
+int32_t isomc_slab_emit(isomc_t *h, uint64_t vertex_base, uint64_t boundary_base) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h->counted) return fail(h, ISOMC_ERR_NO_RESULT, "slab_emit before slab_count");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    const uint64_t ofs = h->g.ghost ? boundary_base : vertex_base;
+    if (ofs >= (1ull << 32)) return fail(h, ISOMC_ERR_INDEX_OVERFLOW, "vertex base %llu does not fit u32", (unsigned long long)ofs);
+    rc = set_vofs(h, (uint32_t)ofs);
+    if (rc) return rc;
+    rc = fetch_totals(h);
+    if (rc) return rc;
+    if (ofs + h->h_totals[0] >= (1ull << 32))
+        return fail(h, ISOMC_ERR_INDEX_OVERFLOW, "global vertex ids exceed u32");
+    rc = ensure_capacity(h, h->h_totals[8], h->h_totals[10]);
+    if (rc) return rc;
+    rc = enqueue_emit(h);
+    if (rc) return rc;
+    return finish_impl(h);
+}
+
+int32_t isomc_slab_emit_gathered(isomc_t *h, const uint64_t *d_gathered, uint32_t rank, uint32_t n_ranks) {
+    if (!h || !d_gathered || rank >= n_ranks) return ISOMC_ERR_BAD_ARG;
+    if (!h->counted) return fail(h, ISOMC_ERR_NO_RESULT, "slab_emit before slab_count");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    CU(h, isomc_launch_slab_bases((const unsigned long long *)d_gathered, rank, h->g.ghost, h->vofs, h->stream));
+    h->stats.kernel_launches += 1;
+    if (h->cap_v > 0 || h->cap_t > 0) {
+        rc = enqueue_emit(h);
+        if (rc) return rc;
+    }
+    return finish_impl(h);
+}
+
+/* ---- debug -------------------------------------------------------------------------------- */
+
+int32_t isomc_debug_cube_indices(isomc_t *h, uint8_t *host_out) {
+    if (!h || !host_out) return ISOMC_ERR_BAD_ARG;
+    if (!h->counted) return fail(h, ISOMC_ERR_NO_RESULT, "no extract has run on this handle");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    const uint64_t n = (uint64_t)h->g.ncl * h->g.ncx * h->g.ncx;
+    if (n == 0) return ISOMC_OK;
+    uint8_t *d = nullptr;
+    CU(h, cudaMalloc(&d, n));
+    cudaError_t e = isomc_launch_cube_indices(h->g, h->signs, h->tabs, d, h->sms, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d, n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, ISOMC_ERR_CUDA, "cube index dump failed: %s", cudaGetErrorString(e));
+    return ISOMC_OK;
+}
+
+int32_t isomc_debug_sample_sdf(int32_t device, const isomc_sdf_node *prog, uint32_t n_nodes, const float *h_xyz,
+                               uint64_t n_points, float *h_out) {
+    SdfProgram P;
+    int32_t rc = validate_program(nullptr, prog, n_nodes, &P);
+    if (rc) return rc;
+    if (!h_xyz || !h_out) return fail(nullptr, ISOMC_ERR_BAD_ARG, "NULL buffer");
+    if (n_points == 0) return ISOMC_OK;
+    CU(nullptr, cudaSetDevice(device));
+    float *dx = nullptr, *dout = nullptr;
+    CU(nullptr, cudaMalloc(&dx, n_points * 12));
+    cudaError_t e = cudaMalloc(&dout, n_points * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, h_xyz, n_points * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = isomc_launch_sample_sdf(P, dx, n_points, dout, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(h_out, dout, n_points * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dx); cudaFree(dout);
+    if (e != cudaSuccess) return fail(nullptr, ISOMC_ERR_CUDA, "sdf sampling failed: %s", cudaGetErrorString(e));
+    return ISOMC_OK;
+}
+
+/* ---- synthetic fields ------------------------------------------------------ */
+
+static uint64_t splitmix64(uint64_t *state) {
+    uint64_t z = (*state += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static float unit24(uint64_t *state) { return (float)(splitmix64(state) >> 40) * (1.0f / 16777216.0f); }
+
+int32_t isomc_synth_field(int32_t device, int32_t kind, uint32_t size, uint64_t seed, uint32_t z_first,
+                          uint32_t n_layers, float *d_out) {
+    if (size < 2 || !d_out || n_layers == 0) return fail(nullptr, ISOMC_ERR_BAD_ARG, "bad synth_field arguments");
+    SynthParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.kind = kind;
+    uint64_t st = seed;
+    if (kind == ISOMC_FIELD_FBM) {
+        /* f(p) = sum_{o<5} 2^-o sum_{k<4} sin(2 pi 4 2^o (d_ok . p) + phi_ok) */
+        for (int o = 0; o < 5; ++o)
+            for (int k = 0; k < 4; ++k) {
+                float dx, dy, dz, len;
+                do {
+                    dx = 2.0f * unit24(&st) - 1.0f; dy = 2.0f * unit24(&st) - 1.0f; dz = 2.0f * unit24(&st) - 1.0f;
+                    len = sqrtf(dx * dx + dy * dy + dz * dz);
+                } while (len < 1e-3f);
+                const int w = o * 4 + k;
+                sp.dx[w] = dx / len; sp.dy[w] = dy / len; sp.dz[w] = dz / len;
+                sp.ph[w] = 6.283185307179586f * unit24(&st);
+                sp.amp[w] = 1.0f / (float)(1 << o);
+                sp.freq[w] = 6.283185307179586f * 4.0f * (float)(1 << o);
+            }
+    } else if (kind == ISOMC_FIELD_SPHERE_UNION) {
+        for (int s = 0; s < 64; ++s) {
+            sp.cx[s] = 0.1f + 0.8f * unit24(&st); sp.cy[s] = 0.1f + 0.8f * unit24(&st); sp.cz[s] = 0.1f + 0.8f * unit24(&st);
+            sp.r[s] = 0.05f + 0.1f * unit24(&st);
+        }
+    } else if (kind != ISOMC_FIELD_GYROID) {
+        return fail(nullptr, ISOMC_ERR_BAD_ARG, "unknown field kind %d", kind);
+    }
+    CU(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    CU(nullptr, isomc_launch_synth(sp, size, z_first, n_layers, d_out, prop.multiProcessorCount, 0));
+    CU(nullptr, cudaDeviceSynchronize());
+    return ISOMC_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,42 @@
+/* isomc_kernels.h -- host-callable launchers of the kernels in isomc_kernels.cu */
+#ifndef ISOMC_KERNELS_H
+#define ISOMC_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct Geo;
+struct SdfProgram;
+struct McTables;
+
+struct SynthParams {
+    int32_t kind;
+    float amp[20], freq[20], dx[20], dy[20], dz[20], ph[20]; /* fBm: 5 octaves x 4 waves */
+    float cx[64], cy[64], cz[64], r[64];                     /* sphere union */
+};
+
+size_t isomc_emit_smem_bytes(uint32_t nws);
+
+cudaError_t isomc_launch_sign_grid(const Geo &g, const float *d_grid, uint32_t *signs, int sms, cudaStream_t st);
+cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, uint32_t *signs, int sms, cudaStream_t st);
+cudaError_t isomc_launch_count(const Geo &g, const uint32_t *signs, const McTables *tabs, uint32_t *segpre,
+                               uint32_t *rowV, uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot,
+                               int sms, cudaStream_t st);
+cudaError_t isomc_launch_scan(const Geo &g, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
+                              unsigned long long *totals, cudaStream_t st);
+cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,
+                                    cudaStream_t st);
+cudaError_t isomc_launch_emit_grid(const Geo &g, const float *d_grid, const uint32_t *signs, const uint32_t *segpre,
+                                   const uint32_t *rowPV, const uint32_t *rowPT, const McTables *tabs,
+                                   const unsigned long long *totals, const uint32_t *vofs, uint32_t *ticket, float *xyz,
+                                   uint32_t *idx, uint64_t cap_v, uint64_t cap_t, int sms, cudaStream_t st);
+cudaError_t isomc_launch_emit_sdf(const Geo &g, const SdfProgram &prog, const uint32_t *signs, const uint32_t *segpre,
+                                  const uint32_t *rowPV, const uint32_t *rowPT, const McTables *tabs,
+                                  const unsigned long long *totals, const uint32_t *vofs, uint32_t *ticket, float *xyz,
+                                  uint32_t *idx, uint64_t cap_v, uint64_t cap_t, int sms, cudaStream_t st);
+cudaError_t isomc_launch_cube_indices(const Geo &g, const uint32_t *signs, const McTables *tabs, uint8_t *out, int sms,
+                                      cudaStream_t st);
+cudaError_t isomc_launch_sample_sdf(const SdfProgram &prog, const float *xyz, uint64_t n, float *out, cudaStream_t st);
+cudaError_t isomc_launch_synth(const SynthParams &sp, uint32_t size, uint32_t z_first, uint32_t n_layers, float *out,
+                               int sms, cudaStream_t st);
+#endif

@@ -1,0 +1,114 @@
+"""MarchingCubes: host-side mirror of reference src/marching_cubes.rs:38-82 over the C ABI."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .extractor import replay
+from .source import DenseGrid, Sampler, encode_program
+
+
+class MarchingCubes:
+    """`MarchingCubes(size).extract(source, extractor)` == reference
+    `MarchingCubes::<Signed>::new(size).extract(&source, &mut extractor)`.
+
+    `size` lattice points per axis in x and y; the reference's z loop runs one layer further
+    (primal_grid.rs:59), so N x N x (N+1) samples and (N-1)^2 x N cells.  One extract at a time
+    per instance (`&mut self`).
+    """
+
+    def __init__(self, size, device=0):
+        lib = _lib.load()
+        self.size, self.device = int(size), int(device)
+        self._h = C.c_void_p()
+        _lib.check(lib.isomc_create(self.size, self.device, C.byref(self._h)))
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.isomc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the reference API -------------------------------------------------------------------
+    def extract(self, source, extractor):
+        self.extract_device(source)
+        xyz, idx = self.copy_out()
+        replay(extractor, xyz, idx)
+
+    # ---- device-resident variants ------------------------------------------------------------
+    def extract_device(self, source):
+        """Run the extraction and leave the mesh in device memory (see `device_buffers`)."""
+        src = source.source if isinstance(source, Sampler) else source
+        if isinstance(src, DenseGrid):
+            if src.size != self.size:
+                raise ValueError("grid is for size %d, MarchingCubes for %d" % (src.size, self.size))
+            fn = self._lib.isomc_extract_grid_device if src.on_device else self._lib.isomc_extract_grid_host
+            _lib.check(fn(self._h, src.ptr), self._h)
+        else:
+            prog = encode_program(src)
+            _lib.check(self._lib.isomc_extract_sdf(self._h, prog.ctypes.data, len(prog)), self._h)
+        return self.counts()
+
+    def enqueue(self, source):
+        """Enqueue an extract on the handle's stream without synchronising; pair with `finish()`."""
+        src = source.source if isinstance(source, Sampler) else source
+        if isinstance(src, DenseGrid):
+            if not src.on_device:
+                raise ValueError("enqueue() needs a device-resident grid")
+            _lib.check(self._lib.isomc_enqueue_grid_device(self._h, src.ptr), self._h)
+        else:
+            prog = encode_program(src)
+            _lib.check(self._lib.isomc_enqueue_sdf(self._h, prog.ctypes.data, len(prog)), self._h)
+
+    def finish(self):
+        _lib.check(self._lib.isomc_finish(self._h), self._h)
+        return self.counts()
+
+    def counts(self):
+        v, t, a = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _lib.check(self._lib.isomc_counts(self._h, C.byref(v), C.byref(t), C.byref(a)), self._h)
+        return v.value, t.value, a.value
+
+    def copy_out(self):
+        nv, nt, _ = self.counts()
+        xyz = np.empty(nv * 3, np.float32)
+        idx = np.empty(nt * 3, np.uint32)
+        _lib.check(self._lib.isomc_copy_out(self._h, xyz.ctypes.data, idx.ctypes.data), self._h)
+        return xyz, idx
+
+    def device_buffers(self):
+        dx, di = C.c_void_p(), C.c_void_p()
+        _lib.check(self._lib.isomc_device_buffers(self._h, C.byref(dx), C.byref(di)), self._h)
+        return dx.value, di.value
+
+    def reserve(self, n_vertices, n_triangles):
+        _lib.check(self._lib.isomc_reserve(self._h, int(n_vertices), int(n_triangles)), self._h)
+
+    def set_stream(self, cuda_stream_ptr):
+        _lib.check(self._lib.isomc_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), self._h)
+
+    def stream(self):
+        s = C.c_void_p()
+        _lib.check(self._lib.isomc_get_stream(self._h, C.byref(s)), self._h)
+        return s.value or 0
+
+    def set_profiling(self, on=True):
+        _lib.check(self._lib.isomc_set_profiling(self._h, 1 if on else 0), self._h)
+
+    def stats(self):
+        s = _lib.Stats()
+        _lib.check(self._lib.isomc_stats_get(self._h, C.byref(s)), self._h)
+        return {name: getattr(s, name) for name, _ in s._fields_}
+
+    def cube_indices(self):
+        """per-cell cube_index (reference corner order) of the last extract, shape (N, N-1, N-1)"""
+        n = self.size
+        out = np.zeros((n, n - 1, n - 1), np.uint8)
+        _lib.check(self._lib.isomc_debug_cube_indices(self._h, out.ctypes.data), self._h)
+        return out

@@ -1,0 +1,128 @@
+"""ctypes loader for the CPU oracle (oracle/mc_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
+import this module.  The product package (isosurface_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+# op codes: same numbering as include/isomc.h (ISOMC_SDF_*), restated independently
+SPHERE, TORUS, CYLINDER, PRISM = 1, 2, 3, 4
+UNION, INTERSECTION, DIFFERENCE = 16, 17, 18
+TRANSLATE_PUSH, TRANSLATE_POP = 32, 33
+FAITHFUL, LEAN = 0, 1
+
+NODE_DTYPE = np.dtype([("op", "<u4"), ("a", "<f4"), ("b", "<f4"), ("c", "<f4")])
+
+
+class _Mesh(C.Structure):
+    _fields_ = [("xyz", C.POINTER(C.c_float)), ("n_vertices", C.c_uint64), ("cap_v", C.c_uint64),
+                ("idx", C.POINTER(C.c_uint32)), ("n_triangles", C.c_uint64), ("cap_i", C.c_uint64),
+                ("n_active_cells", C.c_uint64)]
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", str(_HERE)], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = _HERE / "libmc_oracle.so"
+        if not so.exists() or so.stat().st_mtime < (_HERE / "mc_oracle.c").stat().st_mtime:
+            build()
+        _LIB = C.CDLL(str(so))
+        _LIB.oracle_extract_sdf.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(_Mesh)]
+        _LIB.oracle_extract_grid.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(_Mesh)]
+        _LIB.oracle_cube_indices.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+        _LIB.oracle_fill_grid_sdf.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        _LIB.oracle_sample_sdf.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+        _LIB.oracle_tables.argtypes = [C.c_void_p] * 4
+        _LIB.oracle_mesh_free.argtypes = [C.POINTER(_Mesh)]
+    return _LIB
+
+
+def program(nodes):
+    """nodes: iterable of (op, a, b, c) -> packed node array."""
+    arr = np.zeros(len(nodes), dtype=NODE_DTYPE)
+    for i, nd in enumerate(nodes):
+        nd = tuple(nd) + (0.0,) * (4 - len(nd))
+        arr[i] = nd
+    return arr
+
+
+def _take(mesh):
+    nv, nt = int(mesh.n_vertices), int(mesh.n_triangles)
+    xyz = np.ctypeslib.as_array(mesh.xyz, shape=(nv * 3,)).copy() if nv else np.zeros(0, np.float32)
+    idx = np.ctypeslib.as_array(mesh.idx, shape=(nt * 3,)).copy() if nt else np.zeros(0, np.uint32)
+    act = int(mesh.n_active_cells)
+    lib().oracle_mesh_free(C.byref(mesh))
+    return xyz.astype(np.float32, copy=False), idx.astype(np.uint32, copy=False), act
+
+
+def extract_sdf(size, prog, mode=LEAN):
+    m = _Mesh()
+    prog = np.ascontiguousarray(prog)
+    rc = lib().oracle_extract_sdf(size, prog.ctypes.data, len(prog), mode, C.byref(m))
+    if rc:
+        raise RuntimeError("oracle_extract_sdf rc=%d" % rc)
+    return _take(m)
+
+
+def extract_grid(size, grid, z_cells=None, mode=LEAN):
+    grid = np.ascontiguousarray(grid, dtype=np.float32)
+    z_cells = size if z_cells is None else z_cells
+    assert grid.size >= size * size * (z_cells + 1)
+    m = _Mesh()
+    rc = lib().oracle_extract_grid(size, grid.ctypes.data, z_cells, mode, C.byref(m))
+    if rc:
+        raise RuntimeError("oracle_extract_grid rc=%d" % rc)
+    return _take(m)
+
+
+def cube_indices(size, grid, z_cells=None):
+    grid = np.ascontiguousarray(grid, dtype=np.float32)
+    z_cells = size if z_cells is None else z_cells
+    out = np.zeros((z_cells, size - 1, size - 1), dtype=np.uint8)
+    rc = lib().oracle_cube_indices(size, grid.ctypes.data, z_cells, out.ctypes.data)
+    if rc:
+        raise RuntimeError("oracle_cube_indices rc=%d" % rc)
+    return out
+
+
+def fill_grid_sdf(size, prog, z_layers=None):
+    z_layers = size + 1 if z_layers is None else z_layers
+    prog = np.ascontiguousarray(prog)
+    out = np.zeros((z_layers, size, size), dtype=np.float32)
+    rc = lib().oracle_fill_grid_sdf(size, prog.ctypes.data, len(prog), z_layers, out.ctypes.data)
+    if rc:
+        raise RuntimeError("oracle_fill_grid_sdf rc=%d" % rc)
+    return out
+
+
+def sample_sdf(prog, pts):
+    prog = np.ascontiguousarray(prog)
+    pts = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros(len(pts), dtype=np.float32)
+    rc = lib().oracle_sample_sdf(prog.ctypes.data, len(prog), pts.ctypes.data, len(pts), out.ctypes.data)
+    if rc:
+        raise RuntimeError("oracle_sample_sdf rc=%d" % rc)
+    return out
+
+
+def tables():
+    tri = np.zeros((256, 16), np.int8)
+    em = np.zeros(256, np.uint16)
+    co = np.zeros((8, 3), np.int32)
+    ed = np.zeros((12, 2), np.int32)
+    rc = lib().oracle_tables(tri.ctypes.data, em.ctypes.data, co.ctypes.data, ed.ctypes.data)
+    if rc:
+        raise RuntimeError("oracle_tables rc=%d" % rc)
+    return tri, em, co, ed
