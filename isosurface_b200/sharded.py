@@ -1,0 +1,110 @@
+"""z-slab sharding of one extract across the GPUs of a node.
+
+The reference has no multi-chunk driver; this is new.  Rank g of G owns cell layers
+[z_g, z_{g+1}) and is handed sample layers [z_g - (g > 0), z_{g+1}].  The only exchange is one
+all-gather of three u64 per rank {V_owned, V_owned_before_last_cell_layer, T_owned}; from it every
+rank derives the offset that makes its indices global, and the emission kernel writes global ids
+directly (no re-index pass).  Concatenating the ranks' outputs in rank order is the reference mesh.
+
+Host logic only; the collective goes through `torch.distributed` (NCCL on GPUs, gloo in CPU tests).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def slab_range(size, rank, world):
+    """cell layers [z0, z1) of `rank`: contiguous, balanced to within one layer"""
+    if not (0 <= rank < world) or world > size:
+        raise ValueError("bad rank/world %d/%d for size %d" % (rank, world, size))
+    base, rem = divmod(size, world)
+    z0 = rank * base + min(rank, rem)
+    return z0, z0 + base + (1 if rank < rem else 0)
+
+
+def slab_sample_layers(size, rank, world):
+    """(first sample layer, number of sample layers) a rank must hold"""
+    z0, z1 = slab_range(size, rank, world)
+    ghost = 1 if z0 > 0 else 0
+    return z0 - ghost, (z1 - z0) + ghost + 1
+
+
+def bases_from_totals(gathered, rank):
+    """gathered: (G, 3) integer array of per-rank {V, V_before_last_layer, T}.
+    Returns (vertex_base, boundary_base, triangle_base) of `rank`:
+      vertex_base   = sum of V of lower ranks (id of this rank's first own vertex)
+      boundary_base = id of the first vertex created in the previous rank's last cell layer
+                      (= vertex_base[rank-1] + V_before_last_layer[rank-1]); 0 for rank 0
+      triangle_base = sum of T of lower ranks (position of this rank's triangles in the global list)
+    Mirrors the device-side k_slab_bases."""
+    g = np.asarray(gathered, dtype=np.uint64).reshape(-1, 3)
+    vbase = int(g[:rank, 0].sum())
+    tbase = int(g[:rank, 2].sum())
+    bbase = 0
+    if rank > 0:
+        bbase = vbase - int(g[rank - 1, 0]) + int(g[rank - 1, 1])
+    return vbase, bbase, tbase
+
+
+def allgather_totals(totals, group=None):
+    """all-gather 3 integers per rank through torch.distributed (any backend) -> (G, 3) uint64 array"""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = "cuda" if backend == "nccl" else "cpu"
+    mine = torch.tensor([int(t) for t in totals], dtype=torch.int64, device=dev)
+    out = torch.zeros(3 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out.cpu().numpy().astype(np.uint64).reshape(world, 3)
+
+
+class SlabMarchingCubes:
+    """One rank's share of a sharded extract.  `extract(d_slab_ptr)` runs count -> all-gather -> emit."""
+
+    def __init__(self, size, rank, world, device=0):
+        lib = _lib.load()
+        self.size, self.rank, self.world, self.device = int(size), int(rank), int(world), int(device)
+        self.z0, self.z1 = slab_range(size, rank, world)
+        self._h = C.c_void_p()
+        _lib.check(lib.isomc_slab_create(self.size, self.z0, self.z1, self.device, C.byref(self._h)))
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.isomc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def count(self, d_slab_ptr):
+        _lib.check(self._lib.isomc_slab_count_grid_device(self._h, C.c_void_p(d_slab_ptr)), self._h)
+        t = (C.c_uint64 * 3)()
+        _lib.check(self._lib.isomc_slab_totals(self._h, C.byref(t)), self._h)
+        return [int(t[0]), int(t[1]), int(t[2])]
+
+    def emit(self, vertex_base, boundary_base):
+        _lib.check(self._lib.isomc_slab_emit(self._h, int(vertex_base), int(boundary_base)), self._h)
+
+    def extract(self, d_slab_ptr, gathered=None, group=None):
+        """gathered: optional precomputed (G,3) totals (single-process simulation of all ranks)"""
+        mine = self.count(d_slab_ptr)
+        if gathered is None:
+            gathered = allgather_totals(mine, group) if self.world > 1 else np.array([mine], dtype=np.uint64)
+        vbase, bbase, tbase = bases_from_totals(gathered, self.rank)
+        self.emit(vbase, bbase)
+        return vbase, tbase
+
+    def copy_out(self):
+        v, t, a = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _lib.check(self._lib.isomc_counts(self._h, C.byref(v), C.byref(t), C.byref(a)), self._h)
+        xyz = np.empty(v.value * 3, np.float32)
+        idx = np.empty(t.value * 3, np.uint32)
+        _lib.check(self._lib.isomc_copy_out(self._h, xyz.ctypes.data, idx.ctypes.data), self._h)
+        return xyz, idx

@@ -1,0 +1,316 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Bar: indices bit-exact (memcmp),
+vertex positions bit-exact as well (the north star allows 1e-5 absolute; tolerance used: 0)."""
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import iso_source, mesh_diff, mesh_invariants, oracle_prog, sha
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "mesh_hashes.json").read_text())
+POS_TOL = 0.0  # north star: 1e-5 absolute; achieved: identical bits
+
+
+@pytest.fixture(scope="module")
+def iso():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (the CUDA extension has no fallback)")
+    import isosurface_b200
+    return isosurface_b200
+
+
+def synth(iso, kind, size, seed, z_first=0, n_layers=None):
+    import torch
+    from isosurface_b200 import _lib
+    n_layers = size + 1 if n_layers is None else n_layers
+    t = torch.empty(n_layers * size * size, dtype=torch.float32, device="cuda:0")
+    _lib.check(_lib.load().isomc_synth_field(0, kind, size, seed, z_first, n_layers, C.c_void_p(t.data_ptr())))
+    return t
+
+
+def test_device_sdf_known_answers(iso, isolib):
+    """the reference's exact-equality SDF unit tests, evaluated by the device interpreter"""
+    from isosurface_b200 import _lib
+    from isosurface_b200.source import encode_program
+
+    def s(src, p):
+        prog = encode_program(src)
+        pts = np.array([p], np.float32)
+        out = np.zeros(1, np.float32)
+        _lib.check(isolib.isomc_debug_sample_sdf(0, prog.ctypes.data, len(prog), pts.ctypes.data, 1, out.ctypes.data))
+        return float(out[0])
+
+    sp = iso.Sphere(2.0)
+    assert [s(sp, p) for p in ((0, 0, 0), (2, 0, 0), (0, 0, 8), (8, 0, 0))] == [-2.0, 0.0, 6.0, 6.0]
+    to = iso.Torus(8.0, 2.0)
+    assert [s(to, p) for p in ((0, 0, 0), (8, 0, 0), (10, 0, 0), (12, 0, 0), (8, 0, 8))] == [6.0, -2.0, 0.0, 2.0, 6.0]
+    cy = iso.Cylinder(2.0, 4.0)
+    assert [s(cy, p) for p in ((0, 0, 0), (2, 0, 4), (0, 0, 8), (8, 0, 0))] == [-2.0, 0.0, 4.0, 6.0]
+    pr = iso.RectangularPrism((1.0, 2.0, 4.0))
+    assert [s(pr, p) for p in ((0, 0, 0), (1, 2, 4), (0, 0, 8), (8, 0, 0))] == [-1.0, 0.0, 4.0, 7.0]
+    a, b = iso.RectangularPrism((4.0, 4.0, 1.0)), iso.RectangularPrism((2.0, 2.0, 4.0))
+    assert [s(iso.Union(a, b), p) for p in ((0, 0, 0), (4, 4, 1), (0, 0, 8), (8, 0, 0))] == [-2.0, 0.0, 4.0, 4.0]
+    assert [s(iso.Intersection(a, b), p) for p in ((0, 0, 0), (2, 2, 1), (0, 0, 8), (8, 0, 0))] == [-1.0, 0.0, 7.0, 6.0]
+    assert s(iso.Difference(a, b), (0, 0, 0)) == 1.0
+
+
+def test_device_sdf_matches_oracle_bitwise(iso, isolib, oracle):
+    from isosurface_b200 import _lib
+    from isosurface_b200.source import encode_program
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(-0.2, 1.2, size=(20000, 3)).astype(np.float32)
+    for name in ("torus", "csgA", "csgB", "prism", "cylinder", "nested", "sphere05_origin"):
+        prog = encode_program(iso_source(name))
+        out = np.zeros(len(pts), np.float32)
+        _lib.check(isolib.isomc_debug_sample_sdf(0, prog.ctypes.data, len(prog), pts.ctypes.data, len(pts), out.ctypes.data))
+        want = oracle.sample_sdf(oracle_prog(name), pts)
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), name
+
+
+@pytest.mark.parametrize("g", GOLDEN, ids=lambda g: "%s-%d" % (g["shape"], g["size"]))
+def test_sdf_extract_matches_golden_and_oracle(iso, oracle, g):
+    """BASELINE configs C1a/C1b/C2 and more: committed hashes (incl. the SURVEY 8c pins) + live oracle"""
+    mc = iso.MarchingCubes(g["size"])
+    nv, nt, na = mc.extract_device(iso.Sampler(iso_source(g["shape"])))
+    xyz, idx = mc.copy_out()
+    assert (na, nv, nt) == (g["active_cells"], g["vertices"], g["triangles"])
+    assert sha(idx, "<u4") == g["sha_i"], "index stream differs from golden"
+    assert sha(xyz, "<f4") == g["sha_v"], "vertex stream differs from golden"
+    if g["size"] <= 128:
+        oxyz, oidx, oact = oracle.extract_sdf(g["size"], oracle_prog(g["shape"]))
+        assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    mc.close()
+
+
+def test_active_cell_sets_match(iso, oracle):
+    """parity check #1: per-cell cube_index == oracle (active-cell sets bit-exact)"""
+    for name, n in (("csgA", 70), ("torus_origin", 64)):
+        grid = oracle.fill_grid_sdf(n, oracle_prog(name))
+        mc = iso.MarchingCubes(n)
+        mc.extract_device(iso.DenseGrid(grid))
+        assert np.array_equal(mc.cube_indices(), oracle.cube_indices(n, grid))
+        mc.close()
+
+
+@pytest.mark.parametrize("kind,size,seed", [(1, 64, 0x1505F00D), (1, 129, 3), (2, 96, 0), (3, 100, 0x5EEDBA11), (1, 200, 11)],
+                         ids=["fbm64", "fbm129", "gyroid96", "spheres100", "fbm200"])
+def test_dense_grid_fields_match_oracle(iso, oracle, kind, size, seed):
+    """grid-backed path on the synthetic bench fields (same bytes to both sides), incl. non-multiple-of-32 sizes"""
+    t = synth(iso, kind, size, seed)
+    host = t.cpu().numpy().reshape(size + 1, size, size)
+    mc = iso.MarchingCubes(size)
+    nv, nt, na = mc.extract_device(iso.DenseGrid(t))
+    xyz, idx = mc.copy_out()
+    oxyz, oidx, oact = oracle.extract_grid(size, host)
+    assert na == oact
+    assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    # host-buffer entry point gives the same bytes
+    mc2 = iso.MarchingCubes(size)
+    mc2.extract_device(iso.DenseGrid(host))
+    x2, i2 = mc2.copy_out()
+    assert np.array_equal(i2, idx) and np.array_equal(x2.view(np.uint32), xyz.view(np.uint32))
+    mc.close(); mc2.close()
+
+
+def test_edge_cases(iso, oracle):
+    # sizes 1, 2, 3; all-inside / all-outside; special values
+    for n in (1, 2, 3, 5):
+        mc = iso.MarchingCubes(n)
+        nv, nt, na = mc.extract_device(iso.Sampler(iso_source("sphere03")))
+        oxyz, oidx, oact = oracle.extract_sdf(n, oracle_prog("sphere03"))
+        xyz, idx = mc.copy_out()
+        assert (nv, nt, na) == (len(oxyz) // 3, len(oidx) // 3, oact) and mesh_diff(xyz, idx, oxyz, oidx) == ""
+        mc.close()
+    for v in (1.0, -1.0, 0.0, -0.0, np.nan):
+        g = np.full((34, 33, 33), v, np.float32)
+        mc = iso.MarchingCubes(33)
+        assert mc.extract_device(iso.DenseGrid(g)) == (0, 0, 0)
+        mc.close()
+    rng = np.random.default_rng(5)
+    g = rng.standard_normal((41, 40, 40)).astype(np.float32)     # white noise: every case, max density
+    g[rng.random(g.shape) < 0.05] = 0.0
+    g[rng.random(g.shape) < 0.05] = -0.0
+    g[rng.random(g.shape) < 0.02] = np.nan
+    g[rng.random(g.shape) < 0.02] = np.inf
+    g[rng.random(g.shape) < 0.02] = -np.inf
+    mc = iso.MarchingCubes(40)
+    nv, nt, na = mc.extract_device(iso.DenseGrid(g))
+    xyz, idx = mc.copy_out()
+    oxyz, oidx, oact = oracle.extract_grid(40, g)
+    assert na == oact and np.array_equal(idx, oidx)
+    assert np.array_equal(xyz.view(np.uint32), oxyz.view(np.uint32))   # NaN positions included, bit for bit
+    mc.close()
+
+
+def test_dense_random_field_all_cases(iso, oracle):
+    """white noise at a non-aligned size exercises all 256 cases, boundary ownership on every face and
+    the worst-case compaction density"""
+    rng = np.random.default_rng(11)
+    n = 77
+    g = rng.standard_normal((n + 1, n, n)).astype(np.float32)
+    mc = iso.MarchingCubes(n)
+    mc.extract_device(iso.DenseGrid(g))
+    xyz, idx = mc.copy_out()
+    oxyz, oidx, _ = oracle.extract_grid(n, g)
+    assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    assert len(np.unique(oracle.cube_indices(n, g))) == 256
+    mc.close()
+
+
+def test_handle_reuse_and_determinism(iso, oracle):
+    """one handle, many extracts (buffers grow and shrink); identical bytes every time"""
+    mc = iso.MarchingCubes(64)
+    ref = None
+    for name in ("torus", "csgA", "sphere03", "torus", "csgA", "torus"):
+        mc.extract_device(iso.Sampler(iso_source(name)))
+        xyz, idx = mc.copy_out()
+        oxyz, oidx, _ = oracle.extract_sdf(64, oracle_prog(name))
+        assert mesh_diff(xyz, idx, oxyz, oidx) == "", name
+    t = synth(iso, 1, 64, 99)
+    for _ in range(20):
+        mc.extract_device(iso.DenseGrid(t))
+        cur = tuple(a.tobytes() for a in mc.copy_out())
+        ref = ref or cur
+        assert cur == ref
+    mc.close()
+
+
+def test_extractor_api_paths(iso, oracle):
+    """the crate-shaped call: MarchingCubes(size).extract(Sampler(source), IndexedVertices(v, i))"""
+    vertices, indices = [], []
+    mc = iso.MarchingCubes(32)
+    mc.extract(iso.Sampler(iso_source("sphere03")), iso.IndexedVertices(vertices, indices))
+    oxyz, oidx, _ = oracle.extract_sdf(32, oracle_prog("sphere03"))
+    assert np.array_equal(np.asarray(vertices, np.float32), oxyz) and np.array_equal(np.asarray(indices, np.uint32), oidx)
+
+    class Rec(iso.Extractor):
+        def __init__(self):
+            self.v, self.i, self.late_vertex = [], [], False
+
+        def extract_vertex(self, v):
+            self.late_vertex |= bool(self.i)
+            self.v.extend(v)
+
+        def extract_index(self, i):
+            self.i.append(i)
+    r = Rec()
+    mc.extract(iso.Sampler(iso_source("sphere03")), r)
+    assert not r.late_vertex and np.array_equal(np.asarray(r.v, np.float32), oxyz) and r.i == oidx.tolist()
+    mc.close()
+
+
+def test_unsupported_and_error_paths(iso, isolib):
+    from isosurface_b200 import _lib
+    mc = iso.MarchingCubes(16)
+    with pytest.raises(_lib.IsomcError) as ei:
+        mc.counts()
+    assert ei.value.code == _lib.ERR_NO_RESULT
+    bad = np.zeros(1, dtype=_lib.NODE_DTYPE)
+    bad[0] = (99, 0, 0, 0)
+    assert isolib.isomc_extract_sdf(mc._h, bad.ctypes.data, 1) == _lib.ERR_UNSUPPORTED_SOURCE
+    assert b"closures" in isolib.isomc_last_error(mc._h)
+    two = np.zeros(2, dtype=_lib.NODE_DTYPE)
+    two[0] = (1, 1, 0, 0); two[1] = (1, 1, 0, 0)
+    assert isolib.isomc_extract_sdf(mc._h, two.ctypes.data, 2) == _lib.ERR_BAD_ARG
+    with pytest.raises(ValueError):
+        mc.extract_device(iso.DenseGrid(np.zeros((9, 8, 8), np.float32)))
+    mc.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_slab_decomposition_on_one_gpu(iso, oracle, world):
+    """multi-GPU path simulated serially on one device: concatenated slabs == unsharded == oracle"""
+    from isosurface_b200.sharded import SlabMarchingCubes, slab_sample_layers
+    size = 72
+    t = synth(iso, 1, size, 21)
+    host = t.cpu().numpy().reshape(size + 1, size, size)
+    oxyz, oidx, _ = oracle.extract_grid(size, host)
+    slabs = [SlabMarchingCubes(size, r, world) for r in range(world)]
+    ptrs = []
+    for r in range(world):
+        zf, nl = slab_sample_layers(size, r, world)
+        ptrs.append(t.data_ptr() + 4 * zf * size * size)
+    totals = np.array([s.count(p) for s, p in zip(slabs, ptrs)], dtype=np.uint64)
+    parts = []
+    for r, s in enumerate(slabs):
+        s.extract(ptrs[r], gathered=totals)
+        parts.append(s.copy_out())
+    xyz = np.concatenate([p[0] for p in parts])
+    idx = np.concatenate([p[1] for p in parts])
+    assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    assert int(totals[:, 0].sum()) == len(oxyz) // 3 and int(totals[:, 2].sum()) == len(oidx) // 3
+    for s in slabs:
+        s.close()
+
+
+def test_slab_emit_gathered_on_stream(iso, oracle, isolib):
+    """the on-stream variant (device-side base computation from the all-gathered totals)"""
+    import torch
+    from isosurface_b200 import _lib
+    from isosurface_b200.sharded import SlabMarchingCubes, slab_sample_layers
+    size, world = 48, 4
+    t = synth(iso, 2, size, 0)
+    host = t.cpu().numpy().reshape(size + 1, size, size)
+    oxyz, oidx, _ = oracle.extract_grid(size, host)
+    slabs = [SlabMarchingCubes(size, r, world) for r in range(world)]
+    ptrs = [t.data_ptr() + 4 * slab_sample_layers(size, r, world)[0] * size * size for r in range(world)]
+    totals = np.array([s.count(p) for s, p in zip(slabs, ptrs)], dtype=np.int64)
+    gathered = torch.from_numpy(totals.ravel().copy()).cuda()
+    parts = []
+    for r, s in enumerate(slabs):
+        _lib.check(isolib.isomc_slab_count_grid_device(s._h, C.c_void_p(ptrs[r])), s._h)
+        _lib.check(isolib.isomc_slab_emit_gathered(s._h, C.c_void_p(gathered.data_ptr()), r, world), s._h)
+        parts.append(s.copy_out())
+    assert mesh_diff(np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), oxyz, oidx) == ""
+
+
+def test_full_size_properties_512(iso, oracle):
+    """BASELINE C3 at full size: invariants that do not need the oracle, plus an oracle check on a z-window"""
+    size = 512
+    t = synth(iso, 1, size, 0x1505F00D)
+    mc = iso.MarchingCubes(size)
+    nv, nt, na = mc.extract_device(iso.DenseGrid(t))
+    xyz, idx = mc.copy_out()
+    assert nv == len(xyz) // 3 and nt == len(idx) // 3 and nv > 1_000_000
+    assert int(idx.max()) == nv - 1
+    ref = np.zeros(nv, bool)
+    ref[idx] = True
+    assert ref.all()                                   # every vertex referenced
+    assert np.isfinite(xyz).all() and xyz.min() >= 0.0 and xyz.max() <= 512 / 511 + 1e-6
+    first_use = np.full(nv, np.iinfo(np.int64).max)
+    np.minimum.at(first_use, idx, np.arange(len(idx)))
+    assert np.all(np.diff(first_use) > 0)              # vertex k is first referenced before vertex k+1 (mesh.rs:240-251)
+    # oracle on the first 24 cell layers: exact prefix of the device mesh
+    host = t[: 25 * size * size].cpu().numpy().reshape(25, size, size)
+    wx, wi, _ = oracle.extract_grid(size, host, z_cells=24)
+    assert np.array_equal(idx[:len(wi)], wi) and np.array_equal(xyz[:len(wx)].view(np.uint32), wx.view(np.uint32))
+    mc.close()
+
+
+def test_full_size_slabs_equal_unsharded_1024(iso):
+    """BASELINE C4 (1024^3 gyroid): 8 slabs run serially == one unsharded extract, byte for byte"""
+    from isosurface_b200.sharded import SlabMarchingCubes, slab_sample_layers
+    size, world = 1024, 8
+    t = synth(iso, 2, size, 0)
+    mc = iso.MarchingCubes(size)
+    mc.extract_device(iso.DenseGrid(t))
+    xyz, idx = mc.copy_out()
+    mc.close()
+    slabs = [SlabMarchingCubes(size, r, world) for r in range(world)]
+    ptrs = [t.data_ptr() + 4 * slab_sample_layers(size, r, world)[0] * size * size for r in range(world)]
+    totals = np.array([s.count(p) for s, p in zip(slabs, ptrs)], dtype=np.uint64)
+    vo = io = 0
+    for r, s in enumerate(slabs):
+        s.extract(ptrs[r], gathered=totals)
+        px, pi = s.copy_out()
+        assert np.array_equal(xyz[vo:vo + len(px)].view(np.uint32), px.view(np.uint32))
+        assert np.array_equal(idx[io:io + len(pi)], pi)
+        vo += len(px); io += len(pi)
+        s.close()
+    assert vo == len(xyz) and io == len(idx)
+    facts = mesh_invariants(xyz, idx, closed=False)
+    assert facts["directed_edge_dups"] == 0
