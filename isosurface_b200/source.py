@@ -118,7 +118,7 @@ class DenseGrid:
             self.on_device = bool(getattr(data, "is_cuda", False)) if on_device is None else on_device
             if not self.on_device:
                 raise TypeError("pass host data as a NumPy array")
-            n = int(data.shape[-1]) if size is None else int(size)
+            n = _infer_size(tuple(data.shape), data.numel()) if size is None else int(size)
             if data.numel() != n * n * (n + 1) or str(data.dtype) != "torch.float32" or not data.is_contiguous():
                 raise ValueError("dense grid must be contiguous float32 with N*N*(N+1) elements")
             self.size, self.ptr = n, int(data.data_ptr())
@@ -128,11 +128,22 @@ class DenseGrid:
             self.size, self.ptr, self.on_device = int(size), data, True
         else:
             arr = np.ascontiguousarray(data, dtype=np.float32)
-            n = int(arr.shape[-1]) if size is None else int(size)
+            n = _infer_size(arr.shape, arr.size) if size is None else int(size)
             if arr.size != n * n * (n + 1):
                 raise ValueError("dense grid needs N*N*(N+1) samples, got %d for N=%d" % (arr.size, n))
             self._keep = arr
             self.size, self.ptr, self.on_device = n, arr.ctypes.data, False
+
+
+def _infer_size(shape, numel):
+    """N from a (N+1, N, N) shape, or from N*N*(N+1) elements of a flat buffer"""
+    if len(shape) == 3:
+        return int(shape[-1])
+    n = int(round(numel ** (1.0 / 3.0)))
+    for c in (n - 1, n, n + 1):
+        if c >= 1 and c * c * (c + 1) == numel:
+            return c
+    raise ValueError("cannot infer the lattice size from %d samples; pass size=" % numel)
 
 
 class Sampler:

@@ -142,7 +142,11 @@ def test_edge_cases(iso, oracle):
     xyz, idx = mc.copy_out()
     oxyz, oidx, oact = oracle.extract_grid(40, g)
     assert na == oact and np.array_equal(idx, oidx)
-    assert np.array_equal(xyz.view(np.uint32), oxyz.view(np.uint32))   # NaN positions included, bit for bit
+    # infinities/NaNs in the field give NaN coordinates; NaN *payloads* are hardware-specific (x86 SSE
+    # produces 0xFFC00000, the GPU 0x7FFFFFFF), so: NaN where the oracle has NaN, identical bits elsewhere
+    nan_g, nan_o = np.isnan(xyz), np.isnan(oxyz)
+    assert np.array_equal(nan_g, nan_o) and nan_o.any()
+    assert np.array_equal(xyz.view(np.uint32)[~nan_o], oxyz.view(np.uint32)[~nan_o])
     mc.close()
 
 
