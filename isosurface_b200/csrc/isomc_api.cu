@@ -164,7 +164,7 @@ int32_t enqueue_emit(isomc *h) {
     else
         CU(h, isomc_launch_emit_sdf(g, h->prog, h->signs, h->segpre, h->rowV, h->rowT, h->tabs, h->totals, h->vofs,
                                     h->ticket, h->xyz, h->idx, h->cap_v, h->cap_t, h->sms, h->stream));
-    h->stats.kernel_launches += 1;
+    h->stats.kernel_launches += 2; /* k_emit + k_vertex */
     h->emitted = true;
     return ISOMC_OK;
 }

@@ -95,6 +95,7 @@ __device__ __forceinline__ uint32_t valid_mask(uint32_t n) { /* low n bits, n in
 /* K1: sample -> inside bits                                                                    */
 /* ------------------------------------------------------------------------------------------ */
 
+/* generic path: any source, any size/alignment; one lane per sample, ballot per 32 samples */
 template <class Src>
 __global__ void __launch_bounds__(256) k_sign(Src src, Geo g, uint32_t *__restrict__ signs) {
     constexpr int U = 8;
@@ -122,83 +123,131 @@ __global__ void __launch_bounds__(256) k_sign(Src src, Geo g, uint32_t *__restri
     }
 }
 
+/* dense-grid fast path (N % 4 == 0, 16-byte aligned base): every lane streams float4s (512
+ * contiguous bytes per warp instruction), turns them into a 4-bit nibble and the nibbles of 8
+ * neighbouring lanes are OR-combined with 3 shuffles into one 32-sample word. */
+template <int U>
+__global__ void __launch_bounds__(256) k_sign_vec4(const float4 *__restrict__ grid4, Geo g, uint32_t *__restrict__ signs) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t nrows = g.nsl * g.N;
+    const uint32_t n4 = g.N >> 2;            /* float4 per sample row */
+    const uint32_t steps = (n4 + 31) >> 5;   /* 128-sample chunks per row */
+    const uint32_t sh = (lane & 7u) * 4u;
+    for (uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < nrows; row += nwarps) {
+        const float4 *rp = grid4 + (uint64_t)row * n4;
+        uint32_t *out = signs + (uint64_t)row * g.nws;
+        for (uint32_t c0 = 0; c0 < steps; c0 += U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i4 = (c0 + u) * 32 + lane;
+                v[u] = (i4 < n4) ? __ldg(rp + i4) : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                uint32_t nib = (!(v[u].x > 0.0f) ? 1u : 0u) | (!(v[u].y > 0.0f) ? 2u : 0u) |
+                               (!(v[u].z > 0.0f) ? 4u : 0u) | (!(v[u].w > 0.0f) ? 8u : 0u);
+                uint32_t w = nib << sh;
+                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
+                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
+                w |= __shfl_xor_sync(0xFFFFFFFFu, w, 4);
+                const uint32_t widx = (c0 + u) * 4 + (lane >> 3);
+                if ((lane & 7u) == 0 && widx < g.nws) out[widx] = w;
+            }
+        }
+        /* padding words past the last 128-sample chunk */
+        const uint32_t done = ((steps + U - 1) / U) * U * 4;
+        if (done + lane < g.nws) out[done + lane] = 0u;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* K2: per-segment counts, within-row prefixes, row totals                                      */
 /* ------------------------------------------------------------------------------------------ */
 
+/* One thread per 32-cell segment (all lanes busy whatever the row length); the within-row scan
+ * runs over shared memory afterwards, one warp per row. */
 __global__ void __launch_bounds__(256) k_count(Geo g, const uint32_t *__restrict__ signs,
                                                const McTables *__restrict__ tabs, uint32_t *__restrict__ segpre,
                                                uint32_t *__restrict__ rowV, uint32_t *__restrict__ rowT,
                                                uint32_t *__restrict__ rowA, unsigned long long *__restrict__ layerTot) {
     __shared__ uint8_t s_ntri[256];
+    __shared__ uint32_t s_cnt[256]; /* nv | nt << 16 */
+    __shared__ uint32_t s_act[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = tabs->ntri[i];
-    __syncthreads();
 
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nrows = g.ncl * g.ncx;
+    const uint32_t rows_per_cta = max(1u, 256u / g.nsegx); /* nsegx <= 256 (size <= 8192) */
+    const uint32_t ngroups = (nrows + rows_per_cta - 1) / rows_per_cta;
     const uint64_t layer_stride = (uint64_t)g.N * g.nws;
-    for (uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < nrows; row += nwarps) {
-        const uint32_t lz = row / g.ncx, y = row - lz * g.ncx;
-        const bool Z0 = (g.gz0 + lz) == 0, Y0 = (y == 0);
-        const uint32_t *r00 = signs + ((uint64_t)lz * g.N + y) * g.nws;
-        const uint32_t *r01 = r00 + g.nws, *r10 = r00 + layer_stride, *r11 = r10 + g.nws;
-        uint32_t carryV = 0, carryT = 0, carryA = 0;
-        for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 32) {
-            const uint32_t s = s0 + lane;
-            uint32_t nv = 0, nt = 0, na = 0;
-            if (s < g.nsegx) {
-                uint32_t a0 = __ldg(r00 + s), a1 = __ldg(r00 + s + 1);
-                uint32_t b0 = __ldg(r01 + s), b1 = __ldg(r01 + s + 1);
-                uint32_t c0 = __ldg(r10 + s), c1 = __ldg(r10 + s + 1);
-                uint32_t d0 = __ldg(r11 + s), d1 = __ldg(r11 + s + 1);
-                uint32_t all_or = a0 | b0 | c0 | d0 | (a1 & 1u) | (b1 & 1u) | (c1 & 1u) | (d1 & 1u);
-                uint32_t all_and = a0 & b0 & c0 & d0;
-                bool uniform = (all_or == 0u) || (all_and == 0xFFFFFFFFu && (a1 & b1 & c1 & d1 & 1u));
-                if (!uniform) {
-                    uint32_t an = __funnelshift_r(a0, a1, 1), bn = __funnelshift_r(b0, b1, 1);
-                    uint32_t cn = __funnelshift_r(c0, c1, 1), dn = __funnelshift_r(d0, d1, 1);
-                    uint32_t vm = valid_mask(g.ncx - s * 32);
-                    uint4 pl = owned_planes(a0, an, b0, bn, c0, cn, d0, dn, Z0, Y0, s == 0 ? 1u : 0u, vm);
-                    nv = planes_count(pl, 0xFFFFFFFFu);
-                    uint32_t act = active_mask(a0, an, b0, bn, c0, cn, d0, dn, vm);
-                    na = __popc(act);
-                    while (act) {
-                        uint32_t i = __ffs(act) - 1;
-                        act &= act - 1;
-                        uint32_t ci = (__funnelshift_r(a0, a1, i) & 3u) | (__funnelshift_r(b0, b1, i) & 3u) << 2 |
-                                      (__funnelshift_r(c0, c1, i) & 3u) << 4 | (__funnelshift_r(d0, d1, i) & 3u) << 6;
-                        nt += s_ntri[ci];
-                    }
+    const uint32_t rr = threadIdx.x / g.nsegx, s = threadIdx.x - rr * g.nsegx;
+
+    for (uint32_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        __syncthreads();
+        const uint32_t row = grp * rows_per_cta + rr;
+        uint32_t nv = 0, nt = 0, na = 0;
+        if (rr < rows_per_cta && row < nrows) {
+            const uint32_t lz = row / g.ncx, y = row - lz * g.ncx;
+            const uint32_t *r00 = signs + ((uint64_t)lz * g.N + y) * g.nws + s;
+            const uint32_t *r01 = r00 + g.nws, *r10 = r00 + layer_stride, *r11 = r10 + g.nws;
+            const uint32_t a0 = __ldg(r00), a1 = __ldg(r00 + 1), b0 = __ldg(r01), b1 = __ldg(r01 + 1);
+            const uint32_t c0 = __ldg(r10), c1 = __ldg(r10 + 1), d0 = __ldg(r11), d1 = __ldg(r11 + 1);
+            const uint32_t all_or = a0 | b0 | c0 | d0 | ((a1 | b1 | c1 | d1) & 1u);
+            const uint32_t all_and = a0 & b0 & c0 & d0;
+            const bool uniform = (all_or == 0u) || (all_and == 0xFFFFFFFFu && (a1 & b1 & c1 & d1 & 1u));
+            if (!uniform) {
+                const uint32_t an = __funnelshift_r(a0, a1, 1), bn = __funnelshift_r(b0, b1, 1);
+                const uint32_t cn = __funnelshift_r(c0, c1, 1), dn = __funnelshift_r(d0, d1, 1);
+                const uint32_t vm = valid_mask(g.ncx - s * 32);
+                const uint4 pl = owned_planes(a0, an, b0, bn, c0, cn, d0, dn, (g.gz0 + lz) == 0, y == 0, s == 0 ? 1u : 0u, vm);
+                nv = planes_count(pl, 0xFFFFFFFFu);
+                uint32_t act = active_mask(a0, an, b0, bn, c0, cn, d0, dn, vm);
+                na = __popc(act);
+                while (act) {
+                    const uint32_t i = __ffs(act) - 1;
+                    act &= act - 1;
+                    const uint32_t ci = (__funnelshift_r(a0, a1, i) & 3u) | (__funnelshift_r(b0, b1, i) & 3u) << 2 |
+                                        (__funnelshift_r(c0, c1, i) & 3u) << 4 | (__funnelshift_r(d0, d1, i) & 3u) << 6;
+                    nt += s_ntri[ci];
                 }
             }
-            /* warp inclusive scan of (nv, nt) packed as 2 x 16 bit is not safe in general (a row of
-             * boundary cells can exceed 16 bits only for N > 5461, rejected at create) */
-            uint32_t pk = nv | nt << 16, inc = pk;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= (uint32_t)d) inc += o;
-            }
-            uint32_t exc = inc - pk;
-            if (s < g.nsegx)
-                segpre[(uint64_t)row * g.nsegx + s] = ((carryV + (exc & 0xFFFFu)) & 0xFFFFu) | (carryT + (exc >> 16)) << 16;
-            uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            carryV += tot & 0xFFFFu;
-            carryT += tot >> 16;
-            uint32_t sa = na;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) sa += __shfl_xor_sync(0xFFFFFFFFu, sa, d);
-            carryA += sa;
         }
-        if (lane == 0) {
-            rowV[row] = carryV;
-            rowT[row] = carryT;
-            rowA[row] = carryA;
-            if (carryV | carryT) {
-                atomicAdd(&layerTot[3 * lz + 0], (unsigned long long)carryV);
-                atomicAdd(&layerTot[3 * lz + 1], (unsigned long long)carryT);
-                atomicAdd(&layerTot[3 * lz + 2], (unsigned long long)carryA);
+        s_cnt[threadIdx.x] = nv | nt << 16;
+        s_act[threadIdx.x] = na;
+        __syncthreads();
+        /* within-row exclusive scan: warp w takes rows w, w+8, ... of the group */
+        for (uint32_t r = warp; r < rows_per_cta; r += 8) {
+            const uint32_t grow = grp * rows_per_cta + r;
+            if (grow >= nrows) break;
+            uint32_t carry = 0, acta = 0;
+            for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 32) {
+                const uint32_t ss = s0 + lane;
+                const uint32_t pk = ss < g.nsegx ? s_cnt[r * g.nsegx + ss] : 0u;
+                acta += ss < g.nsegx ? s_act[r * g.nsegx + ss] : 0u;
+                uint32_t inc = pk; /* 16-bit fields cannot carry into each other: row totals < 65536 for size <= 8192 */
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                    if (lane >= (uint32_t)d) inc += o;
+                }
+                if (ss < g.nsegx) segpre[(uint64_t)grow * g.nsegx + ss] = carry + inc - pk;
+                carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acta += __shfl_xor_sync(0xFFFFFFFFu, acta, d);
+            if (lane == 0) {
+                const uint32_t tv = carry & 0xFFFFu, tt = carry >> 16;
+                rowV[grow] = tv;
+                rowT[grow] = tt;
+                rowA[grow] = acta;
+                if (carry) {
+                    const uint32_t lz = grow / g.ncx;
+                    atomicAdd(&layerTot[3 * lz + 0], (unsigned long long)tv);
+                    atomicAdd(&layerTot[3 * lz + 1], (unsigned long long)tt);
+                    atomicAdd(&layerTot[3 * lz + 2], (unsigned long long)acta);
+                }
             }
         }
     }
@@ -299,83 +348,112 @@ __global__ void k_slab_bases(const unsigned long long *__restrict__ gathered, ui
 /* ------------------------------------------------------------------------------------------ */
 /* K4: emission                                                                                 */
 /* ------------------------------------------------------------------------------------------ */
+/*
+ * Work unit: a brick of BX*32 x BY x BZ cells plus a one-cell halo on the low side of every axis
+ * (the cells that created the vertices the brick's triangles refer to): the "region".
+ * Everything variable-length is flattened before it is processed, so that every phase runs with
+ * (nearly) all lanes busy:
+ *
+ *   P1   one thread per 32-cell segment of the region: crossed-edge masks and bit-sliced
+ *        "vertices created" counts from the staged sign words; reserves list space; expands the
+ *        active-cell mask into a flat cell list.
+ *   P2   one thread per active cell of the region: cube index, id of the first vertex it creates,
+ *        and the ids of all edges it creates -> shared-memory id planes (one per edge axis, indexed
+ *        by the cell that would create the edge in an unbounded grid).  Own cells also write one
+ *        12-byte *vertex descriptor* (creator cell + edge) into the slot of each vertex they create
+ *        (k_vertex turns descriptors into positions) and enter their triangles in the triangle list.
+ *   B    one thread per triangle: three id-plane lookups, one 12-byte store (u32 x 3).
+ */
 
-constexpr int BX = 4;  /* brick: segments of 32 cells in x */
+constexpr int BX = 2;  /* brick: segments of 32 cells in x */
 constexpr int BY = 8;  /* rows */
 constexpr int BZ = 4;  /* layers */
 constexpr int EMIT_THREADS = 256;
-constexpr int LIST_CAP = BX * 32 * BY * BZ;
-constexpr int NWIN = (BZ + 2) * (BY + 2) * (BX + 1);
-constexpr int NDESC = (BZ + 1) * (BY + 1) * (BX + 1);
+constexpr int RX = BX * 32 + 1, RY = BY + 1, RZ = BZ + 1; /* region extents in cells */
+constexpr int NREGION = RX * RY * RZ;
+constexpr int NTASK = RZ * RY * BX;                        /* region segments */
+constexpr int NROWS_OWN = BY * BZ;
+constexpr int NROWS_REG = RY * RZ;
+constexpr int NROWS_STAGE = (BY + 2) * (BZ + 2);
+constexpr int TRI_CAP = 2560;                              /* triangles per pass; one row (BX*32*5) always fits */
+static_assert(NTASK <= 128 && NREGION <= 4096, "list entry bit fields");
+
+struct __align__(16) SegDesc {
+    uint32_t w[8];      /* a0 a1 b0 b1 c0 c1 d0 d1: inside bits of rows (y,z) (y+1,z) (y,z+1) (y+1,z+1), words s, s+1 */
+    uint32_t p0, p1, p2, p3; /* bit planes of "vertices created" per cell */
+    uint32_t vbase;     /* id (before vofs) of the first vertex created in this segment */
+    uint32_t tseg;      /* slot of the first triangle of this segment */
+    uint32_t cpos_tch;  /* cell-list start | triangle-list start << 16 */
+    uint32_t info;      /* region pos of cell 0 (12) | y==0 << 24 | z==0 << 25 | listed << 26 | (s == 0) << 27 |
+                           inside bits of sample 32s-1 in the 4 rows << 28 */
+    uint32_t act;       /* active cells */
+    uint32_t pad[3];
+};
 
 struct EmitShared {
     uint64_t tri[256];
-    uint64_t order[256];
-    uint64_t win[NWIN];
-    uint4 planes[NDESC];
-    uint2 list[LIST_CAP];
-    uint32_t dbase[NDESC];
-    uint16_t before[256][12];
+    SegDesc seg[NTASK];
+    uint32_t plane[3 * NREGION]; /* id (before vofs) of the x / y / z edge created by (virtual) cell */
+    uint32_t trilist[TRI_CAP];   /* region pos (12) | ci' << 12 | t << 20 | task << 23 */
+    uint32_t row_pv[NROWS_REG], row_pt[NROWS_REG], row_ptn[NROWS_REG];
+    uint16_t cellmap[NREGION];   /* task | i << 7 | x-halo << 12 */
     uint16_t emask[256];
     uint16_t ownmask[8];
+    int16_t offs[12];            /* plane index of edge e seen from a cell at region pos cp: cp + offs[e] */
+    int16_t back[12];            /* region-pos offset from a cell to the (virtual) creator of its edge e */
+    uint8_t axis[12];
+    uint8_t bstep[12];           /* dx | dy << 1 | dz << 2 of that offset */
     uint8_t ntri[256];
-    uint8_t owner[8][12];
-    uint8_t ends[12];
-    uint32_t list_n;
+    uint8_t rank3[256];
+    uint32_t cell_n, tri_n, overflow;
     uint32_t work;
     uint32_t ticket;
 };
 
 size_t isomc_emit_smem_bytes(uint32_t nws) {
-    return sizeof(EmitShared) + (size_t)(BZ + 2) * (BY + 2) * (nws + 2) * sizeof(uint32_t);
+    return sizeof(EmitShared) + (size_t)NROWS_STAGE * (nws + 2) * sizeof(uint32_t) + (size_t)NROWS_REG * nws * sizeof(uint32_t);
 }
 
-__device__ __forceinline__ int win_index(int li, int ri, int si) { return (li * (BY + 2) + ri) * (BX + 1) + si; }
-__device__ __forceinline__ int desc_index(int li, int ri, int si) { return (li * (BY + 1) + ri) * (BX + 1) + si; }
+__device__ __forceinline__ int region_pos(int rz, int ry, int rx) { return (rz * RY + ry) * RX + rx; }
 
-/* vertices created by cells before the one at descriptor bit p (p = 0: last cell of the previous
- * segment, p = i+1: cell i of this segment) */
-__device__ __forceinline__ uint32_t vertex_prefix(const EmitShared &S, int di, uint32_t p) {
-    const uint4 c = S.planes[di];
-    const uint32_t base = S.dbase[di];
-    if (p == 0) return base - ((c.x & 1u) + 2u * (c.y & 1u) + 4u * (c.z & 1u) + 8u * (c.w & 1u));
-    const uint32_t lt = (uint32_t)((1ull << p) - 1ull) & ~1u;
-    return base + planes_count(c, lt);
+__device__ __forceinline__ uint32_t cube_index_from(const SegDesc &D, uint32_t i) {
+    return (__funnelshift_r(D.w[0], D.w[1], i) & 3u) | (__funnelshift_r(D.w[2], D.w[3], i) & 3u) << 2 |
+           (__funnelshift_r(D.w[4], D.w[5], i) & 3u) << 4 | (__funnelshift_r(D.w[6], D.w[7], i) & 3u) << 6;
 }
 
-/* natural cube index of the cell at descriptor bit p whose low corner row is window (li, ri, si) */
-__device__ __forceinline__ uint32_t cube_index_at(const EmitShared &S, int li, int ri, int si, uint32_t p) {
-    const uint64_t wa = S.win[win_index(li, ri, si)], wb = S.win[win_index(li, ri + 1, si)];
-    const uint64_t wc = S.win[win_index(li + 1, ri, si)], wd = S.win[win_index(li + 1, ri + 1, si)];
-    return (lo32(wa >> p) & 3u) | (lo32(wb >> p) & 3u) << 2 | (lo32(wc >> p) & 3u) << 4 | (lo32(wd >> p) & 3u) << 6;
-}
-
-template <class Src>
-__global__ void __launch_bounds__(EMIT_THREADS) k_emit(Src src, Geo g, const uint32_t *__restrict__ signs,
+__global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__restrict__ signs,
                                                       const uint32_t *__restrict__ segpre,
                                                       const uint32_t *__restrict__ rowPV,
                                                       const uint32_t *__restrict__ rowPT,
                                                       const McTables *__restrict__ tabs,
                                                       const unsigned long long *__restrict__ totals,
                                                       const uint32_t *__restrict__ vofs_ptr, uint32_t *__restrict__ ticket,
-                                                      float *__restrict__ xyz, uint32_t *__restrict__ idx,
+                                                      uint32_t *__restrict__ vdesc, uint32_t *__restrict__ idx,
                                                       unsigned long long cap_v, unsigned long long cap_t) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmitShared &S = *reinterpret_cast<EmitShared *>(smem_raw);
     uint32_t *s_words = reinterpret_cast<uint32_t *>(smem_raw + sizeof(EmitShared));
-    const uint32_t WS = g.nws + 2; /* [0] = pad for segment -1, [1 + w] = word w, [nws + 1] = pad */
+    const uint32_t WS = g.nws + 2; /* [0] = pad for word -1, [1 + w] = word w, [nws + 1] = pad */
+    uint32_t *s_sp = s_words + (size_t)NROWS_STAGE * WS; /* segpre of the region rows: [row][nws] */
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 256; i += EMIT_THREADS) {
         S.tri[i] = tabs->tri[i];
-        S.order[i] = tabs->order[i];
         S.emask[i] = tabs->emask[i];
         S.ntri[i] = tabs->ntri[i];
+        S.rank3[i] = tabs->rank3[i];
     }
-    for (int i = tid; i < 256 * 12; i += EMIT_THREADS) (&S.before[0][0])[i] = (&tabs->before[0][0])[i];
     if (tid < 8) S.ownmask[tid] = tabs->ownmask[tid];
-    if (tid < 96) (&S.owner[0][0])[tid] = (&tabs->owner[0][0])[tid];
-    if (tid < 12) S.ends[tid] = tabs->ends[tid];
+    if (tid < 12) {
+        const uint32_t ow = tabs->owner[0][tid]; /* unbounded grid: every step back is allowed */
+        const uint32_t e2 = ow >> 4;             /* always one of 5 (y edge), 6 (x edge), 10 (z edge) */
+        const int back = (int)((ow & 1) + (ow >> 1 & 1) * RX + (ow >> 2 & 1) * RX * RY);
+        const int axis = e2 == 6 ? 0 : e2 == 5 ? 1 : 2;
+        S.back[tid] = (int16_t)back;
+        S.bstep[tid] = (uint8_t)(ow & 7);
+        S.axis[tid] = (uint8_t)axis;
+        S.offs[tid] = (int16_t)(axis * NREGION - back);
+    }
 
     const uint32_t vofs = *vofs_ptr;
     const uint32_t ghostV = (uint32_t)totals[4], ghostT = (uint32_t)totals[5];
@@ -392,167 +470,256 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Src src, Geo g, const uin
         const uint32_t bz = brow / nby, by = brow - bz * nby;
         const int lz0 = (int)(bz * BZ), y0 = (int)(by * BY);
 
-        /* any triangles in these rows? (prefix differences; rows are consecutive in (lz, y) order) */
+        /* row prefixes of the region rows; any triangles in the own rows? */
+        if (tid < NROWS_REG) {
+            const int rz = tid / RY, ry = tid % RY;
+            const int l = lz0 - 1 + rz, r = y0 - 1 + ry;
+            uint32_t pv = 0, pt = 0, ptn = 0;
+            if (l >= 0 && l < (int)g.ncl && r >= 0 && r < (int)g.ncx) {
+                const uint32_t row = (uint32_t)l * g.ncx + (uint32_t)r;
+                pv = rowPV[row]; pt = rowPT[row]; ptn = rowPT[row + 1];
+            }
+            S.row_pv[tid] = pv; S.row_pt[tid] = pt; S.row_ptn[tid] = ptn;
+        }
+        __syncthreads();
         if (tid == 0) {
             uint32_t t = 0;
-            for (int l = lz0; l < lz0 + BZ && l < (int)g.ncl; ++l) {
-                if ((uint32_t)l < first_own_layer) continue;
-                uint32_t rb = (uint32_t)l * g.ncx + (uint32_t)y0;
-                uint32_t re = (uint32_t)l * g.ncx + min((uint32_t)(y0 + BY), g.ncx);
-                t += rowPT[re] - rowPT[rb];
+            for (int q = 0; q < NROWS_REG; ++q) {
+                const int rz = q / RY, ry = q % RY;
+                if (rz >= 1 && ry >= 1 && lz0 - 1 + rz >= (int)first_own_layer) t |= S.row_ptn[q] - S.row_pt[q];
             }
             S.work = t;
         }
         __syncthreads();
         if (S.work == 0) continue;
 
-        /* stage the sign words of the brick row (+1 halo row/layer on each side) */
-        for (uint32_t rr = warp; rr < (BZ + 2) * (BY + 2); rr += EMIT_THREADS / 32) {
+        /* stage the sign words (+1 halo row/layer on each side) and the segment prefixes of the brick row */
+        for (uint32_t rr = warp; rr < NROWS_STAGE; rr += EMIT_THREADS / 32) {
             const int li = (int)(rr / (BY + 2)), ri = (int)(rr % (BY + 2));
             const int l = lz0 - 1 + li, r = y0 - 1 + ri;
             uint32_t *dst = s_words + (size_t)rr * WS;
             const bool ok = l >= 0 && l < (int)g.nsl && r >= 0 && r < (int)g.N;
-            const uint32_t *srcw = signs + ((uint64_t)(ok ? l : 0) * g.N + (ok ? r : 0)) * g.nws;
-            for (uint32_t w = lane; w < WS; w += 32) dst[w] = (ok && w >= 1 && w <= g.nws) ? __ldg(srcw + w - 1) : 0u;
+            const uint32_t *srcw = signs + ((uint64_t)(ok ? l : 0) * g.N + (ok ? r : 0)) * g.nws - 1;
+            for (uint32_t w = lane; w < WS; w += 32) dst[w] = (ok && w >= 1 && w <= g.nws) ? __ldg(srcw + w) : 0u;
+            if (li < RZ && ri < RY) {
+                const bool okc = l >= 0 && l < (int)g.ncl && r >= 0 && r < (int)g.ncx;
+                const uint32_t *srcp = segpre + ((uint64_t)(okc ? l : 0) * g.ncx + (okc ? r : 0)) * g.nsegx;
+                uint32_t *dp = s_sp + (size_t)(li * RY + ri) * g.nws;
+                for (uint32_t w = lane; w < g.nsegx; w += 32) dp[w] = okc ? __ldg(srcp + w) : 0u;
+            }
         }
-        __syncthreads();
 
         for (uint32_t bx = 0; bx < nbx; ++bx) {
             const int sx0 = (int)(bx * BX);
-            /* windows: bit j of win(l, r, s) = inside bit of sample x = 32 s - 1 + j */
-            for (int w = tid; w < NWIN; w += EMIT_THREADS) {
-                const int si = w % (BX + 1), rr = w / (BX + 1);
-                const int s = sx0 - 1 + si;
-                uint64_t v = 0;
-                if (s >= 0 && s < (int)g.nsegx) {
-                    const uint32_t *rw = s_words + (size_t)rr * WS + 1 + s; /* rw[-1] is valid storage */
-                    const uint32_t wm = rw[-1], w0 = rw[0], w1 = rw[1];
-                    v = (uint64_t)__funnelshift_r(wm, w0, 31) | (uint64_t)__funnelshift_r(w0, w1, 31) << 32;
-                }
-                S.win[w] = v;
-            }
-            if (tid == 0) S.list_n = 0;
-            __syncthreads();
+            /* own rows q = layer * BY + row listed per pass: all 32, then 8 (one layer), then 1 if too dense */
+            int lo = 0, level = 0;
+            bool first = true;
+            for (;;) {
+                const int hi = min(NROWS_OWN, lo + (level == 0 ? NROWS_OWN : level == 1 ? BY : 1));
+                __syncthreads(); /* staged data visible / previous pass done with the lists */
+                if (tid == 0) { S.cell_n = 0; S.tri_n = 0; S.overflow = 0; }
+                __syncthreads();
 
-            /* descriptors: bit planes of "vertices created" per cell + absolute prefix at segment start */
-            for (int d = tid; d < NDESC; d += EMIT_THREADS) {
-                const int si = d % (BX + 1), ri = (d / (BX + 1)) % (BY + 1), li = d / ((BX + 1) * (BY + 1));
-                const int l = lz0 - 1 + li, r = y0 - 1 + ri, s = sx0 - 1 + si;
-                uint4 pl = make_uint4(0, 0, 0, 0);
-                uint32_t base = 0;
-                if (l >= 0 && l < (int)g.ncl && r >= 0 && r < (int)g.ncx && s >= 0 && s < (int)g.nsegx) {
-                    const uint64_t wa = S.win[win_index(li, ri, si)], wb = S.win[win_index(li, ri + 1, si)];
-                    const uint64_t wc = S.win[win_index(li + 1, ri, si)], wd = S.win[win_index(li + 1, ri + 1, si)];
-                    /* bit j <-> cell 32 s - 1 + j; valid cells are [0, ncx) */
-                    const int jhi = (int)g.ncx - 32 * s; /* last valid bit */
-                    uint32_t vm = valid_mask((uint32_t)min(32, jhi + 1));
-                    if (s == 0) vm &= ~1u;
-                    pl = owned_planes(lo32(wa), lo32(wa >> 1), lo32(wb), lo32(wb >> 1), lo32(wc), lo32(wc >> 1),
-                                      lo32(wd), lo32(wd >> 1), (g.gz0 + (uint32_t)l) == 0, r == 0, s == 0 ? 2u : 0u, vm);
-                    const uint32_t row = (uint32_t)l * g.ncx + (uint32_t)r;
-                    base = rowPV[row] + (__ldg(segpre + (uint64_t)row * g.nsegx + s) & 0xFFFFu);
+                /* ---------------- P1: one thread per region segment ---------------- */
+                for (int task = tid; task < NTASK; task += EMIT_THREADS) {
+                    const int sl = task % BX, ry = (task / BX) % RY, rz = task / (BX * RY);
+                    const int l = lz0 - 1 + rz, r = y0 - 1 + ry, s = sx0 + sl;
+                    if (l < 0 || l >= (int)g.ncl || r < 0 || r >= (int)g.ncx || s >= (int)g.nsegx) continue;
+                    const bool own = rz >= 1 && ry >= 1 && (uint32_t)l >= first_own_layer;
+                    const int q = (rz - 1) * BY + (ry - 1);
+                    const bool listed = own && q >= lo && q < hi;
+                    if (!first && !listed) continue;
+                    /* rows (l, r), (l, r+1), (l+1, r), (l+1, r+1): words s-1, s, s+1 */
+                    const uint32_t *wa = s_words + (size_t)(rz * (BY + 2) + ry) * WS + 1 + s;
+                    const uint32_t *wb = wa + WS, *wc = wa + (size_t)(BY + 2) * WS, *wd = wc + WS;
+                    const uint32_t a0 = wa[0], a1 = wa[1], b0 = wb[0], b1 = wb[1];
+                    const uint32_t c0 = wc[0], c1 = wc[1], d0 = wd[0], d1 = wd[1];
+                    const uint32_t gz = g.gz0 + (uint32_t)l;
+                    /* x-halo cell (last cell of the previous segment) of the brick's first segment */
+                    uint32_t prevbits = 0, hx = 0;
+                    if (sl == 0 && s > 0) {
+                        prevbits = (wa[-1] >> 31) | (wb[-1] >> 31) << 1 | (wc[-1] >> 31) << 2 | (wd[-1] >> 31) << 3;
+                        const uint32_t nextbits = (a0 & 1u) | (b0 & 1u) << 1 | (c0 & 1u) << 2 | (d0 & 1u) << 3;
+                        const uint32_t both = prevbits | nextbits << 4;
+                        hx = (first && both != 0 && both != 255) ? 1u : 0u;
+                    }
+                    const uint32_t all_or = a0 | b0 | c0 | d0 | ((a1 | b1 | c1 | d1) & 1u);
+                    const uint32_t all_and = a0 & b0 & c0 & d0;
+                    const bool uniform = (all_or == 0u) || (all_and == 0xFFFFFFFFu && (a1 & b1 & c1 & d1 & 1u));
+                    uint32_t act = 0;
+                    uint4 pl = make_uint4(0, 0, 0, 0);
+                    if (!uniform) {
+                        const uint32_t an = __funnelshift_r(a0, a1, 1), bn = __funnelshift_r(b0, b1, 1);
+                        const uint32_t cn = __funnelshift_r(c0, c1, 1), dn = __funnelshift_r(d0, d1, 1);
+                        const uint32_t vm = valid_mask(g.ncx - (uint32_t)s * 32);
+                        act = active_mask(a0, an, b0, bn, c0, cn, d0, dn, vm);
+                        if (act) pl = owned_planes(a0, an, b0, bn, c0, cn, d0, dn, gz == 0, r == 0, s == 0 ? 1u : 0u, vm);
+                    }
+                    if ((act | hx) == 0) continue;
+                    const int rq = rz * RY + ry;
+                    const uint32_t sp = s_sp[(size_t)rq * g.nws + s];
+                    const uint32_t na = __popc(act);
+                    const uint32_t cpos = atomicAdd(&S.cell_n, na + hx);
+                    uint32_t tch = 0;
+                    const uint32_t tseg = S.row_pt[rq] + (sp >> 16);
+                    if (listed && act) {
+                        /* triangles of this segment = next segment's prefix - ours (row total for the last one) */
+                        const uint32_t tnext = (s + 1 < (int)g.nsegx) ? S.row_pt[rq] + (s_sp[(size_t)rq * g.nws + s + 1] >> 16) : S.row_ptn[rq];
+                        const uint32_t nt_seg = tnext - tseg;
+                        tch = atomicAdd(&S.tri_n, nt_seg);
+                        if (tch + nt_seg > TRI_CAP) { S.overflow = 1; tch = 0; }
+                    }
+                    SegDesc &D = S.seg[task];
+                    D.w[0] = a0; D.w[1] = a1; D.w[2] = b0; D.w[3] = b1; D.w[4] = c0; D.w[5] = c1; D.w[6] = d0; D.w[7] = d1;
+                    D.p0 = pl.x; D.p1 = pl.y; D.p2 = pl.z; D.p3 = pl.w;
+                    D.vbase = S.row_pv[rq] + (sp & 0xFFFFu);
+                    D.tseg = tseg;
+                    D.cpos_tch = cpos | tch << 16;
+                    D.info = (uint32_t)region_pos(rz, ry, 32 * sl + 1) | (r == 0 ? 1u : 0u) << 24 | (gz == 0 ? 1u : 0u) << 25 |
+                             (listed ? 1u : 0u) << 26 | (s == 0 ? 1u : 0u) << 27 | prevbits << 28;
+                    D.act = act;
+                    uint32_t k = cpos;
+                    while (act) { /* expansion: one store per active cell */
+                        const uint32_t i = __ffs(act) - 1;
+                        act &= act - 1;
+                        S.cellmap[k++] = (uint16_t)((uint32_t)task | i << 7);
+                    }
+                    if (hx) S.cellmap[k] = (uint16_t)((uint32_t)task | 1u << 12);
                 }
-                S.planes[d] = pl;
-                S.dbase[d] = base;
-            }
+                __syncthreads();
+                const bool ovf = S.overflow != 0;
+                const uint32_t n_cells = S.cell_n;
 
-            /* compaction of the brick's active cells; one warp per 32-cell segment, lane = cell */
-            for (int sg = warp; sg < BX * BY * BZ; sg += EMIT_THREADS / 32) {
-                const int sl = sg % BX, rl = (sg / BX) % BY, ll = sg / (BX * BY);
-                const int l = lz0 + ll, r = y0 + rl, s = sx0 + sl;
-                if (l >= (int)g.ncl || (uint32_t)l < first_own_layer || r >= (int)g.ncx || s >= (int)g.nsegx) continue;
-                const uint32_t x = (uint32_t)s * 32 + lane;
-                const uint32_t ci = cube_index_at(S, ll + 1, rl + 1, sl + 1, lane + 1);
-                const bool active = x < g.ncx && ci != 0 && ci != 255;
-                const uint32_t nt = active ? S.ntri[ci] : 0;
-                const uint32_t am = __ballot_sync(0xFFFFFFFFu, active);
-                if (am == 0) continue;
-                uint32_t inc = nt;
-#pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {
-                    uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, dd);
-                    if (lane >= (uint32_t)dd) inc += o;
-                }
-                const uint32_t row = (uint32_t)l * g.ncx + (uint32_t)r;
-                const uint32_t tseg = rowPT[row] + (__ldg(segpre + (uint64_t)row * g.nsegx + s) >> 16);
-                uint32_t pos0 = 0;
-                if (lane == 0) pos0 = atomicAdd(&S.list_n, (uint32_t)__popc(am));
-                pos0 = __shfl_sync(0xFFFFFFFFu, pos0, 0);
-                if (active) {
-                    const uint32_t pos = pos0 + __popc(am & ((1u << lane) - 1u));
-                    S.list[pos] = make_uint2(lane | (uint32_t)sl << 5 | (uint32_t)rl << 8 | (uint32_t)ll << 12 | ci << 16,
-                                             tseg + inc - nt);
-                }
-            }
-            __syncthreads();
-
-            /* one thread per active cell: create the owned vertices, write the triangles */
-            const uint32_t n_act = S.list_n;
-            for (uint32_t k = tid; k < n_act; k += EMIT_THREADS) {
-                const uint2 ent = S.list[k];
-                const uint32_t i = ent.x & 31u, ci = (ent.x >> 16) & 255u;
-                const int sl = (int)((ent.x >> 5) & 7u), rl = (int)((ent.x >> 8) & 15u), ll = (int)((ent.x >> 12) & 15u);
-                const uint32_t x = (uint32_t)(sx0 + sl) * 32 + i, y = (uint32_t)(y0 + rl), lz = (uint32_t)(lz0 + ll);
-                const uint32_t gz = g.gz0 + lz;
-                const uint32_t bflags = (x == 0 ? 1u : 0u) | (y == 0 ? 2u : 0u) | (gz == 0 ? 4u : 0u);
-                const uint32_t em = S.emask[ci];
-
-                /* ---- vertices this cell creates (mesh.rs:240-251 cache-miss path), in first-appearance order */
-                const uint32_t owned = em & S.ownmask[bflags];
-                if (owned) {
-                    uint32_t slot = vertex_prefix(S, desc_index(ll + 1, rl + 1, sl + 1), i + 1) - ghostV;
-                    uint64_t ord = S.order[ci];
-                    for (uint32_t rem = em; rem; rem &= rem - 1, ord >>= 4) {
-                        const uint32_t e = (uint32_t)ord & 15u;
-                        if (!(owned >> e & 1u)) continue;
-                        const uint32_t en = S.ends[e];
-                        const uint32_t ux = x + (en & 1u), uy = y + (en >> 1 & 1u), uz = en >> 2 & 1u;
-                        const uint32_t vx = x + (en >> 4 & 1u), vy = y + (en >> 5 & 1u), vz = en >> 6 & 1u;
-                        const float a = src.at(g, ux, uy, lz + uz), b = src.at(g, vx, vy, lz + vz);
-                        /* distance.rs:64-69 */
-                        const float delta = __fsub_rn(b, a);
-                        const float t = (delta == 0.0f) ? 0.5f : __fdiv_rn(-a, delta);
-                        const float omt = __fsub_rn(1.0f, t);
-                        const float pax = __fmul_rn((float)ux, g.inv), pay = __fmul_rn((float)uy, g.inv);
-                        const float paz = __fmul_rn((float)(gz + uz), g.inv);
-                        const float pbx = __fmul_rn((float)vx, g.inv), pby = __fmul_rn((float)vy, g.inv);
-                        const float pbz = __fmul_rn((float)(gz + vz), g.inv);
-                        if (slot < cap_v) {
-                            float *o = xyz + (uint64_t)slot * 3;
-                            o[0] = __fadd_rn(__fmul_rn(pax, omt), __fmul_rn(pbx, t));
-                            o[1] = __fadd_rn(__fmul_rn(pay, omt), __fmul_rn(pby, t));
-                            o[2] = __fadd_rn(__fmul_rn(paz, omt), __fmul_rn(pbz, t));
+                /* ---------------- P2: one thread per active cell of the region ---------------- */
+                for (uint32_t k = tid; k < n_cells; k += EMIT_THREADS) {
+                    const uint32_t cm = S.cellmap[k];
+                    const uint32_t task = cm & 127u, i = (cm >> 7) & 31u;
+                    const SegDesc &D = S.seg[task];
+                    const uint32_t info = D.info;
+                    bool listed = (info >> 26 & 1u) && !ovf;
+                    uint32_t ci, vid, bfl;
+                    int cp;
+                    if (cm >> 12) { /* x-halo cell: corners from sample 32s-1 (prev bits) and sample 32s (bit 0) */
+                        const uint32_t pb = info >> 28;
+                        ci = (pb & 1u) | (D.w[0] & 1u) << 1 | (pb >> 1 & 1u) << 2 | (D.w[2] & 1u) << 3 | (pb >> 2 & 1u) << 4 |
+                             (D.w[4] & 1u) << 5 | (pb >> 3 & 1u) << 6 | (D.w[6] & 1u) << 7;
+                        bfl = (info >> 24 & 1u) << 1 | (info >> 25 & 1u) << 2;
+                        vid = D.vbase - __popc((uint32_t)S.emask[ci] & (uint32_t)S.ownmask[bfl]);
+                        cp = (int)(info & 4095u) - 1;
+                        listed = false; /* belongs to the brick on the left */
+                    } else {
+                        ci = cube_index_from(D, i);
+                        vid = D.vbase + planes_count(make_uint4(D.p0, D.p1, D.p2, D.p3), (1u << i) - 1u);
+                        bfl = ((info >> 27 & 1u) && i == 0 ? 1u : 0u) | (info >> 24 & 1u) << 1 | (info >> 25 & 1u) << 2;
+                        cp = (int)(info & 4095u) + (int)i;
+                    }
+                    const uint32_t em = S.emask[ci];
+                    /* cell coordinates for the vertex descriptors: x | y << 16, local layer | e << 16 */
+                    const int rx = cp % RX, ry = (cp / RX) % RY, rz = cp / (RX * RY);
+                    const uint32_t dxy = (uint32_t)(sx0 * 32 + rx - 1) | (uint32_t)(y0 + ry - 1) << 16;
+                    const uint32_t dlz = (uint32_t)(lz0 + rz - 1);
+                    if (bfl == 0) { /* interior: creates exactly its crossed e5, e6, e10, ranks from rank3 */
+                        const uint32_t r3 = S.rank3[ci];
+                        if (em >> 6 & 1u) {
+                            const uint32_t id = vid + (r3 >> 2 & 3u);
+                            S.plane[cp] = id;
+                            if (listed && id - ghostV < cap_v) { vdesc[3 * (uint64_t)(id - ghostV)] = dxy; vdesc[3 * (uint64_t)(id - ghostV) + 1] = dlz | 6u << 16; }
                         }
-                        ++slot;
+                        if (em >> 5 & 1u) {
+                            const uint32_t id = vid + (r3 & 3u);
+                            S.plane[NREGION + cp] = id;
+                            if (listed && id - ghostV < cap_v) { vdesc[3 * (uint64_t)(id - ghostV)] = dxy; vdesc[3 * (uint64_t)(id - ghostV) + 1] = dlz | 5u << 16; }
+                        }
+                        if (em >> 10 & 1u) {
+                            const uint32_t id = vid + (r3 >> 4 & 3u);
+                            S.plane[2 * NREGION + cp] = id;
+                            if (listed && id - ghostV < cap_v) { vdesc[3 * (uint64_t)(id - ghostV)] = dxy; vdesc[3 * (uint64_t)(id - ghostV) + 1] = dlz | 10u << 16; }
+                        }
+                    } else { /* on a low boundary face: more edges, first-appearance order decides the ranks */
+                        const uint32_t owned = em & S.ownmask[bfl];
+                        uint64_t ord = tabs->order[ci];
+                        uint32_t id = vid;
+                        for (uint32_t rem = em; rem; rem &= rem - 1, ord >>= 4) {
+                            const uint32_t e = (uint32_t)ord & 15u;
+                            if (!(owned >> e & 1u)) continue;
+                            const uint32_t st = S.bstep[e];
+                            if ((int)(st & 1u) <= rx && (int)(st >> 1 & 1u) <= ry && (int)(st >> 2 & 1u) <= rz) S.plane[cp + S.offs[e]] = id;
+                            if (listed && id - ghostV < cap_v) { vdesc[3 * (uint64_t)(id - ghostV)] = dxy; vdesc[3 * (uint64_t)(id - ghostV) + 1] = dlz | e << 16; }
+                            ++id;
+                        }
+                    }
+                    if (listed) {
+                        /* triangle-list position: triangles of the earlier active cells of the segment */
+                        uint32_t tp = D.cpos_tch >> 16;
+                        for (uint32_t m = D.act & ((1u << i) - 1u); m; m &= m - 1) tp += S.ntri[cube_index_from(D, __ffs(m) - 1)];
+                        const uint32_t ent = (uint32_t)cp | ci << 12 | task << 23;
+                        const uint32_t nt = S.ntri[ci];
+                        for (uint32_t t = 0; t < nt; ++t) S.trilist[tp + t] = ent | t << 20;
                     }
                 }
+                __syncthreads();
 
-                /* ---- triangles (march_cube, marching_cubes_impl.rs:102-117), ids by edge ownership */
-                uint64_t tl = S.tri[ci];
-                uint32_t tslot = ent.y - ghostT;
-                const uint32_t nt = S.ntri[ci];
-                for (uint32_t t = 0; t < nt; ++t, ++tslot) {
-                    uint32_t ids[3];
-#pragma unroll
-                    for (int q = 0; q < 3; ++q, tl >>= 4) {
-                        const uint32_t e = (uint32_t)tl & 15u;
-                        const uint32_t ow = S.owner[bflags][e];
-                        const int dx = ow & 1, dy = ow >> 1 & 1, dz = ow >> 2 & 1;
-                        const uint32_t e2 = ow >> 4;
-                        const uint32_t p = i + 1 - dx;
-                        const uint32_t oci = cube_index_at(S, ll + 1 - dz, rl + 1 - dy, sl + 1, p);
-                        const uint32_t ob = ((x - dx) == 0 ? 1u : 0u) | ((y - dy) == 0 ? 2u : 0u) | ((gz - dz) == 0 ? 4u : 0u);
-                        const uint32_t rank = __popc((uint32_t)S.before[oci][e2] & (uint32_t)S.ownmask[ob]);
-                        ids[q] = vofs + vertex_prefix(S, desc_index(ll + 1 - dz, rl + 1 - dy, sl + 1), p) + rank;
+                if (!ovf) {
+                    /* ---------------- B: one thread per triangle ---------------- */
+                    const uint32_t n_tri = S.tri_n;
+                    for (uint32_t j = tid; j < n_tri; j += EMIT_THREADS) {
+                        const uint32_t ent = S.trilist[j];
+                        const int cp = (int)(ent & 4095u);
+                        const uint32_t ci = (ent >> 12) & 255u, t = (ent >> 20) & 7u, task = ent >> 23;
+                        const uint32_t edges = (uint32_t)(S.tri[ci] >> (12 * t));
+                        const uint32_t i0 = vofs + S.plane[cp + S.offs[edges & 15u]];
+                        const uint32_t i1 = vofs + S.plane[cp + S.offs[(edges >> 4) & 15u]];
+                        const uint32_t i2 = vofs + S.plane[cp + S.offs[(edges >> 8) & 15u]];
+                        const SegDesc &D = S.seg[task];
+                        const uint32_t tslot = D.tseg + (j - (D.cpos_tch >> 16)) - ghostT;
+                        if (tslot < cap_t) {
+                            uint32_t *o = idx + (uint64_t)tslot * 3;
+                            o[0] = i0; o[1] = i1; o[2] = i2;
+                        }
                     }
-                    if (tslot < cap_t) {
-                        uint32_t *o = idx + (uint64_t)tslot * 3;
-                        o[0] = ids[0]; o[1] = ids[1]; o[2] = ids[2];
-                    }
+                    lo = hi;
+                    if (lo >= NROWS_OWN) break;
+                } else {
+                    if (level == 2) break; /* cannot happen (one row always fits); never spin */
+                    ++level;               /* too dense: list fewer rows per pass (the id planes are filled) */
                 }
+                first = false;
             }
-            __syncthreads();
         }
+    }
+}
+
+/* vertex descriptor (written by k_emit into the vertex's own 12-byte slot) -> position, in place.
+ * descriptor: [0] = x | y << 16 of the creating cell, [1] = local layer | edge << 16.
+ * Interpolation = Signed::find_crossing_point (distance.rs:64-69) between the edge's ends in
+ * EDGE_CONNECTION direction of the creating cell, corner coordinates = (i as f32) * inv. */
+template <class Src>
+__global__ void __launch_bounds__(256) k_vertex(Src src, Geo g, const McTables *__restrict__ tabs,
+                                                const unsigned long long *__restrict__ totals, float *__restrict__ xyz,
+                                                unsigned long long cap_v) {
+    __shared__ uint8_t s_ends[12];
+    if (threadIdx.x < 12) s_ends[threadIdx.x] = tabs->ends[threadIdx.x];
+    __syncthreads();
+    unsigned long long n = totals[8];
+    if (n > cap_v) n = cap_v;
+    const uint32_t *desc = reinterpret_cast<const uint32_t *>(xyz);
+    for (unsigned long long v = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; v < n;
+         v += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t d0 = desc[3 * v], d1 = desc[3 * v + 1];
+        const uint32_t x = d0 & 0xFFFFu, y = d0 >> 16, lz = d1 & 0xFFFFu, e = d1 >> 16;
+        const uint32_t gz = g.gz0 + lz;
+        const uint32_t en = s_ends[e];
+        const uint32_t ux = x + (en & 1u), uy = y + (en >> 1 & 1u), uz = en >> 2 & 1u;
+        const uint32_t vx = x + (en >> 4 & 1u), vy = y + (en >> 5 & 1u), vz = en >> 6 & 1u;
+        const float a = src.at(g, ux, uy, lz + uz), b = src.at(g, vx, vy, lz + vz);
+        const float delta = __fsub_rn(b, a);
+        const float t = (delta == 0.0f) ? 0.5f : __fdiv_rn(-a, delta);
+        const float omt = __fsub_rn(1.0f, t);
+        const float pax = __fmul_rn((float)ux, g.inv), pay = __fmul_rn((float)uy, g.inv), paz = __fmul_rn((float)(gz + uz), g.inv);
+        const float pbx = __fmul_rn((float)vx, g.inv), pby = __fmul_rn((float)vy, g.inv), pbz = __fmul_rn((float)(gz + vz), g.inv);
+        xyz[3 * v] = __fadd_rn(__fmul_rn(pax, omt), __fmul_rn(pbx, t));
+        xyz[3 * v + 1] = __fadd_rn(__fmul_rn(pay, omt), __fmul_rn(pby, t));
+        xyz[3 * v + 2] = __fadd_rn(__fmul_rn(paz, omt), __fmul_rn(pbz, t));
     }
 }
 
@@ -621,8 +788,15 @@ static inline uint32_t grid_for(uint64_t warps_needed, int sms, int warps_per_bl
 }
 
 cudaError_t isomc_launch_sign_grid(const Geo &g, const float *d_grid, uint32_t *signs, int sms, cudaStream_t st) {
-    GridSrc src{d_grid};
-    k_sign<GridSrc><<<grid_for((uint64_t)g.nsl * g.N, sms, 8, 8), 256, 0, st>>>(src, g, signs);
+    const uint32_t grid = grid_for((uint64_t)g.nsl * g.N, sms, 8, 8);
+    if ((g.N & 3u) == 0 && (reinterpret_cast<uintptr_t>(d_grid) & 15u) == 0) {
+        const float4 *g4 = reinterpret_cast<const float4 *>(d_grid);
+        if (g.N >= 1024) k_sign_vec4<8><<<grid, 256, 0, st>>>(g4, g, signs);
+        else k_sign_vec4<4><<<grid, 256, 0, st>>>(g4, g, signs);
+    } else {
+        GridSrc src{d_grid};
+        k_sign<GridSrc><<<grid, 256, 0, st>>>(src, g, signs);
+    }
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, uint32_t *signs, int sms, cudaStream_t st) {
@@ -633,7 +807,10 @@ cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, uint32_t
 cudaError_t isomc_launch_count(const Geo &g, const uint32_t *signs, const McTables *tabs, uint32_t *segpre,
                                uint32_t *rowV, uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot,
                                int sms, cudaStream_t st) {
-    k_count<<<grid_for((uint64_t)g.ncl * g.ncx, sms, 8, 8), 256, 0, st>>>(g, signs, tabs, segpre, rowV, rowT, rowA, layerTot);
+    const uint32_t rows_per_cta = 256u / g.nsegx > 0 ? 256u / g.nsegx : 1u;
+    const uint64_t groups = ((uint64_t)g.ncl * g.ncx + rows_per_cta - 1) / rows_per_cta;
+    k_count<<<(uint32_t)(groups < (uint64_t)sms * 8 ? groups : (uint64_t)sms * 8), 256, 0, st>>>(g, signs, tabs, segpre, rowV, rowT, rowA,
+                                                                                           layerTot);
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_scan(const Geo &g, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
@@ -647,27 +824,22 @@ cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t
     return cudaGetLastError();
 }
 
-template <class Src>
-static cudaError_t launch_emit(Src src, const Geo &g, const uint32_t *signs, const uint32_t *segpre,
-                               const uint32_t *rowPV, const uint32_t *rowPT, const McTables *tabs,
-                               const unsigned long long *totals, const uint32_t *vofs, uint32_t *ticket, float *xyz,
-                               uint32_t *idx, uint64_t cap_v, uint64_t cap_t, int sms, cudaStream_t st) {
+static cudaError_t launch_emit(const Geo &g, const uint32_t *signs, const uint32_t *segpre, const uint32_t *rowPV,
+                               const uint32_t *rowPT, const McTables *tabs, const unsigned long long *totals,
+                               const uint32_t *vofs, uint32_t *ticket, float *xyz, uint32_t *idx, uint64_t cap_v,
+                               uint64_t cap_t, int sms, cudaStream_t st) {
     const size_t smem = isomc_emit_smem_bytes(g.nws);
-    static size_t configured = 0; /* per template instantiation */
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_emit<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     int per_sm = 1;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit<Src>, EMIT_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit, EMIT_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const uint32_t nby = (g.ncx + BY - 1) / BY, nbz = (g.ncl + BZ - 1) / BZ;
     uint64_t blocks = (uint64_t)nby * nbz;
     if (blocks > (uint64_t)sms * per_sm) blocks = (uint64_t)sms * per_sm;
-    k_emit<Src><<<(uint32_t)blocks, EMIT_THREADS, smem, st>>>(src, g, signs, segpre, rowPV, rowPT, tabs, totals, vofs,
-                                                              ticket, xyz, idx, cap_v, cap_t);
+    k_emit<<<(uint32_t)blocks, EMIT_THREADS, smem, st>>>(g, signs, segpre, rowPV, rowPT, tabs, totals, vofs, ticket,
+                                                         reinterpret_cast<uint32_t *>(xyz), idx, cap_v, cap_t);
     return cudaGetLastError();
 }
 
@@ -675,13 +847,19 @@ cudaError_t isomc_launch_emit_grid(const Geo &g, const float *d_grid, const uint
                                    const uint32_t *rowPV, const uint32_t *rowPT, const McTables *tabs,
                                    const unsigned long long *totals, const uint32_t *vofs, uint32_t *ticket, float *xyz,
                                    uint32_t *idx, uint64_t cap_v, uint64_t cap_t, int sms, cudaStream_t st) {
-    return launch_emit(GridSrc{d_grid}, g, signs, segpre, rowPV, rowPT, tabs, totals, vofs, ticket, xyz, idx, cap_v, cap_t, sms, st);
+    cudaError_t e = launch_emit(g, signs, segpre, rowPV, rowPT, tabs, totals, vofs, ticket, xyz, idx, cap_v, cap_t, sms, st);
+    if (e != cudaSuccess) return e;
+    k_vertex<GridSrc><<<sms * 8, 256, 0, st>>>(GridSrc{d_grid}, g, tabs, totals, xyz, cap_v);
+    return cudaGetLastError();
 }
 cudaError_t isomc_launch_emit_sdf(const Geo &g, const SdfProgram &prog, const uint32_t *signs, const uint32_t *segpre,
                                   const uint32_t *rowPV, const uint32_t *rowPT, const McTables *tabs,
                                   const unsigned long long *totals, const uint32_t *vofs, uint32_t *ticket, float *xyz,
                                   uint32_t *idx, uint64_t cap_v, uint64_t cap_t, int sms, cudaStream_t st) {
-    return launch_emit(SdfSrc{prog}, g, signs, segpre, rowPV, rowPT, tabs, totals, vofs, ticket, xyz, idx, cap_v, cap_t, sms, st);
+    cudaError_t e = launch_emit(g, signs, segpre, rowPV, rowPT, tabs, totals, vofs, ticket, xyz, idx, cap_v, cap_t, sms, st);
+    if (e != cudaSuccess) return e;
+    k_vertex<SdfSrc><<<sms * 8, 256, 0, st>>>(SdfSrc{prog}, g, tabs, totals, xyz, cap_v);
+    return cudaGetLastError();
 }
 
 cudaError_t isomc_launch_cube_indices(const Geo &g, const uint32_t *signs, const McTables *tabs, uint8_t *out, int sms,

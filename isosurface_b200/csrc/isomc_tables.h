@@ -18,6 +18,8 @@
  *                    those no earlier cell in (z,y,x) order contains
  *   owner[b][e]      for a cell with flags b, which earlier cell created edge e and under which
  *                    local edge number: dx | dy<<1 | dz<<2 | e'<<4
+ *   rank3[ci']       for interior cells (which create exactly e5, e6, e10): rank of e5 | e6<<2 | e10<<4
+ *                    among those three in order[ci']
  *   ends[e]          corner offsets of the edge's two ends in EDGE_CONNECTION direction:
  *                    (ux|uy<<1|uz<<2) | (vx|vy<<1|vz<<2)<<4
  */
@@ -39,6 +41,7 @@ struct McTables {
     uint8_t owner[8][12];
     uint8_t ends[12];
     uint8_t ref_of_nat[256]; /* natural cube index -> reference cube index (debug/parity) */
+    uint8_t rank3[256];
     uint8_t pad[4];
 };
 
@@ -115,6 +118,10 @@ static inline int isomc_build_tables(McTables *t) {
         t->order[cnat] = order;
         t->emask[cnat] = seen;
         t->ntri[cnat] = (uint8_t)(n / 3);
+        const uint16_t interior = (uint16_t)(1u << 5 | 1u << 6 | 1u << 10);
+        t->rank3[cnat] = (uint8_t)(__builtin_popcount(t->before[cnat][5] & interior) |
+                                   __builtin_popcount(t->before[cnat][6] & interior) << 2 |
+                                   __builtin_popcount(t->before[cnat][10] & interior) << 4);
     }
     return 0;
 }

@@ -40,7 +40,7 @@ def _product_tables(tmp_path):
     raw = subprocess.run([str(exe)], check=True, capture_output=True).stdout
     dt = np.dtype([("tri", "<u8", 256), ("order", "<u8", 256), ("before", "<u2", (256, 12)), ("emask", "<u2", 256),
                    ("ntri", "u1", 256), ("ownmask", "<u2", 8), ("owner", "u1", (8, 12)), ("ends", "u1", 12),
-                   ("ref_of_nat", "u1", 256), ("pad", "u1", 4)])
+                   ("ref_of_nat", "u1", 256), ("rank3", "u1", 256), ("pad", "u1", 4)])
     assert len(raw) == dt.itemsize, (len(raw), dt.itemsize)
     return np.frombuffer(raw, dtype=dt)[0]
 
@@ -66,6 +66,11 @@ def test_product_tables_agree_with_oracle(oracle, tmp_path):
         assert order == first
         for k, e in enumerate(first):
             assert t["before"][cnat][e] == sum(1 << f for f in first[:k])
+        own = [e for e in first if e in (5, 6, 10)]
+        r3 = int(t["rank3"][cnat])
+        for e, sh in ((5, 0), (6, 2), (10, 4)):
+            if e in own:
+                assert (r3 >> sh) & 3 == own.index(e)
     for e in range(12):
         u, v = co[ed[e][0]], co[ed[e][1]]
         assert t["ends"][e] == (int(u[0]) | int(u[1]) << 1 | int(u[2]) << 2) | (int(v[0]) | int(v[1]) << 1 | int(v[2]) << 2) << 4
