@@ -460,6 +460,12 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
     const uint32_t first_own_layer = g.ghost ? 1u : 0u;
     const uint32_t nby = (g.ncx + BY - 1) / BY, nbz = (g.ncl + BZ - 1) / BZ, nbx = (g.nsegx + BX - 1) / BX;
     const uint32_t n_brick_rows = nby * nbz;
+    /* P1 task of this thread (region segment): invariant over bricks */
+    const bool has_task = tid < NTASK;
+    const int t_sl = (int)(tid % BX), t_ry = (int)((tid / BX) % RY), t_rz = (int)(tid / (BX * RY));
+    const int t_rq = t_rz * RY + t_ry;
+    const uint32_t t_woff = (uint32_t)(t_rz * (BY + 2) + t_ry) * WS + 1 + (uint32_t)t_sl;
+    const uint32_t t_cell0 = (uint32_t)region_pos(t_rz, t_ry, 32 * t_sl + 1);
 
     for (;;) {
         __syncthreads();
@@ -493,19 +499,30 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
         __syncthreads();
         if (S.work == 0) continue;
 
-        /* stage the sign words (+1 halo row/layer on each side) and the segment prefixes of the brick row */
-        for (uint32_t rr = warp; rr < NROWS_STAGE; rr += EMIT_THREADS / 32) {
-            const int li = (int)(rr / (BY + 2)), ri = (int)(rr % (BY + 2));
-            const int l = lz0 - 1 + li, r = y0 - 1 + ri;
-            uint32_t *dst = s_words + (size_t)rr * WS;
-            const bool ok = l >= 0 && l < (int)g.nsl && r >= 0 && r < (int)g.N;
-            const uint32_t *srcw = signs + ((uint64_t)(ok ? l : 0) * g.N + (ok ? r : 0)) * g.nws - 1;
-            for (uint32_t w = lane; w < WS; w += 32) dst[w] = (ok && w >= 1 && w <= g.nws) ? __ldg(srcw + w) : 0u;
-            if (li < RZ && ri < RY) {
-                const bool okc = l >= 0 && l < (int)g.ncl && r >= 0 && r < (int)g.ncx;
-                const uint32_t *srcp = segpre + ((uint64_t)(okc ? l : 0) * g.ncx + (okc ? r : 0)) * g.nsegx;
-                uint32_t *dp = s_sp + (size_t)(li * RY + ri) * g.nws;
-                for (uint32_t w = lane; w < g.nsegx; w += 32) dp[w] = okc ? __ldg(srcp + w) : 0u;
+        /* stage the sign words (+1 halo row/layer on each side) and the segment prefixes of the brick row:
+         * flat element loops, (row, word) advanced incrementally */
+        {
+            uint32_t rr = tid / WS, w = tid - rr * WS;
+            const uint32_t drr = EMIT_THREADS / WS, dw = EMIT_THREADS - drr * WS;
+            for (uint32_t e = tid; rr < NROWS_STAGE; e += EMIT_THREADS) {
+                const int l = lz0 - 1 + (int)(rr / (BY + 2)), r = y0 - 1 + (int)(rr % (BY + 2));
+                uint32_t v = 0;
+                if (l >= 0 && l < (int)g.nsl && r >= 0 && r < (int)g.N && w >= 1 && w <= g.nws)
+                    v = __ldg(signs + ((uint64_t)l * g.N + r) * g.nws + (w - 1));
+                s_words[e] = v;
+                rr += drr; w += dw;
+                if (w >= WS) { w -= WS; ++rr; }
+            }
+            rr = tid / g.nws; w = tid - rr * g.nws;
+            const uint32_t drr2 = EMIT_THREADS / g.nws, dw2 = EMIT_THREADS - drr2 * g.nws;
+            for (uint32_t e = tid; rr < NROWS_REG; e += EMIT_THREADS) {
+                const int l = lz0 - 1 + (int)(rr / RY), r = y0 - 1 + (int)(rr % RY);
+                uint32_t v = 0;
+                if (l >= 0 && l < (int)g.ncl && r >= 0 && r < (int)g.ncx && w < g.nsegx)
+                    v = __ldg(segpre + ((uint64_t)l * g.ncx + r) * g.nsegx + w);
+                s_sp[e] = v;
+                rr += drr2; w += dw2;
+                if (w >= g.nws) { w -= g.nws; ++rr; }
             }
         }
 
@@ -521,8 +538,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                 __syncthreads();
 
                 /* ---------------- P1: one thread per region segment ---------------- */
-                for (int task = tid; task < NTASK; task += EMIT_THREADS) {
-                    const int sl = task % BX, ry = (task / BX) % RY, rz = task / (BX * RY);
+                for (int task = (int)tid; has_task && task < NTASK; task += NTASK) { /* at most one iteration */
+                    const int sl = t_sl, ry = t_ry, rz = t_rz;
                     const int l = lz0 - 1 + rz, r = y0 - 1 + ry, s = sx0 + sl;
                     if (l < 0 || l >= (int)g.ncl || r < 0 || r >= (int)g.ncx || s >= (int)g.nsegx) continue;
                     const bool own = rz >= 1 && ry >= 1 && (uint32_t)l >= first_own_layer;
@@ -530,7 +547,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                     const bool listed = own && q >= lo && q < hi;
                     if (!first && !listed) continue;
                     /* rows (l, r), (l, r+1), (l+1, r), (l+1, r+1): words s-1, s, s+1 */
-                    const uint32_t *wa = s_words + (size_t)(rz * (BY + 2) + ry) * WS + 1 + s;
+                    const uint32_t *wa = s_words + t_woff + sx0;
                     const uint32_t *wb = wa + WS, *wc = wa + (size_t)(BY + 2) * WS, *wd = wc + WS;
                     const uint32_t a0 = wa[0], a1 = wa[1], b0 = wb[0], b1 = wb[1];
                     const uint32_t c0 = wc[0], c1 = wc[1], d0 = wd[0], d1 = wd[1];
@@ -556,7 +573,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                         if (act) pl = owned_planes(a0, an, b0, bn, c0, cn, d0, dn, gz == 0, r == 0, s == 0 ? 1u : 0u, vm);
                     }
                     if ((act | hx) == 0) continue;
-                    const int rq = rz * RY + ry;
+                    const int rq = t_rq;
                     const uint32_t sp = s_sp[(size_t)rq * g.nws + s];
                     const uint32_t na = __popc(act);
                     const uint32_t cpos = atomicAdd(&S.cell_n, na + hx);
@@ -575,9 +592,11 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                     D.vbase = S.row_pv[rq] + (sp & 0xFFFFu);
                     D.tseg = tseg;
                     D.cpos_tch = cpos | tch << 16;
-                    D.info = (uint32_t)region_pos(rz, ry, 32 * sl + 1) | (r == 0 ? 1u : 0u) << 24 | (gz == 0 ? 1u : 0u) << 25 |
+                    D.info = t_cell0 | (r == 0 ? 1u : 0u) << 24 | (gz == 0 ? 1u : 0u) << 25 |
                              (listed ? 1u : 0u) << 26 | (s == 0 ? 1u : 0u) << 27 | prevbits << 28;
                     D.act = act;
+                    D.pad[0] = (uint32_t)(s * 32) | (uint32_t)r << 16; /* x | y << 16 of cell 0 */
+                    D.pad[1] = (uint32_t)l;
                     uint32_t k = cpos;
                     while (act) { /* expansion: one store per active cell */
                         const uint32_t i = __ffs(act) - 1;
@@ -591,14 +610,16 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                 const uint32_t n_cells = S.cell_n;
 
                 /* ---------------- P2: one thread per active cell of the region ---------------- */
-                for (uint32_t k = tid; k < n_cells; k += EMIT_THREADS) {
-                    const uint32_t cm = S.cellmap[k];
+                for (uint32_t base = warp * 32; base < n_cells; base += EMIT_THREADS) { /* warp-uniform trip count */
+                    const uint32_t k = base + lane;
+                    const bool valid = k < n_cells;
+                    const uint32_t cm = valid ? S.cellmap[k] : 0u;
                     const uint32_t task = cm & 127u, i = (cm >> 7) & 31u;
                     const SegDesc &D = S.seg[task];
                     const uint32_t info = D.info;
-                    bool listed = (info >> 26 & 1u) && !ovf;
-                    uint32_t ci, vid, bfl;
-                    int cp;
+                    bool listed = valid && (info >> 26 & 1u) && !ovf;
+                    uint32_t ci = 0, vid = 0, bfl = 0;
+                    int cp = 0;
                     if (cm >> 12) { /* x-halo cell: corners from sample 32s-1 (prev bits) and sample 32s (bit 0) */
                         const uint32_t pb = info >> 28;
                         ci = (pb & 1u) | (D.w[0] & 1u) << 1 | (pb >> 1 & 1u) << 2 | (D.w[2] & 1u) << 3 | (pb >> 2 & 1u) << 4 |
@@ -607,18 +628,15 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                         vid = D.vbase - __popc((uint32_t)S.emask[ci] & (uint32_t)S.ownmask[bfl]);
                         cp = (int)(info & 4095u) - 1;
                         listed = false; /* belongs to the brick on the left */
-                    } else {
+                    } else if (valid) {
                         ci = cube_index_from(D, i);
                         vid = D.vbase + planes_count(make_uint4(D.p0, D.p1, D.p2, D.p3), (1u << i) - 1u);
                         bfl = ((info >> 27 & 1u) && i == 0 ? 1u : 0u) | (info >> 24 & 1u) << 1 | (info >> 25 & 1u) << 2;
                         cp = (int)(info & 4095u) + (int)i;
                     }
                     const uint32_t em = S.emask[ci];
-                    /* cell coordinates for the vertex descriptors: x | y << 16, local layer | e << 16 */
-                    const int rx = cp % RX, ry = (cp / RX) % RY, rz = cp / (RX * RY);
-                    const uint32_t dxy = (uint32_t)(sx0 * 32 + rx - 1) | (uint32_t)(y0 + ry - 1) << 16;
-                    const uint32_t dlz = (uint32_t)(lz0 + rz - 1);
-                    if (bfl == 0) { /* interior: creates exactly its crossed e5, e6, e10, ranks from rank3 */
+                    const uint32_t dxy = D.pad[0] + i, dlz = D.pad[1]; /* creator cell for the vertex descriptors */
+                    if (valid && bfl == 0) { /* interior: creates exactly its crossed e5, e6, e10, ranks from rank3 */
                         const uint32_t r3 = S.rank3[ci];
                         if (em >> 6 & 1u) {
                             const uint32_t id = vid + (r3 >> 2 & 3u);
@@ -635,8 +653,9 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                             S.plane[2 * NREGION + cp] = id;
                             if (listed && id - ghostV < cap_v) { vdesc[3 * (uint64_t)(id - ghostV)] = dxy; vdesc[3 * (uint64_t)(id - ghostV) + 1] = dlz | 10u << 16; }
                         }
-                    } else { /* on a low boundary face: more edges, first-appearance order decides the ranks */
+                    } else if (valid) { /* on a low boundary face: more edges, first-appearance order decides the ranks */
                         const uint32_t owned = em & S.ownmask[bfl];
+                        const int rx = cp % RX, ry = (cp / RX) % RY, rz = cp / (RX * RY);
                         uint64_t ord = tabs->order[ci];
                         uint32_t id = vid;
                         for (uint32_t rem = em; rem; rem &= rem - 1, ord >>= 4) {
@@ -648,12 +667,25 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                             ++id;
                         }
                     }
+                    /* triangle-list positions: exclusive sum of the triangle counts of the earlier cells of the
+                     * same segment.  Cells of a segment are consecutive lanes: segmented warp scan ... */
+                    const uint32_t nt = listed ? S.ntri[ci] : 0u;
+                    const uint32_t key = valid ? task : 0xFFFFu;
+                    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, key, 1);
+                    bool flag = (lane == 0) || (up != key);
+                    uint32_t inc = nt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v_up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                        const uint32_t f_up = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)flag, d);
+                        if (lane >= (uint32_t)d && !flag) { inc += v_up; flag = f_up != 0; }
+                    }
                     if (listed) {
-                        /* triangle-list position: triangles of the earlier active cells of the segment */
-                        uint32_t tp = D.cpos_tch >> 16;
-                        for (uint32_t m = D.act & ((1u << i) - 1u); m; m &= m - 1) tp += S.ntri[cube_index_from(D, __ffs(m) - 1)];
+                        uint32_t tp = (D.cpos_tch >> 16) + inc - nt;
+                        /* ... plus the cells of this segment that fell into the previous warp batch (rare) */
+                        for (uint32_t j = D.cpos_tch & 0xFFFFu; j < base; ++j)
+                            tp += S.ntri[cube_index_from(D, ((uint32_t)S.cellmap[j] >> 7) & 31u)];
                         const uint32_t ent = (uint32_t)cp | ci << 12 | task << 23;
-                        const uint32_t nt = S.ntri[ci];
                         for (uint32_t t = 0; t < nt; ++t) S.trilist[tp + t] = ent | t << 20;
                     }
                 }
