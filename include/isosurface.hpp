@@ -1,0 +1,140 @@
+// isosurface.hpp -- C++ host-side mirror of the swiftcoder/isosurface crate API for the one path this
+// repo accelerates, layered over the C ABI in isomc.h (header-only; link libisomc_b200.so).
+//
+//   Rust (reference)                                          C++ (this header)
+//   ---------------------------------------------------------------------------------------------
+//   MarchingCubes::<Signed>::new(size)                        isosurface::MarchingCubes mc(size);
+//   mc.extract(&Sampler::new(&source), &mut extractor)        mc.extract(isosurface::Sampler(source), extractor);
+//   implicit::{Sphere,Torus,Cylinder,RectangularPrism}        isosurface::Sphere{r}, Torus{R,r}, Cylinder{r,h}, RectangularPrism{hx,hy,hz}
+//   implicit::{Union,Intersection,Difference}                 isosurface::Union(a,b), Intersection(a,b), Difference(a,b)
+//   examples/common/sources.rs DemoSource (p - 0.5)           isosurface::Translate(dx,dy,dz, child)
+//   extractor::IndexedVertices::new(&mut v, &mut i)           isosurface::IndexedVertices sink(v, i);
+//   trait Extractor { extract_vertex; extract_index }         struct Extractor (virtual), replayed in protocol order
+//
+// Reference files: src/marching_cubes.rs:38-82, src/sampler.rs:26-41, src/source.rs:21-28,
+// src/extractor.rs:17-93, src/implicit/*.rs.  Sources are *encoded* for the device (DeviceSource);
+// an arbitrary callable is not a device path and does not compile against this API (no CPU fallback).
+#ifndef ISOSURFACE_HPP
+#define ISOSURFACE_HPP
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "isomc.h"
+
+namespace isosurface {
+
+struct Error : std::runtime_error {
+    int32_t code;
+    Error(int32_t c, const std::string &m) : std::runtime_error("isomc error " + std::to_string(c) + ": " + m), code(c) {}
+};
+
+using SdfProgram = std::vector<isomc_sdf_node>;
+
+// ---- implicit sources (reference src/implicit/) ---------------------------------------------
+struct Sphere { float radius; void encode(SdfProgram &p) const { p.push_back({ISOMC_SDF_SPHERE, radius, 0, 0}); } };
+struct Torus { float radius, tube_radius; void encode(SdfProgram &p) const { p.push_back({ISOMC_SDF_TORUS, radius, tube_radius, 0}); } };
+struct Cylinder { float radius, half_length; void encode(SdfProgram &p) const { p.push_back({ISOMC_SDF_CYLINDER, radius, half_length, 0}); } };
+struct RectangularPrism { float hx, hy, hz; void encode(SdfProgram &p) const { p.push_back({ISOMC_SDF_PRISM, hx, hy, hz}); } };
+
+template <class A, class B, uint32_t OP>
+struct Binary {
+    A a; B b;
+    Binary(A a_, B b_) : a(a_), b(b_) {}
+    void encode(SdfProgram &p) const { a.encode(p); b.encode(p); p.push_back({OP, 0, 0, 0}); }
+};
+template <class A, class B> using UnionT = Binary<A, B, ISOMC_SDF_UNION>;                 // csg.rs:20-39   min(a, b)
+template <class A, class B> using IntersectionT = Binary<A, B, ISOMC_SDF_INTERSECTION>;   // csg.rs:54-72   max(a, b)
+template <class A, class B> using DifferenceT = Binary<A, B, ISOMC_SDF_DIFFERENCE>;       // csg.rs:82-100  max(b, -a)
+template <class A, class B> UnionT<A, B> Union(A a, B b) { return {a, b}; }
+template <class A, class B> IntersectionT<A, B> Intersection(A a, B b) { return {a, b}; }
+template <class A, class B> DifferenceT<A, B> Difference(A a, B b) { return {a, b}; }
+
+template <class S>
+struct TranslateT {  // q = p - (dx,dy,dz), examples/common/sources.rs:38-43
+    float dx, dy, dz; S child;
+    void encode(SdfProgram &p) const {
+        p.push_back({ISOMC_SDF_TRANSLATE_PUSH, dx, dy, dz});
+        child.encode(p);
+        p.push_back({ISOMC_SDF_TRANSLATE_POP, 0, 0, 0});
+    }
+};
+template <class S> TranslateT<S> Translate(float dx, float dy, float dz, S child) { return {dx, dy, dz, child}; }
+
+// Dense lattice source (new): N*N*(N+1) f32, x fastest; host or device memory.
+struct DenseGrid { const float *data; uint32_t size; bool on_device; };
+
+// sampler.rs:26-41
+template <class S> struct SamplerT { const S &source; };
+template <class S> SamplerT<S> Sampler(const S &s) { return {s}; }
+
+// ---- extractors (reference src/extractor.rs) -------------------------------------------------
+struct Extractor {
+    virtual ~Extractor() = default;
+    virtual void extract_vertex(float x, float y, float z) = 0;
+    virtual void extract_index(size_t index) = 0;
+};
+struct IndexedVertices : Extractor {  // extractor.rs:72-93
+    std::vector<float> &vertices; std::vector<uint32_t> &indices;
+    IndexedVertices(std::vector<float> &v, std::vector<uint32_t> &i) : vertices(v), indices(i) {}
+    void extract_vertex(float x, float y, float z) override { vertices.push_back(x); vertices.push_back(y); vertices.push_back(z); }
+    void extract_index(size_t index) override { indices.push_back((uint32_t)index); }
+};
+struct OnlyVertices : Extractor {  // extractor.rs:24-43
+    std::vector<float> &vertices;
+    explicit OnlyVertices(std::vector<float> &v) : vertices(v) {}
+    void extract_vertex(float x, float y, float z) override { vertices.push_back(x); vertices.push_back(y); vertices.push_back(z); }
+    void extract_index(size_t) override {}
+};
+
+// ---- MarchingCubes (reference src/marching_cubes.rs:38-82) ------------------------------------
+class MarchingCubes {
+  public:
+    explicit MarchingCubes(uint32_t size, int32_t device = 0) : size_(size) {
+        int32_t rc = isomc_create(size, device, &h_);
+        if (rc) throw Error(rc, isomc_last_error(nullptr));
+    }
+    ~MarchingCubes() { isomc_destroy(h_); }
+    MarchingCubes(const MarchingCubes &) = delete;
+    MarchingCubes &operator=(const MarchingCubes &) = delete;
+
+    template <class S> void extract(const SamplerT<S> &sampler, Extractor &extractor) { extract(sampler.source, extractor); }
+    template <class S> void extract(const S &source, Extractor &extractor) {
+        SdfProgram prog;
+        source.encode(prog);
+        check(isomc_extract_sdf(h_, prog.data(), (uint32_t)prog.size()));
+        deliver(extractor);
+    }
+    void extract(const DenseGrid &grid, Extractor &extractor) {
+        if (grid.size != size_) throw Error(ISOMC_ERR_BAD_ARG, "grid size does not match");
+        check(grid.on_device ? isomc_extract_grid_device(h_, grid.data) : isomc_extract_grid_host(h_, grid.data));
+        deliver(extractor);
+    }
+    isomc_t *handle() { return h_; }
+
+  private:
+    void check(int32_t rc) { if (rc) throw Error(rc, isomc_last_error(h_)); }
+    void deliver(Extractor &ex) {
+        uint64_t nv = 0, nt = 0;
+        check(isomc_counts(h_, &nv, &nt, nullptr));
+        if (auto *iv = dynamic_cast<IndexedVertices *>(&ex)) {  // bulk fast path: two memcpys
+            size_t v0 = iv->vertices.size(), i0 = iv->indices.size();
+            iv->vertices.resize(v0 + 3 * nv);
+            iv->indices.resize(i0 + 3 * nt);
+            check(isomc_copy_out(h_, iv->vertices.data() + v0, iv->indices.data() + i0));
+            return;
+        }
+        std::vector<float> xyz(3 * nv);
+        std::vector<uint32_t> idx(3 * nt);
+        check(isomc_copy_out(h_, xyz.data(), idx.data()));
+        for (uint64_t v = 0; v < nv; ++v) ex.extract_vertex(xyz[3 * v], xyz[3 * v + 1], xyz[3 * v + 2]);  // all vertices first ...
+        for (uint64_t i = 0; i < 3 * nt; ++i) ex.extract_index(idx[i]);                                 // ... then all indices
+    }
+    isomc_t *h_ = nullptr;
+    uint32_t size_;
+};
+
+}  // namespace isosurface
+#endif
