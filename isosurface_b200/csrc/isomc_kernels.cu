@@ -166,28 +166,36 @@ __global__ void __launch_bounds__(256) k_sign_vec4(const float4 *__restrict__ gr
 /* K2: per-segment counts, within-row prefixes, row totals                                      */
 /* ------------------------------------------------------------------------------------------ */
 
-/* One thread per 32-cell segment (all lanes busy whatever the row length); the within-row scan
- * runs over shared memory afterwards, one warp per row. */
-__global__ void __launch_bounds__(256) k_count(Geo g, const uint32_t *__restrict__ signs,
-                                               const McTables *__restrict__ tabs, uint32_t *__restrict__ segpre,
-                                               uint32_t *__restrict__ rowV, uint32_t *__restrict__ rowT,
-                                               uint32_t *__restrict__ rowA, unsigned long long *__restrict__ layerTot) {
+/* P1: one thread per 32-cell segment (bit-parallel masks, "vertices created" counts, expansion of
+ * the active-cell mask into a flat list); P2: one thread per active cell (cube index -> triangle
+ * count, added to its segment with a shared-memory atomic); P3: within-row scan, one warp per row. */
+constexpr int COUNT_THREADS = 256;
+constexpr int COUNT_LIST = COUNT_THREADS * 32;
+
+__global__ void __launch_bounds__(COUNT_THREADS) k_count(Geo g, const uint32_t *__restrict__ signs,
+                                                         const McTables *__restrict__ tabs, uint32_t *__restrict__ segpre,
+                                                         uint32_t *__restrict__ rowV, uint32_t *__restrict__ rowT,
+                                                         uint32_t *__restrict__ rowA, unsigned long long *__restrict__ layerTot) {
     __shared__ uint8_t s_ntri[256];
-    __shared__ uint32_t s_cnt[256]; /* nv | nt << 16 */
-    __shared__ uint32_t s_act[256];
+    __shared__ uint32_t s_w[8][COUNT_THREADS]; /* the 8 sign words of each segment */
+    __shared__ uint32_t s_nv[COUNT_THREADS], s_nt[COUNT_THREADS], s_na[COUNT_THREADS];
+    __shared__ uint16_t s_list[COUNT_LIST];    /* segment | cell << 8 */
+    __shared__ uint32_t s_n;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = tabs->ntri[i];
 
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nrows = g.ncl * g.ncx;
-    const uint32_t rows_per_cta = max(1u, 256u / g.nsegx); /* nsegx <= 256 (size <= 8192) */
+    const uint32_t rows_per_cta = max(1u, (uint32_t)COUNT_THREADS / g.nsegx); /* nsegx <= 256 (size <= 8192) */
     const uint32_t ngroups = (nrows + rows_per_cta - 1) / rows_per_cta;
     const uint64_t layer_stride = (uint64_t)g.N * g.nws;
-    const uint32_t rr = threadIdx.x / g.nsegx, s = threadIdx.x - rr * g.nsegx;
+    const uint32_t rr = tid / g.nsegx, s = tid - rr * g.nsegx;
 
     for (uint32_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         __syncthreads();
+        if (tid == 0) s_n = 0;
+        __syncthreads();
         const uint32_t row = grp * rows_per_cta + rr;
-        uint32_t nv = 0, nt = 0, na = 0;
+        uint32_t nv = 0, na = 0;
         if (rr < rows_per_cta && row < nrows) {
             const uint32_t lz = row / g.ncx, y = row - lz * g.ncx;
             const uint32_t *r00 = signs + ((uint64_t)lz * g.N + y) * g.nws + s;
@@ -201,31 +209,41 @@ __global__ void __launch_bounds__(256) k_count(Geo g, const uint32_t *__restrict
                 const uint32_t an = __funnelshift_r(a0, a1, 1), bn = __funnelshift_r(b0, b1, 1);
                 const uint32_t cn = __funnelshift_r(c0, c1, 1), dn = __funnelshift_r(d0, d1, 1);
                 const uint32_t vm = valid_mask(g.ncx - s * 32);
-                const uint4 pl = owned_planes(a0, an, b0, bn, c0, cn, d0, dn, (g.gz0 + lz) == 0, y == 0, s == 0 ? 1u : 0u, vm);
-                nv = planes_count(pl, 0xFFFFFFFFu);
                 uint32_t act = active_mask(a0, an, b0, bn, c0, cn, d0, dn, vm);
-                na = __popc(act);
-                while (act) {
-                    const uint32_t i = __ffs(act) - 1;
-                    act &= act - 1;
-                    const uint32_t ci = (__funnelshift_r(a0, a1, i) & 3u) | (__funnelshift_r(b0, b1, i) & 3u) << 2 |
-                                        (__funnelshift_r(c0, c1, i) & 3u) << 4 | (__funnelshift_r(d0, d1, i) & 3u) << 6;
-                    nt += s_ntri[ci];
+                if (act) {
+                    const uint4 pl = owned_planes(a0, an, b0, bn, c0, cn, d0, dn, (g.gz0 + lz) == 0, y == 0, s == 0 ? 1u : 0u, vm);
+                    nv = planes_count(pl, 0xFFFFFFFFu);
+                    na = __popc(act);
+                    s_w[0][tid] = a0; s_w[1][tid] = a1; s_w[2][tid] = b0; s_w[3][tid] = b1;
+                    s_w[4][tid] = c0; s_w[5][tid] = c1; s_w[6][tid] = d0; s_w[7][tid] = d1;
+                    uint32_t k = atomicAdd(&s_n, na);
+                    while (act) { /* expansion: one store per active cell */
+                        const uint32_t i = __ffs(act) - 1;
+                        act &= act - 1;
+                        s_list[k++] = (uint16_t)(tid | i << 8);
+                    }
                 }
             }
         }
-        s_cnt[threadIdx.x] = nv | nt << 16;
-        s_act[threadIdx.x] = na;
+        s_nv[tid] = nv; s_nt[tid] = 0; s_na[tid] = na;
+        __syncthreads();
+        const uint32_t n = s_n;
+        for (uint32_t k = tid; k < n; k += COUNT_THREADS) {
+            const uint32_t e = s_list[k], t = e & 255u, i = e >> 8;
+            const uint32_t ci = (__funnelshift_r(s_w[0][t], s_w[1][t], i) & 3u) | (__funnelshift_r(s_w[2][t], s_w[3][t], i) & 3u) << 2 |
+                                (__funnelshift_r(s_w[4][t], s_w[5][t], i) & 3u) << 4 | (__funnelshift_r(s_w[6][t], s_w[7][t], i) & 3u) << 6;
+            atomicAdd(&s_nt[t], (uint32_t)s_ntri[ci]);
+        }
         __syncthreads();
         /* within-row exclusive scan: warp w takes rows w, w+8, ... of the group */
-        for (uint32_t r = warp; r < rows_per_cta; r += 8) {
+        for (uint32_t r = warp; r < rows_per_cta; r += COUNT_THREADS / 32) {
             const uint32_t grow = grp * rows_per_cta + r;
             if (grow >= nrows) break;
             uint32_t carry = 0, acta = 0;
             for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 32) {
                 const uint32_t ss = s0 + lane;
-                const uint32_t pk = ss < g.nsegx ? s_cnt[r * g.nsegx + ss] : 0u;
-                acta += ss < g.nsegx ? s_act[r * g.nsegx + ss] : 0u;
+                const uint32_t pk = ss < g.nsegx ? (s_nv[r * g.nsegx + ss] | s_nt[r * g.nsegx + ss] << 16) : 0u;
+                acta += ss < g.nsegx ? s_na[r * g.nsegx + ss] : 0u;
                 uint32_t inc = pk; /* 16-bit fields cannot carry into each other: row totals < 65536 for size <= 8192 */
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -408,10 +426,14 @@ struct EmitShared {
     uint32_t cell_n, tri_n, overflow;
     uint32_t work;
     uint32_t ticket;
+    uint8_t brick_work[128];     /* per brick of the current brick row: any triangles? (nbx <= 128) */
 };
 
-size_t isomc_emit_smem_bytes(uint32_t nws) {
-    return sizeof(EmitShared) + (size_t)NROWS_STAGE * (nws + 2) * sizeof(uint32_t) + (size_t)NROWS_REG * nws * sizeof(uint32_t);
+constexpr int SW = BX + 2; /* staged sign words per row: s-1 .. s+BX */
+constexpr int SP = BX + 1; /* staged segment prefixes per row: s .. s+BX */
+
+size_t isomc_emit_smem_bytes(uint32_t) {
+    return sizeof(EmitShared) + (size_t)(NROWS_STAGE * SW + NROWS_REG * SP) * sizeof(uint32_t);
 }
 
 __device__ __forceinline__ int region_pos(int rz, int ry, int rx) { return (rz * RY + ry) * RX + rx; }
@@ -433,8 +455,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmitShared &S = *reinterpret_cast<EmitShared *>(smem_raw);
     uint32_t *s_words = reinterpret_cast<uint32_t *>(smem_raw + sizeof(EmitShared));
-    const uint32_t WS = g.nws + 2; /* [0] = pad for word -1, [1 + w] = word w, [nws + 1] = pad */
-    uint32_t *s_sp = s_words + (size_t)NROWS_STAGE * WS; /* segpre of the region rows: [row][nws] */
+    constexpr uint32_t WS = SW;                       /* per brick: words sx0-1 .. sx0+BX of each staged row */
+    uint32_t *s_sp = s_words + NROWS_STAGE * SW;      /* per brick: segpre sx0 .. sx0+BX of each region row */
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 256; i += EMIT_THREADS) {
@@ -464,7 +486,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
     const bool has_task = tid < NTASK;
     const int t_sl = (int)(tid % BX), t_ry = (int)((tid / BX) % RY), t_rz = (int)(tid / (BX * RY));
     const int t_rq = t_rz * RY + t_ry;
-    const uint32_t t_woff = (uint32_t)(t_rz * (BY + 2) + t_ry) * WS + 1 + (uint32_t)t_sl;
+    const uint32_t t_woff = (uint32_t)(t_rz * (BY + 2) + t_ry) * SW + 1 + (uint32_t)t_sl;
     const uint32_t t_cell0 = (uint32_t)region_pos(t_rz, t_ry, 32 * t_sl + 1);
 
     for (;;) {
@@ -499,35 +521,43 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
         __syncthreads();
         if (S.work == 0) continue;
 
-        /* stage the sign words (+1 halo row/layer on each side) and the segment prefixes of the brick row:
-         * flat element loops, (row, word) advanced incrementally */
-        {
-            uint32_t rr = tid / WS, w = tid - rr * WS;
-            const uint32_t drr = EMIT_THREADS / WS, dw = EMIT_THREADS - drr * WS;
-            for (uint32_t e = tid; rr < NROWS_STAGE; e += EMIT_THREADS) {
-                const int l = lz0 - 1 + (int)(rr / (BY + 2)), r = y0 - 1 + (int)(rr % (BY + 2));
-                uint32_t v = 0;
-                if (l >= 0 && l < (int)g.nsl && r >= 0 && r < (int)g.N && w >= 1 && w <= g.nws)
-                    v = __ldg(signs + ((uint64_t)l * g.N + r) * g.nws + (w - 1));
-                s_words[e] = v;
-                rr += drr; w += dw;
-                if (w >= WS) { w -= WS; ++rr; }
+        /* which bricks of the row have any triangle?  (differences of the within-row prefixes at brick borders) */
+        for (uint32_t bx = warp; bx < nbx; bx += EMIT_THREADS / 32) {
+            const int rz = (int)(lane / BY) + 1, ry = (int)(lane % BY) + 1, rq = rz * RY + ry;
+            const int l = lz0 - 1 + rz, r = y0 - 1 + ry;
+            bool has = false;
+            if (l >= (int)first_own_layer && l < (int)g.ncl && r < (int)g.ncx) {
+                const uint32_t *sp = segpre + ((uint64_t)l * g.ncx + r) * g.nsegx;
+                const uint32_t s0 = bx * BX, s1 = s0 + BX;
+                const uint32_t t0 = __ldg(sp + s0) >> 16;
+                const uint32_t t1 = s1 < g.nsegx ? __ldg(sp + s1) >> 16 : S.row_ptn[rq] - S.row_pt[rq];
+                has = t1 != t0;
             }
-            rr = tid / g.nws; w = tid - rr * g.nws;
-            const uint32_t drr2 = EMIT_THREADS / g.nws, dw2 = EMIT_THREADS - drr2 * g.nws;
-            for (uint32_t e = tid; rr < NROWS_REG; e += EMIT_THREADS) {
-                const int l = lz0 - 1 + (int)(rr / RY), r = y0 - 1 + (int)(rr % RY);
-                uint32_t v = 0;
-                if (l >= 0 && l < (int)g.ncl && r >= 0 && r < (int)g.ncx && w < g.nsegx)
-                    v = __ldg(segpre + ((uint64_t)l * g.ncx + r) * g.nsegx + w);
-                s_sp[e] = v;
-                rr += drr2; w += dw2;
-                if (w >= g.nws) { w -= g.nws; ++rr; }
-            }
+            const uint32_t any = __ballot_sync(0xFFFFFFFFu, has);
+            if (lane == 0) S.brick_work[bx] = any ? 1 : 0;
         }
+        __syncthreads();
 
         for (uint32_t bx = 0; bx < nbx; ++bx) {
+            if (!S.brick_work[bx]) continue;
             const int sx0 = (int)(bx * BX);
+            __syncthreads(); /* previous brick done with the staged data */
+            /* stage this brick's sign words (rows +-1 halo, words sx0-1 .. sx0+BX) and segment prefixes */
+            for (uint32_t e = tid; e < NROWS_STAGE * SW + NROWS_REG * SP; e += EMIT_THREADS) {
+                uint32_t v = 0;
+                if (e < NROWS_STAGE * SW) {
+                    const uint32_t rr = e / SW, w = e % SW;
+                    const int l = lz0 - 1 + (int)(rr / (BY + 2)), r = y0 - 1 + (int)(rr % (BY + 2)), wi = sx0 - 1 + (int)w;
+                    if (l >= 0 && l < (int)g.nsl && r >= 0 && r < (int)g.N && wi >= 0 && wi < (int)g.nws)
+                        v = __ldg(signs + ((uint64_t)l * g.N + r) * g.nws + wi);
+                } else {
+                    const uint32_t f = e - NROWS_STAGE * SW, rr = f / SP, w = f % SP;
+                    const int l = lz0 - 1 + (int)(rr / RY), r = y0 - 1 + (int)(rr % RY), si = sx0 + (int)w;
+                    if (l >= 0 && l < (int)g.ncl && r >= 0 && r < (int)g.ncx && si < (int)g.nsegx)
+                        v = __ldg(segpre + ((uint64_t)l * g.ncx + r) * g.nsegx + si);
+                }
+                s_words[e] = v;
+            }
             /* own rows q = layer * BY + row listed per pass: all 32, then 8 (one layer), then 1 if too dense */
             int lo = 0, level = 0;
             bool first = true;
@@ -547,7 +577,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                     const bool listed = own && q >= lo && q < hi;
                     if (!first && !listed) continue;
                     /* rows (l, r), (l, r+1), (l+1, r), (l+1, r+1): words s-1, s, s+1 */
-                    const uint32_t *wa = s_words + t_woff + sx0;
+                    const uint32_t *wa = s_words + t_woff;
                     const uint32_t *wb = wa + WS, *wc = wa + (size_t)(BY + 2) * WS, *wd = wc + WS;
                     const uint32_t a0 = wa[0], a1 = wa[1], b0 = wb[0], b1 = wb[1];
                     const uint32_t c0 = wc[0], c1 = wc[1], d0 = wd[0], d1 = wd[1];
@@ -574,14 +604,14 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                     }
                     if ((act | hx) == 0) continue;
                     const int rq = t_rq;
-                    const uint32_t sp = s_sp[(size_t)rq * g.nws + s];
+                    const uint32_t sp = s_sp[rq * SP + sl];
                     const uint32_t na = __popc(act);
                     const uint32_t cpos = atomicAdd(&S.cell_n, na + hx);
                     uint32_t tch = 0;
                     const uint32_t tseg = S.row_pt[rq] + (sp >> 16);
                     if (listed && act) {
                         /* triangles of this segment = next segment's prefix - ours (row total for the last one) */
-                        const uint32_t tnext = (s + 1 < (int)g.nsegx) ? S.row_pt[rq] + (s_sp[(size_t)rq * g.nws + s + 1] >> 16) : S.row_ptn[rq];
+                        const uint32_t tnext = (s + 1 < (int)g.nsegx) ? S.row_pt[rq] + (s_sp[rq * SP + sl + 1] >> 16) : S.row_ptn[rq];
                         const uint32_t nt_seg = tnext - tseg;
                         tch = atomicAdd(&S.tri_n, nt_seg);
                         if (tch + nt_seg > TRI_CAP) { S.overflow = 1; tch = 0; }
