@@ -384,17 +384,16 @@ __global__ void k_slab_bases(const unsigned long long *__restrict__ gathered, ui
  */
 
 constexpr int BX = 2;  /* brick: segments of 32 cells in x */
-constexpr int BY = 8;  /* rows */
+constexpr int BY = 4;  /* rows */
 constexpr int BZ = 4;  /* layers */
-constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_THREADS = 128;
 constexpr int RX = BX * 32 + 1, RY = BY + 1, RZ = BZ + 1; /* region extents in cells */
 constexpr int NREGION = RX * RY * RZ;
 constexpr int NTASK = RZ * RY * BX;                        /* region segments */
 constexpr int NROWS_OWN = BY * BZ;
 constexpr int NROWS_REG = RY * RZ;
-constexpr int NROWS_STAGE = (BY + 2) * (BZ + 2);
-constexpr int TRI_CAP = 2560;                              /* triangles per pass; one row (BX*32*5) always fits */
-static_assert(NTASK <= 128 && NREGION <= 4096, "list entry bit fields");
+constexpr int TRI_CAP = 1280;                              /* triangles per pass; one layer (BX*32*BY*5) always fits */
+static_assert(NTASK <= 128 && NTASK <= EMIT_THREADS && NREGION <= 4096 && NROWS_OWN <= 32 && NROWS_REG <= EMIT_THREADS, "list entry bit fields / one-task-per-thread mapping");
 
 struct __align__(16) SegDesc {
     uint32_t w[8];      /* a0 a1 b0 b1 c0 c1 d0 d1: inside bits of rows (y,z) (y+1,z) (y,z+1) (y+1,z+1), words s, s+1 */
@@ -414,7 +413,7 @@ struct EmitShared {
     uint32_t plane[3 * NREGION]; /* id (before vofs) of the x / y / z edge created by (virtual) cell */
     uint32_t trilist[TRI_CAP];   /* region pos (12) | ci' << 12 | t << 20 | task << 23 */
     uint32_t row_pv[NROWS_REG], row_pt[NROWS_REG], row_ptn[NROWS_REG];
-    uint16_t cellmap[NREGION];   /* task | i << 7 | x-halo << 12 */
+    uint32_t cellmap[NREGION];   /* task | i << 7 | x-halo << 12 | ci' << 13 | triangles of earlier cells of the segment << 21 */
     uint16_t emask[256];
     uint16_t ownmask[8];
     int16_t offs[12];            /* plane index of edge e seen from a cell at region pos cp: cp + offs[e] */
@@ -429,12 +428,7 @@ struct EmitShared {
     uint8_t brick_work[128];     /* per brick of the current brick row: any triangles? (nbx <= 128) */
 };
 
-constexpr int SW = BX + 2; /* staged sign words per row: s-1 .. s+BX */
-constexpr int SP = BX + 1; /* staged segment prefixes per row: s .. s+BX */
-
-size_t isomc_emit_smem_bytes(uint32_t) {
-    return sizeof(EmitShared) + (size_t)(NROWS_STAGE * SW + NROWS_REG * SP) * sizeof(uint32_t);
-}
+size_t isomc_emit_smem_bytes(uint32_t) { return sizeof(EmitShared); }
 
 __device__ __forceinline__ int region_pos(int rz, int ry, int rx) { return (rz * RY + ry) * RX + rx; }
 
@@ -454,9 +448,6 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                                                       unsigned long long cap_v, unsigned long long cap_t) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmitShared &S = *reinterpret_cast<EmitShared *>(smem_raw);
-    uint32_t *s_words = reinterpret_cast<uint32_t *>(smem_raw + sizeof(EmitShared));
-    constexpr uint32_t WS = SW;                       /* per brick: words sx0-1 .. sx0+BX of each staged row */
-    uint32_t *s_sp = s_words + NROWS_STAGE * SW;      /* per brick: segpre sx0 .. sx0+BX of each region row */
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 256; i += EMIT_THREADS) {
@@ -486,7 +477,6 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
     const bool has_task = tid < NTASK;
     const int t_sl = (int)(tid % BX), t_ry = (int)((tid / BX) % RY), t_rz = (int)(tid / (BX * RY));
     const int t_rq = t_rz * RY + t_ry;
-    const uint32_t t_woff = (uint32_t)(t_rz * (BY + 2) + t_ry) * SW + 1 + (uint32_t)t_sl;
     const uint32_t t_cell0 = (uint32_t)region_pos(t_rz, t_ry, 32 * t_sl + 1);
 
     for (;;) {
@@ -526,7 +516,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
             const int rz = (int)(lane / BY) + 1, ry = (int)(lane % BY) + 1, rq = rz * RY + ry;
             const int l = lz0 - 1 + rz, r = y0 - 1 + ry;
             bool has = false;
-            if (l >= (int)first_own_layer && l < (int)g.ncl && r < (int)g.ncx) {
+            if (lane < NROWS_OWN && l >= (int)first_own_layer && l < (int)g.ncl && r < (int)g.ncx) {
                 const uint32_t *sp = segpre + ((uint64_t)l * g.ncx + r) * g.nsegx;
                 const uint32_t s0 = bx * BX, s1 = s0 + BX;
                 const uint32_t t0 = __ldg(sp + s0) >> 16;
@@ -541,23 +531,6 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
         for (uint32_t bx = 0; bx < nbx; ++bx) {
             if (!S.brick_work[bx]) continue;
             const int sx0 = (int)(bx * BX);
-            __syncthreads(); /* previous brick done with the staged data */
-            /* stage this brick's sign words (rows +-1 halo, words sx0-1 .. sx0+BX) and segment prefixes */
-            for (uint32_t e = tid; e < NROWS_STAGE * SW + NROWS_REG * SP; e += EMIT_THREADS) {
-                uint32_t v = 0;
-                if (e < NROWS_STAGE * SW) {
-                    const uint32_t rr = e / SW, w = e % SW;
-                    const int l = lz0 - 1 + (int)(rr / (BY + 2)), r = y0 - 1 + (int)(rr % (BY + 2)), wi = sx0 - 1 + (int)w;
-                    if (l >= 0 && l < (int)g.nsl && r >= 0 && r < (int)g.N && wi >= 0 && wi < (int)g.nws)
-                        v = __ldg(signs + ((uint64_t)l * g.N + r) * g.nws + wi);
-                } else {
-                    const uint32_t f = e - NROWS_STAGE * SW, rr = f / SP, w = f % SP;
-                    const int l = lz0 - 1 + (int)(rr / RY), r = y0 - 1 + (int)(rr % RY), si = sx0 + (int)w;
-                    if (l >= 0 && l < (int)g.ncl && r >= 0 && r < (int)g.ncx && si < (int)g.nsegx)
-                        v = __ldg(segpre + ((uint64_t)l * g.ncx + r) * g.nsegx + si);
-                }
-                s_words[e] = v;
-            }
             /* own rows q = layer * BY + row listed per pass: all 32, then 8 (one layer), then 1 if too dense */
             int lo = 0, level = 0;
             bool first = true;
@@ -576,16 +549,18 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                     const int q = (rz - 1) * BY + (ry - 1);
                     const bool listed = own && q >= lo && q < hi;
                     if (!first && !listed) continue;
-                    /* rows (l, r), (l, r+1), (l+1, r), (l+1, r+1): words s-1, s, s+1 */
-                    const uint32_t *wa = s_words + t_woff;
-                    const uint32_t *wb = wa + WS, *wc = wa + (size_t)(BY + 2) * WS, *wd = wc + WS;
-                    const uint32_t a0 = wa[0], a1 = wa[1], b0 = wb[0], b1 = wb[1];
-                    const uint32_t c0 = wc[0], c1 = wc[1], d0 = wd[0], d1 = wd[1];
+                    /* rows (l, r), (l, r+1), (l+1, r), (l+1, r+1): words s, s+1 straight from L1/L2 */
+                    const uint32_t *wa = signs + ((uint64_t)l * g.N + (uint32_t)r) * g.nws + s;
+                    const uint32_t *wb = wa + g.nws, *wc = wa + (size_t)g.N * g.nws, *wd = wc + g.nws;
+                    const uint32_t a0 = __ldg(wa), a1 = __ldg(wa + 1), b0 = __ldg(wb), b1 = __ldg(wb + 1);
+                    const uint32_t c0 = __ldg(wc), c1 = __ldg(wc + 1), d0 = __ldg(wd), d1 = __ldg(wd + 1);
+                    const uint32_t *spp = segpre + ((uint64_t)l * g.ncx + (uint32_t)r) * g.nsegx + s;
+                    const uint32_t sp = __ldg(spp);
                     const uint32_t gz = g.gz0 + (uint32_t)l;
                     /* x-halo cell (last cell of the previous segment) of the brick's first segment */
                     uint32_t prevbits = 0, hx = 0;
                     if (sl == 0 && s > 0) {
-                        prevbits = (wa[-1] >> 31) | (wb[-1] >> 31) << 1 | (wc[-1] >> 31) << 2 | (wd[-1] >> 31) << 3;
+                        prevbits = (__ldg(wa - 1) >> 31) | (__ldg(wb - 1) >> 31) << 1 | (__ldg(wc - 1) >> 31) << 2 | (__ldg(wd - 1) >> 31) << 3;
                         const uint32_t nextbits = (a0 & 1u) | (b0 & 1u) << 1 | (c0 & 1u) << 2 | (d0 & 1u) << 3;
                         const uint32_t both = prevbits | nextbits << 4;
                         hx = (first && both != 0 && both != 255) ? 1u : 0u;
@@ -604,14 +579,13 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                     }
                     if ((act | hx) == 0) continue;
                     const int rq = t_rq;
-                    const uint32_t sp = s_sp[rq * SP + sl];
                     const uint32_t na = __popc(act);
                     const uint32_t cpos = atomicAdd(&S.cell_n, na + hx);
                     uint32_t tch = 0;
                     const uint32_t tseg = S.row_pt[rq] + (sp >> 16);
                     if (listed && act) {
                         /* triangles of this segment = next segment's prefix - ours (row total for the last one) */
-                        const uint32_t tnext = (s + 1 < (int)g.nsegx) ? S.row_pt[rq] + (s_sp[rq * SP + sl + 1] >> 16) : S.row_ptn[rq];
+                        const uint32_t tnext = (s + 1 < (int)g.nsegx) ? S.row_pt[rq] + (__ldg(spp + 1) >> 16) : S.row_ptn[rq];
                         const uint32_t nt_seg = tnext - tseg;
                         tch = atomicAdd(&S.tri_n, nt_seg);
                         if (tch + nt_seg > TRI_CAP) { S.overflow = 1; tch = 0; }
@@ -627,30 +601,31 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                     D.act = act;
                     D.pad[0] = (uint32_t)(s * 32) | (uint32_t)r << 16; /* x | y << 16 of cell 0 */
                     D.pad[1] = (uint32_t)l;
-                    uint32_t k = cpos;
-                    while (act) { /* expansion: one store per active cell */
+                    uint32_t k = cpos, tpre = 0;
+                    while (act) { /* expansion: one store per active cell (cube index + triangles of the earlier cells) */
                         const uint32_t i = __ffs(act) - 1;
                         act &= act - 1;
-                        S.cellmap[k++] = (uint16_t)((uint32_t)task | i << 7);
+                        const uint32_t ci = (__funnelshift_r(a0, a1, i) & 3u) | (__funnelshift_r(b0, b1, i) & 3u) << 2 |
+                                            (__funnelshift_r(c0, c1, i) & 3u) << 4 | (__funnelshift_r(d0, d1, i) & 3u) << 6;
+                        S.cellmap[k++] = (uint32_t)task | i << 7 | ci << 13 | tpre << 21;
+                        if (listed) tpre += S.ntri[ci];
                     }
-                    if (hx) S.cellmap[k] = (uint16_t)((uint32_t)task | 1u << 12);
+                    if (hx) S.cellmap[k] = (uint32_t)task | 1u << 12;
                 }
                 __syncthreads();
                 const bool ovf = S.overflow != 0;
                 const uint32_t n_cells = S.cell_n;
 
                 /* ---------------- P2: one thread per active cell of the region ---------------- */
-                for (uint32_t base = warp * 32; base < n_cells; base += EMIT_THREADS) { /* warp-uniform trip count */
-                    const uint32_t k = base + lane;
-                    const bool valid = k < n_cells;
-                    const uint32_t cm = valid ? S.cellmap[k] : 0u;
+                for (uint32_t k = tid; k < n_cells; k += EMIT_THREADS) {
+                    const uint32_t cm = S.cellmap[k];
                     const uint32_t task = cm & 127u, i = (cm >> 7) & 31u;
                     const SegDesc &D = S.seg[task];
                     const uint32_t info = D.info;
-                    bool listed = valid && (info >> 26 & 1u) && !ovf;
-                    uint32_t ci = 0, vid = 0, bfl = 0;
-                    int cp = 0;
-                    if (cm >> 12) { /* x-halo cell: corners from sample 32s-1 (prev bits) and sample 32s (bit 0) */
+                    bool listed = (info >> 26 & 1u) && !ovf;
+                    uint32_t ci, vid, bfl;
+                    int cp;
+                    if (cm >> 12 & 1u) { /* x-halo cell: corners from sample 32s-1 (prev bits) and sample 32s (bit 0) */
                         const uint32_t pb = info >> 28;
                         ci = (pb & 1u) | (D.w[0] & 1u) << 1 | (pb >> 1 & 1u) << 2 | (D.w[2] & 1u) << 3 | (pb >> 2 & 1u) << 4 |
                              (D.w[4] & 1u) << 5 | (pb >> 3 & 1u) << 6 | (D.w[6] & 1u) << 7;
@@ -658,15 +633,15 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                         vid = D.vbase - __popc((uint32_t)S.emask[ci] & (uint32_t)S.ownmask[bfl]);
                         cp = (int)(info & 4095u) - 1;
                         listed = false; /* belongs to the brick on the left */
-                    } else if (valid) {
-                        ci = cube_index_from(D, i);
+                    } else {
+                        ci = (cm >> 13) & 255u;
                         vid = D.vbase + planes_count(make_uint4(D.p0, D.p1, D.p2, D.p3), (1u << i) - 1u);
                         bfl = ((info >> 27 & 1u) && i == 0 ? 1u : 0u) | (info >> 24 & 1u) << 1 | (info >> 25 & 1u) << 2;
                         cp = (int)(info & 4095u) + (int)i;
                     }
                     const uint32_t em = S.emask[ci];
                     const uint32_t dxy = D.pad[0] + i, dlz = D.pad[1]; /* creator cell for the vertex descriptors */
-                    if (valid && bfl == 0) { /* interior: creates exactly its crossed e5, e6, e10, ranks from rank3 */
+                    if (bfl == 0) { /* interior: creates exactly its crossed e5, e6, e10, ranks from rank3 */
                         const uint32_t r3 = S.rank3[ci];
                         if (em >> 6 & 1u) {
                             const uint32_t id = vid + (r3 >> 2 & 3u);
@@ -683,7 +658,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                             S.plane[2 * NREGION + cp] = id;
                             if (listed && id - ghostV < cap_v) { vdesc[3 * (uint64_t)(id - ghostV)] = dxy; vdesc[3 * (uint64_t)(id - ghostV) + 1] = dlz | 10u << 16; }
                         }
-                    } else if (valid) { /* on a low boundary face: more edges, first-appearance order decides the ranks */
+                    } else { /* on a low boundary face: more edges, first-appearance order decides the ranks */
                         const uint32_t owned = em & S.ownmask[bfl];
                         const int rx = cp % RX, ry = (cp / RX) % RY, rz = cp / (RX * RY);
                         uint64_t ord = tabs->order[ci];
@@ -697,25 +672,10 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                             ++id;
                         }
                     }
-                    /* triangle-list positions: exclusive sum of the triangle counts of the earlier cells of the
-                     * same segment.  Cells of a segment are consecutive lanes: segmented warp scan ... */
-                    const uint32_t nt = listed ? S.ntri[ci] : 0u;
-                    const uint32_t key = valid ? task : 0xFFFFu;
-                    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, key, 1);
-                    bool flag = (lane == 0) || (up != key);
-                    uint32_t inc = nt;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t v_up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                        const uint32_t f_up = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)flag, d);
-                        if (lane >= (uint32_t)d && !flag) { inc += v_up; flag = f_up != 0; }
-                    }
-                    if (listed) {
-                        uint32_t tp = (D.cpos_tch >> 16) + inc - nt;
-                        /* ... plus the cells of this segment that fell into the previous warp batch (rare) */
-                        for (uint32_t j = D.cpos_tch & 0xFFFFu; j < base; ++j)
-                            tp += S.ntri[cube_index_from(D, ((uint32_t)S.cellmap[j] >> 7) & 31u)];
+                    if (listed) { /* triangle list: position = segment start + triangles of the earlier cells (from P1) */
+                        const uint32_t tp = (D.cpos_tch >> 16) + (cm >> 21);
                         const uint32_t ent = (uint32_t)cp | ci << 12 | task << 23;
+                        const uint32_t nt = S.ntri[ci];
                         for (uint32_t t = 0; t < nt; ++t) S.trilist[tp + t] = ent | t << 20;
                     }
                 }
