@@ -166,102 +166,104 @@ __global__ void __launch_bounds__(256) k_sign_vec4(const float4 *__restrict__ gr
 /* K2: per-segment counts, within-row prefixes, row totals                                      */
 /* ------------------------------------------------------------------------------------------ */
 
-/* P1: one thread per 32-cell segment (bit-parallel masks, "vertices created" counts, expansion of
- * the active-cell mask into a flat list); P2: one thread per active cell (cube index -> triangle
- * count, added to its segment with a shared-memory atomic); P3: within-row scan, one warp per row. */
-constexpr int COUNT_THREADS = 256;
-constexpr int COUNT_LIST = COUNT_THREADS * 32;
+/* Warp-autonomous (no block barriers in the loop): a lane owns one 32-cell segment; a warp covers
+ * 32/G consecutive cell rows of G = pow2 >= nsegx segments each (one row in 32-segment chunks when
+ * nsegx > 32) and scans them with width-G shuffles.  Vertex counts are pure bit-parallel work on the
+ * sign words; triangle counts walk the (few) active cells of the segment. */
+struct SegCounts { uint32_t nv, nt, na; };
 
-__global__ void __launch_bounds__(COUNT_THREADS) k_count(Geo g, const uint32_t *__restrict__ signs,
-                                                         const McTables *__restrict__ tabs, uint32_t *__restrict__ segpre,
-                                                         uint32_t *__restrict__ rowV, uint32_t *__restrict__ rowT,
-                                                         uint32_t *__restrict__ rowA, unsigned long long *__restrict__ layerTot) {
+__device__ __forceinline__ SegCounts count_segment(const Geo &g, const uint32_t *__restrict__ signs, const uint8_t *s_ntri,
+                                                   uint32_t row, uint32_t lz, uint32_t s) {
+    SegCounts c = {0u, 0u, 0u};
+    const uint32_t y = row - lz * g.ncx;
+    const uint32_t *r00 = signs + (uint64_t)(row + lz) * g.nws + s; /* sample row lz*N + y = row + lz */
+    const uint32_t *r01 = r00 + g.nws, *r10 = r00 + (uint64_t)g.N * g.nws, *r11 = r10 + g.nws;
+    const uint32_t a0 = __ldg(r00), a1 = __ldg(r00 + 1), b0 = __ldg(r01), b1 = __ldg(r01 + 1);
+    const uint32_t c0 = __ldg(r10), c1 = __ldg(r10 + 1), d0 = __ldg(r11), d1 = __ldg(r11 + 1);
+    const uint32_t all_or = a0 | b0 | c0 | d0 | ((a1 | b1 | c1 | d1) & 1u);
+    const uint32_t all_and = a0 & b0 & c0 & d0;
+    if ((all_or == 0u) || (all_and == 0xFFFFFFFFu && (a1 & b1 & c1 & d1 & 1u))) return c;
+    const uint32_t an = __funnelshift_r(a0, a1, 1), bn = __funnelshift_r(b0, b1, 1);
+    const uint32_t cn = __funnelshift_r(c0, c1, 1), dn = __funnelshift_r(d0, d1, 1);
+    const uint32_t vm = valid_mask(g.ncx - s * 32);
+    uint32_t act = active_mask(a0, an, b0, bn, c0, cn, d0, dn, vm);
+    if (act == 0) return c;
+    const uint4 pl = owned_planes(a0, an, b0, bn, c0, cn, d0, dn, (g.gz0 + lz) == 0, y == 0, s == 0 ? 1u : 0u, vm);
+    c.nv = planes_count(pl, 0xFFFFFFFFu);
+    c.na = __popc(act);
+    while (act) {
+        const uint32_t i = __ffs(act) - 1;
+        act &= act - 1;
+        const uint32_t ci = (__funnelshift_r(a0, a1, i) & 3u) | (__funnelshift_r(b0, b1, i) & 3u) << 2 |
+                            (__funnelshift_r(c0, c1, i) & 3u) << 4 | (__funnelshift_r(d0, d1, i) & 3u) << 6;
+        c.nt += s_ntri[ci];
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(256) k_count(Geo g, const uint32_t *__restrict__ signs, const McTables *__restrict__ tabs,
+                                               uint32_t *__restrict__ segpre, uint32_t *__restrict__ rowV,
+                                               uint32_t *__restrict__ rowT, uint32_t *__restrict__ rowA,
+                                               unsigned long long *__restrict__ layerTot, uint32_t gshift) {
     __shared__ uint8_t s_ntri[256];
-    __shared__ uint32_t s_w[8][COUNT_THREADS]; /* the 8 sign words of each segment */
-    __shared__ uint32_t s_nv[COUNT_THREADS], s_nt[COUNT_THREADS], s_na[COUNT_THREADS];
-    __shared__ uint16_t s_list[COUNT_LIST];    /* segment | cell << 8 */
-    __shared__ uint32_t s_n;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = tabs->ntri[i];
-
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
     const uint32_t nrows = g.ncl * g.ncx;
-    const uint32_t rows_per_cta = max(1u, (uint32_t)COUNT_THREADS / g.nsegx); /* nsegx <= 256 (size <= 8192) */
-    const uint32_t ngroups = (nrows + rows_per_cta - 1) / rows_per_cta;
-    const uint64_t layer_stride = (uint64_t)g.N * g.nws;
-    const uint32_t rr = tid / g.nsegx, s = tid - rr * g.nsegx;
-
-    for (uint32_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        __syncthreads();
-        if (tid == 0) s_n = 0;
-        __syncthreads();
-        const uint32_t row = grp * rows_per_cta + rr;
-        uint32_t nv = 0, na = 0;
-        if (rr < rows_per_cta && row < nrows) {
-            const uint32_t lz = row / g.ncx, y = row - lz * g.ncx;
-            const uint32_t *r00 = signs + ((uint64_t)lz * g.N + y) * g.nws + s;
-            const uint32_t *r01 = r00 + g.nws, *r10 = r00 + layer_stride, *r11 = r10 + g.nws;
-            const uint32_t a0 = __ldg(r00), a1 = __ldg(r00 + 1), b0 = __ldg(r01), b1 = __ldg(r01 + 1);
-            const uint32_t c0 = __ldg(r10), c1 = __ldg(r10 + 1), d0 = __ldg(r11), d1 = __ldg(r11 + 1);
-            const uint32_t all_or = a0 | b0 | c0 | d0 | ((a1 | b1 | c1 | d1) & 1u);
-            const uint32_t all_and = a0 & b0 & c0 & d0;
-            const bool uniform = (all_or == 0u) || (all_and == 0xFFFFFFFFu && (a1 & b1 & c1 & d1 & 1u));
-            if (!uniform) {
-                const uint32_t an = __funnelshift_r(a0, a1, 1), bn = __funnelshift_r(b0, b1, 1);
-                const uint32_t cn = __funnelshift_r(c0, c1, 1), dn = __funnelshift_r(d0, d1, 1);
-                const uint32_t vm = valid_mask(g.ncx - s * 32);
-                uint32_t act = active_mask(a0, an, b0, bn, c0, cn, d0, dn, vm);
-                if (act) {
-                    const uint4 pl = owned_planes(a0, an, b0, bn, c0, cn, d0, dn, (g.gz0 + lz) == 0, y == 0, s == 0 ? 1u : 0u, vm);
-                    nv = planes_count(pl, 0xFFFFFFFFu);
-                    na = __popc(act);
-                    s_w[0][tid] = a0; s_w[1][tid] = a1; s_w[2][tid] = b0; s_w[3][tid] = b1;
-                    s_w[4][tid] = c0; s_w[5][tid] = c1; s_w[6][tid] = d0; s_w[7][tid] = d1;
-                    uint32_t k = atomicAdd(&s_n, na);
-                    while (act) { /* expansion: one store per active cell */
-                        const uint32_t i = __ffs(act) - 1;
-                        act &= act - 1;
-                        s_list[k++] = (uint16_t)(tid | i << 8);
-                    }
+    if (g.nsegx <= 32) {
+        const uint32_t G = 1u << gshift, rpw = 32u >> gshift, sub = lane >> gshift, s = lane & (G - 1);
+        const uint32_t niter = (nrows + rpw - 1) / rpw;
+        for (uint32_t it = gwarp; it < niter; it += nwarps) {
+            const uint32_t row = it * rpw + sub;
+            const bool valid = row < nrows && s < g.nsegx;
+            const uint32_t lz = (row < nrows ? row : 0u) / g.ncx;
+            SegCounts c = {0u, 0u, 0u};
+            if (valid) c = count_segment(g, signs, s_ntri, row, lz, s);
+            const uint32_t pk = c.nv | c.nt << 16; /* 16-bit fields: row totals < 65536 for size <= 8192 */
+            uint32_t inc = pk, acta = c.na;
+            for (uint32_t d = 1; d < G; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d, G);
+                if (s >= d) inc += o;
+                acta += __shfl_xor_sync(0xFFFFFFFFu, acta, d, G);
+            }
+            if (valid) segpre[(uint64_t)row * g.nsegx + s] = inc - pk;
+            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, G - 1, G);
+            if (s == 0 && row < nrows) {
+                const uint32_t tv = tot & 0xFFFFu, tt = tot >> 16;
+                rowV[row] = tv; rowT[row] = tt; rowA[row] = acta;
+                if (tot) {
+                    atomicAdd(&layerTot[3 * lz + 0], (unsigned long long)tv);
+                    atomicAdd(&layerTot[3 * lz + 1], (unsigned long long)tt);
+                    atomicAdd(&layerTot[3 * lz + 2], (unsigned long long)acta);
                 }
             }
         }
-        s_nv[tid] = nv; s_nt[tid] = 0; s_na[tid] = na;
-        __syncthreads();
-        const uint32_t n = s_n;
-        for (uint32_t k = tid; k < n; k += COUNT_THREADS) {
-            const uint32_t e = s_list[k], t = e & 255u, i = e >> 8;
-            const uint32_t ci = (__funnelshift_r(s_w[0][t], s_w[1][t], i) & 3u) | (__funnelshift_r(s_w[2][t], s_w[3][t], i) & 3u) << 2 |
-                                (__funnelshift_r(s_w[4][t], s_w[5][t], i) & 3u) << 4 | (__funnelshift_r(s_w[6][t], s_w[7][t], i) & 3u) << 6;
-            atomicAdd(&s_nt[t], (uint32_t)s_ntri[ci]);
-        }
-        __syncthreads();
-        /* within-row exclusive scan: warp w takes rows w, w+8, ... of the group */
-        for (uint32_t r = warp; r < rows_per_cta; r += COUNT_THREADS / 32) {
-            const uint32_t grow = grp * rows_per_cta + r;
-            if (grow >= nrows) break;
+    } else {
+        for (uint32_t row = gwarp; row < nrows; row += nwarps) {
+            const uint32_t lz = row / g.ncx;
             uint32_t carry = 0, acta = 0;
             for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 32) {
-                const uint32_t ss = s0 + lane;
-                const uint32_t pk = ss < g.nsegx ? (s_nv[r * g.nsegx + ss] | s_nt[r * g.nsegx + ss] << 16) : 0u;
-                acta += ss < g.nsegx ? s_na[r * g.nsegx + ss] : 0u;
-                uint32_t inc = pk; /* 16-bit fields cannot carry into each other: row totals < 65536 for size <= 8192 */
+                const uint32_t s = s0 + lane;
+                SegCounts c = {0u, 0u, 0u};
+                if (s < g.nsegx) c = count_segment(g, signs, s_ntri, row, lz, s);
+                const uint32_t pk = c.nv | c.nt << 16;
+                uint32_t inc = pk;
+                acta += c.na;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
                     if (lane >= (uint32_t)d) inc += o;
                 }
-                if (ss < g.nsegx) segpre[(uint64_t)grow * g.nsegx + ss] = carry + inc - pk;
+                if (s < g.nsegx) segpre[(uint64_t)row * g.nsegx + s] = carry + inc - pk;
                 carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) acta += __shfl_xor_sync(0xFFFFFFFFu, acta, d);
             if (lane == 0) {
                 const uint32_t tv = carry & 0xFFFFu, tt = carry >> 16;
-                rowV[grow] = tv;
-                rowT[grow] = tt;
-                rowA[grow] = acta;
+                rowV[row] = tv; rowT[row] = tt; rowA[row] = acta;
                 if (carry) {
-                    const uint32_t lz = grow / g.ncx;
                     atomicAdd(&layerTot[3 * lz + 0], (unsigned long long)tv);
                     atomicAdd(&layerTot[3 * lz + 1], (unsigned long long)tt);
                     atomicAdd(&layerTot[3 * lz + 2], (unsigned long long)acta);
@@ -367,74 +369,75 @@ __global__ void k_slab_bases(const unsigned long long *__restrict__ gathered, ui
 /* K4: emission                                                                                 */
 /* ------------------------------------------------------------------------------------------ */
 /*
- * Work unit: a brick of BX*32 x BY x BZ cells plus a one-cell halo on the low side of every axis
- * (the cells that created the vertices the brick's triangles refer to): the "region".
- * Everything variable-length is flattened before it is processed, so that every phase runs with
- * (nearly) all lanes busy:
+ * Warp-autonomous: every warp pulls "strips" (BY rows x BZ layers x all x) from a ticket counter and
+ * walks the strip's bricks of 32 x BY x BZ cells that contain triangles.  No block barriers; each
+ * warp owns a private slice of shared memory.  A brick plus its one-cell halo on the low side of
+ * every axis (the cells that created the vertices the brick's triangles refer to) is the "region".
+ * Everything variable-length is flattened before it is processed:
  *
- *   P1   one thread per 32-cell segment of the region: crossed-edge masks and bit-sliced
- *        "vertices created" counts from the staged sign words; reserves list space; expands the
- *        active-cell mask into a flat cell list.
- *   P2   one thread per active cell of the region: cube index, id of the first vertex it creates,
- *        and the ids of all edges it creates -> shared-memory id planes (one per edge axis, indexed
- *        by the cell that would create the edge in an unbounded grid).  Own cells also write one
- *        12-byte *vertex descriptor* (creator cell + edge) into the slot of each vertex they create
- *        (k_vertex turns descriptors into positions) and enter their triangles in the triangle list.
- *   B    one thread per triangle: three id-plane lookups, one 12-byte store (u32 x 3).
+ *   P1   one lane per region row (= one 32-cell segment): crossed-edge masks and bit-sliced
+ *        "vertices created" counts from the sign words; list positions by warp scans; the active
+ *        mask is expanded into a flat cell list (cube index + triangles of the earlier cells).
+ *   P2   one lane per active cell of the region: id of the first vertex it creates and the ids of
+ *        all edges it creates -> shared-memory id planes (one per edge axis, indexed by the cell that
+ *        would create the edge in an unbounded grid; 16 bit, relative to the creating row).  Own
+ *        cells also write one 12-byte *vertex descriptor* (creator cell + edge) into the slot of each
+ *        vertex they create (k_vertex turns descriptors into positions) and list their triangles.
+ *   B    one lane per triangle: three id-plane lookups, one 12-byte store (u32 x 3).
  */
 
-constexpr int BX = 2;  /* brick: segments of 32 cells in x */
-constexpr int BY = 4;  /* rows */
-constexpr int BZ = 4;  /* layers */
-constexpr int EMIT_THREADS = 128;
-constexpr int RX = BX * 32 + 1, RY = BY + 1, RZ = BZ + 1; /* region extents in cells */
+constexpr int BY = 4;  /* brick rows */
+constexpr int BZ = 4;  /* brick layers */
+constexpr int EMIT_WARPS = 6;
+constexpr int EMIT_THREADS = EMIT_WARPS * 32;
+constexpr int RX = 33, RY = BY + 1, RZ = BZ + 1; /* region extents in cells */
 constexpr int NREGION = RX * RY * RZ;
-constexpr int NTASK = RZ * RY * BX;                        /* region segments */
+constexpr int NTASK = RZ * RY;                   /* region rows = P1 tasks, one per lane */
 constexpr int NROWS_OWN = BY * BZ;
-constexpr int NROWS_REG = RY * RZ;
-constexpr int TRI_CAP = 1280;                              /* triangles per pass; one layer (BX*32*BY*5) always fits */
-static_assert(NTASK <= 128 && NTASK <= EMIT_THREADS && NREGION <= 4096 && NROWS_OWN <= 32 && NROWS_REG <= EMIT_THREADS, "list entry bit fields / one-task-per-thread mapping");
+constexpr int TRI_CAP = 320;                     /* triangles per pass; two rows (2 * 32 * 5) always fit */
+static_assert(NTASK <= 32 && NREGION <= 1024 && NROWS_OWN <= 32, "one task per lane; list entry bit fields");
 
 struct __align__(16) SegDesc {
-    uint32_t w[8];      /* a0 a1 b0 b1 c0 c1 d0 d1: inside bits of rows (y,z) (y+1,z) (y,z+1) (y+1,z+1), words s, s+1 */
     uint32_t p0, p1, p2, p3; /* bit planes of "vertices created" per cell */
-    uint32_t vbase;     /* id (before vofs) of the first vertex created in this segment */
-    uint32_t tseg;      /* slot of the first triangle of this segment */
-    uint32_t cpos_tch;  /* cell-list start | triangle-list start << 16 */
-    uint32_t info;      /* region pos of cell 0 (12) | y==0 << 24 | z==0 << 25 | listed << 26 | (s == 0) << 27 |
-                           inside bits of sample 32s-1 in the 4 rows << 28 */
-    uint32_t act;       /* active cells */
-    uint32_t pad[3];
+    uint32_t vbase;          /* id (before vofs) of the first vertex created in this segment */
+    uint32_t tseg;           /* slot of the first triangle of this segment */
+    uint32_t cpos_tch;       /* cell-list start | triangle-list start << 16 */
+    uint32_t info;           /* y==0 | z==0 << 1 | listed << 2 | (s == 0) << 3 | inside bits of sample 32s-1 in the 4 rows << 4 |
+                                inside bit of sample 32s in the 4 rows << 8 */
+};
+
+struct WarpShared {
+    SegDesc seg[NTASK];
+    uint32_t cellmap[NREGION];    /* task | i << 5 | x-halo << 10 | ci' << 11 | triangles of earlier cells of the segment << 19 */
+    uint32_t trilist[TRI_CAP];    /* region pos (10) | ci' << 10 | t << 18 | task << 21 */
+    uint32_t rowbase[NTASK];      /* id (before vofs) at the start of each region row; virtual rows: clamped row */
+    uint16_t plane[3 * NREGION];  /* id of the x / y / z edge created by (virtual) cell, relative to rowbase of its row */
+    uint16_t pad[3];
 };
 
 struct EmitShared {
     uint64_t tri[256];
-    SegDesc seg[NTASK];
-    uint32_t plane[3 * NREGION]; /* id (before vofs) of the x / y / z edge created by (virtual) cell */
-    uint32_t trilist[TRI_CAP];   /* region pos (12) | ci' << 12 | t << 20 | task << 23 */
-    uint32_t row_pv[NROWS_REG], row_pt[NROWS_REG], row_ptn[NROWS_REG];
-    uint32_t cellmap[NREGION];   /* task | i << 7 | x-halo << 12 | ci' << 13 | triangles of earlier cells of the segment << 21 */
+    WarpShared w[EMIT_WARPS];
     uint16_t emask[256];
     uint16_t ownmask[8];
-    int16_t offs[12];            /* plane index of edge e seen from a cell at region pos cp: cp + offs[e] */
-    int16_t back[12];            /* region-pos offset from a cell to the (virtual) creator of its edge e */
-    uint8_t axis[12];
-    uint8_t bstep[12];           /* dx | dy << 1 | dz << 2 of that offset */
+    int16_t offs[12];   /* plane index of edge e seen from a cell at region pos cp: cp + offs[e] */
+    uint8_t rowback[12];/* region rows between a cell and the (virtual) creator of its edge e */
+    uint8_t bstep[12];  /* dx | dy << 1 | dz << 2 of that step */
     uint8_t ntri[256];
     uint8_t rank3[256];
-    uint32_t cell_n, tri_n, overflow;
-    uint32_t work;
-    uint32_t ticket;
-    uint8_t brick_work[128];     /* per brick of the current brick row: any triangles? (nbx <= 128) */
 };
 
 size_t isomc_emit_smem_bytes(uint32_t) { return sizeof(EmitShared); }
 
-__device__ __forceinline__ int region_pos(int rz, int ry, int rx) { return (rz * RY + ry) * RX + rx; }
-
-__device__ __forceinline__ uint32_t cube_index_from(const SegDesc &D, uint32_t i) {
-    return (__funnelshift_r(D.w[0], D.w[1], i) & 3u) | (__funnelshift_r(D.w[2], D.w[3], i) & 3u) << 2 |
-           (__funnelshift_r(D.w[4], D.w[5], i) & 3u) << 4 | (__funnelshift_r(D.w[6], D.w[7], i) & 3u) << 6;
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, uint32_t &total) {
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += o;
+    }
+    total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    return inc - v;
 }
 
 __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__restrict__ signs,
@@ -448,7 +451,6 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                                                       unsigned long long cap_v, unsigned long long cap_t) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmitShared &S = *reinterpret_cast<EmitShared *>(smem_raw);
-
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 256; i += EMIT_THREADS) {
         S.tri[i] = tabs->tri[i];
@@ -462,250 +464,235 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
         const uint32_t e2 = ow >> 4;             /* always one of 5 (y edge), 6 (x edge), 10 (z edge) */
         const int back = (int)((ow & 1) + (ow >> 1 & 1) * RX + (ow >> 2 & 1) * RX * RY);
         const int axis = e2 == 6 ? 0 : e2 == 5 ? 1 : 2;
-        S.back[tid] = (int16_t)back;
         S.bstep[tid] = (uint8_t)(ow & 7);
-        S.axis[tid] = (uint8_t)axis;
+        S.rowback[tid] = (uint8_t)((ow >> 1 & 1) + (ow >> 2 & 1) * RY);
         S.offs[tid] = (int16_t)(axis * NREGION - back);
     }
+    __syncthreads(); /* the only block barrier: tables ready */
+    WarpShared &W = S.w[warp];
 
     const uint32_t vofs = *vofs_ptr;
     const uint32_t ghostV = (uint32_t)totals[4], ghostT = (uint32_t)totals[5];
-    const uint32_t first_own_layer = g.ghost ? 1u : 0u;
-    const uint32_t nby = (g.ncx + BY - 1) / BY, nbz = (g.ncl + BZ - 1) / BZ, nbx = (g.nsegx + BX - 1) / BX;
-    const uint32_t n_brick_rows = nby * nbz;
-    /* P1 task of this thread (region segment): invariant over bricks */
-    const bool has_task = tid < NTASK;
-    const int t_sl = (int)(tid % BX), t_ry = (int)((tid / BX) % RY), t_rz = (int)(tid / (BX * RY));
-    const int t_rq = t_rz * RY + t_ry;
-    const uint32_t t_cell0 = (uint32_t)region_pos(t_rz, t_ry, 32 * t_sl + 1);
+    const int first_own_layer = g.ghost ? 1 : 0;
+    const uint32_t nby = (g.ncx + BY - 1) / BY, nbz = (g.ncl + BZ - 1) / BZ;
+    const uint32_t n_strips = nby * nbz;
+    /* P1 task of this lane: region row (t_rz, t_ry) */
+    const bool has_task = lane < NTASK;
+    const int t_rz = (int)(lane / RY), t_ry = (int)(lane % RY);
+    const bool t_own_pos = has_task && t_rz >= 1 && t_ry >= 1;
+    const int t_q = (t_rz - 1) * BY + (t_ry - 1); /* own-row ordinal (valid when t_own_pos) */
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) S.ticket = atomicAdd(ticket, 1u);
-        __syncthreads();
-        const uint32_t brow = S.ticket;
-        if (brow >= n_brick_rows) break;
-        const uint32_t bz = brow / nby, by = brow - bz * nby;
+        uint32_t strip = 0;
+        if (lane == 0) strip = atomicAdd(ticket, 1u);
+        strip = __shfl_sync(0xFFFFFFFFu, strip, 0);
+        if (strip >= n_strips) break;
+        const uint32_t bz = strip / nby, by = strip - bz * nby;
         const int lz0 = (int)(bz * BZ), y0 = (int)(by * BY);
 
-        /* row prefixes of the region rows; any triangles in the own rows? */
-        if (tid < NROWS_REG) {
-            const int rz = tid / RY, ry = tid % RY;
-            const int l = lz0 - 1 + rz, r = y0 - 1 + ry;
-            uint32_t pv = 0, pt = 0, ptn = 0;
-            if (l >= 0 && l < (int)g.ncl && r >= 0 && r < (int)g.ncx) {
-                const uint32_t row = (uint32_t)l * g.ncx + (uint32_t)r;
-                pv = rowPV[row]; pt = rowPT[row]; ptn = rowPT[row + 1];
-            }
-            S.row_pv[tid] = pv; S.row_pt[tid] = pt; S.row_ptn[tid] = ptn;
+        /* region rows of this lane: prefixes at the row start; any triangles in the own rows? */
+        const int l = lz0 - 1 + t_rz, r = y0 - 1 + t_ry;
+        const bool row_ok = has_task && l >= 0 && l < (int)g.ncl && r >= 0 && r < (int)g.ncx;
+        const uint32_t row = row_ok ? (uint32_t)l * g.ncx + (uint32_t)r : 0u;
+        uint32_t pv = 0, pt = 0, ptn = 0;
+        if (row_ok) { pv = rowPV[row]; pt = rowPT[row]; ptn = rowPT[row + 1]; }
+        const bool own_row = row_ok && t_own_pos && l >= first_own_layer;
+        if (__ballot_sync(0xFFFFFFFFu, own_row && ptn != pt) == 0) continue;
+        /* id base of every region row; rows below the grid (virtual creators of boundary edges) use the clamped row */
+        {
+            const int cz = max(t_rz, (lz0 == 0) ? 1 : 0), cy = max(t_ry, (y0 == 0) ? 1 : 0);
+            const uint32_t b = __shfl_sync(0xFFFFFFFFu, pv, has_task ? cz * RY + cy : 0);
+            if (has_task) W.rowbase[lane] = b;
         }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t t = 0;
-            for (int q = 0; q < NROWS_REG; ++q) {
-                const int rz = q / RY, ry = q % RY;
-                if (rz >= 1 && ry >= 1 && lz0 - 1 + rz >= (int)first_own_layer) t |= S.row_ptn[q] - S.row_pt[q];
+        const uint32_t *my_signs = signs + ((uint64_t)(row_ok ? l : 0) * g.N + (uint32_t)(row_ok ? r : 0)) * g.nws;
+        const uint32_t *my_sp = segpre + (uint64_t)row * g.nsegx;
+        const uint32_t gz = g.gz0 + (uint32_t)max(l, 0);
+
+        for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 32) {
+            /* bricks (= segments s0 + lane) with triangles: differences of the within-row prefixes of the own rows */
+            uint32_t has = 0;
+            {
+                const uint32_t sb = s0 + lane;
+                for (int q = 0; q < NROWS_OWN; ++q) {
+                    const int ql = lz0 + q / BY, qr = y0 + q % BY;
+                    if (ql < first_own_layer || ql >= (int)g.ncl || qr >= (int)g.ncx || sb >= g.nsegx) continue;
+                    const uint32_t qrow = (uint32_t)ql * g.ncx + (uint32_t)qr;
+                    const uint32_t t0 = __ldg(segpre + (uint64_t)qrow * g.nsegx + sb) >> 16;
+                    const uint32_t t1 = sb + 1 < g.nsegx ? __ldg(segpre + (uint64_t)qrow * g.nsegx + sb + 1) >> 16 : rowPT[qrow + 1] - rowPT[qrow];
+                    has |= t1 ^ t0;
+                }
             }
-            S.work = t;
-        }
-        __syncthreads();
-        if (S.work == 0) continue;
+            uint32_t todo = __ballot_sync(0xFFFFFFFFu, has != 0);
+            while (todo) {
+                const uint32_t s = s0 + (uint32_t)__ffs(todo) - 1;
+                todo &= todo - 1;
 
-        /* which bricks of the row have any triangle?  (differences of the within-row prefixes at brick borders) */
-        for (uint32_t bx = warp; bx < nbx; bx += EMIT_THREADS / 32) {
-            const int rz = (int)(lane / BY) + 1, ry = (int)(lane % BY) + 1, rq = rz * RY + ry;
-            const int l = lz0 - 1 + rz, r = y0 - 1 + ry;
-            bool has = false;
-            if (lane < NROWS_OWN && l >= (int)first_own_layer && l < (int)g.ncl && r < (int)g.ncx) {
-                const uint32_t *sp = segpre + ((uint64_t)l * g.ncx + r) * g.nsegx;
-                const uint32_t s0 = bx * BX, s1 = s0 + BX;
-                const uint32_t t0 = __ldg(sp + s0) >> 16;
-                const uint32_t t1 = s1 < g.nsegx ? __ldg(sp + s1) >> 16 : S.row_ptn[rq] - S.row_pt[rq];
-                has = t1 != t0;
-            }
-            const uint32_t any = __ballot_sync(0xFFFFFFFFu, has);
-            if (lane == 0) S.brick_work[bx] = any ? 1 : 0;
-        }
-        __syncthreads();
-
-        for (uint32_t bx = 0; bx < nbx; ++bx) {
-            if (!S.brick_work[bx]) continue;
-            const int sx0 = (int)(bx * BX);
-            /* own rows q = layer * BY + row listed per pass: all 32, then 8 (one layer), then 1 if too dense */
-            int lo = 0, level = 0;
-            bool first = true;
-            for (;;) {
-                const int hi = min(NROWS_OWN, lo + (level == 0 ? NROWS_OWN : level == 1 ? BY : 1));
-                __syncthreads(); /* staged data visible / previous pass done with the lists */
-                if (tid == 0) { S.cell_n = 0; S.tri_n = 0; S.overflow = 0; }
-                __syncthreads();
-
-                /* ---------------- P1: one thread per region segment ---------------- */
-                for (int task = (int)tid; has_task && task < NTASK; task += NTASK) { /* at most one iteration */
-                    const int sl = t_sl, ry = t_ry, rz = t_rz;
-                    const int l = lz0 - 1 + rz, r = y0 - 1 + ry, s = sx0 + sl;
-                    if (l < 0 || l >= (int)g.ncl || r < 0 || r >= (int)g.ncx || s >= (int)g.nsegx) continue;
-                    const bool own = rz >= 1 && ry >= 1 && (uint32_t)l >= first_own_layer;
-                    const int q = (rz - 1) * BY + (ry - 1);
-                    const bool listed = own && q >= lo && q < hi;
-                    if (!first && !listed) continue;
-                    /* rows (l, r), (l, r+1), (l+1, r), (l+1, r+1): words s, s+1 straight from L1/L2 */
-                    const uint32_t *wa = signs + ((uint64_t)l * g.N + (uint32_t)r) * g.nws + s;
-                    const uint32_t *wb = wa + g.nws, *wc = wa + (size_t)g.N * g.nws, *wd = wc + g.nws;
-                    const uint32_t a0 = __ldg(wa), a1 = __ldg(wa + 1), b0 = __ldg(wb), b1 = __ldg(wb + 1);
-                    const uint32_t c0 = __ldg(wc), c1 = __ldg(wc + 1), d0 = __ldg(wd), d1 = __ldg(wd + 1);
-                    const uint32_t *spp = segpre + ((uint64_t)l * g.ncx + (uint32_t)r) * g.nsegx + s;
-                    const uint32_t sp = __ldg(spp);
-                    const uint32_t gz = g.gz0 + (uint32_t)l;
-                    /* x-halo cell (last cell of the previous segment) of the brick's first segment */
-                    uint32_t prevbits = 0, hx = 0;
-                    if (sl == 0 && s > 0) {
-                        prevbits = (__ldg(wa - 1) >> 31) | (__ldg(wb - 1) >> 31) << 1 | (__ldg(wc - 1) >> 31) << 2 | (__ldg(wd - 1) >> 31) << 3;
-                        const uint32_t nextbits = (a0 & 1u) | (b0 & 1u) << 1 | (c0 & 1u) << 2 | (d0 & 1u) << 3;
-                        const uint32_t both = prevbits | nextbits << 4;
-                        hx = (first && both != 0 && both != 255) ? 1u : 0u;
-                    }
+                /* ---------------- P1 loads (independent of the pass) ---------------- */
+                uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0, sp = 0, spn = 0, prevbits = 0;
+                if (row_ok) {
+                    const uint32_t *wa = my_signs + s, *wb = wa + g.nws, *wc = wa + (size_t)g.N * g.nws, *wd = wc + g.nws;
+                    a0 = __ldg(wa); a1 = __ldg(wa + 1); b0 = __ldg(wb); b1 = __ldg(wb + 1);
+                    c0 = __ldg(wc); c1 = __ldg(wc + 1); d0 = __ldg(wd); d1 = __ldg(wd + 1);
+                    sp = __ldg(my_sp + s);
+                    spn = s + 1 < g.nsegx ? __ldg(my_sp + s + 1) >> 16 : ptn - pt;
+                    if (s > 0) prevbits = (__ldg(wa - 1) >> 31) | (__ldg(wb - 1) >> 31) << 1 | (__ldg(wc - 1) >> 31) << 2 | (__ldg(wd - 1) >> 31) << 3;
+                }
+                uint32_t act = 0;
+                uint4 pl = make_uint4(0, 0, 0, 0);
+                {
                     const uint32_t all_or = a0 | b0 | c0 | d0 | ((a1 | b1 | c1 | d1) & 1u);
                     const uint32_t all_and = a0 & b0 & c0 & d0;
                     const bool uniform = (all_or == 0u) || (all_and == 0xFFFFFFFFu && (a1 & b1 & c1 & d1 & 1u));
-                    uint32_t act = 0;
-                    uint4 pl = make_uint4(0, 0, 0, 0);
-                    if (!uniform) {
+                    if (row_ok && !uniform) {
                         const uint32_t an = __funnelshift_r(a0, a1, 1), bn = __funnelshift_r(b0, b1, 1);
                         const uint32_t cn = __funnelshift_r(c0, c1, 1), dn = __funnelshift_r(d0, d1, 1);
-                        const uint32_t vm = valid_mask(g.ncx - (uint32_t)s * 32);
+                        const uint32_t vm = valid_mask(g.ncx - s * 32);
                         act = active_mask(a0, an, b0, bn, c0, cn, d0, dn, vm);
                         if (act) pl = owned_planes(a0, an, b0, bn, c0, cn, d0, dn, gz == 0, r == 0, s == 0 ? 1u : 0u, vm);
                     }
-                    if ((act | hx) == 0) continue;
-                    const int rq = t_rq;
-                    const uint32_t na = __popc(act);
-                    const uint32_t cpos = atomicAdd(&S.cell_n, na + hx);
-                    uint32_t tch = 0;
-                    const uint32_t tseg = S.row_pt[rq] + (sp >> 16);
-                    if (listed && act) {
-                        /* triangles of this segment = next segment's prefix - ours (row total for the last one) */
-                        const uint32_t tnext = (s + 1 < (int)g.nsegx) ? S.row_pt[rq] + (__ldg(spp + 1) >> 16) : S.row_ptn[rq];
-                        const uint32_t nt_seg = tnext - tseg;
-                        tch = atomicAdd(&S.tri_n, nt_seg);
-                        if (tch + nt_seg > TRI_CAP) { S.overflow = 1; tch = 0; }
-                    }
-                    SegDesc &D = S.seg[task];
-                    D.w[0] = a0; D.w[1] = a1; D.w[2] = b0; D.w[3] = b1; D.w[4] = c0; D.w[5] = c1; D.w[6] = d0; D.w[7] = d1;
-                    D.p0 = pl.x; D.p1 = pl.y; D.p2 = pl.z; D.p3 = pl.w;
-                    D.vbase = S.row_pv[rq] + (sp & 0xFFFFu);
-                    D.tseg = tseg;
-                    D.cpos_tch = cpos | tch << 16;
-                    D.info = t_cell0 | (r == 0 ? 1u : 0u) << 24 | (gz == 0 ? 1u : 0u) << 25 |
-                             (listed ? 1u : 0u) << 26 | (s == 0 ? 1u : 0u) << 27 | prevbits << 28;
-                    D.act = act;
-                    D.pad[0] = (uint32_t)(s * 32) | (uint32_t)r << 16; /* x | y << 16 of cell 0 */
-                    D.pad[1] = (uint32_t)l;
-                    uint32_t k = cpos, tpre = 0;
-                    while (act) { /* expansion: one store per active cell (cube index + triangles of the earlier cells) */
-                        const uint32_t i = __ffs(act) - 1;
-                        act &= act - 1;
-                        const uint32_t ci = (__funnelshift_r(a0, a1, i) & 3u) | (__funnelshift_r(b0, b1, i) & 3u) << 2 |
-                                            (__funnelshift_r(c0, c1, i) & 3u) << 4 | (__funnelshift_r(d0, d1, i) & 3u) << 6;
-                        S.cellmap[k++] = (uint32_t)task | i << 7 | ci << 13 | tpre << 21;
-                        if (listed) tpre += S.ntri[ci];
-                    }
-                    if (hx) S.cellmap[k] = (uint32_t)task | 1u << 12;
                 }
-                __syncthreads();
-                const bool ovf = S.overflow != 0;
-                const uint32_t n_cells = S.cell_n;
+                const uint32_t nextbits = (a0 & 1u) | (b0 & 1u) << 1 | (c0 & 1u) << 2 | (d0 & 1u) << 3;
+                const uint32_t both = prevbits | nextbits << 4;
+                const uint32_t hx = (row_ok && s > 0 && both != 0 && both != 255) ? 1u : 0u; /* x-halo cell active */
+                const uint32_t nt_seg = spn - (sp >> 16);
 
-                /* ---------------- P2: one thread per active cell of the region ---------------- */
-                for (uint32_t k = tid; k < n_cells; k += EMIT_THREADS) {
-                    const uint32_t cm = S.cellmap[k];
-                    const uint32_t task = cm & 127u, i = (cm >> 7) & 31u;
-                    const SegDesc &D = S.seg[task];
-                    const uint32_t info = D.info;
-                    bool listed = (info >> 26 & 1u) && !ovf;
-                    uint32_t ci, vid, bfl;
-                    int cp;
-                    if (cm >> 12 & 1u) { /* x-halo cell: corners from sample 32s-1 (prev bits) and sample 32s (bit 0) */
-                        const uint32_t pb = info >> 28;
-                        ci = (pb & 1u) | (D.w[0] & 1u) << 1 | (pb >> 1 & 1u) << 2 | (D.w[2] & 1u) << 3 | (pb >> 2 & 1u) << 4 |
-                             (D.w[4] & 1u) << 5 | (pb >> 3 & 1u) << 6 | (D.w[6] & 1u) << 7;
-                        bfl = (info >> 24 & 1u) << 1 | (info >> 25 & 1u) << 2;
-                        vid = D.vbase - __popc((uint32_t)S.emask[ci] & (uint32_t)S.ownmask[bfl]);
-                        cp = (int)(info & 4095u) - 1;
-                        listed = false; /* belongs to the brick on the left */
+                /* own rows listed per pass: all 16, then 4 (one layer), then 2 rows if too dense */
+                int lo = 0, level = 0;
+                bool first = true;
+                for (;;) {
+                    const int hi = min(NROWS_OWN, lo + (level == 0 ? NROWS_OWN : level == 1 ? BY : 2));
+                    const bool listed = own_row && t_q >= lo && t_q < hi && act != 0;
+                    const bool part = first ? ((act | hx) != 0) : listed; /* takes part in this pass */
+                    uint32_t n_cells, n_tri;
+                    const uint32_t cpos = warp_excl_scan(part ? (uint32_t)__popc(act) + (first ? hx : 0u) : 0u, lane, n_cells);
+                    const uint32_t tch = warp_excl_scan(listed ? nt_seg : 0u, lane, n_tri);
+                    const bool ovf = n_tri > TRI_CAP;
+                    __syncwarp();
+                    if (part) {
+                        SegDesc &D = W.seg[lane];
+                        D.p0 = pl.x; D.p1 = pl.y; D.p2 = pl.z; D.p3 = pl.w;
+                        D.vbase = pv + (sp & 0xFFFFu);
+                        D.tseg = pt + (sp >> 16);
+                        D.cpos_tch = cpos | tch << 16;
+                        D.info = (r == 0 ? 1u : 0u) | (gz == 0 ? 2u : 0u) | ((listed && !ovf) ? 4u : 0u) | (s == 0 ? 8u : 0u) | both << 4;
+                        uint32_t k = cpos, tpre = 0, m = act;
+                        while (m) { /* expansion: one store per active cell (cube index + triangles of the earlier cells) */
+                            const uint32_t i = __ffs(m) - 1;
+                            m &= m - 1;
+                            const uint32_t ci = (__funnelshift_r(a0, a1, i) & 3u) | (__funnelshift_r(b0, b1, i) & 3u) << 2 |
+                                                (__funnelshift_r(c0, c1, i) & 3u) << 4 | (__funnelshift_r(d0, d1, i) & 3u) << 6;
+                            W.cellmap[k++] = lane | i << 5 | ci << 11 | tpre << 19;
+                            if (listed) tpre += S.ntri[ci];
+                        }
+                        if (first && hx) W.cellmap[k] = lane | 1u << 10;
+                    }
+                    __syncwarp();
+
+                    /* ---------------- P2: one lane per active cell of the region ---------------- */
+                    for (uint32_t base = 0; base < n_cells; base += 32) {
+                        const uint32_t k = base + lane;
+                        if (k < n_cells) {
+                            const uint32_t cm = W.cellmap[k];
+                            const uint32_t task = cm & 31u, i = (cm >> 5) & 31u;
+                            const SegDesc &D = W.seg[task];
+                            const uint32_t info = D.info;
+                            bool lst = (info >> 2 & 1u) != 0;
+                            uint32_t ci, vid, bfl;
+                            int cp;
+                            const int rq = (int)task;
+                            if (cm >> 10 & 1u) { /* x-halo cell: corners from samples 32s-1 and 32s */
+                                const uint32_t bb = info >> 4;
+                                ci = (bb & 1u) | (bb >> 4 & 1u) << 1 | (bb >> 1 & 1u) << 2 | (bb >> 5 & 1u) << 3 | (bb >> 2 & 1u) << 4 |
+                                     (bb >> 6 & 1u) << 5 | (bb >> 3 & 1u) << 6 | (bb >> 7 & 1u) << 7;
+                                bfl = (info & 1u) << 1 | (info >> 1 & 1u) << 2;
+                                vid = D.vbase - __popc((uint32_t)S.emask[ci] & (uint32_t)S.ownmask[bfl]);
+                                cp = rq * RX;
+                                lst = false; /* belongs to the brick on the left */
+                            } else {
+                                ci = (cm >> 11) & 255u;
+                                vid = D.vbase + planes_count(make_uint4(D.p0, D.p1, D.p2, D.p3), (1u << i) - 1u);
+                                bfl = ((info >> 3 & 1u) && i == 0 ? 1u : 0u) | (info & 1u) << 1 | (info >> 1 & 1u) << 2;
+                                cp = rq * RX + 1 + (int)i;
+                            }
+                            const uint32_t em = S.emask[ci];
+                            const int rz = rq / RY, ry = rq - rz * RY;
+                            const uint32_t rel = vid - W.rowbase[rq]; /* < 65536: row totals are 16 bit */
+                            /* creator cell for the vertex descriptors: x | y << 16, local layer | e << 16 */
+                            const uint32_t dxy = (s * 32 + i) | (uint32_t)(y0 + ry - 1) << 16, dlz = (uint32_t)(lz0 + rz - 1);
+                            if (bfl == 0) { /* interior: creates exactly its crossed e5, e6, e10, ranks from rank3 */
+                                const uint32_t r3 = S.rank3[ci];
+                                if (em >> 6 & 1u) {
+                                    const uint32_t rk = r3 >> 2 & 3u, slot = vid + rk - ghostV;
+                                    W.plane[cp] = (uint16_t)(rel + rk);
+                                    if (lst && slot < cap_v) { vdesc[3 * (uint64_t)slot] = dxy; vdesc[3 * (uint64_t)slot + 1] = dlz | 6u << 16; }
+                                }
+                                if (em >> 5 & 1u) {
+                                    const uint32_t rk = r3 & 3u, slot = vid + rk - ghostV;
+                                    W.plane[NREGION + cp] = (uint16_t)(rel + rk);
+                                    if (lst && slot < cap_v) { vdesc[3 * (uint64_t)slot] = dxy; vdesc[3 * (uint64_t)slot + 1] = dlz | 5u << 16; }
+                                }
+                                if (em >> 10 & 1u) {
+                                    const uint32_t rk = r3 >> 4 & 3u, slot = vid + rk - ghostV;
+                                    W.plane[2 * NREGION + cp] = (uint16_t)(rel + rk);
+                                    if (lst && slot < cap_v) { vdesc[3 * (uint64_t)slot] = dxy; vdesc[3 * (uint64_t)slot + 1] = dlz | 10u << 16; }
+                                }
+                            } else { /* on a low boundary face: more edges, first-appearance order decides the ranks */
+                                const uint32_t owned = em & S.ownmask[bfl];
+                                const int rx = cp - rq * RX;
+                                uint64_t ord = tabs->order[ci];
+                                uint32_t rk = 0;
+                                for (uint32_t rem = em; rem; rem &= rem - 1, ord >>= 4) {
+                                    const uint32_t e = (uint32_t)ord & 15u;
+                                    if (!(owned >> e & 1u)) continue;
+                                    const uint32_t st = S.bstep[e], slot = vid + rk - ghostV;
+                                    /* the (virtual) creator's row has the same id base (clamped rows) */
+                                    if ((int)(st & 1u) <= rx && (int)(st >> 1 & 1u) <= ry && (int)(st >> 2 & 1u) <= rz)
+                                        W.plane[cp + S.offs[e]] = (uint16_t)(vid + rk - W.rowbase[rq - S.rowback[e]]);
+                                    if (lst && slot < cap_v) { vdesc[3 * (uint64_t)slot] = dxy; vdesc[3 * (uint64_t)slot + 1] = dlz | e << 16; }
+                                    ++rk;
+                                }
+                            }
+                            if (lst) { /* triangle list: position = segment start + triangles of the earlier cells (from P1) */
+                                const uint32_t tp = (D.cpos_tch >> 16) + (cm >> 19);
+                                const uint32_t ent = (uint32_t)cp | ci << 10 | task << 21;
+                                const uint32_t nt = S.ntri[ci];
+                                for (uint32_t t = 0; t < nt; ++t) W.trilist[tp + t] = ent | t << 18;
+                            }
+                        }
+                    }
+                    __syncwarp();
+
+                    if (!ovf) {
+                        /* ---------------- B: one lane per triangle ---------------- */
+                        for (uint32_t base = 0; base < n_tri; base += 32) {
+                            const uint32_t j = base + lane;
+                            if (j < n_tri) {
+                                const uint32_t ent = W.trilist[j];
+                                const int cp = (int)(ent & 1023u);
+                                const uint32_t ci = (ent >> 10) & 255u, t = (ent >> 18) & 7u, task = ent >> 21;
+                                const uint32_t edges = (uint32_t)(S.tri[ci] >> (12 * t));
+                                const uint32_t e0 = edges & 15u, e1 = (edges >> 4) & 15u, e2 = (edges >> 8) & 15u;
+                                const uint32_t i0 = vofs + W.rowbase[task - S.rowback[e0]] + W.plane[cp + S.offs[e0]];
+                                const uint32_t i1 = vofs + W.rowbase[task - S.rowback[e1]] + W.plane[cp + S.offs[e1]];
+                                const uint32_t i2 = vofs + W.rowbase[task - S.rowback[e2]] + W.plane[cp + S.offs[e2]];
+                                const SegDesc &D = W.seg[task];
+                                const uint32_t tslot = D.tseg + (j - (D.cpos_tch >> 16)) - ghostT;
+                                if (tslot < cap_t) {
+                                    uint32_t *o = idx + (uint64_t)tslot * 3;
+                                    o[0] = i0; o[1] = i1; o[2] = i2;
+                                }
+                            }
+                        }
+                        lo = hi;
+                        if (lo >= NROWS_OWN) break;
                     } else {
-                        ci = (cm >> 13) & 255u;
-                        vid = D.vbase + planes_count(make_uint4(D.p0, D.p1, D.p2, D.p3), (1u << i) - 1u);
-                        bfl = ((info >> 27 & 1u) && i == 0 ? 1u : 0u) | (info >> 24 & 1u) << 1 | (info >> 25 & 1u) << 2;
-                        cp = (int)(info & 4095u) + (int)i;
+                        if (level == 2) break; /* cannot happen (two rows always fit); never spin */
+                        ++level;               /* too dense: list fewer rows per pass (the id planes are filled) */
                     }
-                    const uint32_t em = S.emask[ci];
-                    const uint32_t dxy = D.pad[0] + i, dlz = D.pad[1]; /* creator cell for the vertex descriptors */
-                    if (bfl == 0) { /* interior: creates exactly its crossed e5, e6, e10, ranks from rank3 */
-                        const uint32_t r3 = S.rank3[ci];
-                        if (em >> 6 & 1u) {
-                            const uint32_t id = vid + (r3 >> 2 & 3u);
-                            S.plane[cp] = id;
-                            if (listed && id - ghostV < cap_v) { vdesc[3 * (uint64_t)(id - ghostV)] = dxy; vdesc[3 * (uint64_t)(id - ghostV) + 1] = dlz | 6u << 16; }
-                        }
-                        if (em >> 5 & 1u) {
-                            const uint32_t id = vid + (r3 & 3u);
-                            S.plane[NREGION + cp] = id;
-                            if (listed && id - ghostV < cap_v) { vdesc[3 * (uint64_t)(id - ghostV)] = dxy; vdesc[3 * (uint64_t)(id - ghostV) + 1] = dlz | 5u << 16; }
-                        }
-                        if (em >> 10 & 1u) {
-                            const uint32_t id = vid + (r3 >> 4 & 3u);
-                            S.plane[2 * NREGION + cp] = id;
-                            if (listed && id - ghostV < cap_v) { vdesc[3 * (uint64_t)(id - ghostV)] = dxy; vdesc[3 * (uint64_t)(id - ghostV) + 1] = dlz | 10u << 16; }
-                        }
-                    } else { /* on a low boundary face: more edges, first-appearance order decides the ranks */
-                        const uint32_t owned = em & S.ownmask[bfl];
-                        const int rx = cp % RX, ry = (cp / RX) % RY, rz = cp / (RX * RY);
-                        uint64_t ord = tabs->order[ci];
-                        uint32_t id = vid;
-                        for (uint32_t rem = em; rem; rem &= rem - 1, ord >>= 4) {
-                            const uint32_t e = (uint32_t)ord & 15u;
-                            if (!(owned >> e & 1u)) continue;
-                            const uint32_t st = S.bstep[e];
-                            if ((int)(st & 1u) <= rx && (int)(st >> 1 & 1u) <= ry && (int)(st >> 2 & 1u) <= rz) S.plane[cp + S.offs[e]] = id;
-                            if (listed && id - ghostV < cap_v) { vdesc[3 * (uint64_t)(id - ghostV)] = dxy; vdesc[3 * (uint64_t)(id - ghostV) + 1] = dlz | e << 16; }
-                            ++id;
-                        }
-                    }
-                    if (listed) { /* triangle list: position = segment start + triangles of the earlier cells (from P1) */
-                        const uint32_t tp = (D.cpos_tch >> 16) + (cm >> 21);
-                        const uint32_t ent = (uint32_t)cp | ci << 12 | task << 23;
-                        const uint32_t nt = S.ntri[ci];
-                        for (uint32_t t = 0; t < nt; ++t) S.trilist[tp + t] = ent | t << 20;
-                    }
+                    first = false;
+                    __syncwarp();
                 }
-                __syncthreads();
-
-                if (!ovf) {
-                    /* ---------------- B: one thread per triangle ---------------- */
-                    const uint32_t n_tri = S.tri_n;
-                    for (uint32_t j = tid; j < n_tri; j += EMIT_THREADS) {
-                        const uint32_t ent = S.trilist[j];
-                        const int cp = (int)(ent & 4095u);
-                        const uint32_t ci = (ent >> 12) & 255u, t = (ent >> 20) & 7u, task = ent >> 23;
-                        const uint32_t edges = (uint32_t)(S.tri[ci] >> (12 * t));
-                        const uint32_t i0 = vofs + S.plane[cp + S.offs[edges & 15u]];
-                        const uint32_t i1 = vofs + S.plane[cp + S.offs[(edges >> 4) & 15u]];
-                        const uint32_t i2 = vofs + S.plane[cp + S.offs[(edges >> 8) & 15u]];
-                        const SegDesc &D = S.seg[task];
-                        const uint32_t tslot = D.tseg + (j - (D.cpos_tch >> 16)) - ghostT;
-                        if (tslot < cap_t) {
-                            uint32_t *o = idx + (uint64_t)tslot * 3;
-                            o[0] = i0; o[1] = i1; o[2] = i2;
-                        }
-                    }
-                    lo = hi;
-                    if (lo >= NROWS_OWN) break;
-                } else {
-                    if (level == 2) break; /* cannot happen (one row always fits); never spin */
-                    ++level;               /* too dense: list fewer rows per pass (the id planes are filled) */
-                }
-                first = false;
+                __syncwarp();
             }
         }
     }
@@ -829,10 +816,11 @@ cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, uint32_t
 cudaError_t isomc_launch_count(const Geo &g, const uint32_t *signs, const McTables *tabs, uint32_t *segpre,
                                uint32_t *rowV, uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot,
                                int sms, cudaStream_t st) {
-    const uint32_t rows_per_cta = 256u / g.nsegx > 0 ? 256u / g.nsegx : 1u;
-    const uint64_t groups = ((uint64_t)g.ncl * g.ncx + rows_per_cta - 1) / rows_per_cta;
-    k_count<<<(uint32_t)(groups < (uint64_t)sms * 8 ? groups : (uint64_t)sms * 8), 256, 0, st>>>(g, signs, tabs, segpre, rowV, rowT, rowA,
-                                                                                           layerTot);
+    uint32_t gshift = 0;
+    while ((1u << gshift) < g.nsegx && gshift < 5) ++gshift;
+    const uint32_t rpw = g.nsegx <= 32 ? (32u >> gshift) : 1u;
+    const uint64_t warps = ((uint64_t)g.ncl * g.ncx + rpw - 1) / rpw;
+    k_count<<<grid_for(warps, sms, 8, 8), 256, 0, st>>>(g, signs, tabs, segpre, rowV, rowT, rowA, layerTot, gshift);
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_scan(const Geo &g, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
@@ -858,7 +846,7 @@ static cudaError_t launch_emit(const Geo &g, const uint32_t *signs, const uint32
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const uint32_t nby = (g.ncx + BY - 1) / BY, nbz = (g.ncl + BZ - 1) / BZ;
-    uint64_t blocks = (uint64_t)nby * nbz;
+    uint64_t blocks = ((uint64_t)nby * nbz + EMIT_WARPS - 1) / EMIT_WARPS;
     if (blocks > (uint64_t)sms * per_sm) blocks = (uint64_t)sms * per_sm;
     k_emit<<<(uint32_t)blocks, EMIT_THREADS, smem, st>>>(g, signs, segpre, rowPV, rowPT, tabs, totals, vofs, ticket,
                                                          reinterpret_cast<uint32_t *>(xyz), idx, cap_v, cap_t);
