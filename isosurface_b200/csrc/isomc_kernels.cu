@@ -421,6 +421,7 @@ struct EmitShared {
     uint16_t emask[256];
     uint16_t ownmask[8];
     int16_t offs[12];   /* plane index of edge e seen from a cell at region pos cp: cp + offs[e] */
+    int32_t look[12];   /* (offs[e] + 4096) | rowback[e] << 16: one load per lookup in phase B */
     uint8_t rowback[12];/* region rows between a cell and the (virtual) creator of its edge e */
     uint8_t bstep[12];  /* dx | dy << 1 | dz << 2 of that step */
     uint8_t ntri[256];
@@ -467,6 +468,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
         S.bstep[tid] = (uint8_t)(ow & 7);
         S.rowback[tid] = (uint8_t)((ow >> 1 & 1) + (ow >> 2 & 1) * RY);
         S.offs[tid] = (int16_t)(axis * NREGION - back);
+        S.look[tid] = (int32_t)((axis * NREGION - back + 4096) | ((ow >> 1 & 1) + (ow >> 2 & 1) * RY) << 16);
     }
     __syncthreads(); /* the only block barrier: tables ready */
     WarpShared &W = S.w[warp];
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
         {
             const int cz = max(t_rz, (lz0 == 0) ? 1 : 0), cy = max(t_ry, (y0 == 0) ? 1 : 0);
             const uint32_t b = __shfl_sync(0xFFFFFFFFu, pv, has_task ? cz * RY + cy : 0);
-            if (has_task) W.rowbase[lane] = b;
+            if (has_task) W.rowbase[lane] = b + vofs; /* global id base of the row */
         }
         const uint32_t *my_signs = signs + ((uint64_t)(row_ok ? l : 0) * g.N + (uint32_t)(row_ok ? r : 0)) * g.nws;
         const uint32_t *my_sp = segpre + (uint64_t)row * g.nsegx;
@@ -616,7 +618,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                             }
                             const uint32_t em = S.emask[ci];
                             const int rz = rq / RY, ry = rq - rz * RY;
-                            const uint32_t rel = vid - W.rowbase[rq]; /* < 65536: row totals are 16 bit */
+                            const uint32_t rel = vid + vofs - W.rowbase[rq]; /* < 65536: row totals are 16 bit */
                             /* creator cell for the vertex descriptors: x | y << 16, local layer | e << 16 */
                             const uint32_t dxy = (s * 32 + i) | (uint32_t)(y0 + ry - 1) << 16, dlz = (uint32_t)(lz0 + rz - 1);
                             if (bfl == 0) { /* interior: creates exactly its crossed e5, e6, e10, ranks from rank3 */
@@ -647,7 +649,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                                     const uint32_t st = S.bstep[e], slot = vid + rk - ghostV;
                                     /* the (virtual) creator's row has the same id base (clamped rows) */
                                     if ((int)(st & 1u) <= rx && (int)(st >> 1 & 1u) <= ry && (int)(st >> 2 & 1u) <= rz)
-                                        W.plane[cp + S.offs[e]] = (uint16_t)(vid + rk - W.rowbase[rq - S.rowback[e]]);
+                                        W.plane[cp + S.offs[e]] = (uint16_t)(vid + vofs + rk - W.rowbase[rq - S.rowback[e]]);
                                     if (lst && slot < cap_v) { vdesc[3 * (uint64_t)slot] = dxy; vdesc[3 * (uint64_t)slot + 1] = dlz | e << 16; }
                                     ++rk;
                                 }
@@ -656,7 +658,12 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                                 const uint32_t tp = (D.cpos_tch >> 16) + (cm >> 19);
                                 const uint32_t ent = (uint32_t)cp | ci << 10 | task << 21;
                                 const uint32_t nt = S.ntri[ci];
-                                for (uint32_t t = 0; t < nt; ++t) W.trilist[tp + t] = ent | t << 18;
+                                uint32_t *tl = W.trilist + tp; /* nt is 1..5 */
+                                tl[0] = ent;
+                                if (nt > 1) tl[1] = ent | 1u << 18;
+                                if (nt > 2) tl[2] = ent | 2u << 18;
+                                if (nt > 3) tl[3] = ent | 3u << 18;
+                                if (nt > 4) tl[4] = ent | 4u << 18;
                             }
                         }
                     }
@@ -671,10 +678,11 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                                 const int cp = (int)(ent & 1023u);
                                 const uint32_t ci = (ent >> 10) & 255u, t = (ent >> 18) & 7u, task = ent >> 21;
                                 const uint32_t edges = (uint32_t)(S.tri[ci] >> (12 * t));
-                                const uint32_t e0 = edges & 15u, e1 = (edges >> 4) & 15u, e2 = (edges >> 8) & 15u;
-                                const uint32_t i0 = vofs + W.rowbase[task - S.rowback[e0]] + W.plane[cp + S.offs[e0]];
-                                const uint32_t i1 = vofs + W.rowbase[task - S.rowback[e1]] + W.plane[cp + S.offs[e1]];
-                                const uint32_t i2 = vofs + W.rowbase[task - S.rowback[e2]] + W.plane[cp + S.offs[e2]];
+                                const uint32_t k0 = (uint32_t)S.look[edges & 15u], k1 = (uint32_t)S.look[(edges >> 4) & 15u], k2 = (uint32_t)S.look[(edges >> 8) & 15u];
+                                const int cq = cp - 4096;
+                                const uint32_t i0 = W.rowbase[task - (k0 >> 16)] + W.plane[cq + (int)(k0 & 0xFFFFu)];
+                                const uint32_t i1 = W.rowbase[task - (k1 >> 16)] + W.plane[cq + (int)(k1 & 0xFFFFu)];
+                                const uint32_t i2 = W.rowbase[task - (k2 >> 16)] + W.plane[cq + (int)(k2 & 0xFFFFu)];
                                 const SegDesc &D = W.seg[task];
                                 const uint32_t tslot = D.tseg + (j - (D.cpos_tch >> 16)) - ghostT;
                                 if (tslot < cap_t) {
@@ -712,23 +720,41 @@ __global__ void __launch_bounds__(256) k_vertex(Src src, Geo g, const McTables *
     unsigned long long n = totals[8];
     if (n > cap_v) n = cap_v;
     const uint32_t *desc = reinterpret_cast<const uint32_t *>(xyz);
-    for (unsigned long long v = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; v < n;
-         v += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint32_t d0 = desc[3 * v], d1 = desc[3 * v + 1];
-        const uint32_t x = d0 & 0xFFFFu, y = d0 >> 16, lz = d1 & 0xFFFFu, e = d1 >> 16;
-        const uint32_t gz = g.gz0 + lz;
-        const uint32_t en = s_ends[e];
-        const uint32_t ux = x + (en & 1u), uy = y + (en >> 1 & 1u), uz = en >> 2 & 1u;
-        const uint32_t vx = x + (en >> 4 & 1u), vy = y + (en >> 5 & 1u), vz = en >> 6 & 1u;
-        const float a = src.at(g, ux, uy, lz + uz), b = src.at(g, vx, vy, lz + vz);
-        const float delta = __fsub_rn(b, a);
-        const float t = (delta == 0.0f) ? 0.5f : __fdiv_rn(-a, delta);
-        const float omt = __fsub_rn(1.0f, t);
-        const float pax = __fmul_rn((float)ux, g.inv), pay = __fmul_rn((float)uy, g.inv), paz = __fmul_rn((float)(gz + uz), g.inv);
-        const float pbx = __fmul_rn((float)vx, g.inv), pby = __fmul_rn((float)vy, g.inv), pbz = __fmul_rn((float)(gz + vz), g.inv);
-        xyz[3 * v] = __fadd_rn(__fmul_rn(pax, omt), __fmul_rn(pbx, t));
-        xyz[3 * v + 1] = __fadd_rn(__fmul_rn(pay, omt), __fmul_rn(pby, t));
-        xyz[3 * v + 2] = __fadd_rn(__fmul_rn(paz, omt), __fmul_rn(pbz, t));
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long v0 = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; v0 < n; v0 += 4 * stride) {
+        /* four independent vertices per iteration: all sample loads are issued before the first use */
+        uint32_t dd0[4], dd1[4];
+        float sa[4], sb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned long long v = v0 + u * stride;
+            dd0[u] = v < n ? desc[3 * v] : 0u;
+            dd1[u] = v < n ? desc[3 * v + 1] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t x = dd0[u] & 0xFFFFu, y = dd0[u] >> 16, lz = dd1[u] & 0xFFFFu, en = s_ends[(dd1[u] >> 16) & 15u];
+            sa[u] = src.at(g, x + (en & 1u), y + (en >> 1 & 1u), lz + (en >> 2 & 1u));
+            sb[u] = src.at(g, x + (en >> 4 & 1u), y + (en >> 5 & 1u), lz + (en >> 6 & 1u));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned long long v = v0 + u * stride;
+            if (v >= n) break;
+            const uint32_t x = dd0[u] & 0xFFFFu, y = dd0[u] >> 16, lz = dd1[u] & 0xFFFFu, en = s_ends[(dd1[u] >> 16) & 15u];
+            const uint32_t gz = g.gz0 + lz;
+            const uint32_t ux = x + (en & 1u), uy = y + (en >> 1 & 1u), uz = en >> 2 & 1u;
+            const uint32_t vx = x + (en >> 4 & 1u), vy = y + (en >> 5 & 1u), vz = en >> 6 & 1u;
+            const float a = sa[u], b = sb[u];
+            const float delta = __fsub_rn(b, a);
+            const float t = (delta == 0.0f) ? 0.5f : __fdiv_rn(-a, delta);
+            const float omt = __fsub_rn(1.0f, t);
+            const float pax = __fmul_rn((float)ux, g.inv), pay = __fmul_rn((float)uy, g.inv), paz = __fmul_rn((float)(gz + uz), g.inv);
+            const float pbx = __fmul_rn((float)vx, g.inv), pby = __fmul_rn((float)vy, g.inv), pbz = __fmul_rn((float)(gz + vz), g.inv);
+            xyz[3 * v] = __fadd_rn(__fmul_rn(pax, omt), __fmul_rn(pbx, t));
+            xyz[3 * v + 1] = __fadd_rn(__fmul_rn(pay, omt), __fmul_rn(pby, t));
+            xyz[3 * v + 2] = __fadd_rn(__fmul_rn(paz, omt), __fmul_rn(pbz, t));
+        }
     }
 }
 
