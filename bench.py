@@ -179,7 +179,7 @@ def run_reference(args):
         import torch
         from isosurface_b200 import _lib
         lib = _lib.load()
-        nl = min(size + 1, 65)
+        nl = min(size + 1, 257)
         host = make_field(lib, torch, 0, wl, 0, nl).cpu().numpy().reshape(nl, size, size)
     # W warm-ups + K steps of a bounded sample; keep the whole run within a few minutes
     per = max(1.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
@@ -326,7 +326,7 @@ def run_ours(args):
     }
     # roofline of the dominant kernel and of the whole extract
     kern = {"k_sign": (prof[0], 4 * S / world), "k_count": (prof[1], 0), "k_scan_rows": (prof[2], 0),
-            "k_emit": (prof[3], (12 * V + 12 * T) / world)}
+            "k_emit": (prof[3], (12 * V + 12 * T) / world)}  # "k_emit" here = k_emit + k_vertex (one CUDA-event interval)
     dom = max(("k_sign", "k_emit"), key=lambda k: kern[k][0])
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
@@ -395,7 +395,7 @@ def run_ours(args):
     if world == 1 and rank == 0 and not args.no_cpu:
         host = None
         if kind == "grid":
-            nl = min(size + 1, 65)
+            nl = min(size + 1, 257)
             host = grid[: nl * size * size].cpu().numpy().reshape(nl, size, size)
         cb = cpu_baseline(wl, host, target_s=args.cpu_seconds)
         line["cpu_baseline"] = cb
