@@ -254,14 +254,18 @@ def run_ours(args):
 
     def step():
         with torch.cuda.stream(stream):
+            if world == 1:  # the plain single-GPU entry points (what MarchingCubes.extract calls)
+                if kind == "grid":
+                    _lib.check(lib.isomc_enqueue_grid_device(h, C.c_void_p(grid.data_ptr())), h)
+                else:
+                    _lib.check(lib.isomc_enqueue_sdf(h, prog.ctypes.data, len(prog)), h)
+                _lib.check(lib.isomc_finish(h), h)
+                return
             if kind == "grid":
                 _lib.check(lib.isomc_slab_count_grid_device(h, C.c_void_p(grid.data_ptr())), h)
             else:
                 _lib.check(lib.isomc_slab_count_sdf(h, prog.ctypes.data, len(prog)), h)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, mine)
-            else:
-                gathered.copy_(mine, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, mine)
             _lib.check(lib.isomc_slab_emit_gathered(h, C.c_void_p(gathered.data_ptr()), rank, world), h)
 
     def barrier():

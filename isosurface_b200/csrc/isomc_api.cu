@@ -11,6 +11,9 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
+#include <vector>
+#include <cstdlib>
 
 #include "../../include/isomc.h"
 #include "isomc_device.cuh"
@@ -22,6 +25,7 @@ namespace {
 thread_local std::string g_create_error;
 
 enum SrcKind { SRC_NONE = 0, SRC_GRID = 1, SRC_SDF = 2 };
+constexpr int MAX_CHUNKS = 16;
 
 }  // namespace
 
@@ -29,7 +33,13 @@ struct isomc {
     uint32_t size = 0, z_begin = 0, z_end = 0;
     int device = 0, sms = 148;
     Geo g{};
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, stream2 = nullptr; /* stream2: odd z-chunks of the pipeline */
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_chunk[MAX_CHUNKS] = {};
+    uint32_t n_chunks = 1, chunk_l[MAX_CHUNKS + 1] = {}; /* cell layers [chunk_l[c], chunk_l[c+1]) */
+    bool pipeline = false; /* two-stream z-chunk pipeline: measured slower than the serial order (profiles/r01_history.md); ISOMC_PIPELINE=1 enables it */
+    /* ISOMC_TIMELINE=1: timing events after every kernel, printed at finish (debugging the stream overlap) */
+    bool timeline = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> tl;
     /* scratch */
     uint32_t *signs = nullptr, *segpre = nullptr, *rowV = nullptr, *rowT = nullptr, *rowA = nullptr;
     unsigned long long *layerTot = nullptr, *totals = nullptr; /* totals: 12 u64 */
@@ -130,41 +140,131 @@ int32_t ensure_capacity(isomc *h, uint64_t nv, uint64_t nt) {
     return ISOMC_OK;
 }
 
-/* phase 1: sign bits, counts, scans.  Everything stream-ordered, nothing synchronises. */
-int32_t enqueue_count(isomc *h) {
+/*
+ * The extract is cut into a few z-chunks (multiples of the emission brick height).  Everything a chunk
+ * needs comes from the chunks below it (the row scan is causal in z), which allows a two-stage pipeline:
+ *
+ *   stream2 (producer, HBM-bound):   sign(0) sign(1) sign(2) ...
+ *   stream  (consumer, issue-bound): wait(sign(c)) -> count(c) -> scan(c) -> [emit(c) -> vertex(c)]   for c = 0, 1, ...
+ *
+ * sign(c) covers sample layers (l0, l1] (chunk 0 also layer 0), which is what count(c) and emit(c) read
+ * beyond the lower chunks.  The sign kernel is launched with few CTAs per SM so that both stages stay
+ * resident.  Nothing synchronises with the host.
+ */
+void tl_mark(isomc *h, const char *name, uint32_t c, cudaStream_t st) {
+    if (!h->timeline) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    h->tl.emplace_back(std::string(name) + "(" + std::to_string(c) + ")", e);
+}
+
+int32_t fork_streams(isomc *h) {
+    if (h->n_chunks > 1) {
+        CU(h, cudaEventRecord(h->ev_fork, h->stream));
+        CU(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    }
+    return ISOMC_OK;
+}
+int32_t join_streams(isomc *h) {
+    if (h->n_chunks > 1) {
+        CU(h, cudaEventRecord(h->ev_join, h->stream2));
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    }
+    return ISOMC_OK;
+}
+
+int32_t launch_emit_chunk(isomc *h, uint32_t c, cudaStream_t st) {
+    const Geo &g = h->g;
+    const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
+    const uint32_t v0 = l0 < g.ghost ? g.ghost : l0; /* the ghost layer of a slab creates no vertices of ours */
+    CU(h, isomc_launch_emit(g, h->signs, h->segpre, h->rowV, h->rowT, h->tabs, h->layerTot, h->vofs, h->ticket + c, h->xyz,
+                            h->idx, h->cap_v, h->cap_t, l0, l1, h->sms, st));
+    if (v0 < l1) {
+        const int per_sm = 8;
+        if (h->kind == SRC_GRID)
+            CU(h, isomc_launch_vertex_grid(g, h->d_grid, h->tabs, h->layerTot, h->rowV, h->xyz, h->cap_v, v0, l1, h->sms, per_sm, st));
+        else
+            CU(h, isomc_launch_vertex_sdf(g, h->prog, h->tabs, h->layerTot, h->rowV, h->xyz, h->cap_v, v0, l1, h->sms, per_sm, st));
+    }
+    h->stats.kernel_launches += 2;
+    return ISOMC_OK;
+}
+
+/* phase 1 (+ optionally phase 2 inline): sign bits, counts, scans [, emission] per z-chunk */
+int32_t enqueue_count(isomc *h, bool emit_inline) {
     const Geo &g = h->g;
     h->have_result = false; h->counted = false; h->emitted = false; h->totals_valid = false;
     h->stats.kernel_launches = 0; h->stats.emit_reruns = 0;
     if (g.ncl == 0 || g.ncx == 0) { /* size == 1: the reference visits no cells */
         CU(h, cudaMemsetAsync(h->totals, 0, 12 * sizeof(unsigned long long), h->stream));
         h->counted = true;
+        h->emitted = emit_inline;
         return ISOMC_OK;
+    }
+    const bool serial = h->profiling || !h->pipeline;
+    /* chunk plan: serial = one chunk; else 4 (<= 1 GiB of samples) .. 8 chunks, multiples of the brick height */
+    {
+        const uint32_t bz = (uint32_t)isomc_emit_layers_per_brick();
+        const uint64_t bytes = 4ull * g.N * g.N * g.nsl;
+        uint32_t n = (serial || g.ncl < 64) ? 1u : (bytes <= (1ull << 30) ? 4u : 8u);
+        uint32_t per = ((g.ncl + n - 1) / n + bz - 1) / bz * bz;
+        n = (g.ncl + per - 1) / per;
+        h->n_chunks = n;
+        for (uint32_t c = 0; c <= n; ++c) h->chunk_l[c] = c * per < g.ncl ? c * per : g.ncl;
     }
     if (h->profiling) CU(h, cudaEventRecord(h->ev[0], h->stream));
     CU(h, cudaMemsetAsync(h->layerTot, 0, (size_t)g.ncl * 3 * sizeof(unsigned long long), h->stream));
-    if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, h->sms, h->stream));
-    else CU(h, isomc_launch_sign_sdf(g, h->prog, h->signs, h->sms, h->stream));
+    CU(h, cudaMemsetAsync(h->ticket, 0, MAX_CHUNKS * sizeof(uint32_t), h->stream));
+    tl_mark(h, "start", 0, h->stream);
+    int32_t rc = fork_streams(h);
+    if (rc) return rc;
+    const bool piped = h->n_chunks > 1;
+    /* producer: all sign chunks on stream2 (few CTAs per SM: HBM-bound, leaves the SMs to the consumer) */
+    for (uint32_t c = 0; c < h->n_chunks; ++c) {
+        cudaStream_t st = piped ? h->stream2 : h->stream;
+        const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
+        const uint32_t row0 = (c == 0 ? 0u : l0 + 1) * g.N, row1 = (l1 + 1) * g.N;
+        if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, row0, row1, h->sms, piped ? 3 : 8, st));
+        else CU(h, isomc_launch_sign_sdf(g, h->prog, h->signs, row0, row1, h->sms, piped ? 3 : 8, st));
+        if (piped) CU(h, cudaEventRecord(h->ev_chunk[c], st));
+        tl_mark(h, "sign", c, st);
+        h->stats.kernel_launches += 1;
+    }
     if (h->profiling) CU(h, cudaEventRecord(h->ev[1], h->stream));
-    CU(h, isomc_launch_count(g, h->signs, h->tabs, h->segpre, h->rowV, h->rowT, h->rowA, h->layerTot, h->sms, h->stream));
-    if (h->profiling) CU(h, cudaEventRecord(h->ev[2], h->stream));
-    CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, h->stream));
-    if (h->profiling) CU(h, cudaEventRecord(h->ev[3], h->stream));
-    h->stats.kernel_launches += 3;
+    /* consumer */
+    for (uint32_t c = 0; c < h->n_chunks; ++c) {
+        cudaStream_t st = h->stream;
+        const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
+        if (piped) CU(h, cudaStreamWaitEvent(st, h->ev_chunk[c], 0));
+        CU(h, isomc_launch_count(g, h->signs, h->tabs, h->segpre, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, 8, st));
+        if (h->profiling) CU(h, cudaEventRecord(h->ev[2], h->stream));
+        tl_mark(h, "count", c, st);
+        CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, l0, l1, st));
+        if (h->profiling) CU(h, cudaEventRecord(h->ev[3], h->stream));
+        h->stats.kernel_launches += 2;
+        if (emit_inline) {
+            rc = launch_emit_chunk(h, c, st);
+            if (rc) return rc;
+            tl_mark(h, "emit+vertex", c, st);
+        }
+    }
+    rc = join_streams(h);
+    if (rc) return rc;
     h->counted = true;
+    h->emitted = emit_inline;
     return ISOMC_OK;
 }
 
+/* phase 2 on its own (after a buffer grow, or after the slab all-gather) */
 int32_t enqueue_emit(isomc *h) {
     const Geo &g = h->g;
     if (g.ncl == 0 || g.ncx == 0) { h->emitted = true; return ISOMC_OK; }
-    CU(h, cudaMemsetAsync(h->ticket, 0, sizeof(uint32_t), h->stream));
-    if (h->kind == SRC_GRID)
-        CU(h, isomc_launch_emit_grid(g, h->d_grid, h->signs, h->segpre, h->rowV, h->rowT, h->tabs, h->totals, h->vofs,
-                                     h->ticket, h->xyz, h->idx, h->cap_v, h->cap_t, h->sms, h->stream));
-    else
-        CU(h, isomc_launch_emit_sdf(g, h->prog, h->signs, h->segpre, h->rowV, h->rowT, h->tabs, h->totals, h->vofs,
-                                    h->ticket, h->xyz, h->idx, h->cap_v, h->cap_t, h->sms, h->stream));
-    h->stats.kernel_launches += 2; /* k_emit + k_vertex */
+    CU(h, cudaMemsetAsync(h->ticket, 0, MAX_CHUNKS * sizeof(uint32_t), h->stream));
+    for (uint32_t c = 0; c < h->n_chunks; ++c) {
+        int32_t rc = launch_emit_chunk(h, c, h->stream);
+        if (rc) return rc;
+    }
     h->emitted = true;
     return ISOMC_OK;
 }
@@ -197,6 +297,15 @@ int32_t finish_impl(isomc *h) {
     }
     if (h->profiling) CU(h, cudaEventRecord(h->ev[4], h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    if (h->timeline && !h->tl.empty()) {
+        for (auto &e : h->tl) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->tl[0].second, e.second);
+            fprintf(stderr, "[isomc timeline] %-16s done at %8.3f ms\n", e.first.c_str(), ms);
+            }
+        for (auto &e : h->tl) cudaEventDestroy(e.second);
+        h->tl.clear();
+    }
     h->n_v = nv; h->n_t = nt; h->n_a = h->h_totals[11];
     h->have_result = true;
     isomc_stats &s = h->stats;
@@ -234,6 +343,8 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
     isomc *h = new (std::nothrow) isomc();
     if (!h) return fail(nullptr, ISOMC_ERR_OOM, "host allocation failed");
     h->size = size; h->z_begin = z_begin; h->z_end = z_end; h->device = device;
+    h->timeline = getenv("ISOMC_TIMELINE") != nullptr;
+    if (const char *p = getenv("ISOMC_PIPELINE")) h->pipeline = atoi(p) != 0;
     Geo &g = h->g;
     g.N = size; g.ncx = size - 1;
     g.nsegx = (g.ncx + 31) / 32; g.nws = g.nsegx + 1;
@@ -266,7 +377,11 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
         CU(h, cudaMemset(h->totals, 0, 12 * sizeof(unsigned long long)));
         CU(h, cudaMalloc(&h->vofs, sizeof(uint32_t)));
         CU(h, cudaMemset(h->vofs, 0, sizeof(uint32_t)));
-        CU(h, cudaMalloc(&h->ticket, sizeof(uint32_t)));
+        CU(h, cudaMalloc(&h->ticket, MAX_CHUNKS * sizeof(uint32_t)));
+        CU(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        CU(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        for (auto &ev : h->ev_chunk) CU(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CU(h, cudaMallocHost(&h->h_totals, 12 * sizeof(unsigned long long)));
         return ISOMC_OK;
     };
@@ -301,6 +416,10 @@ int32_t isomc_destroy(isomc_t *h) {
     cudaFree(h->xyz); cudaFree(h->idx); cudaFree(h->stage_grid);
     if (h->h_totals) cudaFreeHost(h->h_totals);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return ISOMC_OK;
@@ -346,11 +465,8 @@ static int32_t enqueue_full(isomc_t *h) {
     if (rc) return rc;
     rc = set_vofs(h, 0);
     if (rc) return rc;
-    rc = enqueue_count(h);
-    if (rc) return rc;
     /* optimistic emission into the buffers of the previous extract; finish() re-runs it if they are too small */
-    if (h->cap_v > 0 || h->cap_t > 0) rc = enqueue_emit(h);
-    return rc;
+    return enqueue_count(h, h->cap_v > 0 || h->cap_t > 0);
 }
 
 int32_t isomc_enqueue_grid_device(isomc_t *h, const float *d_grid) {
@@ -441,7 +557,7 @@ int32_t isomc_slab_count_grid_device(isomc_t *h, const float *d_slab) {
     int32_t rc = bind_device(h);
     if (rc) return rc;
     h->kind = SRC_GRID; h->d_grid = d_slab;
-    return enqueue_count(h);
+    return enqueue_count(h, false);
 }
 
 int32_t isomc_slab_count_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes) {
@@ -451,7 +567,7 @@ int32_t isomc_slab_count_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_
     rc = validate_program(h, prog, n_nodes, &h->prog);
     if (rc) return rc;
     h->kind = SRC_SDF; h->d_grid = nullptr;
-    return enqueue_count(h);
+    return enqueue_count(h, false);
 }
 
 int32_t isomc_slab_totals(isomc_t *h, uint64_t totals[3]) {

@@ -97,12 +97,11 @@ __device__ __forceinline__ uint32_t valid_mask(uint32_t n) { /* low n bits, n in
 
 /* generic path: any source, any size/alignment; one lane per sample, ballot per 32 samples */
 template <class Src>
-__global__ void __launch_bounds__(256) k_sign(Src src, Geo g, uint32_t *__restrict__ signs) {
+__global__ void __launch_bounds__(256) k_sign(Src src, Geo g, uint32_t *__restrict__ signs, uint32_t row0, uint32_t row1) {
     constexpr int U = 8;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-    const uint32_t nrows = g.nsl * g.N;
-    for (uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < nrows; row += nwarps) {
+    for (uint32_t row = row0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < row1; row += nwarps) {
         const uint32_t lz = row / g.N, y = row - lz * g.N;
         uint32_t *out = signs + (uint64_t)row * g.nws;
         for (uint32_t w0 = 0; w0 < g.nws; w0 += U) {
@@ -127,14 +126,14 @@ __global__ void __launch_bounds__(256) k_sign(Src src, Geo g, uint32_t *__restri
  * contiguous bytes per warp instruction), turns them into a 4-bit nibble and the nibbles of 8
  * neighbouring lanes are OR-combined with 3 shuffles into one 32-sample word. */
 template <int U>
-__global__ void __launch_bounds__(256) k_sign_vec4(const float4 *__restrict__ grid4, Geo g, uint32_t *__restrict__ signs) {
+__global__ void __launch_bounds__(256) k_sign_vec4(const float4 *__restrict__ grid4, Geo g, uint32_t *__restrict__ signs,
+                                                   uint32_t row0, uint32_t row1) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-    const uint32_t nrows = g.nsl * g.N;
     const uint32_t n4 = g.N >> 2;            /* float4 per sample row */
     const uint32_t steps = (n4 + 31) >> 5;   /* 128-sample chunks per row */
     const uint32_t sh = (lane & 7u) * 4u;
-    for (uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < nrows; row += nwarps) {
+    for (uint32_t row = row0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < row1; row += nwarps) {
         const float4 *rp = grid4 + (uint64_t)row * n4;
         uint32_t *out = signs + (uint64_t)row * g.nws;
         for (uint32_t c0 = 0; c0 < steps; c0 += U) {
@@ -204,20 +203,21 @@ __device__ __forceinline__ SegCounts count_segment(const Geo &g, const uint32_t 
 __global__ void __launch_bounds__(256) k_count(Geo g, const uint32_t *__restrict__ signs, const McTables *__restrict__ tabs,
                                                uint32_t *__restrict__ segpre, uint32_t *__restrict__ rowV,
                                                uint32_t *__restrict__ rowT, uint32_t *__restrict__ rowA,
-                                               unsigned long long *__restrict__ layerTot, uint32_t gshift) {
+                                               unsigned long long *__restrict__ layerTot, uint32_t gshift, uint32_t row0,
+                                               uint32_t row1) {
     __shared__ uint8_t s_ntri[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = tabs->ntri[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
-    const uint32_t nrows = g.ncl * g.ncx;
+    const uint32_t nrows = row1;
     if (g.nsegx <= 32) {
         const uint32_t G = 1u << gshift, rpw = 32u >> gshift, sub = lane >> gshift, s = lane & (G - 1);
-        const uint32_t niter = (nrows + rpw - 1) / rpw;
+        const uint32_t niter = (row1 - row0 + rpw - 1) / rpw;
         for (uint32_t it = gwarp; it < niter; it += nwarps) {
-            const uint32_t row = it * rpw + sub;
+            const uint32_t row = row0 + it * rpw + sub;
             const bool valid = row < nrows && s < g.nsegx;
-            const uint32_t lz = (row < nrows ? row : 0u) / g.ncx;
+            const uint32_t lz = (row < nrows ? row : row0) / g.ncx;
             SegCounts c = {0u, 0u, 0u};
             if (valid) c = count_segment(g, signs, s_ntri, row, lz, s);
             const uint32_t pk = c.nv | c.nt << 16; /* 16-bit fields: row totals < 65536 for size <= 8192 */
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) k_count(Geo g, const uint32_t *__restrict
             }
         }
     } else {
-        for (uint32_t row = gwarp; row < nrows; row += nwarps) {
+        for (uint32_t row = row0 + gwarp; row < nrows; row += nwarps) {
             const uint32_t lz = row / g.ncx;
             uint32_t carry = 0, acta = 0;
             for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 32) {
@@ -307,10 +307,10 @@ __device__ __forceinline__ T block_excl_scan_256(T v, T *s_warp, T &total) {
  *   [8] vertices owned  [9] owned vertices created before the last cell layer  [10] triangles owned */
 __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t *__restrict__ rowV, uint32_t *__restrict__ rowT,
                                                    const unsigned long long *__restrict__ layerTot,
-                                                   unsigned long long *__restrict__ totals) {
+                                                   unsigned long long *__restrict__ totals, uint32_t lz_first) {
     __shared__ unsigned long long s_w[8];
     __shared__ unsigned long long s_base[2];
-    const uint32_t lz = blockIdx.x;
+    const uint32_t lz = lz_first + blockIdx.x;
     /* base = sum of the totals of the layers below (<= 4096 values) */
     unsigned long long bv = 0, bt = 0, ba = 0;
     for (uint32_t l = threadIdx.x; l < lz; l += blockDim.x) {
@@ -446,10 +446,11 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                                                       const uint32_t *__restrict__ rowPV,
                                                       const uint32_t *__restrict__ rowPT,
                                                       const McTables *__restrict__ tabs,
-                                                      const unsigned long long *__restrict__ totals,
+                                                      const unsigned long long *__restrict__ layerTot,
                                                       const uint32_t *__restrict__ vofs_ptr, uint32_t *__restrict__ ticket,
                                                       uint32_t *__restrict__ vdesc, uint32_t *__restrict__ idx,
-                                                      unsigned long long cap_v, unsigned long long cap_t) {
+                                                      unsigned long long cap_v, unsigned long long cap_t, uint32_t strip0,
+                                                      uint32_t strip1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmitShared &S = *reinterpret_cast<EmitShared *>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -474,10 +475,9 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
     WarpShared &W = S.w[warp];
 
     const uint32_t vofs = *vofs_ptr;
-    const uint32_t ghostV = (uint32_t)totals[4], ghostT = (uint32_t)totals[5];
+    const uint32_t ghostV = g.ghost ? (uint32_t)layerTot[0] : 0u, ghostT = g.ghost ? (uint32_t)layerTot[1] : 0u;
     const int first_own_layer = g.ghost ? 1 : 0;
-    const uint32_t nby = (g.ncx + BY - 1) / BY, nbz = (g.ncl + BZ - 1) / BZ;
-    const uint32_t n_strips = nby * nbz;
+    const uint32_t nby = (g.ncx + BY - 1) / BY;
     /* P1 task of this lane: region row (t_rz, t_ry) */
     const bool has_task = lane < NTASK;
     const int t_rz = (int)(lane / RY), t_ry = (int)(lane % RY);
@@ -486,9 +486,9 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
 
     for (;;) {
         uint32_t strip = 0;
-        if (lane == 0) strip = atomicAdd(ticket, 1u);
+        if (lane == 0) strip = strip0 + atomicAdd(ticket, 1u);
         strip = __shfl_sync(0xFFFFFFFFu, strip, 0);
-        if (strip >= n_strips) break;
+        if (strip >= strip1) break;
         const uint32_t bz = strip / nby, by = strip - bz * nby;
         const int lz0 = (int)(bz * BZ), y0 = (int)(by * BY);
 
@@ -712,16 +712,20 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
  * EDGE_CONNECTION direction of the creating cell, corner coordinates = (i as f32) * inv. */
 template <class Src>
 __global__ void __launch_bounds__(256) k_vertex(Src src, Geo g, const McTables *__restrict__ tabs,
-                                                const unsigned long long *__restrict__ totals, float *__restrict__ xyz,
-                                                unsigned long long cap_v) {
+                                                const unsigned long long *__restrict__ layerTot,
+                                                const uint32_t *__restrict__ rowPV, float *__restrict__ xyz,
+                                                unsigned long long cap_v, uint32_t lz_begin, uint32_t lz_end) {
     __shared__ uint8_t s_ends[12];
     if (threadIdx.x < 12) s_ends[threadIdx.x] = tabs->ends[threadIdx.x];
     __syncthreads();
-    unsigned long long n = totals[8];
+    /* vertices created by cell layers [lz_begin, lz_end): slots [first, n) */
+    const uint32_t ghostV = g.ghost ? (uint32_t)layerTot[0] : 0u;
+    const unsigned long long first = rowPV[(uint64_t)lz_begin * g.ncx] - ghostV;
+    unsigned long long n = (unsigned long long)rowPV[(uint64_t)(lz_end - 1) * g.ncx] + layerTot[3 * (lz_end - 1)] - ghostV;
     if (n > cap_v) n = cap_v;
     const uint32_t *desc = reinterpret_cast<const uint32_t *>(xyz);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long v0 = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; v0 < n; v0 += 4 * stride) {
+    for (unsigned long long v0 = first + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; v0 < n; v0 += 4 * stride) {
         /* four independent vertices per iteration: all sample loads are issued before the first use */
         uint32_t dd0[4], dd1[4];
         float sa[4], sb[4];
@@ -815,6 +819,7 @@ __global__ void k_synth(SynthParams sp, uint32_t size, float inv, uint32_t z_fir
 /* ------------------------------------------------------------------------------------------ */
 
 static inline uint32_t grid_for(uint64_t warps_needed, int sms, int warps_per_block, int blocks_per_sm) {
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
     uint64_t blocks = (warps_needed + warps_per_block - 1) / warps_per_block;
     uint64_t cap = (uint64_t)sms * blocks_per_sm;
     if (blocks > cap) blocks = cap;
@@ -822,36 +827,41 @@ static inline uint32_t grid_for(uint64_t warps_needed, int sms, int warps_per_bl
     return (uint32_t)blocks;
 }
 
-cudaError_t isomc_launch_sign_grid(const Geo &g, const float *d_grid, uint32_t *signs, int sms, cudaStream_t st) {
-    const uint32_t grid = grid_for((uint64_t)g.nsl * g.N, sms, 8, 8);
+/* sample rows [row0, row1) of the handle's lattice (row = local layer * N + y) */
+cudaError_t isomc_launch_sign_grid(const Geo &g, const float *d_grid, uint32_t *signs, uint32_t row0, uint32_t row1, int sms,
+                                   int ctas_per_sm, cudaStream_t st) {
+    const uint32_t grid = grid_for((uint64_t)(row1 - row0), sms, 8, ctas_per_sm);
     if ((g.N & 3u) == 0 && (reinterpret_cast<uintptr_t>(d_grid) & 15u) == 0) {
         const float4 *g4 = reinterpret_cast<const float4 *>(d_grid);
-        if (g.N >= 1024) k_sign_vec4<8><<<grid, 256, 0, st>>>(g4, g, signs);
-        else k_sign_vec4<4><<<grid, 256, 0, st>>>(g4, g, signs);
+        if (g.N >= 1024) k_sign_vec4<8><<<grid, 256, 0, st>>>(g4, g, signs, row0, row1);
+        else k_sign_vec4<4><<<grid, 256, 0, st>>>(g4, g, signs, row0, row1);
     } else {
         GridSrc src{d_grid};
-        k_sign<GridSrc><<<grid, 256, 0, st>>>(src, g, signs);
+        k_sign<GridSrc><<<grid, 256, 0, st>>>(src, g, signs, row0, row1);
     }
     return cudaGetLastError();
 }
-cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, uint32_t *signs, int sms, cudaStream_t st) {
+cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, uint32_t *signs, uint32_t row0, uint32_t row1, int sms,
+                                  int ctas_per_sm, cudaStream_t st) {
     SdfSrc src{prog};
-    k_sign<SdfSrc><<<grid_for((uint64_t)g.nsl * g.N, sms, 8, 8), 256, 0, st>>>(src, g, signs);
+    k_sign<SdfSrc><<<grid_for((uint64_t)(row1 - row0), sms, 8, ctas_per_sm), 256, 0, st>>>(src, g, signs, row0, row1);
     return cudaGetLastError();
 }
+/* cell layers [lz0, lz1) */
 cudaError_t isomc_launch_count(const Geo &g, const uint32_t *signs, const McTables *tabs, uint32_t *segpre,
                                uint32_t *rowV, uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot,
-                               int sms, cudaStream_t st) {
+                               uint32_t lz0, uint32_t lz1, int sms, int ctas_per_sm, cudaStream_t st) {
     uint32_t gshift = 0;
     while ((1u << gshift) < g.nsegx && gshift < 5) ++gshift;
     const uint32_t rpw = g.nsegx <= 32 ? (32u >> gshift) : 1u;
-    const uint64_t warps = ((uint64_t)g.ncl * g.ncx + rpw - 1) / rpw;
-    k_count<<<grid_for(warps, sms, 8, 8), 256, 0, st>>>(g, signs, tabs, segpre, rowV, rowT, rowA, layerTot, gshift);
+    const uint32_t row0 = lz0 * g.ncx, row1 = lz1 * g.ncx;
+    const uint64_t warps = ((uint64_t)(row1 - row0) + rpw - 1) / rpw;
+    k_count<<<grid_for(warps, sms, 8, ctas_per_sm), 256, 0, st>>>(g, signs, tabs, segpre, rowV, rowT, rowA, layerTot, gshift, row0, row1);
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_scan(const Geo &g, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
-                              unsigned long long *totals, cudaStream_t st) {
-    k_scan_rows<<<g.ncl, 256, 0, st>>>(g, rowV, rowT, layerTot, totals);
+                              unsigned long long *totals, uint32_t lz0, uint32_t lz1, cudaStream_t st) {
+    k_scan_rows<<<lz1 - lz0, 256, 0, st>>>(g, rowV, rowT, layerTot, totals, lz0);
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,
@@ -860,41 +870,48 @@ cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t
     return cudaGetLastError();
 }
 
+int isomc_emit_layers_per_brick() { return BZ; }
+
+/* cell layers [lz0, lz1), lz0 a multiple of BZ */
 static cudaError_t launch_emit(const Geo &g, const uint32_t *signs, const uint32_t *segpre, const uint32_t *rowPV,
-                               const uint32_t *rowPT, const McTables *tabs, const unsigned long long *totals,
+                               const uint32_t *rowPT, const McTables *tabs, const unsigned long long *layerTot,
                                const uint32_t *vofs, uint32_t *ticket, float *xyz, uint32_t *idx, uint64_t cap_v,
-                               uint64_t cap_t, int sms, cudaStream_t st) {
+                               uint64_t cap_t, uint32_t lz0, uint32_t lz1, int sms, cudaStream_t st) {
     const size_t smem = isomc_emit_smem_bytes(g.nws);
-    cudaError_t e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit, EMIT_THREADS, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    const uint32_t nby = (g.ncx + BY - 1) / BY, nbz = (g.ncl + BZ - 1) / BZ;
-    uint64_t blocks = ((uint64_t)nby * nbz + EMIT_WARPS - 1) / EMIT_WARPS;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int n = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_emit, EMIT_THREADS, smem);
+        if (e != cudaSuccess) return e;
+        per_sm = n < 1 ? 1 : n;
+    }
+    const uint32_t nby = (g.ncx + BY - 1) / BY;
+    const uint32_t strip0 = (lz0 / BZ) * nby, strip1 = ((lz1 + BZ - 1) / BZ) * nby;
+    uint64_t blocks = ((uint64_t)(strip1 - strip0) + EMIT_WARPS - 1) / EMIT_WARPS;
     if (blocks > (uint64_t)sms * per_sm) blocks = (uint64_t)sms * per_sm;
-    k_emit<<<(uint32_t)blocks, EMIT_THREADS, smem, st>>>(g, signs, segpre, rowPV, rowPT, tabs, totals, vofs, ticket,
-                                                         reinterpret_cast<uint32_t *>(xyz), idx, cap_v, cap_t);
+    k_emit<<<(uint32_t)blocks, EMIT_THREADS, smem, st>>>(g, signs, segpre, rowPV, rowPT, tabs, layerTot, vofs, ticket,
+                                                         reinterpret_cast<uint32_t *>(xyz), idx, cap_v, cap_t, strip0, strip1);
     return cudaGetLastError();
 }
 
-cudaError_t isomc_launch_emit_grid(const Geo &g, const float *d_grid, const uint32_t *signs, const uint32_t *segpre,
-                                   const uint32_t *rowPV, const uint32_t *rowPT, const McTables *tabs,
-                                   const unsigned long long *totals, const uint32_t *vofs, uint32_t *ticket, float *xyz,
-                                   uint32_t *idx, uint64_t cap_v, uint64_t cap_t, int sms, cudaStream_t st) {
-    cudaError_t e = launch_emit(g, signs, segpre, rowPV, rowPT, tabs, totals, vofs, ticket, xyz, idx, cap_v, cap_t, sms, st);
-    if (e != cudaSuccess) return e;
-    k_vertex<GridSrc><<<sms * 8, 256, 0, st>>>(GridSrc{d_grid}, g, tabs, totals, xyz, cap_v);
+cudaError_t isomc_launch_emit(const Geo &g, const uint32_t *signs, const uint32_t *segpre, const uint32_t *rowPV,
+                              const uint32_t *rowPT, const McTables *tabs, const unsigned long long *layerTot,
+                              const uint32_t *vofs, uint32_t *ticket, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
+                              uint32_t lz0, uint32_t lz1, int sms, cudaStream_t st) {
+    return launch_emit(g, signs, segpre, rowPV, rowPT, tabs, layerTot, vofs, ticket, xyz, idx, cap_v, cap_t, lz0, lz1, sms, st);
+}
+cudaError_t isomc_launch_vertex_grid(const Geo &g, const float *d_grid, const McTables *tabs, const unsigned long long *layerTot,
+                                     const uint32_t *rowPV, float *xyz, uint64_t cap_v, uint32_t lz0, uint32_t lz1, int sms,
+                                     int ctas_per_sm, cudaStream_t st) {
+    k_vertex<GridSrc><<<sms * ctas_per_sm, 256, 0, st>>>(GridSrc{d_grid}, g, tabs, layerTot, rowPV, xyz, cap_v, lz0, lz1);
     return cudaGetLastError();
 }
-cudaError_t isomc_launch_emit_sdf(const Geo &g, const SdfProgram &prog, const uint32_t *signs, const uint32_t *segpre,
-                                  const uint32_t *rowPV, const uint32_t *rowPT, const McTables *tabs,
-                                  const unsigned long long *totals, const uint32_t *vofs, uint32_t *ticket, float *xyz,
-                                  uint32_t *idx, uint64_t cap_v, uint64_t cap_t, int sms, cudaStream_t st) {
-    cudaError_t e = launch_emit(g, signs, segpre, rowPV, rowPT, tabs, totals, vofs, ticket, xyz, idx, cap_v, cap_t, sms, st);
-    if (e != cudaSuccess) return e;
-    k_vertex<SdfSrc><<<sms * 8, 256, 0, st>>>(SdfSrc{prog}, g, tabs, totals, xyz, cap_v);
+cudaError_t isomc_launch_vertex_sdf(const Geo &g, const SdfProgram &prog, const McTables *tabs, const unsigned long long *layerTot,
+                                    const uint32_t *rowPV, float *xyz, uint64_t cap_v, uint32_t lz0, uint32_t lz1, int sms,
+                                    int ctas_per_sm, cudaStream_t st) {
+    k_vertex<SdfSrc><<<sms * ctas_per_sm, 256, 0, st>>>(SdfSrc{prog}, g, tabs, layerTot, rowPV, xyz, cap_v, lz0, lz1);
     return cudaGetLastError();
 }
 

@@ -17,23 +17,29 @@ struct SynthParams {
 
 size_t isomc_emit_smem_bytes(uint32_t nws);
 
-cudaError_t isomc_launch_sign_grid(const Geo &g, const float *d_grid, uint32_t *signs, int sms, cudaStream_t st);
-cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, uint32_t *signs, int sms, cudaStream_t st);
+/* ranges: sample rows [row0,row1) for the sign kernels, cell layers [lz0,lz1) for the rest */
+cudaError_t isomc_launch_sign_grid(const Geo &g, const float *d_grid, uint32_t *signs, uint32_t row0, uint32_t row1, int sms,
+                                   int ctas_per_sm, cudaStream_t st);
+cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, uint32_t *signs, uint32_t row0, uint32_t row1, int sms,
+                                  int ctas_per_sm, cudaStream_t st);
 cudaError_t isomc_launch_count(const Geo &g, const uint32_t *signs, const McTables *tabs, uint32_t *segpre,
                                uint32_t *rowV, uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot,
-                               int sms, cudaStream_t st);
+                               uint32_t lz0, uint32_t lz1, int sms, int ctas_per_sm, cudaStream_t st);
 cudaError_t isomc_launch_scan(const Geo &g, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
-                              unsigned long long *totals, cudaStream_t st);
+                              unsigned long long *totals, uint32_t lz0, uint32_t lz1, cudaStream_t st);
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,
                                     cudaStream_t st);
-cudaError_t isomc_launch_emit_grid(const Geo &g, const float *d_grid, const uint32_t *signs, const uint32_t *segpre,
-                                   const uint32_t *rowPV, const uint32_t *rowPT, const McTables *tabs,
-                                   const unsigned long long *totals, const uint32_t *vofs, uint32_t *ticket, float *xyz,
-                                   uint32_t *idx, uint64_t cap_v, uint64_t cap_t, int sms, cudaStream_t st);
-cudaError_t isomc_launch_emit_sdf(const Geo &g, const SdfProgram &prog, const uint32_t *signs, const uint32_t *segpre,
-                                  const uint32_t *rowPV, const uint32_t *rowPT, const McTables *tabs,
-                                  const unsigned long long *totals, const uint32_t *vofs, uint32_t *ticket, float *xyz,
-                                  uint32_t *idx, uint64_t cap_v, uint64_t cap_t, int sms, cudaStream_t st);
+int isomc_emit_layers_per_brick();
+cudaError_t isomc_launch_emit(const Geo &g, const uint32_t *signs, const uint32_t *segpre, const uint32_t *rowPV,
+                              const uint32_t *rowPT, const McTables *tabs, const unsigned long long *layerTot,
+                              const uint32_t *vofs, uint32_t *ticket, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
+                              uint32_t lz0, uint32_t lz1, int sms, cudaStream_t st);
+cudaError_t isomc_launch_vertex_grid(const Geo &g, const float *d_grid, const McTables *tabs, const unsigned long long *layerTot,
+                                     const uint32_t *rowPV, float *xyz, uint64_t cap_v, uint32_t lz0, uint32_t lz1, int sms,
+                                     int ctas_per_sm, cudaStream_t st);
+cudaError_t isomc_launch_vertex_sdf(const Geo &g, const SdfProgram &prog, const McTables *tabs, const unsigned long long *layerTot,
+                                    const uint32_t *rowPV, float *xyz, uint64_t cap_v, uint32_t lz0, uint32_t lz1, int sms,
+                                    int ctas_per_sm, cudaStream_t st);
 cudaError_t isomc_launch_cube_indices(const Geo &g, const uint32_t *signs, const McTables *tabs, uint8_t *out, int sms,
                                       cudaStream_t st);
 cudaError_t isomc_launch_sample_sdf(const SdfProgram &prog, const float *xyz, uint64_t n, float *out, cudaStream_t st);
