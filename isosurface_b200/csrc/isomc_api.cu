@@ -44,6 +44,7 @@ struct isomc {
     uint32_t *signs = nullptr, *segpre = nullptr, *rowV = nullptr, *rowT = nullptr, *rowA = nullptr;
     unsigned long long *layerTot = nullptr, *totals = nullptr; /* totals: 12 u64 */
     uint32_t *vofs = nullptr, *ticket = nullptr;
+    int64_t vofs_cached = 0; /* value known to be in *vofs (set to 0 at create); -1 = written by the device */
     McTables *tabs = nullptr;
     unsigned long long *h_totals = nullptr; /* pinned */
     float *stage_grid = nullptr;            /* device copy of a host grid */
@@ -214,8 +215,7 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
         for (uint32_t c = 0; c <= n; ++c) h->chunk_l[c] = c * per < g.ncl ? c * per : g.ncl;
     }
     if (h->profiling) CU(h, cudaEventRecord(h->ev[0], h->stream));
-    CU(h, cudaMemsetAsync(h->layerTot, 0, (size_t)g.ncl * 3 * sizeof(unsigned long long), h->stream));
-    CU(h, cudaMemsetAsync(h->ticket, 0, MAX_CHUNKS * sizeof(uint32_t), h->stream));
+    CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + MAX_CHUNKS * sizeof(uint32_t), h->stream));
     tl_mark(h, "start", 0, h->stream);
     int32_t rc = fork_streams(h);
     if (rc) return rc;
@@ -324,7 +324,10 @@ int32_t finish_impl(isomc *h) {
 }
 
 int32_t set_vofs(isomc *h, uint32_t v) {
-    CU(h, cudaMemcpyAsync(h->vofs, &v, sizeof v, cudaMemcpyHostToDevice, h->stream));
+    if (h->vofs_cached == (int64_t)v) return ISOMC_OK;
+    CU(h, cudaMemsetAsync(h->vofs, 0, sizeof(uint32_t), h->stream));
+    if (v != 0) CU(h, cudaMemcpyAsync(h->vofs, &v, sizeof v, cudaMemcpyHostToDevice, h->stream));
+    h->vofs_cached = (int64_t)v;
     return ISOMC_OK;
 }
 
@@ -372,12 +375,13 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
         CU(h, cudaMalloc(&h->rowV, (nrows_c + 4) * sizeof(uint32_t)));
         CU(h, cudaMalloc(&h->rowT, (nrows_c + 4) * sizeof(uint32_t)));
         CU(h, cudaMalloc(&h->rowA, (nrows_c + 4) * sizeof(uint32_t)));
-        CU(h, cudaMalloc(&h->layerTot, ((size_t)g.ncl * 3 + 3) * sizeof(unsigned long long)));
+        /* per-layer totals followed by the emit tickets: zeroed by a single memset per extract */
+        CU(h, cudaMalloc(&h->layerTot, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + MAX_CHUNKS * sizeof(uint32_t)));
+        h->ticket = reinterpret_cast<uint32_t *>(h->layerTot + ((size_t)g.ncl * 3 + 4));
         CU(h, cudaMalloc(&h->totals, 12 * sizeof(unsigned long long)));
         CU(h, cudaMemset(h->totals, 0, 12 * sizeof(unsigned long long)));
         CU(h, cudaMalloc(&h->vofs, sizeof(uint32_t)));
         CU(h, cudaMemset(h->vofs, 0, sizeof(uint32_t)));
-        CU(h, cudaMalloc(&h->ticket, MAX_CHUNKS * sizeof(uint32_t)));
         CU(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
         CU(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CU(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -412,7 +416,7 @@ int32_t isomc_destroy(isomc_t *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->signs); cudaFree(h->segpre); cudaFree(h->rowV); cudaFree(h->rowT); cudaFree(h->rowA);
-    cudaFree(h->layerTot); cudaFree(h->totals); cudaFree(h->vofs); cudaFree(h->ticket); cudaFree(h->tabs);
+    cudaFree(h->layerTot); cudaFree(h->totals); cudaFree(h->vofs); cudaFree(h->tabs);
     cudaFree(h->xyz); cudaFree(h->idx); cudaFree(h->stage_grid);
     if (h->h_totals) cudaFreeHost(h->h_totals);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -613,6 +617,7 @@ int32_t isomc_slab_emit_gathered(isomc_t *h, const uint64_t *d_gathered, uint32_
     int32_t rc = bind_device(h);
     if (rc) return rc;
     CU(h, isomc_launch_slab_bases((const unsigned long long *)d_gathered, rank, h->g.ghost, h->vofs, h->stream));
+    h->vofs_cached = -1;
     h->stats.kernel_launches += 1;
     if (h->cap_v > 0 || h->cap_t > 0) {
         rc = enqueue_emit(h);

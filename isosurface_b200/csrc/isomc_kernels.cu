@@ -394,7 +394,8 @@ constexpr int RX = 33, RY = BY + 1, RZ = BZ + 1; /* region extents in cells */
 constexpr int NREGION = RX * RY * RZ;
 constexpr int NTASK = RZ * RY;                   /* region rows = P1 tasks, one per lane */
 constexpr int NROWS_OWN = BY * BZ;
-constexpr int TRI_CAP = 320;                     /* triangles per pass; two rows (2 * 32 * 5) always fit */
+constexpr int TRI_CAP = 384;                     /* triangles listed per pass; one row (32 * 5) always fits */
+constexpr int CELL_CAP = 192;                    /* active cells per pass; one region layer (5 * 33) always fits */
 static_assert(NTASK <= 32 && NREGION <= 1024 && NROWS_OWN <= 32, "one task per lane; list entry bit fields");
 
 struct __align__(16) SegDesc {
@@ -408,7 +409,7 @@ struct __align__(16) SegDesc {
 
 struct WarpShared {
     SegDesc seg[NTASK];
-    uint32_t cellmap[NREGION];    /* task | i << 5 | x-halo << 10 | ci' << 11 | triangles of earlier cells of the segment << 19 */
+    uint32_t cellmap[CELL_CAP];   /* task | i << 5 | x-halo << 10 | ci' << 11 | triangles of earlier cells of the segment << 19 */
     uint32_t trilist[TRI_CAP];    /* region pos (10) | ci' << 10 | t << 18 | task << 21 */
     uint32_t rowbase[NTASK];      /* id (before vofs) at the start of each region row; virtual rows: clamped row */
     uint16_t plane[3 * NREGION];  /* id of the x / y / z edge created by (virtual) cell, relative to rowbase of its row */
@@ -558,17 +559,33 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                 const uint32_t hx = (row_ok && s > 0 && both != 0 && both != 255) ? 1u : 0u; /* x-halo cell active */
                 const uint32_t nt_seg = spn - (sp >> 16);
 
-                /* own rows listed per pass: all 16, then 4 (one layer), then 2 rows if too dense */
-                int lo = 0, level = 0;
-                bool first = true;
+                /* pass plan.  Usually everything fits one pass: fill the id planes for the whole region and list all
+                 * own rows.  A dense brick is done in pieces: one fill pass per region layer, then list passes over the
+                 * own rows (a layer at a time if it fits the lists, else a row at a time; one row always fits). */
+                const uint32_t my_cells = (uint32_t)__popc(act);
+                const uint32_t my_tris = (own_row && act) ? nt_seg : 0u;
+                const bool cells_fit = __reduce_add_sync(0xFFFFFFFFu, my_cells + hx) <= CELL_CAP;
+                const bool simple = cells_fit && __reduce_add_sync(0xFFFFFFFFu, my_tris) <= TRI_CAP;
+                const int n_fill = cells_fit ? 1 : RZ; /* fill passes of the piecewise plan */
+                int pass = 0, lo = 0;
                 for (;;) {
-                    const int hi = min(NROWS_OWN, lo + (level == 0 ? NROWS_OWN : level == 1 ? BY : 2));
-                    const bool listed = own_row && t_q >= lo && t_q < hi && act != 0;
-                    const bool part = first ? ((act | hx) != 0) : listed; /* takes part in this pass */
+                    bool part, listed, with_hx;
+                    int hi = lo;
+                    if (simple) {
+                        part = (act | hx) != 0; with_hx = true; listed = own_row && act != 0;
+                    } else if (pass < n_fill) {
+                        part = has_task && (cells_fit || t_rz == pass) && (act | hx) != 0; with_hx = true; listed = false;
+                    } else {
+                        const bool g4 = own_row && act != 0 && t_q >= lo && t_q < lo + BY;
+                        const bool fits = __reduce_add_sync(0xFFFFFFFFu, g4 ? my_cells : 0u) <= CELL_CAP &&
+                                          __reduce_add_sync(0xFFFFFFFFu, g4 ? my_tris : 0u) <= TRI_CAP;
+                        hi = fits ? lo + BY : lo + 1;
+                        listed = own_row && act != 0 && t_q >= lo && t_q < hi;
+                        part = listed; with_hx = false;
+                    }
                     uint32_t n_cells, n_tri;
-                    const uint32_t cpos = warp_excl_scan(part ? (uint32_t)__popc(act) + (first ? hx : 0u) : 0u, lane, n_cells);
+                    const uint32_t cpos = warp_excl_scan(part ? my_cells + (with_hx ? hx : 0u) : 0u, lane, n_cells);
                     const uint32_t tch = warp_excl_scan(listed ? nt_seg : 0u, lane, n_tri);
-                    const bool ovf = n_tri > TRI_CAP;
                     __syncwarp();
                     if (part) {
                         SegDesc &D = W.seg[lane];
@@ -576,7 +593,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                         D.vbase = pv + (sp & 0xFFFFu);
                         D.tseg = pt + (sp >> 16);
                         D.cpos_tch = cpos | tch << 16;
-                        D.info = (r == 0 ? 1u : 0u) | (gz == 0 ? 2u : 0u) | ((listed && !ovf) ? 4u : 0u) | (s == 0 ? 8u : 0u) | both << 4;
+                        D.info = (r == 0 ? 1u : 0u) | (gz == 0 ? 2u : 0u) | (listed ? 4u : 0u) | (s == 0 ? 8u : 0u) | both << 4;
                         uint32_t k = cpos, tpre = 0, m = act;
                         while (m) { /* expansion: one store per active cell (cube index + triangles of the earlier cells) */
                             const uint32_t i = __ffs(m) - 1;
@@ -586,7 +603,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                             W.cellmap[k++] = lane | i << 5 | ci << 11 | tpre << 19;
                             if (listed) tpre += S.ntri[ci];
                         }
-                        if (first && hx) W.cellmap[k] = lane | 1u << 10;
+                        if (with_hx && hx) W.cellmap[k] = lane | 1u << 10;
                     }
                     __syncwarp();
 
@@ -669,36 +686,34 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                     }
                     __syncwarp();
 
-                    if (!ovf) {
-                        /* ---------------- B: one lane per triangle ---------------- */
-                        for (uint32_t base = 0; base < n_tri; base += 32) {
-                            const uint32_t j = base + lane;
-                            if (j < n_tri) {
-                                const uint32_t ent = W.trilist[j];
-                                const int cp = (int)(ent & 1023u);
-                                const uint32_t ci = (ent >> 10) & 255u, t = (ent >> 18) & 7u, task = ent >> 21;
-                                const uint32_t edges = (uint32_t)(S.tri[ci] >> (12 * t));
-                                const uint32_t k0 = (uint32_t)S.look[edges & 15u], k1 = (uint32_t)S.look[(edges >> 4) & 15u], k2 = (uint32_t)S.look[(edges >> 8) & 15u];
-                                const int cq = cp - 4096;
-                                const uint32_t i0 = W.rowbase[task - (k0 >> 16)] + W.plane[cq + (int)(k0 & 0xFFFFu)];
-                                const uint32_t i1 = W.rowbase[task - (k1 >> 16)] + W.plane[cq + (int)(k1 & 0xFFFFu)];
-                                const uint32_t i2 = W.rowbase[task - (k2 >> 16)] + W.plane[cq + (int)(k2 & 0xFFFFu)];
-                                const SegDesc &D = W.seg[task];
-                                const uint32_t tslot = D.tseg + (j - (D.cpos_tch >> 16)) - ghostT;
-                                if (tslot < cap_t) {
-                                    uint32_t *o = idx + (uint64_t)tslot * 3;
-                                    o[0] = i0; o[1] = i1; o[2] = i2;
-                                }
+                    /* ---------------- B: one lane per triangle ---------------- */
+                    for (uint32_t base = 0; base < n_tri; base += 32) {
+                        const uint32_t j = base + lane;
+                        if (j < n_tri) {
+                            const uint32_t ent = W.trilist[j];
+                            const int cp = (int)(ent & 1023u);
+                            const uint32_t ci = (ent >> 10) & 255u, t = (ent >> 18) & 7u, task = ent >> 21;
+                            const uint32_t edges = (uint32_t)(S.tri[ci] >> (12 * t));
+                            const uint32_t k0 = (uint32_t)S.look[edges & 15u], k1 = (uint32_t)S.look[(edges >> 4) & 15u], k2 = (uint32_t)S.look[(edges >> 8) & 15u];
+                            const int cq = cp - 4096;
+                            const uint32_t i0 = W.rowbase[task - (k0 >> 16)] + W.plane[cq + (int)(k0 & 0xFFFFu)];
+                            const uint32_t i1 = W.rowbase[task - (k1 >> 16)] + W.plane[cq + (int)(k1 & 0xFFFFu)];
+                            const uint32_t i2 = W.rowbase[task - (k2 >> 16)] + W.plane[cq + (int)(k2 & 0xFFFFu)];
+                            const SegDesc &D = W.seg[task];
+                            const uint32_t tslot = D.tseg + (j - (D.cpos_tch >> 16)) - ghostT;
+                            if (tslot < cap_t) {
+                                uint32_t *o = idx + (uint64_t)tslot * 3;
+                                o[0] = i0; o[1] = i1; o[2] = i2;
                             }
                         }
+                    }
+                    __syncwarp();
+                    if (simple) break;
+                    if (pass >= n_fill) {
                         lo = hi;
                         if (lo >= NROWS_OWN) break;
-                    } else {
-                        if (level == 2) break; /* cannot happen (two rows always fit); never spin */
-                        ++level;               /* too dense: list fewer rows per pass (the id planes are filled) */
                     }
-                    first = false;
-                    __syncwarp();
+                    ++pass;
                 }
                 __syncwarp();
             }
