@@ -3,18 +3,21 @@
  *
  * Pipeline (one stream, no host round trip in steady state):
  *
- *   K1 k_sign<Src>   sample -> inside bit.  One bit per lattice point (`!(v > 0)`,
- *                    marching_cubes_impl.rs:32 / distance.rs:52-54), packed 32 per word with a
- *                    warp ballot.  Grid sources stream every f32 exactly once (HBM bound);
- *                    implicit sources evaluate the SDF program instead of loading.
- *   K2 k_count       per 32-cell segment: bit-parallel classification.  Crossed-edge masks are
- *                    XORs of sign words, the "edges this cell creates" count is a bit-sliced sum
- *                    of the owned masks, triangle counts come from ntri[ci'] for active cells
- *                    only.  Writes within-row exclusive prefixes per segment and row totals.
- *   K3 k_scan_rows   exclusive scan over cell rows in (z, y) order (+ totals).
- *   K4 k_emit<Src>   bricks of 128x8x4 cells: compacts active cells, interpolates each owned
- *                    edge once (edge ownership replaces the reference's HashMap index cache,
- *                    index_cache.rs / mesh.rs:240-251) and writes u32 indices in reference order.
+ *   K1 k_sign_vec4 / k_sign<Src>
+ *                    sample -> inside bit.  One bit per lattice point (`!(v > 0)`,
+ *                    marching_cubes_impl.rs:32 / distance.rs:52-54), 32 per word.  Grid sources
+ *                    stream every f32 exactly once as float4s (HBM bound); implicit sources evaluate
+ *                    the SDF program instead of loading.
+ *   K2 k_count       warp-autonomous, lane per 32-cell segment: bit-parallel classification.
+ *                    Crossed-edge masks are XORs of sign words, the "edges this cell creates" count
+ *                    is a bit-sliced sum of the owned masks, triangle counts come from ntri[ci'] for
+ *                    active cells only.  Writes within-row exclusive prefixes and row totals.
+ *   K3 k_scan_rows   exclusive scan over cell rows in (z, y) order (+ totals); causal in z.
+ *   K4 k_emit        warp-autonomous bricks of 32x4x4 cells: flat cell and triangle lists, 16-bit
+ *                    id planes in shared memory (edge ownership replaces the reference's HashMap
+ *                    index cache, index_cache.rs / mesh.rs:240-251); writes u32 indices in reference
+ *                    order and one 12-byte descriptor per created vertex.
+ *   K5 k_vertex<Src> descriptor -> position (distance.rs:64-69), in place.
  *
  * Vertex numbering = reference numbering: id(cell, e) = (# vertices created by earlier cells in
  * (z,y,x) order) + (# edges the cell creates that precede e in first-appearance order of its
