@@ -7,10 +7,12 @@ A "step" is one full `extract` of the workload's field: device-resident dense f3
 implicit SDF program) in, device-resident globally-indexed mesh (xyz f32 + u32 indices) out.
 
 Workloads (BASELINE.json configs / SURVEY.md 8d):
-    fbm512       512^3 dense f32 grid, random-phase fBm (C3) -- default at --gpus 1 (headline)
+    fbm512       512^3 dense f32 grid, random-phase fBm (C3) -- the default at --gpus 1 (headline)
+    fbmweak      default at --gpus N > 1: the same fBm family with 512^3 voxels PER GPU (size 644 / 812 / 1024
+                 for N = 2 / 4 / 8, same surface density), z-slab sharded: weak scaling
     gyroid1024   1024^3 dense f32 grid, gyroid (C4)
-    spheres2048  2048^3 dense f32 grid, union of 64 spheres (C5) -- default at --gpus > 1, z-slab
-                 sharded, strong scaling (total work fixed)
+    spheres2048  2048^3 dense f32 grid, union of 64 spheres (C5); `--workload spheres2048 --gpus N` is the
+                 strong-scaling sweep of the north star (recorded in profiles/r01_scale_spheres2048.json)
     torus256 / csga256 / csgb256   256^3 implicit SDF evaluated on device (C2)
     sphere32 / torus128            the reference's CPU-sized cases (C1a / C1b)
 
@@ -39,6 +41,9 @@ WORKLOADS = {
     # name: (size, kind, field/source, seed)
     "fbm512": (512, "grid", "fbm", 0x1505F00D),
     "fbm256": (256, "grid", "fbm", 0x1505F00D),
+    "fbm644": (644, "grid", "fbm", 0x1505F00D),    # 2 x 512^3 voxels
+    "fbm812": (812, "grid", "fbm", 0x1505F00D),    # 4 x 512^3 voxels
+    "fbm1024": (1024, "grid", "fbm", 0x1505F00D),  # 8 x 512^3 voxels
     "gyroid1024": (1024, "grid", "gyroid", 0),
     "gyroid512": (512, "grid", "gyroid", 0),
     "spheres2048": (2048, "grid", "spheres", 0x5EEDBA11),
@@ -193,7 +198,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "MarchingCubes Gvoxels/s", "value": v, "unit": "Gvoxels/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": vox_per_step / (v * 1e9) * 1e3, "higher_is_better": True,
-            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak" if (args.gpus == 1 or args.weak) else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "mtris_per_s": float(np.mean([x["mtris_per_s"] for x in vals])),
             "config": {"workload": wl, "size": size, "note": "ms_per_step extrapolated from the bounded sample to the full grid"},
             "cpu_baseline": {"value": v, "unit": "Gvoxels/s", "cores": 1, "kind": "port", "sample": last["sample"]},
@@ -320,7 +325,7 @@ def run_ours(args):
     line = {
         "metric": "MarchingCubes Gvoxels/s", "value": value, "unit": "Gvoxels/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak" if (world == 1 or args.weak) else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "mtris_per_s": T / t_s / 1e6, "gcells_per_s": float(size - 1) ** 2 * size / t_s / 1e9,
         "config": {"workload": wl, "size": size, "source": kind, "vertices": V, "triangles": T, "active_cells": A,
                    "active_fraction": A / (float(size - 1) ** 2 * size), "parallelism": "zslab%d" % world,
@@ -360,7 +365,9 @@ def run_ours(args):
     line["clocks"] = clk.summary()
 
     # ---- e2e through the public API with HOST buffers (H2D of the grid + D2H of the mesh inside the timed region)
-    if world == 1 and rank == 0 and not args.no_e2e:
+    if world == 1 and rank == 0 and not args.no_e2e and 4 * S > (8 << 30):
+        line["e2e"] = None  # a > 8 GiB pinned host copy of the grid is not attempted
+    elif world == 1 and rank == 0 and not args.no_e2e:
         mc = iso.MarchingCubes(size, device=local)
         if kind == "grid":
             hgrid = torch.empty(grid.numel(), dtype=torch.float32, pin_memory=True)
@@ -423,8 +430,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
-    if args.workload == "auto":
-        args.workload = "fbm512" if args.gpus == 1 else "spheres2048"
+    args.weak = args.workload == "auto"
+    if args.workload == "auto":  # 512^3 voxels per GPU of the same fBm family (weak scaling); fbm512 at N = 1
+        args.workload = {1: "fbm512", 2: "fbm644", 4: "fbm812", 8: "fbm1024"}.get(args.gpus, "fbm1024")
     if args.impl == "reference":
         run_reference(args)
     else:

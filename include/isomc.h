@@ -157,7 +157,8 @@ int32_t isomc_debug_sample_sdf(int32_t device, const isomc_sdf_node *prog, uint3
 
 /* ---- synthetic fields used by bench.py and the tests ---------------------- */
 enum { ISOMC_FIELD_FBM = 1, ISOMC_FIELD_GYROID = 2, ISOMC_FIELD_SPHERE_UNION = 3 };
-/* fills sample layers [z_first, z_first + n_layers) of the size*size*(size+1) lattice into d_out */
+/* fills sample layers [z_first, z_first + n_layers) of the size*size*(size+1) lattice into d_out.
+ * FBM: 5 octaves x 4 random-phase waves, 4*2^o periods per unit length at size 512, scaled by (size-1)/511. */
 int32_t isomc_synth_field(int32_t device, int32_t kind, uint32_t size, uint64_t seed,
                           uint32_t z_first, uint32_t n_layers, float *d_out);
 

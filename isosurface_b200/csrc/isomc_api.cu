@@ -694,7 +694,9 @@ int32_t isomc_synth_field(int32_t device, int32_t kind, uint32_t size, uint64_t 
                 sp.dx[w] = dx / len; sp.dy[w] = dy / len; sp.dz[w] = dz / len;
                 sp.ph[w] = 6.283185307179586f * unit24(&st);
                 sp.amp[w] = 1.0f / (float)(1 << o);
-                sp.freq[w] = 6.283185307179586f * 4.0f * (float)(1 << o);
+                /* 4 * 2^o periods per unit length at 512^3; scaled with the lattice so that the
+                 * finest wave stays 8 samples long at other sizes (constant surface density: weak-scaling runs) */
+                sp.freq[w] = 6.283185307179586f * 4.0f * (float)(1 << o) * ((float)(size - 1) / 511.0f);
             }
     } else if (kind == ISOMC_FIELD_SPHERE_UNION) {
         for (int s = 0; s < 64; ++s) {
