@@ -318,3 +318,48 @@ def test_full_size_slabs_equal_unsharded_1024(iso):
     assert vo == len(xyz) and io == len(idx)
     facts = mesh_invariants(xyz, idx, closed=False)
     assert facts["directed_edge_dups"] == 0
+
+
+def test_zchunk_pipeline_mode_is_bit_identical(iso, oracle, monkeypatch):
+    """ISOMC_PIPELINE=1 (two-stream z-chunk pipeline, off by default) must give the same bytes"""
+    size = 160
+    t = synth(iso, 1, size, 5)
+    mc = iso.MarchingCubes(size)
+    mc.extract_device(iso.DenseGrid(t))
+    ref = [a.tobytes() for a in mc.copy_out()]
+    mc.close()
+    monkeypatch.setenv("ISOMC_PIPELINE", "1")
+    mp = iso.MarchingCubes(size)          # the environment is read at create
+    for _ in range(3):                    # first extract sizes the buffers, the next ones emit inline per chunk
+        mp.extract_device(iso.DenseGrid(t))
+        assert [a.tobytes() for a in mp.copy_out()] == ref
+    assert mp.stats()["kernel_launches"] > 6
+    mp.close()
+    host = t.cpu().numpy().reshape(size + 1, size, size)
+    oxyz, oidx, _ = oracle.extract_grid(size, host)
+    assert ref[1] == oidx.tobytes() and ref[0] == oxyz.tobytes()
+
+
+def test_non_multiple_of_four_size_uses_generic_sign_kernel(iso, oracle):
+    """N % 4 != 0 (or a misaligned pointer) takes the scalar k_sign path instead of the float4 one"""
+    import torch
+    for size in (66, 67, 131):
+        t = synth(iso, 3, size, 9)
+        host = t.cpu().numpy().reshape(size + 1, size, size)
+        oxyz, oidx, _ = oracle.extract_grid(size, host)
+        mc = iso.MarchingCubes(size)
+        mc.extract_device(iso.DenseGrid(t))
+        xyz, idx = mc.copy_out()
+        assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+        mc.close()
+    # misaligned device pointer with N % 4 == 0
+    size = 64
+    buf = torch.empty(size * size * (size + 1) + 1, dtype=torch.float32, device="cuda:0")
+    t = synth(iso, 1, size, 2)
+    buf[1:].copy_(t)
+    mc = iso.MarchingCubes(size)
+    mc.extract_device(iso.DenseGrid(buf.data_ptr() + 4, size=size, on_device=True))
+    xyz, idx = mc.copy_out()
+    oxyz, oidx, _ = oracle.extract_grid(size, t.cpu().numpy().reshape(size + 1, size, size))
+    assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    mc.close()
