@@ -363,3 +363,14 @@ def test_non_multiple_of_four_size_uses_generic_sign_kernel(iso, oracle):
     oxyz, oidx, _ = oracle.extract_grid(size, t.cpu().numpy().reshape(size + 1, size, size))
     assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
     mc.close()
+
+
+def test_randomised_stress_subset():
+    """40 cases of tools/gpu_stress.py (random sizes, densities, boundary-aligned fields, random slab counts);
+    the full 400-case run is recorded in profiles/r01_sanitizer.txt"""
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "tools" / "gpu_stress.py"), "40", "123"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "40 cases, 0 failures" in r.stdout
