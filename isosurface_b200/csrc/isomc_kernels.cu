@@ -397,8 +397,8 @@ constexpr int RX = 33, RY = BY + 1, RZ = BZ + 1; /* region extents in cells */
 constexpr int NREGION = RX * RY * RZ;
 constexpr int NTASK = RZ * RY;                   /* region rows = P1 tasks, one per lane */
 constexpr int NROWS_OWN = BY * BZ;
-constexpr int TRI_CAP = 384;                     /* triangles listed per pass; one row (32 * 5) always fits */
-constexpr int CELL_CAP = 192;                    /* active cells per pass; one region layer (5 * 33) always fits */
+constexpr int TRI_CAP = 1024;                    /* triangles listed per pass; one row (32 * 5) always fits */
+constexpr int CELL_CAP = 512;                    /* active cells per pass; one region layer (5 * 33) always fits */
 static_assert(NTASK <= 32 && NREGION <= 1024 && NROWS_OWN <= 32, "one task per lane; list entry bit fields");
 
 struct __align__(16) SegDesc {
@@ -445,7 +445,7 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, ui
     return inc - v;
 }
 
-__global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__restrict__ signs,
+__global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(Geo g, const uint32_t *__restrict__ signs,
                                                       const uint32_t *__restrict__ segpre,
                                                       const uint32_t *__restrict__ rowPV,
                                                       const uint32_t *__restrict__ rowPT,
@@ -519,30 +519,46 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
             uint32_t has = 0;
             {
                 const uint32_t sb = s0 + lane;
+#pragma unroll 4
                 for (int q = 0; q < NROWS_OWN; ++q) {
                     const int ql = lz0 + q / BY, qr = y0 + q % BY;
-                    if (ql < first_own_layer || ql >= (int)g.ncl || qr >= (int)g.ncx || sb >= g.nsegx) continue;
-                    const uint32_t qrow = (uint32_t)ql * g.ncx + (uint32_t)qr;
-                    const uint32_t t0 = __ldg(segpre + (uint64_t)qrow * g.nsegx + sb) >> 16;
-                    const uint32_t t1 = sb + 1 < g.nsegx ? __ldg(segpre + (uint64_t)qrow * g.nsegx + sb + 1) >> 16 : rowPT[qrow + 1] - rowPT[qrow];
-                    has |= t1 ^ t0;
+                    const bool ok = ql >= first_own_layer && ql < (int)g.ncl && qr < (int)g.ncx && sb < g.nsegx;
+                    const uint32_t qrow = ok ? (uint32_t)ql * g.ncx + (uint32_t)qr : 0u;
+                    const uint32_t *qp = segpre + (uint64_t)qrow * g.nsegx + (ok ? sb : 0u);
+                    const uint32_t t0 = __ldg(qp) >> 16;
+                    const uint32_t t1 = (ok && sb + 1 < g.nsegx) ? __ldg(qp + 1) >> 16 : rowPT[qrow + 1] - rowPT[qrow];
+                    if (ok) has |= t1 ^ t0;
                 }
             }
             uint32_t todo = __ballot_sync(0xFFFFFFFFu, has != 0);
-            while (todo) {
-                const uint32_t s = s0 + (uint32_t)__ffs(todo) - 1;
-                todo &= todo - 1;
-
-                /* ---------------- P1 loads (independent of the pass) ---------------- */
-                uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0, sp = 0, spn = 0, prevbits = 0;
-                if (row_ok) {
-                    const uint32_t *wa = my_signs + s, *wb = wa + g.nws, *wc = wa + (size_t)g.N * g.nws, *wd = wc + g.nws;
-                    a0 = __ldg(wa); a1 = __ldg(wa + 1); b0 = __ldg(wb); b1 = __ldg(wb + 1);
-                    c0 = __ldg(wc); c1 = __ldg(wc + 1); d0 = __ldg(wd); d1 = __ldg(wd + 1);
-                    sp = __ldg(my_sp + s);
-                    spn = s + 1 < g.nsegx ? __ldg(my_sp + s + 1) >> 16 : ptn - pt;
-                    if (s > 0) prevbits = (__ldg(wa - 1) >> 31) | (__ldg(wb - 1) >> 31) << 1 | (__ldg(wc - 1) >> 31) << 2 | (__ldg(wd - 1) >> 31) << 3;
+            if (todo == 0) continue;
+            /* software pipeline over the bricks with work: the sign words / prefixes of the NEXT brick are loaded
+             * while the current one is processed, so their L2 latency is hidden behind a whole brick of work */
+            uint32_t n_s = s0 + (uint32_t)__ffs(todo) - 1;
+            todo &= todo - 1;
+            uint32_t na0 = 0, na1 = 0, nb0 = 0, nb1 = 0, nc0 = 0, nc1 = 0, nd0 = 0, nd1 = 0, nsp = 0, nspn = 0, npw = 0;
+#define ISOMC_BRICK_LOADS(S_)                                                                                              \
+    if (row_ok) {                                                                                                          \
+        const uint32_t *wa = my_signs + (S_), *wb = wa + g.nws, *wc = wa + (size_t)g.N * g.nws, *wd = wc + g.nws;          \
+        na0 = __ldg(wa); na1 = __ldg(wa + 1); nb0 = __ldg(wb); nb1 = __ldg(wb + 1);                                        \
+        nc0 = __ldg(wc); nc1 = __ldg(wc + 1); nd0 = __ldg(wd); nd1 = __ldg(wd + 1);                                        \
+        nsp = __ldg(my_sp + (S_));                                                                                         \
+        nspn = (S_) + 1 < g.nsegx ? __ldg(my_sp + (S_) + 1) >> 16 : ptn - pt;                                              \
+        npw = 0;                                                                                                           \
+        if ((S_) > 0) npw = (__ldg(wa - 1) >> 31) | (__ldg(wb - 1) >> 31) << 1 | (__ldg(wc - 1) >> 31) << 2 | (__ldg(wd - 1) >> 31) << 3; \
+    }
+            ISOMC_BRICK_LOADS(n_s)
+            for (bool more = true; more;) {
+                const uint32_t s = n_s;
+                const uint32_t a0 = na0, a1 = na1, b0 = nb0, b1 = nb1, c0 = nc0, c1 = nc1, d0 = nd0, d1 = nd1;
+                const uint32_t sp = nsp, spn = nspn, prevbits = npw;
+                more = todo != 0;
+                if (more) {
+                    n_s = s0 + (uint32_t)__ffs(todo) - 1;
+                    todo &= todo - 1;
+                    ISOMC_BRICK_LOADS(n_s)
                 }
+
                 uint32_t act = 0;
                 uint4 pl = make_uint4(0, 0, 0, 0);
                 {
@@ -720,6 +736,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(Geo g, const uint32_t *__
                 }
                 __syncwarp();
             }
+#undef ISOMC_BRICK_LOADS
         }
     }
 }
