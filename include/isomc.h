@@ -151,7 +151,8 @@ int32_t isomc_slab_emit_gathered(isomc_t *h, const uint64_t *d_gathered, uint32_
 /* per-cell cube_index in the reference's corner order (marching_cubes_impl.rs:26-37) for the
  * last extract: (N-1)*(N-1)*N bytes to host memory, x fastest */
 int32_t isomc_debug_cube_indices(isomc_t *h, uint8_t *host_out);
-/* evaluate an SDF program on the device at n points (xyz packed) -> host values */
+/* evaluate an SDF program on the device at n points (xyz packed) -> host values.  n_nodes | 0x80000000 evaluates
+ * through the chain fast path the extract kernels use for left-deep trees (ISOMC_ERR_CUDA if the program has none) */
 int32_t isomc_debug_sample_sdf(int32_t device, const isomc_sdf_node *prog, uint32_t n_nodes,
                                const float *h_xyz, uint64_t n_points, float *h_out);
 

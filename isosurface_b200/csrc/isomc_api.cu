@@ -647,6 +647,8 @@ int32_t isomc_debug_cube_indices(isomc_t *h, uint8_t *host_out) {
 
 int32_t isomc_debug_sample_sdf(int32_t device, const isomc_sdf_node *prog, uint32_t n_nodes, const float *h_xyz,
                                uint64_t n_points, float *h_out) {
+    const int use_chain = (n_nodes & 0x80000000u) != 0;
+    n_nodes &= 0x7FFFFFFFu;
     SdfProgram P;
     int32_t rc = validate_program(nullptr, prog, n_nodes, &P);
     if (rc) return rc;
@@ -657,7 +659,8 @@ int32_t isomc_debug_sample_sdf(int32_t device, const isomc_sdf_node *prog, uint3
     CU(nullptr, cudaMalloc(&dx, n_points * 12));
     cudaError_t e = cudaMalloc(&dout, n_points * 4);
     if (e == cudaSuccess) e = cudaMemcpy(dx, h_xyz, n_points * 12, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = isomc_launch_sample_sdf(P, dx, n_points, dout, 0);
+    /* device < 0 is not allowed; the high bit of n_nodes selects the chain evaluator (tests compare both) */
+    if (e == cudaSuccess) e = isomc_launch_sample_sdf(P, dx, n_points, dout, use_chain, 0);
     if (e == cudaSuccess) e = cudaMemcpy(h_out, dout, n_points * 4, cudaMemcpyDeviceToHost);
     cudaFree(dx); cudaFree(dout);
     if (e != cudaSuccess) return fail(nullptr, ISOMC_ERR_CUDA, "sdf sampling failed: %s", cudaGetErrorString(e));

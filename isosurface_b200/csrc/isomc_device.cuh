@@ -90,6 +90,104 @@ __device__ __forceinline__ float sdf_eval(const SdfProgram &P, float px, float p
     return s0;
 }
 
+/*
+ * Chain form of an SDF program: ((L0 op0 L1) op1 L2) ... -- every tree the reference's demos build
+ * (examples/sampler.rs:70-95) is left-deep.  No stacks, no per-node dispatch beyond one switch per leaf;
+ * same arithmetic, same operation order as sdf_eval.  Built on the host by sdf_to_chain(); programs that
+ * are not left-deep (or nest more than two translations around a leaf) keep the generic interpreter.
+ */
+#define ISOMC_CHAIN_MAX_LEAVES 8
+struct SdfLeaf {
+    uint32_t type;      /* ISOMC_SDF_SPHERE .. PRISM */
+    float a, b, c;
+    uint32_t n_off;     /* translations around this leaf, outermost first (applied in that order) */
+    float off[2][3];
+    uint32_t op;        /* how this leaf combines with the chain so far (unused for leaf 0) */
+};
+struct SdfChain {
+    SdfLeaf leaf[ISOMC_CHAIN_MAX_LEAVES];
+    uint32_t n;
+};
+
+__device__ __forceinline__ float sdf_leaf(const SdfLeaf &L, float px, float py, float pz) {
+    if (L.n_off > 0) { px = __fsub_rn(px, L.off[0][0]); py = __fsub_rn(py, L.off[0][1]); pz = __fsub_rn(pz, L.off[0][2]); }
+    if (L.n_off > 1) { px = __fsub_rn(px, L.off[1][0]); py = __fsub_rn(py, L.off[1][1]); pz = __fsub_rn(pz, L.off[1][2]); }
+    switch (L.type) {
+    case ISOMC_SDF_SPHERE:
+        return __fsub_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz))), L.a);
+    case ISOMC_SDF_TORUS: {
+        const float qx = __fsub_rn(fabsf(__fsqrt_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)))), L.a);
+        return __fsub_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(pz, pz))), L.b);
+    }
+    case ISOMC_SDF_CYLINDER: {
+        const float qx = __fsub_rn(fabsf(__fsqrt_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)))), L.a);
+        const float qz = __fsub_rn(fabsf(pz), L.b);
+        const float dx = fmaxf(qx, 0.0f), dy = fmaxf(qz, 0.0f);
+        const float dl = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(0.0f, 0.0f)));
+        return __fadd_rn(fminf(fmaxf(qx, qz), 0.0f), dl);
+    }
+    default: { /* ISOMC_SDF_PRISM */
+        const float qx = __fsub_rn(fabsf(px), L.a), qy = __fsub_rn(fabsf(py), L.b), qz = __fsub_rn(fabsf(pz), L.c);
+        const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f), mz = fmaxf(qz, 0.0f);
+        const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(mx, mx), __fmul_rn(my, my)), __fmul_rn(mz, mz)));
+        return __fadd_rn(len, fminf(fmaxf(qx, fmaxf(qy, qz)), 0.0f));
+    }
+    }
+}
+
+__device__ __forceinline__ float sdf_chain_eval(const SdfChain &C, float px, float py, float pz) {
+    float acc = sdf_leaf(C.leaf[0], px, py, pz);
+    for (uint32_t i = 1; i < C.n; ++i) {
+        const float v = sdf_leaf(C.leaf[i], px, py, pz);
+        const uint32_t op = C.leaf[i].op;
+        acc = op == ISOMC_SDF_UNION ? fminf(acc, v) : op == ISOMC_SDF_INTERSECTION ? fmaxf(acc, v) : fmaxf(v, -acc);
+    }
+    return acc;
+}
+
+/* host: postfix program -> chain; false if the program is not a left-deep chain */
+static inline bool sdf_to_chain(const SdfProgram &P, SdfChain *out) {
+    float offs[ISOMC_TR_DEPTH][3];
+    int n_off = 0, depth = 0; /* depth: values on the stack (1 = chain so far, 2 = chain + pending leaf) */
+    SdfChain C;
+    C.n = 0;
+    for (uint32_t i = 0; i < P.n; ++i) {
+        const isomc_sdf_node &nd = P.nodes[i];
+        switch (nd.op) {
+        case ISOMC_SDF_SPHERE: case ISOMC_SDF_TORUS: case ISOMC_SDF_CYLINDER: case ISOMC_SDF_PRISM: {
+            if (depth >= 2 || C.n >= ISOMC_CHAIN_MAX_LEAVES || n_off > 2) return false;
+            if (depth == 1 && C.n == 0) return false;
+            SdfLeaf &L = C.leaf[C.n++];
+            L.type = nd.op; L.a = nd.a; L.b = nd.b; L.c = nd.c; L.op = 0;
+            L.n_off = (uint32_t)n_off;
+            for (int k = 0; k < 2; ++k)
+                for (int j = 0; j < 3; ++j) L.off[k][j] = k < n_off ? offs[k][j] : 0.0f;
+            ++depth;
+        } break;
+        case ISOMC_SDF_UNION: case ISOMC_SDF_INTERSECTION: case ISOMC_SDF_DIFFERENCE:
+            if (depth != 2 || C.n < 2) return false;
+            C.leaf[C.n - 1].op = nd.op; /* (chain, leaf): first-pushed = chain = field `a` */
+            depth = 1;
+            break;
+        case ISOMC_SDF_TRANSLATE_PUSH:
+            /* a translation opened while a chain value is pending would have to apply to later leaves only: fine,
+             * but one opened around an already-combined value cannot be expressed -> only leaves inherit offsets */
+            if (n_off >= ISOMC_TR_DEPTH) return false;
+            offs[n_off][0] = nd.a; offs[n_off][1] = nd.b; offs[n_off][2] = nd.c;
+            ++n_off;
+            break;
+        case ISOMC_SDF_TRANSLATE_POP:
+            if (n_off <= 0) return false;
+            --n_off;
+            break;
+        default: return false;
+        }
+    }
+    if (depth != 1 || C.n < 1) return false;
+    *out = C;
+    return true;
+}
+
 /* Sources as seen by the kernels: value at lattice point (x, y, local layer lz / global gz). */
 struct GridSrc {
     const float *__restrict__ p; /* first sample layer of the handle's slab */
@@ -103,6 +201,13 @@ struct SdfSrc {
         /* primal_grid.rs:50,63-67: (i as f32) * one_over_size */
         return sdf_eval(prog, __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv),
                         __fmul_rn((float)(g.gz0 + lz), g.inv));
+    }
+};
+struct SdfChainSrc {
+    SdfChain chain;
+    __device__ __forceinline__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
+        return sdf_chain_eval(chain, __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv),
+                              __fmul_rn((float)(g.gz0 + lz), g.inv));
     }
 };
 

@@ -820,6 +820,11 @@ __global__ void k_sample_sdf(SdfProgram prog, const float *__restrict__ xyz, uin
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
         out[i] = sdf_eval(prog, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
 }
+/* same points through the chain evaluator (when the program has a chain form): out2 must equal out bit for bit */
+__global__ void k_sample_sdf_chain(SdfChain chain, const float *__restrict__ xyz, uint64_t n, float *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = sdf_chain_eval(chain, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+}
 
 /* ------------------------------------------------------------------------------------------ */
 /* synthetic fields (bench / tests only)                                          */
@@ -878,8 +883,13 @@ cudaError_t isomc_launch_sign_grid(const Geo &g, const float *d_grid, uint32_t *
 }
 cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, uint32_t *signs, uint32_t row0, uint32_t row1, int sms,
                                   int ctas_per_sm, cudaStream_t st) {
-    SdfSrc src{prog};
-    k_sign<SdfSrc><<<grid_for((uint64_t)(row1 - row0), sms, 8, ctas_per_sm), 256, 0, st>>>(src, g, signs, row0, row1);
+    SdfChainSrc csrc;
+    if (sdf_to_chain(prog, &csrc.chain)) {
+        k_sign<SdfChainSrc><<<grid_for((uint64_t)(row1 - row0), sms, 8, ctas_per_sm), 256, 0, st>>>(csrc, g, signs, row0, row1);
+    } else {
+        SdfSrc src{prog};
+        k_sign<SdfSrc><<<grid_for((uint64_t)(row1 - row0), sms, 8, ctas_per_sm), 256, 0, st>>>(src, g, signs, row0, row1);
+    }
     return cudaGetLastError();
 }
 /* cell layers [lz0, lz1) */
@@ -946,7 +956,11 @@ cudaError_t isomc_launch_vertex_grid(const Geo &g, const float *d_grid, const Mc
 cudaError_t isomc_launch_vertex_sdf(const Geo &g, const SdfProgram &prog, const McTables *tabs, const unsigned long long *layerTot,
                                     const uint32_t *rowPV, float *xyz, uint64_t cap_v, uint32_t lz0, uint32_t lz1, int sms,
                                     int ctas_per_sm, cudaStream_t st) {
-    k_vertex<SdfSrc><<<sms * ctas_per_sm, 256, 0, st>>>(SdfSrc{prog}, g, tabs, layerTot, rowPV, xyz, cap_v, lz0, lz1);
+    SdfChainSrc csrc;
+    if (sdf_to_chain(prog, &csrc.chain))
+        k_vertex<SdfChainSrc><<<sms * ctas_per_sm, 256, 0, st>>>(csrc, g, tabs, layerTot, rowPV, xyz, cap_v, lz0, lz1);
+    else
+        k_vertex<SdfSrc><<<sms * ctas_per_sm, 256, 0, st>>>(SdfSrc{prog}, g, tabs, layerTot, rowPV, xyz, cap_v, lz0, lz1);
     return cudaGetLastError();
 }
 
@@ -955,8 +969,16 @@ cudaError_t isomc_launch_cube_indices(const Geo &g, const uint32_t *signs, const
     k_cube_indices<<<sms * 8, 256, 0, st>>>(g, signs, tabs, out);
     return cudaGetLastError();
 }
-cudaError_t isomc_launch_sample_sdf(const SdfProgram &prog, const float *xyz, uint64_t n, float *out, cudaStream_t st) {
-    k_sample_sdf<<<(uint32_t)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(prog, xyz, n, out);
+/* use_chain != 0: evaluate through the chain form (returns cudaErrorInvalidValue if the program has none) */
+cudaError_t isomc_launch_sample_sdf(const SdfProgram &prog, const float *xyz, uint64_t n, float *out, int use_chain, cudaStream_t st) {
+    const uint32_t grid = (uint32_t)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
+    if (use_chain) {
+        SdfChain chain;
+        if (!sdf_to_chain(prog, &chain)) return cudaErrorInvalidValue;
+        k_sample_sdf_chain<<<grid, 256, 0, st>>>(chain, xyz, n, out);
+    } else {
+        k_sample_sdf<<<grid, 256, 0, st>>>(prog, xyz, n, out);
+    }
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_synth(const SynthParams &sp, uint32_t size, uint32_t z_first, uint32_t n_layers, float *out,

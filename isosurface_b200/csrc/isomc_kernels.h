@@ -42,7 +42,7 @@ cudaError_t isomc_launch_vertex_sdf(const Geo &g, const SdfProgram &prog, const 
                                     int ctas_per_sm, cudaStream_t st);
 cudaError_t isomc_launch_cube_indices(const Geo &g, const uint32_t *signs, const McTables *tabs, uint8_t *out, int sms,
                                       cudaStream_t st);
-cudaError_t isomc_launch_sample_sdf(const SdfProgram &prog, const float *xyz, uint64_t n, float *out, cudaStream_t st);
+cudaError_t isomc_launch_sample_sdf(const SdfProgram &prog, const float *xyz, uint64_t n, float *out, int use_chain, cudaStream_t st);
 cudaError_t isomc_launch_synth(const SynthParams &sp, uint32_t size, uint32_t z_first, uint32_t n_layers, float *out,
                                int sms, cudaStream_t st);
 #endif

@@ -69,6 +69,27 @@ def test_device_sdf_matches_oracle_bitwise(iso, isolib, oracle):
         _lib.check(isolib.isomc_debug_sample_sdf(0, prog.ctypes.data, len(prog), pts.ctypes.data, len(pts), out.ctypes.data))
         want = oracle.sample_sdf(oracle_prog(name), pts)
         assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), name
+        # the stack-free chain evaluator the extract kernels use for left-deep trees: same bits
+        out2 = np.zeros(len(pts), np.float32)
+        _lib.check(isolib.isomc_debug_sample_sdf(0, prog.ctypes.data, len(prog) | 0x80000000, pts.ctypes.data, len(pts), out2.ctypes.data))
+        assert np.array_equal(out2.view(np.uint32), want.view(np.uint32)), name + " (chain)"
+    # a right-nested tree has no chain form: the generic interpreter runs it (and the chain request is refused)
+    right = iso.Union(iso.Sphere(.2), iso.Intersection(iso.Translate(.5, iso.Sphere(.3)), iso.RectangularPrism((.2, .3, .4))))
+    prog = encode_program(right)
+    out = np.zeros(len(pts), np.float32)
+    _lib.check(isolib.isomc_debug_sample_sdf(0, prog.ctypes.data, len(prog), pts.ctypes.data, len(pts), out.ctypes.data))
+    O = oracle
+    oprog = O.program([(O.SPHERE, .2), (O.TRANSLATE_PUSH, .5, .5, .5), (O.SPHERE, .3), (O.TRANSLATE_POP,), (O.PRISM, .2, .3, .4),
+                       (O.INTERSECTION,), (O.UNION,)])
+    assert prog.tobytes() == oprog.tobytes()
+    assert np.array_equal(out.view(np.uint32), O.sample_sdf(oprog, pts).view(np.uint32))
+    assert isolib.isomc_debug_sample_sdf(0, prog.ctypes.data, len(prog) | 0x80000000, pts.ctypes.data, len(pts), out.ctypes.data) != 0
+    mc = iso.MarchingCubes(48)
+    mc.extract_device(iso.Sampler(right))
+    xyz, idx = mc.copy_out()
+    oxyz, oidx, _ = O.extract_sdf(48, oprog)
+    assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    mc.close()
 
 
 @pytest.mark.parametrize("g", GOLDEN, ids=lambda g: "%s-%d" % (g["shape"], g["size"]))
