@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "../../include/isomc.h"
+#include "isomc_cell.cuh"
 #include "isomc_device.cuh"
 #include "isomc_kernels.h"
 #include "isomc_tables.h"
@@ -26,6 +27,8 @@ thread_local std::string g_create_error;
 
 enum SrcKind { SRC_NONE = 0, SRC_GRID = 1, SRC_SDF = 2 };
 constexpr int MAX_CHUNKS = 16;
+constexpr int AUX_WORDS = 2 * MAX_CHUNKS + 4; /* u32 after layerTot: emit tickets [MAX_CHUNKS], list block counter, list marks [MAX_CHUNKS + 1] */
+constexpr int LIST_COUNT_CTAS = 4;            /* k_count_list CTAs per SM (64 registers x 256 threads) */
 
 }  // namespace
 
@@ -44,6 +47,12 @@ struct isomc {
     uint32_t *signs = nullptr, *segpre = nullptr, *rowV = nullptr, *rowT = nullptr, *rowA = nullptr;
     unsigned long long *layerTot = nullptr, *totals = nullptr; /* totals: 12 u64 */
     uint32_t *vofs = nullptr, *ticket = nullptr;
+    /* active-cell-list path (ISOMC_EMIT=list; the brick kernels are the default until it is the faster one): isomc_cell.cuh */
+    bool list_mode = false;
+    ListBufs L{};
+    uint32_t *list_marks = nullptr; /* [c] = list blocks handed out before z-chunk c; [0] = 0 */
+    EmitTab *etab = nullptr;
+    bool emit_inline = false;       /* what the extract in flight was enqueued with (re-enqueued after a list grow) */
     int64_t vofs_cached = 0; /* value known to be in *vofs (set to 0 at create); -1 = written by the device */
     McTables *tabs = nullptr;
     unsigned long long *h_totals = nullptr; /* pinned */
@@ -141,6 +150,21 @@ int32_t ensure_capacity(isomc *h, uint64_t nv, uint64_t nt) {
     return ISOMC_OK;
 }
 
+/* list of active cells: grow-only, sized from the previous extract; an overflow is detected from the block counter */
+int32_t ensure_list_capacity(isomc *h, uint64_t blocks) {
+    if (blocks <= h->L.cap_blocks) return ISOMC_OK;
+    if (blocks > 0xFFFFF0ull) return fail(h, ISOMC_ERR_OOM, "active-cell list of %llu blocks exceeds the 32-bit entry positions", (unsigned long long)blocks);
+    if (h->L.ent) CU(h, cudaFree(h->L.ent));
+    if (h->L.ent_yz) CU(h, cudaFree(h->L.ent_yz));
+    if (h->L.blkfill) CU(h, cudaFree(h->L.blkfill));
+    h->L.ent = nullptr; h->L.ent_yz = nullptr; h->L.blkfill = nullptr; h->L.cap_blocks = 0;
+    CU(h, cudaMalloc(&h->L.ent, blocks * LIST_BLOCK * sizeof(uint2)));
+    CU(h, cudaMalloc(&h->L.ent_yz, blocks * LIST_BLOCK * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&h->L.blkfill, blocks * sizeof(uint32_t)));
+    h->L.cap_blocks = (uint32_t)blocks;
+    return ISOMC_OK;
+}
+
 /*
  * The extract is cut into a few z-chunks (multiples of the emission brick height).  Everything a chunk
  * needs comes from the chunks below it (the row scan is causal in z), which allows a two-stage pipeline:
@@ -178,6 +202,17 @@ int32_t join_streams(isomc *h) {
 int32_t launch_emit_chunk(isomc *h, uint32_t c, cudaStream_t st) {
     const Geo &g = h->g;
     const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
+    if (h->list_mode) {
+        /* one kernel: edge ids, vertex positions and triangles of the chunk's active cells */
+        if (h->kind == SRC_GRID)
+            CU(h, isomc_launch_emit_list_grid(g, h->d_grid, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
+                                              h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
+        else
+            CU(h, isomc_launch_emit_list_sdf(g, h->prog, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
+                                             h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
+        h->stats.kernel_launches += 1;
+        return ISOMC_OK;
+    }
     const uint32_t v0 = l0 < g.ghost ? g.ghost : l0; /* the ghost layer of a slab creates no vertices of ours */
     CU(h, isomc_launch_emit(g, h->signs, h->segpre, h->rowV, h->rowT, h->tabs, h->layerTot, h->vofs, h->ticket + c, h->xyz,
                             h->idx, h->cap_v, h->cap_t, l0, l1, h->sms, st));
@@ -197,6 +232,7 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
     const Geo &g = h->g;
     h->have_result = false; h->counted = false; h->emitted = false; h->totals_valid = false;
     h->stats.kernel_launches = 0; h->stats.emit_reruns = 0;
+    h->emit_inline = emit_inline;
     if (g.ncl == 0 || g.ncx == 0) { /* size == 1: the reference visits no cells */
         CU(h, cudaMemsetAsync(h->totals, 0, 12 * sizeof(unsigned long long), h->stream));
         h->counted = true;
@@ -215,7 +251,7 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
         for (uint32_t c = 0; c <= n; ++c) h->chunk_l[c] = c * per < g.ncl ? c * per : g.ncl;
     }
     if (h->profiling) CU(h, cudaEventRecord(h->ev[0], h->stream));
-    CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + MAX_CHUNKS * sizeof(uint32_t), h->stream));
+    CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t), h->stream));
     tl_mark(h, "start", 0, h->stream);
     int32_t rc = fork_streams(h);
     if (rc) return rc;
@@ -237,10 +273,17 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
         cudaStream_t st = h->stream;
         const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
         if (piped) CU(h, cudaStreamWaitEvent(st, h->ev_chunk[c], 0));
-        CU(h, isomc_launch_count(g, h->signs, h->tabs, h->segpre, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, 8, st));
+        if (h->list_mode) {
+            CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms,
+                                          LIST_COUNT_CTAS, st));
+            CU(h, isomc_launch_list_mark(h->L.ctr, h->list_marks + c + 1, st));
+            h->stats.kernel_launches += 1;
+        } else {
+            CU(h, isomc_launch_count(g, h->signs, h->tabs, h->segpre, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, 8, st));
+        }
         if (h->profiling) CU(h, cudaEventRecord(h->ev[2], h->stream));
         tl_mark(h, "count", c, st);
-        CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, l0, l1, st));
+        CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, h->list_mode ? h->L.ctr : nullptr, l0, l1, st));
         if (h->profiling) CU(h, cudaEventRecord(h->ev[3], h->stream));
         h->stats.kernel_launches += 2;
         if (emit_inline) {
@@ -269,12 +312,24 @@ int32_t enqueue_emit(isomc *h) {
     return ISOMC_OK;
 }
 
-/* bring the totals to the host (synchronises) */
+int32_t enqueue_count(isomc *h, bool emit_inline);
+
+/* bring the totals to the host (synchronises).  If the active-cell list was too small, grow it to what the count
+ * asked for and run the count again (same totals; the first extract of a handle, or a much denser field). */
 int32_t fetch_totals(isomc *h) {
-    if (h->totals_valid) return ISOMC_OK;
-    CU(h, cudaMemcpyAsync(h->h_totals, h->totals, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    h->totals_valid = true;
+    for (int attempt = 0; !h->totals_valid; ++attempt) {
+        CU(h, cudaMemcpyAsync(h->h_totals, h->totals, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        const uint64_t blocks = h->h_totals[7];
+        if (!h->list_mode || blocks <= h->L.cap_blocks) { h->totals_valid = true; break; }
+        if (attempt >= 2) return fail(h, ISOMC_ERR_CUDA, "active-cell list still too small after regrowing (%llu blocks)", (unsigned long long)blocks);
+        const uint32_t reruns = h->stats.emit_reruns;
+        int32_t rc = ensure_list_capacity(h, blocks + blocks / 8 + isomc_count_list_max_warps(h->sms, LIST_COUNT_CTAS));
+        if (rc) return rc;
+        rc = enqueue_count(h, h->emit_inline);
+        if (rc) return rc;
+        h->stats.emit_reruns = reruns + 1;
+    }
     return ISOMC_OK;
 }
 
@@ -371,13 +426,27 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
         CU(h, cudaMemcpy(h->tabs, &host_tabs, sizeof(McTables), cudaMemcpyHostToDevice));
         const uint64_t nrows_s = (uint64_t)g.nsl * g.N, nrows_c = (uint64_t)g.ncl * g.ncx;
         CU(h, cudaMalloc(&h->signs, (nrows_s * g.nws + 4) * sizeof(uint32_t)));
-        CU(h, cudaMalloc(&h->segpre, (nrows_c * g.nsegx + 4) * sizeof(uint32_t)));
+        if (const char *p = getenv("ISOMC_EMIT")) h->list_mode = strcmp(p, "list") == 0;
+        if (h->list_mode) {
+            CU(h, cudaMalloc(&h->L.segrec, (nrows_c * g.nsegx + 4) * sizeof(uint2)));
+            EmitTab host_etab;
+            isomc_build_emit_tab(host_tabs, &host_etab);
+            CU(h, cudaMalloc(&h->etab, sizeof(EmitTab)));
+            CU(h, cudaMemcpy(h->etab, &host_etab, sizeof(EmitTab), cudaMemcpyHostToDevice));
+            /* first guess: 1/32 of the cells active, plus the block every counting warp may strand */
+            int32_t lrc = ensure_list_capacity(h, nrows_c * g.ncx / 32 / LIST_BLOCK + isomc_count_list_max_warps(h->sms, LIST_COUNT_CTAS) + 16);
+            if (lrc) return lrc;
+        } else {
+            CU(h, cudaMalloc(&h->segpre, (nrows_c * g.nsegx + 4) * sizeof(uint32_t)));
+        }
         CU(h, cudaMalloc(&h->rowV, (nrows_c + 4) * sizeof(uint32_t)));
         CU(h, cudaMalloc(&h->rowT, (nrows_c + 4) * sizeof(uint32_t)));
         CU(h, cudaMalloc(&h->rowA, (nrows_c + 4) * sizeof(uint32_t)));
         /* per-layer totals followed by the emit tickets: zeroed by a single memset per extract */
-        CU(h, cudaMalloc(&h->layerTot, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + MAX_CHUNKS * sizeof(uint32_t)));
+        CU(h, cudaMalloc(&h->layerTot, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t)));
         h->ticket = reinterpret_cast<uint32_t *>(h->layerTot + ((size_t)g.ncl * 3 + 4));
+        h->L.ctr = h->ticket + MAX_CHUNKS;
+        h->list_marks = h->ticket + MAX_CHUNKS + 1;
         CU(h, cudaMalloc(&h->totals, 12 * sizeof(unsigned long long)));
         CU(h, cudaMemset(h->totals, 0, 12 * sizeof(unsigned long long)));
         CU(h, cudaMalloc(&h->vofs, sizeof(uint32_t)));
@@ -418,6 +487,7 @@ int32_t isomc_destroy(isomc_t *h) {
     cudaFree(h->signs); cudaFree(h->segpre); cudaFree(h->rowV); cudaFree(h->rowT); cudaFree(h->rowA);
     cudaFree(h->layerTot); cudaFree(h->totals); cudaFree(h->vofs); cudaFree(h->tabs);
     cudaFree(h->xyz); cudaFree(h->idx); cudaFree(h->stage_grid);
+    cudaFree(h->L.ent); cudaFree(h->L.ent_yz); cudaFree(h->L.segrec); cudaFree(h->L.blkfill); cudaFree(h->etab);
     if (h->h_totals) cudaFreeHost(h->h_totals);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);

@@ -1,0 +1,578 @@
+/*
+ * isomc_cell.cuh -- the per-item arithmetic of the active-cell-list path, written once as
+ * `__host__ __device__` code: the kernels (isomc_list_kernels.cu) wrap it with the warp-level
+ * plumbing, and tests/list_model.cu runs the very same functions item by item on the host against the
+ * CPU restatement of the reference (the image this is developed in has no GPU; the model pins the entry formats, the
+ * neighbour lookups and the table use before a kernel ever runs).
+ *
+ * Active-cell list.  k_count_list appends one entry per active cell (a cell whose 8 corners are not all
+ * on one side, reference src/marching_cubes_impl.rs:26-37 + marching_cubes_tables.rs:49-70):
+ *
+ *     ent[k]    = { vrel | trel << 16,  x | ci' << 16 }     ent_yz[k] = y | local layer << 16
+ *
+ *   vrel  vertices created by the earlier cells of the same cell row   (id = rowPV[row] + vrel)
+ *   trel  triangles of the earlier cells of the same cell row          (slot = rowPT[row] + trel)
+ *   ci'   natural cube index (isomc_tables.h)
+ *
+ * and one record per 32-cell segment that has active cells:
+ *
+ *     segrec[row * nsegx + s] = { list position of the segment's first active cell, active mask }
+ *
+ * so that "the entry of cell (x, row)" is segrec.x + popc(segrec.y & below(x & 31)).  Entries of one segment
+ * are contiguous and in x order; beyond that the list order is arbitrary (blocks of LIST_BLOCK entries are
+ * handed out by an atomic counter), which is fine: every output slot is computed, never appended.
+ *
+ * emit_cell() is the whole of `march_cube` + the index-cache lookups (reference
+ * src/marching_cubes_impl.rs:102-117, src/index_cache.rs:38-60, src/mesh.rs:240-251) for one cell:
+ * the ids of its crossed edges come from the entries of the (at most 7) earlier cells that created them,
+ * its own created vertices are interpolated (src/distance.rs:64-69) and written to their final slots, its
+ * triangles are written to theirs.
+ */
+#ifndef ISOMC_CELL_CUH
+#define ISOMC_CELL_CUH
+
+#include <stdint.h>
+
+#include "isomc_device.cuh"
+#include "isomc_tables.h"
+
+#define ISOMC_HD __host__ __device__ __forceinline__
+
+constexpr uint32_t LIST_BLOCK = 256; /* entries per list block = threads per emit CTA */
+
+ISOMC_HD uint32_t hd_popc(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
+ISOMC_HD uint32_t hd_ffs0(uint32_t v) { /* index of the lowest set bit, v != 0 */
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffs((int)v) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(v);
+#endif
+}
+ISOMC_HD float hd_mul(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    return a * b; /* host model is compiled with -ffp-contract=off */
+#endif
+}
+ISOMC_HD float hd_add(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+ISOMC_HD float hd_sub(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+ISOMC_HD float hd_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+
+/* tables emit_cell needs (copied into shared memory by the kernel); derived from McTables on the host */
+struct EmitTab {
+    uint64_t tri[256];        /* the case's edges, 4 bits each, table order (marching_cubes_tables.rs:74-331) */
+    uint16_t before[256][12]; /* edges that appear before e in the case's first-appearance order */
+    uint16_t emask[256];      /* crossed edges */
+    uint16_t ownmask[8];      /* edges a cell with boundary flags b creates */
+    uint16_t stepedges[8][8]; /* [b][d]: edges of a cell with flags b that were created by the cell at -d (d = dx|dy<<1|dz<<2) */
+    uint8_t owner[8][12];     /* [b][e]: d | e' << 4 */
+    uint8_t ends[12];
+    uint8_t ntri[256];
+    uint8_t pad[4];
+};
+
+static inline void isomc_build_emit_tab(const McTables &m, EmitTab *t) {
+    memset(t, 0, sizeof *t);
+    memcpy(t->tri, m.tri, sizeof t->tri);
+    memcpy(t->before, m.before, sizeof t->before);
+    memcpy(t->emask, m.emask, sizeof t->emask);
+    memcpy(t->ownmask, m.ownmask, sizeof t->ownmask);
+    memcpy(t->owner, m.owner, sizeof t->owner);
+    memcpy(t->ends, m.ends, sizeof t->ends);
+    memcpy(t->ntri, m.ntri, sizeof t->ntri);
+    for (int b = 0; b < 8; ++b)
+        for (int e = 0; e < 12; ++e) t->stepedges[b][m.owner[b][e] & 7] |= (uint16_t)(1u << e);
+}
+
+struct ListBufs {
+    uint2 *ent;
+    uint32_t *ent_yz;
+    uint2 *segrec;
+    uint32_t *blkfill;  /* valid entries of each handed-out block */
+    uint32_t *ctr;      /* [0] blocks handed out so far (may exceed cap_blocks: the host then grows the list and re-runs) */
+    uint32_t cap_blocks;
+};
+
+ISOMC_HD uint32_t cell_flags(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) {
+    return (x == 0 ? 1u : 0u) | (y == 0 ? 2u : 0u) | ((g.gz0 + lz) == 0 ? 4u : 0u);
+}
+
+struct EmitArgs {
+    const uint32_t *rowPV, *rowPT; /* exclusive prefixes over cell rows (local numbering incl. a slab's ghost layer) */
+    uint32_t vofs;                 /* local id -> global id */
+    uint32_t ghostV, ghostT;       /* vertices / triangles of the ghost layer: local id/slot -> output slot */
+    uint32_t first_own_layer;
+    uint64_t cap_v, cap_t;
+    float *xyz;
+    uint32_t *idx;
+};
+
+/*
+ * One active cell.  eid = 12 words of scratch (stride eid_stride) for the ids of the cell's crossed edges.
+ * Src::at(g, x, y, lz) is the sample at a lattice point of the handle's slab.
+ */
+template <class Src>
+ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const ListBufs &L, const EmitArgs &A, uint2 ea,
+                        uint32_t yz, uint32_t *eid, uint32_t eid_stride) {
+    const uint32_t x = ea.y & 0xFFFFu, ci = ea.y >> 16 & 255u, y = yz & 0xFFFFu, lz = yz >> 16;
+    if (lz < A.first_own_layer) return; /* ghost layer of a slab: looked up by our first layer, emitted by the previous rank */
+    const uint32_t row = lz * g.ncx + y;
+    const uint32_t bfl = cell_flags(g, x, y, lz);
+    const uint32_t em = T.emask[ci];
+    const uint32_t vid = A.rowPV[row] + (ea.x & 0xFFFFu);
+    const uint32_t owned = em & T.ownmask[bfl];
+
+    /* ids of the crossed edges, creator by creator */
+    for (uint32_t m = owned; m; m &= m - 1) {
+        const uint32_t e = hd_ffs0(m);
+        eid[e * eid_stride] = vid + hd_popc(T.before[ci][e] & owned);
+    }
+    for (uint32_t d = 1; d < 8; ++d) {
+        uint32_t es = em & T.stepedges[bfl][d];
+        if (!es) continue;
+        const uint32_t x2 = x - (d & 1u), y2 = y - (d >> 1 & 1u), lz2 = lz - (d >> 2 & 1u);
+        const uint32_t row2 = lz2 * g.ncx + y2;
+        const uint2 rec = L.segrec[(uint64_t)row2 * g.nsegx + (x2 >> 5)];
+        const uint64_t k2 = (uint64_t)rec.x + hd_popc(rec.y & ((1u << (x2 & 31u)) - 1u));
+        uint32_t vid2 = 0, ci2 = 0;
+        if (k2 < (uint64_t)L.cap_blocks * LIST_BLOCK) { /* (garbage only after a list overflow; the host re-runs then) */
+            const uint2 e2 = L.ent[k2];
+            vid2 = A.rowPV[row2] + (e2.x & 0xFFFFu);
+            ci2 = e2.y >> 16 & 255u;
+        }
+        const uint32_t own2 = T.ownmask[cell_flags(g, x2, y2, lz2)];
+        for (; es; es &= es - 1) {
+            const uint32_t e = hd_ffs0(es);
+            eid[e * eid_stride] = vid2 + hd_popc(T.before[ci2][T.owner[bfl][e] >> 4] & own2);
+        }
+    }
+
+    /* vertices this cell creates: Signed::find_crossing_point (distance.rs:64-69) between the edge's ends in
+     * EDGE_CONNECTION direction, corner coordinates = (i as f32) * inv (primal_grid.rs:50,63-67) */
+    for (uint32_t m = owned; m; m &= m - 1) {
+        const uint32_t e = hd_ffs0(m);
+        const uint64_t slot = (uint64_t)(eid[e * eid_stride] - A.ghostV);
+        if (slot >= A.cap_v) continue;
+        const uint32_t en = T.ends[e];
+        const uint32_t ux = x + (en & 1u), uy = y + (en >> 1 & 1u), uz = lz + (en >> 2 & 1u);
+        const uint32_t vx = x + (en >> 4 & 1u), vy = y + (en >> 5 & 1u), vz = lz + (en >> 6 & 1u);
+        const float a = src.at(g, ux, uy, uz), b = src.at(g, vx, vy, vz);
+        const float delta = hd_sub(b, a);
+        const float t = (delta == 0.0f) ? 0.5f : hd_div(-a, delta);
+        const float omt = hd_sub(1.0f, t);
+        const float pax = hd_mul((float)ux, g.inv), pay = hd_mul((float)uy, g.inv), paz = hd_mul((float)(g.gz0 + uz), g.inv);
+        const float pbx = hd_mul((float)vx, g.inv), pby = hd_mul((float)vy, g.inv), pbz = hd_mul((float)(g.gz0 + vz), g.inv);
+        float *o = A.xyz + 3 * slot;
+        o[0] = hd_add(hd_mul(pax, omt), hd_mul(pbx, t));
+        o[1] = hd_add(hd_mul(pay, omt), hd_mul(pby, t));
+        o[2] = hd_add(hd_mul(paz, omt), hd_mul(pbz, t));
+    }
+
+    /* triangles in table order (march_cube, marching_cubes_impl.rs:106-116) */
+    const uint32_t nt = T.ntri[ci];
+    const uint64_t tslot = (uint64_t)(A.rowPT[row] + (ea.x >> 16) - A.ghostT);
+    uint64_t tri = T.tri[ci];
+    for (uint32_t t = 0; t < nt; ++t, tri >>= 12) {
+        if (tslot + t >= A.cap_t) break;
+        uint32_t *o = A.idx + 3 * (tslot + t);
+        o[0] = eid[((uint32_t)tri & 15u) * eid_stride] + A.vofs;
+        o[1] = eid[((uint32_t)tri >> 4 & 15u) * eid_stride] + A.vofs;
+        o[2] = eid[((uint32_t)tri >> 8 & 15u) * eid_stride] + A.vofs;
+    }
+}
+
+/* ---- classification of one 32-cell segment from the inside bits ------------------------------ */
+
+ISOMC_HD uint32_t hd_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { /* sh in [0, 31] */
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
+ISOMC_HD void hd_bs_add(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t m) {
+    uint32_t k0 = c0 & m; c0 ^= m;
+    uint32_t k1 = c1 & k0; c1 ^= k0;
+    uint32_t k2 = c2 & k1; c2 ^= k1;
+    c3 ^= k2;
+}
+
+struct SegClass {
+    uint32_t act;            /* active cells */
+    uint32_t p0, p1, p2, p3; /* bit planes of "vertices this cell creates" */
+    uint32_t a0, b0, c0, d0; /* inside bits of the 4 corner rows at the cells' own x: (y,z) (y+1,z) (y,z+1) (y+1,z+1) */
+    uint32_t nb;             /* bit 0 of the next word of each row: a | b << 1 | c << 2 | d << 3 */
+};
+
+/* w[8] = a0 a1 b0 b1 c0 c1 d0 d1 (word s and s+1 of the four sample rows); returns false if no cell is active.
+ * Ownership: SURVEY.md 3.1-9 (every cell creates e5, e6, e10; cells on the low faces also the edges in those faces). */
+ISOMC_HD bool classify_segment(const Geo &g, const uint32_t w[8], uint32_t s, uint32_t y, uint32_t lz, SegClass &o) {
+    const uint32_t a0 = w[0], a1 = w[1], b0 = w[2], b1 = w[3], c0 = w[4], c1 = w[5], d0 = w[6], d1 = w[7];
+    o.act = 0; o.p0 = o.p1 = o.p2 = o.p3 = 0;
+    o.a0 = a0; o.b0 = b0; o.c0 = c0; o.d0 = d0;
+    o.nb = (a1 & 1u) | (b1 & 1u) << 1 | (c1 & 1u) << 2 | (d1 & 1u) << 3;
+    const uint32_t all_or = a0 | b0 | c0 | d0 | ((a1 | b1 | c1 | d1) & 1u);
+    const uint32_t all_and = a0 & b0 & c0 & d0;
+    if ((all_or == 0u) || (all_and == 0xFFFFFFFFu && (a1 & b1 & c1 & d1 & 1u))) return false;
+    const uint32_t an = hd_funnel_r(a0, a1, 1), bn = hd_funnel_r(b0, b1, 1);
+    const uint32_t cn = hd_funnel_r(c0, c1, 1), dn = hd_funnel_r(d0, d1, 1);
+    const uint32_t ncell = g.ncx - s * 32;
+    const uint32_t vm = ncell >= 32 ? 0xFFFFFFFFu : ((1u << ncell) - 1u);
+    const uint32_t all_in = a0 & an & b0 & bn & c0 & cn & d0 & dn;
+    const uint32_t any_in = a0 | an | b0 | bn | c0 | cn | d0 | dn;
+    o.act = any_in & ~all_in & vm;
+    if (o.act == 0) return false;
+    const bool Z0 = (g.gz0 + lz) == 0, Y0 = y == 0;
+    const uint32_t x0m = s == 0 ? 1u : 0u;
+    uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+    hd_bs_add(p0, p1, p2, p3, (cn ^ dn) & vm);           /* e5: corners 5-6 */
+    hd_bs_add(p0, p1, p2, p3, (dn ^ d0) & vm);           /* e6: corners 6-7 */
+    hd_bs_add(p0, p1, p2, p3, (bn ^ dn) & vm);           /* e10: corners 2-6 */
+    if (Z0) {
+        hd_bs_add(p0, p1, p2, p3, (an ^ bn) & vm);       /* e1 */
+        hd_bs_add(p0, p1, p2, p3, (bn ^ b0) & vm);       /* e2 */
+        hd_bs_add(p0, p1, p2, p3, (b0 ^ a0) & vm & x0m); /* e3 */
+        if (Y0) hd_bs_add(p0, p1, p2, p3, (a0 ^ an) & vm); /* e0 */
+    }
+    if (Y0) {
+        hd_bs_add(p0, p1, p2, p3, (c0 ^ cn) & vm);       /* e4 */
+        hd_bs_add(p0, p1, p2, p3, (an ^ cn) & vm);       /* e9 */
+        hd_bs_add(p0, p1, p2, p3, (a0 ^ c0) & vm & x0m); /* e8 */
+    }
+    if (x0m) {
+        hd_bs_add(p0, p1, p2, p3, (d0 ^ c0) & vm & x0m); /* e7 */
+        hd_bs_add(p0, p1, p2, p3, (b0 ^ d0) & vm & x0m); /* e11 */
+    }
+    o.p0 = p0; o.p1 = p1; o.p2 = p2; o.p3 = p3;
+    return true;
+}
+
+ISOMC_HD uint32_t seg_planes_count(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t m) {
+    return hd_popc(p0 & m) + 2 * hd_popc(p1 & m) + 4 * hd_popc(p2 & m) + 8 * hd_popc(p3 & m);
+}
+
+/* natural cube index of cell i of a segment: bits i, i+1 of the four rows */
+ISOMC_HD uint32_t seg_cube_index(uint32_t a0, uint32_t b0, uint32_t c0, uint32_t d0, uint32_t nb, uint32_t i) {
+    const uint32_t hi = i == 31 ? 1u : 0u; /* bit i+1 lives in the next word */
+    const uint32_t a = hi ? (a0 >> 31) | (nb & 1u) << 1 : (a0 >> i) & 3u;
+    const uint32_t b = hi ? (b0 >> 31) | (nb >> 1 & 1u) << 1 : (b0 >> i) & 3u;
+    const uint32_t c = hi ? (c0 >> 31) | (nb >> 2 & 1u) << 1 : (c0 >> i) & 3u;
+    const uint32_t d = hi ? (d0 >> 31) | (nb >> 3 & 1u) << 1 : (d0 >> i) & 3u;
+    return a | b << 2 | c << 4 | d << 6;
+}
+
+/* position of the j-th (0-based) set bit of m; j < popc(m) */
+ISOMC_HD uint32_t nth_set_bit(uint32_t m, uint32_t j) {
+    uint32_t pos = 0, c;
+    c = hd_popc(m & 0xFFFFu);            if (j >= c) { pos = 16; j -= c; }
+    c = hd_popc((m >> pos) & 0xFFu);     if (j >= c) { pos += 8; j -= c; }
+    c = hd_popc((m >> pos) & 0xFu);      if (j >= c) { pos += 4; j -= c; }
+    c = hd_popc((m >> pos) & 0x3u);      if (j >= c) { pos += 2; j -= c; }
+    c = (m >> pos) & 1u;                 if (j >= c) { pos += 1; }
+    return pos;
+}
+
+
+/* ---- warp-cooperative part of k_count_list ---------------------------------------------------
+ * Written against a tiny warp interface so that tests/list_model.cu can run the SAME source on the host
+ * (32 threads per emulated warp, a barrier per shuffle; ISOMC_HOST_MODEL).  On the device every call is
+ * the intrinsic it names. */
+struct Warp {
+    uint32_t lane;
+    void *emu; /* host model only */
+};
+#if !defined(__CUDA_ARCH__) && defined(ISOMC_HOST_MODEL)
+uint32_t isomc_emu_shfl(void *emu, uint32_t lane, uint32_t v, uint32_t src);
+void isomc_emu_sync(void *emu, uint32_t lane);
+uint32_t isomc_emu_atomic_add_u32(uint32_t *p, uint32_t v);
+void isomc_emu_atomic_add_u64(unsigned long long *p, unsigned long long v);
+#endif
+
+ISOMC_HD uint32_t w_shfl(const Warp &w, uint32_t v, uint32_t src) {
+#if defined(__CUDA_ARCH__)
+    return __shfl_sync(0xFFFFFFFFu, v, src);
+#elif defined(ISOMC_HOST_MODEL)
+    return isomc_emu_shfl(w.emu, w.lane, v, src & 31u);
+#else
+    return v;
+#endif
+}
+/* value of lane - d (own value for the first d lanes) */
+ISOMC_HD uint32_t w_shfl_up(const Warp &w, uint32_t v, uint32_t d) {
+#if defined(__CUDA_ARCH__)
+    return __shfl_up_sync(0xFFFFFFFFu, v, d);
+#elif defined(ISOMC_HOST_MODEL)
+    return isomc_emu_shfl(w.emu, w.lane, v, w.lane >= d ? w.lane - d : w.lane);
+#else
+    return v;
+#endif
+}
+ISOMC_HD void w_sync(const Warp &w) {
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#elif defined(ISOMC_HOST_MODEL)
+    isomc_emu_sync(w.emu, w.lane);
+#endif
+}
+ISOMC_HD uint32_t hd_atomic_add(uint32_t *p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#elif defined(ISOMC_HOST_MODEL)
+    return isomc_emu_atomic_add_u32(p, v);
+#else
+    return 0;
+#endif
+}
+ISOMC_HD void hd_atomic_add64(unsigned long long *p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#elif defined(ISOMC_HOST_MODEL)
+    isomc_emu_atomic_add_u64(p, v);
+#endif
+}
+ISOMC_HD uint32_t hd_ldg(const uint32_t *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+/* exclusive scan over the warp; total = sum over all lanes */
+ISOMC_HD uint32_t w_excl_scan(const Warp &w, uint32_t v, uint32_t &total) {
+    uint32_t inc = v;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t o = w_shfl_up(w, inc, d);
+        if (w.lane >= d) inc += o;
+    }
+    total = w_shfl(w, inc, 31);
+    return inc - v;
+}
+
+/* warp-private cursor into the list: [pos, end) is what is left of the blocks [b0, b0 + m) this warp holds */
+struct ListCursor {
+    uint32_t pos, end, b0, m;
+};
+
+ISOMC_HD void list_close(const ListBufs &L, ListCursor &c, uint32_t lane) {
+    if (c.m && c.b0 + c.m <= L.cap_blocks && lane < c.m) {
+        const uint32_t b = c.b0 + lane, lo = b * LIST_BLOCK;
+        L.blkfill[b] = c.pos <= lo ? 0u : (c.pos - lo >= LIST_BLOCK ? LIST_BLOCK : c.pos - lo);
+    }
+    c.m = 0;
+}
+
+/* space for n (1..1024) contiguous entries; returns the first position; ok = false after a list overflow */
+ISOMC_HD uint32_t list_alloc(const Warp &w, const ListBufs &L, ListCursor &c, uint32_t n, bool &ok) {
+    if (c.pos + n > c.end) {
+        list_close(L, c, w.lane);
+        const uint32_t m = (n + LIST_BLOCK - 1) / LIST_BLOCK;
+        uint32_t b0 = 0;
+        if (w.lane == 0) b0 = hd_atomic_add(L.ctr, m);
+        b0 = w_shfl(w, b0, 0);
+        c.b0 = b0; c.m = m;
+        c.pos = b0 * LIST_BLOCK;
+        c.end = (b0 + m) * LIST_BLOCK;
+    }
+    const uint32_t base = c.pos;
+    c.pos += n;
+    ok = c.b0 + c.m <= L.cap_blocks;
+    return base;
+}
+
+struct CountOut {
+    uint32_t *rowV, *rowT, *rowA;     /* per cell row: vertices created, triangles, active cells */
+    unsigned long long *layerTot;     /* per cell layer: the same three, summed */
+};
+
+/*
+ * Phase B for one pass of a warp: the pass' active cells, one lane per cell.  Lane l holds segment l of the pass
+ * (C, cpos/cend = list range of its cells within the pass, vpre = in-row vertex prefix at the segment start,
+ * yznb = y | layer << 13 | next-word bits << 26).  Returns the triangles of the pass.
+ *   ROWS: the pass covers (32 >> gshift) whole rows of (1 << gshift) segments each: triangle prefixes restart per
+ *         row (Rsm = 32 words of warp-private shared memory) and the lane holding a row's last cell posts the row total;
+ *   else: the pass is a 32-segment chunk of ONE row: prefixes continue from t_row, the caller posts the total.
+ */
+template <bool ROWS>
+ISOMC_HD uint32_t list_phase_b(const Warp &w, const ListBufs &L, const uint8_t *s_ntri, const SegClass &C, uint32_t cpos,
+                               uint32_t cend, uint32_t vpre, uint32_t yznb, uint32_t n_cells, uint32_t base, bool ok,
+                               uint32_t gshift, uint32_t seg0, uint32_t row_first, uint32_t t_row, uint32_t *Rsm,
+                               const CountOut &out) {
+    const uint32_t lane = w.lane;
+    uint32_t tcarry = 0;
+    for (uint32_t kb = 0; kb < n_cells; kb += 32) {
+        const uint32_t k = kb + lane;
+        const bool live = k < n_cells;
+        /* segment of cell k: the first lane whose range ends beyond k (cend is non-decreasing) */
+        uint32_t seg = 0;
+#pragma unroll
+        for (uint32_t step = 16; step; step >>= 1) {
+            const uint32_t t = w_shfl(w, cend, seg + step - 1);
+            if (t <= k) seg += step;
+        }
+        const uint32_t sc = w_shfl(w, cpos, seg), am = w_shfl(w, C.act, seg);
+        const uint32_t a0 = w_shfl(w, C.a0, seg), b0 = w_shfl(w, C.b0, seg);
+        const uint32_t c0 = w_shfl(w, C.c0, seg), d0 = w_shfl(w, C.d0, seg);
+        const uint32_t p0 = w_shfl(w, C.p0, seg), p1 = w_shfl(w, C.p1, seg);
+        const uint32_t p2 = w_shfl(w, C.p2, seg), p3 = w_shfl(w, C.p3, seg);
+        const uint32_t vp = w_shfl(w, vpre, seg), yz = w_shfl(w, yznb, seg);
+        const uint32_t i = live ? nth_set_bit(am, k - sc) : 0u;
+        const uint32_t ci = seg_cube_index(a0, b0, c0, d0, yz >> 26, i);
+        const uint32_t nt = live ? (uint32_t)s_ntri[ci] : 0u;
+        const uint32_t vrel = vp + seg_planes_count(p0, p1, p2, p3, (1u << i) - 1u);
+        uint32_t incl = nt;
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const uint32_t o = w_shfl_up(w, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const uint32_t s_excl = tcarry + incl - nt; /* triangles of the pass' earlier cells */
+        tcarry += w_shfl(w, incl, 31);
+        uint32_t trel, xk;
+        if (ROWS) {
+            const uint32_t G = 1u << gshift, subk = seg >> gshift, fl = subk << gshift;
+            const uint32_t rstart = w_shfl(w, cpos, fl), rend = w_shfl(w, cend, fl + G - 1);
+            if (live && k == rstart) Rsm[subk] = s_excl; /* the row's first active cell: posted in this or an earlier step */
+            w_sync(w);
+            trel = s_excl - (live ? Rsm[subk] : 0u);
+            w_sync(w);
+            xk = (seg & (G - 1)) * 32 + i;
+            if (live && k == rend - 1) { /* the row's last active cell */
+                const uint32_t tt = trel + nt;
+                out.rowT[row_first + subk] = tt;
+                hd_atomic_add64(&out.layerTot[3 * (yz >> 13 & 0x1FFFu) + 1], (unsigned long long)tt);
+            }
+        } else {
+            trel = t_row + s_excl;
+            xk = (seg0 + seg) * 32 + i;
+        }
+        if (live && ok) {
+            L.ent[base + k] = make_uint2(vrel | trel << 16, xk | ci << 16);
+            L.ent_yz[base + k] = (yz & 0x1FFFu) | (yz >> 13 & 0x1FFFu) << 16;
+        }
+    }
+    return tcarry;
+}
+
+ISOMC_HD bool load_classify(const Geo &g, const uint32_t *signs, uint32_t row, uint32_t lz, uint32_t y, uint32_t s, SegClass &C) {
+    const uint32_t *r00 = signs + (uint64_t)(row + lz) * g.nws + s; /* sample row lz*N + y = row + lz */
+    const uint32_t *r01 = r00 + g.nws, *r10 = r00 + (uint64_t)g.N * g.nws, *r11 = r10 + g.nws;
+    uint32_t wd[8];
+    wd[0] = hd_ldg(r00); wd[1] = hd_ldg(r00 + 1); wd[2] = hd_ldg(r01); wd[3] = hd_ldg(r01 + 1);
+    wd[4] = hd_ldg(r10); wd[5] = hd_ldg(r10 + 1); wd[6] = hd_ldg(r11); wd[7] = hd_ldg(r11 + 1);
+    return classify_segment(g, wd, s, y, lz, C);
+}
+
+ISOMC_HD void seg_clear(SegClass &C) {
+    C.act = 0; C.p0 = C.p1 = C.p2 = C.p3 = 0; C.a0 = C.b0 = C.c0 = C.d0 = 0; C.nb = 0;
+}
+
+/* One warp's share of cell rows [row0, row1): warp gwarp of nwarps.  WIDE = rows of more than 32 segments (one row
+ * per warp pass, 32-segment chunks); else a pass covers 32 >> gshift rows of 1 << gshift segments. */
+template <bool WIDE>
+ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs, const uint8_t *s_ntri, const ListBufs &L,
+                              const CountOut &out, uint32_t gshift, uint32_t row0, uint32_t row1, uint32_t gwarp,
+                              uint32_t nwarps, uint32_t *Rsm) {
+    const uint32_t lane = w.lane;
+    ListCursor cur;
+    cur.pos = cur.end = cur.b0 = cur.m = 0;
+    if (!WIDE) {
+        const uint32_t G = 1u << gshift, rpw = 32u >> gshift, sub = lane >> gshift, s = lane & (G - 1);
+        const uint32_t niter = (row1 - row0 + rpw - 1) / rpw;
+        for (uint32_t it = gwarp; it < niter; it += nwarps) {
+            const uint32_t row = row0 + it * rpw + sub;
+            const bool valid = row < row1 && s < g.nsegx;
+            const uint32_t rowc = row < row1 ? row : row1 - 1;
+            const uint32_t lz = rowc / g.ncx, y = rowc - lz * g.ncx;
+            SegClass C;
+            seg_clear(C);
+            uint32_t nv = 0;
+            if (valid && load_classify(g, signs, row, lz, y, s, C)) nv = seg_planes_count(C.p0, C.p1, C.p2, C.p3, 0xFFFFFFFFu);
+            const uint32_t na = hd_popc(C.act);
+            /* scans within the row (lanes [sub * G, sub * G + G)) */
+            uint32_t inc = nv, rinc = na;
+            for (uint32_t d = 1; d < G; d <<= 1) {
+                const uint32_t o = w_shfl_up(w, inc, d), q = w_shfl_up(w, rinc, d);
+                if (s >= d) { inc += o; rinc += q; }
+            }
+            const uint32_t vpre = inc - nv;
+            const uint32_t tv = w_shfl(w, inc, (sub << gshift) + G - 1), ra = w_shfl(w, rinc, (sub << gshift) + G - 1);
+            uint32_t n_cells;
+            const uint32_t cpos = w_excl_scan(w, na, n_cells);
+            if (s == 0 && row < row1) {
+                out.rowV[row] = tv; out.rowA[row] = ra;
+                if (ra == 0) out.rowT[row] = 0; /* rows with active cells: posted by the lane of their last cell */
+                if (tv) hd_atomic_add64(&out.layerTot[3 * lz + 0], (unsigned long long)tv);
+                if (ra) hd_atomic_add64(&out.layerTot[3 * lz + 2], (unsigned long long)ra);
+            }
+            if (n_cells == 0) continue;
+            bool ok;
+            const uint32_t base = list_alloc(w, L, cur, n_cells, ok);
+            if (na && ok) L.segrec[(uint64_t)row * g.nsegx + s] = make_uint2(base + cpos, C.act);
+            list_phase_b<true>(w, L, s_ntri, C, cpos, cpos + na, vpre, y | lz << 13 | C.nb << 26, n_cells, base, ok, gshift, 0u,
+                               row0 + it * rpw, 0u, Rsm, out);
+        }
+    } else {
+        for (uint32_t row = row0 + gwarp; row < row1; row += nwarps) {
+            const uint32_t lz = row / g.ncx, y = row - lz * g.ncx;
+            uint32_t vcarry = 0, tcarry = 0, acarry = 0;
+            for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 32) {
+                const uint32_t s = s0 + lane;
+                SegClass C;
+                seg_clear(C);
+                uint32_t nv = 0;
+                if (s < g.nsegx && load_classify(g, signs, row, lz, y, s, C)) nv = seg_planes_count(C.p0, C.p1, C.p2, C.p3, 0xFFFFFFFFu);
+                const uint32_t na = hd_popc(C.act);
+                uint32_t n_cells, nv_tot;
+                const uint32_t cpos = w_excl_scan(w, na, n_cells);
+                if (n_cells == 0) continue; /* no active cell, no created vertex */
+                const uint32_t vpre = vcarry + w_excl_scan(w, nv, nv_tot);
+                vcarry += nv_tot;
+                acarry += n_cells;
+                bool ok;
+                const uint32_t base = list_alloc(w, L, cur, n_cells, ok);
+                if (na && ok) L.segrec[(uint64_t)row * g.nsegx + s] = make_uint2(base + cpos, C.act);
+                tcarry += list_phase_b<false>(w, L, s_ntri, C, cpos, cpos + na, vpre, y | lz << 13 | C.nb << 26, n_cells, base, ok,
+                                              0u, s0, row, tcarry, Rsm, out);
+            }
+            if (lane == 0) {
+                out.rowV[row] = vcarry; out.rowT[row] = tcarry; out.rowA[row] = acarry;
+                if (acarry) {
+                    hd_atomic_add64(&out.layerTot[3 * lz + 0], (unsigned long long)vcarry);
+                    hd_atomic_add64(&out.layerTot[3 * lz + 1], (unsigned long long)tcarry);
+                    hd_atomic_add64(&out.layerTot[3 * lz + 2], (unsigned long long)acarry);
+                }
+            }
+        }
+    }
+    list_close(L, cur, lane);
+}
+
+#endif /* ISOMC_CELL_CUH */

@@ -306,11 +306,12 @@ __device__ __forceinline__ T block_excl_scan_256(T v, T *s_warp, T &total) {
 /* in: rowV/rowT hold per-row counts; out: exclusive prefixes over rows in (lz, y) order, with a
  * sentinel entry [nrows] = grand total.  totals (u64):
  *   [0] V incl. ghost layer  [1] T incl. ghost  [2] active cells incl. ghost
- *   [3] V prefix at the start of the last cell layer  [4..6] V, T, active of the ghost layer
+ *   [3] V prefix at the start of the last cell layer  [4..6] V, T, active of the ghost layer  [7] list blocks asked for
  *   [8] vertices owned  [9] owned vertices created before the last cell layer  [10] triangles owned */
 __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t *__restrict__ rowV, uint32_t *__restrict__ rowT,
                                                    const unsigned long long *__restrict__ layerTot,
-                                                   unsigned long long *__restrict__ totals, uint32_t lz_first) {
+                                                   unsigned long long *__restrict__ totals,
+                                                   const uint32_t *__restrict__ list_ctr, uint32_t lz_first) {
     __shared__ unsigned long long s_w[8];
     __shared__ unsigned long long s_base[2];
     const uint32_t lz = lz_first + blockIdx.x;
@@ -349,7 +350,8 @@ __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t *__restrict__
         unsigned long long V = tv + layerTot[3 * lz], T = tt + layerTot[3 * lz + 1], A = ta + layerTot[3 * lz + 2];
         unsigned long long gV = g.ghost ? layerTot[0] : 0, gT = g.ghost ? layerTot[1] : 0, gA = g.ghost ? layerTot[2] : 0;
         totals[0] = V; totals[1] = T; totals[2] = A; totals[3] = tv;
-        totals[4] = gV; totals[5] = gT; totals[6] = gA; totals[7] = 0;
+        totals[4] = gV; totals[5] = gT; totals[6] = gA;
+        totals[7] = list_ctr ? *list_ctr : 0u; /* list blocks the count asked for (active-cell-list path) */
         totals[8] = V - gV; totals[9] = tv - gV; totals[10] = T - gT; totals[11] = A - gA;
         rowV[g.ncl * g.ncx] = (uint32_t)V;
         rowT[g.ncl * g.ncx] = (uint32_t)T;
@@ -905,8 +907,8 @@ cudaError_t isomc_launch_count(const Geo &g, const uint32_t *signs, const McTabl
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_scan(const Geo &g, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
-                              unsigned long long *totals, uint32_t lz0, uint32_t lz1, cudaStream_t st) {
-    k_scan_rows<<<lz1 - lz0, 256, 0, st>>>(g, rowV, rowT, layerTot, totals, lz0);
+                              unsigned long long *totals, const uint32_t *list_ctr, uint32_t lz0, uint32_t lz1, cudaStream_t st) {
+    k_scan_rows<<<lz1 - lz0, 256, 0, st>>>(g, rowV, rowT, layerTot, totals, list_ctr, lz0);
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,

@@ -1,0 +1,151 @@
+/*
+ * isomc_list_kernels.cu -- the active-cell-list form of output sizing and emission (sm_100a).
+ *
+ *   K2L k_count_list   replaces k_count: classifies 32-cell segments bit-parallel (phase A, lane per
+ *                      segment), then walks the warp's active cells with one lane per CELL (phase B): cube
+ *                      index, triangles, in-row vertex / triangle prefixes -> one 12-byte list entry per
+ *                      active cell, one record per active segment (isomc_cell.cuh).  List space is handed
+ *                      out in blocks of LIST_BLOCK entries by one atomic per block, not per warp pass.
+ *   K4L k_emit_list    replaces k_emit + k_vertex: one lane per list entry runs emit_cell(): edge ids from
+ *                      the entries of the cells that created them (edge ownership replaces the reference's
+ *                      HashMap index cache, index_cache.rs / mesh.rs:240-251), the cell's own vertices
+ *                      (distance.rs:64-69) and its triangles (marching_cubes_impl.rs:102-117) go straight
+ *                      to their final slots.  No bricks, no halo recomputation, no descriptors.
+ *
+ * Every lane of both hot loops works on an ACTIVE cell, which is what the brick kernels could not offer
+ * (profiles/r01_history.md: 22 of 32 lanes, 1.6 active cells per segment against a warp maximum of 19).
+ */
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "isomc_cell.cuh"
+#include "isomc_kernels.h"
+
+namespace {
+
+/* cell rows [row0, row1); the body is count_list_warp() of isomc_cell.cuh (shared with the host model) */
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_count_list(Geo g, const uint32_t *__restrict__ signs, const uint8_t *__restrict__ ntri_g,
+                                                    ListBufs L, CountOut out, uint32_t gshift, uint32_t row0, uint32_t row1) {
+    __shared__ uint8_t s_ntri[256];
+    __shared__ uint32_t s_R[8][32];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = ntri_g[i];
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5;
+    const Warp w{threadIdx.x & 31u, nullptr};
+    count_list_warp<WIDE>(w, g, signs, s_ntri, L, out, gshift, row0, row1, blockIdx.x * (blockDim.x >> 5) + warp,
+                          gridDim.x * (blockDim.x >> 5), s_R[warp]);
+}
+
+/* device-side copy of the block counter (end of a z-chunk's part of the list) */
+__global__ void k_list_mark(const uint32_t *__restrict__ ctr, uint32_t *__restrict__ dst) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *ctr;
+}
+
+/* list blocks [*blk_first, *blk_end): one CTA per block, one lane per entry */
+template <class Src>
+__global__ void __launch_bounds__(LIST_BLOCK) k_emit_list(Src src, Geo g, ListBufs L, const EmitTab *__restrict__ tab_g,
+                                                          const uint32_t *__restrict__ rowPV, const uint32_t *__restrict__ rowPT,
+                                                          const unsigned long long *__restrict__ layerTot,
+                                                          const uint32_t *__restrict__ vofs_ptr, float *__restrict__ xyz,
+                                                          uint32_t *__restrict__ idx, unsigned long long cap_v,
+                                                          unsigned long long cap_t, const uint32_t *__restrict__ blk_first,
+                                                          const uint32_t *__restrict__ blk_end) {
+    __shared__ EmitTab T;
+    __shared__ uint32_t s_eid[12 * LIST_BLOCK];
+    {
+        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(tab_g);
+        uint32_t *dstw = reinterpret_cast<uint32_t *>(&T);
+        for (uint32_t i = threadIdx.x; i < sizeof(EmitTab) / 4; i += LIST_BLOCK) dstw[i] = srcw[i];
+    }
+    __syncthreads();
+    if (*L.ctr > L.cap_blocks) return; /* list overflow: entries are incomplete; the host grows the list and re-runs */
+    const uint32_t b0 = blk_first ? *blk_first : 0u, b1 = *blk_end;
+    EmitArgs A;
+    A.rowPV = rowPV; A.rowPT = rowPT;
+    A.vofs = *vofs_ptr;
+    A.ghostV = g.ghost ? (uint32_t)layerTot[0] : 0u;
+    A.ghostT = g.ghost ? (uint32_t)layerTot[1] : 0u;
+    A.first_own_layer = g.ghost;
+    A.cap_v = cap_v; A.cap_t = cap_t;
+    A.xyz = xyz; A.idx = idx;
+    for (uint32_t b = b0 + blockIdx.x; b < b1; b += gridDim.x) {
+        const uint32_t fill = L.blkfill[b];
+        if (threadIdx.x < fill) {
+            const uint64_t k = (uint64_t)b * LIST_BLOCK + threadIdx.x;
+            emit_cell(g, src, T, L, A, L.ent[k], L.ent_yz[k], s_eid + threadIdx.x, LIST_BLOCK);
+        }
+    }
+}
+
+inline uint32_t grid_for(uint64_t warps_needed, int sms, int warps_per_block, int blocks_per_sm) {
+    uint64_t blocks = (warps_needed + warps_per_block - 1) / warps_per_block;
+    const uint64_t cap = (uint64_t)sms * (blocks_per_sm < 1 ? 1 : blocks_per_sm);
+    if (blocks > cap) blocks = cap;
+    return (uint32_t)(blocks < 1 ? 1 : blocks);
+}
+
+template <class Src>
+cudaError_t launch_emit_list(const Src &src, const Geo &g, const ListBufs &L, const EmitTab *tab, const uint32_t *rowPV,
+                             const uint32_t *rowPT, const unsigned long long *layerTot, const uint32_t *vofs, float *xyz,
+                             uint32_t *idx, uint64_t cap_v, uint64_t cap_t, const uint32_t *blk_first, const uint32_t *blk_end,
+                             int sms, cudaStream_t st) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int n = 1;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_emit_list<Src>, (int)LIST_BLOCK, 0);
+        if (e != cudaSuccess) return e;
+        per_sm = n < 1 ? 1 : n;
+    }
+    k_emit_list<Src><<<sms * per_sm, LIST_BLOCK, 0, st>>>(src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t,
+                                                          blk_first, blk_end);
+    return cudaGetLastError();
+}
+
+} /* namespace */
+
+/* warps k_count_list may run: each can strand one partly filled block */
+uint32_t isomc_count_list_max_warps(int sms, int ctas_per_sm) { return (uint32_t)(sms * ctas_per_sm * 8); }
+
+cudaError_t isomc_launch_count_list(const Geo &g, const uint32_t *signs, const McTables *tabs, const ListBufs &L, uint32_t *rowV,
+                                    uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot, uint32_t lz0, uint32_t lz1,
+                                    int sms, int ctas_per_sm, cudaStream_t st) {
+    uint32_t gshift = 0;
+    while ((1u << gshift) < g.nsegx && gshift < 5) ++gshift;
+    const uint32_t row0 = lz0 * g.ncx, row1 = lz1 * g.ncx;
+    const uint8_t *ntri = reinterpret_cast<const uint8_t *>(tabs) + offsetof(McTables, ntri);
+    const CountOut out{rowV, rowT, rowA, layerTot};
+    if (g.nsegx <= 32) {
+        const uint32_t rpw = 32u >> gshift;
+        const uint64_t warps = ((uint64_t)(row1 - row0) + rpw - 1) / rpw;
+        k_count_list<false><<<grid_for(warps, sms, 8, ctas_per_sm), 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1);
+    } else {
+        k_count_list<true><<<grid_for(row1 - row0, sms, 8, ctas_per_sm), 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t isomc_launch_list_mark(const uint32_t *ctr, uint32_t *dst, cudaStream_t st) {
+    k_list_mark<<<1, 32, 0, st>>>(ctr, dst);
+    return cudaGetLastError();
+}
+
+cudaError_t isomc_launch_emit_list_grid(const Geo &g, const float *d_grid, const ListBufs &L, const EmitTab *tab,
+                                        const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
+                                        const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
+                                        const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st) {
+    return launch_emit_list(GridSrc{d_grid}, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end,
+                            sms, st);
+}
+
+cudaError_t isomc_launch_emit_list_sdf(const Geo &g, const SdfProgram &prog, const ListBufs &L, const EmitTab *tab,
+                                       const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
+                                       const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
+                                       const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st) {
+    SdfChainSrc csrc;
+    if (sdf_to_chain(prog, &csrc.chain))
+        return launch_emit_list(csrc, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end, sms, st);
+    return launch_emit_list(SdfSrc{prog}, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end, sms,
+                            st);
+}
