@@ -28,7 +28,6 @@ thread_local std::string g_create_error;
 enum SrcKind { SRC_NONE = 0, SRC_GRID = 1, SRC_SDF = 2 };
 constexpr int MAX_CHUNKS = 16;
 constexpr int AUX_WORDS = 2 * MAX_CHUNKS + 4; /* u32 after layerTot: emit tickets [MAX_CHUNKS], list block counter, list marks [MAX_CHUNKS + 1] */
-constexpr int LIST_COUNT_CTAS = 4;            /* k_count_list CTAs per SM (64 registers x 256 threads) */
 
 }  // namespace
 
@@ -47,8 +46,8 @@ struct isomc {
     uint32_t *signs = nullptr, *segpre = nullptr, *rowV = nullptr, *rowT = nullptr, *rowA = nullptr;
     unsigned long long *layerTot = nullptr, *totals = nullptr; /* totals: 12 u64 */
     uint32_t *vofs = nullptr, *ticket = nullptr;
-    /* active-cell-list path (ISOMC_EMIT=list; the brick kernels are the default until it is the faster one): isomc_cell.cuh */
-    bool list_mode = false;
+    /* active-cell-list path (default; ISOMC_EMIT=brick selects the older brick kernels): isomc_cell.cuh */
+    bool list_mode = true;
     ListBufs L{};
     uint32_t *list_marks = nullptr; /* [c] = list blocks handed out before z-chunk c; [0] = 0 */
     EmitTab *etab = nullptr;
@@ -274,16 +273,14 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
         const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
         if (piped) CU(h, cudaStreamWaitEvent(st, h->ev_chunk[c], 0));
         if (h->list_mode) {
-            CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms,
-                                          LIST_COUNT_CTAS, st));
-            CU(h, isomc_launch_list_mark(h->L.ctr, h->list_marks + c + 1, st));
-            h->stats.kernel_launches += 1;
+            CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, st));
         } else {
             CU(h, isomc_launch_count(g, h->signs, h->tabs, h->segpre, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, 8, st));
         }
         if (h->profiling) CU(h, cudaEventRecord(h->ev[2], h->stream));
         tl_mark(h, "count", c, st);
-        CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, h->list_mode ? h->L.ctr : nullptr, l0, l1, st));
+        CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, h->list_mode ? h->L.ctr : nullptr,
+                                h->list_mode ? h->list_marks + c + 1 : nullptr, l0, l1, st));
         if (h->profiling) CU(h, cudaEventRecord(h->ev[3], h->stream));
         h->stats.kernel_launches += 2;
         if (emit_inline) {
@@ -324,7 +321,7 @@ int32_t fetch_totals(isomc *h) {
         if (!h->list_mode || blocks <= h->L.cap_blocks) { h->totals_valid = true; break; }
         if (attempt >= 2) return fail(h, ISOMC_ERR_CUDA, "active-cell list still too small after regrowing (%llu blocks)", (unsigned long long)blocks);
         const uint32_t reruns = h->stats.emit_reruns;
-        int32_t rc = ensure_list_capacity(h, blocks + blocks / 8 + isomc_count_list_max_warps(h->sms, LIST_COUNT_CTAS));
+        int32_t rc = ensure_list_capacity(h, blocks + blocks / 8 + isomc_count_list_max_warps(h->sms));
         if (rc) return rc;
         rc = enqueue_count(h, h->emit_inline);
         if (rc) return rc;
@@ -411,6 +408,7 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
     g.ncl = (g.ncx == 0) ? 0 : (z_end - z_begin + g.ghost);
     g.nsl = g.ncl + 1;
     g.inv = 1.0f / (float)(size - 1);
+    g.row_magic = g.ncx ? ((1ull << 40) + g.ncx - 1) / g.ncx : 0;
     int32_t rc = ISOMC_OK;
     auto body = [&]() -> int32_t {
         CU(h, cudaSetDevice(device));
@@ -426,7 +424,7 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
         CU(h, cudaMemcpy(h->tabs, &host_tabs, sizeof(McTables), cudaMemcpyHostToDevice));
         const uint64_t nrows_s = (uint64_t)g.nsl * g.N, nrows_c = (uint64_t)g.ncl * g.ncx;
         CU(h, cudaMalloc(&h->signs, (nrows_s * g.nws + 4) * sizeof(uint32_t)));
-        if (const char *p = getenv("ISOMC_EMIT")) h->list_mode = strcmp(p, "list") == 0;
+        if (const char *p = getenv("ISOMC_EMIT")) h->list_mode = strcmp(p, "brick") != 0;
         if (h->list_mode) {
             CU(h, cudaMalloc(&h->L.segrec, (nrows_c * g.nsegx + 4) * sizeof(uint2)));
             EmitTab host_etab;
@@ -434,7 +432,7 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
             CU(h, cudaMalloc(&h->etab, sizeof(EmitTab)));
             CU(h, cudaMemcpy(h->etab, &host_etab, sizeof(EmitTab), cudaMemcpyHostToDevice));
             /* first guess: 1/32 of the cells active, plus the block every counting warp may strand */
-            int32_t lrc = ensure_list_capacity(h, nrows_c * g.ncx / 32 / LIST_BLOCK + isomc_count_list_max_warps(h->sms, LIST_COUNT_CTAS) + 16);
+            int32_t lrc = ensure_list_capacity(h, nrows_c * g.ncx / 32 / LIST_BLOCK + isomc_count_list_max_warps(h->sms) + 16);
             if (lrc) return lrc;
         } else {
             CU(h, cudaMalloc(&h->segpre, (nrows_c * g.nsegx + 4) * sizeof(uint32_t)));

@@ -93,6 +93,7 @@ struct EmitTab {
     uint8_t owner[8][12];     /* [b][e]: d | e' << 4 */
     uint8_t ends[12];
     uint8_t ntri[256];
+    uint8_t rank3[256];       /* interior cells: rank of e5 | e6 << 2 | e10 << 4 among the three edges such a cell creates */
     uint8_t pad[4];
 };
 
@@ -105,6 +106,7 @@ static inline void isomc_build_emit_tab(const McTables &m, EmitTab *t) {
     memcpy(t->owner, m.owner, sizeof t->owner);
     memcpy(t->ends, m.ends, sizeof t->ends);
     memcpy(t->ntri, m.ntri, sizeof t->ntri);
+    memcpy(t->rank3, m.rank3, sizeof t->rank3);
     for (int b = 0; b < 8; ++b)
         for (int e = 0; e < 12; ++e) t->stepedges[b][m.owner[b][e] & 7] |= (uint16_t)(1u << e);
 }
@@ -132,43 +134,132 @@ struct EmitArgs {
     uint32_t *idx;
 };
 
+/* entry of the active cell (x2, row2): position from the segment record, then { id of its first vertex, cube index } */
+ISOMC_HD void creator_lookup(const Geo &g, const ListBufs &L, const uint32_t *rowPV, uint32_t x2, uint32_t row2, uint32_t &vid2,
+                             uint32_t &ci2) {
+    const uint2 rec = L.segrec[(uint64_t)row2 * g.nsegx + (x2 >> 5)];
+    const uint32_t k2 = rec.x + hd_popc(rec.y & ((1u << (x2 & 31u)) - 1u));
+    vid2 = 0; ci2 = 0;
+    if (k2 < L.cap_blocks * LIST_BLOCK) { /* (out of range only after a list overflow; the host re-runs then) */
+        const uint2 e2 = L.ent[k2];
+        vid2 = rowPV[row2] + (e2.x & 0xFFFFu);
+        ci2 = e2.y >> 16 & 255u;
+    }
+}
+
 /*
- * One active cell.  eid = 12 words of scratch (stride eid_stride) for the ids of the cell's crossed edges.
- * Src::at(g, x, y, lz) is the sample at a lattice point of the handle's slab.
+ * One active cell: list entry k = (ea, yz).  eid = 12 words of scratch (stride eid_stride) for the ids of the cell's
+ * crossed edges.  Src::at(g, x, y, lz) is the sample at a lattice point of the handle's slab.
  */
 template <class Src>
-ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const ListBufs &L, const EmitArgs &A, uint2 ea,
-                        uint32_t yz, uint32_t *eid, uint32_t eid_stride) {
+ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const ListBufs &L, const EmitArgs &A, uint64_t k,
+                        uint2 ea, uint32_t yz, uint32_t *eid, uint32_t eid_stride) {
     const uint32_t x = ea.y & 0xFFFFu, ci = ea.y >> 16 & 255u, y = yz & 0xFFFFu, lz = yz >> 16;
     if (lz < A.first_own_layer) return; /* ghost layer of a slab: looked up by our first layer, emitted by the previous rank */
     const uint32_t row = lz * g.ncx + y;
-    const uint32_t bfl = cell_flags(g, x, y, lz);
     const uint32_t em = T.emask[ci];
     const uint32_t vid = A.rowPV[row] + (ea.x & 0xFFFFu);
-    const uint32_t owned = em & T.ownmask[bfl];
+    uint32_t owned;
 
-    /* ids of the crossed edges, creator by creator */
-    for (uint32_t m = owned; m; m &= m - 1) {
-        const uint32_t e = hd_ffs0(m);
-        eid[e * eid_stride] = vid + hd_popc(T.before[ci][e] & owned);
-    }
-    for (uint32_t d = 1; d < 8; ++d) {
-        uint32_t es = em & T.stepedges[bfl][d];
-        if (!es) continue;
-        const uint32_t x2 = x - (d & 1u), y2 = y - (d >> 1 & 1u), lz2 = lz - (d >> 2 & 1u);
-        const uint32_t row2 = lz2 * g.ncx + y2;
-        const uint2 rec = L.segrec[(uint64_t)row2 * g.nsegx + (x2 >> 5)];
-        const uint64_t k2 = (uint64_t)rec.x + hd_popc(rec.y & ((1u << (x2 & 31u)) - 1u));
-        uint32_t vid2 = 0, ci2 = 0;
-        if (k2 < (uint64_t)L.cap_blocks * LIST_BLOCK) { /* (garbage only after a list overflow; the host re-runs then) */
-            const uint2 e2 = L.ent[k2];
-            vid2 = A.rowPV[row2] + (e2.x & 0xFFFFu);
-            ci2 = e2.y >> 16 & 255u;
+    if (x >= 2 && y >= 2 && g.gz0 + lz >= 2) {
+        /* Interior cell whose six possible creators are interior too: every cell involved creates exactly its crossed
+         * e5 (y edge), e6 (x edge), e10 (z edge), numbered by rank3[] of its own case.  Which earlier cell created
+         * which of my edges (isomc_tables.h owner[0][]):  -x: e7 as e5, e11 as e10;  -y: e4 as e6, e9 as e10;
+         * -x-y: e8 as e10;  -z: e1 as e5, e2 as e6;  -x-z: e3 as e5;  -y-z: e0 as e6.  Straight-line, predicated. */
+        owned = em & (1u << 5 | 1u << 6 | 1u << 10);
+        const uint32_t r3 = T.rank3[ci];
+        eid[5 * eid_stride] = vid + (r3 & 3u);
+        eid[6 * eid_stride] = vid + (r3 >> 2 & 3u);
+        eid[10 * eid_stride] = vid + (r3 >> 4 & 3u);
+        uint32_t v2, c2, q;
+        if (em & (1u << 7 | 1u << 11)) {
+            if (x & 31u) { /* same segment: the previous list entry */
+                const uint2 e2 = L.ent[k - 1];
+                v2 = A.rowPV[row] + (e2.x & 0xFFFFu);
+                c2 = e2.y >> 16 & 255u;
+            } else {
+                creator_lookup(g, L, A.rowPV, x - 1, row, v2, c2);
+            }
+            q = T.rank3[c2];
+            eid[7 * eid_stride] = v2 + (q & 3u);
+            eid[11 * eid_stride] = v2 + (q >> 4 & 3u);
         }
-        const uint32_t own2 = T.ownmask[cell_flags(g, x2, y2, lz2)];
-        for (; es; es &= es - 1) {
-            const uint32_t e = hd_ffs0(es);
-            eid[e * eid_stride] = vid2 + hd_popc(T.before[ci2][T.owner[bfl][e] >> 4] & own2);
+        if (em & (1u << 4 | 1u << 9)) {
+            creator_lookup(g, L, A.rowPV, x, row - 1, v2, c2);
+            q = T.rank3[c2];
+            eid[4 * eid_stride] = v2 + (q >> 2 & 3u);
+            eid[9 * eid_stride] = v2 + (q >> 4 & 3u);
+        }
+        if (em & (1u << 8)) {
+            creator_lookup(g, L, A.rowPV, x - 1, row - 1, v2, c2);
+            eid[8 * eid_stride] = v2 + (T.rank3[c2] >> 4 & 3u);
+        }
+        if (em & (1u << 1 | 1u << 2)) {
+            creator_lookup(g, L, A.rowPV, x, row - g.ncx, v2, c2);
+            q = T.rank3[c2];
+            eid[1 * eid_stride] = v2 + (q & 3u);
+            eid[2 * eid_stride] = v2 + (q >> 2 & 3u);
+        }
+        if (em & (1u << 3)) {
+            creator_lookup(g, L, A.rowPV, x - 1, row - g.ncx, v2, c2);
+            eid[3 * eid_stride] = v2 + (T.rank3[c2] & 3u);
+        }
+        if (em & 1u) {
+            creator_lookup(g, L, A.rowPV, x, row - g.ncx - 1, v2, c2);
+            eid[0] = v2 + (T.rank3[c2] >> 2 & 3u);
+        }
+        /* the (at most three) vertices this cell creates all end at corner 6 = (x+1, y+1, z+1):
+         *   e5 = corners 5 -> 6 (y edge), e6 = corners 6 -> 7 (x edge), e10 = corners 2 -> 6 (z edge) */
+        if (owned) {
+            const bool o5 = (em >> 5 & 1u) != 0, o6 = (em >> 6 & 1u) != 0, o10 = (em >> 10 & 1u) != 0;
+            float s6, s5, s7, s2;
+            src.corner6(g, x, y, lz, o5, o6, o10, s6, s5, s7, s2);
+            const float fx0 = hd_mul((float)x, g.inv), fx1 = hd_mul((float)(x + 1), g.inv);
+            const float fy0 = hd_mul((float)y, g.inv), fy1 = hd_mul((float)(y + 1), g.inv);
+            const float fz0 = hd_mul((float)(g.gz0 + lz), g.inv), fz1 = hd_mul((float)(g.gz0 + lz + 1), g.inv);
+            const uint64_t s0 = (uint64_t)(vid - A.ghostV);
+            if (o5 && s0 + (r3 & 3u) < A.cap_v) {
+                const float delta = hd_sub(s6, s5), t = (delta == 0.0f) ? 0.5f : hd_div(-s5, delta), omt = hd_sub(1.0f, t);
+                float *o = A.xyz + 3 * (s0 + (r3 & 3u));
+                o[0] = hd_add(hd_mul(fx1, omt), hd_mul(fx1, t));
+                o[1] = hd_add(hd_mul(fy0, omt), hd_mul(fy1, t));
+                o[2] = hd_add(hd_mul(fz1, omt), hd_mul(fz1, t));
+            }
+            if (o6 && s0 + (r3 >> 2 & 3u) < A.cap_v) {
+                const float delta = hd_sub(s7, s6), t = (delta == 0.0f) ? 0.5f : hd_div(-s6, delta), omt = hd_sub(1.0f, t);
+                float *o = A.xyz + 3 * (s0 + (r3 >> 2 & 3u));
+                o[0] = hd_add(hd_mul(fx1, omt), hd_mul(fx0, t));
+                o[1] = hd_add(hd_mul(fy1, omt), hd_mul(fy1, t));
+                o[2] = hd_add(hd_mul(fz1, omt), hd_mul(fz1, t));
+            }
+            if (o10 && s0 + (r3 >> 4 & 3u) < A.cap_v) {
+                const float delta = hd_sub(s6, s2), t = (delta == 0.0f) ? 0.5f : hd_div(-s2, delta), omt = hd_sub(1.0f, t);
+                float *o = A.xyz + 3 * (s0 + (r3 >> 4 & 3u));
+                o[0] = hd_add(hd_mul(fx1, omt), hd_mul(fx1, t));
+                o[1] = hd_add(hd_mul(fy1, omt), hd_mul(fy1, t));
+                o[2] = hd_add(hd_mul(fz0, omt), hd_mul(fz1, t));
+            }
+            owned = 0; /* done here */
+        }
+    } else {
+        /* on or next to a low boundary face: creators and ranks through the general tables */
+        const uint32_t bfl = cell_flags(g, x, y, lz);
+        owned = em & T.ownmask[bfl];
+        for (uint32_t m = owned; m; m &= m - 1) {
+            const uint32_t e = hd_ffs0(m);
+            eid[e * eid_stride] = vid + hd_popc(T.before[ci][e] & owned);
+        }
+        for (uint32_t d = 1; d < 8; ++d) {
+            uint32_t es = em & T.stepedges[bfl][d];
+            if (!es) continue;
+            const uint32_t x2 = x - (d & 1u), y2 = y - (d >> 1 & 1u), lz2 = lz - (d >> 2 & 1u);
+            uint32_t vid2, ci2;
+            creator_lookup(g, L, A.rowPV, x2, lz2 * g.ncx + y2, vid2, ci2);
+            const uint32_t own2 = T.ownmask[cell_flags(g, x2, y2, lz2)];
+            for (; es; es &= es - 1) {
+                const uint32_t e = hd_ffs0(es);
+                eid[e * eid_stride] = vid2 + hd_popc(T.before[ci2][T.owner[bfl][e] >> 4] & own2);
+            }
         }
     }
 
@@ -194,12 +285,13 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
     }
 
     /* triangles in table order (march_cube, marching_cubes_impl.rs:106-116) */
-    const uint32_t nt = T.ntri[ci];
     const uint64_t tslot = (uint64_t)(A.rowPT[row] + (ea.x >> 16) - A.ghostT);
+    uint32_t nt = T.ntri[ci];
+    if (tslot >= A.cap_t) nt = 0;
+    else if (tslot + nt > A.cap_t) nt = (uint32_t)(A.cap_t - tslot);
     uint64_t tri = T.tri[ci];
-    for (uint32_t t = 0; t < nt; ++t, tri >>= 12) {
-        if (tslot + t >= A.cap_t) break;
-        uint32_t *o = A.idx + 3 * (tslot + t);
+    uint32_t *o = A.idx + 3 * tslot;
+    for (uint32_t t = 0; t < nt; ++t, tri >>= 12, o += 3) {
         o[0] = eid[((uint32_t)tri & 15u) * eid_stride] + A.vofs;
         o[1] = eid[((uint32_t)tri >> 4 & 15u) * eid_stride] + A.vofs;
         o[2] = eid[((uint32_t)tri >> 8 & 15u) * eid_stride] + A.vofs;
@@ -277,25 +369,26 @@ ISOMC_HD uint32_t seg_planes_count(uint32_t p0, uint32_t p1, uint32_t p2, uint32
     return hd_popc(p0 & m) + 2 * hd_popc(p1 & m) + 4 * hd_popc(p2 & m) + 8 * hd_popc(p3 & m);
 }
 
-/* natural cube index of cell i of a segment: bits i, i+1 of the four rows */
+/* natural cube index of cell i of a segment: bits i, i+1 of the four rows (bit 32 = bit 0 of the next word, in nb) */
 ISOMC_HD uint32_t seg_cube_index(uint32_t a0, uint32_t b0, uint32_t c0, uint32_t d0, uint32_t nb, uint32_t i) {
-    const uint32_t hi = i == 31 ? 1u : 0u; /* bit i+1 lives in the next word */
-    const uint32_t a = hi ? (a0 >> 31) | (nb & 1u) << 1 : (a0 >> i) & 3u;
-    const uint32_t b = hi ? (b0 >> 31) | (nb >> 1 & 1u) << 1 : (b0 >> i) & 3u;
-    const uint32_t c = hi ? (c0 >> 31) | (nb >> 2 & 1u) << 1 : (c0 >> i) & 3u;
-    const uint32_t d = hi ? (d0 >> 31) | (nb >> 3 & 1u) << 1 : (d0 >> i) & 3u;
-    return a | b << 2 | c << 4 | d << 6;
+    return (hd_funnel_r(a0, nb, i) & 3u) | (hd_funnel_r(b0, nb >> 1, i) & 3u) << 2 | (hd_funnel_r(c0, nb >> 2, i) & 3u) << 4 |
+           (hd_funnel_r(d0, nb >> 3, i) & 3u) << 6;
+}
+
+/* nth8[m * 8 + j] = position of the j-th set bit of the byte m (256 x 8 bytes, built by nth8_fill) */
+ISOMC_HD void nth8_fill(uint8_t *nth8, uint32_t m) {
+    uint32_t j = 0;
+    for (uint32_t b = 0; b < 8; ++b)
+        if (m >> b & 1u) nth8[m * 8 + j++] = (uint8_t)b;
+    for (; j < 8; ++j) nth8[m * 8 + j] = 0;
 }
 
 /* position of the j-th (0-based) set bit of m; j < popc(m) */
-ISOMC_HD uint32_t nth_set_bit(uint32_t m, uint32_t j) {
-    uint32_t pos = 0, c;
-    c = hd_popc(m & 0xFFFFu);            if (j >= c) { pos = 16; j -= c; }
-    c = hd_popc((m >> pos) & 0xFFu);     if (j >= c) { pos += 8; j -= c; }
-    c = hd_popc((m >> pos) & 0xFu);      if (j >= c) { pos += 4; j -= c; }
-    c = hd_popc((m >> pos) & 0x3u);      if (j >= c) { pos += 2; j -= c; }
-    c = (m >> pos) & 1u;                 if (j >= c) { pos += 1; }
-    return pos;
+ISOMC_HD uint32_t nth_set_bit(const uint8_t *nth8, uint32_t m, uint32_t j) {
+    const uint32_t c0 = hd_popc(m & 0xFFu), c1 = hd_popc(m & 0xFFFFu), c2 = hd_popc(m & 0xFFFFFFu);
+    const uint32_t byte = (j >= c0 ? 1u : 0u) + (j >= c1 ? 1u : 0u) + (j >= c2 ? 1u : 0u);
+    const uint32_t before = j >= c2 ? c2 : (j >= c1 ? c1 : (j >= c0 ? c0 : 0u));
+    return byte * 8 + nth8[((m >> (8 * byte)) & 0xFFu) * 8 + (j - before)];
 }
 
 
@@ -331,6 +424,17 @@ ISOMC_HD uint32_t w_shfl_up(const Warp &w, uint32_t v, uint32_t d) {
     return isomc_emu_shfl(w.emu, w.lane, v, w.lane >= d ? w.lane - d : w.lane);
 #else
     return v;
+#endif
+}
+ISOMC_HD bool w_any(const Warp &w, bool pred) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(0xFFFFFFFFu, pred) != 0;
+#elif defined(ISOMC_HOST_MODEL)
+    uint32_t v = pred ? 1u : 0u;
+    for (uint32_t d = 1; d < 32; d <<= 1) v |= isomc_emu_shfl(w.emu, w.lane, v, w.lane ^ d);
+    return v != 0;
+#else
+    return pred;
 #endif
 }
 ISOMC_HD void w_sync(const Warp &w) {
@@ -421,7 +525,8 @@ struct CountOut {
  *   else: the pass is a 32-segment chunk of ONE row: prefixes continue from t_row, the caller posts the total.
  */
 template <bool ROWS>
-ISOMC_HD uint32_t list_phase_b(const Warp &w, const ListBufs &L, const uint8_t *s_ntri, const SegClass &C, uint32_t cpos,
+ISOMC_HD uint32_t list_phase_b(const Warp &w, const ListBufs &L, const uint8_t *s_ntri, const uint8_t *nth8, const SegClass &C,
+                               uint32_t cpos,
                                uint32_t cend, uint32_t vpre, uint32_t yznb, uint32_t n_cells, uint32_t base, bool ok,
                                uint32_t gshift, uint32_t seg0, uint32_t row_first, uint32_t t_row, uint32_t *Rsm,
                                const CountOut &out) {
@@ -443,7 +548,7 @@ ISOMC_HD uint32_t list_phase_b(const Warp &w, const ListBufs &L, const uint8_t *
         const uint32_t p0 = w_shfl(w, C.p0, seg), p1 = w_shfl(w, C.p1, seg);
         const uint32_t p2 = w_shfl(w, C.p2, seg), p3 = w_shfl(w, C.p3, seg);
         const uint32_t vp = w_shfl(w, vpre, seg), yz = w_shfl(w, yznb, seg);
-        const uint32_t i = live ? nth_set_bit(am, k - sc) : 0u;
+        const uint32_t i = live ? nth_set_bit(nth8, am, k - sc) : 0u;
         const uint32_t ci = seg_cube_index(a0, b0, c0, d0, yz >> 26, i);
         const uint32_t nt = live ? (uint32_t)s_ntri[ci] : 0u;
         const uint32_t vrel = vp + seg_planes_count(p0, p1, p2, p3, (1u << i) - 1u);
@@ -497,7 +602,8 @@ ISOMC_HD void seg_clear(SegClass &C) {
 /* One warp's share of cell rows [row0, row1): warp gwarp of nwarps.  WIDE = rows of more than 32 segments (one row
  * per warp pass, 32-segment chunks); else a pass covers 32 >> gshift rows of 1 << gshift segments. */
 template <bool WIDE>
-ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs, const uint8_t *s_ntri, const ListBufs &L,
+ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs, const uint8_t *s_ntri, const uint8_t *nth8,
+                              const ListBufs &L,
                               const CountOut &out, uint32_t gshift, uint32_t row0, uint32_t row1, uint32_t gwarp,
                               uint32_t nwarps, uint32_t *Rsm) {
     const uint32_t lane = w.lane;
@@ -510,12 +616,16 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
             const uint32_t row = row0 + it * rpw + sub;
             const bool valid = row < row1 && s < g.nsegx;
             const uint32_t rowc = row < row1 ? row : row1 - 1;
-            const uint32_t lz = rowc / g.ncx, y = rowc - lz * g.ncx;
+            const uint32_t lz = (uint32_t)(((uint64_t)rowc * g.row_magic) >> 40), y = rowc - lz * g.ncx; /* rowc / ncx */
             SegClass C;
             seg_clear(C);
             uint32_t nv = 0;
             if (valid && load_classify(g, signs, row, lz, y, s, C)) nv = seg_planes_count(C.p0, C.p1, C.p2, C.p3, 0xFFFFFFFFu);
             const uint32_t na = hd_popc(C.act);
+            if (!w_any(w, na != 0)) { /* nothing active in the whole pass */
+                if (s == 0 && row < row1) { out.rowV[row] = 0; out.rowT[row] = 0; out.rowA[row] = 0; }
+                continue;
+            }
             /* scans within the row (lanes [sub * G, sub * G + G)) */
             uint32_t inc = nv, rinc = na;
             for (uint32_t d = 1; d < G; d <<= 1) {
@@ -536,12 +646,12 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
             bool ok;
             const uint32_t base = list_alloc(w, L, cur, n_cells, ok);
             if (na && ok) L.segrec[(uint64_t)row * g.nsegx + s] = make_uint2(base + cpos, C.act);
-            list_phase_b<true>(w, L, s_ntri, C, cpos, cpos + na, vpre, y | lz << 13 | C.nb << 26, n_cells, base, ok, gshift, 0u,
+            list_phase_b<true>(w, L, s_ntri, nth8, C, cpos, cpos + na, vpre, y | lz << 13 | C.nb << 26, n_cells, base, ok, gshift, 0u,
                                row0 + it * rpw, 0u, Rsm, out);
         }
     } else {
         for (uint32_t row = row0 + gwarp; row < row1; row += nwarps) {
-            const uint32_t lz = row / g.ncx, y = row - lz * g.ncx;
+            const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40), y = row - lz * g.ncx; /* row / ncx */
             uint32_t vcarry = 0, tcarry = 0, acarry = 0;
             for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 32) {
                 const uint32_t s = s0 + lane;
@@ -550,16 +660,16 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
                 uint32_t nv = 0;
                 if (s < g.nsegx && load_classify(g, signs, row, lz, y, s, C)) nv = seg_planes_count(C.p0, C.p1, C.p2, C.p3, 0xFFFFFFFFu);
                 const uint32_t na = hd_popc(C.act);
+                if (!w_any(w, na != 0)) continue; /* no active cell, no created vertex */
                 uint32_t n_cells, nv_tot;
                 const uint32_t cpos = w_excl_scan(w, na, n_cells);
-                if (n_cells == 0) continue; /* no active cell, no created vertex */
                 const uint32_t vpre = vcarry + w_excl_scan(w, nv, nv_tot);
                 vcarry += nv_tot;
                 acarry += n_cells;
                 bool ok;
                 const uint32_t base = list_alloc(w, L, cur, n_cells, ok);
                 if (na && ok) L.segrec[(uint64_t)row * g.nsegx + s] = make_uint2(base + cpos, C.act);
-                tcarry += list_phase_b<false>(w, L, s_ntri, C, cpos, cpos + na, vpre, y | lz << 13 | C.nb << 26, n_cells, base, ok,
+                tcarry += list_phase_b<false>(w, L, s_ntri, nth8, C, cpos, cpos + na, vpre, y | lz << 13 | C.nb << 26, n_cells, base, ok,
                                               0u, s0, row, tcarry, Rsm, out);
             }
             if (lane == 0) {

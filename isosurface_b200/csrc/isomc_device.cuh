@@ -27,6 +27,7 @@ struct Geo {
     uint32_t gz0;    /* global z of local layer 0 */
     uint32_t ghost;  /* 1: local cell layer 0 belongs to the previous slab (counted, not emitted) */
     float inv;       /* 1.0f / (float)(N-1)   (primal_grid.rs:44-45) */
+    uint64_t row_magic; /* ceil(2^40 / ncx): row / ncx == (row * row_magic) >> 40 for row < 2^26, ncx < 2^13 */
 };
 
 struct SdfProgram {
@@ -194,7 +195,25 @@ struct GridSrc {
     __device__ __forceinline__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
         return __ldg(p + ((uint64_t)lz * g.N + y) * g.N + x);
     }
+    /* samples at corner 6 = (x+1, y+1, lz+1) of a cell and, where needed, at corners 5 (-y), 7 (-x), 2 (-z) */
+    __device__ __forceinline__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n7, bool n2, float &s6,
+                                            float &s5, float &s7, float &s2) const {
+        const float *q = p + ((uint64_t)(lz + 1) * g.N + (y + 1)) * g.N + (x + 1);
+        s6 = __ldg(q);
+        s5 = n5 ? __ldg(q - g.N) : 0.0f;
+        s7 = n7 ? __ldg(q - 1) : 0.0f;
+        s2 = n2 ? __ldg(q - (uint64_t)g.N * g.N) : 0.0f;
+    }
 };
+/* corner6() for sources that evaluate instead of loading */
+#define ISOMC_CORNER6_BY_AT                                                                                                     \
+    __device__ __forceinline__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n7, bool n2, float &s6, \
+                                            float &s5, float &s7, float &s2) const {                                            \
+        s6 = at(g, x + 1, y + 1, lz + 1);                                                                                        \
+        s5 = n5 ? at(g, x + 1, y, lz + 1) : 0.0f;                                                                                \
+        s7 = n7 ? at(g, x, y + 1, lz + 1) : 0.0f;                                                                                \
+        s2 = n2 ? at(g, x + 1, y + 1, lz) : 0.0f;                                                                                \
+    }
 struct SdfSrc {
     SdfProgram prog;
     __device__ __forceinline__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
@@ -202,6 +221,7 @@ struct SdfSrc {
         return sdf_eval(prog, __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv),
                         __fmul_rn((float)(g.gz0 + lz), g.inv));
     }
+    ISOMC_CORNER6_BY_AT
 };
 struct SdfChainSrc {
     SdfChain chain;
@@ -209,6 +229,7 @@ struct SdfChainSrc {
         return sdf_chain_eval(chain, __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv),
                               __fmul_rn((float)(g.gz0 + lz), g.inv));
     }
+    ISOMC_CORNER6_BY_AT
 };
 
 #endif

@@ -311,8 +311,10 @@ __device__ __forceinline__ T block_excl_scan_256(T v, T *s_warp, T &total) {
 __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t *__restrict__ rowV, uint32_t *__restrict__ rowT,
                                                    const unsigned long long *__restrict__ layerTot,
                                                    unsigned long long *__restrict__ totals,
-                                                   const uint32_t *__restrict__ list_ctr, uint32_t lz_first) {
+                                                   const uint32_t *__restrict__ list_ctr, uint32_t *__restrict__ list_mark,
+                                                   uint32_t lz_first) {
     __shared__ unsigned long long s_w[8];
+    if (list_mark && blockIdx.x == 0 && threadIdx.x == 0) *list_mark = *list_ctr; /* list blocks handed out up to this z-chunk */
     __shared__ unsigned long long s_base[2];
     const uint32_t lz = lz_first + blockIdx.x;
     /* base = sum of the totals of the layers below (<= 4096 values) */
@@ -907,8 +909,9 @@ cudaError_t isomc_launch_count(const Geo &g, const uint32_t *signs, const McTabl
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_scan(const Geo &g, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
-                              unsigned long long *totals, const uint32_t *list_ctr, uint32_t lz0, uint32_t lz1, cudaStream_t st) {
-    k_scan_rows<<<lz1 - lz0, 256, 0, st>>>(g, rowV, rowT, layerTot, totals, list_ctr, lz0);
+                              unsigned long long *totals, const uint32_t *list_ctr, uint32_t *list_mark, uint32_t lz0, uint32_t lz1,
+                              cudaStream_t st) {
+    k_scan_rows<<<lz1 - lz0, 256, 0, st>>>(g, rowV, rowT, layerTot, totals, list_ctr, list_mark, lz0);
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,

@@ -28,7 +28,8 @@ cudaError_t isomc_launch_count(const Geo &g, const uint32_t *signs, const McTabl
                                uint32_t *rowV, uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot,
                                uint32_t lz0, uint32_t lz1, int sms, int ctas_per_sm, cudaStream_t st);
 cudaError_t isomc_launch_scan(const Geo &g, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
-                              unsigned long long *totals, const uint32_t *list_ctr, uint32_t lz0, uint32_t lz1, cudaStream_t st);
+                              unsigned long long *totals, const uint32_t *list_ctr, uint32_t *list_mark, uint32_t lz0, uint32_t lz1,
+                              cudaStream_t st);
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,
                                     cudaStream_t st);
 int isomc_emit_layers_per_brick();
@@ -49,11 +50,10 @@ cudaError_t isomc_launch_synth(const SynthParams &sp, uint32_t size, uint32_t z_
                                int sms, cudaStream_t st);
 
 /* active-cell-list path (isomc_list_kernels.cu): count + list build, emission incl. vertex positions */
-uint32_t isomc_count_list_max_warps(int sms, int ctas_per_sm);
+uint32_t isomc_count_list_max_warps(int sms);
 cudaError_t isomc_launch_count_list(const Geo &g, const uint32_t *signs, const McTables *tabs, const ListBufs &L, uint32_t *rowV,
                                     uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot, uint32_t lz0, uint32_t lz1,
-                                    int sms, int ctas_per_sm, cudaStream_t st);
-cudaError_t isomc_launch_list_mark(const uint32_t *ctr, uint32_t *dst, cudaStream_t st);
+                                    int sms, cudaStream_t st);
 /* list blocks [*blk_first, *blk_end) (device pointers; blk_first == NULL: from block 0) */
 cudaError_t isomc_launch_emit_list_grid(const Geo &g, const float *d_grid, const ListBufs &L, const EmitTab *tab,
                                         const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,

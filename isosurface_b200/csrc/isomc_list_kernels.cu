@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "isomc_cell.cuh"
 #include "isomc_kernels.h"
@@ -25,22 +26,18 @@
 namespace {
 
 /* cell rows [row0, row1); the body is count_list_warp() of isomc_cell.cuh (shared with the host model) */
-template <bool WIDE>
-__global__ void __launch_bounds__(256) k_count_list(Geo g, const uint32_t *__restrict__ signs, const uint8_t *__restrict__ ntri_g,
+template <bool WIDE, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_count_list(Geo g, const uint32_t *__restrict__ signs, const uint8_t *__restrict__ ntri_g,
                                                     ListBufs L, CountOut out, uint32_t gshift, uint32_t row0, uint32_t row1) {
     __shared__ uint8_t s_ntri[256];
     __shared__ uint32_t s_R[8][32];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = ntri_g[i];
+    __shared__ uint8_t s_nth8[256 * 8];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_ntri[i] = ntri_g[i]; nth8_fill(s_nth8, (uint32_t)i); }
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5;
     const Warp w{threadIdx.x & 31u, nullptr};
-    count_list_warp<WIDE>(w, g, signs, s_ntri, L, out, gshift, row0, row1, blockIdx.x * (blockDim.x >> 5) + warp,
+    count_list_warp<WIDE>(w, g, signs, s_ntri, s_nth8, L, out, gshift, row0, row1, blockIdx.x * (blockDim.x >> 5) + warp,
                           gridDim.x * (blockDim.x >> 5), s_R[warp]);
-}
-
-/* device-side copy of the block counter (end of a z-chunk's part of the list) */
-__global__ void k_list_mark(const uint32_t *__restrict__ ctr, uint32_t *__restrict__ dst) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *ctr;
 }
 
 /* list blocks [*blk_first, *blk_end): one CTA per block, one lane per entry */
@@ -74,7 +71,7 @@ __global__ void __launch_bounds__(LIST_BLOCK) k_emit_list(Src src, Geo g, ListBu
         const uint32_t fill = L.blkfill[b];
         if (threadIdx.x < fill) {
             const uint64_t k = (uint64_t)b * LIST_BLOCK + threadIdx.x;
-            emit_cell(g, src, T, L, A, L.ent[k], L.ent_yz[k], s_eid + threadIdx.x, LIST_BLOCK);
+            emit_cell(g, src, T, L, A, k, L.ent[k], L.ent_yz[k], s_eid + threadIdx.x, LIST_BLOCK);
         }
     }
 }
@@ -105,29 +102,46 @@ cudaError_t launch_emit_list(const Src &src, const Geo &g, const ListBufs &L, co
 
 } /* namespace */
 
+/* CTAs per SM of k_count_list: 4 = 64 registers, 5 = 48, 6 = 40 with a few spills (ISOMC_LIST_MINB, default 4: measured best on the dense field) */
+static int count_list_minb() {
+    static int v = 0;
+    if (v == 0) {
+        const char *p = getenv("ISOMC_LIST_MINB");
+        v = p ? atoi(p) : 4;
+        if (v != 4 && v != 5 && v != 6) v = 4;
+    }
+    return v;
+}
+
 /* warps k_count_list may run: each can strand one partly filled block */
-uint32_t isomc_count_list_max_warps(int sms, int ctas_per_sm) { return (uint32_t)(sms * ctas_per_sm * 8); }
+uint32_t isomc_count_list_max_warps(int sms) { return (uint32_t)(sms * 6 * 8); }
+
+template <bool WIDE>
+static void launch_count_list_v(uint32_t grid, cudaStream_t st, const Geo &g, const uint32_t *signs, const uint8_t *ntri,
+                                const ListBufs &L, const CountOut &out, uint32_t gshift, uint32_t row0, uint32_t row1) {
+    switch (count_list_minb()) {
+    default: k_count_list<WIDE, 4><<<grid, 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1); break;
+    case 6: k_count_list<WIDE, 6><<<grid, 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1); break;
+    case 5: k_count_list<WIDE, 5><<<grid, 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1); break;
+    }
+}
 
 cudaError_t isomc_launch_count_list(const Geo &g, const uint32_t *signs, const McTables *tabs, const ListBufs &L, uint32_t *rowV,
                                     uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot, uint32_t lz0, uint32_t lz1,
-                                    int sms, int ctas_per_sm, cudaStream_t st) {
+                                    int sms, cudaStream_t st) {
     uint32_t gshift = 0;
     while ((1u << gshift) < g.nsegx && gshift < 5) ++gshift;
     const uint32_t row0 = lz0 * g.ncx, row1 = lz1 * g.ncx;
     const uint8_t *ntri = reinterpret_cast<const uint8_t *>(tabs) + offsetof(McTables, ntri);
     const CountOut out{rowV, rowT, rowA, layerTot};
+    const int per_sm = count_list_minb();
     if (g.nsegx <= 32) {
         const uint32_t rpw = 32u >> gshift;
         const uint64_t warps = ((uint64_t)(row1 - row0) + rpw - 1) / rpw;
-        k_count_list<false><<<grid_for(warps, sms, 8, ctas_per_sm), 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1);
+        launch_count_list_v<false>(grid_for(warps, sms, 8, per_sm), st, g, signs, ntri, L, out, gshift, row0, row1);
     } else {
-        k_count_list<true><<<grid_for(row1 - row0, sms, 8, ctas_per_sm), 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1);
+        launch_count_list_v<true>(grid_for(row1 - row0, sms, 8, per_sm), st, g, signs, ntri, L, out, gshift, row0, row1);
     }
-    return cudaGetLastError();
-}
-
-cudaError_t isomc_launch_list_mark(const uint32_t *ctr, uint32_t *dst, cudaStream_t st) {
-    k_list_mark<<<1, 32, 0, st>>>(ctr, dst);
     return cudaGetLastError();
 }
 

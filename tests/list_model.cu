@@ -50,7 +50,7 @@ struct WarpJob {
     bool wide;
     Geo g;
     const uint32_t *signs;
-    const uint8_t *ntri;
+    const uint8_t *ntri, *nth8;
     ListBufs L;
     CountOut out;
     uint32_t gshift, row0, row1, gwarp, nwarps;
@@ -61,8 +61,8 @@ WarpJob *g_job = nullptr;
 void lane_main(int lane) {
     WarpJob &J = *g_job;
     const Warp w{(uint32_t)lane, (void *)g_emu};
-    if (J.wide) count_list_warp<true>(w, J.g, J.signs, J.ntri, J.L, J.out, J.gshift, J.row0, J.row1, J.gwarp, J.nwarps, J.Rsm);
-    else count_list_warp<false>(w, J.g, J.signs, J.ntri, J.L, J.out, J.gshift, J.row0, J.row1, J.gwarp, J.nwarps, J.Rsm);
+    if (J.wide) count_list_warp<true>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.gwarp, J.nwarps, J.Rsm);
+    else count_list_warp<false>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.gwarp, J.nwarps, J.Rsm);
     g_emu->done[lane] = true;
 }
 
@@ -95,6 +95,13 @@ void run_warp(Emu &E, WarpJob &J) {
 struct HostGridSrc {
     const float *p;
     __host__ __device__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const { return p[((uint64_t)lz * g.N + y) * g.N + x]; }
+    __host__ __device__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n7, bool n2, float &s6, float &s5,
+                                     float &s7, float &s2) const {
+        s6 = at(g, x + 1, y + 1, lz + 1);
+        s5 = n5 ? at(g, x + 1, y, lz + 1) : 0.0f;
+        s7 = n7 ? at(g, x, y + 1, lz + 1) : 0.0f;
+        s2 = n2 ? at(g, x + 1, y + 1, lz) : 0.0f;
+    }
 };
 
 }  // namespace
@@ -132,6 +139,7 @@ int list_model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const fl
     g.ncl = (g.ncx == 0) ? 0 : (z_end - z_begin + g.ghost);
     g.nsl = g.ncl + 1;
     g.inv = 1.0f / (float)(size - 1);
+    g.row_magic = g.ncx ? ((1ull << 40) + g.ncx - 1) / g.ncx : 0;
     memset(out_totals, 0, 6 * sizeof(uint64_t));
     if (g.ncl == 0) return 0;
 
@@ -167,11 +175,13 @@ int list_model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const fl
         st = st * 6364136223846793005ull + 1442695040888963407ull;
         std::swap(order[i - 1], order[(st >> 33) % i]);
     }
+    std::vector<uint8_t> nth8(256 * 8);
+    for (uint32_t m = 0; m < 256; ++m) nth8_fill(nth8.data(), m);
     static Emu E;
     for (uint32_t wi = 0; wi < n_warps; ++wi) {
         WarpJob J;
         J.wide = g.nsegx > 32;
-        J.g = g; J.signs = signs.data(); J.ntri = mt.ntri; J.L = L; J.out = out;
+        J.g = g; J.signs = signs.data(); J.ntri = mt.ntri; J.nth8 = nth8.data(); J.L = L; J.out = out;
         J.gshift = gshift; J.row0 = 0; J.row1 = (uint32_t)nrows_c; J.gwarp = order[wi]; J.nwarps = n_warps;
         run_warp(E, J);
     }
@@ -225,7 +235,7 @@ int list_model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const fl
     for (uint32_t b = 0; b < ctr; ++b)
         for (uint32_t j = 0; j < blkfill[b]; ++j) {
             const uint64_t k = (uint64_t)b * LIST_BLOCK + j;
-            emit_cell(g, src, et, L, A, ent[k], ent_yz[k], eid + j, LIST_BLOCK);
+            emit_cell(g, src, et, L, A, k, ent[k], ent_yz[k], eid + j, LIST_BLOCK);
         }
     return 0;
 }
