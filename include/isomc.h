@@ -46,7 +46,8 @@ typedef enum isomc_status {
                                        (the reference silently truncates, src/extractor.rs:90-92) */
     ISOMC_ERR_UNSUPPORTED_SOURCE = -5,
     ISOMC_ERR_NO_RESULT = -6,       /* counts/copy-out before any successful extract */
-    ISOMC_ERR_NCCL = -7
+    ISOMC_ERR_NCCL = -7,
+    ISOMC_ERR_BUFFER_TOO_SMALL = -8 /* caller-provided mesh buffers are smaller than the result (which stays on the device) */
 } isomc_status;
 
 /* ---- implicit sources: a postfix program over the crate's shapes -------------------------
@@ -104,6 +105,13 @@ int32_t isomc_extract_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nod
 int32_t isomc_extract_grid_device(isomc_t *h, const float *d_grid);
 /* source = dense lattice in host memory (H2D copy, then as above) */
 int32_t isomc_extract_grid_host(isomc_t *h, const float *h_grid);
+/* host lattice in, host mesh out in ONE call -- what `extract(&DenseGrid, &mut IndexedVertices)` does for a host-resident
+ * grid (reference src/marching_cubes.rs:59-82 + src/extractor.rs:72-93).  The extract is pipelined in z-chunks: the copy-in
+ * of the lattice, the kernels and the copy-out of the finished part of the mesh overlap (use pinned memory for all three
+ * buffers to get the overlap).  xyz holds 3*cap_vertices floats, idx 3*cap_triangles u32.  If the mesh is larger the call
+ * returns ISOMC_ERR_BUFFER_TOO_SMALL with the result left on the device: read isomc_counts(), grow, isomc_copy_out(). */
+int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, uint64_t cap_vertices, uint32_t *idx,
+                                   uint64_t cap_triangles);
 
 /* ---- results:  the two Vecs behind extractor::IndexedVertices --------------------------- */
 int32_t isomc_counts(isomc_t *h, uint64_t *n_vertices, uint64_t *n_triangles, uint64_t *n_active_cells);

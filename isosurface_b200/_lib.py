@@ -13,7 +13,9 @@ LIB_PATH = PKG / "libisomc_b200.so"
 
 OK = 0
 ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_INDEX_OVERFLOW, ERR_UNSUPPORTED_SOURCE, ERR_NO_RESULT, ERR_NCCL = -1, -2, -3, -4, -5, -6, -7
-_ERR_NAMES = {-1: "BAD_ARG", -2: "CUDA", -3: "OOM", -4: "INDEX_OVERFLOW", -5: "UNSUPPORTED_SOURCE", -6: "NO_RESULT", -7: "NCCL"}
+ERR_BUFFER_TOO_SMALL = -8
+_ERR_NAMES = {-1: "BAD_ARG", -2: "CUDA", -3: "OOM", -4: "INDEX_OVERFLOW", -5: "UNSUPPORTED_SOURCE", -6: "NO_RESULT", -7: "NCCL",
+              -8: "BUFFER_TOO_SMALL"}
 
 SDF_SPHERE, SDF_TORUS, SDF_CYLINDER, SDF_PRISM = 1, 2, 3, 4
 SDF_UNION, SDF_INTERSECTION, SDF_DIFFERENCE = 16, 17, 18
@@ -46,6 +48,7 @@ SIGNATURES = {
     "isomc_extract_sdf": (_I32, [_P, _P, _U32]),
     "isomc_extract_grid_device": (_I32, [_P, _P]),
     "isomc_extract_grid_host": (_I32, [_P, _P]),
+    "isomc_extract_grid_host_to": (_I32, [_P, _P, _P, _U64, _P, _U64]),
     "isomc_counts": (_I32, [_P, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
     "isomc_device_buffers": (_I32, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "isomc_copy_out": (_I32, [_P, _P, _P]),

@@ -27,7 +27,8 @@ thread_local std::string g_create_error;
 
 enum SrcKind { SRC_NONE = 0, SRC_GRID = 1, SRC_SDF = 2 };
 constexpr int MAX_CHUNKS = 16;
-constexpr int AUX_WORDS = 2 * MAX_CHUNKS + 4; /* u32 after layerTot: emit tickets [MAX_CHUNKS], list block counter, list marks [MAX_CHUNKS + 1] */
+/* u32 after layerTot: emit tickets [MAX_CHUNKS], list block counter, list marks [MAX_CHUNKS + 1], chunk ends [2 * MAX_CHUNKS] */
+constexpr int AUX_WORDS = 4 * MAX_CHUNKS + 4;
 
 }  // namespace
 
@@ -51,6 +52,11 @@ struct isomc {
     ListBufs L{};
     uint32_t *list_marks = nullptr; /* [c] = list blocks handed out before z-chunk c; [0] = 0 */
     EmitTab *etab = nullptr;
+    /* streamed host-to-host extract (isomc_extract_grid_host_to): copy-in / copy-out streams, per-chunk events */
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_cnt[MAX_CHUNKS] = {}, ev_emit[MAX_CHUNKS] = {};
+    uint32_t *chunk_ends = nullptr;   /* device: {vertices, triangles} below the end of z-chunk c */
+    uint32_t *h_chunk_ends = nullptr; /* pinned copy */
     bool emit_inline = false;       /* what the extract in flight was enqueued with (re-enqueued after a list grow) */
     int64_t vofs_cached = 0; /* value known to be in *vofs (set to 0 at create); -1 = written by the device */
     McTables *tabs = nullptr;
@@ -280,7 +286,7 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
         if (h->profiling) CU(h, cudaEventRecord(h->ev[2], h->stream));
         tl_mark(h, "count", c, st);
         CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, h->list_mode ? h->L.ctr : nullptr,
-                                h->list_mode ? h->list_marks + c + 1 : nullptr, l0, l1, st));
+                                h->list_mode ? h->list_marks + c + 1 : nullptr, nullptr, l0, l1, st));
         if (h->profiling) CU(h, cudaEventRecord(h->ev[3], h->stream));
         h->stats.kernel_launches += 2;
         if (emit_inline) {
@@ -445,6 +451,7 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
         h->ticket = reinterpret_cast<uint32_t *>(h->layerTot + ((size_t)g.ncl * 3 + 4));
         h->L.ctr = h->ticket + MAX_CHUNKS;
         h->list_marks = h->ticket + MAX_CHUNKS + 1;
+        h->chunk_ends = h->ticket + 2 * MAX_CHUNKS + 2;
         CU(h, cudaMalloc(&h->totals, 12 * sizeof(unsigned long long)));
         CU(h, cudaMemset(h->totals, 0, 12 * sizeof(unsigned long long)));
         CU(h, cudaMalloc(&h->vofs, sizeof(uint32_t)));
@@ -454,6 +461,7 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
         CU(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
         for (auto &ev : h->ev_chunk) CU(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CU(h, cudaMallocHost(&h->h_totals, 12 * sizeof(unsigned long long)));
+        CU(h, cudaMallocHost(&h->h_chunk_ends, 2 * MAX_CHUNKS * sizeof(uint32_t)));
         return ISOMC_OK;
     };
     rc = body();
@@ -487,6 +495,14 @@ int32_t isomc_destroy(isomc_t *h) {
     cudaFree(h->xyz); cudaFree(h->idx); cudaFree(h->stage_grid);
     cudaFree(h->L.ent); cudaFree(h->L.ent_yz); cudaFree(h->L.segrec); cudaFree(h->L.blkfill); cudaFree(h->etab);
     if (h->h_totals) cudaFreeHost(h->h_totals);
+    if (h->h_chunk_ends) cudaFreeHost(h->h_chunk_ends);
+    for (int c = 0; c < MAX_CHUNKS; ++c) {
+        if (h->ev_in[c]) cudaEventDestroy(h->ev_in[c]);
+        if (h->ev_cnt[c]) cudaEventDestroy(h->ev_cnt[c]);
+        if (h->ev_emit[c]) cudaEventDestroy(h->ev_emit[c]);
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -582,6 +598,115 @@ int32_t isomc_extract_grid_host(isomc_t *h, const float *h_grid) {
     if (!h->stage_grid) CU(h, cudaMalloc(&h->stage_grid, bytes > 0 ? bytes : 4));
     CU(h, cudaMemcpyAsync(h->stage_grid, h_grid, bytes, cudaMemcpyHostToDevice, h->stream));
     return isomc_extract_grid_device(h, h->stage_grid);
+}
+
+/*
+ * Host lattice in, host mesh out, pipelined in z-chunks (the row scan is causal in z, so a chunk's part of the mesh
+ * is final as soon as the chunk is emitted):
+ *
+ *   s_in   : H2D(0) H2D(1) H2D(2) ...
+ *   stream :        sign/count/scan/emit(0)  sign/count/scan/emit(1) ...
+ *   s_out  :                                 D2H(mesh part 0)        D2H(mesh part 1) ...
+ *
+ * PCIe is full duplex, so the copy-out of the mesh hides behind the copy-in of the lattice; the kernels hide behind
+ * both.  The host only waits for one small event per chunk (how many vertices / triangles lie below the chunk's end).
+ * Needs output buffers from an earlier extract (optimistic emission); the first extract of a handle takes the plain path.
+ */
+int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, uint64_t cap_vertices, uint32_t *idx,
+                                   uint64_t cap_triangles) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h_grid) return fail(h, ISOMC_ERR_BAD_ARG, "h_grid == NULL");
+    if (h->z_begin != 0 || h->z_end != h->size)
+        return fail(h, ISOMC_ERR_BAD_ARG, "this handle is a slab [%u, %u): use the isomc_slab_* calls", h->z_begin, h->z_end);
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    const Geo &g = h->g;
+    const size_t bytes = (size_t)g.N * g.N * g.nsl * sizeof(float);
+    if (!h->stage_grid) CU(h, cudaMalloc(&h->stage_grid, bytes > 0 ? bytes : 4));
+    const bool streamed = g.ncl >= 32 && h->cap_v > 0 && h->cap_t > 0 && !h->profiling && !h->pipeline;
+    bool delivered = false;
+    if (!streamed) {
+        CU(h, cudaMemcpyAsync(h->stage_grid, h_grid, bytes, cudaMemcpyHostToDevice, h->stream));
+        rc = isomc_extract_grid_device(h, h->stage_grid);
+        if (rc) return rc;
+    } else {
+        if (!h->s_in) {
+            CU(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+            CU(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+            for (int c = 0; c < MAX_CHUNKS; ++c) {
+                CU(h, cudaEventCreateWithFlags(&h->ev_in[c], cudaEventDisableTiming));
+                CU(h, cudaEventCreateWithFlags(&h->ev_cnt[c], cudaEventDisableTiming));
+                CU(h, cudaEventCreateWithFlags(&h->ev_emit[c], cudaEventDisableTiming));
+            }
+        }
+        rc = set_vofs(h, 0);
+        if (rc) return rc;
+        h->kind = SRC_GRID; h->d_grid = h->stage_grid;
+        h->have_result = false; h->counted = false; h->emitted = false; h->totals_valid = false;
+        h->stats.kernel_launches = 0; h->stats.emit_reruns = 0;
+        h->emit_inline = true;
+        /* chunk plan: up to MAX_CHUNKS chunks of >= 8 cell layers, multiples of the brick height */
+        {
+            const uint32_t bz = (uint32_t)isomc_emit_layers_per_brick();
+            uint32_t n = g.ncl / 8 < (uint32_t)MAX_CHUNKS ? g.ncl / 8 : (uint32_t)MAX_CHUNKS;
+            if (n < 1) n = 1;
+            const uint32_t per = ((g.ncl + n - 1) / n + bz - 1) / bz * bz;
+            n = (g.ncl + per - 1) / per;
+            h->n_chunks = n;
+            for (uint32_t c = 0; c <= n; ++c) h->chunk_l[c] = c * per < g.ncl ? c * per : g.ncl;
+        }
+        const uint64_t cap_v0 = h->cap_v, cap_t0 = h->cap_t;
+        CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t), h->stream));
+        for (uint32_t c = 0; c < h->n_chunks; ++c) {
+            const uint64_t row0 = (uint64_t)(c == 0 ? 0u : h->chunk_l[c] + 1) * g.N, row1 = (uint64_t)(h->chunk_l[c + 1] + 1) * g.N;
+            CU(h, cudaMemcpyAsync(h->stage_grid + row0 * g.N, h_grid + row0 * g.N, (row1 - row0) * g.N * sizeof(float),
+                                  cudaMemcpyHostToDevice, h->s_in));
+            CU(h, cudaEventRecord(h->ev_in[c], h->s_in));
+        }
+        for (uint32_t c = 0; c < h->n_chunks; ++c) {
+            cudaStream_t st = h->stream;
+            const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
+            const uint32_t row0 = (c == 0 ? 0u : l0 + 1) * g.N, row1 = (l1 + 1) * g.N;
+            CU(h, cudaStreamWaitEvent(st, h->ev_in[c], 0));
+            CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, row0, row1, h->sms, 8, st));
+            if (h->list_mode)
+                CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, st));
+            else
+                CU(h, isomc_launch_count(g, h->signs, h->tabs, h->segpre, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, 8, st));
+            CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, h->list_mode ? h->L.ctr : nullptr,
+                                    h->list_mode ? h->list_marks + c + 1 : nullptr, h->chunk_ends + 2 * c, l0, l1, st));
+            CU(h, cudaMemcpyAsync(h->h_chunk_ends + 2 * c, h->chunk_ends + 2 * c, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(h, cudaEventRecord(h->ev_cnt[c], st));
+            h->stats.kernel_launches += 3;
+            rc = launch_emit_chunk(h, c, st);
+            if (rc) return rc;
+            CU(h, cudaEventRecord(h->ev_emit[c], st));
+        }
+        h->counted = true;
+        h->emitted = true;
+        /* copy-out of each chunk's part of the mesh as soon as its size is known and it is emitted */
+        bool fits = true;
+        uint64_t v_prev = 0, t_prev = 0;
+        for (uint32_t c = 0; c < h->n_chunks && fits; ++c) {
+            CU(h, cudaEventSynchronize(h->ev_cnt[c]));
+            const uint64_t v_end = h->h_chunk_ends[2 * c], t_end = h->h_chunk_ends[2 * c + 1];
+            if (v_end > cap_v0 || t_end > cap_t0 || v_end > cap_vertices || t_end > cap_triangles || !xyz || !idx) { fits = false; break; }
+            CU(h, cudaStreamWaitEvent(h->s_out, h->ev_emit[c], 0));
+            if (v_end > v_prev) CU(h, cudaMemcpyAsync(xyz + 3 * v_prev, h->xyz + 3 * v_prev, (v_end - v_prev) * 12, cudaMemcpyDeviceToHost, h->s_out));
+            if (t_end > t_prev) CU(h, cudaMemcpyAsync(idx + 3 * t_prev, h->idx + 3 * t_prev, (t_end - t_prev) * 12, cudaMemcpyDeviceToHost, h->s_out));
+            v_prev = v_end; t_prev = t_end;
+        }
+        CU(h, cudaStreamSynchronize(h->s_out));
+        rc = finish_impl(h); /* synchronises; grows the list / the output buffers and re-runs what is needed */
+        if (rc) return rc;
+        delivered = fits && h->stats.emit_reruns == 0;
+    }
+    if (h->n_v > cap_vertices || h->n_t > cap_triangles || (h->n_v && !xyz) || (h->n_t && !idx))
+        return fail(h, ISOMC_ERR_BUFFER_TOO_SMALL, "mesh has %llu vertices / %llu triangles, the caller's buffers hold %llu / %llu "
+                    "(the result stays on the device: grow and call isomc_copy_out)", (unsigned long long)h->n_v,
+                    (unsigned long long)h->n_t, (unsigned long long)cap_vertices, (unsigned long long)cap_triangles);
+    if (!delivered) return isomc_copy_out(h, xyz, idx);
+    return ISOMC_OK;
 }
 
 /* ---- results ------------------------------------------------------------------------------ */

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t *__restrict__
                                                    const unsigned long long *__restrict__ layerTot,
                                                    unsigned long long *__restrict__ totals,
                                                    const uint32_t *__restrict__ list_ctr, uint32_t *__restrict__ list_mark,
-                                                   uint32_t lz_first) {
+                                                   uint32_t *__restrict__ chunk_end, uint32_t lz_first) {
     __shared__ unsigned long long s_w[8];
     if (list_mark && blockIdx.x == 0 && threadIdx.x == 0) *list_mark = *list_ctr; /* list blocks handed out up to this z-chunk */
     __shared__ unsigned long long s_base[2];
@@ -347,6 +347,10 @@ __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t *__restrict__
         rowT[lz * g.ncx + y] = pt;
         pv += cv;
         pt += ct;
+    }
+    if (chunk_end && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { /* ids / slots below the end of this z-chunk */
+        chunk_end[0] = (uint32_t)(tv + layerTot[3 * lz]);
+        chunk_end[1] = (uint32_t)(tt + layerTot[3 * lz + 1]);
     }
     if (lz == g.ncl - 1 && threadIdx.x == 0) {
         unsigned long long V = tv + layerTot[3 * lz], T = tt + layerTot[3 * lz + 1], A = ta + layerTot[3 * lz + 2];
@@ -909,9 +913,9 @@ cudaError_t isomc_launch_count(const Geo &g, const uint32_t *signs, const McTabl
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_scan(const Geo &g, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
-                              unsigned long long *totals, const uint32_t *list_ctr, uint32_t *list_mark, uint32_t lz0, uint32_t lz1,
-                              cudaStream_t st) {
-    k_scan_rows<<<lz1 - lz0, 256, 0, st>>>(g, rowV, rowT, layerTot, totals, list_ctr, list_mark, lz0);
+                              unsigned long long *totals, const uint32_t *list_ctr, uint32_t *list_mark, uint32_t *chunk_end,
+                              uint32_t lz0, uint32_t lz1, cudaStream_t st) {
+    k_scan_rows<<<lz1 - lz0, 256, 0, st>>>(g, rowV, rowT, layerTot, totals, list_ctr, list_mark, chunk_end, lz0);
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,

@@ -28,8 +28,8 @@ cudaError_t isomc_launch_count(const Geo &g, const uint32_t *signs, const McTabl
                                uint32_t *rowV, uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot,
                                uint32_t lz0, uint32_t lz1, int sms, int ctas_per_sm, cudaStream_t st);
 cudaError_t isomc_launch_scan(const Geo &g, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
-                              unsigned long long *totals, const uint32_t *list_ctr, uint32_t *list_mark, uint32_t lz0, uint32_t lz1,
-                              cudaStream_t st);
+                              unsigned long long *totals, const uint32_t *list_ctr, uint32_t *list_mark, uint32_t *chunk_end,
+                              uint32_t lz0, uint32_t lz1, cudaStream_t st);
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,
                                     cudaStream_t st);
 int isomc_emit_layers_per_brick();

@@ -37,9 +37,36 @@ class MarchingCubes:
 
     # ---- the reference API -------------------------------------------------------------------
     def extract(self, source, extractor):
-        self.extract_device(source)
-        xyz, idx = self.copy_out()
+        src = source.source if isinstance(source, Sampler) else source
+        if isinstance(src, DenseGrid) and not src.on_device:
+            xyz, idx = self.extract_host(src)  # host lattice in, host mesh out: one pipelined call
+        else:
+            self.extract_device(source)
+            xyz, idx = self.copy_out()
         replay(extractor, xyz, idx)
+
+    def extract_host(self, grid, xyz=None, idx=None):
+        """Host lattice -> host mesh through `isomc_extract_grid_host_to` (copy-in, kernels and copy-out overlap in
+        z-chunks).  `xyz` / `idx` are caller buffers (float32 / uint32, ideally pinned); without them the instance keeps
+        its own, sized from the previous extract.  Returns views of the filled parts."""
+        if grid.size != self.size:
+            raise ValueError("grid is for size %d, MarchingCubes for %d" % (grid.size, self.size))
+        own = xyz is None or idx is None
+        if own:
+            xyz = getattr(self, "_hxyz", None)
+            idx = getattr(self, "_hidx", None)
+            if xyz is None:
+                xyz = self._hxyz = np.empty(3 * 1024, np.float32)
+                idx = self._hidx = np.empty(3 * 1024, np.uint32)
+        rc = self._lib.isomc_extract_grid_host_to(self._h, grid.ptr, xyz.ctypes.data, xyz.size // 3, idx.ctypes.data, idx.size // 3)
+        if rc == _lib.ERR_BUFFER_TOO_SMALL and own:  # result is on the device: grow (with headroom) and fetch it
+            nv, nt, _ = self.counts()
+            xyz = self._hxyz = np.empty(3 * (nv + nv // 8 + 1024), np.float32)
+            idx = self._hidx = np.empty(3 * (nt + nt // 8 + 1024), np.uint32)
+            rc = self._lib.isomc_copy_out(self._h, xyz.ctypes.data, idx.ctypes.data)
+        _lib.check(rc, self._h)
+        nv, nt, _ = self.counts()
+        return xyz[:3 * nv], idx[:3 * nt]
 
     # ---- device-resident variants ------------------------------------------------------------
     def extract_device(self, source):

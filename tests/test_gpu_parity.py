@@ -395,3 +395,58 @@ def test_randomised_stress_subset():
     r = subprocess.run([sys.executable, str(root / "tools" / "gpu_stress.py"), "40", "123"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "40 cases, 0 failures" in r.stdout
+
+
+def test_streamed_host_to_host_extract(iso, oracle):
+    """isomc_extract_grid_host_to: z-chunked copy-in / kernels / copy-out pipeline gives the oracle's bytes, on the
+    plain first call, on the streamed later calls, when the mesh changes size, and reports too-small caller buffers"""
+    import torch
+    from isosurface_b200 import _lib
+    size = 96
+    fields = [synth(iso, 1, size, s).cpu().numpy().reshape(size + 1, size, size) for s in (3, 4)]
+    fields.append(synth(iso, 3, size, 5).cpu().numpy().reshape(size + 1, size, size))      # much smaller mesh
+    rng = np.random.default_rng(0)
+    fields.append(rng.standard_normal((size + 1, size, size)).astype(np.float32))         # much larger mesh: regrow + re-run
+    want = [oracle.extract_grid(size, f) for f in fields]
+    mc = iso.MarchingCubes(size)
+    for rep in range(2):
+        for f, (oxyz, oidx, _) in zip(fields, want):
+            xyz, idx = mc.extract_host(iso.DenseGrid(f))
+            assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    # caller-owned pinned buffers, exactly sized, streamed path
+    f, (oxyz, oidx, _) = fields[0], want[0]
+    hg = torch.from_numpy(f).pin_memory()
+    hx = torch.empty(len(oxyz), dtype=torch.float32).pin_memory()
+    hi = torch.empty(len(oidx), dtype=torch.int32).pin_memory()
+    lib = _lib.load()
+    for _ in range(2):
+        hx.fill_(-1); hi.fill_(-1)
+        _lib.check(lib.isomc_extract_grid_host_to(mc._h, C.c_void_p(hg.data_ptr()), C.c_void_p(hx.data_ptr()), len(oxyz) // 3,
+                                                  C.c_void_p(hi.data_ptr()), len(oidx) // 3), mc._h)
+        assert mesh_diff(hx.numpy(), hi.numpy().view(np.uint32), oxyz, oidx, POS_TOL) == ""
+    # one triangle short: reported, result stays fetchable
+    rc = lib.isomc_extract_grid_host_to(mc._h, C.c_void_p(hg.data_ptr()), C.c_void_p(hx.data_ptr()), len(oxyz) // 3,
+                                        C.c_void_p(hi.data_ptr()), len(oidx) // 3 - 1)
+    assert rc == _lib.ERR_BUFFER_TOO_SMALL
+    xyz, idx = mc.copy_out()
+    assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    # Extractor API with a host grid goes through the same call
+    sink = iso.ArrayMesh()
+    mc.extract(iso.DenseGrid(fields[1]), sink)
+    assert mesh_diff(sink.vertices.ravel(), sink.indices.ravel(), want[1][0], want[1][1], POS_TOL) == ""
+    mc.close()
+
+
+def test_brick_kernels_still_match(iso, oracle, monkeypatch):
+    """ISOMC_EMIT=brick keeps the older brick emission kernels selectable; same bytes as the list path"""
+    monkeypatch.setenv("ISOMC_EMIT", "brick")
+    for kind, size, seed in ((1, 128, 7), (3, 100, 8)):
+        t = synth(iso, kind, size, seed)
+        host = t.cpu().numpy().reshape(size + 1, size, size)
+        oxyz, oidx, _ = oracle.extract_grid(size, host)
+        mc = iso.MarchingCubes(size)
+        for _ in range(2):
+            mc.extract_device(iso.DenseGrid(t))
+            xyz, idx = mc.copy_out()
+            assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+        mc.close()
