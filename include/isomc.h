@@ -113,6 +113,14 @@ int32_t isomc_extract_grid_host(isomc_t *h, const float *h_grid);
 int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, uint64_t cap_vertices, uint32_t *idx,
                                    uint64_t cap_triangles);
 
+/* ---- PointCloud::<Signed>::new(size).extract(&source, &mut extractor)  (reference src/point_cloud.rs:50-63) ----
+ * One point per active cell (cube index neither 0 nor 255): corners[0].lerp(corners[6], 0.5), in (z, y, x) cell order.
+ * Results through the same calls as a mesh: isomc_counts() reports the points as vertices (0 triangles),
+ * isomc_copy_out(h, xyz, NULL) / isomc_device_buffers() deliver them.  Whole-lattice handles only. */
+int32_t isomc_points_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes);
+int32_t isomc_points_grid_device(isomc_t *h, const float *d_grid);
+int32_t isomc_points_grid_host(isomc_t *h, const float *h_grid);
+
 /* ---- results:  the two Vecs behind extractor::IndexedVertices --------------------------- */
 int32_t isomc_counts(isomc_t *h, uint64_t *n_vertices, uint64_t *n_triangles, uint64_t *n_active_cells);
 int32_t isomc_device_buffers(isomc_t *h, const float **d_xyz, const uint32_t **d_idx);

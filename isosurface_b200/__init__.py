@@ -3,14 +3,15 @@ crate swiftcoder/isosurface.  The product is `libisomc_b200.so` (C ABI: include/
 package is the Python host-side mirror of the crate's interface for that one path:
 
     MarchingCubes(size).extract(Sampler(source), IndexedVertices(vertices, indices))
+    PointCloud(size).extract(Sampler(source), OnlyVertices(vertices))
 
 See DESIGN.md for the path, INTEGRATION.md for the Rust-side binding.
 """
 from .extractor import ArrayMesh, Extractor, IndexedVertices, OnlyVertices
-from .marching_cubes import MarchingCubes
+from .marching_cubes import MarchingCubes, PointCloud
 from .source import (Cylinder, DenseGrid, DeviceSource, Difference, Intersection, RectangularPrism, Sampler,
                      Sphere, Torus, Translate, Union)
 
-__all__ = ["MarchingCubes", "Sampler", "DenseGrid", "DeviceSource", "Sphere", "Torus", "Cylinder",
+__all__ = ["MarchingCubes", "PointCloud", "Sampler", "DenseGrid", "DeviceSource", "Sphere", "Torus", "Cylinder",
            "RectangularPrism", "Union", "Intersection", "Difference", "Translate", "Extractor",
            "IndexedVertices", "OnlyVertices", "ArrayMesh"]

@@ -49,6 +49,9 @@ SIGNATURES = {
     "isomc_extract_grid_device": (_I32, [_P, _P]),
     "isomc_extract_grid_host": (_I32, [_P, _P]),
     "isomc_extract_grid_host_to": (_I32, [_P, _P, _P, _U64, _P, _U64]),
+    "isomc_points_sdf": (_I32, [_P, _P, _U32]),
+    "isomc_points_grid_device": (_I32, [_P, _P]),
+    "isomc_points_grid_host": (_I32, [_P, _P]),
     "isomc_counts": (_I32, [_P, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
     "isomc_device_buffers": (_I32, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "isomc_copy_out": (_I32, [_P, _P, _P]),

@@ -433,6 +433,7 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
         if (const char *p = getenv("ISOMC_EMIT")) h->list_mode = strcmp(p, "brick") != 0;
         if (h->list_mode) {
             CU(h, cudaMalloc(&h->L.segrec, (nrows_c * g.nsegx + 4) * sizeof(uint2)));
+            CU(h, cudaMalloc(&h->L.segtpre, (nrows_c * g.nsegx + 4) * sizeof(uint32_t)));
             EmitTab host_etab;
             isomc_build_emit_tab(host_tabs, &host_etab);
             CU(h, cudaMalloc(&h->etab, sizeof(EmitTab)));
@@ -493,7 +494,7 @@ int32_t isomc_destroy(isomc_t *h) {
     cudaFree(h->signs); cudaFree(h->segpre); cudaFree(h->rowV); cudaFree(h->rowT); cudaFree(h->rowA);
     cudaFree(h->layerTot); cudaFree(h->totals); cudaFree(h->vofs); cudaFree(h->tabs);
     cudaFree(h->xyz); cudaFree(h->idx); cudaFree(h->stage_grid);
-    cudaFree(h->L.ent); cudaFree(h->L.ent_yz); cudaFree(h->L.segrec); cudaFree(h->L.blkfill); cudaFree(h->etab);
+    cudaFree(h->L.ent); cudaFree(h->L.ent_yz); cudaFree(h->L.segrec); cudaFree(h->L.segtpre); cudaFree(h->L.blkfill); cudaFree(h->etab);
     if (h->h_totals) cudaFreeHost(h->h_totals);
     if (h->h_chunk_ends) cudaFreeHost(h->h_chunk_ends);
     for (int c = 0; c < MAX_CHUNKS; ++c) {
@@ -707,6 +708,72 @@ int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, 
                     (unsigned long long)h->n_t, (unsigned long long)cap_vertices, (unsigned long long)cap_triangles);
     if (!delivered) return isomc_copy_out(h, xyz, idx);
     return ISOMC_OK;
+}
+
+/* ---- PointCloud::new(size).extract(&source, &mut extractor)  (reference src/point_cloud.rs:50-63) -------- */
+
+static int32_t points_impl(isomc_t *h) {
+    if (h->z_begin != 0 || h->z_end != h->size)
+        return fail(h, ISOMC_ERR_BAD_ARG, "point clouds are extracted on whole-lattice handles (this one is a slab [%u, %u))", h->z_begin, h->z_end);
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    const Geo &g = h->g;
+    h->have_result = false; h->counted = false; h->emitted = false; h->totals_valid = false;
+    h->stats.kernel_launches = 0; h->stats.emit_reruns = 0;
+    if (g.ncl == 0 || g.ncx == 0) {
+        h->n_v = h->n_t = h->n_a = 0;
+        h->have_result = true;
+        return ISOMC_OK;
+    }
+    /* per-segment prefixes live in the scratch the mesh path uses for its own per-segment data */
+    uint32_t *segA = h->list_mode ? reinterpret_cast<uint32_t *>(h->L.segrec) : h->segpre;
+    CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t), h->stream));
+    if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, 0, g.nsl * g.N, h->sms, 8, h->stream));
+    else CU(h, isomc_launch_sign_sdf(g, h->prog, h->signs, 0, g.nsl * g.N, h->sms, 8, h->stream));
+    CU(h, isomc_launch_points_count(g, h->signs, segA, h->rowV, h->rowT, h->layerTot, h->sms, h->stream));
+    CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, nullptr, nullptr, nullptr, 0, g.ncl, h->stream));
+    CU(h, cudaMemcpyAsync(h->h_totals, h->totals, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    const uint64_t np = h->h_totals[0];
+    if (np >= (1ull << 32)) return fail(h, ISOMC_ERR_INDEX_OVERFLOW, "%llu points", (unsigned long long)np);
+    rc = ensure_capacity(h, np, 0);
+    if (rc) return rc;
+    CU(h, isomc_launch_points_emit(g, h->signs, segA, h->rowV, h->xyz, h->cap_v, h->sms, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->stats.kernel_launches = 4;
+    h->n_v = np; h->n_t = 0; h->n_a = np;
+    h->stats.n_vertices = np; h->stats.n_triangles = 0; h->stats.n_active_cells = np;
+    h->stats.n_samples = (uint64_t)g.N * g.N * g.nsl;
+    h->stats.n_cells = (uint64_t)g.ncx * g.ncx * g.ncl;
+    h->stats.algorithmic_bytes = 4 * h->stats.n_samples + 12 * np;
+    h->have_result = true;
+    return ISOMC_OK;
+}
+
+int32_t isomc_points_grid_device(isomc_t *h, const float *d_grid) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!d_grid) return fail(h, ISOMC_ERR_BAD_ARG, "d_grid == NULL");
+    h->kind = SRC_GRID; h->d_grid = d_grid;
+    return points_impl(h);
+}
+
+int32_t isomc_points_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    int32_t rc = validate_program(h, prog, n_nodes, &h->prog);
+    if (rc) return rc;
+    h->kind = SRC_SDF; h->d_grid = nullptr;
+    return points_impl(h);
+}
+
+int32_t isomc_points_grid_host(isomc_t *h, const float *h_grid) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h_grid) return fail(h, ISOMC_ERR_BAD_ARG, "h_grid == NULL");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    const size_t bytes = (size_t)h->g.N * h->g.N * h->g.nsl * sizeof(float);
+    if (!h->stage_grid) CU(h, cudaMalloc(&h->stage_grid, bytes > 0 ? bytes : 4));
+    CU(h, cudaMemcpyAsync(h->stage_grid, h_grid, bytes, cudaMemcpyHostToDevice, h->stream));
+    return isomc_points_grid_device(h, h->stage_grid);
 }
 
 /* ---- results ------------------------------------------------------------------------------ */

@@ -8,15 +8,17 @@
  * Active-cell list.  k_count_list appends one entry per active cell (a cell whose 8 corners are not all
  * on one side, reference src/marching_cubes_impl.rs:26-37 + marching_cubes_tables.rs:49-70):
  *
- *     ent[k]    = { vrel | trel << 16,  x | ci' << 16 }     ent_yz[k] = y | local layer << 16
+ *     ent[k]    = { vrel | tseg << 16,  x | ci' << 16 }     ent_yz[k] = y | local layer << 16
  *
- *   vrel  vertices created by the earlier cells of the same cell row   (id = rowPV[row] + vrel)
- *   trel  triangles of the earlier cells of the same cell row          (slot = rowPT[row] + trel)
+ *   vrel  vertices created by the earlier cells of the same cell row      (id = rowPV[row] + vrel)
+ *   tseg  triangles of the earlier cells of the same 32-cell segment
  *   ci'   natural cube index (isomc_tables.h)
  *
- * and one record per 32-cell segment that has active cells:
+ * and, per 32-cell segment that has active cells,
  *
  *     segrec[row * nsegx + s] = { list position of the segment's first active cell, active mask }
+ *     segtpre[row * nsegx + s] = triangles of the earlier segments of the same cell row
+ *                                                          (triangle slot = rowPT[row] + segtpre + tseg)
  *
  * so that "the entry of cell (x, row)" is segrec.x + popc(segrec.y & below(x & 31)).  Entries of one segment
  * are contiguous and in x order; beyond that the list order is arbitrary (blocks of LIST_BLOCK entries are
@@ -115,6 +117,7 @@ struct ListBufs {
     uint2 *ent;
     uint32_t *ent_yz;
     uint2 *segrec;
+    uint32_t *segtpre;
     uint32_t *blkfill;  /* valid entries of each handed-out block */
     uint32_t *ctr;      /* [0] blocks handed out so far (may exceed cap_blocks: the host then grows the list and re-runs) */
     uint32_t cap_blocks;
@@ -285,7 +288,7 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
     }
 
     /* triangles in table order (march_cube, marching_cubes_impl.rs:106-116) */
-    const uint64_t tslot = (uint64_t)(A.rowPT[row] + (ea.x >> 16) - A.ghostT);
+    const uint64_t tslot = (uint64_t)(A.rowPT[row] + L.segtpre[(uint64_t)row * g.nsegx + (x >> 5)] + (ea.x >> 16) - A.ghostT);
     uint32_t nt = T.ntri[ci];
     if (tslot >= A.cap_t) nt = 0;
     else if (tslot + nt > A.cap_t) nt = (uint32_t)(A.cap_t - tslot);
@@ -365,6 +368,10 @@ ISOMC_HD bool classify_segment(const Geo &g, const uint32_t w[8], uint32_t s, ui
     return true;
 }
 
+ISOMC_HD void seg_clear(SegClass &C) {
+    C.act = 0; C.p0 = C.p1 = C.p2 = C.p3 = 0; C.a0 = C.b0 = C.c0 = C.d0 = 0; C.nb = 0;
+}
+
 ISOMC_HD uint32_t seg_planes_count(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t m) {
     return hd_popc(p0 & m) + 2 * hd_popc(p1 & m) + 4 * hd_popc(p2 & m) + 8 * hd_popc(p3 & m);
 }
@@ -437,6 +444,25 @@ ISOMC_HD bool w_any(const Warp &w, bool pred) {
     return pred;
 #endif
 }
+ISOMC_HD uint32_t w_ballot(const Warp &w, bool pred) {
+#if defined(__CUDA_ARCH__)
+    return __ballot_sync(0xFFFFFFFFu, pred);
+#elif defined(ISOMC_HOST_MODEL)
+    uint32_t v = pred ? 1u << w.lane : 0u;
+    for (uint32_t d = 1; d < 32; d <<= 1) v |= isomc_emu_shfl(w.emu, w.lane, v, w.lane ^ d);
+    return v;
+#else
+    return pred ? 1u : 0u;
+#endif
+}
+ISOMC_HD uint32_t hd_clz(uint32_t v) { /* v != 0 */
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__clz((int)v);
+#else
+    return (uint32_t)__builtin_clz(v);
+#endif
+}
+
 ISOMC_HD void w_sync(const Warp &w) {
 #if defined(__CUDA_ARCH__)
     __syncwarp();
@@ -493,22 +519,37 @@ ISOMC_HD void list_close(const ListBufs &L, ListCursor &c, uint32_t lane) {
     c.m = 0;
 }
 
-/* space for n (1..1024) contiguous entries; returns the first position; ok = false after a list overflow */
-ISOMC_HD uint32_t list_alloc(const Warp &w, const ListBufs &L, ListCursor &c, uint32_t n, bool &ok) {
-    if (c.pos + n > c.end) {
+/* List space for the n (1..1024) cells of a flush window.  The cells of one SEGMENT must be contiguous, the window need
+ * not be: the leading segments that still fit the warp's current block (cend <= room; cend = running cell count, one per
+ * lane, non-decreasing) stay there, the rest goes to freshly handed-out blocks.  Cell k of the window lives at
+ * (k < n_old ? pos_old + k : pos_new + k - n_old); ok = false after a list overflow (nothing may be written then). */
+struct ListSpan {
+    uint32_t n_old, pos_old, pos_new;
+};
+ISOMC_HD ListSpan list_alloc(const Warp &w, const ListBufs &L, ListCursor &c, uint32_t n, uint32_t cend, bool &ok) {
+    ListSpan sp;
+    const uint32_t room = c.end - c.pos;
+    const uint32_t fit = hd_popc(w_ballot(w, cend <= room)); /* leading lanes whose cells all fit */
+    sp.n_old = fit ? w_shfl(w, cend, fit - 1) : 0u;
+    sp.pos_old = c.pos;
+    sp.pos_new = 0;
+    bool ok_old = c.m == 0 || c.b0 + c.m <= L.cap_blocks;
+    c.pos += sp.n_old;
+    ok = ok_old;
+    if (sp.n_old < n) {
         list_close(L, c, w.lane);
-        const uint32_t m = (n + LIST_BLOCK - 1) / LIST_BLOCK;
+        const uint32_t need = n - sp.n_old, m = (need + LIST_BLOCK - 1) / LIST_BLOCK;
         uint32_t b0 = 0;
         if (w.lane == 0) b0 = hd_atomic_add(L.ctr, m);
         b0 = w_shfl(w, b0, 0);
         c.b0 = b0; c.m = m;
         c.pos = b0 * LIST_BLOCK;
         c.end = (b0 + m) * LIST_BLOCK;
+        sp.pos_new = c.pos;
+        c.pos += need;
+        ok = ok_old && b0 + m <= L.cap_blocks;
     }
-    const uint32_t base = c.pos;
-    c.pos += n;
-    ok = c.b0 + c.m <= L.cap_blocks;
-    return base;
+    return sp;
 }
 
 struct CountOut {
@@ -517,21 +558,42 @@ struct CountOut {
 };
 
 /*
- * Phase B for one pass of a warp: the pass' active cells, one lane per cell.  Lane l holds segment l of the pass
- * (C, cpos/cend = list range of its cells within the pass, vpre = in-row vertex prefix at the segment start,
- * yznb = y | layer << 13 | next-word bits << 26).  Returns the triangles of the pass.
- *   ROWS: the pass covers (32 >> gshift) whole rows of (1 << gshift) segments each: triangle prefixes restart per
- *         row (Rsm = 32 words of warp-private shared memory) and the lane holding a row's last cell posts the row total;
- *   else: the pass is a 32-segment chunk of ONE row: prefixes continue from t_row, the caller posts the total.
+ * k_count_list, one warp.  Two stages with a queue in between, so that both run with full warps whatever the
+ * density of the field:
+ *
+ *   scan     lane per 32-cell segment, a pass = 32 segments in (row, x) order: load the 8 sign words, keep the
+ *            segments that are not uniform (they are the ones with active cells) in a ring of SEGQ_CAP raw segments.
+ *            Rows without any are finished on the spot (three zeros).
+ *   flush    whenever 32 segments wait (and at the end): lane per queued segment: classify (active mask, bit-sliced
+ *            "vertices created" planes), list space for the window's active cells; then prefixes within
+ *            the cell row of vertices and active cells by a segmented scan (a row's segments are consecutive in the
+ *            queue; the row still open at the end of a window is carried in registers); then lane per CELL (list_cells):
+ *            cube index, triangles -> list entries; then back to lane per segment: the same scan for the triangles ->
+ *            segment records, row totals.
  */
-template <bool ROWS>
-ISOMC_HD uint32_t list_phase_b(const Warp &w, const ListBufs &L, const uint8_t *s_ntri, const uint8_t *nth8, const SegClass &C,
-                               uint32_t cpos,
-                               uint32_t cend, uint32_t vpre, uint32_t yznb, uint32_t n_cells, uint32_t base, bool ok,
-                               uint32_t gshift, uint32_t seg0, uint32_t row_first, uint32_t t_row, uint32_t *Rsm,
-                               const CountOut &out) {
+constexpr uint32_t SEGQ_CAP = 64;
+constexpr uint32_t SEGQ_FIRST = 1u << 16, SEGQ_LAST = 1u << 17; /* meta = s | flags: first / last queued segment of its row */
+
+struct SegQueue {             /* one per warp, shared memory */
+    uint32_t w[8][SEGQ_CAP];  /* a0 a1 b0 b1 c0 c1 d0 d1 */
+    uint32_t row[SEGQ_CAP];
+    uint32_t meta[SEGQ_CAP];
+    uint32_t segT[32];        /* triangles of each segment of the window being flushed */
+};
+
+struct CountState {           /* warp-uniform */
+    uint32_t enq, deq;        /* segments ever queued / flushed */
+    ListCursor cur;
+    uint32_t p_va, p_t;       /* the row left open by the last window: vertices | active cells << 16, triangles so far */
+};
+
+/* lane per cell over the n_cells active cells of a flush window; lane l holds segment l (C, cpos/cend = range of its
+ * cells within the window, yznb = y | layer << 13 | next-word bits << 26, s = segment index in its row) */
+ISOMC_HD void list_cells(const Warp &w, const ListBufs &L, const uint8_t *s_ntri, const uint8_t *nth8, const SegClass &C,
+                         uint32_t cpos, uint32_t cend, uint32_t vpre, uint32_t yznb, uint32_t s, uint32_t n_cells, ListSpan sp,
+                         bool ok, uint32_t *segT) {
     const uint32_t lane = w.lane;
-    uint32_t tcarry = 0;
+    uint32_t carry_t = 0; /* triangles so far of the segment that straddles the 32-cell step boundary */
     for (uint32_t kb = 0; kb < n_cells; kb += 32) {
         const uint32_t k = kb + lane;
         const bool live = k < n_cells;
@@ -542,147 +604,220 @@ ISOMC_HD uint32_t list_phase_b(const Warp &w, const ListBufs &L, const uint8_t *
             const uint32_t t = w_shfl(w, cend, seg + step - 1);
             if (t <= k) seg += step;
         }
-        const uint32_t sc = w_shfl(w, cpos, seg), am = w_shfl(w, C.act, seg);
+        const uint32_t sc = w_shfl(w, cpos, seg), ec = w_shfl(w, cend, seg), am = w_shfl(w, C.act, seg);
         const uint32_t a0 = w_shfl(w, C.a0, seg), b0 = w_shfl(w, C.b0, seg);
         const uint32_t c0 = w_shfl(w, C.c0, seg), d0 = w_shfl(w, C.d0, seg);
         const uint32_t p0 = w_shfl(w, C.p0, seg), p1 = w_shfl(w, C.p1, seg);
         const uint32_t p2 = w_shfl(w, C.p2, seg), p3 = w_shfl(w, C.p3, seg);
-        const uint32_t vp = w_shfl(w, vpre, seg), yz = w_shfl(w, yznb, seg);
+        const uint32_t yz = w_shfl(w, yznb, seg), sk = w_shfl(w, s, seg), vp = w_shfl(w, vpre, seg);
         const uint32_t i = live ? nth_set_bit(nth8, am, k - sc) : 0u;
         const uint32_t ci = seg_cube_index(a0, b0, c0, d0, yz >> 26, i);
         const uint32_t nt = live ? (uint32_t)s_ntri[ci] : 0u;
-        const uint32_t vrel = vp + seg_planes_count(p0, p1, p2, p3, (1u << i) - 1u);
+        /* inclusive scan of nt within the segment: lane - d belongs to my segment iff d <= (cells of it before me in this step) */
+        const uint32_t dist = live ? (k - sc < lane ? k - sc : lane) : 0u;
         uint32_t incl = nt;
 #pragma unroll
         for (uint32_t d = 1; d < 32; d <<= 1) {
             const uint32_t o = w_shfl_up(w, incl, d);
-            if (lane >= d) incl += o;
+            if (d <= dist) incl += o;
         }
-        const uint32_t s_excl = tcarry + incl - nt; /* triangles of the pass' earlier cells */
-        tcarry += w_shfl(w, incl, 31);
-        uint32_t trel, xk;
-        if (ROWS) {
-            const uint32_t G = 1u << gshift, subk = seg >> gshift, fl = subk << gshift;
-            const uint32_t rstart = w_shfl(w, cpos, fl), rend = w_shfl(w, cend, fl + G - 1);
-            if (live && k == rstart) Rsm[subk] = s_excl; /* the row's first active cell: posted in this or an earlier step */
-            w_sync(w);
-            trel = s_excl - (live ? Rsm[subk] : 0u);
-            w_sync(w);
-            xk = (seg & (G - 1)) * 32 + i;
-            if (live && k == rend - 1) { /* the row's last active cell */
-                const uint32_t tt = trel + nt;
-                out.rowT[row_first + subk] = tt;
-                hd_atomic_add64(&out.layerTot[3 * (yz >> 13 & 0x1FFFu) + 1], (unsigned long long)tt);
+        if (live && sc < kb) incl += carry_t; /* my segment began in the previous step */
+        carry_t = w_shfl(w, incl, 31);        /* (only used if lane 31's segment continues) */
+        if (live) {
+            if (k == ec - 1) segT[seg] = incl; /* last cell of the segment */
+            if (ok) {
+                const uint32_t pos = k < sp.n_old ? sp.pos_old + k : sp.pos_new + (k - sp.n_old);
+                L.ent[pos] = make_uint2((vp + seg_planes_count(p0, p1, p2, p3, (1u << i) - 1u)) | (incl - nt) << 16, (sk * 32 + i) | ci << 16);
+                L.ent_yz[pos] = (yz & 0x1FFFu) | (yz >> 13 & 0x1FFFu) << 16;
             }
-        } else {
-            trel = t_row + s_excl;
-            xk = (seg0 + seg) * 32 + i;
-        }
-        if (live && ok) {
-            L.ent[base + k] = make_uint2(vrel | trel << 16, xk | ci << 16);
-            L.ent_yz[base + k] = (yz & 0x1FFFu) | (yz >> 13 & 0x1FFFu) << 16;
         }
     }
-    return tcarry;
 }
 
-ISOMC_HD bool load_classify(const Geo &g, const uint32_t *signs, uint32_t row, uint32_t lz, uint32_t y, uint32_t s, SegClass &C) {
+/* flush the n (1..32) oldest queued segments */
+ISOMC_HD void count_flush(const Warp &w, const Geo &g, const uint8_t *s_ntri, const uint8_t *nth8, const ListBufs &L,
+                          const CountOut &out, SegQueue &Q, CountState &S, uint32_t n) {
+    const uint32_t lane = w.lane;
+    const bool valid = lane < n;
+    const uint32_t slot = (S.deq + lane) & (SEGQ_CAP - 1);
+    uint32_t row = 0, meta = 0, lz = 0, y = 0, nv = 0;
+    SegClass C;
+    seg_clear(C);
+    if (valid) {
+        uint32_t wd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wd[j] = Q.w[j][slot];
+        row = Q.row[slot];
+        meta = Q.meta[slot];
+        lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40); /* row / ncx */
+        y = row - lz * g.ncx;
+        if (classify_segment(g, wd, meta & 0xFFFFu, y, lz, C)) nv = seg_planes_count(C.p0, C.p1, C.p2, C.p3, 0xFFFFFFFFu);
+    }
+    const uint32_t na = hd_popc(C.act);
+    uint32_t n_cells;
+    const uint32_t cpos = w_excl_scan(w, na, n_cells);
+    /* prefixes within the cell row: segmented inclusive scans over the window, heads = first queued segment of a row.
+     * Vertices and active cells now, triangles after the cell pass. */
+    const uint32_t head = (valid && (meta & SEGQ_FIRST)) ? 1u : 0u;
+    uint32_t v1 = nv | na << 16, f = head;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t o1 = w_shfl_up(w, v1, d), of = w_shfl_up(w, f, d);
+        if (lane >= d) {
+            if (!f) v1 += o1;
+            f |= of;
+        }
+    }
+    const bool cont = f == 0; /* no head at or before me: my row was left open by the previous window */
+    if (cont) v1 += S.p_va;
+    Q.segT[lane] = 0;
+    w_sync(w);
+    bool ok = true;
+    ListSpan sp;
+    sp.n_old = sp.pos_old = sp.pos_new = 0;
+    if (n_cells) {
+        sp = list_alloc(w, L, S.cur, n_cells, cpos + na, ok);
+        list_cells(w, L, s_ntri, nth8, C, cpos, cpos + na, (v1 & 0xFFFFu) - nv, y | lz << 13 | C.nb << 26, meta & 0xFFFFu, n_cells, sp,
+                   ok, Q.segT);
+    }
+    w_sync(w);
+    const uint32_t nt = Q.segT[lane];
+    uint32_t v2 = nt;
+    f = head;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t o2 = w_shfl_up(w, v2, d), of = w_shfl_up(w, f, d);
+        if (lane >= d) {
+            if (!f) v2 += o2;
+            f |= of;
+        }
+    }
+    if (cont) v2 += S.p_t;
+    if (valid && na && ok) {
+        const uint64_t q = (uint64_t)row * g.nsegx + (meta & 0xFFFFu);
+        L.segrec[q] = make_uint2(cpos < sp.n_old ? sp.pos_old + cpos : sp.pos_new + (cpos - sp.n_old), C.act);
+        L.segtpre[q] = v2 - nt;
+    }
+    if (valid && (meta & SEGQ_LAST)) { /* the row is complete */
+        const uint32_t tv = v1 & 0xFFFFu, ta = v1 >> 16;
+        out.rowV[row] = tv; out.rowT[row] = v2; out.rowA[row] = ta;
+        if (tv) hd_atomic_add64(&out.layerTot[3 * lz + 0], (unsigned long long)tv);
+        if (v2) hd_atomic_add64(&out.layerTot[3 * lz + 1], (unsigned long long)v2);
+        if (ta) hd_atomic_add64(&out.layerTot[3 * lz + 2], (unsigned long long)ta);
+    }
+    const uint32_t lmeta = w_shfl(w, meta, n - 1), lv1 = w_shfl(w, v1, n - 1), lv2 = w_shfl(w, v2, n - 1);
+    if (lmeta & SEGQ_LAST) { S.p_va = 0; S.p_t = 0; } else { S.p_va = lv1; S.p_t = lv2; }
+    S.deq += n;
+}
+
+ISOMC_HD bool seg_uniform(const uint32_t wd[8]) { /* all 4 x 33 samples on one side: no active cell */
+    const uint32_t all_or = wd[0] | wd[2] | wd[4] | wd[6] | ((wd[1] | wd[3] | wd[5] | wd[7]) & 1u);
+    const uint32_t all_and = wd[0] & wd[2] & wd[4] & wd[6];
+    return (all_or == 0u) || (all_and == 0xFFFFFFFFu && (wd[1] & wd[3] & wd[5] & wd[7] & 1u));
+}
+
+ISOMC_HD void load_words(const Geo &g, const uint32_t *signs, uint32_t row, uint32_t lz, uint32_t s, uint32_t wd[8]) {
     const uint32_t *r00 = signs + (uint64_t)(row + lz) * g.nws + s; /* sample row lz*N + y = row + lz */
     const uint32_t *r01 = r00 + g.nws, *r10 = r00 + (uint64_t)g.N * g.nws, *r11 = r10 + g.nws;
-    uint32_t wd[8];
     wd[0] = hd_ldg(r00); wd[1] = hd_ldg(r00 + 1); wd[2] = hd_ldg(r01); wd[3] = hd_ldg(r01 + 1);
     wd[4] = hd_ldg(r10); wd[5] = hd_ldg(r10 + 1); wd[6] = hd_ldg(r11); wd[7] = hd_ldg(r11 + 1);
-    return classify_segment(g, wd, s, y, lz, C);
 }
 
-ISOMC_HD void seg_clear(SegClass &C) {
-    C.act = 0; C.p0 = C.p1 = C.p2 = C.p3 = 0; C.a0 = C.b0 = C.c0 = C.d0 = 0; C.nb = 0;
+/* queue the lanes with `keep` (segments of one pass, lane order = (row, x) order) */
+ISOMC_HD void seg_enqueue(const Warp &w, SegQueue &Q, CountState &S, uint32_t mask, bool keep, const uint32_t wd[8], uint32_t row,
+                          uint32_t meta) {
+    if (keep) {
+        const uint32_t slot = (S.enq + hd_popc(mask & ((1u << w.lane) - 1u))) & (SEGQ_CAP - 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Q.w[j][slot] = wd[j];
+        Q.row[slot] = row;
+        Q.meta[slot] = meta;
+    }
+    S.enq += hd_popc(mask);
+    w_sync(w);
 }
 
-/* One warp's share of cell rows [row0, row1): warp gwarp of nwarps.  WIDE = rows of more than 32 segments (one row
- * per warp pass, 32-segment chunks); else a pass covers 32 >> gshift rows of 1 << gshift segments. */
+/* One warp's share of cell rows [row0, row1): warp gwarp of nwarps.  WIDE = rows of more than 32 segments (a pass is a
+ * 32-segment chunk of one row); else a pass covers 32 >> gshift whole rows of 1 << gshift segments. */
 template <bool WIDE>
 ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs, const uint8_t *s_ntri, const uint8_t *nth8,
-                              const ListBufs &L,
-                              const CountOut &out, uint32_t gshift, uint32_t row0, uint32_t row1, uint32_t gwarp,
-                              uint32_t nwarps, uint32_t *Rsm) {
+                              const ListBufs &L, const CountOut &out, uint32_t gshift, uint32_t row0, uint32_t row1, uint32_t gwarp,
+                              uint32_t nwarps, SegQueue &Q) {
     const uint32_t lane = w.lane;
-    ListCursor cur;
-    cur.pos = cur.end = cur.b0 = cur.m = 0;
+    CountState S;
+    S.enq = S.deq = 0;
+    S.cur.pos = S.cur.end = S.cur.b0 = S.cur.m = 0;
+    S.p_va = S.p_t = 0;
     if (!WIDE) {
         const uint32_t G = 1u << gshift, rpw = 32u >> gshift, sub = lane >> gshift, s = lane & (G - 1);
+        const uint32_t gmask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << (sub << gshift);
         const uint32_t niter = (row1 - row0 + rpw - 1) / rpw;
         for (uint32_t it = gwarp; it < niter; it += nwarps) {
             const uint32_t row = row0 + it * rpw + sub;
             const bool valid = row < row1 && s < g.nsegx;
-            const uint32_t rowc = row < row1 ? row : row1 - 1;
-            const uint32_t lz = (uint32_t)(((uint64_t)rowc * g.row_magic) >> 40), y = rowc - lz * g.ncx; /* rowc / ncx */
-            SegClass C;
-            seg_clear(C);
-            uint32_t nv = 0;
-            if (valid && load_classify(g, signs, row, lz, y, s, C)) nv = seg_planes_count(C.p0, C.p1, C.p2, C.p3, 0xFFFFFFFFu);
-            const uint32_t na = hd_popc(C.act);
-            if (!w_any(w, na != 0)) { /* nothing active in the whole pass */
-                if (s == 0 && row < row1) { out.rowV[row] = 0; out.rowT[row] = 0; out.rowA[row] = 0; }
-                continue;
+            uint32_t wd[8];
+            bool keep = false;
+            if (valid) {
+                const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40);
+                load_words(g, signs, row, lz, s, wd);
+                keep = !seg_uniform(wd);
             }
-            /* scans within the row (lanes [sub * G, sub * G + G)) */
-            uint32_t inc = nv, rinc = na;
-            for (uint32_t d = 1; d < G; d <<= 1) {
-                const uint32_t o = w_shfl_up(w, inc, d), q = w_shfl_up(w, rinc, d);
-                if (s >= d) { inc += o; rinc += q; }
+            const uint32_t mask = w_ballot(w, keep), rmask = mask & gmask;
+            if (s == 0 && row < row1 && rmask == 0) { out.rowV[row] = 0; out.rowT[row] = 0; out.rowA[row] = 0; }
+            if (mask == 0) continue;
+            uint32_t meta = s;
+            if (keep) {
+                if (hd_ffs0(rmask) == lane) meta |= SEGQ_FIRST;
+                if (31u - hd_clz(rmask) == lane) meta |= SEGQ_LAST;
             }
-            const uint32_t vpre = inc - nv;
-            const uint32_t tv = w_shfl(w, inc, (sub << gshift) + G - 1), ra = w_shfl(w, rinc, (sub << gshift) + G - 1);
-            uint32_t n_cells;
-            const uint32_t cpos = w_excl_scan(w, na, n_cells);
-            if (s == 0 && row < row1) {
-                out.rowV[row] = tv; out.rowA[row] = ra;
-                if (ra == 0) out.rowT[row] = 0; /* rows with active cells: posted by the lane of their last cell */
-                if (tv) hd_atomic_add64(&out.layerTot[3 * lz + 0], (unsigned long long)tv);
-                if (ra) hd_atomic_add64(&out.layerTot[3 * lz + 2], (unsigned long long)ra);
-            }
-            if (n_cells == 0) continue;
-            bool ok;
-            const uint32_t base = list_alloc(w, L, cur, n_cells, ok);
-            if (na && ok) L.segrec[(uint64_t)row * g.nsegx + s] = make_uint2(base + cpos, C.act);
-            list_phase_b<true>(w, L, s_ntri, nth8, C, cpos, cpos + na, vpre, y | lz << 13 | C.nb << 26, n_cells, base, ok, gshift, 0u,
-                               row0 + it * rpw, 0u, Rsm, out);
+            seg_enqueue(w, Q, S, mask, keep, wd, row, meta);
+            if (S.enq - S.deq >= 32) count_flush(w, g, s_ntri, nth8, L, out, Q, S, 32);
         }
     } else {
         for (uint32_t row = row0 + gwarp; row < row1; row += nwarps) {
-            const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40), y = row - lz * g.ncx; /* row / ncx */
-            uint32_t vcarry = 0, tcarry = 0, acarry = 0;
+            const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40);
+            bool row_has = false;
+            uint32_t last_seq = 0;
             for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 32) {
                 const uint32_t s = s0 + lane;
-                SegClass C;
-                seg_clear(C);
-                uint32_t nv = 0;
-                if (s < g.nsegx && load_classify(g, signs, row, lz, y, s, C)) nv = seg_planes_count(C.p0, C.p1, C.p2, C.p3, 0xFFFFFFFFu);
-                const uint32_t na = hd_popc(C.act);
-                if (!w_any(w, na != 0)) continue; /* no active cell, no created vertex */
-                uint32_t n_cells, nv_tot;
-                const uint32_t cpos = w_excl_scan(w, na, n_cells);
-                const uint32_t vpre = vcarry + w_excl_scan(w, nv, nv_tot);
-                vcarry += nv_tot;
-                acarry += n_cells;
-                bool ok;
-                const uint32_t base = list_alloc(w, L, cur, n_cells, ok);
-                if (na && ok) L.segrec[(uint64_t)row * g.nsegx + s] = make_uint2(base + cpos, C.act);
-                tcarry += list_phase_b<false>(w, L, s_ntri, nth8, C, cpos, cpos + na, vpre, y | lz << 13 | C.nb << 26, n_cells, base, ok,
-                                              0u, s0, row, tcarry, Rsm, out);
-            }
-            if (lane == 0) {
-                out.rowV[row] = vcarry; out.rowT[row] = tcarry; out.rowA[row] = acarry;
-                if (acarry) {
-                    hd_atomic_add64(&out.layerTot[3 * lz + 0], (unsigned long long)vcarry);
-                    hd_atomic_add64(&out.layerTot[3 * lz + 1], (unsigned long long)tcarry);
-                    hd_atomic_add64(&out.layerTot[3 * lz + 2], (unsigned long long)acarry);
+                uint32_t wd[8];
+                bool keep = false;
+                if (s < g.nsegx) {
+                    load_words(g, signs, row, lz, s, wd);
+                    keep = !seg_uniform(wd);
                 }
+                const uint32_t mask = w_ballot(w, keep);
+                if (mask == 0) continue;
+                uint32_t meta = s;
+                if (keep && !row_has && hd_ffs0(mask) == lane) meta |= SEGQ_FIRST;
+                seg_enqueue(w, Q, S, mask, keep, wd, row, meta);
+                row_has = true;
+                last_seq = S.enq - 1;
+                if (S.enq - S.deq >= 32) count_flush(w, g, s_ntri, nth8, L, out, Q, S, 32);
+            }
+            /* end of the row: close it */
+            if (!row_has) {
+                if (lane == 0) { out.rowV[row] = 0; out.rowT[row] = 0; out.rowA[row] = 0; }
+            } else if ((int32_t)(last_seq - S.deq) >= 0) { /* its last segment still waits: mark it */
+                if (lane == 0) Q.meta[last_seq & (SEGQ_CAP - 1)] |= SEGQ_LAST;
+                w_sync(w);
+            } else { /* all of it is flushed: it is the row the last window left open */
+                if (lane == 0) {
+                    const uint32_t tv = S.p_va & 0xFFFFu, ta = S.p_va >> 16;
+                    out.rowV[row] = tv; out.rowT[row] = S.p_t; out.rowA[row] = ta;
+                    if (tv) hd_atomic_add64(&out.layerTot[3 * lz + 0], (unsigned long long)tv);
+                    if (S.p_t) hd_atomic_add64(&out.layerTot[3 * lz + 1], (unsigned long long)S.p_t);
+                    if (ta) hd_atomic_add64(&out.layerTot[3 * lz + 2], (unsigned long long)ta);
+                }
+                S.p_va = 0; S.p_t = 0;
             }
         }
     }
-    list_close(L, cur, lane);
+    while (S.enq != S.deq) {
+        const uint32_t n = S.enq - S.deq;
+        count_flush(w, g, s_ntri, nth8, L, out, Q, S, n < 32 ? n : 32);
+    }
+    list_close(L, S.cur, lane);
 }
 
 #endif /* ISOMC_CELL_CUH */

@@ -63,4 +63,10 @@ cudaError_t isomc_launch_emit_list_sdf(const Geo &g, const SdfProgram &prog, con
                                        const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                        const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
                                        const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st);
+
+/* PointCloud (isomc_points.cu): segA = one u32 per 32-cell segment (in-row prefix of the active-cell count) */
+cudaError_t isomc_launch_points_count(const Geo &g, const uint32_t *signs, uint32_t *segA, uint32_t *rowV, uint32_t *rowT,
+                                      unsigned long long *layerTot, int sms, cudaStream_t st);
+cudaError_t isomc_launch_points_emit(const Geo &g, const uint32_t *signs, const uint32_t *segA, const uint32_t *rowPV, float *xyz,
+                                     uint64_t cap_v, int sms, cudaStream_t st);
 #endif

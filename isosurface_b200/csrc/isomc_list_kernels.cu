@@ -30,14 +30,14 @@ template <bool WIDE, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_count_list(Geo g, const uint32_t *__restrict__ signs, const uint8_t *__restrict__ ntri_g,
                                                     ListBufs L, CountOut out, uint32_t gshift, uint32_t row0, uint32_t row1) {
     __shared__ uint8_t s_ntri[256];
-    __shared__ uint32_t s_R[8][32];
+    __shared__ SegQueue s_q[8];
     __shared__ uint8_t s_nth8[256 * 8];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_ntri[i] = ntri_g[i]; nth8_fill(s_nth8, (uint32_t)i); }
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5;
     const Warp w{threadIdx.x & 31u, nullptr};
     count_list_warp<WIDE>(w, g, signs, s_ntri, s_nth8, L, out, gshift, row0, row1, blockIdx.x * (blockDim.x >> 5) + warp,
-                          gridDim.x * (blockDim.x >> 5), s_R[warp]);
+                          gridDim.x * (blockDim.x >> 5), s_q[warp]);
 }
 
 /* list blocks [*blk_first, *blk_end): one CTA per block, one lane per entry */

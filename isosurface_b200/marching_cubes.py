@@ -139,3 +139,32 @@ class MarchingCubes:
         out = np.zeros((n, n - 1, n - 1), np.uint8)
         _lib.check(self._lib.isomc_debug_cube_indices(self._h, out.ctypes.data), self._h)
         return out
+
+
+class PointCloud(MarchingCubes):
+    """`PointCloud(size).extract(source, extractor)` == reference `PointCloud::<Signed>::new(size).extract(&source,
+    &mut extractor)` (src/point_cloud.rs:33-63): one vertex per active cell, the midpoint of the cell's corners 0 and 6,
+    in cell order; no face data.  Shares the handle machinery of MarchingCubes (same lattice, same sources)."""
+
+    def extract(self, source, extractor):
+        self.extract_device(source)
+        xyz, _ = self.copy_out()
+        replay(extractor, xyz, np.zeros(0, np.uint32))
+
+    def extract_device(self, source):
+        src = source.source if isinstance(source, Sampler) else source
+        if isinstance(src, DenseGrid):
+            if src.size != self.size:
+                raise ValueError("grid is for size %d, PointCloud for %d" % (src.size, self.size))
+            fn = self._lib.isomc_points_grid_device if src.on_device else self._lib.isomc_points_grid_host
+            _lib.check(fn(self._h, src.ptr), self._h)
+        else:
+            prog = encode_program(src)
+            _lib.check(self._lib.isomc_points_sdf(self._h, prog.ctypes.data, len(prog)), self._h)
+        return self.counts()
+
+    def extract_host(self, grid, xyz=None, idx=None):
+        raise NotImplementedError("PointCloud delivers through extract() / extract_device() + copy_out()")
+
+    def enqueue(self, source):
+        raise NotImplementedError("PointCloud extracts synchronously")

@@ -533,3 +533,69 @@ int oracle_cube_indices(uint32_t size, const float *grid, uint32_t z_cells, uint
     if (!rc) oracle_mesh_free(&tmp);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* PointCloud::<Signed>::new(size).extract(&source, &mut extractor)                      */
+/*   reference src/point_cloud.rs:50-63: the same PrimalGrid traversal; every cell whose */
+/*   cube_index is neither 0 nor 255 emits corners[0].lerp(corners[6], 0.5)              */
+/*   (src/math/vector.rs:325-333: of = 1.0 - f; of * self.c + f * other.c per component) */
+/*   in cell order.  No face data.                                                       */
+/* ------------------------------------------------------------------------------------ */
+static int point_cloud_impl(source_t *src, uint32_t z_cells, oracle_mesh *out) {
+    const uint32_t size = src->size;
+    memset(out, 0, sizeof *out);
+    if (size < 1) return -1;
+    int rc = 0;
+    lattice_entry *layers[2];
+    layers[0] = (lattice_entry *)malloc((size_t)size * size * sizeof(lattice_entry));
+    layers[1] = (lattice_entry *)malloc((size_t)size * size * sizeof(lattice_entry));
+    if (!layers[0] || !layers[1]) { rc = -4; goto done; }
+    const uint32_t size_minus_one = size - 1;
+    const float one_over_size = 1.0f / (float)size_minus_one;
+    for (uint32_t y = 0; y < size; ++y)
+        for (uint32_t x = 0; x < size; ++x) {
+            v3 c = {(float)x * one_over_size, (float)y * one_over_size, 0.0f};
+            lattice_entry e = {c, source_at(src, c, x, y, 0)};
+            layers[0][(size_t)y * size + x] = e;
+        }
+    for (uint32_t z = 0; z < z_cells; ++z) {
+        for (uint32_t y = 0; y < size; ++y)
+            for (uint32_t x = 0; x < size; ++x) {
+                v3 c = {(float)x * one_over_size, (float)y * one_over_size, (float)(z + 1) * one_over_size};
+                lattice_entry e = {c, source_at(src, c, x, y, z + 1)};
+                layers[1][(size_t)y * size + x] = e;
+            }
+        if (src->err) { rc = -2; goto done; }
+        for (uint32_t y = 0; y < size_minus_one; ++y)
+            for (uint32_t x = 0; x < size_minus_one; ++x) {
+                unsigned cube_index = 0;
+                for (int i = 0; i < 8; ++i) {
+                    float v = layers[CORNER_OFF[i][2]][(size_t)(y + CORNER_OFF[i][1]) * size + x + CORNER_OFF[i][0]].value;
+                    if (!(v > 0.0f)) cube_index |= 1u << i;
+                }
+                if (cube_index != 0 && cube_index != 255) {
+                    v3 a = layers[0][(size_t)y * size + x].corner;             /* corners[0] */
+                    v3 b = layers[1][(size_t)(y + 1) * size + x + 1].corner;   /* corners[6] */
+                    const float f = 0.5f, of = 1.0f - f;
+                    v3 p = {of * a.x + f * b.x, of * a.y + f * b.y, of * a.z + f * b.z};
+                    if (push_vertex(out, p)) { rc = -4; goto done; }
+                    out->n_active_cells++;
+                }
+            }
+        lattice_entry *t = layers[0]; layers[0] = layers[1]; layers[1] = t;
+    }
+done:
+    free(layers[0]); free(layers[1]);
+    if (rc) oracle_mesh_free(out);
+    return rc;
+}
+
+int oracle_point_cloud_sdf(uint32_t size, const osdf_node *prog, uint32_t n, oracle_mesh *out) {
+    source_t s = {prog, n, NULL, size, 0};
+    return point_cloud_impl(&s, size, out);
+}
+
+int oracle_point_cloud_grid(uint32_t size, const float *grid, uint32_t z_cells, oracle_mesh *out) {
+    source_t s = {NULL, 0, grid, size, 0};
+    return point_cloud_impl(&s, z_cells, out);
+}

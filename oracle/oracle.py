@@ -46,6 +46,8 @@ def lib():
         _LIB.oracle_sample_sdf.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         _LIB.oracle_tables.argtypes = [C.c_void_p] * 4
         _LIB.oracle_mesh_free.argtypes = [C.POINTER(_Mesh)]
+        _LIB.oracle_point_cloud_sdf.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
+        _LIB.oracle_point_cloud_grid.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
     return _LIB
 
 
@@ -85,6 +87,26 @@ def extract_grid(size, grid, z_cells=None, mode=LEAN):
     if rc:
         raise RuntimeError("oracle_extract_grid rc=%d" % rc)
     return _take(m)
+
+
+def point_cloud_sdf(size, prog):
+    """PointCloud::<Signed>::new(size).extract (reference src/point_cloud.rs:50-63): xyz of one point per active cell"""
+    m = _Mesh()
+    prog = np.ascontiguousarray(prog)
+    rc = lib().oracle_point_cloud_sdf(size, prog.ctypes.data, len(prog), C.byref(m))
+    if rc:
+        raise RuntimeError("oracle_point_cloud_sdf rc=%d" % rc)
+    return _take(m)[0]
+
+
+def point_cloud_grid(size, grid, z_cells=None):
+    grid = np.ascontiguousarray(grid, dtype=np.float32)
+    z_cells = size if z_cells is None else z_cells
+    m = _Mesh()
+    rc = lib().oracle_point_cloud_grid(size, grid.ctypes.data, z_cells, C.byref(m))
+    if rc:
+        raise RuntimeError("oracle_point_cloud_grid rc=%d" % rc)
+    return _take(m)[0]
 
 
 def cube_indices(size, grid, z_cells=None):

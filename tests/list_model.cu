@@ -54,15 +54,15 @@ struct WarpJob {
     ListBufs L;
     CountOut out;
     uint32_t gshift, row0, row1, gwarp, nwarps;
-    uint32_t Rsm[32];
+    SegQueue Q;
 };
 WarpJob *g_job = nullptr;
 
 void lane_main(int lane) {
     WarpJob &J = *g_job;
     const Warp w{(uint32_t)lane, (void *)g_emu};
-    if (J.wide) count_list_warp<true>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.gwarp, J.nwarps, J.Rsm);
-    else count_list_warp<false>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.gwarp, J.nwarps, J.Rsm);
+    if (J.wide) count_list_warp<true>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.gwarp, J.nwarps, J.Q);
+    else count_list_warp<false>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.gwarp, J.nwarps, J.Q);
     g_emu->done[lane] = true;
 }
 
@@ -155,13 +155,15 @@ int list_model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const fl
     EmitTab et;
     isomc_build_emit_tab(mt, &et);
 
-    std::vector<uint2> ent((size_t)cap_blocks * LIST_BLOCK), segrec(nrows_c * g.nsegx);
+    std::vector<uint2> ent((size_t)cap_blocks * LIST_BLOCK);
+    std::vector<uint2> segrec(nrows_c * g.nsegx);
+    std::vector<uint32_t> segtpre(nrows_c * g.nsegx, 0xEEEEEEEEu);
     std::vector<uint32_t> ent_yz((size_t)cap_blocks * LIST_BLOCK), blkfill(cap_blocks, 0xDEADBEEFu);
     /* poison what the kernels may only read after writing */
     memset(ent.data(), 0xEE, ent.size() * sizeof(uint2));
     memset(segrec.data(), 0xEE, segrec.size() * sizeof(uint2));
     uint32_t ctr = 0;
-    ListBufs L{ent.data(), ent_yz.data(), segrec.data(), blkfill.data(), &ctr, cap_blocks};
+    ListBufs L{ent.data(), ent_yz.data(), segrec.data(), segtpre.data(), blkfill.data(), &ctr, cap_blocks};
     std::vector<uint32_t> rowV(nrows_c + 4, 0xDEADBEEFu), rowT(nrows_c + 4, 0xDEADBEEFu), rowA(nrows_c + 4, 0xDEADBEEFu);
     std::vector<unsigned long long> layerTot((size_t)g.ncl * 3 + 4, 0ull);
     CountOut out{rowV.data(), rowT.data(), rowA.data(), layerTot.data()};

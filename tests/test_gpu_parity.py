@@ -450,3 +450,35 @@ def test_brick_kernels_still_match(iso, oracle, monkeypatch):
             xyz, idx = mc.copy_out()
             assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
         mc.close()
+
+
+def test_point_cloud_matches_oracle(iso, oracle):
+    """PointCloud(size).extract: same points, same order, same bits as the restated reference (point_cloud.rs:50-63)"""
+    for name, size in (("sphere03", 32), ("csgA", 64), ("torus_origin", 128)):
+        want = oracle.point_cloud_sdf(size, oracle_prog(name))
+        pc = iso.PointCloud(size)
+        verts = []
+        pc.extract(iso.Sampler(iso_source(name)), iso.OnlyVertices(verts))
+        assert np.asarray(verts, np.float32).tobytes() == want.tobytes()
+        nv, nt, na = pc.counts()
+        assert (nv, nt, na) == (len(want) // 3, 0, len(want) // 3)
+        pc.close()
+    rng = np.random.default_rng(3)
+    for size in (2, 3, 33, 70, 130):
+        f = rng.standard_normal((size + 1, size, size)).astype(np.float32)
+        want = oracle.point_cloud_grid(size, f)
+        pc = iso.PointCloud(size)
+        for _ in range(2):
+            sink = iso.ArrayMesh()
+            pc.extract(iso.DenseGrid(f), sink)
+            assert sink.vertices.tobytes() == want.tobytes() and sink.indices.size == 0
+        pc.close()
+    # device-resident lattice, a mesh extract on the same handle type afterwards is unaffected
+    size = 160
+    t = synth(iso, 2, size, 1)
+    want = oracle.point_cloud_grid(size, t.cpu().numpy().reshape(size + 1, size, size))
+    pc = iso.PointCloud(size)
+    pc.extract_device(iso.DenseGrid(t))
+    assert pc.copy_out()[0].tobytes() == want.tobytes()
+    pc.close()
+    assert iso.PointCloud(1).extract_device(iso.Sampler(iso_source("sphere03")))[0] == 0

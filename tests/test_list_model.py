@@ -85,6 +85,33 @@ def test_model_wide_rows(model, oracle):
     assert mesh_diff(xyz, idx, oxyz, oidx) == ""
 
 
+@pytest.mark.parametrize("size,zc,n_warps", [(1060, 1, 3), (1100, 1, 1), (2080, 1, 5)])
+def test_model_wide_rows_dense(model, oracle, size, zc, n_warps):
+    """dense wide rows: more than 32 queued segments per row, so rows are flushed piecewise (open-row carries, the
+    row-end cases 'last segment still queued' and 'everything already flushed'); every 7th row is empty"""
+    rng = np.random.default_rng(size)
+    grid = rng.standard_normal((zc + 1, size, size)).astype(np.float32)
+    grid[:, ::7, :] = 1.0
+    grid[:, 5, : size // 2] = 1.0  # a row whose queued segments start mid-row
+    oxyz, oidx, oact = oracle.extract_grid(size, grid, z_cells=zc)
+    rc, xyz, idx, tot = run_model(model, size, grid, z_end=zc, n_warps=n_warps, cap_blocks=60000)
+    assert rc == 0 and tot[3] == oact
+    assert mesh_diff(xyz, idx, oxyz, oidx) == ""
+
+
+def test_model_sparse_rows_batch_across_passes(model, oracle):
+    """a sparse field: few non-uniform segments per pass, so one flush window mixes segments of many rows and passes"""
+    size = 96
+    prog = oracle_prog("sphere03")
+    grid = oracle.fill_grid_sdf(size, prog)
+    grid[40:44, 10:12, 3:90] *= -1.0  # some scattered sign flips
+    oxyz, oidx, oact = oracle.extract_grid(size, grid)
+    for n_warps in (1, 4, 29):
+        rc, xyz, idx, tot = run_model(model, size, grid, n_warps=n_warps, seed=n_warps)
+        assert rc == 0 and tot[3] == oact
+        assert mesh_diff(xyz, idx, oxyz, oidx) == ""
+
+
 def test_model_slabs_concatenate(model, oracle):
     """two slabs with the ghost layer and the all-gathered bases give the unsharded mesh"""
     size, cut = 24, 11

@@ -133,3 +133,22 @@ def test_edge_cases(oracle):
     g[2, 2, 2] = -np.inf
     xyz, idx, act = O.extract_grid(4, g)
     assert act == 8 and len(idx) // 3 == 8 and len(xyz) // 3 == 6
+
+
+def test_point_cloud_oracle_properties(oracle):
+    """PointCloud restatement (reference src/point_cloud.rs:50-63): one point per active cell, cell order, cell centres"""
+    from helpers import oracle_prog
+    for name, size in (("sphere03", 32), ("torus", 40)):
+        prog = oracle_prog(name)
+        pts = oracle.point_cloud_sdf(size, prog).reshape(-1, 3)
+        _, _, act = oracle.extract_sdf(size, prog)
+        assert len(pts) == act                                   # same active-cell predicate as MarchingCubes
+        grid = oracle.fill_grid_sdf(size, prog)
+        assert oracle.point_cloud_grid(size, grid).tobytes() == pts.tobytes()
+        ci = oracle.cube_indices(size, grid)
+        z, y, x = np.nonzero((ci != 0) & (ci != 255))            # C order == (z, y, x) cell order
+        inv = np.float32(1.0) / np.float32(size - 1)
+        half = np.float32(0.5)
+        want = np.stack([half * (c.astype(np.float32) * inv) + half * ((c + 1).astype(np.float32) * inv) for c in (x, y, z)], axis=1)
+        assert want.astype(np.float32).tobytes() == pts.tobytes()
+    assert oracle.point_cloud_sdf(1, oracle_prog("sphere03")).size == 0
