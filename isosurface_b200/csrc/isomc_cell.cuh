@@ -174,43 +174,42 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
         eid[5 * eid_stride] = vid + (r3 & 3u);
         eid[6 * eid_stride] = vid + (r3 >> 2 & 3u);
         eid[10 * eid_stride] = vid + (r3 >> 4 & 3u);
-        uint32_t v2, c2, q;
-        if (em & (1u << 7 | 1u << 11)) {
-            if (x & 31u) { /* same segment: the previous list entry */
-                const uint2 e2 = L.ent[k - 1];
-                v2 = A.rowPV[row] + (e2.x & 0xFFFFu);
-                c2 = e2.y >> 16 & 255u;
-            } else {
-                creator_lookup(g, L, A.rowPV, x - 1, row, v2, c2);
-            }
-            q = T.rank3[c2];
-            eid[7 * eid_stride] = v2 + (q & 3u);
-            eid[11 * eid_stride] = v2 + (q >> 4 & 3u);
-        }
-        if (em & (1u << 4 | 1u << 9)) {
-            creator_lookup(g, L, A.rowPV, x, row - 1, v2, c2);
-            q = T.rank3[c2];
-            eid[4 * eid_stride] = v2 + (q >> 2 & 3u);
-            eid[9 * eid_stride] = v2 + (q >> 4 & 3u);
-        }
-        if (em & (1u << 8)) {
-            creator_lookup(g, L, A.rowPV, x - 1, row - 1, v2, c2);
-            eid[8 * eid_stride] = v2 + (T.rank3[c2] >> 4 & 3u);
-        }
-        if (em & (1u << 1 | 1u << 2)) {
-            creator_lookup(g, L, A.rowPV, x, row - g.ncx, v2, c2);
-            q = T.rank3[c2];
-            eid[1 * eid_stride] = v2 + (q & 3u);
-            eid[2 * eid_stride] = v2 + (q >> 2 & 3u);
-        }
-        if (em & (1u << 3)) {
-            creator_lookup(g, L, A.rowPV, x - 1, row - g.ncx, v2, c2);
-            eid[3 * eid_stride] = v2 + (T.rank3[c2] & 3u);
-        }
-        if (em & 1u) {
-            creator_lookup(g, L, A.rowPV, x, row - g.ncx - 1, v2, c2);
-            eid[0] = v2 + (T.rank3[c2] >> 2 & 3u);
-        }
+        /* all segment records first, then all entries, then the ranks: the loads of one stage are independent, so their
+         * latencies overlap (the kernel is latency-bound, not bandwidth-bound) */
+        const bool n1 = (em & (1u << 7 | 1u << 11)) != 0, n2 = (em & (1u << 4 | 1u << 9)) != 0, n3 = (em & (1u << 8)) != 0;
+        const bool n4 = (em & (1u << 1 | 1u << 2)) != 0, n5 = (em & (1u << 3)) != 0, n6 = (em & 1u) != 0;
+        const bool n1g = n1 && (x & 31u) == 0; /* -x neighbour in the previous segment; otherwise it is list entry k - 1 */
+        const uint32_t rowy = row - 1, rowz = row - g.ncx, rowyz = row - g.ncx - 1;
+        const uint32_t sx = x >> 5, sxm = (x - 1) >> 5, bx = (1u << (x & 31u)) - 1u, bxm = (1u << ((x - 1) & 31u)) - 1u;
+        const uint2 z2 = make_uint2(0u, 0u);
+        const uint2 rA = n1g ? L.segrec[(uint64_t)row * g.nsegx + sxm] : z2;
+        const uint2 rB = n2 ? L.segrec[(uint64_t)rowy * g.nsegx + sx] : z2;
+        const uint2 rC = n3 ? L.segrec[(uint64_t)rowy * g.nsegx + sxm] : z2;
+        const uint2 rD = n4 ? L.segrec[(uint64_t)rowz * g.nsegx + sx] : z2;
+        const uint2 rE = n5 ? L.segrec[(uint64_t)rowz * g.nsegx + sxm] : z2;
+        const uint2 rF = n6 ? L.segrec[(uint64_t)rowyz * g.nsegx + sx] : z2;
+        const uint32_t pvy = (n2 || n3) ? A.rowPV[rowy] : 0u, pvz = (n4 || n5) ? A.rowPV[rowz] : 0u, pvyz = n6 ? A.rowPV[rowyz] : 0u;
+        const uint32_t cap = L.cap_blocks * LIST_BLOCK; /* (positions beyond it only after a list overflow; the host re-runs then) */
+        const uint32_t kA = n1g ? rA.x + hd_popc(rA.y & bxm) : (uint32_t)k - 1u;
+        const uint32_t kB = rB.x + hd_popc(rB.y & bx), kC = rC.x + hd_popc(rC.y & bxm);
+        const uint32_t kD = rD.x + hd_popc(rD.y & bx), kE = rE.x + hd_popc(rE.y & bxm), kF = rF.x + hd_popc(rF.y & bx);
+        const uint2 eA = (n1 && kA < cap) ? L.ent[kA] : z2, eB = (n2 && kB < cap) ? L.ent[kB] : z2;
+        const uint2 eC = (n3 && kC < cap) ? L.ent[kC] : z2, eD = (n4 && kD < cap) ? L.ent[kD] : z2;
+        const uint2 eE = (n5 && kE < cap) ? L.ent[kE] : z2, eF = (n6 && kF < cap) ? L.ent[kF] : z2;
+        const uint32_t pv0 = vid - (ea.x & 0xFFFFu); /* rowPV[row] */
+        uint32_t q;
+        q = T.rank3[eA.y >> 16 & 255u];
+        eid[7 * eid_stride] = pv0 + (eA.x & 0xFFFFu) + (q & 3u);
+        eid[11 * eid_stride] = pv0 + (eA.x & 0xFFFFu) + (q >> 4 & 3u);
+        q = T.rank3[eB.y >> 16 & 255u];
+        eid[4 * eid_stride] = pvy + (eB.x & 0xFFFFu) + (q >> 2 & 3u);
+        eid[9 * eid_stride] = pvy + (eB.x & 0xFFFFu) + (q >> 4 & 3u);
+        eid[8 * eid_stride] = pvy + (eC.x & 0xFFFFu) + (T.rank3[eC.y >> 16 & 255u] >> 4 & 3u);
+        q = T.rank3[eD.y >> 16 & 255u];
+        eid[1 * eid_stride] = pvz + (eD.x & 0xFFFFu) + (q & 3u);
+        eid[2 * eid_stride] = pvz + (eD.x & 0xFFFFu) + (q >> 2 & 3u);
+        eid[3 * eid_stride] = pvz + (eE.x & 0xFFFFu) + (T.rank3[eE.y >> 16 & 255u] & 3u);
+        eid[0] = pvyz + (eF.x & 0xFFFFu) + (T.rank3[eF.y >> 16 & 255u] >> 2 & 3u);
         /* the (at most three) vertices this cell creates all end at corner 6 = (x+1, y+1, z+1):
          *   e5 = corners 5 -> 6 (y edge), e6 = corners 6 -> 7 (x edge), e10 = corners 2 -> 6 (z edge) */
         if (owned) {
