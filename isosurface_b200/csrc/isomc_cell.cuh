@@ -170,6 +170,10 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
          * which of my edges (isomc_tables.h owner[0][]):  -x: e7 as e5, e11 as e10;  -y: e4 as e6, e9 as e10;
          * -x-y: e8 as e10;  -z: e1 as e5, e2 as e6;  -x-z: e3 as e5;  -y-z: e0 as e6.  Straight-line, predicated. */
         owned = em & (1u << 5 | 1u << 6 | 1u << 10);
+        /* samples for the vertices this cell creates: requested first, used last */
+        const bool o5 = (em >> 5 & 1u) != 0, o6 = (em >> 6 & 1u) != 0, o10 = (em >> 10 & 1u) != 0;
+        float s6 = 0.0f, s5 = 0.0f, s7 = 0.0f, s2 = 0.0f;
+        if (owned) src.corner6(g, x, y, lz, o5, o6, o10, s6, s5, s7, s2);
         const uint32_t r3 = T.rank3[ci];
         eid[5 * eid_stride] = vid + (r3 & 3u);
         eid[6 * eid_stride] = vid + (r3 >> 2 & 3u);
@@ -213,9 +217,6 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
         /* the (at most three) vertices this cell creates all end at corner 6 = (x+1, y+1, z+1):
          *   e5 = corners 5 -> 6 (y edge), e6 = corners 6 -> 7 (x edge), e10 = corners 2 -> 6 (z edge) */
         if (owned) {
-            const bool o5 = (em >> 5 & 1u) != 0, o6 = (em >> 6 & 1u) != 0, o10 = (em >> 10 & 1u) != 0;
-            float s6, s5, s7, s2;
-            src.corner6(g, x, y, lz, o5, o6, o10, s6, s5, s7, s2);
             const float fx0 = hd_mul((float)x, g.inv), fx1 = hd_mul((float)(x + 1), g.inv);
             const float fy0 = hd_mul((float)y, g.inv), fy1 = hd_mul((float)(y + 1), g.inv);
             const float fz0 = hd_mul((float)(g.gz0 + lz), g.inv), fz1 = hd_mul((float)(g.gz0 + lz + 1), g.inv);

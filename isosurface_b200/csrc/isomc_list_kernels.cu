@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(256, MINB) k_count_list(Geo g, const uint32_t 
 }
 
 /* list blocks [*blk_first, *blk_end): one CTA per block, one lane per entry */
-template <class Src>
-__global__ void __launch_bounds__(LIST_BLOCK) k_emit_list(Src src, Geo g, ListBufs L, const EmitTab *__restrict__ tab_g,
+template <class Src, int MINB>
+__global__ void __launch_bounds__(LIST_BLOCK, MINB) k_emit_list(Src src, Geo g, ListBufs L, const EmitTab *__restrict__ tab_g,
                                                           const uint32_t *__restrict__ rowPV, const uint32_t *__restrict__ rowPT,
                                                           const unsigned long long *__restrict__ layerTot,
                                                           const uint32_t *__restrict__ vofs_ptr, float *__restrict__ xyz,
@@ -83,20 +83,29 @@ inline uint32_t grid_for(uint64_t warps_needed, int sms, int warps_per_block, in
     return (uint32_t)(blocks < 1 ? 1 : blocks);
 }
 
+/* CTAs per SM of k_emit_list: register budget vs. warps in flight (ISOMC_EMIT_MINB = 4, 5 or 6; default 5) */
+static int emit_list_minb() {
+    static int v = 0;
+    if (v == 0) {
+        const char *p = getenv("ISOMC_EMIT_MINB");
+        v = p ? atoi(p) : 5;
+        if (v != 4 && v != 5 && v != 6) v = 5;
+    }
+    return v;
+}
+
 template <class Src>
 cudaError_t launch_emit_list(const Src &src, const Geo &g, const ListBufs &L, const EmitTab *tab, const uint32_t *rowPV,
                              const uint32_t *rowPT, const unsigned long long *layerTot, const uint32_t *vofs, float *xyz,
                              uint32_t *idx, uint64_t cap_v, uint64_t cap_t, const uint32_t *blk_first, const uint32_t *blk_end,
                              int sms, cudaStream_t st) {
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        int n = 1;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_emit_list<Src>, (int)LIST_BLOCK, 0);
-        if (e != cudaSuccess) return e;
-        per_sm = n < 1 ? 1 : n;
+    const int minb = emit_list_minb();
+    const uint32_t grid = (uint32_t)(sms * minb);
+    switch (minb) {
+    case 4: k_emit_list<Src, 4><<<grid, LIST_BLOCK, 0, st>>>(src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end); break;
+    case 6: k_emit_list<Src, 6><<<grid, LIST_BLOCK, 0, st>>>(src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end); break;
+    default: k_emit_list<Src, 5><<<grid, LIST_BLOCK, 0, st>>>(src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end); break;
     }
-    k_emit_list<Src><<<sms * per_sm, LIST_BLOCK, 0, st>>>(src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t,
-                                                          blk_first, blk_end);
     return cudaGetLastError();
 }
 

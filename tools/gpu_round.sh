@@ -4,8 +4,10 @@ mkdir -p gpurun_out
 export ISOMC_EMIT=list
 ( timeout 300 python tools/gpu_check.py ) > gpurun_out/check_list.log 2>&1; echo "check rc=$?"
 tail -2 gpurun_out/check_list.log
+if [ -z "$SKIP_PYTEST" ]; then
 ( timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu_list.log 2>&1; echo "pytest rc=$?"
 tail -3 gpurun_out/pytest_gpu_list.log
+fi
 run() { # name env...
   local tag=$1; shift
   for wl in fbm512 gyroid1024 spheres2048; do
@@ -24,5 +26,8 @@ for v in "$@"; do
     list5) run list5 ISOMC_EMIT=list ISOMC_LIST_MINB=5;;
     list6) run list6 ISOMC_EMIT=list ISOMC_LIST_MINB=6;;
     brick) run brick ISOMC_EMIT=brick;;
+    emit4) run emit4 ISOMC_EMIT=list ISOMC_EMIT_MINB=4;;
+    emit5) run emit5 ISOMC_EMIT=list ISOMC_EMIT_MINB=5;;
+    emit6) run emit6 ISOMC_EMIT=list ISOMC_EMIT_MINB=6;;
   esac
 done
