@@ -225,6 +225,8 @@ def run_ours(args):
             raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout to the one JSON line: a box-level NCCL_DEBUG=VERSION would print a banner there
+        os.environ["NCCL_DEBUG"] = os.environ.get("ISOMC_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not _lib.LIB_PATH.exists():
         if rank == 0:
@@ -334,9 +336,13 @@ def run_ours(args):
         "gpu_launches": launches_per_step * args.steps,
     }
     # roofline of the dominant kernel and of the whole extract
-    kern = {"k_sign": (prof[0], 4 * S / world), "k_count": (prof[1], 0), "k_scan_rows": (prof[2], 0),
-            "k_emit": (prof[3], (12 * V + 12 * T) / world)}  # "k_emit" here = k_emit + k_vertex (one CUDA-event interval)
-    dom = max(("k_sign", "k_emit"), key=lambda k: kern[k][0])
+    # kernel names of the path in use: active-cell list (default) or the older brick kernels (ISOMC_EMIT=brick)
+    brick = os.environ.get("ISOMC_EMIT", "list") == "brick"
+    k_count, k_emit = ("k_count", "k_emit") if brick else ("k_count_list", "k_emit_list")
+    # k_emit_list writes vertices and triangles; in the brick path the interval covers k_emit + k_vertex
+    kern = {"k_sign": (prof[0], 4 * S / world), k_count: (prof[1], 0), "k_scan_rows": (prof[2], 0),
+            k_emit: (prof[3], (12 * V + 12 * T) / world)}
+    dom = max(("k_sign", k_emit), key=lambda k: kern[k][0])
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
@@ -350,7 +356,7 @@ def run_ours(args):
                             "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": kern[dom][1], "ms_per_launch": kern[dom][0]}
         ach_all = b_alg / world / t_s / 1e9
-        line["roofline_extract"] = {"bound": "hbm", "scope": "whole extract (k_sign+k_count+k_scan_rows+k_emit)",
+        line["roofline_extract"] = {"bound": "hbm", "scope": "whole extract (k_sign+%s+k_scan_rows+%s)" % (k_count, k_emit),
                                     "achieved": ach_all * world, "per_gpu": ach_all, "peak": hbm_peak, "unit": "GB/s",
                                     "frac": ach_all / hbm_peak, "algorithmic_bytes": b_alg,
                                     "formula": "4*S + 12*V + 12*T"}
@@ -361,7 +367,8 @@ def run_ours(args):
         line["roofline"] = {"bound": "fp32", "kernel": "k_sign<SdfSrc>", "achieved": ach, "peak": peak, "unit": "Tlane-op/s",
                             "frac": ach / peak, "traffic": None, "peak_source": "148 SM x 128 lanes x 1.965 GHz, non-FMA",
                             "ops_per_sample": ops}
-    line["kernels_ms"] = {"k_sign": prof[0], "k_count": prof[1], "k_scan_rows": prof[2], "k_emit": prof[3], "sum": prof[4]}
+    line["kernels_ms"] = {"k_sign": prof[0], k_count: prof[1], "k_scan_rows": prof[2], k_emit: prof[3], "sum": prof[4]}
+    line["config"]["path"] = "brick kernels" if brick else "active-cell list"
     line["clocks"] = clk.summary()
 
     # ---- e2e through the public API with HOST buffers (H2D of the grid + D2H of the mesh inside the timed region)
