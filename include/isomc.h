@@ -125,6 +125,13 @@ int32_t isomc_points_grid_host(isomc_t *h, const float *h_grid);
 int32_t isomc_counts(isomc_t *h, uint64_t *n_vertices, uint64_t *n_triangles, uint64_t *n_active_cells);
 int32_t isomc_device_buffers(isomc_t *h, const float **d_xyz, const uint32_t **d_idx);
 int32_t isomc_copy_out(isomc_t *h, float *xyz /* 3*V */, uint32_t *idx /* 3*T */);
+/* extractor::IndexedInterleavedNormals (reference src/extractor.rs:95-127) for a `CentralDifference` source around an
+ * implicit tree (src/source.rs:82-94; epsilon 1e-6 by default there): 6 floats per vertex, position then
+ * normal = (f(q+dx)-f(q-dx), f(q+dy)-f(q-dy), f(q+dz)-f(q-dz)) / (2*epsilon), evaluated on the device at the vertices of
+ * the last extract.  Translations that enclose the whole program are applied to the vertex first (q = v - offset, as
+ * DemoSource does around its CentralDifference, examples/common/sources.rs:55-60).  xyzn holds 6*V floats, idx 3*T (may be NULL). */
+int32_t isomc_copy_out_interleaved_normals(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes, float epsilon, float *xyzn,
+                                           uint32_t *idx);
 int32_t isomc_stats_get(isomc_t *h, isomc_stats *out);
 
 /* ---- stream control (benchmarks time with CUDA events on the launching stream) ---------- */

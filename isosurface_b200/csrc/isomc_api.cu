@@ -806,6 +806,53 @@ int32_t isomc_copy_out(isomc_t *h, float *xyz, uint32_t *idx) {
     return ISOMC_OK;
 }
 
+/* IndexedInterleavedNormals with a CentralDifference source (reference src/extractor.rs:95-127, src/source.rs:82-94) */
+int32_t isomc_copy_out_interleaved_normals(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes, float epsilon, float *xyzn,
+                                           uint32_t *idx) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h->have_result) return fail(h, ISOMC_ERR_NO_RESULT, "no extract has completed on this handle");
+    if (!(epsilon > 0.0f)) return fail(h, ISOMC_ERR_BAD_ARG, "epsilon must be positive");
+    SdfProgram P;
+    int32_t rc = validate_program(h, prog, n_nodes, &P);
+    if (rc) return rc;
+    rc = bind_device(h);
+    if (rc) return rc;
+    /* translations that enclose the whole program are applied to the vertex first (DemoSource around CentralDifference,
+     * examples/common/sources.rs:55-60); the differences are taken on what is inside */
+    float offsets[ISOMC_SDF_MAX_TRANSLATE][3];
+    uint32_t n_off = 0, lo = 0, hi = P.n;
+    while (hi - lo >= 3 && P.nodes[lo].op == ISOMC_SDF_TRANSLATE_PUSH && P.nodes[hi - 1].op == ISOMC_SDF_TRANSLATE_POP) {
+        int depth = 0;
+        bool encloses = true;
+        for (uint32_t i = lo; i < hi; ++i) {
+            if (P.nodes[i].op == ISOMC_SDF_TRANSLATE_PUSH) ++depth;
+            if (P.nodes[i].op == ISOMC_SDF_TRANSLATE_POP && --depth == 0 && i != hi - 1) { encloses = false; break; }
+        }
+        if (!encloses) break;
+        offsets[n_off][0] = P.nodes[lo].a; offsets[n_off][1] = P.nodes[lo].b; offsets[n_off][2] = P.nodes[lo].c;
+        ++n_off; ++lo; --hi;
+    }
+    SdfProgram inner;
+    memset(&inner, 0, sizeof inner);
+    inner.n = hi - lo;
+    memcpy(inner.nodes, P.nodes + lo, inner.n * sizeof(isomc_sdf_node));
+    if (h->n_v) {
+        if (!xyzn) return fail(h, ISOMC_ERR_BAD_ARG, "xyzn == NULL");
+        float *d_out = nullptr;
+        CU(h, cudaMalloc(&d_out, h->n_v * 24));
+        cudaError_t e = isomc_launch_normals_cd(inner, offsets, n_off, epsilon, h->xyz, h->n_v, d_out, h->sms, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(xyzn, d_out, h->n_v * 24, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(d_out);
+        if (e != cudaSuccess) return fail(h, ISOMC_ERR_CUDA, "normal sampling failed: %s", cudaGetErrorString(e));
+    }
+    if (idx && h->n_t) {
+        CU(h, cudaMemcpyAsync(idx, h->idx, h->n_t * 12, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
+    return ISOMC_OK;
+}
+
 int32_t isomc_stats_get(isomc_t *h, isomc_stats *out) {
     if (!h || !out) return ISOMC_ERR_BAD_ARG;
     if (!h->have_result) return fail(h, ISOMC_ERR_NO_RESULT, "no extract has completed on this handle");

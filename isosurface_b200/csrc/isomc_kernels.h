@@ -67,6 +67,9 @@ cudaError_t isomc_launch_emit_list_sdf(const Geo &g, const SdfProgram &prog, con
 /* PointCloud (isomc_points.cu): segA = one u32 per 32-cell segment (in-row prefix of the active-cell count) */
 cudaError_t isomc_launch_points_count(const Geo &g, const uint32_t *signs, uint32_t *segA, uint32_t *rowV, uint32_t *rowT,
                                       unsigned long long *layerTot, int sms, cudaStream_t st);
+/* central-difference normals of an implicit tree at the vertices of the last extract, interleaved xyz | normal */
+cudaError_t isomc_launch_normals_cd(const SdfProgram &inner, const float (*offsets)[3], uint32_t n_offsets, float eps,
+                                    const float *xyz, uint64_t n_vertices, float *out, int sms, cudaStream_t st);
 cudaError_t isomc_launch_points_emit(const Geo &g, const uint32_t *signs, const uint32_t *segA, const uint32_t *rowPV, float *xyz,
                                      uint64_t cap_v, int sms, cudaStream_t st);
 #endif

@@ -103,3 +103,52 @@ cudaError_t isomc_launch_points_emit(const Geo &g, const uint32_t *signs, const 
     k_pc_emit<<<sms * 8, 256, 0, st>>>(g, signs, segA, rowPV, xyz, cap_v, 0u, g.ncl * g.ncx);
     return cudaGetLastError();
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Normals for extractor::IndexedInterleavedNormals (reference src/extractor.rs:95-127): every vertex v of the
+ * last extract is followed by `source.sample_normal(v)`, with `source` = a CentralDifference adaptor around an
+ * implicit tree (src/source.rs:82-94), possibly inside translations (examples/common/sources.rs:55-60:
+ * q = p - offset, then the wrapped source's normal at q):
+ *
+ *     n = ( f(q + dx) - f(q - dx),  f(q + dy) - f(q - dy),  f(q + dz) - f(q - dz) ) / (2 * epsilon)
+ *
+ * with dx = (epsilon, 0, 0) etc. added as whole vectors (the other two components get + 0.0 / - 0.0), every
+ * operation rounded to binary32 in the reference's order.  One lane per vertex, six evaluations of the program.
+ * ------------------------------------------------------------------------------------------------------------ */
+struct NormalOffsets {
+    float off[ISOMC_TR_DEPTH][3];
+    uint32_t n;
+};
+
+__global__ void __launch_bounds__(256) k_normals_cd(SdfProgram prog, NormalOffsets tr, float eps, const float *__restrict__ xyz,
+                                                    uint64_t n_vertices, float *__restrict__ out /* 6 floats per vertex */) {
+    const float two_eps = __fmul_rn(2.0f, eps);
+    for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < n_vertices; v += (uint64_t)gridDim.x * blockDim.x) {
+        const float px = xyz[3 * v], py = xyz[3 * v + 1], pz = xyz[3 * v + 2];
+        float qx = px, qy = py, qz = pz;
+        for (uint32_t k = 0; k < tr.n; ++k) {
+            qx = __fsub_rn(qx, tr.off[k][0]); qy = __fsub_rn(qy, tr.off[k][1]); qz = __fsub_rn(qz, tr.off[k][2]);
+        }
+        const float z = 0.0f;
+        const float vx = __fsub_rn(sdf_eval(prog, __fadd_rn(qx, eps), __fadd_rn(qy, z), __fadd_rn(qz, z)),
+                                   sdf_eval(prog, __fsub_rn(qx, eps), __fsub_rn(qy, z), __fsub_rn(qz, z)));
+        const float vy = __fsub_rn(sdf_eval(prog, __fadd_rn(qx, z), __fadd_rn(qy, eps), __fadd_rn(qz, z)),
+                                   sdf_eval(prog, __fsub_rn(qx, z), __fsub_rn(qy, eps), __fsub_rn(qz, z)));
+        const float vz = __fsub_rn(sdf_eval(prog, __fadd_rn(qx, z), __fadd_rn(qy, z), __fadd_rn(qz, eps)),
+                                   sdf_eval(prog, __fsub_rn(qx, z), __fsub_rn(qy, z), __fsub_rn(qz, eps)));
+        float *o = out + 6 * v;
+        o[0] = px; o[1] = py; o[2] = pz;
+        o[3] = __fdiv_rn(vx, two_eps); o[4] = __fdiv_rn(vy, two_eps); o[5] = __fdiv_rn(vz, two_eps);
+    }
+}
+
+/* inner = program without the translations that enclose all of it (applied to the vertex first, outermost first) */
+cudaError_t isomc_launch_normals_cd(const SdfProgram &inner, const float (*offsets)[3], uint32_t n_offsets, float eps,
+                                    const float *xyz, uint64_t n_vertices, float *out, int sms, cudaStream_t st) {
+    NormalOffsets tr;
+    tr.n = n_offsets;
+    for (uint32_t k = 0; k < ISOMC_TR_DEPTH; ++k)
+        for (int j = 0; j < 3; ++j) tr.off[k][j] = k < n_offsets ? offsets[k][j] : 0.0f;
+    k_normals_cd<<<sms * 4, 256, 0, st>>>(inner, tr, eps, xyz, n_vertices, out);
+    return cudaGetLastError();
+}

@@ -49,6 +49,30 @@ class OnlyVertices(Extractor):
         self.vertices.extend(xyz.tolist() if isinstance(self.vertices, list) else xyz)
 
 
+class IndexedInterleavedNormals(Extractor):
+    """reference src/extractor.rs:95-127: x y z nx ny nz per vertex, normals sampled from `source` (a HermiteSource).
+    On the B200 path `source` must be (a Sampler / Translate around) a CentralDifference of an implicit tree; its
+    normals are evaluated on the device at the extracted vertices (isomc_copy_out_interleaved_normals)."""
+
+    def __init__(self, vertices, indices, source):
+        from .source import find_central_difference
+        self.vertices, self.indices, self.source = vertices, indices, source
+        self.central_difference = find_central_difference(source)
+        if self.central_difference is None:
+            raise TypeError("IndexedInterleavedNormals needs a CentralDifference source on the device path "
+                            "(analytic sample_normal implementations are host code in the reference and not a device path)")
+
+    def extract_vertex(self, v):
+        raise TypeError("IndexedInterleavedNormals is filled in bulk by MarchingCubes.extract")
+
+    def extract_index(self, index):
+        self.indices.append(index & 0xFFFFFFFF)
+
+    def _bulk_normals(self, xyzn, idx):
+        self.vertices.extend(xyzn.tolist() if isinstance(self.vertices, list) else xyzn)
+        self.indices.extend(idx.tolist() if isinstance(self.indices, list) else idx)
+
+
 class ArrayMesh(Extractor):
     """Convenience sink holding the mesh as NumPy arrays (`vertices` (V,3) f32, `indices` (T,3) u32)."""
 

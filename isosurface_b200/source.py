@@ -146,6 +146,31 @@ def _infer_size(shape, numel):
     raise ValueError("cannot infer the lattice size from %d samples; pass size=" % numel)
 
 
+class CentralDifference(DeviceSource):
+    """reference src/source.rs:52-94: adds `sample_normal` by central differences (epsilon 1e-6 by default) to a
+    ScalarSource.  As a scalar source it is transparent; as the source of an IndexedInterleavedNormals extractor its
+    normals are evaluated on the device."""
+
+    def __init__(self, source, epsilon=0.000001):
+        _require_device_source(source)
+        self.source, self.epsilon = source, float(epsilon)
+
+    def encode(self, prog):
+        self.source.encode(prog)
+
+
+def find_central_difference(source):
+    """the CentralDifference adaptor of a source, looking through Sampler and enclosing Translate wrappers"""
+    s = source
+    while True:
+        if isinstance(s, CentralDifference):
+            return s
+        if isinstance(s, (Sampler, Translate)):
+            s = s.source
+            continue
+        return None
+
+
 class Sampler:
     """reference src/sampler.rs:26-41: wraps a source for `MarchingCubes.extract`"""
 

@@ -599,3 +599,31 @@ int oracle_point_cloud_grid(uint32_t size, const float *grid, uint32_t z_cells, 
     source_t s = {NULL, 0, grid, size, 0};
     return point_cloud_impl(&s, z_cells, out);
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* IndexedInterleavedNormals (reference src/extractor.rs:113-122) over a                 */
+/* CentralDifference source (src/source.rs:82-94), optionally inside DemoSource-style    */
+/* translations (examples/common/sources.rs:55-60: q = p - Vec3::from_scalar(0.5)).      */
+/* For each vertex v: out = [v.x v.y v.z n.x n.y n.z].                                    */
+/* ------------------------------------------------------------------------------------ */
+int oracle_interleaved_normals_cd(const osdf_node *inner, uint32_t n, float epsilon, const float *offsets, uint32_t n_offsets,
+                                  const float *xyz, uint64_t n_vertices, float *out) {
+    int err = 0;
+    for (uint64_t i = 0; i < n_vertices; ++i) {
+        v3 p = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, q = p;
+        for (uint32_t k = 0; k < n_offsets; ++k) {
+            q.x = q.x - offsets[3 * k]; q.y = q.y - offsets[3 * k + 1]; q.z = q.z - offsets[3 * k + 2];
+        }
+        const v3 d[3] = {{epsilon, 0.0f, 0.0f}, {0.0f, epsilon, 0.0f}, {0.0f, 0.0f, epsilon}};
+        float nn[3];
+        for (int a = 0; a < 3; ++a) {
+            v3 plus = {q.x + d[a].x, q.y + d[a].y, q.z + d[a].z}, minus = {q.x - d[a].x, q.y - d[a].y, q.z - d[a].z};
+            nn[a] = sdf_eval(inner, n, plus, &err) - sdf_eval(inner, n, minus, &err);
+        }
+        const float two_eps = 2.0f * epsilon;
+        float *o = out + 6 * i;
+        o[0] = p.x; o[1] = p.y; o[2] = p.z;
+        o[3] = nn[0] / two_eps; o[4] = nn[1] / two_eps; o[5] = nn[2] / two_eps;
+    }
+    return err ? -2 : 0;
+}

@@ -46,6 +46,8 @@ def lib():
         _LIB.oracle_sample_sdf.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         _LIB.oracle_tables.argtypes = [C.c_void_p] * 4
         _LIB.oracle_mesh_free.argtypes = [C.POINTER(_Mesh)]
+        _LIB.oracle_interleaved_normals_cd.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                       C.c_uint64, C.c_void_p]
         _LIB.oracle_point_cloud_sdf.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
         _LIB.oracle_point_cloud_grid.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
     return _LIB
@@ -87,6 +89,20 @@ def extract_grid(size, grid, z_cells=None, mode=LEAN):
     if rc:
         raise RuntimeError("oracle_extract_grid rc=%d" % rc)
     return _take(m)
+
+
+def interleaved_normals_cd(inner_prog, xyz, epsilon=0.000001, offsets=()):
+    """IndexedInterleavedNormals over CentralDifference(inner_prog) (reference src/extractor.rs:113-122, src/source.rs:82-94),
+    the vertex first moved by `offsets` (q = p - o, outermost first) as DemoSource does: (V, 6) floats"""
+    inner_prog = np.ascontiguousarray(inner_prog)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    off = np.ascontiguousarray(np.asarray(offsets, np.float32).reshape(-1, 3))
+    out = np.zeros((len(xyz), 6), np.float32)
+    rc = lib().oracle_interleaved_normals_cd(inner_prog.ctypes.data, len(inner_prog), epsilon, off.ctypes.data, len(off),
+                                             xyz.ctypes.data, len(xyz), out.ctypes.data)
+    if rc:
+        raise RuntimeError("oracle_interleaved_normals_cd rc=%d" % rc)
+    return out
 
 
 def point_cloud_sdf(size, prog):

@@ -482,3 +482,34 @@ def test_point_cloud_matches_oracle(iso, oracle):
     assert pc.copy_out()[0].tobytes() == want.tobytes()
     pc.close()
     assert iso.PointCloud(1).extract_device(iso.Sampler(iso_source("sphere03")))[0] == 0
+
+
+def test_interleaved_normals_match_oracle(iso, oracle):
+    """IndexedInterleavedNormals + CentralDifference (examples/sampler.rs:79-103): positions and central-difference
+    normals, evaluated on the device, bit-identical to the restated reference"""
+    O = oracle
+    cases = {
+        "csgA": (iso.Union(iso.Difference(iso.Sphere(.25), iso.RectangularPrism((.2, .2, .2))), iso.Cylinder(.02, .25)),
+                 [(O.SPHERE, .25), (O.PRISM, .2, .2, .2), (O.DIFFERENCE,), (O.CYLINDER, .02, .25), (O.UNION,)]),
+        "csgB": (iso.Intersection(iso.Sphere(.3), iso.RectangularPrism((.2, .2, .2))),
+                 [(O.SPHERE, .3), (O.PRISM, .2, .2, .2), (O.INTERSECTION,)]),
+        "torus": (iso.Torus(.25, .1), [(O.TORUS, .25, .1)]),
+    }
+    for name, (tree, nodes) in cases.items():
+        for eps in (0.000001, 0.001):
+            size = 64
+            src = iso.Translate(.5, iso.CentralDifference(tree, eps))          # DemoSource(CentralDifference(tree))
+            sampler = iso.Sampler(src)
+            verts, inds = [], []
+            mc = iso.MarchingCubes(size)
+            mc.extract(sampler, iso.IndexedInterleavedNormals(verts, inds, sampler))
+            mc.close()
+            oxyz, oidx, _ = O.extract_sdf(size, oracle_prog(name))
+            want = O.interleaved_normals_cd(O.program(nodes), oxyz, eps, [(.5, .5, .5)])
+            got = np.asarray(verts, np.float32).reshape(-1, 6)
+            assert np.asarray(inds, np.uint32).tobytes() == oidx.tobytes()
+            assert got[:, :3].tobytes() == oxyz.tobytes()
+            same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+            assert same.all(), "%s eps=%g: %d normal components differ" % (name, eps, int((~same).sum()))
+    with pytest.raises(TypeError):
+        iso.IndexedInterleavedNormals([], [], iso.Sampler(iso.Sphere(.3)))     # no CentralDifference: not a device path

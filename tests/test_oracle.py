@@ -152,3 +152,18 @@ def test_point_cloud_oracle_properties(oracle):
         want = np.stack([half * (c.astype(np.float32) * inv) + half * ((c + 1).astype(np.float32) * inv) for c in (x, y, z)], axis=1)
         assert want.astype(np.float32).tobytes() == pts.tobytes()
     assert oracle.point_cloud_sdf(1, oracle_prog("sphere03")).size == 0
+
+
+def test_central_difference_normals_oracle(oracle):
+    """IndexedInterleavedNormals over CentralDifference (reference src/extractor.rs:113-122, src/source.rs:82-94):
+    float64 central differences agree to the precision f32 differences at epsilon = 1e-6 allow; layout x y z nx ny nz"""
+    inner = oracle.program([(oracle.SPHERE, .3)])
+    xyz, _, _ = oracle.extract_sdf(24, oracle.program([(oracle.TRANSLATE_PUSH, .5, .5, .5), (oracle.SPHERE, .3), (oracle.TRANSLATE_POP,)]))
+    out = oracle.interleaved_normals_cd(inner, xyz, 0.000001, [(.5, .5, .5)])
+    assert out.shape == (len(xyz) // 3, 6) and out[:, :3].tobytes() == xyz.tobytes()
+    q = xyz.reshape(-1, 3).astype(np.float64) - 0.5
+    want = q / np.linalg.norm(q, axis=1, keepdims=True)          # gradient of |q| - r
+    assert np.abs(out[:, 3:] - want).max() < 0.05                # f32 differences over 2e-6: a few ulps of 0.3 / 2e-6
+    # a larger epsilon is accurate
+    out2 = oracle.interleaved_normals_cd(inner, xyz, 0.001, [(.5, .5, .5)])
+    assert np.abs(out2[:, 3:] - want).max() < 1e-3
