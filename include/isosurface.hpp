@@ -10,9 +10,12 @@
 //   examples/common/sources.rs DemoSource (p - 0.5)           isosurface::Translate(dx,dy,dz, child)
 //   extractor::IndexedVertices::new(&mut v, &mut i)           isosurface::IndexedVertices sink(v, i);
 //   trait Extractor { extract_vertex; extract_index }         struct Extractor (virtual), replayed in protocol order
+//   PointCloud::<Signed>::new(size).extract(..)               isosurface::PointCloud pc(size); pc.extract(source, extractor);
+//   source::CentralDifference::new(source)                    isosurface::CentralDifference(source [, epsilon])
+//   extractor::IndexedInterleavedNormals::new(&mut v,&mut i,&s)   isosurface::IndexedInterleavedNormals sink(v, i, source);
 //
 // Reference files: src/marching_cubes.rs:38-82, src/sampler.rs:26-41, src/source.rs:21-28,
-// src/extractor.rs:17-93, src/implicit/*.rs.  Sources are *encoded* for the device (DeviceSource);
+// src/extractor.rs:17-127, src/point_cloud.rs:33-63, src/source.rs:52-94, src/implicit/*.rs.  Sources are *encoded* for the device (DeviceSource);
 // an arbitrary callable is not a device path and does not compile against this API (no CPU fallback).
 #ifndef ISOSURFACE_HPP
 #define ISOSURFACE_HPP
@@ -63,6 +66,23 @@ struct TranslateT {  // q = p - (dx,dy,dz), examples/common/sources.rs:38-43
 };
 template <class S> TranslateT<S> Translate(float dx, float dy, float dz, S child) { return {dx, dy, dz, child}; }
 
+// source.rs:52-94: a ScalarSource with central-difference normals; transparent as a scalar source
+template <class S>
+struct CentralDifferenceT {
+    S source; float epsilon;
+    void encode(SdfProgram &p) const { source.encode(p); }
+};
+template <class S> CentralDifferenceT<S> CentralDifference(S source, float epsilon = 0.000001f) { return {source, epsilon}; }
+template <class S> struct has_central_difference { static constexpr bool value = false; static float epsilon(const S &) { return 0; } };
+template <class S> struct has_central_difference<CentralDifferenceT<S>> {
+    static constexpr bool value = true;
+    static float epsilon(const CentralDifferenceT<S> &s) { return s.epsilon; }
+};
+template <class S> struct has_central_difference<TranslateT<S>> {
+    static constexpr bool value = has_central_difference<S>::value;
+    static float epsilon(const TranslateT<S> &s) { return has_central_difference<S>::epsilon(s.child); }
+};
+
 // Dense lattice source (new): N*N*(N+1) f32, x fastest; host or device memory.
 struct DenseGrid { const float *data; uint32_t size; bool on_device; };
 
@@ -89,6 +109,18 @@ struct OnlyVertices : Extractor {  // extractor.rs:24-43
     void extract_index(size_t) override {}
 };
 
+// extractor.rs:95-127: x y z nx ny nz per vertex; the normals of a CentralDifference source are sampled on the device
+struct InterleavedNormalsSink {
+    std::vector<float> &vertices; std::vector<uint32_t> &indices; SdfProgram program; float epsilon;
+};
+template <class S>
+InterleavedNormalsSink IndexedInterleavedNormals(std::vector<float> &v, std::vector<uint32_t> &i, const S &source) {
+    static_assert(has_central_difference<S>::value, "IndexedInterleavedNormals needs a CentralDifference source on the device path");
+    InterleavedNormalsSink sink{v, i, {}, has_central_difference<S>::epsilon(source)};
+    source.encode(sink.program);
+    return sink;
+}
+
 // ---- MarchingCubes (reference src/marching_cubes.rs:38-82) ------------------------------------
 class MarchingCubes {
   public:
@@ -109,12 +141,45 @@ class MarchingCubes {
     }
     void extract(const DenseGrid &grid, Extractor &extractor) {
         if (grid.size != size_) throw Error(ISOMC_ERR_BAD_ARG, "grid size does not match");
-        check(grid.on_device ? isomc_extract_grid_device(h_, grid.data) : isomc_extract_grid_host(h_, grid.data));
+        if (!grid.on_device) {
+            // host lattice -> host mesh in one pipelined call (copy-in, kernels and copy-out overlap), straight into the
+            // Vecs of an IndexedVertices whose capacity is kept from the previous extract
+            if (auto *iv = dynamic_cast<IndexedVertices *>(&extractor)) {
+                const size_t v0 = iv->vertices.size(), i0 = iv->indices.size();
+                iv->vertices.resize(v0 + 3 * (last_v_ + last_v_ / 8 + 1024));
+                iv->indices.resize(i0 + 3 * (last_t_ + last_t_ / 8 + 1024));
+                int32_t rc = isomc_extract_grid_host_to(h_, grid.data, iv->vertices.data() + v0, (iv->vertices.size() - v0) / 3,
+                                                        iv->indices.data() + i0, (iv->indices.size() - i0) / 3);
+                if (rc && rc != ISOMC_ERR_BUFFER_TOO_SMALL) check(rc);
+                check(isomc_counts(h_, &last_v_, &last_t_, nullptr));
+                iv->vertices.resize(v0 + 3 * last_v_);
+                iv->indices.resize(i0 + 3 * last_t_);
+                if (rc == ISOMC_ERR_BUFFER_TOO_SMALL) check(isomc_copy_out(h_, iv->vertices.data() + v0, iv->indices.data() + i0));
+                return;
+            }
+            check(isomc_extract_grid_host(h_, grid.data));
+        } else {
+            check(isomc_extract_grid_device(h_, grid.data));
+        }
         deliver(extractor);
     }
+    // IndexedInterleavedNormals: extract, then positions + central-difference normals from the device
+    template <class S> void extract(const S &source, InterleavedNormalsSink &sink) {
+        SdfProgram prog;
+        source.encode(prog);
+        check(isomc_extract_sdf(h_, prog.data(), (uint32_t)prog.size()));
+        uint64_t nv = 0, nt = 0;
+        check(isomc_counts(h_, &nv, &nt, nullptr));
+        const size_t v0 = sink.vertices.size(), i0 = sink.indices.size();
+        sink.vertices.resize(v0 + 6 * nv);
+        sink.indices.resize(i0 + 3 * nt);
+        check(isomc_copy_out_interleaved_normals(h_, sink.program.data(), (uint32_t)sink.program.size(), sink.epsilon,
+                                                 sink.vertices.data() + v0, sink.indices.data() + i0));
+    }
+    template <class S> void extract(const SamplerT<S> &sampler, InterleavedNormalsSink &sink) { extract(sampler.source, sink); }
     isomc_t *handle() { return h_; }
 
-  private:
+  protected:
     void check(int32_t rc) { if (rc) throw Error(rc, isomc_last_error(h_)); }
     void deliver(Extractor &ex) {
         uint64_t nv = 0, nt = 0;
@@ -134,6 +199,24 @@ class MarchingCubes {
     }
     isomc_t *h_ = nullptr;
     uint32_t size_;
+    uint64_t last_v_ = 0, last_t_ = 0;
+};
+
+// ---- PointCloud (reference src/point_cloud.rs:33-63): one vertex per active cell, no face data ---------------
+class PointCloud : public MarchingCubes {
+  public:
+    explicit PointCloud(uint32_t size, int32_t device = 0) : MarchingCubes(size, device) {}
+    template <class S> void extract(const SamplerT<S> &sampler, Extractor &extractor) { extract(sampler.source, extractor); }
+    template <class S> void extract(const S &source, Extractor &extractor) {
+        SdfProgram prog;
+        source.encode(prog);
+        check(isomc_points_sdf(h_, prog.data(), (uint32_t)prog.size()));
+        deliver(extractor);
+    }
+    void extract(const DenseGrid &grid, Extractor &extractor) {
+        check(grid.on_device ? isomc_points_grid_device(h_, grid.data) : isomc_points_grid_host(h_, grid.data));
+        deliver(extractor);
+    }
 };
 
 }  // namespace isosurface

@@ -22,9 +22,16 @@ extern "C" {
     fn isomc_extract_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
     fn isomc_extract_grid_host(h: *mut isomc_t, grid: *const f32) -> i32;
     fn isomc_extract_grid_device(h: *mut isomc_t, d_grid: *const f32) -> i32;
+    fn isomc_extract_grid_host_to(h: *mut isomc_t, grid: *const f32, xyz: *mut f32, cap_vertices: u64, idx: *mut u32,
+                                  cap_triangles: u64) -> i32;
+    fn isomc_points_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
+    fn isomc_points_grid_host(h: *mut isomc_t, grid: *const f32) -> i32;
     fn isomc_counts(h: *mut isomc_t, nv: *mut u64, nt: *mut u64, na: *mut u64) -> i32;
     fn isomc_copy_out(h: *mut isomc_t, xyz: *mut f32, idx: *mut u32) -> i32;
+    fn isomc_copy_out_interleaved_normals(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32, epsilon: f32,
+                                          xyzn: *mut f32, idx: *mut u32) -> i32;
 }
+const ERR_BUFFER_TOO_SMALL: i32 = -8;
 
 const SPHERE: u32 = 1; const TORUS: u32 = 2; const CYLINDER: u32 = 3; const PRISM: u32 = 4;
 const UNION: u32 = 16; const INTERSECTION: u32 = 17; const DIFFERENCE: u32 = 18;
@@ -69,6 +76,16 @@ impl<S: DeviceSource> DeviceSource for Translate<S> {
         p.push(node(TRANSLATE_POP, 0.0, 0.0, 0.0));
     }
 }
+/// reference src/source.rs:52-94: central-difference normals around a scalar source (transparent as a scalar source)
+pub struct CentralDifference<S> { pub source: S, pub epsilon: f32 }
+impl<S> CentralDifference<S> { pub fn new(source: S) -> Self { Self { source, epsilon: 0.000001 } } }
+impl<S: DeviceSource> DeviceSource for CentralDifference<S> { fn encode(&self, p: &mut Vec<isomc_sdf_node>) { self.source.encode(p) } }
+/// Sources whose `sample_normal` the device can evaluate: a CentralDifference, possibly inside Translate / Sampler.
+pub trait DeviceNormals: DeviceSource { fn epsilon(&self) -> f32; }
+impl<S: DeviceSource> DeviceNormals for CentralDifference<S> { fn epsilon(&self) -> f32 { self.epsilon } }
+impl<S: DeviceNormals> DeviceNormals for Translate<S> { fn epsilon(&self) -> f32 { self.source.epsilon() } }
+impl<'a, S: DeviceNormals> DeviceNormals for Sampler<'a, S> { fn epsilon(&self) -> f32 { self.source.epsilon() } }
+
 impl<'a, S: DeviceSource> DeviceSource for Sampler<'a, S> { fn encode(&self, p: &mut Vec<isomc_sdf_node>) { self.source.encode(p) } }
 
 /// reference src/extractor.rs:17-20
@@ -80,6 +97,13 @@ impl<'a> IndexedVertices<'a> { pub fn new(vertices: &'a mut Vec<f32>, indices: &
 impl<'a> Extractor for IndexedVertices<'a> {
     fn extract_vertex(&mut self, v: [f32; 3]) { self.vertices.extend_from_slice(&v) }
     fn extract_index(&mut self, index: usize) { self.indices.push(index as u32) }
+}
+
+/// reference src/extractor.rs:95-127: x y z nx ny nz per vertex.  On this path the normals of `source` are sampled on the
+/// device in one call after the extract instead of one `sample_normal` callback per vertex.
+pub struct IndexedInterleavedNormals<'a, S: DeviceNormals> { vertices: &'a mut Vec<f32>, indices: &'a mut Vec<u32>, source: &'a S }
+impl<'a, S: DeviceNormals> IndexedInterleavedNormals<'a, S> {
+    pub fn new(vertices: &'a mut Vec<f32>, indices: &'a mut Vec<u32>, source: &'a S) -> Self { Self { vertices, indices, source } }
 }
 
 pub struct MarchingCubes { h: *mut isomc_t, size: usize }
@@ -109,6 +133,42 @@ impl MarchingCubes {
         self.deliver(extractor);
     }
 
+    /// Host lattice in, `IndexedVertices` out in one pipelined call: copy-in, kernels and copy-out overlap in z-chunks.
+    /// The Vecs are grown to the capacity the previous extract needed; if this mesh is larger the result is fetched
+    /// with `isomc_copy_out` after growing (the extraction itself is not repeated).
+    pub fn extract_grid_into(&mut self, grid: &DenseGrid, sink: &mut IndexedVertices) {
+        let (v0, i0) = (sink.vertices.len(), sink.indices.len());
+        let (cv, ct) = ((sink.vertices.capacity() - v0) / 3, (sink.indices.capacity() - i0) / 3);
+        sink.vertices.resize(v0 + 3 * cv, 0.0);
+        sink.indices.resize(i0 + 3 * ct, 0);
+        let rc = unsafe { isomc_extract_grid_host_to(self.h, grid.data.as_ptr(), sink.vertices.as_mut_ptr().add(v0), cv as u64,
+                                                      sink.indices.as_mut_ptr().add(i0), ct as u64) };
+        if rc != ERR_BUFFER_TOO_SMALL { self.check(rc); }
+        let (mut nv, mut nt) = (0u64, 0u64);
+        self.check(unsafe { isomc_counts(self.h, &mut nv, &mut nt, std::ptr::null_mut()) });
+        sink.vertices.resize(v0 + 3 * nv as usize, 0.0);
+        sink.indices.resize(i0 + 3 * nt as usize, 0);
+        if rc == ERR_BUFFER_TOO_SMALL {
+            self.check(unsafe { isomc_copy_out(self.h, sink.vertices.as_mut_ptr().add(v0), sink.indices.as_mut_ptr().add(i0)) });
+        }
+    }
+
+    /// `extract(&sampler, &mut IndexedInterleavedNormals::new(&mut v, &mut i, &sampler))` (examples/sampler.rs:99-108)
+    pub fn extract_with_normals<S: DeviceNormals>(&mut self, source: &S, sink: &mut IndexedInterleavedNormals<S>) {
+        let mut prog = Vec::new();
+        source.encode(&mut prog);
+        self.check(unsafe { isomc_extract_sdf(self.h, prog.as_ptr(), prog.len() as u32) });
+        let (mut nv, mut nt) = (0u64, 0u64);
+        self.check(unsafe { isomc_counts(self.h, &mut nv, &mut nt, std::ptr::null_mut()) });
+        let (v0, i0) = (sink.vertices.len(), sink.indices.len());
+        sink.vertices.resize(v0 + 6 * nv as usize, 0.0);
+        sink.indices.resize(i0 + 3 * nt as usize, 0);
+        let mut nprog = Vec::new();
+        sink.source.encode(&mut nprog);
+        self.check(unsafe { isomc_copy_out_interleaved_normals(self.h, nprog.as_ptr(), nprog.len() as u32, sink.source.epsilon(),
+                                                               sink.vertices.as_mut_ptr().add(v0), sink.indices.as_mut_ptr().add(i0)) });
+    }
+
     /// # Safety: `d_grid` must be a device pointer to N*N*(N+1) f32 on the handle's device.
     pub unsafe fn extract_grid_device<E: Extractor>(&mut self, d_grid: *const f32, extractor: &mut E) {
         self.check(isomc_extract_grid_device(self.h, d_grid));
@@ -132,3 +192,20 @@ impl MarchingCubes {
 }
 
 impl Drop for MarchingCubes { fn drop(&mut self) { unsafe { isomc_destroy(self.h); } } }
+
+/// reference src/point_cloud.rs:33-63: one vertex per active cell (midpoint of corners 0 and 6), no face data
+pub struct PointCloud { mc: MarchingCubes }
+impl PointCloud {
+    pub fn new(size: usize) -> Self { Self { mc: MarchingCubes::new(size) } }
+    pub fn extract<S: DeviceSource, E: Extractor>(&mut self, source: &S, extractor: &mut E) {
+        let mut prog = Vec::new();
+        source.encode(&mut prog);
+        self.mc.check(unsafe { isomc_points_sdf(self.mc.h, prog.as_ptr(), prog.len() as u32) });
+        self.mc.deliver(extractor);
+    }
+    pub fn extract_grid<E: Extractor>(&mut self, grid: &DenseGrid, extractor: &mut E) {
+        assert_eq!(grid.size, self.mc.size);
+        self.mc.check(unsafe { isomc_points_grid_host(self.mc.h, grid.data.as_ptr()) });
+        self.mc.deliver(extractor);
+    }
+}

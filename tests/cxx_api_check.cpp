@@ -18,6 +18,33 @@ int main() {
         std::printf("%s\n", e.what());
         return e.code == ISOMC_ERR_CUDA ? 0 : 1;  // no device: loud failure is the expected behaviour
     }
+    // the other extractors of the crate behind the same handle type: PointCloud, IndexedInterleavedNormals, host DenseGrid
+    try {
+        std::vector<float> pts, vn, hv;
+        std::vector<uint32_t> ni, hi;
+        auto src = Translate(0.5f, 0.5f, 0.5f, CentralDifference(Intersection(Sphere{0.3f}, RectangularPrism{0.2f, 0.2f, 0.2f})));
+        PointCloud pc(64);
+        OnlyVertices only(pts);
+        pc.extract(Sampler(src), only);
+        MarchingCubes mc(64);
+        auto sink = IndexedInterleavedNormals(vn, ni, src);
+        mc.extract(Sampler(src), sink);
+        if (pts.size() / 3 != 4058 || vn.size() / 6 != 4056 || ni.size() / 3 != 8108) { // csgB @0.5, N=64
+            std::printf("unexpected counts: points %zu, vertices %zu, triangles %zu\n", pts.size() / 3, vn.size() / 6, ni.size() / 3);
+            return 1;
+        }
+        std::vector<float> grid((size_t)64 * 64 * 65);
+        for (size_t i = 0; i < grid.size(); ++i) grid[i] = (float)((i * 2654435761u >> 7) % 1000) - 500.0f;
+        IndexedVertices hsink(hv, hi);
+        for (int rep = 0; rep < 2; ++rep) { // second call takes the streamed host-to-host path
+            hv.clear(); hi.clear();
+            mc.extract(DenseGrid{grid.data(), 64, false}, hsink);
+        }
+        if (hv.empty() || hi.empty()) { std::printf("host grid extract produced nothing\n"); return 1; }
+    } catch (const Error &e) {
+        std::printf("%s\n", e.what());
+        return 1;
+    }
     std::printf("V=%zu T=%zu\n", vertices.size() / 3, indices.size() / 3);
     return 0;
 }
