@@ -408,7 +408,7 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
     if (const char *p = getenv("ISOMC_PIPELINE")) h->pipeline = atoi(p) != 0;
     Geo &g = h->g;
     g.N = size; g.ncx = size - 1;
-    g.nsegx = (g.ncx + 31) / 32; g.nws = g.nsegx + 1;
+    g.nsegx = (g.ncx + 31) / 32; g.nws = (g.nsegx + 2) & ~1u; /* >= nsegx + 1, even: word 2j of a row is 8-byte aligned */
     g.ghost = z_begin > 0 ? 1u : 0u;
     g.gz0 = z_begin - g.ghost;
     g.ncl = (g.ncx == 0) ? 0 : (z_end - z_begin + g.ghost);

@@ -571,7 +571,7 @@ struct CountOut {
  *            cube index, triangles -> list entries; then back to lane per segment: the same scan for the triangles ->
  *            segment records, row totals.
  */
-constexpr uint32_t SEGQ_CAP = 64;
+constexpr uint32_t SEGQ_CAP = 128; /* up to 31 waiting + 64 from one pass */
 constexpr uint32_t SEGQ_FIRST = 1u << 16, SEGQ_LAST = 1u << 17; /* meta = s | flags: first / last queued segment of its row */
 
 struct SegQueue {             /* one per warp, shared memory */
@@ -716,29 +716,52 @@ ISOMC_HD bool seg_uniform(const uint32_t wd[8]) { /* all 4 x 33 samples on one s
     return (all_or == 0u) || (all_and == 0xFFFFFFFFu && (wd[1] & wd[3] & wd[5] & wd[7] & 1u));
 }
 
-ISOMC_HD void load_words(const Geo &g, const uint32_t *signs, uint32_t row, uint32_t lz, uint32_t s, uint32_t wd[8]) {
-    const uint32_t *r00 = signs + (uint64_t)(row + lz) * g.nws + s; /* sample row lz*N + y = row + lz */
-    const uint32_t *r01 = r00 + g.nws, *r10 = r00 + (uint64_t)g.N * g.nws, *r11 = r10 + g.nws;
-    wd[0] = hd_ldg(r00); wd[1] = hd_ldg(r00 + 1); wd[2] = hd_ldg(r01); wd[3] = hd_ldg(r01 + 1);
-    wd[4] = hd_ldg(r10); wd[5] = hd_ldg(r10 + 1); wd[6] = hd_ldg(r11); wd[7] = hd_ldg(r11 + 1);
+/* the sign words of segments 2j and 2j + 1 of a cell row: one 8-byte and one 4-byte load per sample row (nws is even, so
+ * word 2j of every row is 8-byte aligned); wa = words of segment 2j, wb = of segment 2j + 1 (valid_b: it exists) */
+ISOMC_HD void load_pair(const Geo &g, const uint32_t *signs, uint32_t row, uint32_t lz, uint32_t j, bool valid_b, uint32_t wa[8],
+                        uint32_t wb[8]) {
+    const uint32_t *r = signs + (uint64_t)(row + lz) * g.nws + 2 * j; /* sample row lz*N + y = row + lz */
+    const uint64_t dz = (uint64_t)g.N * g.nws;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t *q = r + (k & 1 ? g.nws : 0u) + (k & 2 ? dz : 0u);
+#if defined(__CUDA_ARCH__)
+        const uint2 p = __ldg(reinterpret_cast<const uint2 *>(q));
+#else
+        const uint2 p = *reinterpret_cast<const uint2 *>(q);
+#endif
+        const uint32_t third = valid_b ? hd_ldg(q + 2) : 0u;
+        wa[2 * k] = p.x; wa[2 * k + 1] = p.y;
+        wb[2 * k] = p.y; wb[2 * k + 1] = third;
+    }
 }
 
-/* queue the lanes with `keep` (segments of one pass, lane order = (row, x) order) */
-ISOMC_HD void seg_enqueue(const Warp &w, SegQueue &Q, CountState &S, uint32_t mask, bool keep, const uint32_t wd[8], uint32_t row,
-                          uint32_t meta) {
-    if (keep) {
-        const uint32_t slot = (S.enq + hd_popc(mask & ((1u << w.lane) - 1u))) & (SEGQ_CAP - 1);
+/* queue the segments a pass keeps: lane order, and within a lane segment a before segment b */
+ISOMC_HD void pair_enqueue(const Warp &w, SegQueue &Q, CountState &S, uint32_t mask_a, uint32_t mask_b, bool keep_a, bool keep_b,
+                           const uint32_t wa[8], const uint32_t wb[8], uint32_t row, uint32_t meta_a, uint32_t meta_b) {
+    const uint32_t below = (1u << w.lane) - 1u;
+    const uint32_t pos = S.enq + hd_popc(mask_a & below) + hd_popc(mask_b & below);
+    if (keep_a) {
+        const uint32_t slot = pos & (SEGQ_CAP - 1);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) Q.w[j][slot] = wd[j];
+        for (int k = 0; k < 8; ++k) Q.w[k][slot] = wa[k];
         Q.row[slot] = row;
-        Q.meta[slot] = meta;
+        Q.meta[slot] = meta_a;
     }
-    S.enq += hd_popc(mask);
+    if (keep_b) {
+        const uint32_t slot = (pos + (keep_a ? 1u : 0u)) & (SEGQ_CAP - 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) Q.w[k][slot] = wb[k];
+        Q.row[slot] = row;
+        Q.meta[slot] = meta_b;
+    }
+    S.enq += hd_popc(mask_a) + hd_popc(mask_b);
     w_sync(w);
 }
 
-/* One warp's share of cell rows [row0, row1): warp gwarp of nwarps.  WIDE = rows of more than 32 segments (a pass is a
- * 32-segment chunk of one row); else a pass covers 32 >> gshift whole rows of 1 << gshift segments. */
+/* One warp's share of cell rows [row0, row1): warp gwarp of nwarps.  Every lane scans TWO neighbouring segments.
+ * WIDE = rows of more than 64 segments (a pass is a 64-segment chunk of one row); else a pass covers 32 >> gshift whole
+ * rows of 1 << gshift lanes (segment pairs) each. */
 template <bool WIDE>
 ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs, const uint8_t *s_ntri, const uint8_t *nth8,
                               const ListBufs &L, const CountOut &out, uint32_t gshift, uint32_t row0, uint32_t row1, uint32_t gwarp,
@@ -749,51 +772,54 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
     S.cur.pos = S.cur.end = S.cur.b0 = S.cur.m = 0;
     S.p_va = S.p_t = 0;
     if (!WIDE) {
-        const uint32_t G = 1u << gshift, rpw = 32u >> gshift, sub = lane >> gshift, s = lane & (G - 1);
+        const uint32_t G = 1u << gshift, rpw = 32u >> gshift, sub = lane >> gshift, j = lane & (G - 1);
         const uint32_t gmask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << (sub << gshift);
         const uint32_t niter = (row1 - row0 + rpw - 1) / rpw;
         for (uint32_t it = gwarp; it < niter; it += nwarps) {
             const uint32_t row = row0 + it * rpw + sub;
-            const bool valid = row < row1 && s < g.nsegx;
-            uint32_t wd[8];
-            bool keep = false;
-            if (valid) {
+            const bool va = row < row1 && 2 * j < g.nsegx, vb = row < row1 && 2 * j + 1 < g.nsegx;
+            uint32_t wa[8], wb[8];
+            bool ka = false, kb = false;
+            if (va) {
                 const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40);
-                load_words(g, signs, row, lz, s, wd);
-                keep = !seg_uniform(wd);
+                load_pair(g, signs, row, lz, j, vb, wa, wb);
+                ka = !seg_uniform(wa);
+                kb = vb && !seg_uniform(wb);
             }
-            const uint32_t mask = w_ballot(w, keep), rmask = mask & gmask;
-            if (s == 0 && row < row1 && rmask == 0) { out.rowV[row] = 0; out.rowT[row] = 0; out.rowA[row] = 0; }
-            if (mask == 0) continue;
-            uint32_t meta = s;
-            if (keep) {
-                if (hd_ffs0(rmask) == lane) meta |= SEGQ_FIRST;
-                if (31u - hd_clz(rmask) == lane) meta |= SEGQ_LAST;
+            const uint32_t ma = w_ballot(w, ka), mb = w_ballot(w, kb), rany = (ma | mb) & gmask;
+            if (j == 0 && row < row1 && rany == 0) { out.rowV[row] = 0; out.rowT[row] = 0; out.rowA[row] = 0; }
+            if ((ma | mb) == 0) continue;
+            uint32_t meta_a = 2 * j, meta_b = 2 * j + 1;
+            if (ka || kb) {
+                if (hd_ffs0(rany) == lane) { if (ka) meta_a |= SEGQ_FIRST; else meta_b |= SEGQ_FIRST; }
+                if (31u - hd_clz(rany) == lane) { if (kb) meta_b |= SEGQ_LAST; else meta_a |= SEGQ_LAST; }
             }
-            seg_enqueue(w, Q, S, mask, keep, wd, row, meta);
-            if (S.enq - S.deq >= 32) count_flush(w, g, s_ntri, nth8, L, out, Q, S, 32);
+            pair_enqueue(w, Q, S, ma, mb, ka, kb, wa, wb, row, meta_a, meta_b);
+            while (S.enq - S.deq >= 32) count_flush(w, g, s_ntri, nth8, L, out, Q, S, 32);
         }
     } else {
         for (uint32_t row = row0 + gwarp; row < row1; row += nwarps) {
             const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40);
             bool row_has = false;
             uint32_t last_seq = 0;
-            for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 32) {
-                const uint32_t s = s0 + lane;
-                uint32_t wd[8];
-                bool keep = false;
-                if (s < g.nsegx) {
-                    load_words(g, signs, row, lz, s, wd);
-                    keep = !seg_uniform(wd);
+            for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 64) {
+                const uint32_t j = (s0 >> 1) + lane;
+                const bool va = 2 * j < g.nsegx, vb = 2 * j + 1 < g.nsegx;
+                uint32_t wa[8], wb[8];
+                bool ka = false, kb = false;
+                if (va) {
+                    load_pair(g, signs, row, lz, j, vb, wa, wb);
+                    ka = !seg_uniform(wa);
+                    kb = vb && !seg_uniform(wb);
                 }
-                const uint32_t mask = w_ballot(w, keep);
-                if (mask == 0) continue;
-                uint32_t meta = s;
-                if (keep && !row_has && hd_ffs0(mask) == lane) meta |= SEGQ_FIRST;
-                seg_enqueue(w, Q, S, mask, keep, wd, row, meta);
+                const uint32_t ma = w_ballot(w, ka), mb = w_ballot(w, kb);
+                if ((ma | mb) == 0) continue;
+                uint32_t meta_a = 2 * j, meta_b = 2 * j + 1;
+                if (!row_has && (ka || kb) && hd_ffs0(ma | mb) == lane) { if (ka) meta_a |= SEGQ_FIRST; else meta_b |= SEGQ_FIRST; }
+                pair_enqueue(w, Q, S, ma, mb, ka, kb, wa, wb, row, meta_a, meta_b);
                 row_has = true;
                 last_seq = S.enq - 1;
-                if (S.enq - S.deq >= 32) count_flush(w, g, s_ntri, nth8, L, out, Q, S, 32);
+                while (S.enq - S.deq >= 32) count_flush(w, g, s_ntri, nth8, L, out, Q, S, 32);
             }
             /* end of the row: close it */
             if (!row_has) {

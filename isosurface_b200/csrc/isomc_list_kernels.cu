@@ -138,13 +138,14 @@ static void launch_count_list_v(uint32_t grid, cudaStream_t st, const Geo &g, co
 cudaError_t isomc_launch_count_list(const Geo &g, const uint32_t *signs, const McTables *tabs, const ListBufs &L, uint32_t *rowV,
                                     uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot, uint32_t lz0, uint32_t lz1,
                                     int sms, cudaStream_t st) {
+    const uint32_t npair = (g.nsegx + 1) / 2; /* lanes per row: every lane scans two neighbouring segments */
     uint32_t gshift = 0;
-    while ((1u << gshift) < g.nsegx && gshift < 5) ++gshift;
+    while ((1u << gshift) < npair && gshift < 5) ++gshift;
     const uint32_t row0 = lz0 * g.ncx, row1 = lz1 * g.ncx;
     const uint8_t *ntri = reinterpret_cast<const uint8_t *>(tabs) + offsetof(McTables, ntri);
     const CountOut out{rowV, rowT, rowA, layerTot};
     const int per_sm = count_list_minb();
-    if (g.nsegx <= 32) {
+    if (npair <= 32) {
         const uint32_t rpw = 32u >> gshift;
         const uint64_t warps = ((uint64_t)(row1 - row0) + rpw - 1) / rpw;
         launch_count_list_v<false>(grid_for(warps, sms, 8, per_sm), st, g, signs, ntri, L, out, gshift, row0, row1);

@@ -133,7 +133,7 @@ int list_model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const fl
                        uint64_t *out_totals) {
     Geo g;
     g.N = size; g.ncx = size - 1;
-    g.nsegx = (g.ncx + 31) / 32; g.nws = g.nsegx + 1;
+    g.nsegx = (g.ncx + 31) / 32; g.nws = (g.nsegx + 2) & ~1u;
     g.ghost = z_begin > 0 ? 1u : 0u;
     g.gz0 = z_begin - g.ghost;
     g.ncl = (g.ncx == 0) ? 0 : (z_end - z_begin + g.ghost);
@@ -168,8 +168,9 @@ int list_model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const fl
     std::vector<unsigned long long> layerTot((size_t)g.ncl * 3 + 4, 0ull);
     CountOut out{rowV.data(), rowT.data(), rowA.data(), layerTot.data()};
 
+    const uint32_t npair = (g.nsegx + 1) / 2; /* lanes per row: every lane scans two segments */
     uint32_t gshift = 0;
-    while ((1u << gshift) < g.nsegx && gshift < 5) ++gshift;
+    while ((1u << gshift) < npair && gshift < 5) ++gshift;
     std::vector<uint32_t> order(n_warps);
     for (uint32_t i = 0; i < n_warps; ++i) order[i] = i;
     uint64_t st = seed * 0x9E3779B97F4A7C15ull + 1;
@@ -182,7 +183,7 @@ int list_model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const fl
     static Emu E;
     for (uint32_t wi = 0; wi < n_warps; ++wi) {
         WarpJob J;
-        J.wide = g.nsegx > 32;
+        J.wide = npair > 32;
         J.g = g; J.signs = signs.data(); J.ntri = mt.ntri; J.nth8 = nth8.data(); J.L = L; J.out = out;
         J.gshift = gshift; J.row0 = 0; J.row1 = (uint32_t)nrows_c; J.gwarp = order[wi]; J.nwarps = n_warps;
         run_warp(E, J);
