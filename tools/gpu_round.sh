@@ -26,6 +26,7 @@ for v in "$@"; do
     list5) run list5 ISOMC_EMIT=list ISOMC_LIST_MINB=5;;
     list6) run list6 ISOMC_EMIT=list ISOMC_LIST_MINB=6;;
     brick) run brick ISOMC_EMIT=brick;;
+    pipe) run pipe ISOMC_EMIT=list ISOMC_PIPELINE=1;;
     emit4) run emit4 ISOMC_EMIT=list ISOMC_EMIT_MINB=4;;
     emit5) run emit5 ISOMC_EMIT=list ISOMC_EMIT_MINB=5;;
     emit6) run emit6 ISOMC_EMIT=list ISOMC_EMIT_MINB=6;;
