@@ -101,6 +101,11 @@ const char *isomc_version(void);
 /* ---- extract(&source, ...) --------------------------------------------------------------- */
 /* source = implicit tree (evaluated on device; no grid is materialised) */
 int32_t isomc_extract_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes);
+/* the same tree sampled as Directed distances: `MarchingCubes::<Directed>::new(size).extract(..)` (reference
+ * src/distance.rs:43-45,72-104; sample_vector of src/implicit/{sphere,torus,cylinder,rectangular_prism,csg}.rs): a lattice
+ * point is outside iff any of its three axis distances is positive, and each crossing is interpolated from the distance
+ * along its own edge's axis.  Same output contract as isomc_extract_sdf. */
+int32_t isomc_extract_sdf_directed(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes);
 /* source = dense lattice already resident on the handle's device: N*N*(N+1) f32 */
 int32_t isomc_extract_grid_device(isomc_t *h, const float *d_grid);
 /* source = dense lattice in host memory (H2D copy, then as above) */

@@ -4,6 +4,7 @@
 //   Rust (reference)                                          C++ (this header)
 //   ---------------------------------------------------------------------------------------------
 //   MarchingCubes::<Signed>::new(size)                        isosurface::MarchingCubes mc(size);
+//   MarchingCubes::<Directed>::new(size)                      isosurface::MarchingCubes mc(size, 0, isosurface::Distance::Directed);
 //   mc.extract(&Sampler::new(&source), &mut extractor)        mc.extract(isosurface::Sampler(source), extractor);
 //   implicit::{Sphere,Torus,Cylinder,RectangularPrism}        isosurface::Sphere{r}, Torus{R,r}, Cylinder{r,h}, RectangularPrism{hx,hy,hz}
 //   implicit::{Union,Intersection,Difference}                 isosurface::Union(a,b), Intersection(a,b), Difference(a,b)
@@ -122,9 +123,12 @@ InterleavedNormalsSink IndexedInterleavedNormals(std::vector<float> &v, std::vec
 }
 
 // ---- MarchingCubes (reference src/marching_cubes.rs:38-82) ------------------------------------
+// distance.rs:39-45: Signed = one scalar distance; Directed = a signed distance along each cardinal axis (implicit sources only)
+enum class Distance { Signed, Directed };
+
 class MarchingCubes {
   public:
-    explicit MarchingCubes(uint32_t size, int32_t device = 0) : size_(size) {
+    explicit MarchingCubes(uint32_t size, int32_t device = 0, Distance distance = Distance::Signed) : size_(size), distance_(distance) {
         int32_t rc = isomc_create(size, device, &h_);
         if (rc) throw Error(rc, isomc_last_error(nullptr));
     }
@@ -136,11 +140,13 @@ class MarchingCubes {
     template <class S> void extract(const S &source, Extractor &extractor) {
         SdfProgram prog;
         source.encode(prog);
-        check(isomc_extract_sdf(h_, prog.data(), (uint32_t)prog.size()));
+        check(distance_ == Distance::Directed ? isomc_extract_sdf_directed(h_, prog.data(), (uint32_t)prog.size())
+                                              : isomc_extract_sdf(h_, prog.data(), (uint32_t)prog.size()));
         deliver(extractor);
     }
     void extract(const DenseGrid &grid, Extractor &extractor) {
         if (grid.size != size_) throw Error(ISOMC_ERR_BAD_ARG, "grid size does not match");
+        if (distance_ == Distance::Directed) throw Error(ISOMC_ERR_UNSUPPORTED_SOURCE, "a dense scalar lattice has no Directed distances");
         if (!grid.on_device) {
             // host lattice -> host mesh in one pipelined call (copy-in, kernels and copy-out overlap), straight into the
             // Vecs of an IndexedVertices whose capacity is kept from the previous extract
@@ -199,6 +205,7 @@ class MarchingCubes {
     }
     isomc_t *h_ = nullptr;
     uint32_t size_;
+    Distance distance_ = Distance::Signed;
     uint64_t last_v_ = 0, last_t_ = 0;
 };
 

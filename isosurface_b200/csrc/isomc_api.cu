@@ -72,6 +72,7 @@ struct isomc {
     SrcKind kind = SRC_NONE;
     const float *d_grid = nullptr;
     SdfProgram prog{};
+    bool directed = false; /* implicit source sampled as Directed distances (MarchingCubes<Directed>) */
     /* profiling */
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -213,7 +214,7 @@ int32_t launch_emit_chunk(isomc *h, uint32_t c, cudaStream_t st) {
             CU(h, isomc_launch_emit_list_grid(g, h->d_grid, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
                                               h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
         else
-            CU(h, isomc_launch_emit_list_sdf(g, h->prog, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
+            CU(h, isomc_launch_emit_list_sdf(g, h->prog, h->directed, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
                                              h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
         h->stats.kernel_launches += 1;
         return ISOMC_OK;
@@ -267,7 +268,7 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
         const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
         const uint32_t row0 = (c == 0 ? 0u : l0 + 1) * g.N, row1 = (l1 + 1) * g.N;
         if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, row0, row1, h->sms, piped ? 3 : 8, st));
-        else CU(h, isomc_launch_sign_sdf(g, h->prog, h->signs, row0, row1, h->sms, piped ? 3 : 8, st));
+        else CU(h, isomc_launch_sign_sdf(g, h->prog, h->directed, h->signs, row0, row1, h->sms, piped ? 3 : 8, st));
         if (piped) CU(h, cudaEventRecord(h->ev_chunk[c], st));
         tl_mark(h, "sign", c, st);
         h->stats.kernel_launches += 1;
@@ -561,7 +562,7 @@ static int32_t enqueue_full(isomc_t *h) {
 int32_t isomc_enqueue_grid_device(isomc_t *h, const float *d_grid) {
     if (!h) return ISOMC_ERR_BAD_ARG;
     if (!d_grid) return fail(h, ISOMC_ERR_BAD_ARG, "d_grid == NULL");
-    h->kind = SRC_GRID; h->d_grid = d_grid;
+    h->kind = SRC_GRID; h->d_grid = d_grid; h->directed = false;
     return enqueue_full(h);
 }
 
@@ -569,8 +570,19 @@ int32_t isomc_enqueue_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nod
     if (!h) return ISOMC_ERR_BAD_ARG;
     int32_t rc = validate_program(h, prog, n_nodes, &h->prog);
     if (rc) return rc;
-    h->kind = SRC_SDF; h->d_grid = nullptr;
+    h->kind = SRC_SDF; h->d_grid = nullptr; h->directed = false;
     return enqueue_full(h);
+}
+
+/* MarchingCubes::<Directed>::new(size).extract(&Sampler::new(&implicit_tree), ..)  (reference src/distance.rs:72-104) */
+int32_t isomc_extract_sdf_directed(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h->list_mode) return fail(h, ISOMC_ERR_UNSUPPORTED_SOURCE, "Directed distances are served by the active-cell-list kernels (unset ISOMC_EMIT=brick)");
+    int32_t rc = validate_program(h, prog, n_nodes, &h->prog);
+    if (rc) return rc;
+    h->kind = SRC_SDF; h->d_grid = nullptr; h->directed = true;
+    rc = enqueue_full(h);
+    return rc ? rc : isomc_finish(h);
 }
 
 int32_t isomc_finish(isomc_t *h) {
@@ -642,7 +654,7 @@ int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, 
         }
         rc = set_vofs(h, 0);
         if (rc) return rc;
-        h->kind = SRC_GRID; h->d_grid = h->stage_grid;
+        h->kind = SRC_GRID; h->d_grid = h->stage_grid; h->directed = false;
         h->have_result = false; h->counted = false; h->emitted = false; h->totals_valid = false;
         h->stats.kernel_launches = 0; h->stats.emit_reruns = 0;
         h->emit_inline = true;
@@ -729,7 +741,7 @@ static int32_t points_impl(isomc_t *h) {
     uint32_t *segA = h->list_mode ? reinterpret_cast<uint32_t *>(h->L.segrec) : h->segpre;
     CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t), h->stream));
     if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, 0, g.nsl * g.N, h->sms, 8, h->stream));
-    else CU(h, isomc_launch_sign_sdf(g, h->prog, h->signs, 0, g.nsl * g.N, h->sms, 8, h->stream));
+    else CU(h, isomc_launch_sign_sdf(g, h->prog, h->directed, h->signs, 0, g.nsl * g.N, h->sms, 8, h->stream));
     CU(h, isomc_launch_points_count(g, h->signs, segA, h->rowV, h->rowT, h->layerTot, h->sms, h->stream));
     CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, nullptr, nullptr, nullptr, 0, g.ncl, h->stream));
     CU(h, cudaMemcpyAsync(h->h_totals, h->totals, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
@@ -753,7 +765,7 @@ static int32_t points_impl(isomc_t *h) {
 int32_t isomc_points_grid_device(isomc_t *h, const float *d_grid) {
     if (!h) return ISOMC_ERR_BAD_ARG;
     if (!d_grid) return fail(h, ISOMC_ERR_BAD_ARG, "d_grid == NULL");
-    h->kind = SRC_GRID; h->d_grid = d_grid;
+    h->kind = SRC_GRID; h->d_grid = d_grid; h->directed = false;
     return points_impl(h);
 }
 
@@ -761,7 +773,7 @@ int32_t isomc_points_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_node
     if (!h) return ISOMC_ERR_BAD_ARG;
     int32_t rc = validate_program(h, prog, n_nodes, &h->prog);
     if (rc) return rc;
-    h->kind = SRC_SDF; h->d_grid = nullptr;
+    h->kind = SRC_SDF; h->d_grid = nullptr; h->directed = false;
     return points_impl(h);
 }
 
@@ -867,7 +879,7 @@ int32_t isomc_slab_count_grid_device(isomc_t *h, const float *d_slab) {
     if (!d_slab) return fail(h, ISOMC_ERR_BAD_ARG, "d_slab == NULL");
     int32_t rc = bind_device(h);
     if (rc) return rc;
-    h->kind = SRC_GRID; h->d_grid = d_slab;
+    h->kind = SRC_GRID; h->d_grid = d_slab; h->directed = false;
     return enqueue_count(h, false);
 }
 
@@ -877,7 +889,7 @@ int32_t isomc_slab_count_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_
     if (rc) return rc;
     rc = validate_program(h, prog, n_nodes, &h->prog);
     if (rc) return rc;
-    h->kind = SRC_SDF; h->d_grid = nullptr;
+    h->kind = SRC_SDF; h->d_grid = nullptr; h->directed = false;
     return enqueue_count(h, false);
 }
 

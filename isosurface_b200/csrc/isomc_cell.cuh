@@ -38,52 +38,7 @@
 #include "isomc_device.cuh"
 #include "isomc_tables.h"
 
-#define ISOMC_HD __host__ __device__ __forceinline__
-
 constexpr uint32_t LIST_BLOCK = 256; /* entries per list block = threads per emit CTA */
-
-ISOMC_HD uint32_t hd_popc(uint32_t v) {
-#ifdef __CUDA_ARCH__
-    return (uint32_t)__popc(v);
-#else
-    return (uint32_t)__builtin_popcount(v);
-#endif
-}
-ISOMC_HD uint32_t hd_ffs0(uint32_t v) { /* index of the lowest set bit, v != 0 */
-#ifdef __CUDA_ARCH__
-    return (uint32_t)__ffs((int)v) - 1u;
-#else
-    return (uint32_t)__builtin_ctz(v);
-#endif
-}
-ISOMC_HD float hd_mul(float a, float b) {
-#ifdef __CUDA_ARCH__
-    return __fmul_rn(a, b);
-#else
-    return a * b; /* host model is compiled with -ffp-contract=off */
-#endif
-}
-ISOMC_HD float hd_add(float a, float b) {
-#ifdef __CUDA_ARCH__
-    return __fadd_rn(a, b);
-#else
-    return a + b;
-#endif
-}
-ISOMC_HD float hd_sub(float a, float b) {
-#ifdef __CUDA_ARCH__
-    return __fsub_rn(a, b);
-#else
-    return a - b;
-#endif
-}
-ISOMC_HD float hd_div(float a, float b) {
-#ifdef __CUDA_ARCH__
-    return __fdiv_rn(a, b);
-#else
-    return a / b;
-#endif
-}
 
 /* tables emit_cell needs (copied into shared memory by the kernel); derived from McTables on the host */
 struct EmitTab {
@@ -172,8 +127,8 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
         owned = em & (1u << 5 | 1u << 6 | 1u << 10);
         /* samples for the vertices this cell creates: requested first, used last */
         const bool o5 = (em >> 5 & 1u) != 0, o6 = (em >> 6 & 1u) != 0, o10 = (em >> 10 & 1u) != 0;
-        float s6 = 0.0f, s5 = 0.0f, s7 = 0.0f, s2 = 0.0f;
-        if (owned) src.corner6(g, x, y, lz, o5, o6, o10, s6, s5, s7, s2);
+        float a5 = 0.0f, b5 = 0.0f, a6 = 0.0f, b6 = 0.0f, a10 = 0.0f, b10 = 0.0f;
+        if (owned) src.corner6(g, x, y, lz, o5, o6, o10, a5, b5, a6, b6, a10, b10);
         const uint32_t r3 = T.rank3[ci];
         eid[5 * eid_stride] = vid + (r3 & 3u);
         eid[6 * eid_stride] = vid + (r3 >> 2 & 3u);
@@ -222,21 +177,21 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
             const float fz0 = hd_mul((float)(g.gz0 + lz), g.inv), fz1 = hd_mul((float)(g.gz0 + lz + 1), g.inv);
             const uint64_t s0 = (uint64_t)(vid - A.ghostV);
             if (o5 && s0 + (r3 & 3u) < A.cap_v) {
-                const float delta = hd_sub(s6, s5), t = (delta == 0.0f) ? 0.5f : hd_div(-s5, delta), omt = hd_sub(1.0f, t);
+                const float delta = hd_sub(b5, a5), t = (delta == 0.0f) ? 0.5f : hd_div(-a5, delta), omt = hd_sub(1.0f, t);
                 float *o = A.xyz + 3 * (s0 + (r3 & 3u));
                 o[0] = hd_add(hd_mul(fx1, omt), hd_mul(fx1, t));
                 o[1] = hd_add(hd_mul(fy0, omt), hd_mul(fy1, t));
                 o[2] = hd_add(hd_mul(fz1, omt), hd_mul(fz1, t));
             }
             if (o6 && s0 + (r3 >> 2 & 3u) < A.cap_v) {
-                const float delta = hd_sub(s7, s6), t = (delta == 0.0f) ? 0.5f : hd_div(-s6, delta), omt = hd_sub(1.0f, t);
+                const float delta = hd_sub(b6, a6), t = (delta == 0.0f) ? 0.5f : hd_div(-a6, delta), omt = hd_sub(1.0f, t);
                 float *o = A.xyz + 3 * (s0 + (r3 >> 2 & 3u));
                 o[0] = hd_add(hd_mul(fx1, omt), hd_mul(fx0, t));
                 o[1] = hd_add(hd_mul(fy1, omt), hd_mul(fy1, t));
                 o[2] = hd_add(hd_mul(fz1, omt), hd_mul(fz1, t));
             }
             if (o10 && s0 + (r3 >> 4 & 3u) < A.cap_v) {
-                const float delta = hd_sub(s6, s2), t = (delta == 0.0f) ? 0.5f : hd_div(-s2, delta), omt = hd_sub(1.0f, t);
+                const float delta = hd_sub(b10, a10), t = (delta == 0.0f) ? 0.5f : hd_div(-a10, delta), omt = hd_sub(1.0f, t);
                 float *o = A.xyz + 3 * (s0 + (r3 >> 4 & 3u));
                 o[0] = hd_add(hd_mul(fx1, omt), hd_mul(fx1, t));
                 o[1] = hd_add(hd_mul(fy1, omt), hd_mul(fy1, t));
@@ -275,7 +230,8 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
         const uint32_t en = T.ends[e];
         const uint32_t ux = x + (en & 1u), uy = y + (en >> 1 & 1u), uz = lz + (en >> 2 & 1u);
         const uint32_t vx = x + (en >> 4 & 1u), vy = y + (en >> 5 & 1u), vz = lz + (en >> 6 & 1u);
-        const float a = src.at(g, ux, uy, uz), b = src.at(g, vx, vy, vz);
+        float a, b;
+        src.pair(g, ux, uy, uz, vx, vy, vz, ((en ^ en >> 4) & 7u) >> 1, a, b); /* axis of the edge: 0 x, 1 y, 2 z */
         const float delta = hd_sub(b, a);
         const float t = (delta == 0.0f) ? 0.5f : hd_div(-a, delta);
         const float omt = hd_sub(1.0f, t);

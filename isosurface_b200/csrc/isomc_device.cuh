@@ -10,12 +10,66 @@
 #define ISOMC_DEVICE_CUH
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "../../include/isomc.h"
 
 #define ISOMC_VAL_DEPTH 8   /* value stack held in registers */
 #define ISOMC_TR_DEPTH 4    /* nested translations */
+
+#define ISOMC_HD __host__ __device__ __forceinline__
+
+ISOMC_HD uint32_t hd_popc(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
+ISOMC_HD uint32_t hd_ffs0(uint32_t v) { /* index of the lowest set bit, v != 0 */
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffs((int)v) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(v);
+#endif
+}
+ISOMC_HD float hd_mul(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    return a * b; /* host model is compiled with -ffp-contract=off */
+#endif
+}
+ISOMC_HD float hd_add(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+ISOMC_HD float hd_sub(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+ISOMC_HD float hd_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+
+ISOMC_HD float hd_sqrt(float a) {
+#ifdef __CUDA_ARCH__
+    return __fsqrt_rn(a);
+#else
+    return sqrtf(a);
+#endif
+}
 
 struct Geo {
     uint32_t N;      /* lattice points per x/y axis (= size) */
@@ -189,30 +243,118 @@ static inline bool sdf_to_chain(const SdfProgram &P, SdfChain *out) {
     return true;
 }
 
+/*
+ * Directed distances: VectorSource::sample_vector of the implicit shapes (reference src/implicit/sphere.rs:41-57,
+ * torus.rs:47-97, cylinder.rs:50-72, rectangular_prism.rs:42-74, csg.rs:41-45,74-78,102-106; the translation of
+ * examples/common/sources.rs:46-51), same operation order; f32::min / f32::max ignore a NaN operand like fminf / fmaxf.
+ * Host + device: tests/list_model.cu runs the same function on the CPU.
+ */
+#define ISOMC_F32_MAX 3.40282347e+38f
+struct Vec3f { float x, y, z; };
+
+ISOMC_HD Vec3f sdf_eval_vec(const SdfProgram &P, float px, float py, float pz) {
+    Vec3f vs[ISOMC_VAL_DEPTH];
+    float ts[ISOMC_TR_DEPTH][3];
+    int nv = 0, nt = 0;
+    for (uint32_t i = 0; i < P.n; ++i) {
+        const uint32_t op = P.nodes[i].op;
+        const float pa = P.nodes[i].a, pb = P.nodes[i].b, pc = P.nodes[i].c;
+        const float ax = fabsf(px), ay = fabsf(py), az = fabsf(pz); /* the point flipped into the positive octant */
+        Vec3f r;
+        r.x = r.y = r.z = 0.0f;
+        if (op == ISOMC_SDF_SPHERE) {
+            const float r2 = hd_mul(pa, pa);
+            const float l_yz = hd_sub(r2, hd_add(hd_mul(ay, ay), hd_mul(az, az)));
+            const float l_xz = hd_sub(r2, hd_add(hd_mul(ax, ax), hd_mul(az, az)));
+            const float l_xy = hd_sub(r2, hd_add(hd_mul(ax, ax), hd_mul(ay, ay)));
+            r.x = l_yz < 0.0f ? ISOMC_F32_MAX : hd_sub(ax, hd_sqrt(l_yz));
+            r.y = l_xz < 0.0f ? ISOMC_F32_MAX : hd_sub(ay, hd_sqrt(l_xz));
+            r.z = l_xy < 0.0f ? ISOMC_F32_MAX : hd_sub(az, hd_sqrt(l_xy));
+        } else if (op == ISOMC_SDF_TORUS) {
+            const float R = pa, tr = pb;
+            const float l_xy = hd_sub(hd_sqrt(hd_add(hd_mul(ax, ax), hd_mul(ay, ay))), R);
+            const float tz = hd_sqrt(hd_sub(hd_mul(tr, tr), hd_mul(az, az))); /* NaN beyond the tube: comparisons are false then */
+            const float rx = hd_add(R, tz), ry = hd_sub(R, tz);
+            if (az > tr || ay > hd_add(R, tz)) r.x = ISOMC_F32_MAX;
+            else if (ax == 0.0f) r.x = hd_sub(fabsf(hd_sub(ay, R)), tr);
+            else r.x = fmaxf(hd_sub(ax, hd_sqrt(hd_sub(hd_mul(rx, rx), hd_mul(ay, ay)))), hd_sub(hd_sqrt(hd_sub(hd_mul(ry, ry), hd_mul(ay, ay))), ax));
+            if (az > tr || ax > hd_add(R, tz)) r.y = ISOMC_F32_MAX;
+            else if (ay == 0.0f) r.y = hd_sub(fabsf(hd_sub(ax, R)), tr);
+            else r.y = fmaxf(hd_sub(ay, hd_sqrt(hd_sub(hd_mul(rx, rx), hd_mul(ax, ax)))), hd_sub(hd_sqrt(hd_sub(hd_mul(ry, ry), hd_mul(ax, ax))), ay));
+            if (fabsf(l_xy) > tr) r.z = ISOMC_F32_MAX;
+            else r.z = hd_sub(az, hd_sqrt(hd_sub(hd_mul(tr, tr), hd_mul(l_xy, l_xy))));
+        } else if (op == ISOMC_SDF_CYLINDER) {
+            const float R = pa, h = pb, R2 = hd_mul(R, R);
+            r.x = (az > h || ay > R) ? ISOMC_F32_MAX : hd_sub(ax, hd_sqrt(hd_sub(R2, hd_mul(ay, ay))));
+            r.y = (az > h || ax > R) ? ISOMC_F32_MAX : hd_sub(ay, hd_sqrt(hd_sub(R2, hd_mul(ax, ax))));
+            r.z = (hd_add(hd_mul(ax, ax), hd_mul(ay, ay)) > R2) ? ISOMC_F32_MAX : hd_sub(az, h);
+        } else if (op == ISOMC_SDF_PRISM) {
+            const bool ox = hd_sub(ax, pa) > 0.0f, oy = hd_sub(ay, pb) > 0.0f, oz = hd_sub(az, pc) > 0.0f;
+            const float mx = hd_mul((oy || oz) ? 1.0f : -1.0f, ISOMC_F32_MAX), my = hd_mul((ox || oz) ? 1.0f : -1.0f, ISOMC_F32_MAX);
+            const float mz = hd_mul((ox || oy) ? 1.0f : -1.0f, ISOMC_F32_MAX);
+            const bool inside = ax < pa && ay < pb && az < pc;
+            const float cx = inside ? fmaxf(ax, pa) : fminf(ax, pa), cy = inside ? fmaxf(ay, pb) : fminf(ay, pb);
+            const float cz = inside ? fmaxf(az, pc) : fminf(az, pc);
+            r.x = fmaxf(hd_sub(ax, cx), mx); r.y = fmaxf(hd_sub(ay, cy), my); r.z = fmaxf(hd_sub(az, cz), mz);
+        } else if (op == ISOMC_SDF_UNION || op == ISOMC_SDF_INTERSECTION || op == ISOMC_SDF_DIFFERENCE) {
+            const Vec3f A = vs[nv - 2], B = vs[nv - 1]; /* first-pushed = field `a` */
+            if (op == ISOMC_SDF_UNION) { r.x = fminf(A.x, B.x); r.y = fminf(A.y, B.y); r.z = fminf(A.z, B.z); }
+            else if (op == ISOMC_SDF_INTERSECTION) { r.x = fmaxf(A.x, B.x); r.y = fmaxf(A.y, B.y); r.z = fmaxf(A.z, B.z); }
+            else { r.x = fmaxf(B.x, -A.x); r.y = fmaxf(B.y, -A.y); r.z = fmaxf(B.z, -A.z); }
+            vs[nv - 2] = r;
+            --nv;
+            continue;
+        } else if (op == ISOMC_SDF_TRANSLATE_PUSH) {
+            ts[nt][0] = px; ts[nt][1] = py; ts[nt][2] = pz;
+            ++nt;
+            px = hd_sub(px, pa); py = hd_sub(py, pb); pz = hd_sub(pz, pc);
+            continue;
+        } else { /* ISOMC_SDF_TRANSLATE_POP (programs are validated on the host) */
+            --nt;
+            px = ts[nt][0]; py = ts[nt][1]; pz = ts[nt][2];
+            continue;
+        }
+        vs[nv++] = r;
+    }
+    return vs[0];
+}
+
 /* Sources as seen by the kernels: value at lattice point (x, y, local layer lz / global gz). */
 struct GridSrc {
     const float *__restrict__ p; /* first sample layer of the handle's slab */
     __device__ __forceinline__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
         return __ldg(p + ((uint64_t)lz * g.N + y) * g.N + x);
     }
-    /* samples at corner 6 = (x+1, y+1, lz+1) of a cell and, where needed, at corners 5 (-y), 7 (-x), 2 (-z) */
-    __device__ __forceinline__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n7, bool n2, float &s6,
-                                            float &s5, float &s7, float &s2) const {
+    /* the two ends of a lattice edge along `axis` (a scalar field has one value whatever the axis) */
+    __device__ __forceinline__ void pair(const Geo &g, uint32_t ux, uint32_t uy, uint32_t uz, uint32_t vx, uint32_t vy, uint32_t vz,
+                                         uint32_t, float &a, float &b) const {
+        a = at(g, ux, uy, uz);
+        b = at(g, vx, vy, vz);
+    }
+    /* the (a, b) ends of the three edges a cell creates, all meeting at corner 6 = (x+1, y+1, lz+1):
+     * e5 = corners 5 -> 6 (y), e6 = corners 6 -> 7 (x), e10 = corners 2 -> 6 (z); only the requested ones are loaded */
+    __device__ __forceinline__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n6, bool n10, float &a5,
+                                            float &b5, float &a6, float &b6, float &a10, float &b10) const {
         const float *q = p + ((uint64_t)(lz + 1) * g.N + (y + 1)) * g.N + (x + 1);
-        s6 = __ldg(q);
-        s5 = n5 ? __ldg(q - g.N) : 0.0f;
-        s7 = n7 ? __ldg(q - 1) : 0.0f;
-        s2 = n2 ? __ldg(q - (uint64_t)g.N * g.N) : 0.0f;
+        const float s6 = __ldg(q);
+        a5 = n5 ? __ldg(q - g.N) : 0.0f; b5 = s6;
+        a6 = s6; b6 = n6 ? __ldg(q - 1) : 0.0f;
+        a10 = n10 ? __ldg(q - (uint64_t)g.N * g.N) : 0.0f; b10 = s6;
     }
 };
-/* corner6() for sources that evaluate instead of loading */
-#define ISOMC_CORNER6_BY_AT                                                                                                     \
-    __device__ __forceinline__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n7, bool n2, float &s6, \
-                                            float &s5, float &s7, float &s2) const {                                            \
-        s6 = at(g, x + 1, y + 1, lz + 1);                                                                                        \
-        s5 = n5 ? at(g, x + 1, y, lz + 1) : 0.0f;                                                                                \
-        s7 = n7 ? at(g, x, y + 1, lz + 1) : 0.0f;                                                                                \
-        s2 = n2 ? at(g, x + 1, y + 1, lz) : 0.0f;                                                                                \
+/* pair() / corner6() for scalar sources that evaluate instead of loading */
+#define ISOMC_SCALAR_EDGE_SAMPLES                                                                                                  \
+    __device__ __forceinline__ void pair(const Geo &g, uint32_t ux, uint32_t uy, uint32_t uz, uint32_t vx, uint32_t vy, uint32_t vz, \
+                                         uint32_t, float &a, float &b) const {                                                     \
+        a = at(g, ux, uy, uz);                                                                                                      \
+        b = at(g, vx, vy, vz);                                                                                                      \
+    }                                                                                                                               \
+    __device__ __forceinline__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n6, bool n10, float &a5, \
+                                            float &b5, float &a6, float &b6, float &a10, float &b10) const {                       \
+        const float s6 = at(g, x + 1, y + 1, lz + 1);                                                                               \
+        a5 = n5 ? at(g, x + 1, y, lz + 1) : 0.0f; b5 = s6;                                                                          \
+        a6 = s6; b6 = n6 ? at(g, x, y + 1, lz + 1) : 0.0f;                                                                          \
+        a10 = n10 ? at(g, x + 1, y + 1, lz) : 0.0f; b10 = s6;                                                                       \
     }
 struct SdfSrc {
     SdfProgram prog;
@@ -221,7 +363,7 @@ struct SdfSrc {
         return sdf_eval(prog, __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv),
                         __fmul_rn((float)(g.gz0 + lz), g.inv));
     }
-    ISOMC_CORNER6_BY_AT
+    ISOMC_SCALAR_EDGE_SAMPLES
 };
 struct SdfChainSrc {
     SdfChain chain;
@@ -229,7 +371,34 @@ struct SdfChainSrc {
         return sdf_chain_eval(chain, __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv),
                               __fmul_rn((float)(g.gz0 + lz), g.inv));
     }
-    ISOMC_CORNER6_BY_AT
+    ISOMC_SCALAR_EDGE_SAMPLES
+};
+
+/* MarchingCubes<Directed> over an implicit tree (reference src/distance.rs:72-104): outside iff any component > 0,
+ * crossings interpolated from the component along the edge's own axis */
+struct SdfDirSrc {
+    SdfProgram prog;
+    __device__ __forceinline__ Vec3f vec(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
+        return sdf_eval_vec(prog, __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv), __fmul_rn((float)(g.gz0 + lz), g.inv));
+    }
+    /* value for the sign test: positive iff some component is positive (NaN components never are) */
+    __device__ __forceinline__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
+        const Vec3f v = vec(g, x, y, lz);
+        return (v.x > 0.0f || v.y > 0.0f || v.z > 0.0f) ? 1.0f : -1.0f;
+    }
+    static __device__ __forceinline__ float comp(const Vec3f &v, uint32_t axis) { return axis == 0 ? v.x : axis == 1 ? v.y : v.z; }
+    __device__ __forceinline__ void pair(const Geo &g, uint32_t ux, uint32_t uy, uint32_t uz, uint32_t vx, uint32_t vy, uint32_t vz,
+                                         uint32_t axis, float &a, float &b) const {
+        a = comp(vec(g, ux, uy, uz), axis);
+        b = comp(vec(g, vx, vy, vz), axis);
+    }
+    __device__ __forceinline__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n6, bool n10, float &a5,
+                                            float &b5, float &a6, float &b6, float &a10, float &b10) const {
+        const Vec3f s6 = vec(g, x + 1, y + 1, lz + 1);
+        a5 = n5 ? vec(g, x + 1, y, lz + 1).y : 0.0f; b5 = s6.y;
+        a6 = s6.x; b6 = n6 ? vec(g, x, y + 1, lz + 1).x : 0.0f;
+        a10 = n10 ? vec(g, x + 1, y + 1, lz).z : 0.0f; b10 = s6.z;
+    }
 };
 
 #endif

@@ -889,8 +889,12 @@ cudaError_t isomc_launch_sign_grid(const Geo &g, const float *d_grid, uint32_t *
     }
     return cudaGetLastError();
 }
-cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, uint32_t *signs, uint32_t row0, uint32_t row1, int sms,
-                                  int ctas_per_sm, cudaStream_t st) {
+cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, bool directed, uint32_t *signs, uint32_t row0, uint32_t row1,
+                                  int sms, int ctas_per_sm, cudaStream_t st) {
+    if (directed) {
+        k_sign<SdfDirSrc><<<grid_for((uint64_t)(row1 - row0), sms, 8, ctas_per_sm), 256, 0, st>>>(SdfDirSrc{prog}, g, signs, row0, row1);
+        return cudaGetLastError();
+    }
     SdfChainSrc csrc;
     if (sdf_to_chain(prog, &csrc.chain)) {
         k_sign<SdfChainSrc><<<grid_for((uint64_t)(row1 - row0), sms, 8, ctas_per_sm), 256, 0, st>>>(csrc, g, signs, row0, row1);

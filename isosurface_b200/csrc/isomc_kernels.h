@@ -22,8 +22,9 @@ size_t isomc_emit_smem_bytes(uint32_t nws);
 /* ranges: sample rows [row0,row1) for the sign kernels, cell layers [lz0,lz1) for the rest */
 cudaError_t isomc_launch_sign_grid(const Geo &g, const float *d_grid, uint32_t *signs, uint32_t row0, uint32_t row1, int sms,
                                    int ctas_per_sm, cudaStream_t st);
-cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, uint32_t *signs, uint32_t row0, uint32_t row1, int sms,
-                                  int ctas_per_sm, cudaStream_t st);
+/* directed: sample the tree as Directed distances (inside iff no component is positive) */
+cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, bool directed, uint32_t *signs, uint32_t row0, uint32_t row1,
+                                  int sms, int ctas_per_sm, cudaStream_t st);
 cudaError_t isomc_launch_count(const Geo &g, const uint32_t *signs, const McTables *tabs, uint32_t *segpre,
                                uint32_t *rowV, uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot,
                                uint32_t lz0, uint32_t lz1, int sms, int ctas_per_sm, cudaStream_t st);
@@ -59,7 +60,7 @@ cudaError_t isomc_launch_emit_list_grid(const Geo &g, const float *d_grid, const
                                         const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                         const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
                                         const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st);
-cudaError_t isomc_launch_emit_list_sdf(const Geo &g, const SdfProgram &prog, const ListBufs &L, const EmitTab *tab,
+cudaError_t isomc_launch_emit_list_sdf(const Geo &g, const SdfProgram &prog, bool directed, const ListBufs &L, const EmitTab *tab,
                                        const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                        const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
                                        const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st);

@@ -17,8 +17,13 @@ class MarchingCubes:
     per instance (`&mut self`).
     """
 
-    def __init__(self, size, device=0):
+    def __init__(self, size, device=0, distance="signed"):
+        """distance: "signed" = MarchingCubes::<Signed> (scalar distances), "directed" = MarchingCubes::<Directed> (a signed
+        distance along each axis, reference src/distance.rs:43-45,72-104; implicit sources only)"""
+        if distance not in ("signed", "directed"):
+            raise ValueError("distance must be 'signed' or 'directed'")
         lib = _lib.load()
+        self.distance = distance
         self.size, self.device = int(size), int(device)
         self._h = C.c_void_p()
         _lib.check(lib.isomc_create(self.size, self.device, C.byref(self._h)))
@@ -80,11 +85,14 @@ class MarchingCubes:
         if isinstance(src, DenseGrid):
             if src.size != self.size:
                 raise ValueError("grid is for size %d, MarchingCubes for %d" % (src.size, self.size))
+            if self.distance == "directed":
+                raise TypeError("a dense scalar lattice has no Directed distances; use an implicit source")
             fn = self._lib.isomc_extract_grid_device if src.on_device else self._lib.isomc_extract_grid_host
             _lib.check(fn(self._h, src.ptr), self._h)
         else:
             prog = encode_program(src)
-            _lib.check(self._lib.isomc_extract_sdf(self._h, prog.ctypes.data, len(prog)), self._h)
+            fn = self._lib.isomc_extract_sdf_directed if self.distance == "directed" else self._lib.isomc_extract_sdf
+            _lib.check(fn(self._h, prog.ctypes.data, len(prog)), self._h)
         return self.counts()
 
     def enqueue(self, source):

@@ -627,3 +627,204 @@ int oracle_interleaved_normals_cd(const osdf_node *inner, uint32_t n, float epsi
     }
     return err ? -2 : 0;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* MarchingCubes::<Directed>: the same traversal with a signed distance along each of    */
+/* the three cardinal axes (reference src/distance.rs:43-45,72-104).                      */
+/*   sample_vector:  src/implicit/sphere.rs:41-57, torus.rs:47-97, cylinder.rs:50-72,     */
+/*                   rectangular_prism.rs:42-74, csg.rs:41-45,74-78,102-106,              */
+/*                   examples/common/sources.rs:46-51 (q = p - 0.5)                       */
+/*   is_positive:    any component > 0                                  distance.rs:77-80 */
+/*   crossing point: t from the component along the edge's axis          distance.rs:90-103 */
+/* f32::min / f32::max ignore a NaN operand, as fminf / fmaxf do.                        */
+/* ------------------------------------------------------------------------------------ */
+#define OSDF_FMAX 3.40282347e+38f /* std::f32::MAX */
+
+static v3 sdf_eval_vec(const osdf_node *prog, uint32_t n, v3 p, int *err) {
+    v3 vs[OSDF_MAX_STACK], ps[OSDF_MAX_STACK];
+    const v3 zero = {0.0f, 0.0f, 0.0f};
+    int nv = 0, np = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const osdf_node *nd = &prog[i];
+        const v3 a = {fabsf(p.x), fabsf(p.y), fabsf(p.z)}; /* "flip the point into the positive quadrant" */
+        v3 r = zero;
+        switch (nd->op) {
+        case O_SPHERE: {
+            const float r2 = nd->a * nd->a;
+            const float l_yz = r2 - (a.y * a.y + a.z * a.z), l_xz = r2 - (a.x * a.x + a.z * a.z), l_xy = r2 - (a.x * a.x + a.y * a.y);
+            r.x = l_yz < 0.0f ? OSDF_FMAX : a.x - sqrtf(l_yz);
+            r.y = l_xz < 0.0f ? OSDF_FMAX : a.y - sqrtf(l_xz);
+            r.z = l_xy < 0.0f ? OSDF_FMAX : a.z - sqrtf(l_xy);
+        } break;
+        case O_TORUS: {
+            const float R = nd->a, tr = nd->b;
+            const float l = sqrtf(a.x * a.x + a.y * a.y), l_xy = l - R;
+            const float tz = sqrtf(tr * tr - a.z * a.z); /* tube_radius_at_z: NaN beyond the tube, comparisons are then false */
+            const float rx = R + tz, ry = R - tz;
+            if (a.z > tr || a.y > R + tz) r.x = OSDF_FMAX;
+            else if (a.x == 0.0f) r.x = fabsf(a.y - R) - tr;
+            else r.x = fmaxf(a.x - sqrtf(rx * rx - a.y * a.y), sqrtf(ry * ry - a.y * a.y) - a.x);
+            if (a.z > tr || a.x > R + tz) r.y = OSDF_FMAX;
+            else if (a.y == 0.0f) r.y = fabsf(a.x - R) - tr;
+            else r.y = fmaxf(a.y - sqrtf(rx * rx - a.x * a.x), sqrtf(ry * ry - a.x * a.x) - a.y);
+            if (fabsf(l_xy) > tr) r.z = OSDF_FMAX;
+            else r.z = a.z - sqrtf(tr * tr - l_xy * l_xy);
+        } break;
+        case O_CYLINDER: {
+            const float R = nd->a, h = nd->b;
+            r.x = (a.z > h || a.y > R) ? OSDF_FMAX : a.x - sqrtf(R * R - a.y * a.y);
+            r.y = (a.z > h || a.x > R) ? OSDF_FMAX : a.y - sqrtf(R * R - a.x * a.x);
+            r.z = (a.x * a.x + a.y * a.y > R * R) ? OSDF_FMAX : a.z - h;
+        } break;
+        case O_PRISM: {
+            const v3 he = {nd->a, nd->b, nd->c};
+            v3 mask;
+            mask.x = (((a.y - he.y) > 0.0f || (a.z - he.z) > 0.0f) ? 1.0f : -1.0f) * OSDF_FMAX;
+            mask.y = (((a.x - he.x) > 0.0f || (a.z - he.z) > 0.0f) ? 1.0f : -1.0f) * OSDF_FMAX;
+            mask.z = (((a.x - he.x) > 0.0f || (a.y - he.y) > 0.0f) ? 1.0f : -1.0f) * OSDF_FMAX;
+            v3 c;
+            if (a.x < he.x && a.y < he.y && a.z < he.z) { c.x = fmaxf(a.x, he.x); c.y = fmaxf(a.y, he.y); c.z = fmaxf(a.z, he.z); }
+            else { c.x = fminf(a.x, he.x); c.y = fminf(a.y, he.y); c.z = fminf(a.z, he.z); }
+            r.x = fmaxf(a.x - c.x, mask.x); r.y = fmaxf(a.y - c.y, mask.y); r.z = fmaxf(a.z - c.z, mask.z);
+        } break;
+        case O_UNION: case O_INTERSECTION: case O_DIFFERENCE: {
+            if (nv < 2) { *err = 1; return zero; }
+            const v3 A = vs[nv - 2], B = vs[nv - 1];
+            if (nd->op == O_UNION) { r.x = fminf(A.x, B.x); r.y = fminf(A.y, B.y); r.z = fminf(A.z, B.z); }
+            else if (nd->op == O_INTERSECTION) { r.x = fmaxf(A.x, B.x); r.y = fmaxf(A.y, B.y); r.z = fmaxf(A.z, B.z); }
+            else { r.x = fmaxf(B.x, -A.x); r.y = fmaxf(B.y, -A.y); r.z = fmaxf(B.z, -A.z); } /* b.max(-a) */
+            vs[nv - 2] = r;
+            --nv;
+            continue;
+        }
+        case O_TRANSLATE_PUSH:
+            if (np >= OSDF_MAX_STACK) { *err = 1; return zero; }
+            ps[np++] = p;
+            p.x = p.x - nd->a; p.y = p.y - nd->b; p.z = p.z - nd->c;
+            continue;
+        case O_TRANSLATE_POP:
+            if (np < 1) { *err = 1; return zero; }
+            p = ps[--np];
+            continue;
+        default:
+            *err = 1;
+            return zero;
+        }
+        if (nv >= OSDF_MAX_STACK) { *err = 1; return zero; }
+        vs[nv++] = r;
+    }
+    if (nv != 1 || np != 0) { *err = 1; return zero; }
+    return vs[0];
+}
+
+int oracle_sample_sdf_vector(const osdf_node *prog, uint32_t n, const float *xyz, uint64_t npts, float *out) {
+    int err = 0;
+    for (uint64_t i = 0; i < npts; ++i) {
+        v3 p = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        v3 r = sdf_eval_vec(prog, n, p, &err);
+        if (err) return -2;
+        out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+    }
+    return 0;
+}
+
+/* MarchingCubes::<Directed>::new(size).extract(&Sampler::new(&implicit_tree), &mut IndexedVertices); lean dedup
+ * (same semantics as the faithful maps: first sight of a lattice edge creates the vertex). */
+int oracle_extract_sdf_directed(uint32_t size, const osdf_node *prog, uint32_t n, oracle_mesh *out) {
+    memset(out, 0, sizeof *out);
+    if (tables_init()) return -3;
+    if (size < 1) return -1;
+    int rc = 0, err = 0;
+    typedef struct { v3 corner; v3 value; } dentry;
+    dentry *layers[2];
+    lean_map lmap = {0};
+    uint64_t *faces = NULL, n_faces = 0, cap_faces = 0;
+    layers[0] = (dentry *)malloc((size_t)size * size * sizeof(dentry));
+    layers[1] = (dentry *)malloc((size_t)size * size * sizeof(dentry));
+    if (!layers[0] || !layers[1]) { rc = -4; goto done; }
+    const uint32_t sm1 = size - 1;
+    const float inv = 1.0f / (float)sm1;
+    for (uint32_t y = 0; y < size; ++y)
+        for (uint32_t x = 0; x < size; ++x) {
+            v3 c = {(float)x * inv, (float)y * inv, 0.0f};
+            dentry e = {c, sdf_eval_vec(prog, n, c, &err)};
+            layers[0][(size_t)y * size + x] = e;
+        }
+    for (uint32_t z = 0; z < size; ++z) {
+        for (uint32_t y = 0; y < size; ++y)
+            for (uint32_t x = 0; x < size; ++x) {
+                v3 c = {(float)x * inv, (float)y * inv, (float)(z + 1) * inv};
+                dentry e = {c, sdf_eval_vec(prog, n, c, &err)};
+                layers[1][(size_t)y * size + x] = e;
+            }
+        if (err) { rc = -2; goto done; }
+        for (uint32_t y = 0; y < sm1; ++y)
+            for (uint32_t x = 0; x < sm1; ++x) {
+                uint64_t keys[8][3];
+                v3 corners[8], values[8];
+                unsigned cube_index = 0;
+                for (int i = 0; i < 8; ++i) {
+                    keys[i][0] = x + CORNER_OFF[i][0]; keys[i][1] = y + CORNER_OFF[i][1]; keys[i][2] = z + CORNER_OFF[i][2];
+                    dentry e = layers[CORNER_OFF[i][2]][(size_t)(y + CORNER_OFF[i][1]) * size + x + CORNER_OFF[i][0]];
+                    corners[i] = e.corner; values[i] = e.value;
+                    const int positive = e.value.x > 0.0f || e.value.y > 0.0f || e.value.z > 0.0f; /* Directed::is_positive */
+                    if (!positive) cube_index |= 1u << i;
+                }
+                if (cube_index != 0 && cube_index != 255) out->n_active_cells++;
+                v3 vertices[12];
+                const unsigned edges = EDGE_MASK[cube_index];
+                for (int i = 0; i < 12; ++i)
+                    if (edges & (1u << i)) {
+                        const int u = EDGE_ENDS[i][0], v = EDGE_ENDS[i][1];
+                        const v3 pa = corners[u], pb = corners[v];
+                        /* axis = (p_a - p_b).abs().max_component_index()   (vector.rs:255-263) */
+                        const float dx = fabsf(pa.x - pb.x), dy = fabsf(pa.y - pb.y), dz = fabsf(pa.z - pb.z);
+                        const int axis = (dx > dy && dx > dz) ? 0 : (dy > dz) ? 1 : 2;
+                        const float a = axis == 0 ? values[u].x : axis == 1 ? values[u].y : values[u].z;
+                        const float b = axis == 0 ? values[v].x : axis == 1 ? values[v].y : values[v].z;
+                        const float delta = b - a;
+                        const float t = (delta == 0.0f) ? 0.5f : -a / delta;
+                        const float omt = 1.0f - t;
+                        v3 r = {pa.x * omt + pb.x * t, pa.y * omt + pb.y * t, pa.z * omt + pb.z * t};
+                        vertices[i] = r;
+                    }
+                for (int i = 0; i < 5; ++i) {
+                    if (TRI[cube_index][3 * i] < 0) break;
+                    uint64_t h[3];
+                    for (int k = 0; k < 3; ++k) {
+                        const int e = TRI[cube_index][3 * i + k];
+                        const int u = EDGE_ENDS[e][0], v = EDGE_ENDS[e][1];
+                        const uint64_t *a = keys[u], *b = keys[v];
+                        const int a_gt_b = (a[0] != b[0]) ? (a[0] > b[0]) : (a[1] != b[1]) ? (a[1] > b[1]) : (a[2] > b[2]);
+                        if (a_gt_b) { const uint64_t *t = a; a = b; b = t; }
+                        /* lattice edge -> handle: the edge is (lower point, axis) */
+                        const uint64_t ax = (a[0] != b[0]) ? 0 : (a[1] != b[1]) ? 1 : 2;
+                        const uint64_t key = (((a[2] * size + a[1]) * size + a[0]) * 3 + ax) + 1;
+                        if ((lmap.len + 1) * 8 > lmap.cap * 5) if (lean_grow(&lmap)) { rc = -4; goto done; }
+                        uint64_t j = mix64(key) & (lmap.cap - 1);
+                        while (lmap.k[j] != UINT64_MAX && lmap.k[j] != key) j = (j + 1) & (lmap.cap - 1);
+                        if (lmap.k[j] == UINT64_MAX) {
+                            lmap.k[j] = key; lmap.v[j] = (uint32_t)out->n_vertices; lmap.len++;
+                            if (push_vertex(out, vertices[e])) { rc = -4; goto done; }
+                        }
+                        h[k] = lmap.v[j];
+                    }
+                    if (n_faces + 3 > cap_faces) {
+                        cap_faces = cap_faces ? cap_faces * 2 : 4096;
+                        uint64_t *nf = (uint64_t *)realloc(faces, cap_faces * sizeof(uint64_t));
+                        if (!nf) { rc = -4; goto done; }
+                        faces = nf;
+                    }
+                    faces[n_faces] = h[0]; faces[n_faces + 1] = h[1]; faces[n_faces + 2] = h[2];
+                    n_faces += 3;
+                }
+            }
+        { dentry *t = layers[0]; layers[0] = layers[1]; layers[1] = t; }
+    }
+    for (uint64_t i = 0; i < n_faces; i += 3)
+        if (push_indices(out, faces[i], faces[i + 1], faces[i + 2])) { rc = -4; goto done; }
+done:
+    free(layers[0]); free(layers[1]); free(lmap.k); free(lmap.v); free(faces);
+    if (rc) oracle_mesh_free(out);
+    return rc;
+}

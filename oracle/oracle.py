@@ -48,6 +48,8 @@ def lib():
         _LIB.oracle_mesh_free.argtypes = [C.POINTER(_Mesh)]
         _LIB.oracle_interleaved_normals_cd.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p,
                                                        C.c_uint64, C.c_void_p]
+        _LIB.oracle_sample_sdf_vector.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+        _LIB.oracle_extract_sdf_directed.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
         _LIB.oracle_point_cloud_sdf.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
         _LIB.oracle_point_cloud_grid.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
     return _LIB
@@ -88,6 +90,27 @@ def extract_grid(size, grid, z_cells=None, mode=LEAN):
     rc = lib().oracle_extract_grid(size, grid.ctypes.data, z_cells, mode, C.byref(m))
     if rc:
         raise RuntimeError("oracle_extract_grid rc=%d" % rc)
+    return _take(m)
+
+
+def sample_sdf_vector(prog, pts):
+    """VectorSource::sample_vector of the implicit tree at pts -> (n, 3) Directed distances"""
+    prog = np.ascontiguousarray(prog)
+    pts = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros((len(pts), 3), dtype=np.float32)
+    rc = lib().oracle_sample_sdf_vector(prog.ctypes.data, len(prog), pts.ctypes.data, len(pts), out.ctypes.data)
+    if rc:
+        raise RuntimeError("oracle_sample_sdf_vector rc=%d" % rc)
+    return out
+
+
+def extract_sdf_directed(size, prog):
+    """MarchingCubes::<Directed>::new(size).extract (reference src/distance.rs:72-104)"""
+    m = _Mesh()
+    prog = np.ascontiguousarray(prog)
+    rc = lib().oracle_extract_sdf_directed(size, prog.ctypes.data, len(prog), C.byref(m))
+    if rc:
+        raise RuntimeError("oracle_extract_sdf_directed rc=%d" % rc)
     return _take(m)
 
 

@@ -20,6 +20,7 @@ extern "C" {
     fn isomc_destroy(h: *mut isomc_t) -> i32;
     fn isomc_last_error(h: *const isomc_t) -> *const c_char;
     fn isomc_extract_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
+    fn isomc_extract_sdf_directed(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
     fn isomc_extract_grid_host(h: *mut isomc_t, grid: *const f32) -> i32;
     fn isomc_extract_grid_device(h: *mut isomc_t, d_grid: *const f32) -> i32;
     fn isomc_extract_grid_host_to(h: *mut isomc_t, grid: *const f32, xyz: *mut f32, cap_vertices: u64, idx: *mut u32,
@@ -123,6 +124,15 @@ impl MarchingCubes {
         let mut prog = Vec::new();
         source.encode(&mut prog);
         self.check(unsafe { isomc_extract_sdf(self.h, prog.as_ptr(), prog.len() as u32) });
+        self.deliver(extractor);
+    }
+
+    /// `MarchingCubes::<Directed>::extract` (reference src/distance.rs:72-104): in the crate this is the `D = Directed`
+    /// instantiation of the same generic method; the tree is sampled through its `VectorSource` side on the device.
+    pub fn extract_directed<S: DeviceSource, E: Extractor>(&mut self, source: &S, extractor: &mut E) {
+        let mut prog = Vec::new();
+        source.encode(&mut prog);
+        self.check(unsafe { isomc_extract_sdf_directed(self.h, prog.as_ptr(), prog.len() as u32) });
         self.deliver(extractor);
     }
 

@@ -33,6 +33,11 @@ int main() {
             std::printf("unexpected counts: points %zu, vertices %zu, triangles %zu\n", pts.size() / 3, vn.size() / 6, ni.size() / 3);
             return 1;
         }
+        std::vector<float> dv; std::vector<uint32_t> di;
+        MarchingCubes dmc(64, 0, Distance::Directed);   // MarchingCubes::<Directed>
+        IndexedVertices dsink(dv, di);
+        dmc.extract(Sampler(src), dsink);
+        if (di.size() / 3 != ni.size() / 3) { std::printf("Directed: %zu triangles, Signed %zu\n", di.size() / 3, ni.size() / 3); return 1; }
         std::vector<float> grid((size_t)64 * 64 * 65);
         for (size_t i = 0; i < grid.size(); ++i) grid[i] = (float)((i * 2654435761u >> 7) % 1000) - 500.0f;
         IndexedVertices hsink(hv, hi);

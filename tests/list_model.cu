@@ -95,12 +95,42 @@ void run_warp(Emu &E, WarpJob &J) {
 struct HostGridSrc {
     const float *p;
     __host__ __device__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const { return p[((uint64_t)lz * g.N + y) * g.N + x]; }
-    __host__ __device__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n7, bool n2, float &s6, float &s5,
-                                     float &s7, float &s2) const {
-        s6 = at(g, x + 1, y + 1, lz + 1);
-        s5 = n5 ? at(g, x + 1, y, lz + 1) : 0.0f;
-        s7 = n7 ? at(g, x, y + 1, lz + 1) : 0.0f;
-        s2 = n2 ? at(g, x + 1, y + 1, lz) : 0.0f;
+    __host__ __device__ void pair(const Geo &g, uint32_t ux, uint32_t uy, uint32_t uz, uint32_t vx, uint32_t vy, uint32_t vz, uint32_t,
+                                  float &a, float &b) const {
+        a = at(g, ux, uy, uz);
+        b = at(g, vx, vy, vz);
+    }
+    __host__ __device__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n6, bool n10, float &a5, float &b5,
+                                     float &a6, float &b6, float &a10, float &b10) const {
+        const float s6 = at(g, x + 1, y + 1, lz + 1);
+        a5 = n5 ? at(g, x + 1, y, lz + 1) : 0.0f; b5 = s6;
+        a6 = s6; b6 = n6 ? at(g, x, y + 1, lz + 1) : 0.0f;
+        a10 = n10 ? at(g, x + 1, y + 1, lz) : 0.0f; b10 = s6;
+    }
+};
+
+/* MarchingCubes<Directed> over an implicit tree: the device source SdfDirSrc restated for the host, same sdf_eval_vec */
+struct HostDirSrc {
+    SdfProgram prog;
+    __host__ __device__ Vec3f vec(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
+        return sdf_eval_vec(prog, (float)x * g.inv, (float)y * g.inv, (float)(g.gz0 + lz) * g.inv);
+    }
+    __host__ __device__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
+        const Vec3f v = vec(g, x, y, lz);
+        return (v.x > 0.0f || v.y > 0.0f || v.z > 0.0f) ? 1.0f : -1.0f;
+    }
+    static __host__ __device__ float comp(const Vec3f &v, uint32_t axis) { return axis == 0 ? v.x : axis == 1 ? v.y : v.z; }
+    __host__ __device__ void pair(const Geo &g, uint32_t ux, uint32_t uy, uint32_t uz, uint32_t vx, uint32_t vy, uint32_t vz, uint32_t axis,
+                                  float &a, float &b) const {
+        a = comp(vec(g, ux, uy, uz), axis);
+        b = comp(vec(g, vx, vy, vz), axis);
+    }
+    __host__ __device__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n6, bool n10, float &a5, float &b5,
+                                     float &a6, float &b6, float &a10, float &b10) const {
+        const Vec3f s6 = vec(g, x + 1, y + 1, lz + 1);
+        a5 = n5 ? vec(g, x + 1, y, lz + 1).y : 0.0f; b5 = s6.y;
+        a6 = s6.x; b6 = n6 ? vec(g, x, y + 1, lz + 1).x : 0.0f;
+        a10 = n10 ? vec(g, x + 1, y + 1, lz).z : 0.0f; b10 = s6.z;
     }
 };
 
@@ -128,9 +158,9 @@ extern "C" {
  *             [3] active cells owned, [4] list blocks handed out, [5] list entries.
  * Returns 0, or 1 if the list overflowed cap_blocks (outputs invalid then, totals still right).
  */
-int list_model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const float *slab, uint32_t n_warps, uint32_t seed,
-                       uint32_t vofs, uint32_t cap_blocks, float *xyz, uint64_t cap_v, uint32_t *idx, uint64_t cap_t,
-                       uint64_t *out_totals) {
+static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const float *slab, const SdfProgram *directed,
+                         uint32_t n_warps, uint32_t seed, uint32_t vofs, uint32_t cap_blocks, float *xyz, uint64_t cap_v, uint32_t *idx,
+                         uint64_t cap_t, uint64_t *out_totals) {
     Geo g;
     g.N = size; g.ncx = size - 1;
     g.nsegx = (g.ncx + 31) / 32; g.nws = (g.nsegx + 2) & ~1u;
@@ -146,9 +176,13 @@ int list_model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const fl
     /* K1 restated: inside bit = !(v > 0) */
     const uint64_t nrows_s = (uint64_t)g.nsl * g.N, nrows_c = (uint64_t)g.ncl * g.ncx;
     std::vector<uint32_t> signs(nrows_s * g.nws + 4, 0u);
+    HostDirSrc dsrc;
+    if (directed) dsrc.prog = *directed;
     for (uint64_t r = 0; r < nrows_s; ++r)
-        for (uint32_t x = 0; x < g.N; ++x)
-            if (!(slab[r * g.N + x] > 0.0f)) signs[r * g.nws + (x >> 5)] |= 1u << (x & 31);
+        for (uint32_t x = 0; x < g.N; ++x) {
+            const float v = directed ? dsrc.at(g, x, (uint32_t)(r % g.N), (uint32_t)(r / g.N)) : slab[r * g.N + x];
+            if (!(v > 0.0f)) signs[r * g.nws + (x >> 5)] |= 1u << (x & 31);
+        }
 
     McTables mt;
     if (isomc_build_tables(&mt)) return -1;
@@ -238,8 +272,40 @@ int list_model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const fl
     for (uint32_t b = 0; b < ctr; ++b)
         for (uint32_t j = 0; j < blkfill[b]; ++j) {
             const uint64_t k = (uint64_t)b * LIST_BLOCK + j;
-            emit_cell(g, src, et, L, A, k, ent[k], ent_yz[k], eid + j, LIST_BLOCK);
+            if (directed) emit_cell(g, dsrc, et, L, A, k, ent[k], ent_yz[k], eid + j, LIST_BLOCK);
+            else emit_cell(g, src, et, L, A, k, ent[k], ent_yz[k], eid + j, LIST_BLOCK);
         }
+    return 0;
+}
+
+int list_model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const float *slab, uint32_t n_warps, uint32_t seed,
+                       uint32_t vofs, uint32_t cap_blocks, float *xyz, uint64_t cap_v, uint32_t *idx, uint64_t cap_t,
+                       uint64_t *out_totals) {
+    return model_extract(size, z_begin, z_end, slab, nullptr, n_warps, seed, vofs, cap_blocks, xyz, cap_v, idx, cap_t, out_totals);
+}
+
+/* MarchingCubes<Directed> over an implicit tree (whole lattice): the list kernels' source with the Directed host source */
+int list_model_extract_directed(uint32_t size, const isomc_sdf_node *prog, uint32_t n_nodes, uint32_t n_warps, uint32_t seed,
+                                uint32_t cap_blocks, float *xyz, uint64_t cap_v, uint32_t *idx, uint64_t cap_t, uint64_t *out_totals) {
+    SdfProgram P;
+    memset(&P, 0, sizeof P);
+    if (n_nodes > ISOMC_SDF_MAX_NODES) return -1;
+    memcpy(P.nodes, prog, n_nodes * sizeof(isomc_sdf_node));
+    P.n = n_nodes;
+    return model_extract(size, 0, size, nullptr, &P, n_warps, seed, 0, cap_blocks, xyz, cap_v, idx, cap_t, out_totals);
+}
+
+/* VectorSource::sample_vector through the device evaluator's source, on the host */
+int list_model_sample_vector(const isomc_sdf_node *prog, uint32_t n_nodes, const float *xyz, uint64_t n, float *out) {
+    SdfProgram P;
+    memset(&P, 0, sizeof P);
+    if (n_nodes > ISOMC_SDF_MAX_NODES) return -1;
+    memcpy(P.nodes, prog, n_nodes * sizeof(isomc_sdf_node));
+    P.n = n_nodes;
+    for (uint64_t i = 0; i < n; ++i) {
+        const Vec3f v = sdf_eval_vec(P, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
+    }
     return 0;
 }
 

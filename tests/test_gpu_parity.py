@@ -513,3 +513,21 @@ def test_interleaved_normals_match_oracle(iso, oracle):
             assert same.all(), "%s eps=%g: %d normal components differ" % (name, eps, int((~same).sum()))
     with pytest.raises(TypeError):
         iso.IndexedInterleavedNormals([], [], iso.Sampler(iso.Sphere(.3)))     # no CentralDifference: not a device path
+
+
+def test_directed_marching_cubes_matches_oracle(iso, oracle):
+    """MarchingCubes<Directed> (reference src/distance.rs:72-104 + the shapes' sample_vector): indices and vertex bits
+    identical to the restated reference; the restatement's sample_vector is pinned by the reference's own unit tests"""
+    for name, size in (("sphere03", 32), ("torus", 64), ("csgA", 64), ("csgB", 64), ("nested", 100), ("cylinder", 65),
+                       ("prism", 33), ("torus_origin", 128), ("csgA", 256)):
+        oxyz, oidx, oact = oracle.extract_sdf_directed(size, oracle_prog(name))
+        mc = iso.MarchingCubes(size, distance="directed")
+        for _ in range(2):
+            sink = iso.ArrayMesh()
+            mc.extract(iso.Sampler(iso_source(name)), sink)
+            assert mesh_diff(sink.vertices.ravel(), sink.indices.ravel(), oxyz, oidx, POS_TOL) == "", (name, size)
+            assert mc.counts()[2] == oact
+        mc.close()
+    with pytest.raises(TypeError):
+        mc = iso.MarchingCubes(8, distance="directed")
+        mc.extract_device(iso.DenseGrid(np.zeros((9, 8, 8), np.float32)))

@@ -28,6 +28,9 @@ def model():
     lib = C.CDLL(str(SO))
     lib.list_model_extract.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.list_model_extract_directed.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                                C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.list_model_sample_vector.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
     return lib
 
 
@@ -132,3 +135,37 @@ def test_model_list_overflow_is_reported(model, oracle):
     assert rc == 1 and tot[3] == oact and tot[4] > 8     # totals stay right, the host can size the list and re-run
     rc, xyz, idx, tot2 = run_model(model, size, grid, cap_blocks=tot[4])
     assert rc == 0 and tot2[:4] == tot[:4]
+
+
+DIRECTED_SHAPES = ["sphere03", "torus", "csgA", "csgB", "prism", "cylinder", "nested", "torus_origin"]
+
+
+@pytest.mark.parametrize("name", DIRECTED_SHAPES)
+def test_device_vector_evaluator_matches_oracle_bitwise(model, oracle, name):
+    """sdf_eval_vec (the device's VectorSource::sample_vector, run on the host) against the C restatement: random points
+    plus lattice points (exact zeros, points on the axes), every component bit for bit (NaN where both are NaN)"""
+    prog = oracle_prog(name)
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-0.2, 1.2, (20000, 3)).astype(np.float32)
+    lat = np.stack(np.meshgrid(*[np.arange(17, dtype=np.float32) / np.float32(16)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    pts = np.concatenate([pts, lat, lat - np.float32(0.5)]).astype(np.float32)
+    want = oracle.sample_sdf_vector(prog, pts)
+    got = np.zeros_like(want)
+    assert model.list_model_sample_vector(prog.ctypes.data, len(prog), pts.ctypes.data, len(pts), got.ctypes.data) == 0
+    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), "%d components differ, first at point %s" % (int((~same).sum()), pts[np.argwhere(~same)[0][0]])
+
+
+@pytest.mark.parametrize("name,size", [("sphere03", 32), ("torus", 40), ("csgA", 48), ("csgB", 33), ("torus_origin", 64), ("nested", 36)])
+def test_model_directed_extract_matches_oracle(model, oracle, name, size):
+    """MarchingCubes<Directed>: the list kernels' source with the Directed source against the restated reference"""
+    prog = oracle_prog(name)
+    oxyz, oidx, oact = oracle.extract_sdf_directed(size, prog)
+    cap_v, cap_t = len(oxyz) // 3 + 64, len(oidx) // 3 + 64
+    xyz = np.full(3 * cap_v, np.nan, np.float32)
+    idx = np.full(3 * cap_t, 0xFFFFFFFF, np.uint32)
+    tot = np.zeros(6, np.uint64)
+    rc = model.list_model_extract_directed(size, prog.ctypes.data, len(prog), 5, 3, 4096, xyz.ctypes.data, cap_v, idx.ctypes.data, cap_t,
+                                           tot.ctypes.data)
+    assert rc == 0 and int(tot[3]) == oact
+    assert mesh_diff(xyz[:3 * int(tot[0])], idx[:3 * int(tot[2])], oxyz, oidx) == ""

@@ -167,3 +167,68 @@ def test_central_difference_normals_oracle(oracle):
     # a larger epsilon is accurate
     out2 = oracle.interleaved_normals_cd(inner, xyz, 0.001, [(.5, .5, .5)])
     assert np.abs(out2[:, 3:] - want).max() < 1e-3
+
+
+def test_directed_sample_vector_known_answers(oracle):
+    """the reference's exact-equality unit tests of VectorSource::sample_vector (sphere.rs:78-93, torus.rs:124-155,
+    cylinder.rs:101-124, rectangular_prism.rs:95-115, csg.rs:126-136,157-167) pin the Directed restatement"""
+    O = oracle
+    MAX = np.finfo(np.float32).max
+    f = np.float32
+
+    def sv(nodes, p):
+        return tuple(O.sample_sdf_vector(O.program(nodes), [p])[0].tolist())
+
+    sph = [(O.SPHERE, 2.0)]
+    assert sv(sph, (0, 0, 0)) == (-2.0, -2.0, -2.0)
+    assert sv(sph, (2, 0, 0)) == (0.0, 0.0, 0.0)
+    assert sv(sph, (0, 0, 8)) == (MAX, MAX, 6.0)
+    assert sv(sph, (8, 0, 0)) == (6.0, MAX, MAX)
+    tor = [(O.TORUS, 8.0, 2.0)]
+    assert sv(tor, (0, 0, 0)) == (6.0, 6.0, MAX)
+    assert sv(tor, (8, 0, 0)) == (-2.0, -2.0, -2.0)
+    assert sv(tor, (10, 0, 0)) == (0.0, 0.0, 0.0)
+    assert sv(tor, (12, 0, 0)) == (2.0, MAX, MAX)
+    assert sv(tor, (12, 12, 0)) == (MAX, MAX, MAX)
+    v = float(f(9.0) - np.sqrt(f(10.0 * 10.0 - 9.0 * 9.0)))
+    assert sv(tor, (9, 9, 0)) == (v, v, MAX)
+    v = float(np.sqrt(f(6.0 * 6.0 - 2.0 * 2.0)) - f(2.0))
+    assert sv(tor, (2, 2, 0)) == (v, v, MAX)
+    assert sv(tor, (8, 0, 8)) == (MAX, MAX, 6.0)
+    cyl = [(O.CYLINDER, 2.0, 4.0)]
+    assert sv(cyl, (0, 0, 0)) == (-2.0, -2.0, -4.0)
+    assert sv(cyl, (0, 0, 1)) == (-2.0, -2.0, -3.0)
+    v = float(f(1.0) - np.sqrt(f(4.0) - f(1.0)))
+    assert sv(cyl, (1, 1, 1)) == (v, v, -3.0)
+    assert sv(cyl, (2, 0, 4)) == (0.0, 0.0, 0.0)
+    assert sv(cyl, (0, 0, 8)) == (MAX, MAX, 4.0)
+    assert sv(cyl, (8, 0, 0)) == (6.0, MAX, MAX)
+    pri = [(O.PRISM, 1.0, 2.0, 4.0)]
+    assert sv(pri, (0, 0, 0)) == (-1.0, -2.0, -4.0)
+    assert sv(pri, (1, 2, 4)) == (0.0, 0.0, 0.0)
+    assert sv(pri, (0, 0, 8)) == (MAX, MAX, 4.0)
+    assert sv(pri, (8, 0, 0)) == (7.0, MAX, MAX)
+    assert sv(pri, (8, 8, 8)) == (MAX, MAX, MAX)
+    a, b = (O.PRISM, 4.0, 4.0, 1.0), (O.PRISM, 2.0, 2.0, 4.0)
+    uni = [a, b, (O.UNION,)]
+    assert sv(uni, (0, 0, 0)) == (-4.0, -4.0, -4.0)
+    assert sv(uni, (4, 4, 1)) == (0.0, 0.0, 0.0)
+    assert sv(uni, (0, 0, 8)) == (MAX, MAX, 4.0)
+    assert sv(uni, (8, 0, 0)) == (4.0, MAX, MAX)
+    inter = [a, b, (O.INTERSECTION,)]
+    assert sv(inter, (0, 0, 0)) == (-2.0, -2.0, -1.0)
+    assert sv(inter, (2, 2, 1)) == (0.0, 0.0, 0.0)
+    assert sv(inter, (0, 0, 8)) == (MAX, MAX, 7.0)
+    assert sv(inter, (8, 0, 0)) == (6.0, MAX, MAX)
+
+
+def test_directed_extract_oracle_sanity(oracle):
+    """MarchingCubes<Directed> restatement: a closed surface near the Signed one (same shape, different distance field)"""
+    from helpers import oracle_prog, mesh_invariants
+    for name in ("sphere03", "torus", "csgB"):
+        xyz, idx, act = oracle.extract_sdf_directed(32, oracle_prog(name))
+        sxyz, sidx, sact = oracle.extract_sdf(32, oracle_prog(name))
+        assert len(idx) > 0 and act > 0
+        facts = mesh_invariants(xyz, idx, closed=False)
+        assert facts["directed_edge_dups"] == 0
+        assert abs(len(idx) - len(sidx)) < 0.2 * len(sidx)          # same surface, slightly different cell set at most
