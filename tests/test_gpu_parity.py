@@ -531,3 +531,25 @@ def test_directed_marching_cubes_matches_oracle(iso, oracle):
     with pytest.raises(TypeError):
         mc = iso.MarchingCubes(8, distance="directed")
         mc.extract_device(iso.DenseGrid(np.zeros((9, 8, 8), np.float32)))
+
+
+def test_chunked_driver_overlaps_small_extracts(iso, oracle):
+    """ChunkedMarchingCubes: many 32^3 chunks in flight on independent handles/streams; every chunk's mesh is the plain
+    API's (= the oracle's), in submission order"""
+    size = 32
+    offsets = [(0.3 + 0.05 * i, 0.5, 0.45 + 0.01 * i) for i in range(13)]
+    sources = [iso.Translate(o, iso.Union(iso.Sphere(0.2), iso.Torus(0.25, 0.08))) for o in offsets]
+    want = []
+    for o in offsets:
+        prog = oracle.program([(oracle.TRANSLATE_PUSH,) + o, (oracle.SPHERE, .2), (oracle.TORUS, .25, .08), (oracle.UNION,), (oracle.TRANSLATE_POP,)])
+        want.append(oracle.extract_sdf(size, prog))
+    drv = iso.ChunkedMarchingCubes(size, n_inflight=4)
+    for _ in range(2):
+        got = drv.extract_many([iso.Sampler(s) for s in sources])
+        assert len(got) == len(want)
+        for (xyz, idx), (oxyz, oidx, _) in zip(got, want):
+            assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    seen = []
+    drv.extract_many(sources[:5], deliver=lambda i, xyz, idx: seen.append((i, len(idx))))
+    assert [i for i, _ in seen] == [0, 1, 2, 3, 4] and all(n == len(w[1]) for (_, n), w in zip(seen, want))
+    drv.close()
