@@ -1,18 +1,23 @@
 /*
- * isomc_kernels.cu -- the sm_100a kernels of the MarchingCubes extract path.
+ * isomc_kernels.cu -- sm_100a kernels of the MarchingCubes extract path: the two kernels every path shares, and the
+ * older "brick" form of output sizing and emission (ISOMC_EMIT=brick; the default is the active-cell-list form in
+ * isomc_list_kernels.cu, which replaced it: profiles/r01_history.md).
  *
- * Pipeline (one stream, no host round trip in steady state):
+ * Shared (one stream, no host round trip in steady state):
  *
  *   K1 k_sign_vec4 / k_sign<Src>
  *                    sample -> inside bit.  One bit per lattice point (`!(v > 0)`,
  *                    marching_cubes_impl.rs:32 / distance.rs:52-54), 32 per word.  Grid sources
  *                    stream every f32 exactly once as float4s (HBM bound); implicit sources evaluate
- *                    the SDF program instead of loading.
+ *                    the SDF program instead of loading (Directed: outside iff any component > 0, distance.rs:77-80).
+ *   K3 k_scan_rows   exclusive scan over cell rows in (z, y) order (+ totals, list marks); causal in z.
+ *
+ * Brick path:
+ *
  *   K2 k_count       warp-autonomous, lane per 32-cell segment: bit-parallel classification.
  *                    Crossed-edge masks are XORs of sign words, the "edges this cell creates" count
  *                    is a bit-sliced sum of the owned masks, triangle counts come from ntri[ci'] for
  *                    active cells only.  Writes within-row exclusive prefixes and row totals.
- *   K3 k_scan_rows   exclusive scan over cell rows in (z, y) order (+ totals); causal in z.
  *   K4 k_emit        warp-autonomous bricks of 32x4x4 cells: flat cell and triangle lists, 16-bit
  *                    id planes in shared memory (edge ownership replaces the reference's HashMap
  *                    index cache, index_cache.rs / mesh.rs:240-251); writes u32 indices in reference

@@ -1,5 +1,7 @@
 /*
- * isomc_points.cu -- PointCloud extraction (reference src/point_cloud.rs:50-63) on the sign words:
+ * isomc_points.cu -- the crate's other sinks of the same traversal: PointCloud extraction and central-difference normals.
+ *
+ * PointCloud (reference src/point_cloud.rs:50-63) on the sign words:
  * every active cell (cube index neither 0 nor 255) emits the midpoint of its corners 0 and 6,
  * `corners[0].lerp(corners[6], 0.5)` (src/math/vector.rs:325-333), in (z, y, x) cell order.
  *
