@@ -280,7 +280,7 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
         const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
         if (piped) CU(h, cudaStreamWaitEvent(st, h->ev_chunk[c], 0));
         if (h->list_mode) {
-            CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, st));
+            CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, h->ticket + c, l0, l1, h->sms, st));
         } else {
             CU(h, isomc_launch_count(g, h->signs, h->tabs, h->segpre, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, 8, st));
         }
@@ -683,7 +683,7 @@ int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, 
             CU(h, cudaStreamWaitEvent(st, h->ev_in[c], 0));
             CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, row0, row1, h->sms, 8, st));
             if (h->list_mode)
-                CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, st));
+                CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, h->ticket + c, l0, l1, h->sms, st));
             else
                 CU(h, isomc_launch_count(g, h->signs, h->tabs, h->segpre, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, 8, st));
             CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, h->list_mode ? h->L.ctr : nullptr,

@@ -367,6 +367,7 @@ struct Warp {
 uint32_t isomc_emu_shfl(void *emu, uint32_t lane, uint32_t v, uint32_t src);
 void isomc_emu_sync(void *emu, uint32_t lane);
 uint32_t isomc_emu_atomic_add_u32(uint32_t *p, uint32_t v);
+uint32_t isomc_emu_next_task(uint32_t *ticket); /* the model deals the tasks out to its emulated warps itself */
 void isomc_emu_atomic_add_u64(unsigned long long *p, unsigned long long v);
 #endif
 
@@ -715,13 +716,28 @@ ISOMC_HD void pair_enqueue(const Warp &w, SegQueue &Q, CountState &S, uint32_t m
     w_sync(w);
 }
 
-/* One warp's share of cell rows [row0, row1): warp gwarp of nwarps.  Every lane scans TWO neighbouring segments.
+/* consecutive passes a warp takes per ticket: neighbouring rows end up next to each other in the list, so that the
+ * emission's look-ups of the -y neighbours (and the scan's own sign-word loads) hit lines that are already close */
+constexpr uint32_t COUNT_TASK_PASSES = 8;
+
+ISOMC_HD uint32_t next_task(const Warp &w, uint32_t *ticket) {
+    uint32_t t = 0;
+#if !defined(__CUDA_ARCH__) && defined(ISOMC_HOST_MODEL)
+    if (w.lane == 0) t = isomc_emu_next_task(ticket);
+#else
+    if (w.lane == 0) t = hd_atomic_add(ticket, 1u);
+#endif
+    return w_shfl(w, t, 0);
+}
+
+/* One warp's share of cell rows [row0, row1): tasks of COUNT_TASK_PASSES consecutive passes, handed out by a ticket
+ * counter.  Every lane scans TWO neighbouring segments.
  * WIDE = rows of more than 64 segments (a pass is a 64-segment chunk of one row); else a pass covers 32 >> gshift whole
  * rows of 1 << gshift lanes (segment pairs) each. */
 template <bool WIDE>
 ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs, const uint8_t *s_ntri, const uint8_t *nth8,
-                              const ListBufs &L, const CountOut &out, uint32_t gshift, uint32_t row0, uint32_t row1, uint32_t gwarp,
-                              uint32_t nwarps, SegQueue &Q) {
+                              const ListBufs &L, const CountOut &out, uint32_t gshift, uint32_t row0, uint32_t row1, uint32_t *ticket,
+                              SegQueue &Q) {
     const uint32_t lane = w.lane;
     CountState S;
     S.enq = S.deq = 0;
@@ -731,7 +747,8 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
         const uint32_t G = 1u << gshift, rpw = 32u >> gshift, sub = lane >> gshift, j = lane & (G - 1);
         const uint32_t gmask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << (sub << gshift);
         const uint32_t niter = (row1 - row0 + rpw - 1) / rpw;
-        for (uint32_t it = gwarp; it < niter; it += nwarps) {
+        for (uint32_t task = next_task(w, ticket); task * COUNT_TASK_PASSES < niter; task = next_task(w, ticket))
+        for (uint32_t it = task * COUNT_TASK_PASSES; it < niter && it < (task + 1) * COUNT_TASK_PASSES; ++it) {
             const uint32_t row = row0 + it * rpw + sub;
             const bool va = row < row1 && 2 * j < g.nsegx, vb = row < row1 && 2 * j + 1 < g.nsegx;
             uint32_t wa[8], wb[8];
@@ -754,7 +771,9 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
             while (S.enq - S.deq >= 32) count_flush(w, g, s_ntri, nth8, L, out, Q, S, 32);
         }
     } else {
-        for (uint32_t row = row0 + gwarp; row < row1; row += nwarps) {
+        const uint32_t nrow = row1 - row0;
+        for (uint32_t task = next_task(w, ticket); task * COUNT_TASK_PASSES < nrow; task = next_task(w, ticket))
+        for (uint32_t row = row0 + task * COUNT_TASK_PASSES; row < row1 && row < row0 + (task + 1) * COUNT_TASK_PASSES; ++row) {
             const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40);
             bool row_has = false;
             uint32_t last_seq = 0;

@@ -53,8 +53,8 @@ cudaError_t isomc_launch_synth(const SynthParams &sp, uint32_t size, uint32_t z_
 /* active-cell-list path (isomc_list_kernels.cu): count + list build, emission incl. vertex positions */
 uint32_t isomc_count_list_max_warps(int sms);
 cudaError_t isomc_launch_count_list(const Geo &g, const uint32_t *signs, const McTables *tabs, const ListBufs &L, uint32_t *rowV,
-                                    uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot, uint32_t lz0, uint32_t lz1,
-                                    int sms, cudaStream_t st);
+                                    uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot, uint32_t *ticket /* zeroed */,
+                                    uint32_t lz0, uint32_t lz1, int sms, cudaStream_t st);
 /* list blocks [*blk_first, *blk_end) (device pointers; blk_first == NULL: from block 0) */
 cudaError_t isomc_launch_emit_list_grid(const Geo &g, const float *d_grid, const ListBufs &L, const EmitTab *tab,
                                         const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,

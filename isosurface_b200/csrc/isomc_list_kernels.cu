@@ -28,7 +28,8 @@ namespace {
 /* cell rows [row0, row1); the body is count_list_warp() of isomc_cell.cuh (shared with the host model) */
 template <bool WIDE, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_count_list(Geo g, const uint32_t *__restrict__ signs, const uint8_t *__restrict__ ntri_g,
-                                                    ListBufs L, CountOut out, uint32_t gshift, uint32_t row0, uint32_t row1) {
+                                                    ListBufs L, CountOut out, uint32_t gshift, uint32_t row0, uint32_t row1,
+                                                    uint32_t *ticket) {
     __shared__ uint8_t s_ntri[256];
     __shared__ SegQueue s_q[8];
     __shared__ uint8_t s_nth8[256 * 8];
@@ -36,8 +37,7 @@ __global__ void __launch_bounds__(256, MINB) k_count_list(Geo g, const uint32_t 
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5;
     const Warp w{threadIdx.x & 31u, nullptr};
-    count_list_warp<WIDE>(w, g, signs, s_ntri, s_nth8, L, out, gshift, row0, row1, blockIdx.x * (blockDim.x >> 5) + warp,
-                          gridDim.x * (blockDim.x >> 5), s_q[warp]);
+    count_list_warp<WIDE>(w, g, signs, s_ntri, s_nth8, L, out, gshift, row0, row1, ticket, s_q[warp]);
 }
 
 /* list blocks [*blk_first, *blk_end): one CTA per block, one lane per entry */
@@ -127,17 +127,17 @@ uint32_t isomc_count_list_max_warps(int sms) { return (uint32_t)(sms * 6 * 8); }
 
 template <bool WIDE>
 static void launch_count_list_v(uint32_t grid, cudaStream_t st, const Geo &g, const uint32_t *signs, const uint8_t *ntri,
-                                const ListBufs &L, const CountOut &out, uint32_t gshift, uint32_t row0, uint32_t row1) {
+                                const ListBufs &L, const CountOut &out, uint32_t gshift, uint32_t row0, uint32_t row1, uint32_t *ticket) {
     switch (count_list_minb()) {
-    default: k_count_list<WIDE, 4><<<grid, 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1); break;
-    case 6: k_count_list<WIDE, 6><<<grid, 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1); break;
-    case 5: k_count_list<WIDE, 5><<<grid, 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1); break;
+    default: k_count_list<WIDE, 4><<<grid, 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1, ticket); break;
+    case 6: k_count_list<WIDE, 6><<<grid, 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1, ticket); break;
+    case 5: k_count_list<WIDE, 5><<<grid, 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1, ticket); break;
     }
 }
 
 cudaError_t isomc_launch_count_list(const Geo &g, const uint32_t *signs, const McTables *tabs, const ListBufs &L, uint32_t *rowV,
-                                    uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot, uint32_t lz0, uint32_t lz1,
-                                    int sms, cudaStream_t st) {
+                                    uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot, uint32_t *ticket, uint32_t lz0,
+                                    uint32_t lz1, int sms, cudaStream_t st) {
     const uint32_t npair = (g.nsegx + 1) / 2; /* lanes per row: every lane scans two neighbouring segments */
     uint32_t gshift = 0;
     while ((1u << gshift) < npair && gshift < 5) ++gshift;
@@ -148,9 +148,9 @@ cudaError_t isomc_launch_count_list(const Geo &g, const uint32_t *signs, const M
     if (npair <= 32) {
         const uint32_t rpw = 32u >> gshift;
         const uint64_t warps = ((uint64_t)(row1 - row0) + rpw - 1) / rpw;
-        launch_count_list_v<false>(grid_for(warps, sms, 8, per_sm), st, g, signs, ntri, L, out, gshift, row0, row1);
+        launch_count_list_v<false>(grid_for(warps, sms, 8, per_sm), st, g, signs, ntri, L, out, gshift, row0, row1, ticket);
     } else {
-        launch_count_list_v<true>(grid_for(row1 - row0, sms, 8, per_sm), st, g, signs, ntri, L, out, gshift, row0, row1);
+        launch_count_list_v<true>(grid_for(row1 - row0, sms, 8, per_sm), st, g, signs, ntri, L, out, gshift, row0, row1, ticket);
     }
     return cudaGetLastError();
 }

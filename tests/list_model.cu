@@ -53,7 +53,8 @@ struct WarpJob {
     const uint8_t *ntri, *nth8;
     ListBufs L;
     CountOut out;
-    uint32_t gshift, row0, row1, gwarp, nwarps;
+    uint32_t gshift, row0, row1;
+    uint32_t *ticket;
     SegQueue Q;
 };
 WarpJob *g_job = nullptr;
@@ -61,8 +62,8 @@ WarpJob *g_job = nullptr;
 void lane_main(int lane) {
     WarpJob &J = *g_job;
     const Warp w{(uint32_t)lane, (void *)g_emu};
-    if (J.wide) count_list_warp<true>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.gwarp, J.nwarps, J.Q);
-    else count_list_warp<false>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.gwarp, J.nwarps, J.Q);
+    if (J.wide) count_list_warp<true>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.ticket, J.Q);
+    else count_list_warp<false>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.ticket, J.Q);
     g_emu->done[lane] = true;
 }
 
@@ -147,6 +148,14 @@ uint32_t isomc_emu_shfl(void *emu, uint32_t lane, uint32_t v, uint32_t src) {
 }
 void isomc_emu_sync(void *emu, uint32_t lane) { emu_barrier((Emu *)emu, lane); }
 uint32_t isomc_emu_atomic_add_u32(uint32_t *p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
+/* tasks of the emulated warp that is running (a shuffled share of all tasks); 0xFFFFFFFF = none left */
+static std::vector<uint32_t> g_tasks;
+uint32_t isomc_emu_next_task(uint32_t *) {
+    if (g_tasks.empty()) return 0xFFFFFFFFu;
+    const uint32_t t = g_tasks.back();
+    g_tasks.pop_back();
+    return t;
+}
 void isomc_emu_atomic_add_u64(unsigned long long *p, unsigned long long v) { *p += v; }
 
 extern "C" {
@@ -214,12 +223,24 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
     }
     std::vector<uint8_t> nth8(256 * 8);
     for (uint32_t m = 0; m < 256; ++m) nth8_fill(nth8.data(), m);
+    /* on the GPU a ticket counter hands tasks of COUNT_TASK_PASSES passes to whichever warp asks next; here every task goes
+     * to a random emulated warp, and the warps run one after the other in shuffled order */
+    uint32_t ticket = 0;
+    const uint32_t npass = npair > 32 ? (uint32_t)nrows_c : (uint32_t)((nrows_c + (32u >> gshift) - 1) / (32u >> gshift));
+    const uint32_t ntask = (npass + COUNT_TASK_PASSES - 1) / COUNT_TASK_PASSES;
+    std::vector<std::vector<uint32_t>> share(n_warps);
+    for (uint32_t t = 0; t < ntask; ++t) {
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        share[(st >> 33) % n_warps].push_back(t);
+    }
     static Emu E;
     for (uint32_t wi = 0; wi < n_warps; ++wi) {
+        g_tasks = share[order[wi]];
+        std::reverse(g_tasks.begin(), g_tasks.end()); /* increasing task order within a warp, as a ticket counter gives */
         WarpJob J;
         J.wide = npair > 32;
         J.g = g; J.signs = signs.data(); J.ntri = mt.ntri; J.nth8 = nth8.data(); J.L = L; J.out = out;
-        J.gshift = gshift; J.row0 = 0; J.row1 = (uint32_t)nrows_c; J.gwarp = order[wi]; J.nwarps = n_warps;
+        J.gshift = gshift; J.row0 = 0; J.row1 = (uint32_t)nrows_c; J.ticket = &ticket;
         run_warp(E, J);
     }
 
