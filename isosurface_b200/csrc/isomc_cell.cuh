@@ -718,7 +718,12 @@ ISOMC_HD void pair_enqueue(const Warp &w, SegQueue &Q, CountState &S, uint32_t m
 
 /* consecutive passes a warp takes per ticket: neighbouring rows end up next to each other in the list, so that the
  * emission's look-ups of the -y neighbours (and the scan's own sign-word loads) hit lines that are already close */
-constexpr uint32_t COUNT_TASK_PASSES = 8;
+#ifndef ISOMC_COUNT_LONG_TASK_AT
+#define ISOMC_COUNT_LONG_TASK_AT (1u << 20) /* (the host model is also built with a small value to cover the long-task branch) */
+#endif
+ISOMC_HD uint32_t count_task_passes(uint32_t n_passes) { /* short tasks balance small lattices, long ones amortise the ticket */
+    return n_passes > ISOMC_COUNT_LONG_TASK_AT ? 64u : 8u;
+}
 
 ISOMC_HD uint32_t next_task(const Warp &w, uint32_t *ticket) {
     uint32_t t = 0;
@@ -730,7 +735,7 @@ ISOMC_HD uint32_t next_task(const Warp &w, uint32_t *ticket) {
     return w_shfl(w, t, 0);
 }
 
-/* One warp's share of cell rows [row0, row1): tasks of COUNT_TASK_PASSES consecutive passes, handed out by a ticket
+/* One warp's share of cell rows [row0, row1): tasks of count_task_passes() consecutive passes, handed out by a ticket
  * counter.  Every lane scans TWO neighbouring segments.
  * WIDE = rows of more than 64 segments (a pass is a 64-segment chunk of one row); else a pass covers 32 >> gshift whole
  * rows of 1 << gshift lanes (segment pairs) each. */
@@ -746,9 +751,9 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
     if (!WIDE) {
         const uint32_t G = 1u << gshift, rpw = 32u >> gshift, sub = lane >> gshift, j = lane & (G - 1);
         const uint32_t gmask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << (sub << gshift);
-        const uint32_t niter = (row1 - row0 + rpw - 1) / rpw;
-        for (uint32_t task = next_task(w, ticket); task * COUNT_TASK_PASSES < niter; task = next_task(w, ticket))
-        for (uint32_t it = task * COUNT_TASK_PASSES; it < niter && it < (task + 1) * COUNT_TASK_PASSES; ++it) {
+        const uint32_t niter = (row1 - row0 + rpw - 1) / rpw, P = count_task_passes(niter);
+        for (uint32_t task = next_task(w, ticket); task * P < niter; task = next_task(w, ticket))
+        for (uint32_t it = task * P; it < niter && it < (task + 1) * P; ++it) {
             const uint32_t row = row0 + it * rpw + sub;
             const bool va = row < row1 && 2 * j < g.nsegx, vb = row < row1 && 2 * j + 1 < g.nsegx;
             uint32_t wa[8], wb[8];
@@ -771,9 +776,9 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
             while (S.enq - S.deq >= 32) count_flush(w, g, s_ntri, nth8, L, out, Q, S, 32);
         }
     } else {
-        const uint32_t nrow = row1 - row0;
-        for (uint32_t task = next_task(w, ticket); task * COUNT_TASK_PASSES < nrow; task = next_task(w, ticket))
-        for (uint32_t row = row0 + task * COUNT_TASK_PASSES; row < row1 && row < row0 + (task + 1) * COUNT_TASK_PASSES; ++row) {
+        const uint32_t nrow = row1 - row0, P = count_task_passes(nrow);
+        for (uint32_t task = next_task(w, ticket); task * P < nrow; task = next_task(w, ticket))
+        for (uint32_t row = row0 + task * P; row < row1 && row < row0 + (task + 1) * P; ++row) {
             const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40);
             bool row_has = false;
             uint32_t last_seq = 0;

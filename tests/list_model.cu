@@ -223,11 +223,11 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
     }
     std::vector<uint8_t> nth8(256 * 8);
     for (uint32_t m = 0; m < 256; ++m) nth8_fill(nth8.data(), m);
-    /* on the GPU a ticket counter hands tasks of COUNT_TASK_PASSES passes to whichever warp asks next; here every task goes
+    /* on the GPU a ticket counter hands tasks of count_task_passes() passes to whichever warp asks next; here every task goes
      * to a random emulated warp, and the warps run one after the other in shuffled order */
     uint32_t ticket = 0;
     const uint32_t npass = npair > 32 ? (uint32_t)nrows_c : (uint32_t)((nrows_c + (32u >> gshift) - 1) / (32u >> gshift));
-    const uint32_t ntask = (npass + COUNT_TASK_PASSES - 1) / COUNT_TASK_PASSES;
+    const uint32_t ntask = (npass + count_task_passes(npass) - 1) / count_task_passes(npass);
     std::vector<std::vector<uint32_t>> share(n_warps);
     for (uint32_t t = 0; t < ntask; ++t) {
         st = st * 6364136223846793005ull + 1442695040888963407ull;

@@ -19,13 +19,26 @@ SO = ROOT / "tests" / "_build" / "liblist_model.so"
 DEPS = [SRC] + [ROOT / "isosurface_b200" / "csrc" / n for n in ("isomc_cell.cuh", "isomc_device.cuh", "isomc_tables.h", "isomc_case_table.h")]
 
 
+def _load(so, extra=()):
+    so.parent.mkdir(exist_ok=True)
+    if not so.exists() or any(d.stat().st_mtime > so.stat().st_mtime for d in DEPS):
+        subprocess.run(["nvcc", "-O2", "-std=c++17", "-arch=sm_100a", "-DISOMC_HOST_MODEL", *extra, "-Xcompiler",
+                        "-ffp-contract=off,-fPIC,-fno-fast-math", "-shared", "-o", str(so), str(SRC)], check=True)
+    lib = C.CDLL(str(so))
+    lib.list_model_extract.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def model_long_tasks():
+    """the same model with the 64-pass tasks of very large lattices switched on for anything above 64 passes"""
+    return _load(SO.with_name("liblist_model_long.so"), ("-DISOMC_COUNT_LONG_TASK_AT=64u",))
+
+
 @pytest.fixture(scope="module")
 def model():
-    SO.parent.mkdir(exist_ok=True)
-    if not SO.exists() or any(d.stat().st_mtime > SO.stat().st_mtime for d in DEPS):
-        subprocess.run(["nvcc", "-O2", "-std=c++17", "-arch=sm_100a", "-DISOMC_HOST_MODEL", "-Xcompiler",
-                        "-ffp-contract=off,-fPIC,-fno-fast-math", "-shared", "-o", str(SO), str(SRC)], check=True)
-    lib = C.CDLL(str(SO))
+    lib = _load(SO)
     lib.list_model_extract.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.list_model_extract_directed.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
@@ -125,6 +138,17 @@ def test_model_slabs_concatenate(model, oracle):
     rc1, x1, i1, t1 = run_model(model, size, grid, cut, size, vofs=t0[1])
     assert rc0 == 0 and rc1 == 0
     assert mesh_diff(np.concatenate([x0, x1]), np.concatenate([i0, i1]), oxyz, oidx) == ""
+
+
+@pytest.mark.parametrize("size,seed,n_warps", [(70, 7, 3), (33, 4, 9), (1060, 2, 5)])
+def test_model_long_tasks(model_long_tasks, oracle, size, seed, n_warps):
+    """the 64-pass tasks (lattices with more than 2^20 passes on the GPU) on small inputs"""
+    zc = 1 if size > 1000 else None
+    grid = noise(size, seed, z_layers=(zc + 1) if zc else None)
+    oxyz, oidx, oact = oracle.extract_grid(size, grid, z_cells=zc)
+    rc, xyz, idx, tot = run_model(model_long_tasks, size, grid, z_end=zc, n_warps=n_warps, seed=seed, cap_blocks=40000)
+    assert rc == 0 and tot[3] == oact
+    assert mesh_diff(xyz, idx, oxyz, oidx) == ""
 
 
 def test_model_list_overflow_is_reported(model, oracle):
