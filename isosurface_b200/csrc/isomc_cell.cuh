@@ -390,17 +390,6 @@ ISOMC_HD uint32_t w_shfl_up(const Warp &w, uint32_t v, uint32_t d) {
     return v;
 #endif
 }
-ISOMC_HD bool w_any(const Warp &w, bool pred) {
-#if defined(__CUDA_ARCH__)
-    return __any_sync(0xFFFFFFFFu, pred) != 0;
-#elif defined(ISOMC_HOST_MODEL)
-    uint32_t v = pred ? 1u : 0u;
-    for (uint32_t d = 1; d < 32; d <<= 1) v |= isomc_emu_shfl(w.emu, w.lane, v, w.lane ^ d);
-    return v != 0;
-#else
-    return pred;
-#endif
-}
 ISOMC_HD uint32_t w_ballot(const Warp &w, bool pred) {
 #if defined(__CUDA_ARCH__)
     return __ballot_sync(0xFFFFFFFFu, pred);
