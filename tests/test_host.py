@@ -88,3 +88,24 @@ def test_bases_from_totals():
     assert bases_from_totals(g, 0) == (0, 0, 0)
     assert bases_from_totals(g, 1) == (10, 7, 20)          # boundary = first vertex of rank 0's last layer
     assert bases_from_totals(g, 2) == (15, 11, 29)
+
+
+def test_new_host_side_argument_checks_need_no_gpu():
+    """argument validation of the widened API happens before any device call"""
+    import isosurface_b200 as iso
+    from isosurface_b200.source import find_central_difference
+    cd = iso.CentralDifference(iso.Sphere(0.3), 0.001)
+    assert find_central_difference(iso.Sampler(iso.Translate(0.5, cd))) is cd
+    assert find_central_difference(iso.Sampler(iso.Translate(0.5, iso.Sphere(0.3)))) is None
+    assert find_central_difference(iso.Union(cd, iso.Sphere(0.1))) is None      # only enclosing wrappers are looked through
+    with pytest.raises(TypeError):
+        iso.IndexedInterleavedNormals([], [], iso.Sampler(iso.Sphere(0.3)))
+    sink = iso.IndexedInterleavedNormals([], [], iso.Sampler(cd))
+    assert sink.central_difference.epsilon == 0.001
+    with pytest.raises(ValueError):
+        iso.MarchingCubes(32, distance="euclidean")
+    with pytest.raises(ValueError):
+        iso.ChunkedMarchingCubes(32, n_inflight=0)
+    # CentralDifference is transparent as a scalar source: same program as the tree it wraps
+    from isosurface_b200.source import encode_program
+    assert encode_program(iso.Translate(0.5, cd)).tobytes() == encode_program(iso.Translate(0.5, iso.Sphere(0.3))).tobytes()
