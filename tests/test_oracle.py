@@ -232,3 +232,29 @@ def test_directed_extract_oracle_sanity(oracle):
         facts = mesh_invariants(xyz, idx, closed=False)
         assert facts["directed_edge_dups"] == 0
         assert abs(len(idx) - len(sidx)) < 0.2 * len(sidx)          # same surface, slightly different cell set at most
+
+
+EXTRAS = json.loads((Path(__file__).parent / "golden" / "extras_hashes.json").read_text())
+
+
+def test_widened_rows_match_committed_golden_hashes(oracle):
+    """PointCloud, MarchingCubes<Directed> and interleaved central-difference normals against tests/golden/extras_hashes.json
+    (tools/gen_golden_extras.py): the restatements may not drift silently"""
+    from helpers import oracle_prog, sha
+    for g in EXTRAS["point_cloud"]:
+        if g["size"] <= 100:
+            pts = oracle.point_cloud_sdf(g["size"], oracle_prog(g["shape"]))
+            assert (len(pts) // 3, sha(pts, "<f4")) == (g["points"], g["sha_p"]), g
+    for g in EXTRAS["directed"]:
+        if g["size"] <= 65:
+            xyz, idx, act = oracle.extract_sdf_directed(g["size"], oracle_prog(g["shape"]))
+            assert (act, len(xyz) // 3, len(idx) // 3, sha(xyz, "<f4"), sha(idx, "<u4")) == \
+                (g["active_cells"], g["vertices"], g["triangles"], g["sha_v"], g["sha_i"]), g
+    O = oracle
+    inner = {"torus": [(O.TORUS, .25, .1)],
+             "csgA": [(O.SPHERE, .25), (O.PRISM, .2, .2, .2), (O.DIFFERENCE,), (O.CYLINDER, .02, .25), (O.UNION,)],
+             "csgB": [(O.SPHERE, .3), (O.PRISM, .2, .2, .2), (O.INTERSECTION,)]}
+    for g in EXTRAS["normals"]:
+        xyz, _, _ = O.extract_sdf(g["size"], oracle_prog(g["shape"]))
+        xyzn = O.interleaved_normals_cd(O.program(inner[g["shape"]]), xyz, g["epsilon"], [(.5, .5, .5)])
+        assert (len(xyzn), sha(xyzn, "<f4")) == (g["vertices"], g["sha_vn"]), g
