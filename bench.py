@@ -336,13 +336,14 @@ def run_ours(args):
         "gpu_launches": launches_per_step * args.steps,
     }
     # roofline of the dominant kernel and of the whole extract
-    # kernel names of the path in use: active-cell list (default) or the older brick kernels (ISOMC_EMIT=brick)
-    brick = os.environ.get("ISOMC_EMIT", "list") == "brick"
-    k_count, k_emit = ("k_count", "k_emit") if brick else ("k_count_list", "k_emit_list")
-    # k_emit_list writes vertices and triangles; in the brick path the interval covers k_emit + k_vertex
-    kern = {"k_sign": (prof[0], 4 * S / world), k_count: (prof[1], 0), "k_scan_rows": (prof[2], 0),
-            k_emit: (prof[3], (12 * V + 12 * T) / world)}
-    dom = max(("k_sign", k_emit), key=lambda k: kern[k][0])
+    # kernel names of the path in use: the tile path (default) or the older active-cell-list kernels (ISOMC_PATH=list)
+    tile = os.environ.get("ISOMC_PATH", "tile") != "list"
+    k_first, k_count, k_emit = ("k_tile_count", None, "k_tile_emit") if tile else ("k_sign", "k_count_list", "k_emit_list")
+    # k_tile_count / k_sign read every sample once; the emit kernels write vertices and triangles
+    kern = {k_first: (prof[0], 4 * S / world), "k_scan_rows": (prof[2], 0), k_emit: (prof[3], (12 * V + 12 * T) / world)}
+    if k_count:
+        kern[k_count] = (prof[1], 0)
+    dom = max((k_first, k_emit), key=lambda k: kern[k][0])
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
@@ -356,7 +357,7 @@ def run_ours(args):
                             "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": kern[dom][1], "ms_per_launch": kern[dom][0]}
         ach_all = b_alg / world / t_s / 1e9
-        line["roofline_extract"] = {"bound": "hbm", "scope": "whole extract (k_sign+%s+k_scan_rows+%s)" % (k_count, k_emit),
+        line["roofline_extract"] = {"bound": "hbm", "scope": "whole extract (%s)" % "+".join(kern),
                                     "achieved": ach_all * world, "per_gpu": ach_all, "peak": hbm_peak, "unit": "GB/s",
                                     "frac": ach_all / hbm_peak, "algorithmic_bytes": b_alg,
                                     "formula": "4*S + 12*V + 12*T"}
@@ -364,11 +365,12 @@ def run_ours(args):
         ops = SDF_OPS.get(field, 20)
         peak = 148 * 128 * 1.965e9 / 1e12
         ach = S * ops / (prof[0] * 1e-3) / 1e12 if prof[0] > 0 else 0.0
-        line["roofline"] = {"bound": "fp32", "kernel": "k_sign<SdfSrc>", "achieved": ach, "peak": peak, "unit": "Tlane-op/s",
+        line["roofline"] = {"bound": "fp32", "kernel": k_first + "<Sdf>", "achieved": ach, "peak": peak, "unit": "Tlane-op/s",
                             "frac": ach / peak, "traffic": None, "peak_source": "148 SM x 128 lanes x 1.965 GHz, non-FMA",
                             "ops_per_sample": ops}
-    line["kernels_ms"] = {"k_sign": prof[0], k_count: prof[1], "k_scan_rows": prof[2], k_emit: prof[3], "sum": prof[4]}
-    line["config"]["path"] = "brick kernels" if brick else "active-cell list"
+    line["kernels_ms"] = {k: v[0] for k, v in kern.items()}
+    line["kernels_ms"]["sum"] = prof[4]
+    line["config"]["path"] = "tile path (TMA-staged count, plane emission)" if tile else "active-cell list"
     line["clocks"] = clk.summary()
 
     # ---- e2e through the public API with HOST buffers (H2D of the grid + D2H of the mesh inside the timed region)

@@ -20,6 +20,7 @@
 #include "isomc_device.cuh"
 #include "isomc_kernels.h"
 #include "isomc_tables.h"
+#include "isomc_tile.cuh"
 
 namespace {
 
@@ -27,8 +28,10 @@ thread_local std::string g_create_error;
 
 enum SrcKind { SRC_NONE = 0, SRC_GRID = 1, SRC_SDF = 2 };
 constexpr int MAX_CHUNKS = 16;
-/* u32 after layerTot: emit tickets [MAX_CHUNKS], list block counter, list marks [MAX_CHUNKS + 1], chunk ends [2 * MAX_CHUNKS] */
-constexpr int AUX_WORDS = 4 * MAX_CHUNKS + 4;
+/* u32 after layerTot: emit tickets [MAX_CHUNKS], list block counter, list marks [MAX_CHUNKS + 1], chunk ends [2 * MAX_CHUNKS],
+ * tile path: block counters [2] (+ 2 pad), tickets of pass 1 [MAX_CHUNKS] and of pass 2 [MAX_CHUNKS] */
+constexpr int AUX_WORDS = 6 * MAX_CHUNKS + 8;
+constexpr int N_TOTALS = 16;
 
 }  // namespace
 
@@ -36,19 +39,21 @@ struct isomc {
     uint32_t size = 0, z_begin = 0, z_end = 0;
     int device = 0, sms = 148;
     Geo g{};
-    cudaStream_t own_stream = nullptr, stream = nullptr, stream2 = nullptr; /* stream2: odd z-chunks of the pipeline */
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_chunk[MAX_CHUNKS] = {};
-    uint32_t n_chunks = 1, chunk_l[MAX_CHUNKS + 1] = {}; /* cell layers [chunk_l[c], chunk_l[c+1]) */
-    bool pipeline = false; /* two-stream z-chunk pipeline: measured slower than the serial order (profiles/r01_history.md); ISOMC_PIPELINE=1 enables it */
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    uint32_t n_chunks = 1, chunk_l[MAX_CHUNKS + 1] = {}; /* cell layers [chunk_l[c], chunk_l[c+1]): one chunk, or the z-chunks of the streamed host extract */
     /* ISOMC_TIMELINE=1: timing events after every kernel, printed at finish (debugging the stream overlap) */
     bool timeline = false;
     std::vector<std::pair<std::string, cudaEvent_t>> tl;
     /* scratch */
-    uint32_t *signs = nullptr, *segpre = nullptr, *rowV = nullptr, *rowT = nullptr, *rowA = nullptr;
+    uint32_t *signs = nullptr, *rowV = nullptr, *rowT = nullptr, *rowA = nullptr;
     unsigned long long *layerTot = nullptr, *totals = nullptr; /* totals: 12 u64 */
     uint32_t *vofs = nullptr, *ticket = nullptr;
-    /* active-cell-list path (default; ISOMC_EMIT=brick selects the older brick kernels): isomc_cell.cuh */
-    bool list_mode = true;
+    /* tile path (default): isomc_tile.cuh.  ISOMC_PATH=list selects the older active-cell-list kernels (isomc_cell.cuh) */
+    bool tile_mode = true;
+    TileGeo tg{};
+    TileBufs TB{};
+    uint32_t *tile_tickets = nullptr; /* [MAX_CHUNKS] pass 1, [MAX_CHUNKS] pass 2 */
+    uint32_t *segA = nullptr;         /* PointCloud: per-segment prefixes (allocated on first use, with `signs`) */
     ListBufs L{};
     uint32_t *list_marks = nullptr; /* [c] = list blocks handed out before z-chunk c; [0] = 0 */
     EmitTab *etab = nullptr;
@@ -171,17 +176,36 @@ int32_t ensure_list_capacity(isomc *h, uint64_t blocks) {
     return ISOMC_OK;
 }
 
-/*
- * The extract is cut into a few z-chunks (multiples of the emission brick height).  Everything a chunk
- * needs comes from the chunks below it (the row scan is causal in z), which allows a two-stage pipeline:
- *
- *   stream2 (producer, HBM-bound):   sign(0) sign(1) sign(2) ...
- *   stream  (consumer, issue-bound): wait(sign(c)) -> count(c) -> scan(c) -> [emit(c) -> vertex(c)]   for c = 0, 1, ...
- *
- * sign(c) covers sample layers (l0, l1] (chunk 0 also layer 0), which is what count(c) and emit(c) read
- * beyond the lower chunks.  The sign kernel is launched with few CTAs per SM so that both stages stay
- * resident.  Nothing synchronises with the host.
- */
+/* tile path: entry list and crossing-parameter buffer, in blocks of ENT_BLOCK; grow-only, sized from the previous extract */
+int32_t ensure_tile_capacity(isomc *h, uint64_t eb, uint64_t tb) {
+    if (eb > 0xFFFFF0ull || tb > 0xFFFFF0ull)
+        return fail(h, ISOMC_ERR_OOM, "entry list of %llu / %llu blocks exceeds the 32-bit positions", (unsigned long long)eb, (unsigned long long)tb);
+    if (eb > h->TB.cap_eb) {
+        if (h->TB.ent) CU(h, cudaFree(h->TB.ent));
+        h->TB.ent = nullptr; h->TB.cap_eb = 0;
+        CU(h, cudaMalloc(&h->TB.ent, eb * ENT_BLOCK * sizeof(uint2)));
+        h->TB.cap_eb = (uint32_t)eb;
+    }
+    if (tb > h->TB.cap_tb) {
+        if (h->TB.tbuf) CU(h, cudaFree(h->TB.tbuf));
+        h->TB.tbuf = nullptr; h->TB.cap_tb = 0;
+        CU(h, cudaMalloc(&h->TB.tbuf, tb * ENT_BLOCK * sizeof(float)));
+        h->TB.cap_tb = (uint32_t)tb;
+    }
+    return ISOMC_OK;
+}
+/* blocks the counting warps may strand: one partly filled block per warp and space */
+uint64_t tile_stranded_blocks(const isomc *h) { return (uint64_t)h->sms * 4 * TILE_Y + 16; }
+
+/* sign words + per-segment scratch of the PointCloud path and the cube-index dump (the mesh path needs neither) */
+int32_t ensure_signs(isomc *h) {
+    const Geo &g = h->g;
+    const uint64_t nrows_s = (uint64_t)g.nsl * g.N, nrows_c = (uint64_t)g.ncl * g.ncx;
+    if (!h->signs) CU(h, cudaMalloc(&h->signs, (nrows_s * g.nws + 4) * sizeof(uint32_t)));
+    if (!h->segA) CU(h, cudaMalloc(&h->segA, (nrows_c * g.nsegx + 4) * sizeof(uint32_t)));
+    return ISOMC_OK;
+}
+
 void tl_mark(isomc *h, const char *name, uint32_t c, cudaStream_t st) {
     if (!h->timeline) return;
     cudaEvent_t e;
@@ -190,46 +214,51 @@ void tl_mark(isomc *h, const char *name, uint32_t c, cudaStream_t st) {
     h->tl.emplace_back(std::string(name) + "(" + std::to_string(c) + ")", e);
 }
 
-int32_t fork_streams(isomc *h) {
-    if (h->n_chunks > 1) {
-        CU(h, cudaEventRecord(h->ev_fork, h->stream));
-        CU(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-    }
-    return ISOMC_OK;
-}
-int32_t join_streams(isomc *h) {
-    if (h->n_chunks > 1) {
-        CU(h, cudaEventRecord(h->ev_join, h->stream2));
-        CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-    }
-    return ISOMC_OK;
-}
-
 int32_t launch_emit_chunk(isomc *h, uint32_t c, cudaStream_t st) {
     const Geo &g = h->g;
     const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
-    if (h->list_mode) {
-        /* one kernel: edge ids, vertex positions and triangles of the chunk's active cells */
-        if (h->kind == SRC_GRID)
-            CU(h, isomc_launch_emit_list_grid(g, h->d_grid, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
-                                              h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
-        else
-            CU(h, isomc_launch_emit_list_sdf(g, h->prog, h->directed, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
-                                             h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
+    if (h->tile_mode) {
+        /* pass 2: edge ids, vertex positions and triangles of the chunk's cell layers (warm-up on the layer below) */
+        CU(h, isomc_launch_tile_emit(g, h->tg, h->TB, h->etab, h->vofs, h->xyz, h->idx, h->cap_v, h->cap_t, l0, l1,
+                                     h->tile_tickets + MAX_CHUNKS + c, h->sms, st));
         h->stats.kernel_launches += 1;
         return ISOMC_OK;
     }
-    const uint32_t v0 = l0 < g.ghost ? g.ghost : l0; /* the ghost layer of a slab creates no vertices of ours */
-    CU(h, isomc_launch_emit(g, h->signs, h->segpre, h->rowV, h->rowT, h->tabs, h->layerTot, h->vofs, h->ticket + c, h->xyz,
-                            h->idx, h->cap_v, h->cap_t, l0, l1, h->sms, st));
-    if (v0 < l1) {
-        const int per_sm = 8;
+    /* one kernel: edge ids, vertex positions and triangles of the chunk's active cells */
+    if (h->kind == SRC_GRID)
+        CU(h, isomc_launch_emit_list_grid(g, h->d_grid, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
+                                          h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
+    else
+        CU(h, isomc_launch_emit_list_sdf(g, h->prog, h->directed, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
+                                         h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
+    h->stats.kernel_launches += 1;
+    return ISOMC_OK;
+}
+
+/* counting stage of z-chunk c (cell layers [l0, l1)) + the row scan; tile path: one kernel reads the samples once */
+int32_t launch_count_chunk(isomc *h, uint32_t c, cudaStream_t st, uint32_t *chunk_end) {
+    const Geo &g = h->g;
+    const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
+    if (h->tile_mode) {
         if (h->kind == SRC_GRID)
-            CU(h, isomc_launch_vertex_grid(g, h->d_grid, h->tabs, h->layerTot, h->rowV, h->xyz, h->cap_v, v0, l1, h->sms, per_sm, st));
+            CU(h, isomc_launch_tile_count_grid(g, h->tg, h->d_grid, h->TB, h->etab, l0, l1, h->tile_tickets + c, h->sms, st));
         else
-            CU(h, isomc_launch_vertex_sdf(g, h->prog, h->tabs, h->layerTot, h->rowV, h->xyz, h->cap_v, v0, l1, h->sms, per_sm, st));
+            CU(h, isomc_launch_tile_count_sdf(g, h->tg, h->prog, h->directed, h->TB, h->etab, l0, l1, h->tile_tickets + c, h->sms, st));
+        if (h->profiling) { CU(h, cudaEventRecord(h->ev[1], st)); CU(h, cudaEventRecord(h->ev[2], st)); }
+        CU(h, isomc_launch_scan(g, h->tg.ppl, h->rowV, h->rowT, h->layerTot, h->totals, h->TB.ctr, nullptr, chunk_end, l0, l1, st));
+        if (h->profiling) CU(h, cudaEventRecord(h->ev[3], st));
+        h->stats.kernel_launches += 2;
+        return ISOMC_OK;
     }
-    h->stats.kernel_launches += 2;
+    const uint32_t row0 = (c == 0 ? 0u : l0 + 1) * g.N, row1 = (l1 + 1) * g.N;
+    if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, row0, row1, h->sms, 8, st));
+    else CU(h, isomc_launch_sign_sdf(g, h->prog, h->directed, h->signs, row0, row1, h->sms, 8, st));
+    if (h->profiling) CU(h, cudaEventRecord(h->ev[1], st));
+    CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, h->ticket + c, l0, l1, h->sms, st));
+    if (h->profiling) CU(h, cudaEventRecord(h->ev[2], st));
+    CU(h, isomc_launch_scan(g, g.ncx, h->rowV, h->rowT, h->layerTot, h->totals, h->L.ctr, h->list_marks + c + 1, chunk_end, l0, l1, st));
+    if (h->profiling) CU(h, cudaEventRecord(h->ev[3], st));
+    h->stats.kernel_launches += 3;
     return ISOMC_OK;
 }
 
@@ -240,64 +269,26 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
     h->stats.kernel_launches = 0; h->stats.emit_reruns = 0;
     h->emit_inline = emit_inline;
     if (g.ncl == 0 || g.ncx == 0) { /* size == 1: the reference visits no cells */
-        CU(h, cudaMemsetAsync(h->totals, 0, 12 * sizeof(unsigned long long), h->stream));
+        CU(h, cudaMemsetAsync(h->totals, 0, N_TOTALS * sizeof(unsigned long long), h->stream));
         h->counted = true;
         h->emitted = emit_inline;
         return ISOMC_OK;
     }
-    const bool serial = h->profiling || !h->pipeline;
-    /* chunk plan: serial = one chunk; else 4 (<= 1 GiB of samples) .. 8 chunks, multiples of the brick height */
-    {
-        const uint32_t bz = (uint32_t)isomc_emit_layers_per_brick();
-        const uint64_t bytes = 4ull * g.N * g.N * g.nsl;
-        uint32_t n = (serial || g.ncl < 64) ? 1u : (bytes <= (1ull << 30) ? 4u : 8u);
-        uint32_t per = ((g.ncl + n - 1) / n + bz - 1) / bz * bz;
-        n = (g.ncl + per - 1) / per;
-        h->n_chunks = n;
-        for (uint32_t c = 0; c <= n; ++c) h->chunk_l[c] = c * per < g.ncl ? c * per : g.ncl;
-    }
+    /* one chunk: the z-chunked forms are the streamed host extract and (measured slower, profiles/r01_history.md) a two-stream
+     * producer / consumer pipeline that round 1 carried; the tile path reads the samples once, so there is nothing to overlap */
+    h->n_chunks = 1;
+    h->chunk_l[0] = 0; h->chunk_l[1] = g.ncl;
     if (h->profiling) CU(h, cudaEventRecord(h->ev[0], h->stream));
     CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t), h->stream));
     tl_mark(h, "start", 0, h->stream);
-    int32_t rc = fork_streams(h);
+    int32_t rc = launch_count_chunk(h, 0, h->stream, nullptr);
     if (rc) return rc;
-    const bool piped = h->n_chunks > 1;
-    /* producer: all sign chunks on stream2 (few CTAs per SM: HBM-bound, leaves the SMs to the consumer) */
-    for (uint32_t c = 0; c < h->n_chunks; ++c) {
-        cudaStream_t st = piped ? h->stream2 : h->stream;
-        const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
-        const uint32_t row0 = (c == 0 ? 0u : l0 + 1) * g.N, row1 = (l1 + 1) * g.N;
-        if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, row0, row1, h->sms, piped ? 3 : 8, st));
-        else CU(h, isomc_launch_sign_sdf(g, h->prog, h->directed, h->signs, row0, row1, h->sms, piped ? 3 : 8, st));
-        if (piped) CU(h, cudaEventRecord(h->ev_chunk[c], st));
-        tl_mark(h, "sign", c, st);
-        h->stats.kernel_launches += 1;
+    tl_mark(h, "count+scan", 0, h->stream);
+    if (emit_inline) {
+        rc = launch_emit_chunk(h, 0, h->stream);
+        if (rc) return rc;
+        tl_mark(h, "emit", 0, h->stream);
     }
-    if (h->profiling) CU(h, cudaEventRecord(h->ev[1], h->stream));
-    /* consumer */
-    for (uint32_t c = 0; c < h->n_chunks; ++c) {
-        cudaStream_t st = h->stream;
-        const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
-        if (piped) CU(h, cudaStreamWaitEvent(st, h->ev_chunk[c], 0));
-        if (h->list_mode) {
-            CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, h->ticket + c, l0, l1, h->sms, st));
-        } else {
-            CU(h, isomc_launch_count(g, h->signs, h->tabs, h->segpre, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, 8, st));
-        }
-        if (h->profiling) CU(h, cudaEventRecord(h->ev[2], h->stream));
-        tl_mark(h, "count", c, st);
-        CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, h->list_mode ? h->L.ctr : nullptr,
-                                h->list_mode ? h->list_marks + c + 1 : nullptr, nullptr, l0, l1, st));
-        if (h->profiling) CU(h, cudaEventRecord(h->ev[3], h->stream));
-        h->stats.kernel_launches += 2;
-        if (emit_inline) {
-            rc = launch_emit_chunk(h, c, st);
-            if (rc) return rc;
-            tl_mark(h, "emit+vertex", c, st);
-        }
-    }
-    rc = join_streams(h);
-    if (rc) return rc;
     h->counted = true;
     h->emitted = emit_inline;
     return ISOMC_OK;
@@ -307,7 +298,7 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
 int32_t enqueue_emit(isomc *h) {
     const Geo &g = h->g;
     if (g.ncl == 0 || g.ncx == 0) { h->emitted = true; return ISOMC_OK; }
-    CU(h, cudaMemsetAsync(h->ticket, 0, MAX_CHUNKS * sizeof(uint32_t), h->stream));
+    CU(h, cudaMemsetAsync(h->tile_mode ? h->tile_tickets + MAX_CHUNKS : h->ticket, 0, MAX_CHUNKS * sizeof(uint32_t), h->stream));
     for (uint32_t c = 0; c < h->n_chunks; ++c) {
         int32_t rc = launch_emit_chunk(h, c, h->stream);
         if (rc) return rc;
@@ -322,13 +313,14 @@ int32_t enqueue_count(isomc *h, bool emit_inline);
  * asked for and run the count again (same totals; the first extract of a handle, or a much denser field). */
 int32_t fetch_totals(isomc *h) {
     for (int attempt = 0; !h->totals_valid; ++attempt) {
-        CU(h, cudaMemcpyAsync(h->h_totals, h->totals, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(h->h_totals, h->totals, N_TOTALS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
-        const uint64_t blocks = h->h_totals[7];
-        if (!h->list_mode || blocks <= h->L.cap_blocks) { h->totals_valid = true; break; }
+        const uint64_t blocks = h->h_totals[7], tblocks = h->h_totals[12];
+        if (h->tile_mode ? (blocks <= h->TB.cap_eb && tblocks <= h->TB.cap_tb) : blocks <= h->L.cap_blocks) { h->totals_valid = true; break; }
         if (attempt >= 2) return fail(h, ISOMC_ERR_CUDA, "active-cell list still too small after regrowing (%llu blocks)", (unsigned long long)blocks);
         const uint32_t reruns = h->stats.emit_reruns;
-        int32_t rc = ensure_list_capacity(h, blocks + blocks / 8 + isomc_count_list_max_warps(h->sms));
+        int32_t rc = h->tile_mode ? ensure_tile_capacity(h, blocks + blocks / 8 + tile_stranded_blocks(h), tblocks + tblocks / 8 + tile_stranded_blocks(h))
+                                  : ensure_list_capacity(h, blocks + blocks / 8 + isomc_count_list_max_warps(h->sms));
         if (rc) return rc;
         rc = enqueue_count(h, h->emit_inline);
         if (rc) return rc;
@@ -406,7 +398,6 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
     if (!h) return fail(nullptr, ISOMC_ERR_OOM, "host allocation failed");
     h->size = size; h->z_begin = z_begin; h->z_end = z_end; h->device = device;
     h->timeline = getenv("ISOMC_TIMELINE") != nullptr;
-    if (const char *p = getenv("ISOMC_PIPELINE")) h->pipeline = atoi(p) != 0;
     Geo &g = h->g;
     g.N = size; g.ncx = size - 1;
     g.nsegx = (g.ncx + 31) / 32; g.nws = (g.nsegx + 2) & ~1u; /* >= nsegx + 1, even: word 2j of a row is 8-byte aligned */
@@ -430,39 +421,51 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
         CU(h, cudaMalloc(&h->tabs, sizeof(McTables)));
         CU(h, cudaMemcpy(h->tabs, &host_tabs, sizeof(McTables), cudaMemcpyHostToDevice));
         const uint64_t nrows_s = (uint64_t)g.nsl * g.N, nrows_c = (uint64_t)g.ncl * g.ncx;
-        CU(h, cudaMalloc(&h->signs, (nrows_s * g.nws + 4) * sizeof(uint32_t)));
-        if (const char *p = getenv("ISOMC_EMIT")) h->list_mode = strcmp(p, "brick") != 0;
-        if (h->list_mode) {
+        if (const char *p = getenv("ISOMC_PATH")) h->tile_mode = strcmp(p, "list") != 0;
+        h->tg = tile_geo(g);
+        EmitTab host_etab;
+        isomc_build_emit_tab(host_tabs, &host_etab);
+        isomc_tile_fill_eloc(host_etab.eloc);
+        CU(h, cudaMalloc(&h->etab, sizeof(EmitTab)));
+        CU(h, cudaMemcpy(h->etab, &host_etab, sizeof(EmitTab), cudaMemcpyHostToDevice));
+        if (h->tile_mode) {
+            /* per row piece: counts -> prefixes (rowV / rowT), entry and t positions, active cells */
+            const uint64_t np = (uint64_t)g.ncl * h->tg.ppl;
+            CU(h, cudaMalloc(&h->rowV, (np + 4) * sizeof(uint32_t)));
+            CU(h, cudaMalloc(&h->rowT, (np + 4) * sizeof(uint32_t)));
+            CU(h, cudaMalloc(&h->TB.pE, (np + 4) * sizeof(uint32_t)));
+            CU(h, cudaMalloc(&h->TB.pTp, (np + 4) * sizeof(uint32_t)));
+            CU(h, cudaMalloc(&h->TB.pA, (np + 4) * sizeof(uint16_t)));
+            h->TB.pV = h->rowV; h->TB.pT = h->rowT;
+            /* first guess: 1/32 of the cells active, plus the blocks the counting warps may strand */
+            const uint64_t guess = nrows_c * g.ncx / 32 / ENT_BLOCK + tile_stranded_blocks(h);
+            int32_t lrc = ensure_tile_capacity(h, guess, guess);
+            if (lrc) return lrc;
+        } else {
+            CU(h, cudaMalloc(&h->signs, (nrows_s * g.nws + 4) * sizeof(uint32_t)));
             CU(h, cudaMalloc(&h->L.segrec, (nrows_c * g.nsegx + 4) * sizeof(uint2)));
             CU(h, cudaMalloc(&h->L.segtpre, (nrows_c * g.nsegx + 4) * sizeof(uint32_t)));
-            EmitTab host_etab;
-            isomc_build_emit_tab(host_tabs, &host_etab);
-            CU(h, cudaMalloc(&h->etab, sizeof(EmitTab)));
-            CU(h, cudaMemcpy(h->etab, &host_etab, sizeof(EmitTab), cudaMemcpyHostToDevice));
             /* first guess: 1/32 of the cells active, plus the block every counting warp may strand */
             int32_t lrc = ensure_list_capacity(h, nrows_c * g.ncx / 32 / LIST_BLOCK + isomc_count_list_max_warps(h->sms) + 16);
             if (lrc) return lrc;
-        } else {
-            CU(h, cudaMalloc(&h->segpre, (nrows_c * g.nsegx + 4) * sizeof(uint32_t)));
+            CU(h, cudaMalloc(&h->rowV, (nrows_c + 4) * sizeof(uint32_t)));
+            CU(h, cudaMalloc(&h->rowT, (nrows_c + 4) * sizeof(uint32_t)));
+            CU(h, cudaMalloc(&h->rowA, (nrows_c + 4) * sizeof(uint32_t)));
         }
-        CU(h, cudaMalloc(&h->rowV, (nrows_c + 4) * sizeof(uint32_t)));
-        CU(h, cudaMalloc(&h->rowT, (nrows_c + 4) * sizeof(uint32_t)));
-        CU(h, cudaMalloc(&h->rowA, (nrows_c + 4) * sizeof(uint32_t)));
         /* per-layer totals followed by the emit tickets: zeroed by a single memset per extract */
         CU(h, cudaMalloc(&h->layerTot, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t)));
         h->ticket = reinterpret_cast<uint32_t *>(h->layerTot + ((size_t)g.ncl * 3 + 4));
         h->L.ctr = h->ticket + MAX_CHUNKS;
         h->list_marks = h->ticket + MAX_CHUNKS + 1;
         h->chunk_ends = h->ticket + 2 * MAX_CHUNKS + 2;
-        CU(h, cudaMalloc(&h->totals, 12 * sizeof(unsigned long long)));
-        CU(h, cudaMemset(h->totals, 0, 12 * sizeof(unsigned long long)));
+        h->TB.ctr = h->ticket + 4 * MAX_CHUNKS + 4;
+        h->tile_tickets = h->ticket + 4 * MAX_CHUNKS + 8;
+        h->TB.layerTot = h->layerTot;
+        CU(h, cudaMalloc(&h->totals, N_TOTALS * sizeof(unsigned long long)));
+        CU(h, cudaMemset(h->totals, 0, N_TOTALS * sizeof(unsigned long long)));
         CU(h, cudaMalloc(&h->vofs, sizeof(uint32_t)));
         CU(h, cudaMemset(h->vofs, 0, sizeof(uint32_t)));
-        CU(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-        CU(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-        CU(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-        for (auto &ev : h->ev_chunk) CU(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        CU(h, cudaMallocHost(&h->h_totals, 12 * sizeof(unsigned long long)));
+        CU(h, cudaMallocHost(&h->h_totals, N_TOTALS * sizeof(unsigned long long)));
         CU(h, cudaMallocHost(&h->h_chunk_ends, 2 * MAX_CHUNKS * sizeof(uint32_t)));
         return ISOMC_OK;
     };
@@ -492,7 +495,8 @@ int32_t isomc_destroy(isomc_t *h) {
     if (!h) return ISOMC_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->signs); cudaFree(h->segpre); cudaFree(h->rowV); cudaFree(h->rowT); cudaFree(h->rowA);
+    cudaFree(h->signs); cudaFree(h->segA); cudaFree(h->rowV); cudaFree(h->rowT); cudaFree(h->rowA);
+    cudaFree(h->TB.pE); cudaFree(h->TB.pTp); cudaFree(h->TB.pA); cudaFree(h->TB.ent); cudaFree(h->TB.tbuf);
     cudaFree(h->layerTot); cudaFree(h->totals); cudaFree(h->vofs); cudaFree(h->tabs);
     cudaFree(h->xyz); cudaFree(h->idx); cudaFree(h->stage_grid);
     cudaFree(h->L.ent); cudaFree(h->L.ent_yz); cudaFree(h->L.segrec); cudaFree(h->L.segtpre); cudaFree(h->L.blkfill); cudaFree(h->etab);
@@ -506,10 +510,6 @@ int32_t isomc_destroy(isomc_t *h) {
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
-    for (auto &ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return ISOMC_OK;
@@ -577,7 +577,6 @@ int32_t isomc_enqueue_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nod
 /* MarchingCubes::<Directed>::new(size).extract(&Sampler::new(&implicit_tree), ..)  (reference src/distance.rs:72-104) */
 int32_t isomc_extract_sdf_directed(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes) {
     if (!h) return ISOMC_ERR_BAD_ARG;
-    if (!h->list_mode) return fail(h, ISOMC_ERR_UNSUPPORTED_SOURCE, "Directed distances are served by the active-cell-list kernels (unset ISOMC_EMIT=brick)");
     int32_t rc = validate_program(h, prog, n_nodes, &h->prog);
     if (rc) return rc;
     h->kind = SRC_SDF; h->d_grid = nullptr; h->directed = true;
@@ -636,7 +635,7 @@ int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, 
     const Geo &g = h->g;
     const size_t bytes = (size_t)g.N * g.N * g.nsl * sizeof(float);
     if (!h->stage_grid) CU(h, cudaMalloc(&h->stage_grid, bytes > 0 ? bytes : 4));
-    const bool streamed = g.ncl >= 32 && h->cap_v > 0 && h->cap_t > 0 && !h->profiling && !h->pipeline;
+    const bool streamed = g.ncl >= 32 && h->cap_v > 0 && h->cap_t > 0 && !h->profiling;
     bool delivered = false;
     if (!streamed) {
         CU(h, cudaMemcpyAsync(h->stage_grid, h_grid, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -658,12 +657,11 @@ int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, 
         h->have_result = false; h->counted = false; h->emitted = false; h->totals_valid = false;
         h->stats.kernel_launches = 0; h->stats.emit_reruns = 0;
         h->emit_inline = true;
-        /* chunk plan: up to MAX_CHUNKS chunks of >= 8 cell layers, multiples of the brick height */
+        /* chunk plan: up to MAX_CHUNKS chunks of >= 8 cell layers */
         {
-            const uint32_t bz = (uint32_t)isomc_emit_layers_per_brick();
             uint32_t n = g.ncl / 8 < (uint32_t)MAX_CHUNKS ? g.ncl / 8 : (uint32_t)MAX_CHUNKS;
             if (n < 1) n = 1;
-            const uint32_t per = ((g.ncl + n - 1) / n + bz - 1) / bz * bz;
+            const uint32_t per = (g.ncl + n - 1) / n;
             n = (g.ncl + per - 1) / per;
             h->n_chunks = n;
             for (uint32_t c = 0; c <= n; ++c) h->chunk_l[c] = c * per < g.ncl ? c * per : g.ncl;
@@ -678,19 +676,11 @@ int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, 
         }
         for (uint32_t c = 0; c < h->n_chunks; ++c) {
             cudaStream_t st = h->stream;
-            const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
-            const uint32_t row0 = (c == 0 ? 0u : l0 + 1) * g.N, row1 = (l1 + 1) * g.N;
             CU(h, cudaStreamWaitEvent(st, h->ev_in[c], 0));
-            CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, row0, row1, h->sms, 8, st));
-            if (h->list_mode)
-                CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, h->ticket + c, l0, l1, h->sms, st));
-            else
-                CU(h, isomc_launch_count(g, h->signs, h->tabs, h->segpre, h->rowV, h->rowT, h->rowA, h->layerTot, l0, l1, h->sms, 8, st));
-            CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, h->list_mode ? h->L.ctr : nullptr,
-                                    h->list_mode ? h->list_marks + c + 1 : nullptr, h->chunk_ends + 2 * c, l0, l1, st));
+            rc = launch_count_chunk(h, c, st, h->chunk_ends + 2 * c);
+            if (rc) return rc;
             CU(h, cudaMemcpyAsync(h->h_chunk_ends + 2 * c, h->chunk_ends + 2 * c, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CU(h, cudaEventRecord(h->ev_cnt[c], st));
-            h->stats.kernel_launches += 3;
             rc = launch_emit_chunk(h, c, st);
             if (rc) return rc;
             CU(h, cudaEventRecord(h->ev_emit[c], st));
@@ -737,14 +727,15 @@ static int32_t points_impl(isomc_t *h) {
         h->have_result = true;
         return ISOMC_OK;
     }
-    /* per-segment prefixes live in the scratch the mesh path uses for its own per-segment data */
-    uint32_t *segA = h->list_mode ? reinterpret_cast<uint32_t *>(h->L.segrec) : h->segpre;
+    rc = ensure_signs(h);
+    if (rc) return rc;
+    uint32_t *segA = h->segA;
     CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t), h->stream));
     if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, 0, g.nsl * g.N, h->sms, 8, h->stream));
     else CU(h, isomc_launch_sign_sdf(g, h->prog, h->directed, h->signs, 0, g.nsl * g.N, h->sms, 8, h->stream));
     CU(h, isomc_launch_points_count(g, h->signs, segA, h->rowV, h->rowT, h->layerTot, h->sms, h->stream));
-    CU(h, isomc_launch_scan(g, h->rowV, h->rowT, h->layerTot, h->totals, nullptr, nullptr, nullptr, 0, g.ncl, h->stream));
-    CU(h, cudaMemcpyAsync(h->h_totals, h->totals, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, isomc_launch_scan(g, g.ncx, h->rowV, h->rowT, h->layerTot, h->totals, nullptr, nullptr, nullptr, 0, g.ncl, h->stream));
+    CU(h, cudaMemcpyAsync(h->h_totals, h->totals, N_TOTALS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     const uint64_t np = h->h_totals[0];
     if (np >= (1ull << 32)) return fail(h, ISOMC_ERR_INDEX_OVERFLOW, "%llu points", (unsigned long long)np);
@@ -954,6 +945,12 @@ int32_t isomc_debug_cube_indices(isomc_t *h, uint8_t *host_out) {
     if (rc) return rc;
     const uint64_t n = (uint64_t)h->g.ncl * h->g.ncx * h->g.ncx;
     if (n == 0) return ISOMC_OK;
+    if (h->tile_mode) { /* the tile path keeps no sign words: derive them from the source of the last extract */
+        rc = ensure_signs(h);
+        if (rc) return rc;
+        if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(h->g, h->d_grid, h->signs, 0, h->g.nsl * h->g.N, h->sms, 8, h->stream));
+        else CU(h, isomc_launch_sign_sdf(h->g, h->prog, h->directed, h->signs, 0, h->g.nsl * h->g.N, h->sms, 8, h->stream));
+    }
     uint8_t *d = nullptr;
     CU(h, cudaMalloc(&d, n));
     cudaError_t e = isomc_launch_cube_indices(h->g, h->signs, h->tabs, d, h->sms, h->stream);

@@ -52,6 +52,7 @@ struct EmitTab {
     uint8_t ntri[256];
     uint8_t rank3[256];       /* interior cells: rank of e5 | e6 << 2 | e10 << 4 among the three edges such a cell creates */
     uint8_t pad[4];
+    uint32_t eloc[2][12];     /* tile path: plane location of edge e on a cell layer of parity p (isomc_tile.cuh: tile_edge_loc) */
 };
 
 static inline void isomc_build_emit_tab(const McTables &m, EmitTab *t) {

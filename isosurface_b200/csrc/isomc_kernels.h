@@ -10,6 +10,8 @@ struct SdfProgram;
 struct McTables;
 struct ListBufs;
 struct EmitTab;
+struct TileGeo;
+struct TileBufs;
 
 struct SynthParams {
     int32_t kind;
@@ -17,33 +19,18 @@ struct SynthParams {
     float cx[64], cy[64], cz[64], r[64];                     /* sphere union */
 };
 
-size_t isomc_emit_smem_bytes(uint32_t nws);
-
 /* ranges: sample rows [row0,row1) for the sign kernels, cell layers [lz0,lz1) for the rest */
 cudaError_t isomc_launch_sign_grid(const Geo &g, const float *d_grid, uint32_t *signs, uint32_t row0, uint32_t row1, int sms,
                                    int ctas_per_sm, cudaStream_t st);
 /* directed: sample the tree as Directed distances (inside iff no component is positive) */
 cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, bool directed, uint32_t *signs, uint32_t row0, uint32_t row1,
                                   int sms, int ctas_per_sm, cudaStream_t st);
-cudaError_t isomc_launch_count(const Geo &g, const uint32_t *signs, const McTables *tabs, uint32_t *segpre,
-                               uint32_t *rowV, uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot,
-                               uint32_t lz0, uint32_t lz1, int sms, int ctas_per_sm, cudaStream_t st);
-cudaError_t isomc_launch_scan(const Geo &g, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
+/* ppl = row pieces per cell layer (cell rows, times the x-tiles of a row on the tile path) */
+cudaError_t isomc_launch_scan(const Geo &g, uint32_t ppl, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
                               unsigned long long *totals, const uint32_t *list_ctr, uint32_t *list_mark, uint32_t *chunk_end,
                               uint32_t lz0, uint32_t lz1, cudaStream_t st);
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,
                                     cudaStream_t st);
-int isomc_emit_layers_per_brick();
-cudaError_t isomc_launch_emit(const Geo &g, const uint32_t *signs, const uint32_t *segpre, const uint32_t *rowPV,
-                              const uint32_t *rowPT, const McTables *tabs, const unsigned long long *layerTot,
-                              const uint32_t *vofs, uint32_t *ticket, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
-                              uint32_t lz0, uint32_t lz1, int sms, cudaStream_t st);
-cudaError_t isomc_launch_vertex_grid(const Geo &g, const float *d_grid, const McTables *tabs, const unsigned long long *layerTot,
-                                     const uint32_t *rowPV, float *xyz, uint64_t cap_v, uint32_t lz0, uint32_t lz1, int sms,
-                                     int ctas_per_sm, cudaStream_t st);
-cudaError_t isomc_launch_vertex_sdf(const Geo &g, const SdfProgram &prog, const McTables *tabs, const unsigned long long *layerTot,
-                                    const uint32_t *rowPV, float *xyz, uint64_t cap_v, uint32_t lz0, uint32_t lz1, int sms,
-                                    int ctas_per_sm, cudaStream_t st);
 cudaError_t isomc_launch_cube_indices(const Geo &g, const uint32_t *signs, const McTables *tabs, uint8_t *out, int sms,
                                       cudaStream_t st);
 cudaError_t isomc_launch_sample_sdf(const SdfProgram &prog, const float *xyz, uint64_t n, float *out, int use_chain, cudaStream_t st);
@@ -64,6 +51,18 @@ cudaError_t isomc_launch_emit_list_sdf(const Geo &g, const SdfProgram &prog, boo
                                        const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                        const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
                                        const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st);
+
+/* tile path (isomc_tile_kernels.cu): pass 1 = samples -> entries, crossing parameters, per-piece counts over cell layers
+ * [lz0, lz1); pass 2 = entries -> mesh.  ticket: a zeroed u32 per launch */
+size_t isomc_tile_emit_smem_bytes();
+void isomc_tile_fill_eloc(uint32_t eloc[2][12]);
+cudaError_t isomc_launch_tile_count_grid(const Geo &g, const TileGeo &tg, const float *d_grid, const TileBufs &B, const EmitTab *tab,
+                                         uint32_t lz0, uint32_t lz1, uint32_t *ticket, int sms, cudaStream_t st);
+cudaError_t isomc_launch_tile_count_sdf(const Geo &g, const TileGeo &tg, const SdfProgram &prog, bool directed, const TileBufs &B,
+                                        const EmitTab *tab, uint32_t lz0, uint32_t lz1, uint32_t *ticket, int sms, cudaStream_t st);
+cudaError_t isomc_launch_tile_emit(const Geo &g, const TileGeo &tg, const TileBufs &B, const EmitTab *tab, const uint32_t *vofs,
+                                   float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t, uint32_t lz0, uint32_t lz1, uint32_t *ticket,
+                                   int sms, cudaStream_t st);
 
 /* PointCloud (isomc_points.cu): segA = one u32 per 32-cell segment (in-row prefix of the active-cell count) */
 cudaError_t isomc_launch_points_count(const Geo &g, const uint32_t *signs, uint32_t *segA, uint32_t *rowV, uint32_t *rowT,

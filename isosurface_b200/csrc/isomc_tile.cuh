@@ -90,7 +90,7 @@ ISOMC_HD void cta_sync(const Cta &c) {
 }
 
 /* ---- TMA bulk copy + mbarrier (device only) -------------------------------------------------------------- */
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 __device__ __forceinline__ uint32_t tile_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tile_mbar_init(unsigned long long *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tile_smem_u32(bar)), "r"(count) : "memory");
@@ -155,7 +155,7 @@ ISOMC_HD float crossing_t(float a, float b) { /* Signed::find_crossing_point, di
 
 struct CountCtx {          /* warp-uniform state of a counting CTA that lives across items */
     Cursor curE, curT;
-    uint32_t uses[3];      /* how often each mbarrier has been armed (parity of the next wait) */
+    uint32_t phase;        /* bit s: parity of the next wait on mbarrier s */
 };
 
 /* sample layer L of the item's column -> slot s (synchronous sources: evaluated / loaded by all threads) */
@@ -209,8 +209,8 @@ ISOMC_HD void tile_count_item(const Cta &c, const Geo &g, const TileGeo &tg, con
         (void)s;
 #if defined(__CUDA_ARCH__)
         if constexpr (Src::ASYNC) {
-            tile_mbar_wait(&S.mbar[s], X.uses[s] & 1u);
-            X.uses[s]++;
+            tile_mbar_wait(&S.mbar[s], X.phase >> s & 1u);
+            X.phase ^= 1u << s;
             return;
         }
 #endif

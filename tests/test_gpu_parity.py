@@ -341,28 +341,28 @@ def test_full_size_slabs_equal_unsharded_1024(iso):
     assert facts["directed_edge_dups"] == 0
 
 
-def test_zchunk_pipeline_mode_is_bit_identical(iso, oracle, monkeypatch):
-    """ISOMC_PIPELINE=1 (two-stream z-chunk pipeline, off by default) must give the same bytes"""
+def test_plain_fill_and_list_path_are_bit_identical(iso, oracle, monkeypatch):
+    """ISOMC_FILL=plain (all-thread loads instead of the TMA bulk copies) and ISOMC_PATH=list (the round-1 kernels) must give
+    the same bytes as the default tile path"""
     size = 160
     t = synth(iso, 1, size, 5)
     mc = iso.MarchingCubes(size)
     mc.extract_device(iso.DenseGrid(t))
     ref = [a.tobytes() for a in mc.copy_out()]
     mc.close()
-    monkeypatch.setenv("ISOMC_PIPELINE", "1")
-    mp = iso.MarchingCubes(size)          # the environment is read at create
-    for _ in range(3):                    # first extract sizes the buffers, the next ones emit inline per chunk
-        mp.extract_device(iso.DenseGrid(t))
-        assert [a.tobytes() for a in mp.copy_out()] == ref
-    assert mp.stats()["kernel_launches"] > 6
-    mp.close()
     host = t.cpu().numpy().reshape(size + 1, size, size)
     oxyz, oidx, _ = oracle.extract_grid(size, host)
     assert ref[1] == oidx.tobytes() and ref[0] == oxyz.tobytes()
+    monkeypatch.setenv("ISOMC_PATH", "list")
+    mp = iso.MarchingCubes(size)          # the environment is read at create
+    for _ in range(2):
+        mp.extract_device(iso.DenseGrid(t))
+        assert [a.tobytes() for a in mp.copy_out()] == ref
+    mp.close()
 
 
-def test_non_multiple_of_four_size_uses_generic_sign_kernel(iso, oracle):
-    """N % 4 != 0 (or a misaligned pointer) takes the scalar k_sign path instead of the float4 one"""
+def test_non_multiple_of_four_size_uses_plain_fill(iso, oracle):
+    """N % 4 != 0 (or a misaligned pointer) cannot be staged by TMA bulk copies: all-thread loads fill the tile slots"""
     import torch
     for size in (66, 67, 131):
         t = synth(iso, 3, size, 9)
@@ -435,21 +435,6 @@ def test_streamed_host_to_host_extract(iso, oracle):
     mc.extract(iso.DenseGrid(fields[1]), sink)
     assert mesh_diff(sink.vertices.ravel(), sink.indices.ravel(), want[1][0], want[1][1], POS_TOL) == ""
     mc.close()
-
-
-def test_brick_kernels_still_match(iso, oracle, monkeypatch):
-    """ISOMC_EMIT=brick keeps the older brick emission kernels selectable; same bytes as the list path"""
-    monkeypatch.setenv("ISOMC_EMIT", "brick")
-    for kind, size, seed in ((1, 128, 7), (3, 100, 8)):
-        t = synth(iso, kind, size, seed)
-        host = t.cpu().numpy().reshape(size + 1, size, size)
-        oxyz, oidx, _ = oracle.extract_grid(size, host)
-        mc = iso.MarchingCubes(size)
-        for _ in range(2):
-            mc.extract_device(iso.DenseGrid(t))
-            xyz, idx = mc.copy_out()
-            assert mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
-        mc.close()
 
 
 def test_point_cloud_matches_oracle(iso, oracle):
