@@ -146,6 +146,7 @@ int32_t isomc_set_stream(isomc_t *h, void *cuda_stream);
 /* enqueue the whole extract without synchronising; finish with isomc_finish() */
 int32_t isomc_enqueue_grid_device(isomc_t *h, const float *d_grid);
 int32_t isomc_enqueue_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes);
+int32_t isomc_enqueue_sdf_directed(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes);
 int32_t isomc_finish(isomc_t *h);
 /* pre-size the output buffers so steady-state extracts never re-run emission */
 int32_t isomc_reserve(isomc_t *h, uint64_t n_vertices, uint64_t n_triangles);
@@ -174,6 +175,32 @@ int32_t isomc_slab_emit(isomc_t *h, uint64_t vertex_base, uint64_t boundary_base
 /* phase 2, fully on-stream: d_gathered = all-gathered totals, 3 x u64 per rank, rank-major;
  * the bases are derived on the device, no host round trip between count and emit. */
 int32_t isomc_slab_emit_gathered(isomc_t *h, const uint64_t *d_gathered, uint32_t rank, uint32_t n_ranks);
+/* the same without the final synchronisation: finish with isomc_finish() (which also reports ISOMC_ERR_INDEX_OVERFLOW if the
+ * global ids of this slab do not fit u32) */
+int32_t isomc_slab_enqueue_emit_gathered(isomc_t *h, const uint64_t *d_gathered, uint32_t rank, uint32_t n_ranks);
+
+/* ---- the same sharding driven from ONE process over the GPUs of a box (new) ----------------
+ * `MarchingCubes::new(size)` for a host that owns several devices (the Rust shim, include/isosurface.hpp): one slab handle
+ * per listed device, cell layers split evenly; each extract = count on every device, ONE ncclAllGather of 3 x u64 per rank
+ * on the extraction streams (NCCL over NVLink / NVSwitch; libnccl.so.2 is loaded on first use), emission with global ids.
+ * devices == NULL: devices 0 .. n_gpus-1.  Listing one device several times runs all slabs there (a single-GPU box can
+ * exercise the sharded path; the exchange is then a stream-ordered device copy, NCCL refuses duplicate devices).
+ * Concatenating the ranks' parts in rank order (isomc_sharded_copy_out does) gives exactly the unsharded mesh. */
+typedef struct isomc_sharded isomc_sharded_t;
+int32_t isomc_sharded_create(uint32_t size, uint32_t n_gpus, const int32_t *devices, isomc_sharded_t **out);
+int32_t isomc_sharded_destroy(isomc_sharded_t *s);
+const char *isomc_sharded_last_error(const isomc_sharded_t *s);   /* s may be NULL: last create() error */
+int32_t isomc_sharded_uses_nccl(const isomc_sharded_t *s);        /* 1: the exchange is an NCCL all-gather */
+/* rank's cell layers [z_begin, z_end) and the sample layers it must be given: n_sample_layers starting at first_sample_layer */
+int32_t isomc_sharded_slab(const isomc_sharded_t *s, uint32_t rank, uint32_t *z_begin, uint32_t *z_end, uint32_t *first_sample_layer,
+                           uint32_t *n_sample_layers);
+int32_t isomc_sharded_handle(isomc_sharded_t *s, uint32_t rank, isomc_t **h);   /* the rank's slab handle (device buffers, stats) */
+/* d_slabs[r] = rank r's sample layers on ITS device (n_sample_layers * N * N f32, first = first_sample_layer) */
+int32_t isomc_sharded_extract_grid(isomc_sharded_t *s, const float *const *d_slabs);
+int32_t isomc_sharded_extract_sdf(isomc_sharded_t *s, const isomc_sdf_node *prog, uint32_t n_nodes);
+int32_t isomc_sharded_counts(isomc_sharded_t *s, uint64_t *n_vertices, uint64_t *n_triangles, uint64_t *n_active_cells);   /* whole mesh */
+int32_t isomc_sharded_rank_counts(isomc_sharded_t *s, uint32_t rank, uint64_t *n_vertices, uint64_t *n_triangles, uint64_t *n_active_cells);
+int32_t isomc_sharded_copy_out(isomc_sharded_t *s, float *xyz /* 3*V */, uint32_t *idx /* 3*T */);
 
 /* ---- debug / parity helpers -------------------------------------------------------------- */
 /* per-cell cube_index in the reference's corner order (marching_cubes_impl.rs:26-37) for the

@@ -7,11 +7,11 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libisomc_b200.so"
-SOURCES = ["isomc_kernels.cu", "isomc_list_kernels.cu", "isomc_tile_kernels.cu", "isomc_points.cu", "isomc_api.cu"]
+SOURCES = ["isomc_kernels.cu", "isomc_list_kernels.cu", "isomc_tile_kernels.cu", "isomc_points.cu", "isomc_api.cu", "isomc_sharded.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false",  # the reference (rustc) never contracts a*b+c; keep sample signs / vertex bits identical
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-ldl",
 ]
 
 

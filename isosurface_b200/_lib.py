@@ -62,6 +62,7 @@ SIGNATURES = {
     "isomc_set_stream": (_I32, [_P, _P]),
     "isomc_enqueue_grid_device": (_I32, [_P, _P]),
     "isomc_enqueue_sdf": (_I32, [_P, _P, _U32]),
+    "isomc_enqueue_sdf_directed": (_I32, [_P, _P, _U32]),
     "isomc_finish": (_I32, [_P]),
     "isomc_reserve": (_I32, [_P, _U64, _U64]),
     "isomc_set_profiling": (_I32, [_P, _I32]),
@@ -72,6 +73,18 @@ SIGNATURES = {
     "isomc_slab_totals_device": (_I32, [_P, C.POINTER(_P)]),
     "isomc_slab_emit": (_I32, [_P, _U64, _U64]),
     "isomc_slab_emit_gathered": (_I32, [_P, _P, _U32, _U32]),
+    "isomc_slab_enqueue_emit_gathered": (_I32, [_P, _P, _U32, _U32]),
+    "isomc_sharded_create": (_I32, [_U32, _U32, _P, C.POINTER(_P)]),
+    "isomc_sharded_destroy": (_I32, [_P]),
+    "isomc_sharded_last_error": (C.c_char_p, [_P]),
+    "isomc_sharded_uses_nccl": (_I32, [_P]),
+    "isomc_sharded_slab": (_I32, [_P, _U32, C.POINTER(_U32), C.POINTER(_U32), C.POINTER(_U32), C.POINTER(_U32)]),
+    "isomc_sharded_handle": (_I32, [_P, _U32, C.POINTER(_P)]),
+    "isomc_sharded_extract_grid": (_I32, [_P, _P]),
+    "isomc_sharded_extract_sdf": (_I32, [_P, _P, _U32]),
+    "isomc_sharded_counts": (_I32, [_P, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
+    "isomc_sharded_rank_counts": (_I32, [_P, _U32, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
+    "isomc_sharded_copy_out": (_I32, [_P, _P, _P]),
     "isomc_debug_cube_indices": (_I32, [_P, _P]),
     "isomc_debug_sample_sdf": (_I32, [_I32, _P, _U32, _P, _U64, _P]),
     "isomc_synth_field": (_I32, [_I32, _I32, _U32, _U64, _U32, _U32, _P]),

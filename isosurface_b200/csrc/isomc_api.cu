@@ -338,6 +338,9 @@ int32_t finish_impl(isomc *h) {
     if (h->h_totals[0] >= (1ull << 32) || h->h_totals[1] >= (1ull << 32))
         return fail(h, ISOMC_ERR_INDEX_OVERFLOW, "mesh has %llu vertices / %llu triangles: does not fit u32 indices",
                     (unsigned long long)h->h_totals[0], (unsigned long long)h->h_totals[1]);
+    if (h->vofs_cached < 0 && h->h_totals[13] + h->h_totals[0] >= (1ull << 32)) /* offset derived on the device (slab_emit_gathered) */
+        return fail(h, ISOMC_ERR_INDEX_OVERFLOW, "global vertex ids of this slab reach %llu: do not fit u32 indices",
+                    (unsigned long long)(h->h_totals[13] + h->h_totals[0]));
     const bool must_rerun = !h->emitted || nv > h->cap_v || nt > h->cap_t;
     if (must_rerun) {
         if (h->emitted) h->stats.emit_reruns = 1;
@@ -575,12 +578,16 @@ int32_t isomc_enqueue_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nod
 }
 
 /* MarchingCubes::<Directed>::new(size).extract(&Sampler::new(&implicit_tree), ..)  (reference src/distance.rs:72-104) */
-int32_t isomc_extract_sdf_directed(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes) {
+int32_t isomc_enqueue_sdf_directed(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes) {
     if (!h) return ISOMC_ERR_BAD_ARG;
     int32_t rc = validate_program(h, prog, n_nodes, &h->prog);
     if (rc) return rc;
     h->kind = SRC_SDF; h->d_grid = nullptr; h->directed = true;
-    rc = enqueue_full(h);
+    return enqueue_full(h);
+}
+
+int32_t isomc_extract_sdf_directed(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes) {
+    int32_t rc = isomc_enqueue_sdf_directed(h, prog, n_nodes);
     return rc ? rc : isomc_finish(h);
 }
 
@@ -921,19 +928,26 @@ int32_t isomc_slab_emit(isomc_t *h, uint64_t vertex_base, uint64_t boundary_base
     return finish_impl(h);
 }
 
-int32_t isomc_slab_emit_gathered(isomc_t *h, const uint64_t *d_gathered, uint32_t rank, uint32_t n_ranks) {
+int32_t isomc_slab_enqueue_emit_gathered(isomc_t *h, const uint64_t *d_gathered, uint32_t rank, uint32_t n_ranks) {
     if (!h || !d_gathered || rank >= n_ranks) return ISOMC_ERR_BAD_ARG;
     if (!h->counted) return fail(h, ISOMC_ERR_NO_RESULT, "slab_emit before slab_count");
     int32_t rc = bind_device(h);
     if (rc) return rc;
-    CU(h, isomc_launch_slab_bases((const unsigned long long *)d_gathered, rank, h->g.ghost, h->vofs, h->stream));
+    /* id offset on the device; its 64-bit value goes to totals[13] so that finish() can tell an overflow of the global ids */
+    CU(h, isomc_launch_slab_bases((const unsigned long long *)d_gathered, rank, h->g.ghost, h->vofs, h->totals + 13, h->stream));
     h->vofs_cached = -1;
+    h->totals_valid = false; /* (totals[13] is new) */
     h->stats.kernel_launches += 1;
     if (h->cap_v > 0 || h->cap_t > 0) {
         rc = enqueue_emit(h);
         if (rc) return rc;
     }
-    return finish_impl(h);
+    return ISOMC_OK;
+}
+
+int32_t isomc_slab_emit_gathered(isomc_t *h, const uint64_t *d_gathered, uint32_t rank, uint32_t n_ranks) {
+    int32_t rc = isomc_slab_enqueue_emit_gathered(h, d_gathered, rank, n_ranks);
+    return rc ? rc : finish_impl(h);
 }
 
 /* ---- debug -------------------------------------------------------------------------------- */

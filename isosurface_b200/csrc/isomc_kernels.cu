@@ -184,13 +184,14 @@ __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t ppl, uint32_t
 
 /* vertex-id offset of a slab from the all-gathered per-rank totals {V, V_before_last, T} */
 __global__ void k_slab_bases(const unsigned long long *__restrict__ gathered, uint32_t rank, uint32_t ghost,
-                             uint32_t *__restrict__ vofs) {
+                             uint32_t *__restrict__ vofs, unsigned long long *__restrict__ ofs64) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long vbase = 0;
         for (uint32_t h = 0; h < rank; ++h) vbase += gathered[3 * h];
         unsigned long long ofs = vbase;
         if (ghost && rank > 0) ofs = vbase - gathered[3 * (rank - 1)] + gathered[3 * (rank - 1) + 1];
         *vofs = (uint32_t)ofs;
+        if (ofs64) *ofs64 = ofs; /* untruncated: the host checks that ofs + local ids fit u32 */
     }
 }
 
@@ -300,8 +301,8 @@ cudaError_t isomc_launch_scan(const Geo &g, uint32_t ppl, uint32_t *rowV, uint32
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,
-                                    cudaStream_t st) {
-    k_slab_bases<<<1, 32, 0, st>>>(gathered, rank, ghost, vofs);
+                                    unsigned long long *ofs64, cudaStream_t st) {
+    k_slab_bases<<<1, 32, 0, st>>>(gathered, rank, ghost, vofs, ofs64);
     return cudaGetLastError();
 }
 

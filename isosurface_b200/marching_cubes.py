@@ -50,6 +50,9 @@ class MarchingCubes:
             return
         if isinstance(src, DenseGrid) and not src.on_device:
             xyz, idx = self.extract_host(src)  # host lattice in, host mesh out: one pipelined call
+            # extract_host() hands out views of this instance's persistent buffers; an extractor may keep what it is given
+            # (ArrayMesh does), so it gets its own copy -- the next extract() must not change an earlier mesh
+            xyz, idx = xyz.copy(), idx.copy()
         else:
             self.extract_device(source)
             xyz, idx = self.copy_out()
@@ -58,9 +61,12 @@ class MarchingCubes:
     def extract_host(self, grid, xyz=None, idx=None):
         """Host lattice -> host mesh through `isomc_extract_grid_host_to` (copy-in, kernels and copy-out overlap in
         z-chunks).  `xyz` / `idx` are caller buffers (float32 / uint32, ideally pinned); without them the instance keeps
-        its own, sized from the previous extract.  Returns views of the filled parts."""
+        its own, sized from the previous extract.  Returns VIEWS of the filled parts: with the instance's own buffers they
+        are overwritten by the next extract_host() call on this instance."""
         if grid.size != self.size:
             raise ValueError("grid is for size %d, MarchingCubes for %d" % (grid.size, self.size))
+        if self.distance == "directed":
+            raise TypeError("a dense scalar lattice has no Directed distances; use an implicit source")
         own = xyz is None or idx is None
         if own:
             xyz = getattr(self, "_hxyz", None)
@@ -101,10 +107,15 @@ class MarchingCubes:
         if isinstance(src, DenseGrid):
             if not src.on_device:
                 raise ValueError("enqueue() needs a device-resident grid")
+            if src.size != self.size:
+                raise ValueError("grid is for size %d, MarchingCubes for %d" % (src.size, self.size))
+            if self.distance == "directed":
+                raise TypeError("a dense scalar lattice has no Directed distances; use an implicit source")
             _lib.check(self._lib.isomc_enqueue_grid_device(self._h, src.ptr), self._h)
         else:
             prog = encode_program(src)
-            _lib.check(self._lib.isomc_enqueue_sdf(self._h, prog.ctypes.data, len(prog)), self._h)
+            fn = self._lib.isomc_enqueue_sdf_directed if self.distance == "directed" else self._lib.isomc_enqueue_sdf
+            _lib.check(fn(self._h, prog.ctypes.data, len(prog)), self._h)
 
     def finish(self):
         _lib.check(self._lib.isomc_finish(self._h), self._h)
