@@ -115,16 +115,27 @@ __device__ __forceinline__ void tile_mbar_wait(unsigned long long *bar, uint32_t
 }
 #endif
 
+ISOMC_HD uint32_t hd_ldg8(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ldg(p);
+#else
+    return *p;
+#endif
+}
+ISOMC_HD uint32_t hd_ldg16(const uint16_t *p) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ldg(p);
+#else
+    return *p;
+#endif
+}
+
 /* ---- pass 1 ------------------------------------------------------------------------------------------------ */
 
 template <int NS, int NC>
 struct alignas(16) CountSmem {
     float slot[NS][NC][TILE_Y + 1][TILE_PITCH];
     uint32_t sgn[2][TILE_Y + 1][TILE_NW];
-    uint16_t desc[TILE_Y][TILE_X];
-    uint16_t emask[256];
-    uint8_t ntri[256];
-    uint8_t rank3[256];
     unsigned long long mbar[NS];
 };
 
@@ -153,6 +164,17 @@ ISOMC_HD float crossing_t(float a, float b) { /* Signed::find_crossing_point, di
     return (delta == 0.0f) ? 0.5f : hd_div(-a, delta);
 }
 
+/* position of the n-th (0-based) set bit of m; n < popc(m) */
+ISOMC_HD uint32_t nth_bit(uint32_t m, uint32_t n) {
+    uint32_t pos = 0;
+#pragma unroll
+    for (uint32_t wd = 16; wd; wd >>= 1) {
+        const uint32_t c = hd_popc((m >> pos) & ((1u << wd) - 1u));
+        if (n >= c) { n -= c; pos += wd; }
+    }
+    return pos;
+}
+
 struct CountCtx {          /* warp-uniform state of a counting CTA that lives across items */
     Cursor curE, curT;
     uint32_t phase;        /* bit s: parity of the next wait on mbarrier s */
@@ -170,6 +192,13 @@ ISOMC_HD void tile_fill_sync(const Cta &c, const Geo &g, const Src &src, CountSm
 #pragma unroll
         for (int k = 0; k < NC; ++k) S.slot[s][k][r][xx] = v[k];
     }
+}
+
+/* inside bit of the staged sample (row r, column xx): `!(v > 0)`; Directed: outside iff any component is positive */
+template <int NS, int NC>
+ISOMC_HD bool tile_inside(const CountSmem<NS, NC> &S, uint32_t s, uint32_t r, uint32_t xx) {
+    if (NC == 1) return !(S.slot[s][0][r][xx] > 0.0f);
+    return !(S.slot[s][0][r][xx] > 0.0f || S.slot[s][NC > 1 ? 1 : 0][r][xx] > 0.0f || S.slot[s][NC > 2 ? 2 : 0][r][xx] > 0.0f);
 }
 
 /*
@@ -193,11 +222,12 @@ ISOMC_HD void tile_count_item(const Cta &c, const Geo &g, const TileGeo &tg, con
         (void)s;
 #if defined(__CUDA_ARCH__)
         if constexpr (Src::ASYNC) {
-            if (c.tid == 0) {
+            if (warp == 0) { /* one bulk copy per sample row, issued by as many lanes */
                 const uint32_t nfl = g.N - x0 < TILE_PITCH ? g.N - x0 : TILE_PITCH; /* floats per row (N % 4 == 0) */
-                tile_mbar_expect_tx(&S.mbar[s], nsr * nfl * 4u);
-                const float *p = src.base() + ((uint64_t)L * g.N + y0) * g.N + x0;
-                for (uint32_t r = 0; r < nsr; ++r) tile_bulk_g2s(&S.slot[s][0][r][0], p + (uint64_t)r * g.N, nfl * 4u, &S.mbar[s]);
+                if (lane == 0) tile_mbar_expect_tx(&S.mbar[s], nsr * nfl * 4u);
+                __syncwarp();
+                if (lane < nsr)
+                    tile_bulk_g2s(&S.slot[s][0][lane][0], src.base() + ((uint64_t)L * g.N + y0 + lane) * g.N + x0, nfl * 4u, &S.mbar[s]);
             }
             return;
         }
@@ -216,18 +246,26 @@ ISOMC_HD void tile_count_item(const Cta &c, const Geo &g, const TileGeo &tg, con
 #endif
         cta_sync(c);
     };
-    /* inside bits of sample layer L from its slot */
+    /* inside bits of sample layer L from its slot: warp r takes sample row r (a ballot per 32 samples, lane k keeps word k);
+     * the tile's last sample row is shared out word by word */
     auto signs = [&](uint32_t L) {
         const uint32_t s = (L - l0) % NS, par = (L - l0) & 1u;
-        for (uint32_t t = warp; t < nsr * nwt; t += TILE_Y) {
-            const uint32_t r = t / nwt, k = t - r * nwt, xx = k * 32 + lane;
-            bool inside = false;
-            if (xx < nsx) {
-                if (NC == 1) inside = !(S.slot[s][0][r][xx] > 0.0f);
-                else inside = !(S.slot[s][0][r][xx] > 0.0f || S.slot[s][NC > 1 ? 1 : 0][r][xx] > 0.0f || S.slot[s][NC > 2 ? 2 : 0][r][xx] > 0.0f);
+        if (warp < nrows) {
+            uint32_t mine = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < TILE_X / 32 + 1; ++k) {
+                if (k < nwt) {
+                    const uint32_t xx = k * 32 + lane;
+                    const uint32_t word = w_ballot(w, xx < nsx && tile_inside(S, s, warp, xx));
+                    if (lane == k) mine = word;
+                }
             }
-            const uint32_t word = w_ballot(w, inside);
-            if (lane == 0) S.sgn[par][r][k] = word;
+            if (lane < nwt) S.sgn[par][warp][lane] = mine;
+        }
+        for (uint32_t k = warp; k < nwt; k += TILE_Y) {
+            const uint32_t xx = k * 32 + lane;
+            const uint32_t word = w_ballot(w, xx < nsx && tile_inside(S, s, nrows, xx));
+            if (lane == 0) S.sgn[par][nrows][k] = word;
         }
     };
 
@@ -271,24 +309,25 @@ ISOMC_HD void tile_count_item(const Cta &c, const Geo &g, const TileGeo &tg, con
                 uint32_t tpos = 0;
                 if (rowV) tpos = cursor_alloc(w, X.curT, B.ctr + 1, rowV, B.cap_tb, okT);
                 const bool ok = okE && okT;
-                /* flatten the active bits: desc[k] = segment << 5 | bit, in x order */
-                {
-                    uint32_t k = apre;
-                    for (uint32_t m = C.act; m; m &= m - 1) S.desc[r][k++] = (uint16_t)(lane << 5 | hd_ffs0(m));
-                }
-                w_sync(w);
                 uint32_t carry = 0;
                 const bool zlow = (g.gz0 + lz) == 0;
-                for (uint32_t j0 = 0; j0 < rowA; j0 += 32) {
+                for (uint32_t j0 = 0; j0 < rowA; j0 += 32) { /* lane per active cell, in x order */
                     const uint32_t j = j0 + lane;
                     const bool live = j < rowA;
-                    const uint32_t d = live ? (uint32_t)S.desc[r][j] : 0u;
-                    const uint32_t sg = d >> 5, i = d & 31u;
+                    /* the cell's segment: the last lane whose exclusive prefix of active cells is <= j (lanes past the row hold rowA) */
+                    uint32_t sg = 0;
+#pragma unroll
+                    for (uint32_t step = 16; step; step >>= 1) {
+                        const uint32_t t = w_shfl(w, apre, sg + step);
+                        if (live && t <= j) sg += step;
+                    }
+                    const uint32_t am = w_shfl(w, C.act, sg), ap = w_shfl(w, apre, sg);
+                    const uint32_t i = live ? nth_bit(am, j - ap) : 0u;
                     const uint32_t a0 = w_shfl(w, C.a0, sg), b0 = w_shfl(w, C.b0, sg), c0 = w_shfl(w, C.c0, sg), d0 = w_shfl(w, C.d0, sg);
                     const uint32_t nb = w_shfl(w, C.nb, sg), vp = w_shfl(w, vpre, sg);
                     const uint32_t p0 = w_shfl(w, C.p0, sg), p1 = w_shfl(w, C.p1, sg), p2 = w_shfl(w, C.p2, sg), p3 = w_shfl(w, C.p3, sg);
                     const uint32_t ci = seg_cube_index(a0, b0, c0, d0, nb, i);
-                    const uint32_t nt = live ? (uint32_t)S.ntri[ci] : 0u;
+                    const uint32_t nt = live ? (uint32_t)hd_ldg8(&tabg->ntri[ci]) : 0u;
                     uint32_t tt;
                     const uint32_t tpre = w_excl_scan(w, nt, tt) + carry;
                     carry += tt;
@@ -297,11 +336,11 @@ ISOMC_HD void tile_count_item(const Cta &c, const Geo &g, const TileGeo &tg, con
                     if (live && ok) {
                         B.ent[epos + j] = tile_entry_pack(vrel, tpre, tx, ci);
                         /* crossing parameters of the edges this cell creates, at their rank */
-                        const uint32_t em = S.emask[ci];
+                        const uint32_t em = hd_ldg16(&tabg->emask[ci]);
                         float *tp = B.tbuf + tpos + vrel;
                         if (!zlow && y != 0 && (x0 + tx) != 0) { /* creates its crossed e5 (y), e6 (x), e10 (z): all end at corner 6 */
-                            const uint32_t r3 = S.rank3[ci];
-                            const int cx = NC > 2 ? 0 : 0, cy = NC > 2 ? 1 : 0, cz = NC > 2 ? 2 : 0;
+                            const uint32_t r3 = hd_ldg8(&tabg->rank3[ci]);
+                            const int cx = 0, cy = NC > 2 ? 1 : 0, cz = NC > 2 ? 2 : 0;
                             if (em >> 5 & 1u) tp[r3 & 3u] = crossing_t(S.slot[st][cy][r][tx + 1], S.slot[st][cy][r + 1][tx + 1]);
                             if (em >> 6 & 1u) tp[r3 >> 2 & 3u] = crossing_t(S.slot[st][cx][r + 1][tx + 1], S.slot[st][cx][r + 1][tx]);
                             if (em >> 10 & 1u) tp[r3 >> 4 & 3u] = crossing_t(S.slot[sb][cz][r + 1][tx + 1], S.slot[st][cz][r + 1][tx + 1]);
@@ -346,21 +385,22 @@ constexpr uint32_t PL_ROWS = PL_ZROW + TILE_Y + 1;       /* 43 */
 constexpr uint32_t INFO_K = 2 * (TILE_Y + 1);            /* 18 row pieces a tile layer looks at */
 
 struct LayerInfo {          /* k = 0..8: halo column (x tile - 1), rows -1..7;  k = 9: halo row;  k = 10..17: own rows */
-    uint32_t V[INFO_K], T[INFO_K], E[INFO_K], Tp[INFO_K], A[INFO_K];
-    uint32_t cum[32];       /* phase-A sequence: prefix of the lengths (halo column cells: 0/1 each), padded with the total */
+    uint32_t V[INFO_K], T[INFO_K], E[INFO_K], Tp[INFO_K];
+    uint16_t A[INFO_K];
+    uint16_t cum[32];       /* phase-A sequence: prefix of the lengths (halo column cells: 0/1 each), padded with the total */
 };
 
 struct alignas(16) EmitSmem {
     int16_t plane[PL_ROWS * PL_PITCH + 2];
-    LayerInfo li[2];
+    LayerInfo li[EMIT_ZC + 1]; /* every layer of the item, the warm-up layer first */
     uint32_t flatB[PL_ROWS + 5]; /* id base of every plane row (+ vofs) */
     unsigned long long tri[256]; /* 15 nibbles + triangle count << 60 */
     uint16_t emask[256];
     uint8_t rank3[256];
-    uint32_t etab[2][12];        /* [cell-layer parity][edge]: plane row at ty = 0 | dx << 8 | dy << 9 */
+    uint32_t etab[2][12];        /* [cell-layer parity][edge]: plane row at ty = 0 | dx << 8 | dy << 9 | (row * PL_PITCH + dx) << 12 */
 };
 
-/* plane location of edge e of the cell (tx, ty) on a cell layer of parity par: row index at ty = 0, dx, dy */
+/* plane location of edge e of the cell (tx, ty) on a cell layer of parity par: row index at ty = 0, dx, dy, flat offset */
 static inline uint32_t tile_edge_loc(uint32_t par, uint32_t e) {
     static const uint8_t kind[12] = {0, 1, 0, 1, 0, 1, 0, 1, 2, 2, 2, 2};   /* X, Y, Z plane */
     static const uint8_t top[12] = {0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0};
@@ -369,7 +409,7 @@ static inline uint32_t tile_edge_loc(uint32_t par, uint32_t e) {
     const uint32_t p = par ^ top[e];
     uint32_t row = kind[e] == 0 ? PL_XROW + p * (TILE_Y + 1) : kind[e] == 1 ? PL_YROW + p * TILE_Y : PL_ZROW;
     row += dy[e];
-    return row | (uint32_t)dx[e] << 8 | (uint32_t)dy[e] << 9;
+    return row | (uint32_t)dx[e] << 8 | (uint32_t)dy[e] << 9 | (row * PL_PITCH + dx[e]) << 12;
 }
 
 struct EmitParams {
@@ -386,49 +426,17 @@ struct EmitParams {
 };
 
 /* position of the vertex on edge e of cell (x, y, gz): p_a*(1-t) + p_b*t per component (distance.rs:64-69, vector.rs:56-79),
- * corner coordinates (i as f32) * inv (primal_grid.rs:50,63-67) */
-ISOMC_HD void tile_vertex_store(const Geo &g, const EmitTab *tabg, float *o, uint32_t e, uint32_t x, uint32_t y, uint32_t gz, float t) {
-    const uint32_t en = tabg->ends[e];
+ * corner coordinates (i as f32) * inv (primal_grid.rs:50,63-67).  f[axis][0/1] = coordinate of the cell's low / high corner. */
+struct CellCorners { float x0, x1, y0, y1, z0, z1; };
+ISOMC_HD void tile_vertex_store(float *o, uint32_t en, const CellCorners &f, float t) {
     const float omt = hd_sub(1.0f, t);
-    const float pax = hd_mul((float)(x + (en & 1u)), g.inv), pay = hd_mul((float)(y + (en >> 1 & 1u)), g.inv), paz = hd_mul((float)(gz + (en >> 2 & 1u)), g.inv);
-    const float pbx = hd_mul((float)(x + (en >> 4 & 1u)), g.inv), pby = hd_mul((float)(y + (en >> 5 & 1u)), g.inv), pbz = hd_mul((float)(gz + (en >> 6 & 1u)), g.inv);
-    o[0] = hd_add(hd_mul(pax, omt), hd_mul(pbx, t));
-    o[1] = hd_add(hd_mul(pay, omt), hd_mul(pby, t));
-    o[2] = hd_add(hd_mul(paz, omt), hd_mul(pbz, t));
-}
-
-/* info of layer lz -> smem (one warp): what the 18 row pieces hold, the phase-A sequence */
-ISOMC_HD void tile_info_load(const Warp &w, const Geo &g, const TileGeo &tg, const EmitParams &P, uint32_t xt, uint32_t y0, uint32_t lz,
-                             uint32_t vals[5]) {
-    const uint32_t k = w.lane;
-    vals[0] = vals[1] = vals[2] = vals[3] = vals[4] = 0;
-    if (k < INFO_K) {
-        const bool xh = k < TILE_Y + 1;
-        const int32_t row = xh ? (int32_t)k - 1 : (int32_t)k - (int32_t)(TILE_Y + 2);
-        const int64_t y = (int64_t)y0 + row;
-        if (y >= 0 && y < (int64_t)g.ncx && (!xh || xt > 0)) {
-            const uint32_t p = (lz * g.ncx + (uint32_t)y) * tg.nxt + xt - (xh ? 1u : 0u);
-            vals[0] = P.pV[p];
-            const uint32_t a = P.pA[p];
-            vals[4] = a;
-            if (a) { vals[1] = P.pT[p]; vals[2] = P.pE[p]; vals[3] = P.pTp[p]; }
-        }
-    }
-}
-ISOMC_HD void tile_info_store(const Warp &w, LayerInfo &I, const uint32_t vals[5]) {
-    const uint32_t k = w.lane;
-    uint32_t len = 0;
-    if (k < INFO_K) {
-        I.V[k] = vals[0]; I.T[k] = vals[1]; I.E[k] = vals[2]; I.Tp[k] = vals[3]; I.A[k] = vals[4];
-        len = k < TILE_Y + 1 ? (vals[4] ? 1u : 0u) : vals[4];
-    }
-    uint32_t tot;
-    const uint32_t ex = w_excl_scan(w, len, tot);
-    I.cum[k] = k < INFO_K ? ex : tot;
+    o[0] = hd_add(hd_mul((en & 1u) ? f.x1 : f.x0, omt), hd_mul((en >> 4 & 1u) ? f.x1 : f.x0, t));
+    o[1] = hd_add(hd_mul((en >> 1 & 1u) ? f.y1 : f.y0, omt), hd_mul((en >> 5 & 1u) ? f.y1 : f.y0, t));
+    o[2] = hd_add(hd_mul((en >> 2 & 1u) ? f.z1 : f.z0, omt), hd_mul((en >> 6 & 1u) ? f.z1 : f.z0, t));
 }
 
 /*
- * One work item of pass 2: cell layers [l0, l1) of tile column `col` (plus phase A of layer l0 - 1).
+ * One work item of pass 2: cell layers [l0, l1) (at most EMIT_ZC) of tile column `col`, plus phase A of layer l0 - 1.
  */
 ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, EmitSmem &S, const EmitParams &P, const EmitTab *tabg,
                              uint32_t col, uint32_t l0, uint32_t l1) {
@@ -436,107 +444,147 @@ ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, Emit
     const uint32_t warp = c.tid >> 5;
     const uint32_t xt = col % tg.nxt, yt = col / tg.nxt;
     const uint32_t x0 = xt * TILE_X, y0 = yt * TILE_Y;
-    const uint32_t la = l0 > 0 ? l0 - 1 : 0;
+    const uint32_t la = l0 > 0 ? l0 - 1 : 0, nl = l1 - la;
 
     cta_sync(c); /* the previous item is done with the shared state */
-    if (warp == 0) {
-        uint32_t vals[5];
-        tile_info_load(w, g, tg, P, xt, y0, la, vals);
-        tile_info_store(w, S.li[la & 1u], vals);
+    /* what the 18 row pieces of every layer hold (an empty piece still has its id base) */
+    for (uint32_t i = c.tid; i < nl * INFO_K; i += TILE_NT) {
+        const uint32_t l = i / INFO_K, k = i - l * INFO_K;
+        const bool xh = k < TILE_Y + 1;
+        const int32_t row = xh ? (int32_t)k - 1 : (int32_t)k - (int32_t)(TILE_Y + 2);
+        const int64_t y = (int64_t)y0 + row;
+        uint32_t v = 0, t = 0, e = 0, tp = 0, a = 0;
+        if (y >= 0 && y < (int64_t)g.ncx && (!xh || xt > 0)) {
+            const uint32_t p = ((la + l) * g.ncx + (uint32_t)y) * tg.nxt + xt - (xh ? 1u : 0u);
+            v = P.pV[p];
+            a = P.pA[p];
+            if (a) { t = P.pT[p]; e = P.pE[p]; tp = P.pTp[p]; }
+        }
+        LayerInfo &I = S.li[l];
+        I.V[k] = v; I.T[k] = t; I.E[k] = e; I.Tp[k] = tp; I.A[k] = (uint16_t)a;
     }
+    cta_sync(c);
+    for (uint32_t l = warp; l < nl; l += TILE_Y) { /* the phase-A sequence of every layer */
+        LayerInfo &I = S.li[l];
+        const uint32_t k = w.lane;
+        uint32_t len = 0;
+        if (k < INFO_K) len = k < TILE_Y + 1 ? (I.A[k] ? 1u : 0u) : I.A[k];
+        uint32_t tot;
+        const uint32_t ex = w_excl_scan(w, len, tot);
+        I.cum[k] = (uint16_t)(k < INFO_K ? ex : tot);
+    }
+    cta_sync(c);
 
     for (uint32_t lz = la; lz < l1; ++lz) {
-        cta_sync(c); /* (A) info of this layer is visible; the planes of two layers ago may be overwritten */
-        const LayerInfo &I = S.li[lz & 1u];
-        const LayerInfo &Iprev = S.li[(lz & 1u) ^ 1u];
+        const LayerInfo &I = S.li[lz - la];
+        const uint32_t nA = I.cum[31];
+        if (!nA) continue; /* nothing created here: nothing to write, and nothing above can refer to this layer */
+        cta_sync(c); /* (A) the planes of the layers below may be overwritten */
         const uint32_t par = lz & 1u, gz = g.gz0 + lz;
         const bool emit = lz >= l0 && lz >= P.first_own_layer;
-        const uint32_t nA = I.cum[31];
-        /* next layer's info: loads now, stores after phase A */
-        uint32_t nvals[5];
-        const bool prefetch = warp == TILE_Y - 1 && lz + 1 < l1;
-        if (prefetch) tile_info_load(w, g, tg, P, xt, y0, lz + 1, nvals);
-        if (nA) {
-            /* id base of every plane row: the row piece of the cells that create the edges in it */
-            if (c.tid < PL_ROWS) {
-                const uint32_t i = c.tid;
-                uint32_t k;       /* info slot of the creating piece */
-                bool bottom;      /* plane of the cell layer's lower sample layer */
-                if (i < PL_YROW) {
-                    const uint32_t p = i / (TILE_Y + 1), py = i - p * (TILE_Y + 1);
-                    bottom = p == par;
-                    k = (y0 + py == 0) ? TILE_Y + 2 : TILE_Y + 1 + py;
-                } else if (i < PL_ZROW) {
-                    const uint32_t p = (i - PL_YROW) / TILE_Y, cy = (i - PL_YROW) - p * TILE_Y;
-                    bottom = p == par;
-                    k = TILE_Y + 2 + cy;
-                } else {
-                    const uint32_t py = i - PL_ZROW;
-                    bottom = false;
-                    k = (y0 + py == 0) ? TILE_Y + 2 : TILE_Y + 1 + py;
-                }
-                /* edges in the lower sample layer were created one cell layer down -- except on the lattice's z = 0 face */
-                const LayerInfo &J = (bottom && gz != 0) ? Iprev : I;
-                S.flatB[i] = J.V[k] + P.vofs;
+        /* id base of every plane row: the row piece of the cells that create the edges in it */
+        if (c.tid < PL_ROWS) {
+            const uint32_t i = c.tid;
+            uint32_t k;       /* info slot of the creating piece */
+            bool bottom;      /* plane of the cell layer's lower sample layer */
+            if (i < PL_YROW) {
+                const uint32_t p = i / (TILE_Y + 1), py = i - p * (TILE_Y + 1);
+                bottom = p == par;
+                k = (y0 + py == 0) ? TILE_Y + 2 : TILE_Y + 1 + py;
+            } else if (i < PL_ZROW) {
+                const uint32_t p = (i - PL_YROW) / TILE_Y, cy = (i - PL_YROW) - p * TILE_Y;
+                bottom = p == par;
+                k = TILE_Y + 2 + cy;
+            } else {
+                const uint32_t py = i - PL_ZROW;
+                bottom = false;
+                k = (y0 + py == 0) ? TILE_Y + 2 : TILE_Y + 1 + py;
             }
-            for (uint32_t j0 = 0; j0 < nA; j0 += TILE_NT) {
-                const uint32_t j = j0 + c.tid;
-                bool have = j < nA;
-                uint32_t k = 0;
-                if (have) { /* largest k with cum[k] <= j */
+            /* edges in the lower sample layer were created one cell layer down -- except on the lattice's z = 0 face */
+            const LayerInfo &J = (bottom && gz != 0 && lz > la) ? S.li[lz - la - 1] : I;
+            S.flatB[i] = J.V[k] + P.vofs;
+        }
+        const float fz0 = hd_mul((float)gz, g.inv), fz1 = hd_mul((float)(gz + 1), g.inv);
+        for (uint32_t j0 = 0; j0 < nA; j0 += TILE_NT) {
+            const uint32_t j = j0 + c.tid;
+            bool have = j < nA;
+            uint32_t k = 0;
+            if (have) { /* largest k with cum[k] <= j */
 #pragma unroll
-                    for (uint32_t step = 16; step; step >>= 1)
-                        if (I.cum[k + step] <= j) k += step;
-                }
-                const bool xh = k < TILE_Y + 1;
-                uint2 ea = make_uint2(0u, 0u);
-                if (have) ea = P.ent[xh ? I.E[k] + I.A[k] - 1u : I.E[k] + (j - I.cum[k])];
-                if (xh && (ea.y & 511u) != TILE_X - 1) have = false; /* the piece's last cell is not the tile's neighbour */
-                const int32_t tx = xh ? -1 : (int32_t)(ea.y & 511u);
-                const int32_t ty = xh ? (int32_t)k - 1 : (int32_t)k - (int32_t)(TILE_Y + 2);
-                const uint32_t ci = ea.y >> 9 & 255u, vrel = ea.x & 8191u, tpre = ea.x >> 13 & 4095u;
-                const uint32_t x = x0 + (uint32_t)tx, y = y0 + (uint32_t)ty;
+                for (uint32_t step = 16; step; step >>= 1)
+                    if (I.cum[k + step] <= j) k += step;
+            }
+            const bool xh = k < TILE_Y + 1;
+            uint2 ea = make_uint2(0u, 0u);
+            if (have) ea = P.ent[xh ? I.E[k] + I.A[k] - 1u : I.E[k] + (j - I.cum[k])];
+            if (xh && (ea.y & 511u) != TILE_X - 1) have = false; /* the piece's last cell is not the tile's neighbour */
+            const int32_t tx = xh ? -1 : (int32_t)(ea.y & 511u);
+            const int32_t ty = xh ? (int32_t)k - 1 : (int32_t)k - (int32_t)(TILE_Y + 2);
+            const uint32_t ci = ea.y >> 9 & 255u, vrel = ea.x & 8191u, tpre = ea.x >> 13 & 4095u;
+            const uint32_t x = x0 + (uint32_t)tx, y = y0 + (uint32_t)ty;
+            const bool own = have && !xh && ty >= 0;
+            const int32_t cell = ty * (int32_t)PL_PITCH + tx;
+            if (have) {
                 const uint32_t em = S.emask[ci];
-                const bool own = have && !xh && ty >= 0;
-                const uint32_t ko = (uint32_t)(ty + (int32_t)(TILE_Y + 2)); /* own-tile piece of the cell's row */
-                if (have) {
-                    /* ids are stored relative to the base of the plane row = the own-tile piece of the creating row */
-                    const int32_t rel0 = (int32_t)(I.V[k] - I.V[ko]) + (int32_t)vrel;
-                    const uint32_t fl = (x == 0 ? 1u : 0u) | (y == 0 ? 2u : 0u) | (gz == 0 ? 4u : 0u);
-                    const uint32_t owned = em & (fl ? (uint32_t)tabg->ownmask[fl] : (1u << 5 | 1u << 6 | 1u << 10));
+                const uint32_t fl = (x == 0 ? 1u : 0u) | (y == 0 ? 2u : 0u) | (gz == 0 ? 4u : 0u);
+                /* ids are stored relative to the base of the plane row = the own-tile piece of the creating row */
+                const uint32_t ko = (uint32_t)(ty + (int32_t)(TILE_Y + 2));
+                const int32_t rel0 = (int32_t)(I.V[k] - I.V[ko]) + (int32_t)vrel;
+                const uint64_t vslot0 = (uint64_t)I.V[k] + vrel - P.ghostV;
+                const float *tp = P.tbuf + I.Tp[k] + vrel;
+                const bool put = own && emit;
+                CellCorners f;
+                f.x0 = hd_mul((float)x, g.inv); f.x1 = hd_mul((float)(x + 1), g.inv);
+                f.y0 = hd_mul((float)y, g.inv); f.y1 = hd_mul((float)(y + 1), g.inv);
+                f.z0 = fz0; f.z1 = fz1;
+                if (fl == 0 && own) { /* an interior cell of the tile creates its crossed e5, e6, e10 */
                     const uint32_t r3 = S.rank3[ci];
-                    const uint64_t vslot0 = (uint64_t)I.V[k] + vrel - P.ghostV;
-                    const float *tp = P.tbuf + I.Tp[k] + vrel;
+                    const uint32_t l5 = S.etab[par][5] >> 12, l6 = S.etab[par][6] >> 12, l10 = S.etab[par][10] >> 12;
+                    if (em >> 5 & 1u) {
+                        const uint32_t rank = r3 & 3u;
+                        S.plane[(int32_t)l5 + cell] = (int16_t)(rel0 + (int32_t)rank);
+                        if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), 0x75u, f, tp[rank]);  /* corners 5 -> 6 */
+                    }
+                    if (em >> 6 & 1u) {
+                        const uint32_t rank = r3 >> 2 & 3u;
+                        S.plane[(int32_t)l6 + cell] = (int16_t)(rel0 + (int32_t)rank);
+                        if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), 0x67u, f, tp[rank]);  /* corners 6 -> 7 */
+                    }
+                    if (em >> 10 & 1u) {
+                        const uint32_t rank = r3 >> 4 & 3u;
+                        S.plane[(int32_t)l10 + cell] = (int16_t)(rel0 + (int32_t)rank);
+                        if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), 0x73u, f, tp[rank]);  /* corners 2 -> 6 */
+                    }
+                } else { /* on a low face of the lattice, or a halo cell: the general tables, range-checked */
+                    const uint32_t owned = em & (uint32_t)tabg->ownmask[fl];
                     for (uint32_t m = owned; m; m &= m - 1) {
                         const uint32_t e = hd_ffs0(m);
-                        const uint32_t rank = fl ? hd_popc(tabg->before[ci][e] & owned) : (r3 >> (e == 5 ? 0 : e == 6 ? 2 : 4) & 3u);
+                        const uint32_t rank = hd_popc(tabg->before[ci][e] & owned);
                         const uint32_t loc = S.etab[par][e];
                         if ((ty >= 0 || (loc >> 9 & 1u)) && (tx >= 0 || (loc >> 8 & 1u)))
-                            S.plane[(int32_t)((loc & 255u) * PL_PITCH) + ty * (int32_t)PL_PITCH + tx + (int32_t)(loc >> 8 & 1u)] = (int16_t)(rel0 + (int32_t)rank);
-                        if (own && emit && vslot0 + rank < P.cap_v) tile_vertex_store(g, tabg, P.xyz + 3 * (vslot0 + rank), e, x, y, gz, tp[rank]);
+                            S.plane[(int32_t)(loc >> 12) + cell] = (int16_t)(rel0 + (int32_t)rank);
+                        if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), tabg->ends[e], f, tp[rank]);
                     }
                 }
-                cta_sync(c); /* (B) the ids of this round (and of all earlier cells) are in the planes */
-                if (own && emit) {
-                    unsigned long long tri = S.tri[ci];
-                    uint32_t nt = (uint32_t)(tri >> 60);
-                    const uint64_t tslot = (uint64_t)I.T[k] + tpre - P.ghostT;
-                    if (tslot >= P.cap_t) nt = 0;
-                    else if (tslot + nt > P.cap_t) nt = (uint32_t)(P.cap_t - tslot);
-                    uint32_t *o = P.idx + 3 * tslot;
-                    const int32_t cell = ty * (int32_t)PL_PITCH + tx;
-                    for (uint32_t t = 0; t < nt; ++t, tri >>= 12, o += 3) {
+            }
+            cta_sync(c); /* (B) the ids of this round (and of all earlier cells) are in the planes */
+            if (own && emit) {
+                unsigned long long tri = S.tri[ci];
+                uint32_t nt = (uint32_t)(tri >> 60);
+                const uint64_t tslot = (uint64_t)I.T[k] + tpre - P.ghostT;
+                if (tslot >= P.cap_t) nt = 0;
+                else if (tslot + nt > P.cap_t) nt = (uint32_t)(P.cap_t - tslot);
+                uint32_t *o = P.idx + 3 * tslot;
+                const uint32_t *et = S.etab[par];
+                for (uint32_t t = 0; t < nt; ++t, tri >>= 12, o += 3) {
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            const uint32_t loc = S.etab[par][(uint32_t)(tri >> (4 * q)) & 15u];
-                            const uint32_t row = (loc & 255u) + (uint32_t)ty;
-                            o[q] = S.flatB[row] + (uint32_t)(int32_t)S.plane[(int32_t)((loc & 255u) * PL_PITCH) + cell + (int32_t)(loc >> 8 & 1u)];
-                        }
+                    for (int q = 0; q < 3; ++q) {
+                        const uint32_t loc = et[(uint32_t)(tri >> (4 * q)) & 15u];
+                        o[q] = S.flatB[(loc & 255u) + (uint32_t)ty] + (uint32_t)(int32_t)S.plane[(int32_t)(loc >> 12) + cell];
                     }
                 }
             }
         }
-        if (prefetch) tile_info_store(w, S.li[(lz + 1) & 1u], nvals);
     }
 }
 

@@ -78,11 +78,6 @@ __global__ void __launch_bounds__(TILE_NT, MINB) k_tile_count(Src src, Geo g, Ti
     using Smem = CountSmem<Src::NS, Src::NC>;
     Smem &S = *reinterpret_cast<Smem *>(tile_smem_raw);
     __shared__ uint32_t s_item;
-    for (uint32_t i = threadIdx.x; i < 256; i += TILE_NT) {
-        S.emask[i] = tabg->emask[i];
-        S.ntri[i] = tabg->ntri[i];
-        S.rank3[i] = tabg->rank3[i];
-    }
     if (Src::ASYNC && threadIdx.x == 0) {
         for (int s = 0; s < Src::NS; ++s) tile_mbar_init(&S.mbar[s], 1);
         tile_mbar_fence_init();
@@ -206,16 +201,16 @@ cudaError_t isomc_launch_tile_count_grid(const Geo &g, const TileGeo &tg, const 
         plain = (p && strcmp(p, "plain") == 0) ? 1 : 0;
     }
     const bool aligned = (g.N % 4u) == 0 && (reinterpret_cast<uintptr_t>(d_grid) & 15u) == 0;
-    if (aligned && !plain) return launch_count<GridBulkSrc, 3>(GridBulkSrc{d_grid}, g, tg, B, tab, lz0, lz1, ticket, sms, st);
-    return launch_count<GridPlainSrc, 3>(GridPlainSrc{d_grid}, g, tg, B, tab, lz0, lz1, ticket, sms, st);
+    if (aligned && !plain) return launch_count<GridBulkSrc, 4>(GridBulkSrc{d_grid}, g, tg, B, tab, lz0, lz1, ticket, sms, st);
+    return launch_count<GridPlainSrc, 4>(GridPlainSrc{d_grid}, g, tg, B, tab, lz0, lz1, ticket, sms, st);
 }
 
 cudaError_t isomc_launch_tile_count_sdf(const Geo &g, const TileGeo &tg, const SdfProgram &prog, bool directed, const TileBufs &B,
                                         const EmitTab *tab, uint32_t lz0, uint32_t lz1, uint32_t *ticket, int sms, cudaStream_t st) {
     if (directed) return launch_count<SdfDirTileSrc, 1>(SdfDirTileSrc{prog}, g, tg, B, tab, lz0, lz1, ticket, sms, st);
     SdfChainTileSrc csrc;
-    if (sdf_to_chain(prog, &csrc.chain)) return launch_count<SdfChainTileSrc, 3>(csrc, g, tg, B, tab, lz0, lz1, ticket, sms, st);
-    return launch_count<SdfTileSrc, 3>(SdfTileSrc{prog}, g, tg, B, tab, lz0, lz1, ticket, sms, st);
+    if (sdf_to_chain(prog, &csrc.chain)) return launch_count<SdfChainTileSrc, 4>(csrc, g, tg, B, tab, lz0, lz1, ticket, sms, st);
+    return launch_count<SdfTileSrc, 4>(SdfTileSrc{prog}, g, tg, B, tab, lz0, lz1, ticket, sms, st);
 }
 
 cudaError_t isomc_launch_tile_emit(const Geo &g, const TileGeo &tg, const TileBufs &B, const EmitTab *tab, const uint32_t *vofs,

@@ -204,9 +204,6 @@ int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const Src &sr
     {
         auto *S = new CountSmem<Src::NS, Src::NC>();
         memset((void *)S, 0xEE, sizeof *S);
-        memcpy(S->emask, mt.emask, sizeof S->emask);
-        memcpy(S->ntri, mt.ntri, sizeof S->ntri);
-        memcpy(S->rank3, mt.rank3, sizeof S->rank3);
         for (uint32_t ci = 0; ci < n_ctas; ++ci) {
             const std::vector<uint32_t> &items = share[order[ci]];
             if (items.empty()) continue;
