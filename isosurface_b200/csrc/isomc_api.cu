@@ -182,8 +182,12 @@ int32_t ensure_tile_capacity(isomc *h, uint64_t eb, uint64_t tb) {
         return fail(h, ISOMC_ERR_OOM, "entry list of %llu / %llu blocks exceeds the 32-bit positions", (unsigned long long)eb, (unsigned long long)tb);
     if (eb > h->TB.cap_eb) {
         if (h->TB.ent) CU(h, cudaFree(h->TB.ent));
-        h->TB.ent = nullptr; h->TB.cap_eb = 0;
+        if (h->TB.tq) CU(h, cudaFree(h->TB.tq));
+        h->TB.ent = nullptr; h->TB.tq = nullptr; h->TB.cap_eb = 0;
         CU(h, cudaMalloc(&h->TB.ent, eb * ENT_BLOCK * sizeof(uint2)));
+        CU(h, cudaMalloc(&h->TB.tq, eb * ENT_BLOCK * 3 * sizeof(float)));
+        /* pass 2 fetches all three slots of an entry before it knows which are in use: never read uninitialised memory */
+        CU(h, cudaMemsetAsync(h->TB.tq, 0, eb * ENT_BLOCK * 3 * sizeof(float), h->stream));
         h->TB.cap_eb = (uint32_t)eb;
     }
     if (tb > h->TB.cap_tb) {
@@ -499,7 +503,7 @@ int32_t isomc_destroy(isomc_t *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->signs); cudaFree(h->segA); cudaFree(h->rowV); cudaFree(h->rowT); cudaFree(h->rowA);
-    cudaFree(h->TB.pE); cudaFree(h->TB.pTp); cudaFree(h->TB.pA); cudaFree(h->TB.ent); cudaFree(h->TB.tbuf);
+    cudaFree(h->TB.pE); cudaFree(h->TB.pTp); cudaFree(h->TB.pA); cudaFree(h->TB.ent); cudaFree(h->TB.tq); cudaFree(h->TB.tbuf);
     cudaFree(h->layerTot); cudaFree(h->totals); cudaFree(h->vofs); cudaFree(h->tabs);
     cudaFree(h->xyz); cudaFree(h->idx); cudaFree(h->stage_grid);
     cudaFree(h->L.ent); cudaFree(h->L.ent_yz); cudaFree(h->L.segrec); cudaFree(h->L.segtpre); cudaFree(h->L.blkfill); cudaFree(h->etab);

@@ -66,7 +66,8 @@ struct TileBufs {
     uint32_t *pE, *pTp;     /* per row piece: position of its first entry / of its first t value */
     uint16_t *pA;           /* per row piece: active cells */
     uint2 *ent;
-    float *tbuf;
+    float *tq;              /* 3 floats per entry: crossing parameters of the cell's e5, e6, e10 (cells off the low faces) */
+    float *tbuf;            /* crossing parameters of the cells ON the low faces (up to 12 edges each), at piece position + rank */
     uint32_t *ctr;          /* [0] entry blocks handed out, [1] t blocks handed out (may exceed the capacity: the host grows and re-runs) */
     uint32_t cap_eb, cap_tb;
     unsigned long long *layerTot; /* per cell layer: vertices, triangles, active cells */
@@ -250,6 +251,40 @@ ISOMC_HD void tile_count_item(const Cta &c, const Geo &g, const TileGeo &tg, con
      * the tile's last sample row is shared out word by word */
     auto signs = [&](uint32_t L) {
         const uint32_t s = (L - l0) % NS, par = (L - l0) & 1u;
+        if (NC == 1) {
+            /* a lane takes 4 neighbouring samples (one 16-byte shared load), the nibbles of 8 neighbouring lanes make a word.
+             * Samples past the lattice give arbitrary bits: every use masks the cells that do not exist.  Warp r takes sample
+             * row r, the tile's last sample row is shared out chunk by chunk. */
+            const uint32_t sh = (lane & 7u) * 4u;
+            auto chunk = [&](uint32_t r, uint32_t ch) {
+                const uint32_t xx = ch * 128 + lane * 4;
+                float v0 = 1.0f, v1 = 1.0f, v2 = 1.0f, v3 = 1.0f;
+                if (xx < TILE_PITCH) {
+                    const float *q = &S.slot[s][0][r][xx];
+#if defined(__CUDA_ARCH__)
+                    const float4 v = *reinterpret_cast<const float4 *>(q);
+                    v0 = v.x; v1 = v.y; v2 = v.z; v3 = v.w;
+#else
+                    v0 = q[0]; v1 = q[1]; v2 = q[2]; v3 = q[3];
+#endif
+                }
+                uint32_t word = ((!(v0 > 0.0f) ? 1u : 0u) | (!(v1 > 0.0f) ? 2u : 0u) | (!(v2 > 0.0f) ? 4u : 0u) | (!(v3 > 0.0f) ? 8u : 0u)) << sh;
+                word |= w_shfl(w, word, lane ^ 1u);
+                word |= w_shfl(w, word, lane ^ 2u);
+                word |= w_shfl(w, word, lane ^ 4u);
+                const uint32_t k = ch * 4 + (lane >> 3);
+                if ((lane & 7u) == 0 && k < nwt) S.sgn[par][r][k] = word;
+            };
+            constexpr uint32_t NCH = (TILE_X + 127) / 128 + 1;
+            if (warp < nrows) {
+#pragma unroll
+                for (uint32_t ch = 0; ch < NCH; ++ch)
+                    if (ch * 128 < nsx) chunk(warp, ch);
+            }
+            for (uint32_t ch = warp; ch < NCH; ch += TILE_Y)
+                if (ch * 128 < nsx) chunk(nrows, ch);
+            return;
+        }
         if (warp < nrows) {
             uint32_t mine = 0;
 #pragma unroll
@@ -307,10 +342,10 @@ ISOMC_HD void tile_count_item(const Cta &c, const Geo &g, const TileGeo &tg, con
                 bool okE = true, okT = true;
                 const uint32_t epos = cursor_alloc(w, X.curE, B.ctr, rowA, B.cap_eb, okE);
                 uint32_t tpos = 0;
-                if (rowV) tpos = cursor_alloc(w, X.curT, B.ctr + 1, rowV, B.cap_tb, okT);
+                const bool zlow = (g.gz0 + lz) == 0;
+                if (rowV && (zlow || y == 0 || x0 == 0)) tpos = cursor_alloc(w, X.curT, B.ctr + 1, rowV, B.cap_tb, okT); /* rows with cells on a low face */
                 const bool ok = okE && okT;
                 uint32_t carry = 0;
-                const bool zlow = (g.gz0 + lz) == 0;
                 for (uint32_t j0 = 0; j0 < rowA; j0 += 32) { /* lane per active cell, in x order */
                     const uint32_t j = j0 + lane;
                     const bool live = j < rowA;
@@ -337,15 +372,15 @@ ISOMC_HD void tile_count_item(const Cta &c, const Geo &g, const TileGeo &tg, con
                         B.ent[epos + j] = tile_entry_pack(vrel, tpre, tx, ci);
                         /* crossing parameters of the edges this cell creates, at their rank */
                         const uint32_t em = hd_ldg16(&tabg->emask[ci]);
-                        float *tp = B.tbuf + tpos + vrel;
                         if (!zlow && y != 0 && (x0 + tx) != 0) { /* creates its crossed e5 (y), e6 (x), e10 (z): all end at corner 6 */
-                            const uint32_t r3 = hd_ldg8(&tabg->rank3[ci]);
                             const int cx = 0, cy = NC > 2 ? 1 : 0, cz = NC > 2 ? 2 : 0;
-                            if (em >> 5 & 1u) tp[r3 & 3u] = crossing_t(S.slot[st][cy][r][tx + 1], S.slot[st][cy][r + 1][tx + 1]);
-                            if (em >> 6 & 1u) tp[r3 >> 2 & 3u] = crossing_t(S.slot[st][cx][r + 1][tx + 1], S.slot[st][cx][r + 1][tx]);
-                            if (em >> 10 & 1u) tp[r3 >> 4 & 3u] = crossing_t(S.slot[sb][cz][r + 1][tx + 1], S.slot[st][cz][r + 1][tx + 1]);
+                            float *tq = B.tq + 3 * (uint64_t)(epos + j); /* beside the entry: pass 2 fetches both without decoding either */
+                            if (em >> 5 & 1u) tq[0] = crossing_t(S.slot[st][cy][r][tx + 1], S.slot[st][cy][r + 1][tx + 1]);
+                            if (em >> 6 & 1u) tq[1] = crossing_t(S.slot[st][cx][r + 1][tx + 1], S.slot[st][cx][r + 1][tx]);
+                            if (em >> 10 & 1u) tq[2] = crossing_t(S.slot[sb][cz][r + 1][tx + 1], S.slot[st][cz][r + 1][tx + 1]);
                         } else { /* on a low face: also the edges lying in it */
                             const uint32_t owned = em & tabg->ownmask[cell_flags(g, x0 + tx, y, lz)];
+                            float *tp = B.tbuf + tpos + vrel;
                             for (uint32_t m = owned; m; m &= m - 1) {
                                 const uint32_t e = hd_ffs0(m), en = tabg->ends[e];
                                 const uint32_t axis = ((en ^ en >> 4) & 7u) >> 1, pl = NC > 2 ? axis : 0u;
@@ -416,7 +451,7 @@ struct EmitParams {
     const uint32_t *pV, *pT, *pE, *pTp; /* pV / pT hold exclusive prefixes now */
     const uint16_t *pA;
     const uint2 *ent;
-    const float *tbuf;
+    const float *tq, *tbuf;
     uint32_t vofs;                 /* local id -> global id */
     uint32_t ghostV, ghostT;       /* vertices / triangles of a slab's ghost layer: local id / slot -> output slot */
     uint32_t first_own_layer;
@@ -433,6 +468,32 @@ ISOMC_HD void tile_vertex_store(float *o, uint32_t en, const CellCorners &f, flo
     o[0] = hd_add(hd_mul((en & 1u) ? f.x1 : f.x0, omt), hd_mul((en >> 4 & 1u) ? f.x1 : f.x0, t));
     o[1] = hd_add(hd_mul((en >> 1 & 1u) ? f.y1 : f.y0, omt), hd_mul((en >> 5 & 1u) ? f.y1 : f.y0, t));
     o[2] = hd_add(hd_mul((en >> 2 & 1u) ? f.z1 : f.z0, omt), hd_mul((en >> 6 & 1u) ? f.z1 : f.z0, t));
+}
+
+/* what a thread works on in round 0 of a layer: its place in the phase-A sequence, its entry and (own cells) the crossing
+ * parameters stored beside it -- fetched a whole layer ahead, so that no global load latency is left inside a layer */
+struct EmitFetch {
+    uint32_t k;        /* info slot of the entry's row piece; INFO_K = none */
+    uint2 ea;
+    float t5, t6, t10;
+};
+
+ISOMC_HD void emit_fetch(const LayerInfo &I, const EmitParams &P, uint32_t j, EmitFetch &F) {
+    F.k = INFO_K; F.ea = make_uint2(0u, 0u); F.t5 = F.t6 = F.t10 = 0.0f;
+    if (j < I.cum[31]) {
+        uint32_t k = 0; /* largest k with cum[k] <= j */
+#pragma unroll
+        for (uint32_t step = 16; step; step >>= 1)
+            if (I.cum[k + step] <= j) k += step;
+        const bool xh = k < TILE_Y + 1;
+        const uint32_t pos = xh ? I.E[k] + I.A[k] - 1u : I.E[k] + (j - I.cum[k]);
+        F.k = k;
+        F.ea = P.ent[pos];
+        if (k > TILE_Y + 1) {
+            const float *q = P.tq + 3 * (uint64_t)pos;
+            F.t5 = q[0]; F.t6 = q[1]; F.t10 = q[2];
+        }
+    }
 }
 
 /*
@@ -475,11 +536,21 @@ ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, Emit
     }
     cta_sync(c);
 
-    for (uint32_t lz = la; lz < l1; ++lz) {
+    /* first layer that creates anything; its round-0 work is fetched here, every later layer's one layer ahead */
+    uint32_t lz = la;
+    while (lz < l1 && S.li[lz - la].cum[31] == 0) ++lz;
+    EmitFetch F;
+    if (lz < l1) emit_fetch(S.li[lz - la], P, c.tid, F);
+
+    while (lz < l1) {
         const LayerInfo &I = S.li[lz - la];
         const uint32_t nA = I.cum[31];
-        if (!nA) continue; /* nothing created here: nothing to write, and nothing above can refer to this layer */
         cta_sync(c); /* (A) the planes of the layers below may be overwritten */
+        uint32_t lzn = lz + 1; /* next layer that creates anything (nothing can refer to a layer that creates nothing) */
+        while (lzn < l1 && S.li[lzn - la].cum[31] == 0) ++lzn;
+        EmitFetch Fn;
+        Fn.k = INFO_K; Fn.ea = make_uint2(0u, 0u); Fn.t5 = Fn.t6 = Fn.t10 = 0.0f;
+        if (lzn < l1) emit_fetch(S.li[lzn - la], P, c.tid, Fn);
         const uint32_t par = lz & 1u, gz = g.gz0 + lz;
         const bool emit = lz >= l0 && lz >= P.first_own_layer;
         /* id base of every plane row: the row piece of the cells that create the edges in it */
@@ -506,17 +577,11 @@ ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, Emit
         }
         const float fz0 = hd_mul((float)gz, g.inv), fz1 = hd_mul((float)(gz + 1), g.inv);
         for (uint32_t j0 = 0; j0 < nA; j0 += TILE_NT) {
-            const uint32_t j = j0 + c.tid;
-            bool have = j < nA;
-            uint32_t k = 0;
-            if (have) { /* largest k with cum[k] <= j */
-#pragma unroll
-                for (uint32_t step = 16; step; step >>= 1)
-                    if (I.cum[k + step] <= j) k += step;
-            }
+            if (j0) emit_fetch(I, P, j0 + c.tid, F); /* (rounds beyond the first: more than TILE_NT entries in a tile layer) */
+            bool have = F.k < INFO_K;
+            const uint32_t k = have ? F.k : 0u;
             const bool xh = k < TILE_Y + 1;
-            uint2 ea = make_uint2(0u, 0u);
-            if (have) ea = P.ent[xh ? I.E[k] + I.A[k] - 1u : I.E[k] + (j - I.cum[k])];
+            const uint2 ea = F.ea;
             if (xh && (ea.y & 511u) != TILE_X - 1) have = false; /* the piece's last cell is not the tile's neighbour */
             const int32_t tx = xh ? -1 : (int32_t)(ea.y & 511u);
             const int32_t ty = xh ? (int32_t)k - 1 : (int32_t)k - (int32_t)(TILE_Y + 2);
@@ -531,32 +596,32 @@ ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, Emit
                 const uint32_t ko = (uint32_t)(ty + (int32_t)(TILE_Y + 2));
                 const int32_t rel0 = (int32_t)(I.V[k] - I.V[ko]) + (int32_t)vrel;
                 const uint64_t vslot0 = (uint64_t)I.V[k] + vrel - P.ghostV;
-                const float *tp = P.tbuf + I.Tp[k] + vrel;
                 const bool put = own && emit;
                 CellCorners f;
                 f.x0 = hd_mul((float)x, g.inv); f.x1 = hd_mul((float)(x + 1), g.inv);
                 f.y0 = hd_mul((float)y, g.inv); f.y1 = hd_mul((float)(y + 1), g.inv);
                 f.z0 = fz0; f.z1 = fz1;
-                if (fl == 0 && own) { /* an interior cell of the tile creates its crossed e5, e6, e10 */
+                if (fl == 0 && own) { /* a cell off the low faces creates its crossed e5, e6, e10 */
                     const uint32_t r3 = S.rank3[ci];
                     const uint32_t l5 = S.etab[par][5] >> 12, l6 = S.etab[par][6] >> 12, l10 = S.etab[par][10] >> 12;
                     if (em >> 5 & 1u) {
                         const uint32_t rank = r3 & 3u;
                         S.plane[(int32_t)l5 + cell] = (int16_t)(rel0 + (int32_t)rank);
-                        if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), 0x75u, f, tp[rank]);  /* corners 5 -> 6 */
+                        if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), 0x75u, f, F.t5);  /* corners 5 -> 6 */
                     }
                     if (em >> 6 & 1u) {
                         const uint32_t rank = r3 >> 2 & 3u;
                         S.plane[(int32_t)l6 + cell] = (int16_t)(rel0 + (int32_t)rank);
-                        if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), 0x67u, f, tp[rank]);  /* corners 6 -> 7 */
+                        if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), 0x67u, f, F.t6);  /* corners 6 -> 7 */
                     }
                     if (em >> 10 & 1u) {
                         const uint32_t rank = r3 >> 4 & 3u;
                         S.plane[(int32_t)l10 + cell] = (int16_t)(rel0 + (int32_t)rank);
-                        if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), 0x73u, f, tp[rank]);  /* corners 2 -> 6 */
+                        if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), 0x73u, f, F.t10); /* corners 2 -> 6 */
                     }
                 } else { /* on a low face of the lattice, or a halo cell: the general tables, range-checked */
                     const uint32_t owned = em & (uint32_t)tabg->ownmask[fl];
+                    const float *tp = P.tbuf + I.Tp[k] + vrel;
                     for (uint32_t m = owned; m; m &= m - 1) {
                         const uint32_t e = hd_ffs0(m);
                         const uint32_t rank = hd_popc(tabg->before[ci][e] & owned);
@@ -585,6 +650,8 @@ ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, Emit
                 }
             }
         }
+        F = Fn;
+        lz = lzn;
     }
 }
 

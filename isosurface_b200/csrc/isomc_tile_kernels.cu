@@ -108,7 +108,7 @@ struct EmitArgsDev {
     const uint32_t *pV, *pT, *pE, *pTp;
     const uint16_t *pA;
     const uint2 *ent;
-    const float *tbuf;
+    const float *tq, *tbuf;
     const uint32_t *vofs_ptr;
     const unsigned long long *layerTot;
     const uint32_t *ctr;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(TILE_NT, 4) k_tile_emit(Geo g, TileGeo tg, Emi
     if (threadIdx.x < 24) S.etab[threadIdx.x / 12][threadIdx.x % 12] = tabg->eloc[threadIdx.x / 12][threadIdx.x % 12];
     EmitParams P;
     P.pV = A.pV; P.pT = A.pT; P.pE = A.pE; P.pTp = A.pTp; P.pA = A.pA;
-    P.ent = A.ent; P.tbuf = A.tbuf;
+    P.ent = A.ent; P.tq = A.tq; P.tbuf = A.tbuf;
     P.vofs = *A.vofs_ptr;
     P.ghostV = g.ghost ? (uint32_t)A.layerTot[0] : 0u;
     P.ghostT = g.ghost ? (uint32_t)A.layerTot[1] : 0u;
@@ -224,7 +224,7 @@ cudaError_t isomc_launch_tile_emit(const Geo &g, const TileGeo &tg, const TileBu
     }
     EmitArgsDev A;
     A.pV = B.pV; A.pT = B.pT; A.pE = B.pE; A.pTp = B.pTp; A.pA = B.pA;
-    A.ent = B.ent; A.tbuf = B.tbuf;
+    A.ent = B.ent; A.tq = B.tq; A.tbuf = B.tbuf;
     A.vofs_ptr = vofs;
     A.layerTot = B.layerTot;
     A.ctr = B.ctr;

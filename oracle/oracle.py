@@ -36,7 +36,7 @@ def lib():
     global _LIB
     if _LIB is None:
         so = _HERE / "libmc_oracle.so"
-        if not so.exists() or so.stat().st_mtime < (_HERE / "mc_oracle.c").stat().st_mtime:
+        if not so.exists() or so.stat().st_mtime < max((_HERE / n).stat().st_mtime for n in ("mc_oracle.c", "synth_field.c", "Makefile")):
             build()
         _LIB = C.CDLL(str(so))
         _LIB.oracle_extract_sdf.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(_Mesh)]
@@ -52,6 +52,7 @@ def lib():
         _LIB.oracle_extract_sdf_directed.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
         _LIB.oracle_point_cloud_sdf.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
         _LIB.oracle_point_cloud_grid.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
+        _LIB.oracle_synth_field.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
     return _LIB
 
 
@@ -187,3 +188,16 @@ def tables():
     if rc:
         raise RuntimeError("oracle_tables rc=%d" % rc)
     return tri, em, co, ed
+
+
+FIELD_FBM, FIELD_GYROID, FIELD_SPHERE_UNION = 1, 2, 3
+
+
+def synth_field(kind, size, seed, z_first=0, n_layers=None):
+    """host-generated benchmark field, shape (n_layers, size, size); see oracle/synth_field.c"""
+    n_layers = size + 1 - z_first if n_layers is None else n_layers
+    out = np.empty((n_layers, size, size), np.float32)
+    rc = lib().oracle_synth_field(kind, size, seed, z_first, n_layers, out.ctypes.data)
+    if rc:
+        raise ValueError("oracle_synth_field failed (%d)" % rc)
+    return out

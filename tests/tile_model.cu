@@ -183,12 +183,13 @@ int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const Src &sr
     std::vector<uint32_t> pV(np + 4, 0xDEADBEEFu), pT(np + 4, 0xDEADBEEFu), pE(np + 4, 0xDEADBEEFu), pTp(np + 4, 0xDEADBEEFu);
     std::vector<uint16_t> pA(np + 4, 0xDEADu);
     std::vector<uint2> ent((size_t)cap_eb * ENT_BLOCK);
-    std::vector<float> tbuf((size_t)cap_tb * ENT_BLOCK);
+    std::vector<float> tbuf((size_t)cap_tb * ENT_BLOCK), tq((size_t)cap_eb * ENT_BLOCK * 3);
     memset(ent.data(), 0xEE, ent.size() * sizeof(uint2));
+    memset(tq.data(), 0xEE, tq.size() * sizeof(float));
     memset(tbuf.data(), 0xEE, tbuf.size() * sizeof(float));
     uint32_t ctr[2] = {0, 0};
     std::vector<unsigned long long> layerTot((size_t)g.ncl * 3 + 4, 0ull);
-    TileBufs B{pV.data(), pT.data(), pE.data(), pTp.data(), pA.data(), ent.data(), tbuf.data(), ctr, cap_eb, cap_tb, layerTot.data()};
+    TileBufs B{pV.data(), pT.data(), pE.data(), pTp.data(), pA.data(), ent.data(), tq.data(), tbuf.data(), ctr, cap_eb, cap_tb, layerTot.data()};
 
     /* work items (chunk-major, then column), dealt to n_ctas emulated CTAs at random; CTAs run in shuffled order */
     uint64_t st = seed * 0x9E3779B97F4A7C15ull + 1;
@@ -254,7 +255,7 @@ int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const Src &sr
 
     EmitParams P;
     P.pV = pV.data(); P.pT = pT.data(); P.pE = pE.data(); P.pTp = pTp.data(); P.pA = pA.data();
-    P.ent = ent.data(); P.tbuf = tbuf.data();
+    P.ent = ent.data(); P.tq = tq.data(); P.tbuf = tbuf.data();
     P.vofs = vofs; P.ghostV = (uint32_t)gV; P.ghostT = (uint32_t)gT; P.first_own_layer = g.ghost;
     P.cap_v = cap_v; P.cap_t = cap_t; P.xyz = xyz; P.idx = idx;
     {
