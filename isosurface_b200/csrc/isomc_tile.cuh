@@ -375,9 +375,13 @@ ISOMC_HD void tile_count_item(const Cta &c, const Geo &g, const TileGeo &tg, con
                         if (!zlow && y != 0 && (x0 + tx) != 0) { /* creates its crossed e5 (y), e6 (x), e10 (z): all end at corner 6 */
                             const int cx = 0, cy = NC > 2 ? 1 : 0, cz = NC > 2 ? 2 : 0;
                             float *tq = B.tq + 3 * (uint64_t)(epos + j); /* beside the entry: pass 2 fetches both without decoding either */
-                            if (em >> 5 & 1u) tq[0] = crossing_t(S.slot[st][cy][r][tx + 1], S.slot[st][cy][r + 1][tx + 1]);
-                            if (em >> 6 & 1u) tq[1] = crossing_t(S.slot[st][cx][r + 1][tx + 1], S.slot[st][cx][r + 1][tx]);
-                            if (em >> 10 & 1u) tq[2] = crossing_t(S.slot[sb][cz][r + 1][tx + 1], S.slot[st][cz][r + 1][tx + 1]);
+                            /* all three computed straight-line (an uncrossed edge just gives a value nobody stores) */
+                            const float t5 = crossing_t(S.slot[st][cy][r][tx + 1], S.slot[st][cy][r + 1][tx + 1]);
+                            const float t6 = crossing_t(S.slot[st][cx][r + 1][tx + 1], S.slot[st][cx][r + 1][tx]);
+                            const float t10 = crossing_t(S.slot[sb][cz][r + 1][tx + 1], S.slot[st][cz][r + 1][tx + 1]);
+                            if (em >> 5 & 1u) tq[0] = t5;
+                            if (em >> 6 & 1u) tq[1] = t6;
+                            if (em >> 10 & 1u) tq[2] = t10;
                         } else { /* on a low face: also the edges lying in it */
                             const uint32_t owned = em & tabg->ownmask[cell_flags(g, x0 + tx, y, lz)];
                             float *tp = B.tbuf + tpos + vrel;
@@ -433,6 +437,7 @@ struct alignas(16) EmitSmem {
     uint16_t emask[256];
     uint8_t rank3[256];
     uint32_t etab[2][12];        /* [cell-layer parity][edge]: plane row at ty = 0 | dx << 8 | dy << 9 | (row * PL_PITCH + dx) << 12 */
+    uint2 eofs[2][16];           /* the same as byte offsets: x into flatB (row at ty = 0), y into plane (cell (0, 0)) */
 };
 
 /* plane location of edge e of the cell (tx, ty) on a cell layer of parity par: row index at ty = 0, dx, dy, flat offset */
@@ -601,15 +606,15 @@ ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, Emit
                 f.x0 = hd_mul((float)x, g.inv); f.x1 = hd_mul((float)(x + 1), g.inv);
                 f.y0 = hd_mul((float)y, g.inv); f.y1 = hd_mul((float)(y + 1), g.inv);
                 f.z0 = fz0; f.z1 = fz1;
-                if (fl == 0 && own) { /* a cell off the low faces creates its crossed e5, e6, e10 */
+                if (fl == 0) { /* a cell off the low faces creates its crossed e5, e6, e10 (a halo cell: those that lie in the tile) */
                     const uint32_t r3 = S.rank3[ci];
                     const uint32_t l5 = S.etab[par][5] >> 12, l6 = S.etab[par][6] >> 12, l10 = S.etab[par][10] >> 12;
-                    if (em >> 5 & 1u) {
+                    if ((em >> 5 & 1u) && ty >= 0) {
                         const uint32_t rank = r3 & 3u;
                         S.plane[(int32_t)l5 + cell] = (int16_t)(rel0 + (int32_t)rank);
                         if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), 0x75u, f, F.t5);  /* corners 5 -> 6 */
                     }
-                    if (em >> 6 & 1u) {
+                    if ((em >> 6 & 1u) && tx >= 0) {
                         const uint32_t rank = r3 >> 2 & 3u;
                         S.plane[(int32_t)l6 + cell] = (int16_t)(rel0 + (int32_t)rank);
                         if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), 0x67u, f, F.t6);  /* corners 6 -> 7 */
@@ -619,7 +624,7 @@ ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, Emit
                         S.plane[(int32_t)l10 + cell] = (int16_t)(rel0 + (int32_t)rank);
                         if (put && vslot0 + rank < P.cap_v) tile_vertex_store(P.xyz + 3 * (vslot0 + rank), 0x73u, f, F.t10); /* corners 2 -> 6 */
                     }
-                } else { /* on a low face of the lattice, or a halo cell: the general tables, range-checked */
+                } else { /* on a low face of the lattice: the general tables, range-checked for halo cells */
                     const uint32_t owned = em & (uint32_t)tabg->ownmask[fl];
                     const float *tp = P.tbuf + I.Tp[k] + vrel;
                     for (uint32_t m = owned; m; m &= m - 1) {
@@ -640,12 +645,13 @@ ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, Emit
                 if (tslot >= P.cap_t) nt = 0;
                 else if (tslot + nt > P.cap_t) nt = (uint32_t)(P.cap_t - tslot);
                 uint32_t *o = P.idx + 3 * tslot;
-                const uint32_t *et = S.etab[par];
+                const uint2 *eo = S.eofs[par];
+                const char *fb = reinterpret_cast<const char *>(S.flatB) + 4 * ty, *pl = reinterpret_cast<const char *>(S.plane) + 2 * cell;
                 for (uint32_t t = 0; t < nt; ++t, tri >>= 12, o += 3) {
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
-                        const uint32_t loc = et[(uint32_t)(tri >> (4 * q)) & 15u];
-                        o[q] = S.flatB[(loc & 255u) + (uint32_t)ty] + (uint32_t)(int32_t)S.plane[(int32_t)(loc >> 12) + cell];
+                        const uint2 ofs = eo[(uint32_t)(tri >> (4 * q)) & 15u];
+                        o[q] = *reinterpret_cast<const uint32_t *>(fb + ofs.x) + (uint32_t)(int32_t)*reinterpret_cast<const int16_t *>(pl + ofs.y);
                     }
                 }
             }

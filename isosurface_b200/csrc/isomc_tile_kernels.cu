@@ -129,7 +129,11 @@ __global__ void __launch_bounds__(TILE_NT, 4) k_tile_emit(Geo g, TileGeo tg, Emi
         S.emask[i] = tabg->emask[i];
         S.rank3[i] = tabg->rank3[i];
     }
-    if (threadIdx.x < 24) S.etab[threadIdx.x / 12][threadIdx.x % 12] = tabg->eloc[threadIdx.x / 12][threadIdx.x % 12];
+    if (threadIdx.x < 24) {
+        const uint32_t loc = tabg->eloc[threadIdx.x / 12][threadIdx.x % 12];
+        S.etab[threadIdx.x / 12][threadIdx.x % 12] = loc;
+        S.eofs[threadIdx.x / 12][threadIdx.x % 12] = make_uint2((loc & 255u) * 4u, (loc >> 12) * 2u);
+    }
     EmitParams P;
     P.pV = A.pV; P.pT = A.pT; P.pE = A.pE; P.pTp = A.pTp; P.pA = A.pA;
     P.ent = A.ent; P.tq = A.tq; P.tbuf = A.tbuf;

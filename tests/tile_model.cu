@@ -265,7 +265,10 @@ int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const Src &sr
         memcpy(S->emask, mt.emask, sizeof S->emask);
         memcpy(S->rank3, mt.rank3, sizeof S->rank3);
         for (uint32_t par = 0; par < 2; ++par)
-            for (uint32_t e = 0; e < 12; ++e) S->etab[par][e] = tile_edge_loc(par, e);
+            for (uint32_t e = 0; e < 12; ++e) {
+                S->etab[par][e] = tile_edge_loc(par, e);
+                S->eofs[par][e] = make_uint2((S->etab[par][e] & 255u) * 4u, (S->etab[par][e] >> 12) * 2u);
+            }
         const uint32_t nch2 = (g.ncl + EMIT_ZC - 1) / EMIT_ZC, nit2 = nch2 * tg.ncols;
         std::vector<std::vector<uint32_t>> share2(n_ctas);
         for (uint32_t it = 0; it < nit2; ++it) share2[rnd(n_ctas)].push_back(it);
