@@ -40,6 +40,8 @@ constexpr uint32_t TILE_PITCH = TILE_X + 4;  /* staged floats per sample row (16
 constexpr uint32_t TILE_NW = TILE_X / 32 + 2;/* sign words per staged sample row (TILE_X/32 + 1 used) */
 constexpr uint32_t ENT_BLOCK = 256;          /* entries (and t values) per allocation block */
 constexpr uint32_t EMIT_ZC = 16;             /* cell layers per work item of pass 2 */
+constexpr uint32_t EMIT_Y = 4;               /* cell rows per tile of pass 2 (its tiles are its own: row pieces are what the passes share) */
+constexpr uint32_t EMIT_NT = 160;            /* threads per CTA of pass 2: ~26 entries per row of a dense field + the halo row */
 
 /* entry of an active cell: x = vrel (13) | tpre (12) << 13 ; y = x in tile (9) | cube index (8) << 9 */
 ISOMC_HD uint2 tile_entry_pack(uint32_t vrel, uint32_t tpre, uint32_t tx, uint32_t ci) {
@@ -50,6 +52,7 @@ struct TileGeo {
     uint32_t nxt, nyt;   /* tiles per row / per column of rows */
     uint32_t ncols;      /* nxt * nyt */
     uint32_t ppl;        /* row pieces per cell layer = ncx * nxt */
+    uint32_t ncols_emit; /* tile columns of pass 2: nxt * ceil(ncx / EMIT_Y) */
 };
 
 static inline TileGeo tile_geo(const Geo &g) {
@@ -58,6 +61,7 @@ static inline TileGeo tile_geo(const Geo &g) {
     t.nyt = g.ncx ? (g.ncx + TILE_Y - 1) / TILE_Y : 0;
     t.ncols = t.nxt * t.nyt;
     t.ppl = g.ncx * t.nxt;
+    t.ncols_emit = t.nxt * (g.ncx ? (g.ncx + EMIT_Y - 1) / EMIT_Y : 0);
     return t;
 }
 
@@ -417,13 +421,13 @@ ISOMC_HD void tile_count_item(const Cta &c, const Geo &g, const TileGeo &tg, con
 /* ---- pass 2 ------------------------------------------------------------------------------------------------ */
 
 constexpr uint32_t PL_PITCH = TILE_X + 1;
-constexpr uint32_t PL_XROW = 0;                          /* X-edge planes: [parity][py 0..TILE_Y] */
-constexpr uint32_t PL_YROW = 2 * (TILE_Y + 1);           /* Y-edge planes: [parity][cy 0..TILE_Y-1] */
-constexpr uint32_t PL_ZROW = PL_YROW + 2 * TILE_Y;       /* Z-edge plane:  [py 0..TILE_Y] */
-constexpr uint32_t PL_ROWS = PL_ZROW + TILE_Y + 1;       /* 43 */
-constexpr uint32_t INFO_K = 2 * (TILE_Y + 1);            /* 18 row pieces a tile layer looks at */
+constexpr uint32_t PL_XROW = 0;                          /* X-edge planes: [parity][py 0..EMIT_Y] */
+constexpr uint32_t PL_YROW = 2 * (EMIT_Y + 1);           /* Y-edge planes: [parity][cy 0..EMIT_Y-1] */
+constexpr uint32_t PL_ZROW = PL_YROW + 2 * EMIT_Y;       /* Z-edge plane:  [py 0..EMIT_Y] */
+constexpr uint32_t PL_ROWS = PL_ZROW + EMIT_Y + 1;       
+constexpr uint32_t INFO_K = 2 * (EMIT_Y + 1);            /* row pieces a tile layer looks at */
 
-struct LayerInfo {          /* k = 0..8: halo column (x tile - 1), rows -1..7;  k = 9: halo row;  k = 10..17: own rows */
+struct LayerInfo {          /* k = 0..EMIT_Y: halo column (x tile - 1), rows -1..EMIT_Y-1;  k = EMIT_Y+1: halo row;  then the own rows */
     uint32_t V[INFO_K], T[INFO_K], E[INFO_K], Tp[INFO_K];
     uint16_t A[INFO_K];
     uint16_t cum[32];       /* phase-A sequence: prefix of the lengths (halo column cells: 0/1 each), padded with the total */
@@ -447,7 +451,7 @@ static inline uint32_t tile_edge_loc(uint32_t par, uint32_t e) {
     static const uint8_t dx[12] = {0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 0};
     static const uint8_t dy[12] = {0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 1};
     const uint32_t p = par ^ top[e];
-    uint32_t row = kind[e] == 0 ? PL_XROW + p * (TILE_Y + 1) : kind[e] == 1 ? PL_YROW + p * TILE_Y : PL_ZROW;
+    uint32_t row = kind[e] == 0 ? PL_XROW + p * (EMIT_Y + 1) : kind[e] == 1 ? PL_YROW + p * EMIT_Y : PL_ZROW;
     row += dy[e];
     return row | (uint32_t)dx[e] << 8 | (uint32_t)dy[e] << 9 | (row * PL_PITCH + dx[e]) << 12;
 }
@@ -490,11 +494,11 @@ ISOMC_HD void emit_fetch(const LayerInfo &I, const EmitParams &P, uint32_t j, Em
 #pragma unroll
         for (uint32_t step = 16; step; step >>= 1)
             if (I.cum[k + step] <= j) k += step;
-        const bool xh = k < TILE_Y + 1;
+        const bool xh = k < EMIT_Y + 1;
         const uint32_t pos = xh ? I.E[k] + I.A[k] - 1u : I.E[k] + (j - I.cum[k]);
         F.k = k;
         F.ea = P.ent[pos];
-        if (k > TILE_Y + 1) {
+        if (k > EMIT_Y + 1) {
             const float *q = P.tq + 3 * (uint64_t)pos;
             F.t5 = q[0]; F.t6 = q[1]; F.t10 = q[2];
         }
@@ -509,15 +513,15 @@ ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, Emit
     const Warp &w = c.w;
     const uint32_t warp = c.tid >> 5;
     const uint32_t xt = col % tg.nxt, yt = col / tg.nxt;
-    const uint32_t x0 = xt * TILE_X, y0 = yt * TILE_Y;
+    const uint32_t x0 = xt * TILE_X, y0 = yt * EMIT_Y;
     const uint32_t la = l0 > 0 ? l0 - 1 : 0, nl = l1 - la;
 
     cta_sync(c); /* the previous item is done with the shared state */
     /* what the 18 row pieces of every layer hold (an empty piece still has its id base) */
-    for (uint32_t i = c.tid; i < nl * INFO_K; i += TILE_NT) {
+    for (uint32_t i = c.tid; i < nl * INFO_K; i += EMIT_NT) {
         const uint32_t l = i / INFO_K, k = i - l * INFO_K;
-        const bool xh = k < TILE_Y + 1;
-        const int32_t row = xh ? (int32_t)k - 1 : (int32_t)k - (int32_t)(TILE_Y + 2);
+        const bool xh = k < EMIT_Y + 1;
+        const int32_t row = xh ? (int32_t)k - 1 : (int32_t)k - (int32_t)(EMIT_Y + 2);
         const int64_t y = (int64_t)y0 + row;
         uint32_t v = 0, t = 0, e = 0, tp = 0, a = 0;
         if (y >= 0 && y < (int64_t)g.ncx && (!xh || xt > 0)) {
@@ -530,11 +534,11 @@ ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, Emit
         I.V[k] = v; I.T[k] = t; I.E[k] = e; I.Tp[k] = tp; I.A[k] = (uint16_t)a;
     }
     cta_sync(c);
-    for (uint32_t l = warp; l < nl; l += TILE_Y) { /* the phase-A sequence of every layer */
+    for (uint32_t l = warp; l < nl; l += EMIT_NT / 32) { /* the phase-A sequence of every layer */
         LayerInfo &I = S.li[l];
         const uint32_t k = w.lane;
         uint32_t len = 0;
-        if (k < INFO_K) len = k < TILE_Y + 1 ? (I.A[k] ? 1u : 0u) : I.A[k];
+        if (k < INFO_K) len = k < EMIT_Y + 1 ? (I.A[k] ? 1u : 0u) : I.A[k];
         uint32_t tot;
         const uint32_t ex = w_excl_scan(w, len, tot);
         I.cum[k] = (uint16_t)(k < INFO_K ? ex : tot);
@@ -564,32 +568,32 @@ ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, Emit
             uint32_t k;       /* info slot of the creating piece */
             bool bottom;      /* plane of the cell layer's lower sample layer */
             if (i < PL_YROW) {
-                const uint32_t p = i / (TILE_Y + 1), py = i - p * (TILE_Y + 1);
+                const uint32_t p = i / (EMIT_Y + 1), py = i - p * (EMIT_Y + 1);
                 bottom = p == par;
-                k = (y0 + py == 0) ? TILE_Y + 2 : TILE_Y + 1 + py;
+                k = (y0 + py == 0) ? EMIT_Y + 2 : EMIT_Y + 1 + py;
             } else if (i < PL_ZROW) {
-                const uint32_t p = (i - PL_YROW) / TILE_Y, cy = (i - PL_YROW) - p * TILE_Y;
+                const uint32_t p = (i - PL_YROW) / EMIT_Y, cy = (i - PL_YROW) - p * EMIT_Y;
                 bottom = p == par;
-                k = TILE_Y + 2 + cy;
+                k = EMIT_Y + 2 + cy;
             } else {
                 const uint32_t py = i - PL_ZROW;
                 bottom = false;
-                k = (y0 + py == 0) ? TILE_Y + 2 : TILE_Y + 1 + py;
+                k = (y0 + py == 0) ? EMIT_Y + 2 : EMIT_Y + 1 + py;
             }
             /* edges in the lower sample layer were created one cell layer down -- except on the lattice's z = 0 face */
             const LayerInfo &J = (bottom && gz != 0 && lz > la) ? S.li[lz - la - 1] : I;
             S.flatB[i] = J.V[k] + P.vofs;
         }
         const float fz0 = hd_mul((float)gz, g.inv), fz1 = hd_mul((float)(gz + 1), g.inv);
-        for (uint32_t j0 = 0; j0 < nA; j0 += TILE_NT) {
-            if (j0) emit_fetch(I, P, j0 + c.tid, F); /* (rounds beyond the first: more than TILE_NT entries in a tile layer) */
+        for (uint32_t j0 = 0; j0 < nA; j0 += EMIT_NT) {
+            if (j0) emit_fetch(I, P, j0 + c.tid, F); /* (rounds beyond the first: more than EMIT_NT entries in a tile layer) */
             bool have = F.k < INFO_K;
             const uint32_t k = have ? F.k : 0u;
-            const bool xh = k < TILE_Y + 1;
+            const bool xh = k < EMIT_Y + 1;
             const uint2 ea = F.ea;
             if (xh && (ea.y & 511u) != TILE_X - 1) have = false; /* the piece's last cell is not the tile's neighbour */
             const int32_t tx = xh ? -1 : (int32_t)(ea.y & 511u);
-            const int32_t ty = xh ? (int32_t)k - 1 : (int32_t)k - (int32_t)(TILE_Y + 2);
+            const int32_t ty = xh ? (int32_t)k - 1 : (int32_t)k - (int32_t)(EMIT_Y + 2);
             const uint32_t ci = ea.y >> 9 & 255u, vrel = ea.x & 8191u, tpre = ea.x >> 13 & 4095u;
             const uint32_t x = x0 + (uint32_t)tx, y = y0 + (uint32_t)ty;
             const bool own = have && !xh && ty >= 0;
@@ -598,7 +602,7 @@ ISOMC_HD void tile_emit_item(const Cta &c, const Geo &g, const TileGeo &tg, Emit
                 const uint32_t em = S.emask[ci];
                 const uint32_t fl = (x == 0 ? 1u : 0u) | (y == 0 ? 2u : 0u) | (gz == 0 ? 4u : 0u);
                 /* ids are stored relative to the base of the plane row = the own-tile piece of the creating row */
-                const uint32_t ko = (uint32_t)(ty + (int32_t)(TILE_Y + 2));
+                const uint32_t ko = (uint32_t)(ty + (int32_t)(EMIT_Y + 2));
                 const int32_t rel0 = (int32_t)(I.V[k] - I.V[ko]) + (int32_t)vrel;
                 const uint64_t vslot0 = (uint64_t)I.V[k] + vrel - P.ghostV;
                 const bool put = own && emit;

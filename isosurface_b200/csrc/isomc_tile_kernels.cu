@@ -31,6 +31,15 @@ struct GridBulkSrc { /* TMA-staged device lattice: N % 4 == 0, 16-byte aligned b
         out[0] = __ldg(p + ((uint64_t)lz * g.N + y) * g.N + x);
     }
 };
+struct GridBulk2Src { /* the same with a two-layer ring: the copy of a layer is not overlapped within the CTA, but more CTAs fit an SM */
+    static constexpr int NS = 2, NC = 1;
+    static constexpr bool ASYNC = true;
+    const float *p;
+    __device__ __forceinline__ const float *base() const { return p; }
+    __device__ __forceinline__ void sample(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, float *out) const {
+        out[0] = __ldg(p + ((uint64_t)lz * g.N + y) * g.N + x);
+    }
+};
 struct GridPlainSrc { /* any size / alignment: loaded by all threads */
     static constexpr int NS = 2, NC = 1;
     static constexpr bool ASYNC = false;
@@ -118,13 +127,13 @@ struct EmitArgsDev {
     uint32_t *idx;
 };
 
-__global__ void __launch_bounds__(TILE_NT, 4) k_tile_emit(Geo g, TileGeo tg, EmitArgsDev A, const EmitTab *__restrict__ tabg, uint32_t lz0,
+__global__ void __launch_bounds__(EMIT_NT, 7) k_tile_emit(Geo g, TileGeo tg, EmitArgsDev A, const EmitTab *__restrict__ tabg, uint32_t lz0,
                                                      uint32_t lz1, uint32_t *ticket) {
     EmitSmem &S = *reinterpret_cast<EmitSmem *>(tile_smem_raw);
     __shared__ uint32_t s_item;
     /* entry list / t buffer overflow: what was counted is incomplete; the host grows the buffers and re-runs */
     if (A.ctr[0] > A.cap_eb || A.ctr[1] > A.cap_tb) return;
-    for (uint32_t i = threadIdx.x; i < 256; i += TILE_NT) {
+    for (uint32_t i = threadIdx.x; i < 256; i += EMIT_NT) {
         S.tri[i] = (tabg->tri[i] & 0x0FFFFFFFFFFFFFFFull) | (unsigned long long)tabg->ntri[i] << 60;
         S.emask[i] = tabg->emask[i];
         S.rank3[i] = tabg->rank3[i];
@@ -148,14 +157,14 @@ __global__ void __launch_bounds__(TILE_NT, 4) k_tile_emit(Geo g, TileGeo tg, Emi
     c.w.lane = threadIdx.x & 31u;
     c.w.emu = nullptr;
     c.bemu = nullptr;
-    const uint32_t nchunks = (lz1 - lz0 + EMIT_ZC - 1) / EMIT_ZC, nitems = nchunks * tg.ncols;
+    const uint32_t nchunks = (lz1 - lz0 + EMIT_ZC - 1) / EMIT_ZC, nitems = nchunks * tg.ncols_emit;
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(ticket, 1u);
         __syncthreads();
         const uint32_t item = s_item;
         __syncthreads();
         if (item >= nitems) break;
-        const uint32_t chunk = item / tg.ncols, col = item - chunk * tg.ncols;
+        const uint32_t chunk = item / tg.ncols_emit, col = item - chunk * tg.ncols_emit;
         const uint32_t l0 = lz0 + chunk * EMIT_ZC, l1 = min(lz1, l0 + EMIT_ZC);
         tile_emit_item(c, g, tg, S, P, tabg, col, l0, l1);
     }
@@ -204,7 +213,13 @@ cudaError_t isomc_launch_tile_count_grid(const Geo &g, const TileGeo &tg, const 
         const char *p = getenv("ISOMC_FILL");
         plain = (p && strcmp(p, "plain") == 0) ? 1 : 0;
     }
+    static int ring = -1;
+    if (ring < 0) {
+        const char *p = getenv("ISOMC_RING");
+        ring = p ? atoi(p) : 3;
+    }
     const bool aligned = (g.N % 4u) == 0 && (reinterpret_cast<uintptr_t>(d_grid) & 15u) == 0;
+    if (aligned && !plain && ring == 2) return launch_count<GridBulk2Src, 5>(GridBulk2Src{d_grid}, g, tg, B, tab, lz0, lz1, ticket, sms, st);
     if (aligned && !plain) return launch_count<GridBulkSrc, 4>(GridBulkSrc{d_grid}, g, tg, B, tab, lz0, lz1, ticket, sms, st);
     return launch_count<GridPlainSrc, 4>(GridPlainSrc{d_grid}, g, tg, B, tab, lz0, lz1, ticket, sms, st);
 }
@@ -235,9 +250,9 @@ cudaError_t isomc_launch_tile_emit(const Geo &g, const TileGeo &tg, const TileBu
     A.cap_eb = B.cap_eb; A.cap_tb = B.cap_tb;
     A.cap_v = cap_v; A.cap_t = cap_t;
     A.xyz = xyz; A.idx = idx;
-    const uint64_t nitems = (uint64_t)((lz1 - lz0 + EMIT_ZC - 1) / EMIT_ZC) * tg.ncols;
-    const uint32_t slots = (uint32_t)sms * 4u;
+    const uint64_t nitems = (uint64_t)((lz1 - lz0 + EMIT_ZC - 1) / EMIT_ZC) * tg.ncols_emit;
+    const uint32_t slots = (uint32_t)sms * 7u;
     const uint32_t grid = (uint32_t)(nitems < slots ? nitems : slots);
-    k_tile_emit<<<grid, TILE_NT, sizeof(EmitSmem), st>>>(g, tg, A, tab, lz0, lz1, ticket);
+    k_tile_emit<<<grid, EMIT_NT, sizeof(EmitSmem), st>>>(g, tg, A, tab, lz0, lz1, ticket);
     return cudaGetLastError();
 }

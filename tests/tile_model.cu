@@ -36,6 +36,7 @@ struct WarpEmu {
 };
 struct BlockEmu {
     ucontext_t main_ctx, ctx[TILE_NT];
+    uint32_t nthreads = TILE_NT;
     std::vector<char> stacks;
     WarpEmu warp[TILE_Y];
     uint32_t arrived = 0, gen = 0;
@@ -52,11 +53,13 @@ void thread_main(int tid) {
 }
 
 /* runs body(tid) for all threads of one emulated CTA; threads are resumed in an order shuffled with `seed` */
-void run_cta(BlockEmu &E, uint64_t seed, std::function<void(uint32_t)> body) {
+void run_cta(BlockEmu &E, uint64_t seed, uint32_t nthreads, std::function<void(uint32_t)> body) {
     g_blk = &E;
+    E.nthreads = nthreads;
+    const uint32_t NT = nthreads;
     E.body = std::move(body);
     const size_t STK = 192 * 1024;
-    E.stacks.resize((size_t)TILE_NT * STK);
+    E.stacks.resize((size_t)NT * STK);
     E.arrived = 0;
     for (uint32_t wi = 0; wi < TILE_Y; ++wi) {
         E.warp[wi].arrived = 0;
@@ -64,8 +67,8 @@ void run_cta(BlockEmu &E, uint64_t seed, std::function<void(uint32_t)> body) {
         E.warp[wi].index = wi;
         memset(E.warp[wi].parity, 0, sizeof E.warp[wi].parity);
     }
-    std::vector<uint32_t> order(TILE_NT);
-    for (uint32_t t = 0; t < TILE_NT; ++t) {
+    std::vector<uint32_t> order(NT);
+    for (uint32_t t = 0; t < NT; ++t) {
         order[t] = t;
         E.done[t] = false;
         getcontext(&E.ctx[t]);
@@ -76,12 +79,12 @@ void run_cta(BlockEmu &E, uint64_t seed, std::function<void(uint32_t)> body) {
     }
     uint64_t st = seed * 0x9E3779B97F4A7C15ull + 12345;
     for (;;) {
-        for (uint32_t i = TILE_NT; i > 1; --i) {
+        for (uint32_t i = NT; i > 1; --i) {
             st = st * 6364136223846793005ull + 1442695040888963407ull;
             std::swap(order[i - 1], order[(st >> 33) % i]);
         }
         bool any = false;
-        for (uint32_t i = 0; i < TILE_NT; ++i) {
+        for (uint32_t i = 0; i < NT; ++i) {
             const uint32_t t = order[i];
             if (!E.done[t]) {
                 any = true;
@@ -149,7 +152,7 @@ void isomc_emu_sync(void *emu, uint32_t lane) {
 void isomc_emu_block_sync(void *bemu, uint32_t tid) {
     BlockEmu *b = (BlockEmu *)bemu;
     const uint32_t my = b->gen;
-    if (++b->arrived == TILE_NT) { b->arrived = 0; b->gen++; return; }
+    if (++b->arrived == b->nthreads) { b->arrived = 0; b->gen++; return; }
     while (b->gen == my) yield_thread(b, tid);
 }
 uint32_t isomc_emu_atomic_add_u32(uint32_t *p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
@@ -208,7 +211,7 @@ int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const Src &sr
         for (uint32_t ci = 0; ci < n_ctas; ++ci) {
             const std::vector<uint32_t> &items = share[order[ci]];
             if (items.empty()) continue;
-            run_cta(E, seed + ci, [&](uint32_t tid) {
+            run_cta(E, seed + ci, TILE_NT, [&](uint32_t tid) {
                 const Cta c = make_cta(E, tid);
                 CountCtx X;
                 memset(&X, 0, sizeof X);
@@ -269,16 +272,16 @@ int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const Src &sr
                 S->etab[par][e] = tile_edge_loc(par, e);
                 S->eofs[par][e] = make_uint2((S->etab[par][e] & 255u) * 4u, (S->etab[par][e] >> 12) * 2u);
             }
-        const uint32_t nch2 = (g.ncl + EMIT_ZC - 1) / EMIT_ZC, nit2 = nch2 * tg.ncols;
+        const uint32_t nch2 = (g.ncl + EMIT_ZC - 1) / EMIT_ZC, nit2 = nch2 * tg.ncols_emit;
         std::vector<std::vector<uint32_t>> share2(n_ctas);
         for (uint32_t it = 0; it < nit2; ++it) share2[rnd(n_ctas)].push_back(it);
         for (uint32_t ci = 0; ci < n_ctas; ++ci) {
             const std::vector<uint32_t> &items = share2[order[ci]];
             if (items.empty()) continue;
-            run_cta(E, seed + 77 + ci, [&](uint32_t tid) {
+            run_cta(E, seed + 77 + ci, EMIT_NT, [&](uint32_t tid) {
                 const Cta c = make_cta(E, tid);
                 for (uint32_t it : items) {
-                    const uint32_t chunk = it / tg.ncols, col = it % tg.ncols;
+                    const uint32_t chunk = it / tg.ncols_emit, col = it % tg.ncols_emit;
                     const uint32_t l0 = chunk * EMIT_ZC, l1 = std::min(g.ncl, l0 + EMIT_ZC);
                     tile_emit_item(c, g, tg, *S, P, &et, col, l0, l1);
                 }
