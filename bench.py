@@ -453,7 +453,7 @@ def run_ours(args):
     }
     # roofline of the dominant kernel and of the whole extract
     # kernel names of the path in use: the tile path (default) or the older active-cell-list kernels (ISOMC_PATH=list)
-    tile = os.environ.get("ISOMC_PATH", "tile") != "list"
+    tile = os.environ.get("ISOMC_PATH", "list") == "tile"
     k_first, k_count, k_emit = ("k_tile_count", None, "k_tile_emit") if tile else ("k_sign", "k_count_list", "k_emit_list")
     # k_tile_count / k_sign read every sample once; the emit kernels write vertices and triangles
     kern = {k_first: (prof[0], 4 * S / world), "k_scan_rows": (prof[2], 0), k_emit: (prof[3], (12 * V + 12 * T) / world)}
@@ -481,7 +481,7 @@ def run_ours(args):
                             "ops_per_sample": ops}
     line["kernels_ms"] = {k: v[0] for k, v in kern.items()}
     line["kernels_ms"]["sum"] = prof[4]
-    line["config"]["path"] = "tile path (TMA-staged count, plane emission)" if tile else "active-cell list"
+    line["config"]["path"] = "tile path (TMA-staged count, plane emission; ISOMC_PATH=tile)" if tile else "active-cell list"
     line["config"]["kernel_src_sha"] = kernel_source_sha()
     line["clocks"] = clk.summary()
 

@@ -48,8 +48,9 @@ struct isomc {
     uint32_t *signs = nullptr, *rowV = nullptr, *rowT = nullptr, *rowA = nullptr;
     unsigned long long *layerTot = nullptr, *totals = nullptr; /* totals: 12 u64 */
     uint32_t *vofs = nullptr, *ticket = nullptr;
-    /* tile path (default): isomc_tile.cuh.  ISOMC_PATH=list selects the older active-cell-list kernels (isomc_cell.cuh) */
-    bool tile_mode = true;
+    /* active-cell-list kernels (isomc_cell.cuh) by default; ISOMC_PATH=tile selects the TMA-staged tile path (isomc_tile.cuh):
+     * parity-green and profiled, but measured slower on every workload (profiles/r02_tile_path.md) */
+    bool tile_mode = false;
     TileGeo tg{};
     TileBufs TB{};
     uint32_t *tile_tickets = nullptr; /* [MAX_CHUNKS] pass 1, [MAX_CHUNKS] pass 2 */
@@ -428,7 +429,7 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
         CU(h, cudaMalloc(&h->tabs, sizeof(McTables)));
         CU(h, cudaMemcpy(h->tabs, &host_tabs, sizeof(McTables), cudaMemcpyHostToDevice));
         const uint64_t nrows_s = (uint64_t)g.nsl * g.N, nrows_c = (uint64_t)g.ncl * g.ncx;
-        if (const char *p = getenv("ISOMC_PATH")) h->tile_mode = strcmp(p, "list") != 0;
+        if (const char *p = getenv("ISOMC_PATH")) h->tile_mode = strcmp(p, "tile") == 0;
         h->tg = tile_geo(g);
         EmitTab host_etab;
         isomc_build_emit_tab(host_tabs, &host_etab);

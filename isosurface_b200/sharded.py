@@ -108,3 +108,68 @@ class SlabMarchingCubes:
         idx = np.empty(t.value * 3, np.uint32)
         _lib.check(self._lib.isomc_copy_out(self._h, xyz.ctypes.data, idx.ctypes.data), self._h)
         return xyz, idx
+
+
+class ShardedMarchingCubes:
+    """`MarchingCubes(size)` over several GPUs of one box, driven from THIS process through the in-library
+    `isomc_sharded_*` entry points (include/isomc.h): one slab handle per device, one NCCL all-gather of 3 x u64 per
+    rank per extract.  `devices` may list one device several times (a single-GPU box exercising the sharded path)."""
+
+    def __init__(self, size, devices):
+        lib = _lib.load()
+        self.size, self.devices = int(size), [int(d) for d in devices]
+        self._h = C.c_void_p()
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        rc = lib.isomc_sharded_create(self.size, len(self.devices), arr, C.byref(self._h))
+        if rc:
+            raise _lib.IsomcError(rc, (lib.isomc_sharded_last_error(None) or b"").decode())
+        self._lib = lib
+
+    def _check(self, rc):
+        if rc:
+            raise _lib.IsomcError(rc, (self._lib.isomc_sharded_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.isomc_sharded_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def uses_nccl(self):
+        return bool(self._lib.isomc_sharded_uses_nccl(self._h))
+
+    def slab(self, rank):
+        """(z_begin, z_end, first sample layer, number of sample layers) of `rank`"""
+        v = [C.c_uint32() for _ in range(4)]
+        self._check(self._lib.isomc_sharded_slab(self._h, rank, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def extract_grid(self, slab_ptrs):
+        """slab_ptrs[r]: device pointer (on devices[r]) to rank r's sample layers"""
+        arr = (C.c_void_p * len(self.devices))(*[int(p) for p in slab_ptrs])
+        self._check(self._lib.isomc_sharded_extract_grid(self._h, arr))
+        return self.counts()
+
+    def extract_sdf(self, source):
+        from .source import Sampler, encode_program
+        prog = encode_program(source.source if isinstance(source, Sampler) else source)
+        self._check(self._lib.isomc_sharded_extract_sdf(self._h, prog.ctypes.data, len(prog)))
+        return self.counts()
+
+    def counts(self):
+        v, t, a = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.isomc_sharded_counts(self._h, C.byref(v), C.byref(t), C.byref(a)))
+        return v.value, t.value, a.value
+
+    def copy_out(self):
+        nv, nt, _ = self.counts()
+        xyz = np.empty(nv * 3, np.float32)
+        idx = np.empty(nt * 3, np.uint32)
+        self._check(self._lib.isomc_sharded_copy_out(self._h, xyz.ctypes.data, idx.ctypes.data))
+        return xyz, idx

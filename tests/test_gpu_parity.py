@@ -341,9 +341,12 @@ def test_full_size_slabs_equal_unsharded_1024(iso):
     assert facts["directed_edge_dups"] == 0
 
 
-def test_plain_fill_and_list_path_are_bit_identical(iso, oracle, monkeypatch):
-    """ISOMC_FILL=plain (all-thread loads instead of the TMA bulk copies) and ISOMC_PATH=list (the round-1 kernels) must give
-    the same bytes as the default tile path"""
+@pytest.mark.parametrize("env", [{"ISOMC_PATH": "tile"}, {"ISOMC_PATH": "tile", "ISOMC_FILL": "plain"}, {"ISOMC_PATH": "tile", "ISOMC_RING": "2"}])
+def test_tile_path_is_bit_identical(iso, oracle, monkeypatch, env):
+    """ISOMC_PATH=tile (TMA-staged one-pass count + plane emission; opt-in, profiles/r02_tile_path.md), with the TMA bulk
+    copies, with all-thread loads (ISOMC_FILL=plain) and with the two-slot ring: same bytes as the default path and the oracle
+    -- grids, slabs, implicit and Directed sources, the streamed host extract"""
+    from isosurface_b200.sharded import SlabMarchingCubes, slab_sample_layers
     size = 160
     t = synth(iso, 1, size, 5)
     mc = iso.MarchingCubes(size)
@@ -353,16 +356,55 @@ def test_plain_fill_and_list_path_are_bit_identical(iso, oracle, monkeypatch):
     host = t.cpu().numpy().reshape(size + 1, size, size)
     oxyz, oidx, _ = oracle.extract_grid(size, host)
     assert ref[1] == oidx.tobytes() and ref[0] == oxyz.tobytes()
-    monkeypatch.setenv("ISOMC_PATH", "list")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     mp = iso.MarchingCubes(size)          # the environment is read at create
     for _ in range(2):
         mp.extract_device(iso.DenseGrid(t))
         assert [a.tobytes() for a in mp.copy_out()] == ref
+    xyz, idx = mp.extract_host(iso.DenseGrid(host))
+    assert xyz.tobytes() == ref[0] and idx.tobytes() == ref[1]
+    xyz, idx = mp.extract_host(iso.DenseGrid(host))    # second call: the streamed z-chunk pipeline
+    assert xyz.tobytes() == ref[0] and idx.tobytes() == ref[1]
     mp.close()
+    for size2, kind, seed in ((67, 3, 9), (520, 1, 3)):   # N % 4 != 0; rows of two tiles (halo columns)
+        nl = size2 + 1 if size2 < 200 else 13
+        t2 = synth(iso, kind, size2, seed, 0, nl)
+        h2 = t2.cpu().numpy().reshape(nl, size2, size2)
+        wx, wi, _ = oracle.extract_grid(size2, h2, nl - 1)
+        s0 = SlabMarchingCubes(size2, 0, 1) if nl == size2 + 1 else None
+        if s0 is not None:
+            s0.extract(t2.data_ptr())
+            px, pi = s0.copy_out()
+            s0.close()
+            assert mesh_diff(px, pi, wx, wi, POS_TOL) == ""
+    world = 3
+    slabs = [SlabMarchingCubes(size, r, world) for r in range(world)]
+    ptrs = [t.data_ptr() + 4 * slab_sample_layers(size, r, world)[0] * size * size for r in range(world)]
+    totals = np.array([s.count(p) for s, p in zip(slabs, ptrs)], dtype=np.uint64)
+    parts = []
+    for r, s in enumerate(slabs):
+        s.extract(ptrs[r], gathered=totals)
+        parts.append(s.copy_out())
+        s.close()
+    assert np.concatenate([p[0] for p in parts]).tobytes() == ref[0] and np.concatenate([p[1] for p in parts]).tobytes() == ref[1]
+    for name, n in (("csgA", 64), ("torus_origin", 96)):
+        m2 = iso.MarchingCubes(n)
+        m2.extract_device(iso.Sampler(iso_source(name)))
+        xyz, idx = m2.copy_out()
+        m2.close()
+        oxyz2, oidx2, _ = oracle.extract_sdf(n, oracle_prog(name))
+        assert mesh_diff(xyz, idx, oxyz2, oidx2, POS_TOL) == ""
+    md = iso.MarchingCubes(48, distance="directed")
+    md.extract_device(iso.Sampler(iso_source("csgB")))
+    xyz, idx = md.copy_out()
+    md.close()
+    oxyz3, oidx3, _ = oracle.extract_sdf_directed(48, oracle_prog("csgB"))
+    assert mesh_diff(xyz, idx, oxyz3, oidx3, POS_TOL) == ""
 
 
-def test_non_multiple_of_four_size_uses_plain_fill(iso, oracle):
-    """N % 4 != 0 (or a misaligned pointer) cannot be staged by TMA bulk copies: all-thread loads fill the tile slots"""
+def test_non_multiple_of_four_size_uses_generic_sign_kernel(iso, oracle):
+    """N % 4 != 0 (or a misaligned pointer) takes the scalar k_sign path instead of the float4 one"""
     import torch
     for size in (66, 67, 131):
         t = synth(iso, 3, size, 9)
@@ -538,3 +580,151 @@ def test_chunked_driver_overlaps_small_extracts(iso, oracle):
     drv.extract_many(sources[:5], deliver=lambda i, xyz, idx: seen.append((i, len(idx))))
     assert [i for i, _ in seen] == [0, 1, 2, 3, 4] and all(n == len(w[1]) for (_, n), w in zip(seen, want))
     drv.close()
+
+
+# ---- full-size parity (SURVEY 8c / VERDICT r01): committed oracle hashes of the benchmark fields, made on a B200 box by
+# tools/gen_golden_full.py (device-generated field bytes -> CPU oracle in lean mode); plus one live full-size oracle run
+FULL_PATH = Path(__file__).parent / "golden" / "full_hashes.json"
+FULL = json.loads(FULL_PATH.read_text()) if FULL_PATH.exists() else {}
+
+
+def _golden_field(iso, name):
+    if name not in FULL:
+        pytest.skip("tests/golden/full_hashes.json has no entry for %s (run tools/gen_golden_full.py on the GPU box)" % name)
+    g = FULL[name]
+    t = synth(iso, g["kind"], g["size"], g["seed"], 0, g["z_cells"] + 1)
+    return g, t
+
+
+@pytest.mark.parametrize("name", ["fbm512", "gyroid1024"])
+def test_full_size_mesh_matches_committed_oracle_hashes(iso, name):
+    """BASELINE C3 / C4 at full size: the WHOLE device mesh (every layer, the last ones included) hashes to what the CPU
+    oracle produced from the same field bytes"""
+    g, t = _golden_field(iso, name)
+    mc = iso.MarchingCubes(g["size"])
+    nv, nt, na = mc.extract_device(iso.DenseGrid(t))
+    xyz, idx = mc.copy_out()
+    mc.close()
+    assert (na, nv, nt) == (g["active_cells"], g["vertices"], g["triangles"])
+    assert sha(idx, "<u4") == g["sha_i"], "index stream differs from the oracle's"
+    assert sha(xyz, "<f4") == g["sha_v"], "vertex stream differs from the oracle's"
+
+
+@pytest.mark.parametrize("name", ["fbm644_z32", "fbm812_z32", "fbm1024_z24", "spheres2048_z64"])
+def test_window_matches_committed_oracle_hashes(iso, isolib, name):
+    """the workloads the scaling runs time (fbm644 / fbm812 / fbm1024) and C5: the first cell layers against the oracle"""
+    from isosurface_b200 import _lib
+    g, t = _golden_field(iso, name)
+    h = C.c_void_p()
+    _lib.check(isolib.isomc_slab_create(g["size"], 0, g["z_cells"], 0, C.byref(h)))
+    _lib.check(isolib.isomc_slab_count_grid_device(h, C.c_void_p(t.data_ptr())), h)
+    _lib.check(isolib.isomc_slab_emit(h, 0, 0), h)
+    v, tr, a = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    _lib.check(isolib.isomc_counts(h, C.byref(v), C.byref(tr), C.byref(a)), h)
+    xyz, idx = np.empty(3 * v.value, np.float32), np.empty(3 * tr.value, np.uint32)
+    _lib.check(isolib.isomc_copy_out(h, xyz.ctypes.data, idx.ctypes.data), h)
+    isolib.isomc_destroy(h)
+    assert (a.value, v.value, tr.value) == (g["active_cells"], g["vertices"], g["triangles"])
+    assert sha(idx, "<u4") == g["sha_i"] and sha(xyz, "<f4") == g["sha_v"]
+
+
+def test_fbm512_whole_mesh_against_live_oracle(iso, oracle):
+    """BASELINE C3: the whole 512^3 fBm mesh (6.9 M vertices, 13.8 M triangles) against a LIVE lean oracle run on the same
+    field bytes -- memcmp on both streams (tens of seconds of CPU time)"""
+    size = 512
+    t = synth(iso, 1, size, 0x1505F00D)
+    mc = iso.MarchingCubes(size)
+    mc.extract_device(iso.DenseGrid(t))
+    xyz, idx = mc.copy_out()
+    mc.close()
+    host = t.cpu().numpy().reshape(size + 1, size, size)
+    oxyz, oidx, _ = oracle.extract_grid(size, host, size, oracle.LEAN)
+    assert len(idx) == len(oidx) and np.array_equal(idx, oidx)
+    assert len(xyz) == len(oxyz) and np.array_equal(xyz.view(np.uint32), oxyz.view(np.uint32))
+
+
+def test_full_size_2048_slabs_equal_unsharded(iso):
+    """BASELINE C5 (2048^3 sphere union, 34 GB): the unsharded extract -- sample offsets beyond 2^32, 8.6 G cells in one
+    handle -- equals the 8-slab decomposition byte for byte, and the size-independent invariants hold"""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 60 * (1 << 30):
+        pytest.skip("needs ~45 GB of device memory")
+    from isosurface_b200.sharded import SlabMarchingCubes, slab_sample_layers
+    size, world = 2048, 8
+    t = synth(iso, 3, size, 0x5EEDBA11)
+    mc = iso.MarchingCubes(size)
+    nv, nt, na = mc.extract_device(iso.DenseGrid(t))
+    xyz, idx = mc.copy_out()
+    mc.close()
+    assert nv == len(xyz) // 3 and nt == len(idx) // 3 and nt > 50_000_000
+    assert int(idx.max()) == nv - 1
+    ref = np.zeros(nv, bool)
+    ref[idx] = True
+    assert ref.all()                                   # every vertex referenced
+    del ref
+    assert np.isfinite(xyz).all() and xyz.min() >= 0.0 and xyz.max() <= 2048 / 2047 + 1e-6
+    head = idx[: 30_000_000]
+    first_use = np.full(int(head.max()) + 1, np.iinfo(np.int64).max)
+    np.minimum.at(first_use, head, np.arange(len(head)))
+    assert np.all(np.diff(first_use) > 0)              # vertex k is first referenced before vertex k+1 (mesh.rs:240-251)
+    del first_use, head
+    slabs = [SlabMarchingCubes(size, r, world) for r in range(world)]
+    ptrs = [t.data_ptr() + 4 * slab_sample_layers(size, r, world)[0] * size * size for r in range(world)]
+    totals = np.array([s.count(p) for s, p in zip(slabs, ptrs)], dtype=np.uint64)
+    vo = io = 0
+    for r, s in enumerate(slabs):
+        s.extract(ptrs[r], gathered=totals)
+        px, pi = s.copy_out()
+        assert np.array_equal(xyz[vo:vo + len(px)].view(np.uint32), px.view(np.uint32)), "slab %d vertices" % r
+        assert np.array_equal(idx[io:io + len(pi)], pi), "slab %d indices" % r
+        vo += len(px); io += len(pi)
+        s.close()
+    assert vo == len(xyz) and io == len(idx)
+
+
+@pytest.mark.parametrize("world", [1, 3, 4])
+def test_sharded_api_on_one_device(iso, oracle, world):
+    """isomc_sharded_*: all slabs on device 0 (the exchange is then a stream-ordered device copy): == unsharded == oracle;
+    a second extract of a different field re-uses the handles"""
+    from isosurface_b200.sharded import ShardedMarchingCubes
+    size = 80
+    sh = ShardedMarchingCubes(size, [0] * world)
+    assert not sh.uses_nccl
+    for kind, seed in ((1, 31), (3, 7), (1, 32)):
+        t = synth(iso, kind, size, seed)
+        host = t.cpu().numpy().reshape(size + 1, size, size)
+        oxyz, oidx, oact = oracle.extract_grid(size, host)
+        ptrs = [t.data_ptr() + 4 * sh.slab(r)[2] * size * size for r in range(world)]
+        nv, nt, na = sh.extract_grid(ptrs)
+        xyz, idx = sh.copy_out()
+        assert na == oact and mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    nv, nt, na = sh.extract_sdf(iso.Sampler(iso_source("csgA")))
+    xyz, idx = sh.copy_out()
+    oxyz, oidx, oact = oracle.extract_sdf(size, oracle_prog("csgA"))
+    assert na == oact and mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    sh.close()
+
+
+def test_sharded_api_nccl_all_devices(iso, oracle):
+    """isomc_sharded_* over every GPU of the box: one NCCL all-gather per extract, each slab's lattice on its own device"""
+    import torch
+    from isosurface_b200 import _lib
+    from isosurface_b200.sharded import ShardedMarchingCubes
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (the single-device mode is covered by test_sharded_api_on_one_device)")
+    size = 96
+    t = synth(iso, 1, size, 77)
+    host = t.cpu().numpy().reshape(size + 1, size, size)
+    oxyz, oidx, oact = oracle.extract_grid(size, host)
+    sh = ShardedMarchingCubes(size, list(range(n)))
+    assert sh.uses_nccl
+    parts = []
+    for r in range(n):
+        zb, ze, first, nl = sh.slab(r)
+        parts.append(torch.from_numpy(host[first:first + nl].copy()).to("cuda:%d" % r))
+    for _ in range(2):
+        nv, nt, na = sh.extract_grid([p.data_ptr() for p in parts])
+        xyz, idx = sh.copy_out()
+        assert na == oact and mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    sh.close()
