@@ -137,6 +137,12 @@ int32_t isomc_copy_out(isomc_t *h, float *xyz /* 3*V */, uint32_t *idx /* 3*T */
  * DemoSource does around its CentralDifference, examples/common/sources.rs:55-60).  xyzn holds 6*V floats, idx 3*T (may be NULL). */
 int32_t isomc_copy_out_interleaved_normals(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes, float epsilon, float *xyzn,
                                            uint32_t *idx);
+/* the same with the POSITION of the CentralDifference adaptor made explicit: only the first `n_outer_translations` enclosing
+ * TRANSLATE pairs are outside the adaptor (applied to the vertex before differencing: f((v - o) +- eps)); translations inside
+ * it are part of the differenced function (f((v +- eps) - o)), which is what `CentralDifference(Translate(..))` means in the
+ * reference (src/source.rs:82-94).  The call above treats every enclosing translation as outside (`Translate(CentralDifference(..))`). */
+int32_t isomc_copy_out_interleaved_normals_at(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes, float epsilon,
+                                              uint32_t n_outer_translations, float *xyzn, uint32_t *idx);
 int32_t isomc_stats_get(isomc_t *h, isomc_stats *out);
 
 /* ---- stream control (benchmarks time with CUDA events on the launching stream) ---------- */

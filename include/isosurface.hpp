@@ -74,13 +74,17 @@ struct CentralDifferenceT {
     void encode(SdfProgram &p) const { source.encode(p); }
 };
 template <class S> CentralDifferenceT<S> CentralDifference(S source, float epsilon = 0.000001f) { return {source, epsilon}; }
-template <class S> struct has_central_difference { static constexpr bool value = false; static float epsilon(const S &) { return 0; } };
+// outer = Translate wrappers OUTSIDE the adaptor: Translate(o, CentralDifference(T)) differentiates f at v - o, while
+// CentralDifference(Translate(o, T)) differentiates the translated function; both encode to the same program
+template <class S> struct has_central_difference { static constexpr bool value = false; static constexpr uint32_t outer = 0; static float epsilon(const S &) { return 0; } };
 template <class S> struct has_central_difference<CentralDifferenceT<S>> {
     static constexpr bool value = true;
+    static constexpr uint32_t outer = 0;
     static float epsilon(const CentralDifferenceT<S> &s) { return s.epsilon; }
 };
 template <class S> struct has_central_difference<TranslateT<S>> {
     static constexpr bool value = has_central_difference<S>::value;
+    static constexpr uint32_t outer = has_central_difference<S>::outer + 1;
     static float epsilon(const TranslateT<S> &s) { return has_central_difference<S>::epsilon(s.child); }
 };
 
@@ -112,12 +116,12 @@ struct OnlyVertices : Extractor {  // extractor.rs:24-43
 
 // extractor.rs:95-127: x y z nx ny nz per vertex; the normals of a CentralDifference source are sampled on the device
 struct InterleavedNormalsSink {
-    std::vector<float> &vertices; std::vector<uint32_t> &indices; SdfProgram program; float epsilon;
+    std::vector<float> &vertices; std::vector<uint32_t> &indices; SdfProgram program; float epsilon; uint32_t outer_translations;
 };
 template <class S>
 InterleavedNormalsSink IndexedInterleavedNormals(std::vector<float> &v, std::vector<uint32_t> &i, const S &source) {
     static_assert(has_central_difference<S>::value, "IndexedInterleavedNormals needs a CentralDifference source on the device path");
-    InterleavedNormalsSink sink{v, i, {}, has_central_difference<S>::epsilon(source)};
+    InterleavedNormalsSink sink{v, i, {}, has_central_difference<S>::epsilon(source), has_central_difference<S>::outer};
     source.encode(sink.program);
     return sink;
 }
@@ -179,8 +183,8 @@ class MarchingCubes {
         const size_t v0 = sink.vertices.size(), i0 = sink.indices.size();
         sink.vertices.resize(v0 + 6 * nv);
         sink.indices.resize(i0 + 3 * nt);
-        check(isomc_copy_out_interleaved_normals(h_, sink.program.data(), (uint32_t)sink.program.size(), sink.epsilon,
-                                                 sink.vertices.data() + v0, sink.indices.data() + i0));
+        check(isomc_copy_out_interleaved_normals_at(h_, sink.program.data(), (uint32_t)sink.program.size(), sink.epsilon,
+                                                    sink.outer_translations, sink.vertices.data() + v0, sink.indices.data() + i0));
     }
     template <class S> void extract(const SamplerT<S> &sampler, InterleavedNormalsSink &sink) { extract(sampler.source, sink); }
     isomc_t *handle() { return h_; }
@@ -221,6 +225,7 @@ class PointCloud : public MarchingCubes {
         deliver(extractor);
     }
     void extract(const DenseGrid &grid, Extractor &extractor) {
+        if (grid.size != size_) throw Error(ISOMC_ERR_BAD_ARG, "grid size does not match");
         check(grid.on_device ? isomc_points_grid_device(h_, grid.data) : isomc_points_grid_host(h_, grid.data));
         deliver(extractor);
     }

@@ -57,6 +57,7 @@ SIGNATURES = {
     "isomc_device_buffers": (_I32, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "isomc_copy_out": (_I32, [_P, _P, _P]),
     "isomc_copy_out_interleaved_normals": (_I32, [_P, _P, _U32, C.c_float, _P, _P]),
+    "isomc_copy_out_interleaved_normals_at": (_I32, [_P, _P, _U32, C.c_float, _U32, _P, _P]),
     "isomc_stats_get": (_I32, [_P, C.POINTER(Stats)]),
     "isomc_get_stream": (_I32, [_P, C.POINTER(_P)]),
     "isomc_set_stream": (_I32, [_P, _P]),

@@ -824,6 +824,11 @@ int32_t isomc_copy_out(isomc_t *h, float *xyz, uint32_t *idx) {
 /* IndexedInterleavedNormals with a CentralDifference source (reference src/extractor.rs:95-127, src/source.rs:82-94) */
 int32_t isomc_copy_out_interleaved_normals(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes, float epsilon, float *xyzn,
                                            uint32_t *idx) {
+    return isomc_copy_out_interleaved_normals_at(h, prog, n_nodes, epsilon, 0xFFFFFFFFu, xyzn, idx);
+}
+
+int32_t isomc_copy_out_interleaved_normals_at(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes, float epsilon,
+                                              uint32_t n_outer_translations, float *xyzn, uint32_t *idx) {
     if (!h) return ISOMC_ERR_BAD_ARG;
     if (!h->have_result) return fail(h, ISOMC_ERR_NO_RESULT, "no extract has completed on this handle");
     if (!(epsilon > 0.0f)) return fail(h, ISOMC_ERR_BAD_ARG, "epsilon must be positive");
@@ -832,11 +837,11 @@ int32_t isomc_copy_out_interleaved_normals(isomc_t *h, const isomc_sdf_node *pro
     if (rc) return rc;
     rc = bind_device(h);
     if (rc) return rc;
-    /* translations that enclose the whole program are applied to the vertex first (DemoSource around CentralDifference,
-     * examples/common/sources.rs:55-60); the differences are taken on what is inside */
+    /* translations that enclose the whole program AND lie outside the CentralDifference adaptor are applied to the vertex
+     * first (DemoSource around CentralDifference, examples/common/sources.rs:55-60); the differences are taken on what is inside */
     float offsets[ISOMC_SDF_MAX_TRANSLATE][3];
     uint32_t n_off = 0, lo = 0, hi = P.n;
-    while (hi - lo >= 3 && P.nodes[lo].op == ISOMC_SDF_TRANSLATE_PUSH && P.nodes[hi - 1].op == ISOMC_SDF_TRANSLATE_POP) {
+    while (n_off < n_outer_translations && hi - lo >= 3 && P.nodes[lo].op == ISOMC_SDF_TRANSLATE_PUSH && P.nodes[hi - 1].op == ISOMC_SDF_TRANSLATE_POP) {
         int depth = 0;
         bool encloses = true;
         for (uint32_t i = lo; i < hi; ++i) {
@@ -847,6 +852,8 @@ int32_t isomc_copy_out_interleaved_normals(isomc_t *h, const isomc_sdf_node *pro
         offsets[n_off][0] = P.nodes[lo].a; offsets[n_off][1] = P.nodes[lo].b; offsets[n_off][2] = P.nodes[lo].c;
         ++n_off; ++lo; --hi;
     }
+    if (n_outer_translations != 0xFFFFFFFFu && n_off != n_outer_translations)
+        return fail(h, ISOMC_ERR_BAD_ARG, "the program is enclosed by %u translations, %u were said to lie outside the CentralDifference", n_off, n_outer_translations);
     SdfProgram inner;
     memset(&inner, 0, sizeof inner);
     inner.n = hi - lo;

@@ -55,9 +55,9 @@ class IndexedInterleavedNormals(Extractor):
     normals are evaluated on the device at the extracted vertices (isomc_copy_out_interleaved_normals)."""
 
     def __init__(self, vertices, indices, source):
-        from .source import find_central_difference
+        from .source import locate_central_difference
         self.vertices, self.indices, self.source = vertices, indices, source
-        self.central_difference = find_central_difference(source)
+        self.central_difference, self.outer_translations = locate_central_difference(source)
         if self.central_difference is None:
             raise TypeError("IndexedInterleavedNormals needs a CentralDifference source on the device path "
                             "(analytic sample_normal implementations are host code in the reference and not a device path)")

@@ -45,7 +45,8 @@ class MarchingCubes:
         src = source.source if isinstance(source, Sampler) else source
         if hasattr(extractor, "_bulk_normals"):  # IndexedInterleavedNormals: normals sampled on the device
             self.extract_device(source)
-            xyzn, idx = self.copy_out_interleaved_normals(extractor.source, extractor.central_difference.epsilon)
+            xyzn, idx = self.copy_out_interleaved_normals(extractor.source, extractor.central_difference.epsilon,
+                                                          extractor.outer_translations)
             extractor._bulk_normals(xyzn, idx)
             return
         if isinstance(src, DenseGrid) and not src.on_device:
@@ -133,15 +134,17 @@ class MarchingCubes:
         _lib.check(self._lib.isomc_copy_out(self._h, xyz.ctypes.data, idx.ctypes.data), self._h)
         return xyz, idx
 
-    def copy_out_interleaved_normals(self, normal_source, epsilon=0.000001):
+    def copy_out_interleaved_normals(self, normal_source, epsilon=0.000001, outer_translations=None):
         """(6V,) float32 x y z nx ny nz and (3T,) uint32 of the last extract; normals = central differences of
-        `normal_source` (reference src/extractor.rs:113-122, src/source.rs:82-94), evaluated on the device"""
+        `normal_source` (reference src/extractor.rs:113-122, src/source.rs:82-94), evaluated on the device.
+        outer_translations: how many enclosing Translate wrappers lie outside the CentralDifference adaptor (None: all)"""
         nv, nt, _ = self.counts()
         prog = encode_program(normal_source)
         xyzn = np.empty(nv * 6, np.float32)
         idx = np.empty(nt * 3, np.uint32)
-        _lib.check(self._lib.isomc_copy_out_interleaved_normals(self._h, prog.ctypes.data, len(prog), epsilon, xyzn.ctypes.data,
-                                                                idx.ctypes.data), self._h)
+        outer = 0xFFFFFFFF if outer_translations is None else int(outer_translations)
+        _lib.check(self._lib.isomc_copy_out_interleaved_normals_at(self._h, prog.ctypes.data, len(prog), epsilon, outer,
+                                                                   xyzn.ctypes.data, idx.ctypes.data), self._h)
         return xyzn, idx
 
     def device_buffers(self):

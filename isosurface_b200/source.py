@@ -161,14 +161,24 @@ class CentralDifference(DeviceSource):
 
 def find_central_difference(source):
     """the CentralDifference adaptor of a source, looking through Sampler and enclosing Translate wrappers"""
-    s = source
+    return locate_central_difference(source)[0]
+
+
+def locate_central_difference(source):
+    """(adaptor, number of Translate wrappers OUTSIDE it): `Translate(o, CentralDifference(T))` differentiates f at v - o,
+    `CentralDifference(Translate(o, T))` differentiates the translated function -- the encodings are the same program, so the
+    position of the adaptor travels beside it (isomc_copy_out_interleaved_normals_at)"""
+    s, outer = source, 0
     while True:
         if isinstance(s, CentralDifference):
-            return s
-        if isinstance(s, (Sampler, Translate)):
+            return s, outer
+        if isinstance(s, Sampler):
             s = s.source
             continue
-        return None
+        if isinstance(s, Translate):
+            s, outer = s.source, outer + 1
+            continue
+        return None, 0
 
 
 class Sampler:
