@@ -118,6 +118,19 @@ int32_t isomc_extract_grid_host(isomc_t *h, const float *h_grid);
 int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, uint64_t cap_vertices, uint32_t *idx,
                                    uint64_t cap_triangles);
 
+/* ---- many chunks in one go (new) --------------------------------------------------------------
+ * The crate's usage model is many `size`^3 chunks (reference src/marching_cubes.rs:44-45, README.md:19), each one
+ * `MarchingCubes::new(size).extract(&Sampler::new(&tree_b), ..)` over its own tree (a chunk is placed by the TRANSLATE nodes of
+ * its tree: the reference has no chunk offset either).  A batch handle extracts up to `n_chunks` of them as ONE kernel sequence
+ * with one size read-back, which removes the launch / synchronisation latency that dominates a 32^3 extract.
+ * `progs` = the chunks' programs back to back, n_nodes[b] nodes each.  Results: isomc_counts() = totals over the batch,
+ * isomc_copy_out() = the chunks' meshes back to back; chunk b owns vertices [v_offsets[b], v_offsets[b+1]) and triangles
+ * [t_offsets[b], t_offsets[b+1]) (n_chunks + 1 entries each), and its indices are relative to ITS first vertex -- every chunk
+ * is byte for byte what a single isomc_extract_sdf of its program returns. */
+int32_t isomc_batch_create(uint32_t size, uint32_t n_chunks, int32_t device, isomc_t **out);
+int32_t isomc_extract_sdf_batch(isomc_t *h, const isomc_sdf_node *progs, const uint32_t *n_nodes, uint32_t n_chunks);
+int32_t isomc_batch_offsets(isomc_t *h, uint64_t *v_offsets, uint64_t *t_offsets);
+
 /* ---- PointCloud::<Signed>::new(size).extract(&source, &mut extractor)  (reference src/point_cloud.rs:50-63) ----
  * One point per active cell (cube index neither 0 nor 255): corners[0].lerp(corners[6], 0.5), in (z, y, x) cell order.
  * Results through the same calls as a mesh: isomc_counts() reports the points as vertices (0 triangles),

@@ -8,11 +8,11 @@ package is the Python host-side mirror of the crate's interface for that one pat
 See DESIGN.md for the path, INTEGRATION.md for the Rust-side binding.
 """
 from .extractor import ArrayMesh, Extractor, IndexedInterleavedNormals, IndexedVertices, OnlyVertices
-from .chunks import ChunkedMarchingCubes
+from .chunks import BatchedMarchingCubes, ChunkedMarchingCubes
 from .marching_cubes import MarchingCubes, PointCloud
 from .source import (CentralDifference, Cylinder, DenseGrid, DeviceSource, Difference, Intersection, RectangularPrism, Sampler,
                      Sphere, Torus, Translate, Union)
 
-__all__ = ["MarchingCubes", "PointCloud", "ChunkedMarchingCubes", "Sampler", "DenseGrid", "DeviceSource", "Sphere", "Torus", "Cylinder",
+__all__ = ["MarchingCubes", "PointCloud", "ChunkedMarchingCubes", "BatchedMarchingCubes", "Sampler", "DenseGrid", "DeviceSource", "Sphere", "Torus", "Cylinder",
            "RectangularPrism", "Union", "Intersection", "Difference", "Translate", "Extractor",
            "IndexedVertices", "OnlyVertices", "ArrayMesh", "IndexedInterleavedNormals", "CentralDifference"]

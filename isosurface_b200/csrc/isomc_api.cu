@@ -26,7 +26,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum SrcKind { SRC_NONE = 0, SRC_GRID = 1, SRC_SDF = 2 };
+enum SrcKind { SRC_NONE = 0, SRC_GRID = 1, SRC_SDF = 2, SRC_SDF_BATCH = 3 };
 constexpr int MAX_CHUNKS = 16;
 /* u32 after layerTot: emit tickets [MAX_CHUNKS], list block counter, list marks [MAX_CHUNKS + 1], chunk ends [2 * MAX_CHUNKS],
  * tile path: block counters [2] (+ 2 pad), tickets of pass 1 [MAX_CHUNKS] and of pass 2 [MAX_CHUNKS] */
@@ -55,6 +55,11 @@ struct isomc {
     TileBufs TB{};
     uint32_t *tile_tickets = nullptr; /* [MAX_CHUNKS] pass 1, [MAX_CHUNKS] pass 2 */
     uint32_t *segA = nullptr;         /* PointCloud: per-segment prefixes (allocated on first use, with `signs`) */
+    /* batched chunks (isomc_batch_create): `batch` lattices stacked in z (Geo.zper), one implicit tree each */
+    uint32_t batch = 0, batch_used = 0;
+    SdfProgram *d_progs = nullptr, *h_progs = nullptr; /* h_progs pinned */
+    uint32_t *chunkV = nullptr, *chunkT = nullptr;     /* device: [batch + 1] output slots of the chunks' first vertex / triangle */
+    uint32_t *h_chunk = nullptr;                       /* pinned: 2 * (batch + 1) */
     ListBufs L{};
     uint32_t *list_marks = nullptr; /* [c] = list blocks handed out before z-chunk c; [0] = 0 */
     EmitTab *etab = nullptr;
@@ -230,7 +235,10 @@ int32_t launch_emit_chunk(isomc *h, uint32_t c, cudaStream_t st) {
         return ISOMC_OK;
     }
     /* one kernel: edge ids, vertex positions and triangles of the chunk's active cells */
-    if (h->kind == SRC_GRID)
+    if (h->kind == SRC_SDF_BATCH)
+        CU(h, isomc_launch_emit_list_sdf_batch(g, h->d_progs, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
+                                               h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
+    else if (h->kind == SRC_GRID)
         CU(h, isomc_launch_emit_list_grid(g, h->d_grid, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
                                           h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
     else
@@ -256,12 +264,17 @@ int32_t launch_count_chunk(isomc *h, uint32_t c, cudaStream_t st, uint32_t *chun
         return ISOMC_OK;
     }
     const uint32_t row0 = (c == 0 ? 0u : l0 + 1) * g.N, row1 = (l1 + 1) * g.N;
-    if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, row0, row1, h->sms, 8, st));
+    if (h->kind == SRC_SDF_BATCH) CU(h, isomc_launch_sign_sdf_batch(g, h->d_progs, h->signs, row0, row1, h->sms, st));
+    else if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, row0, row1, h->sms, 8, st));
     else CU(h, isomc_launch_sign_sdf(g, h->prog, h->directed, h->signs, row0, row1, h->sms, 8, st));
     if (h->profiling) CU(h, cudaEventRecord(h->ev[1], st));
     CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, h->ticket + c, l0, l1, h->sms, st));
     if (h->profiling) CU(h, cudaEventRecord(h->ev[2], st));
     CU(h, isomc_launch_scan(g, g.ncx, h->rowV, h->rowT, h->layerTot, h->totals, h->L.ctr, h->list_marks + c + 1, chunk_end, l0, l1, st));
+    if (h->batch) { /* per-lattice totals -> output bases, grand totals */
+        CU(h, isomc_launch_chunk_bases(h->batch, h->totals, h->L.ctr, h->chunkV, h->chunkT, st));
+        h->stats.kernel_launches += 1;
+    }
     if (h->profiling) CU(h, cudaEventRecord(h->ev[3], st));
     h->stats.kernel_launches += 3;
     return ISOMC_OK;
@@ -390,7 +403,7 @@ int32_t set_vofs(isomc *h, uint32_t v) {
     return ISOMC_OK;
 }
 
-int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t device, isomc_t **out) {
+int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t device, isomc_t **out, uint32_t batch = 0) {
     if (!out) return fail(nullptr, ISOMC_ERR_BAD_ARG, "out == NULL");
     *out = nullptr;
     /* size == 0 underflows in the reference (primal_grid.rs:44); size > 8192 overflows the packed row prefixes */
@@ -415,6 +428,21 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
     g.nsl = g.ncl + 1;
     g.inv = 1.0f / (float)(size - 1);
     g.row_magic = g.ncx ? ((1ull << 40) + g.ncx - 1) / g.ncx : 0;
+    if (batch) { /* `batch` lattices of size^2 x (size+1) samples stacked in z; the cell layer between two of them is dead */
+        if (size < 2) {
+            delete h;
+            return fail(nullptr, ISOMC_ERR_BAD_ARG, "batched chunks need size >= 2");
+        }
+        g.zper = size + 1;
+        g.ncl = batch * (size + 1) - 1;
+        g.nsl = g.ncl + 1;
+        if ((uint64_t)g.ncl * g.ncx >= (1ull << 26) || batch > 65535u) {
+            delete h;
+            return fail(nullptr, ISOMC_ERR_BAD_ARG, "batch of %u chunks of size %u is too large for one handle (%llu cell rows, limit 2^26)", batch,
+                        size, (unsigned long long)g.ncl * g.ncx);
+        }
+        h->batch = batch;
+    }
     int32_t rc = ISOMC_OK;
     auto body = [&]() -> int32_t {
         CU(h, cudaSetDevice(device));
@@ -430,6 +458,7 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
         CU(h, cudaMemcpy(h->tabs, &host_tabs, sizeof(McTables), cudaMemcpyHostToDevice));
         const uint64_t nrows_s = (uint64_t)g.nsl * g.N, nrows_c = (uint64_t)g.ncl * g.ncx;
         if (const char *p = getenv("ISOMC_PATH")) h->tile_mode = strcmp(p, "tile") == 0;
+        if (h->batch) h->tile_mode = false; /* (stacked lattices are served by the list kernels) */
         h->tg = tile_geo(g);
         EmitTab host_etab;
         isomc_build_emit_tab(host_tabs, &host_etab);
@@ -469,8 +498,16 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
         h->TB.ctr = h->ticket + 4 * MAX_CHUNKS + 4;
         h->tile_tickets = h->ticket + 4 * MAX_CHUNKS + 8;
         h->TB.layerTot = h->layerTot;
-        CU(h, cudaMalloc(&h->totals, N_TOTALS * sizeof(unsigned long long)));
-        CU(h, cudaMemset(h->totals, 0, N_TOTALS * sizeof(unsigned long long)));
+        CU(h, cudaMalloc(&h->totals, (N_TOTALS + 3 * (size_t)h->batch) * sizeof(unsigned long long)));
+        CU(h, cudaMemset(h->totals, 0, (N_TOTALS + 3 * (size_t)h->batch) * sizeof(unsigned long long)));
+        if (h->batch) {
+            CU(h, cudaMalloc(&h->d_progs, h->batch * sizeof(SdfProgram)));
+            CU(h, cudaMallocHost(&h->h_progs, h->batch * sizeof(SdfProgram)));
+            CU(h, cudaMalloc(&h->chunkV, (h->batch + 1) * sizeof(uint32_t)));
+            CU(h, cudaMalloc(&h->chunkT, (h->batch + 1) * sizeof(uint32_t)));
+            CU(h, cudaMallocHost(&h->h_chunk, 2 * (h->batch + 1) * sizeof(uint32_t)));
+            h->L.chunkV = h->chunkV; h->L.chunkT = h->chunkT;
+        }
         CU(h, cudaMalloc(&h->vofs, sizeof(uint32_t)));
         CU(h, cudaMemset(h->vofs, 0, sizeof(uint32_t)));
         CU(h, cudaMallocHost(&h->h_totals, N_TOTALS * sizeof(unsigned long long)));
@@ -503,6 +540,9 @@ int32_t isomc_destroy(isomc_t *h) {
     if (!h) return ISOMC_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_progs); cudaFree(h->chunkV); cudaFree(h->chunkT);
+    if (h->h_progs) cudaFreeHost(h->h_progs);
+    if (h->h_chunk) cudaFreeHost(h->h_chunk);
     cudaFree(h->signs); cudaFree(h->segA); cudaFree(h->rowV); cudaFree(h->rowT); cudaFree(h->rowA);
     cudaFree(h->TB.pE); cudaFree(h->TB.pTp); cudaFree(h->TB.pA); cudaFree(h->TB.ent); cudaFree(h->TB.tq); cudaFree(h->TB.tbuf);
     cudaFree(h->layerTot); cudaFree(h->totals); cudaFree(h->vofs); cudaFree(h->tabs);
@@ -557,6 +597,8 @@ int32_t isomc_reserve(isomc_t *h, uint64_t n_vertices, uint64_t n_triangles) {
 /* ---- full extracts ------------------------------------------------------------------------ */
 
 static int32_t enqueue_full(isomc_t *h) {
+    if (h->batch && h->kind != SRC_SDF_BATCH)
+        return fail(h, ISOMC_ERR_BAD_ARG, "this handle is a batch of %u chunks: use isomc_extract_sdf_batch", h->batch);
     if (h->z_begin != 0 || h->z_end != h->size)
         return fail(h, ISOMC_ERR_BAD_ARG, "this handle is a slab [%u, %u): use the isomc_slab_* calls", h->z_begin, h->z_end);
     int32_t rc = bind_device(h);
@@ -724,9 +766,63 @@ int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, 
     return ISOMC_OK;
 }
 
+/* ---- batched chunks: the crate's usage model is many size^3 chunks (src/marching_cubes.rs:44-45, README.md:19),
+ * each one `MarchingCubes::new(size).extract(&Sampler::new(&tree_b), ..)` with its own (translated) tree.  A batch handle runs
+ * all of them as ONE sign / count / scan / emit sequence over stacked lattices, with one size read-back. */
+int32_t isomc_batch_create(uint32_t size, uint32_t n_chunks, int32_t device, isomc_t **out) {
+    if (n_chunks < 1) return fail(nullptr, ISOMC_ERR_BAD_ARG, "n_chunks == 0");
+    return create_impl(size, 0, size, device, out, n_chunks);
+}
+
+int32_t isomc_extract_sdf_batch(isomc_t *h, const isomc_sdf_node *progs, const uint32_t *n_nodes, uint32_t n_chunks) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h->batch) return fail(h, ISOMC_ERR_BAD_ARG, "not a batch handle (isomc_batch_create)");
+    if (!progs || !n_nodes || n_chunks < 1 || n_chunks > h->batch)
+        return fail(h, ISOMC_ERR_BAD_ARG, "bad batch arguments (%u chunks, the handle holds %u)", n_chunks, h->batch);
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream)); /* (the pinned program staging buffer may still be in flight) */
+    const isomc_sdf_node *p = progs;
+    for (uint32_t b = 0; b < h->batch; ++b) {
+        if (b < n_chunks) {
+            rc = validate_program(h, p, n_nodes[b], &h->h_progs[b]);
+            if (rc) return rc;
+            p += n_nodes[b];
+        } else { /* unused lattice: a field that is positive everywhere has no surface */
+            memset(&h->h_progs[b], 0, sizeof(SdfProgram));
+            h->h_progs[b].nodes[0].op = ISOMC_SDF_SPHERE;
+            h->h_progs[b].nodes[0].a = -1.0f;
+            h->h_progs[b].n = 1;
+        }
+    }
+    CU(h, cudaMemcpyAsync(h->d_progs, h->h_progs, h->batch * sizeof(SdfProgram), cudaMemcpyHostToDevice, h->stream));
+    h->kind = SRC_SDF_BATCH; h->d_grid = nullptr; h->directed = false;
+    h->batch_used = n_chunks;
+    rc = enqueue_full(h);
+    return rc ? rc : isomc_finish(h);
+}
+
+int32_t isomc_batch_offsets(isomc_t *h, uint64_t *v_offsets, uint64_t *t_offsets) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h->batch) return fail(h, ISOMC_ERR_BAD_ARG, "not a batch handle (isomc_batch_create)");
+    if (!h->have_result) return fail(h, ISOMC_ERR_NO_RESULT, "no extract has completed on this handle");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    const uint32_t n = h->batch + 1;
+    CU(h, cudaMemcpyAsync(h->h_chunk, h->chunkV, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(h->h_chunk + n, h->chunkT, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (uint32_t b = 0; b <= h->batch_used; ++b) {
+        if (v_offsets) v_offsets[b] = h->h_chunk[b];
+        if (t_offsets) t_offsets[b] = h->h_chunk[n + b];
+    }
+    return ISOMC_OK;
+}
+
 /* ---- PointCloud::new(size).extract(&source, &mut extractor)  (reference src/point_cloud.rs:50-63) -------- */
 
 static int32_t points_impl(isomc_t *h) {
+    if (h->batch) return fail(h, ISOMC_ERR_BAD_ARG, "this handle is a batch of chunks");
     if (h->z_begin != 0 || h->z_end != h->size)
         return fail(h, ISOMC_ERR_BAD_ARG, "point clouds are extracted on whole-lattice handles (this one is a slab [%u, %u))", h->z_begin, h->z_end);
     int32_t rc = bind_device(h);

@@ -77,10 +77,11 @@ struct ListBufs {
     uint32_t *blkfill;  /* valid entries of each handed-out block */
     uint32_t *ctr;      /* [0] blocks handed out so far (may exceed cap_blocks: the host then grows the list and re-runs) */
     uint32_t cap_blocks;
+    const uint32_t *chunkV, *chunkT; /* batched chunks: output slot of a chunk's first vertex / triangle (ids stay chunk-local); else NULL */
 };
 
 ISOMC_HD uint32_t cell_flags(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) {
-    return (x == 0 ? 1u : 0u) | (y == 0 ? 2u : 0u) | ((g.gz0 + lz) == 0 ? 4u : 0u);
+    return (x == 0 ? 1u : 0u) | (y == 0 ? 2u : 0u) | (geo_z(g, lz) == 0 ? 4u : 0u);
 }
 
 struct EmitArgs {
@@ -118,9 +119,13 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
     const uint32_t row = lz * g.ncx + y;
     const uint32_t em = T.emask[ci];
     const uint32_t vid = A.rowPV[row] + (ea.x & 0xFFFFu);
+    const uint32_t gz = geo_z(g, lz);
+    /* id -> output slot: a slab drops its ghost layer's vertices; batched chunks keep chunk-local ids and add the chunk's base */
+    const uint32_t vbase = L.chunkV ? L.chunkV[lz / g.zper] : 0u - A.ghostV;
+    const uint32_t tbase = L.chunkT ? L.chunkT[lz / g.zper] : 0u - A.ghostT;
     uint32_t owned;
 
-    if (x >= 2 && y >= 2 && g.gz0 + lz >= 2) {
+    if (x >= 2 && y >= 2 && gz >= 2) {
         /* Interior cell whose six possible creators are interior too: every cell involved creates exactly its crossed
          * e5 (y edge), e6 (x edge), e10 (z edge), numbered by rank3[] of its own case.  Which earlier cell created
          * which of my edges (isomc_tables.h owner[0][]):  -x: e7 as e5, e11 as e10;  -y: e4 as e6, e9 as e10;
@@ -175,8 +180,8 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
         if (owned) {
             const float fx0 = hd_mul((float)x, g.inv), fx1 = hd_mul((float)(x + 1), g.inv);
             const float fy0 = hd_mul((float)y, g.inv), fy1 = hd_mul((float)(y + 1), g.inv);
-            const float fz0 = hd_mul((float)(g.gz0 + lz), g.inv), fz1 = hd_mul((float)(g.gz0 + lz + 1), g.inv);
-            const uint64_t s0 = (uint64_t)(vid - A.ghostV);
+            const float fz0 = hd_mul((float)gz, g.inv), fz1 = hd_mul((float)(gz + 1), g.inv);
+            const uint64_t s0 = (uint64_t)(vid + vbase);
             if (o5 && s0 + (r3 & 3u) < A.cap_v) {
                 const float delta = hd_sub(b5, a5), t = (delta == 0.0f) ? 0.5f : hd_div(-a5, delta), omt = hd_sub(1.0f, t);
                 float *o = A.xyz + 3 * (s0 + (r3 & 3u));
@@ -226,7 +231,7 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
      * EDGE_CONNECTION direction, corner coordinates = (i as f32) * inv (primal_grid.rs:50,63-67) */
     for (uint32_t m = owned; m; m &= m - 1) {
         const uint32_t e = hd_ffs0(m);
-        const uint64_t slot = (uint64_t)(eid[e * eid_stride] - A.ghostV);
+        const uint64_t slot = (uint64_t)(eid[e * eid_stride] + vbase);
         if (slot >= A.cap_v) continue;
         const uint32_t en = T.ends[e];
         const uint32_t ux = x + (en & 1u), uy = y + (en >> 1 & 1u), uz = lz + (en >> 2 & 1u);
@@ -236,8 +241,8 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
         const float delta = hd_sub(b, a);
         const float t = (delta == 0.0f) ? 0.5f : hd_div(-a, delta);
         const float omt = hd_sub(1.0f, t);
-        const float pax = hd_mul((float)ux, g.inv), pay = hd_mul((float)uy, g.inv), paz = hd_mul((float)(g.gz0 + uz), g.inv);
-        const float pbx = hd_mul((float)vx, g.inv), pby = hd_mul((float)vy, g.inv), pbz = hd_mul((float)(g.gz0 + vz), g.inv);
+        const float pax = hd_mul((float)ux, g.inv), pay = hd_mul((float)uy, g.inv), paz = hd_mul((float)(gz + (uz - lz)), g.inv);
+        const float pbx = hd_mul((float)vx, g.inv), pby = hd_mul((float)vy, g.inv), pbz = hd_mul((float)(gz + (vz - lz)), g.inv);
         float *o = A.xyz + 3 * slot;
         o[0] = hd_add(hd_mul(pax, omt), hd_mul(pbx, t));
         o[1] = hd_add(hd_mul(pay, omt), hd_mul(pby, t));
@@ -245,7 +250,7 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
     }
 
     /* triangles in table order (march_cube, marching_cubes_impl.rs:106-116) */
-    const uint64_t tslot = (uint64_t)(A.rowPT[row] + L.segtpre[(uint64_t)row * g.nsegx + (x >> 5)] + (ea.x >> 16) - A.ghostT);
+    const uint64_t tslot = (uint64_t)(A.rowPT[row] + L.segtpre[(uint64_t)row * g.nsegx + (x >> 5)] + (ea.x >> 16) + tbase);
     uint32_t nt = T.ntri[ci];
     if (tslot >= A.cap_t) nt = 0;
     else if (tslot + nt > A.cap_t) nt = (uint32_t)(A.cap_t - tslot);
@@ -300,7 +305,7 @@ ISOMC_HD bool classify_segment(const Geo &g, const uint32_t w[8], uint32_t s, ui
     const uint32_t any_in = a0 | an | b0 | bn | c0 | cn | d0 | dn;
     o.act = any_in & ~all_in & vm;
     if (o.act == 0) return false;
-    const bool Z0 = (g.gz0 + lz) == 0, Y0 = y == 0;
+    const bool Z0 = geo_z(g, lz) == 0, Y0 = y == 0;
     const uint32_t x0m = s == 0 ? 1u : 0u;
     uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
     hd_bs_add(p0, p1, p2, p3, (cn ^ dn) & vm);           /* e5: corners 5-6 */
@@ -751,8 +756,9 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
             if (va) {
                 const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40);
                 load_pair(g, signs, row, lz, j, vb, wa, wb);
-                ka = !seg_uniform(wa);
-                kb = vb && !seg_uniform(wb);
+                const bool dead = geo_dead(g, lz); /* (batched chunks: the layer between two lattices has no cells) */
+                ka = !dead && !seg_uniform(wa);
+                kb = !dead && vb && !seg_uniform(wb);
             }
             const uint32_t ma = w_ballot(w, ka), mb = w_ballot(w, kb), rany = (ma | mb) & gmask;
             if (j == 0 && row < row1 && rany == 0) { out.rowV[row] = 0; out.rowT[row] = 0; out.rowA[row] = 0; }
@@ -770,6 +776,7 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
         for (uint32_t task = next_task(w, ticket); task * P < nrow; task = next_task(w, ticket))
         for (uint32_t row = row0 + task * P; row < row1 && row < row0 + (task + 1) * P; ++row) {
             const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40);
+            const bool dead = geo_dead(g, lz);
             bool row_has = false;
             uint32_t last_seq = 0;
             for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 64) {
@@ -779,8 +786,8 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
                 bool ka = false, kb = false;
                 if (va) {
                     load_pair(g, signs, row, lz, j, vb, wa, wb);
-                    ka = !seg_uniform(wa);
-                    kb = vb && !seg_uniform(wb);
+                    ka = !dead && !seg_uniform(wa);
+                    kb = !dead && vb && !seg_uniform(wb);
                 }
                 const uint32_t ma = w_ballot(w, ka), mb = w_ballot(w, kb);
                 if ((ma | mb) == 0) continue;

@@ -82,7 +82,14 @@ struct Geo {
     uint32_t ghost;  /* 1: local cell layer 0 belongs to the previous slab (counted, not emitted) */
     float inv;       /* 1.0f / (float)(N-1)   (primal_grid.rs:44-45) */
     uint64_t row_magic; /* ceil(2^40 / ncx): row / ncx == (row * row_magic) >> 40 for row < 2^26, ncx < 2^13 */
+    uint32_t zper;   /* 0, or (batched chunks) sample layers per chunk = N+1: the handle's layers are B lattices stacked in z;
+                        layer l belongs to chunk l / zper at z = l % zper, and cell layer z = zper-1 (between two chunks) is dead */
+    uint32_t pad_;
 };
+
+/* z of a (cell or sample) layer within its lattice: what the reference's loop variable is (primal_grid.rs:59-67) */
+ISOMC_HD uint32_t geo_z(const Geo &g, uint32_t lz) { return g.zper ? lz % g.zper : g.gz0 + lz; }
+ISOMC_HD bool geo_dead(const Geo &g, uint32_t lz) { return g.zper != 0 && lz % g.zper == g.zper - 1; }
 
 struct SdfProgram {
     isomc_sdf_node nodes[ISOMC_SDF_MAX_NODES];
@@ -361,7 +368,7 @@ struct SdfSrc {
     __device__ __forceinline__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
         /* primal_grid.rs:50,63-67: (i as f32) * one_over_size */
         return sdf_eval(prog, __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv),
-                        __fmul_rn((float)(g.gz0 + lz), g.inv));
+                        __fmul_rn((float)geo_z(g, lz), g.inv));
     }
     ISOMC_SCALAR_EDGE_SAMPLES
 };
@@ -369,7 +376,17 @@ struct SdfChainSrc {
     SdfChain chain;
     __device__ __forceinline__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
         return sdf_chain_eval(chain, __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv),
-                              __fmul_rn((float)(g.gz0 + lz), g.inv));
+                              __fmul_rn((float)geo_z(g, lz), g.inv));
+    }
+    ISOMC_SCALAR_EDGE_SAMPLES
+};
+
+/* batched chunks: B implicit trees, one per stacked lattice (the programs live in global memory; a warp's row is one chunk's) */
+struct SdfBatchSrc {
+    const SdfProgram *progs;
+    __device__ __forceinline__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
+        const uint32_t b = lz / g.zper;
+        return sdf_eval(progs[b], __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv), __fmul_rn((float)(lz - b * g.zper), g.inv));
     }
     ISOMC_SCALAR_EDGE_SAMPLES
 };
@@ -379,7 +396,7 @@ struct SdfChainSrc {
 struct SdfDirSrc {
     SdfProgram prog;
     __device__ __forceinline__ Vec3f vec(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
-        return sdf_eval_vec(prog, __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv), __fmul_rn((float)(g.gz0 + lz), g.inv));
+        return sdf_eval_vec(prog, __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv), __fmul_rn((float)geo_z(g, lz), g.inv));
     }
     /* value for the sign test: positive iff some component is positive (NaN components never are) */
     __device__ __forceinline__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {

@@ -133,9 +133,10 @@ __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t ppl, uint32_t
     if (list_mark && blockIdx.x == 0 && threadIdx.x == 0) *list_mark = *list_ctr; /* list blocks handed out up to this z-chunk */
     __shared__ unsigned long long s_base[2];
     const uint32_t lz = lz_first + blockIdx.x;
-    /* base = sum of the totals of the layers below (<= 4096 values) */
+    /* base = sum of the totals of the layers below (batched chunks: of the layers below in the same lattice, ids are chunk-local) */
+    const uint32_t l_first = g.zper ? lz - lz % g.zper : 0u;
     unsigned long long bv = 0, bt = 0, ba = 0;
-    for (uint32_t l = threadIdx.x; l < lz; l += blockDim.x) {
+    for (uint32_t l = l_first + threadIdx.x; l < lz; l += blockDim.x) {
         bv += layerTot[3 * l];
         bt += layerTot[3 * l + 1];
         ba += layerTot[3 * l + 2];
@@ -169,7 +170,11 @@ __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t ppl, uint32_t
         chunk_end[0] = (uint32_t)(tv + layerTot[3 * lz]);
         chunk_end[1] = (uint32_t)(tt + layerTot[3 * lz + 1]);
     }
-    if (lz == g.ncl - 1 && threadIdx.x == 0) {
+    if (g.zper && lz % g.zper == g.zper - 2 && threadIdx.x == 0) { /* last cell layer of a lattice of the batch: its totals */
+        unsigned long long *ct = totals + 16 + 3 * (size_t)(lz / g.zper);
+        ct[0] = tv + layerTot[3 * lz]; ct[1] = tt + layerTot[3 * lz + 1]; ct[2] = ta + layerTot[3 * lz + 2];
+    }
+    if (lz == g.ncl - 1 && threadIdx.x == 0 && !g.zper) {
         unsigned long long V = tv + layerTot[3 * lz], T = tt + layerTot[3 * lz + 1], A = ta + layerTot[3 * lz + 2];
         unsigned long long gV = g.ghost ? layerTot[0] : 0, gT = g.ghost ? layerTot[1] : 0, gA = g.ghost ? layerTot[2] : 0;
         totals[0] = V; totals[1] = T; totals[2] = A; totals[3] = tv;
@@ -179,6 +184,37 @@ __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t ppl, uint32_t
         totals[12] = (list_ctr && !list_mark) ? list_ctr[1] : 0u; /* tile path: blocks of crossing parameters asked for */
         rowV[(uint64_t)g.ncl * ppl] = (uint32_t)V;
         rowT[(uint64_t)g.ncl * ppl] = (uint32_t)T;
+    }
+}
+
+/* batched chunks: totals[16 + 3b ..] = {V, T, A} of chunk b -> output slot of each chunk's first vertex / triangle (exclusive
+ * prefixes, n + 1 entries each) and the grand totals in the slots finish() reads */
+__global__ void __launch_bounds__(256) k_chunk_bases(uint32_t n, unsigned long long *__restrict__ totals, const uint32_t *__restrict__ list_ctr,
+                                                     uint32_t *__restrict__ chunkV, uint32_t *__restrict__ chunkT) {
+    __shared__ unsigned long long s_w[8];
+    __shared__ unsigned long long s_carry[3];
+    if (threadIdx.x < 3) s_carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < n; b0 += 256) {
+        const uint32_t b = b0 + threadIdx.x;
+        const unsigned long long v = b < n ? totals[16 + 3 * (size_t)b] : 0, t = b < n ? totals[16 + 3 * (size_t)b + 1] : 0,
+                                 a = b < n ? totals[16 + 3 * (size_t)b + 2] : 0;
+        unsigned long long sv, st, sa;
+        const unsigned long long ev = block_excl_scan_256<unsigned long long>(v, s_w, sv);
+        const unsigned long long et = block_excl_scan_256<unsigned long long>(t, s_w, st);
+        block_excl_scan_256<unsigned long long>(a, s_w, sa);
+        if (b < n) { chunkV[b] = (uint32_t)(s_carry[0] + ev); chunkT[b] = (uint32_t)(s_carry[1] + et); }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_carry[0] += sv; s_carry[1] += st; s_carry[2] += sa; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long V = s_carry[0], T = s_carry[1], A = s_carry[2];
+        chunkV[n] = (uint32_t)V; chunkT[n] = (uint32_t)T;
+        totals[0] = V; totals[1] = T; totals[2] = A; totals[3] = 0;
+        totals[4] = 0; totals[5] = 0; totals[6] = 0;
+        totals[7] = list_ctr ? list_ctr[0] : 0u;
+        totals[8] = V; totals[9] = 0; totals[10] = T; totals[11] = A; totals[12] = 0;
     }
 }
 
@@ -298,6 +334,16 @@ cudaError_t isomc_launch_scan(const Geo &g, uint32_t ppl, uint32_t *rowV, uint32
                               unsigned long long *totals, const uint32_t *list_ctr, uint32_t *list_mark, uint32_t *chunk_end,
                               uint32_t lz0, uint32_t lz1, cudaStream_t st) {
     k_scan_rows<<<lz1 - lz0, 256, 0, st>>>(g, ppl, rowV, rowT, layerTot, totals, list_ctr, list_mark, chunk_end, lz0);
+    return cudaGetLastError();
+}
+cudaError_t isomc_launch_chunk_bases(uint32_t n, unsigned long long *totals, const uint32_t *list_ctr, uint32_t *chunkV, uint32_t *chunkT,
+                                     cudaStream_t st) {
+    k_chunk_bases<<<1, 256, 0, st>>>(n, totals, list_ctr, chunkV, chunkT);
+    return cudaGetLastError();
+}
+cudaError_t isomc_launch_sign_sdf_batch(const Geo &g, const SdfProgram *d_progs, uint32_t *signs, uint32_t row0, uint32_t row1, int sms,
+                                        cudaStream_t st) {
+    k_sign<SdfBatchSrc><<<grid_for((uint64_t)(row1 - row0), sms, 8, 8), 256, 0, st>>>(SdfBatchSrc{d_progs}, g, signs, row0, row1);
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,

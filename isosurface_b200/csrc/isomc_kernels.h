@@ -29,6 +29,11 @@ cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, bool dir
 cudaError_t isomc_launch_scan(const Geo &g, uint32_t ppl, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
                               unsigned long long *totals, const uint32_t *list_ctr, uint32_t *list_mark, uint32_t *chunk_end,
                               uint32_t lz0, uint32_t lz1, cudaStream_t st);
+/* batched chunks (Geo.zper != 0): per-chunk programs in device memory; chunk totals -> output bases */
+cudaError_t isomc_launch_sign_sdf_batch(const Geo &g, const SdfProgram *d_progs, uint32_t *signs, uint32_t row0, uint32_t row1, int sms,
+                                        cudaStream_t st);
+cudaError_t isomc_launch_chunk_bases(uint32_t n, unsigned long long *totals, const uint32_t *list_ctr, uint32_t *chunkV, uint32_t *chunkT,
+                                     cudaStream_t st);
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,
                                     unsigned long long *ofs64, cudaStream_t st);
 cudaError_t isomc_launch_cube_indices(const Geo &g, const uint32_t *signs, const McTables *tabs, uint8_t *out, int sms,
@@ -47,6 +52,10 @@ cudaError_t isomc_launch_emit_list_grid(const Geo &g, const float *d_grid, const
                                         const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                         const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
                                         const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st);
+cudaError_t isomc_launch_emit_list_sdf_batch(const Geo &g, const SdfProgram *d_progs, const ListBufs &L, const EmitTab *tab,
+                                             const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
+                                             const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
+                                             const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st);
 cudaError_t isomc_launch_emit_list_sdf(const Geo &g, const SdfProgram &prog, bool directed, const ListBufs &L, const EmitTab *tab,
                                        const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                        const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,

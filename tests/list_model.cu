@@ -169,7 +169,7 @@ extern "C" {
  */
 static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const float *slab, const SdfProgram *directed,
                          uint32_t n_warps, uint32_t seed, uint32_t vofs, uint32_t cap_blocks, float *xyz, uint64_t cap_v, uint32_t *idx,
-                         uint64_t cap_t, uint64_t *out_totals) {
+                         uint64_t cap_t, uint64_t *out_totals, uint32_t batch = 0, uint64_t *chunk_v = nullptr, uint64_t *chunk_t = nullptr) {
     Geo g;
     g.N = size; g.ncx = size - 1;
     g.nsegx = (g.ncx + 31) / 32; g.nws = (g.nsegx + 2) & ~1u;
@@ -179,6 +179,12 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
     g.nsl = g.ncl + 1;
     g.inv = 1.0f / (float)(size - 1);
     g.row_magic = g.ncx ? ((1ull << 40) + g.ncx - 1) / g.ncx : 0;
+    g.zper = 0; g.pad_ = 0;
+    if (batch) { /* `batch` whole lattices stacked in z (isomc_batch_create): the cell layer between two of them is dead */
+        g.zper = size + 1;
+        g.ncl = batch * (size + 1) - 1;
+        g.nsl = g.ncl + 1;
+    }
     memset(out_totals, 0, 6 * sizeof(uint64_t));
     if (g.ncl == 0) return 0;
 
@@ -206,7 +212,7 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
     memset(ent.data(), 0xEE, ent.size() * sizeof(uint2));
     memset(segrec.data(), 0xEE, segrec.size() * sizeof(uint2));
     uint32_t ctr = 0;
-    ListBufs L{ent.data(), ent_yz.data(), segrec.data(), segtpre.data(), blkfill.data(), &ctr, cap_blocks};
+    ListBufs L{ent.data(), ent_yz.data(), segrec.data(), segtpre.data(), blkfill.data(), &ctr, cap_blocks, nullptr, nullptr};
     std::vector<uint32_t> rowV(nrows_c + 4, 0xDEADBEEFu), rowT(nrows_c + 4, 0xDEADBEEFu), rowA(nrows_c + 4, 0xDEADBEEFu);
     std::vector<unsigned long long> layerTot((size_t)g.ncl * 3 + 4, 0ull);
     CountOut out{rowV.data(), rowT.data(), rowA.data(), layerTot.data()};
@@ -245,9 +251,14 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
     }
 
     /* k_scan_rows restated */
-    std::vector<uint32_t> rowPV(nrows_c + 1), rowPT(nrows_c + 1);
-    uint64_t V = 0, T = 0, Act = 0;
+    std::vector<uint32_t> rowPV(nrows_c + 1), rowPT(nrows_c + 1), chunkV(batch + 1, 0u), chunkT(batch + 1, 0u);
+    uint64_t V = 0, T = 0, Act = 0, Vb = 0, Tb = 0;
     for (uint64_t r = 0; r < nrows_c; ++r) {
+        if (batch && r % ((uint64_t)g.zper * g.ncx) == 0) { /* a new lattice: ids are chunk-local (k_scan_rows), bases as k_chunk_bases */
+            Vb += V; Tb += T;
+            chunkV[r / ((uint64_t)g.zper * g.ncx)] = (uint32_t)Vb; chunkT[r / ((uint64_t)g.zper * g.ncx)] = (uint32_t)Tb;
+            V = 0; T = 0;
+        }
         rowPV[r] = (uint32_t)V; rowPT[r] = (uint32_t)T;
         if (rowV[r] == 0xDEADBEEFu || rowT[r] == 0xDEADBEEFu || rowA[r] == 0xDEADBEEFu) {
             fprintf(stderr, "list_model: row %llu totals not written (V %x T %x A %x)\n", (unsigned long long)r, rowV[r], rowT[r], rowA[r]);
@@ -256,6 +267,12 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
         V += rowV[r]; T += rowT[r]; Act += rowA[r];
     }
     rowPV[nrows_c] = (uint32_t)V; rowPT[nrows_c] = (uint32_t)T;
+    if (batch) {
+        chunkV[batch] = (uint32_t)(Vb + V); chunkT[batch] = (uint32_t)(Tb + T);
+        for (uint32_t b = 0; b <= batch; ++b) { chunk_v[b] = chunkV[b]; chunk_t[b] = chunkT[b]; }
+        L.chunkV = chunkV.data(); L.chunkT = chunkT.data();
+        V += Vb; T += Tb;
+    }
     /* layer totals must agree with the row totals */
     for (uint32_t l = 0; l < g.ncl; ++l) {
         uint64_t sv = 0, stt = 0, sa = 0;
@@ -267,7 +284,7 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
     }
     const uint64_t gV = g.ghost ? layerTot[0] : 0, gT = g.ghost ? layerTot[1] : 0, gA = g.ghost ? layerTot[2] : 0;
     out_totals[0] = V - gV;
-    out_totals[1] = rowPV[(uint64_t)(g.ncl - 1) * g.ncx] - gV;
+    out_totals[1] = batch ? 0 : rowPV[(uint64_t)(g.ncl - 1) * g.ncx] - gV;
     out_totals[2] = T - gT;
     out_totals[3] = Act - gA;
     out_totals[4] = ctr;
@@ -303,6 +320,15 @@ int list_model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const fl
                        uint32_t vofs, uint32_t cap_blocks, float *xyz, uint64_t cap_v, uint32_t *idx, uint64_t cap_t,
                        uint64_t *out_totals) {
     return model_extract(size, z_begin, z_end, slab, nullptr, n_warps, seed, vofs, cap_blocks, xyz, cap_v, idx, cap_t, out_totals);
+}
+
+/* isomc_extract_sdf_batch: `batch` lattices (size^2 x (size+1) samples each, back to back) through one count / scan / emit;
+ * chunk b's vertices are [chunk_v[b], chunk_v[b+1]), its triangles [chunk_t[b], chunk_t[b+1]), its indices chunk-local */
+int list_model_extract_batch(uint32_t size, uint32_t batch, const float *lattices, uint32_t n_warps, uint32_t seed, uint32_t cap_blocks,
+                             float *xyz, uint64_t cap_v, uint32_t *idx, uint64_t cap_t, uint64_t *out_totals, uint64_t *chunk_v,
+                             uint64_t *chunk_t) {
+    return model_extract(size, 0, size, lattices, nullptr, n_warps, seed, 0, cap_blocks, xyz, cap_v, idx, cap_t, out_totals, batch, chunk_v,
+                         chunk_t);
 }
 
 /* MarchingCubes<Directed> over an implicit tree (whole lattice): the list kernels' source with the Directed host source */

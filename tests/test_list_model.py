@@ -193,3 +193,29 @@ def test_model_directed_extract_matches_oracle(model, oracle, name, size):
                                            tot.ctypes.data)
     assert rc == 0 and int(tot[3]) == oact
     assert mesh_diff(xyz[:3 * int(tot[0])], idx[:3 * int(tot[2])], oxyz, oidx) == ""
+
+
+@pytest.mark.parametrize("size,batch,n_warps", [(9, 3, 3), (33, 4, 5), (40, 2, 7), (66, 2, 4)])
+def test_model_batched_chunks_equal_single_extracts(model, oracle, size, batch, n_warps):
+    """isomc_extract_sdf_batch layout: `batch` lattices stacked in z, one count / scan / emit, chunk-local ids; every chunk must be
+    byte for byte what the oracle returns for that lattice alone (the dead cell layer between two lattices contributes nothing)"""
+    model.list_model_extract_batch.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                               C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    names = ["sphere03", "torus", "csgA", "sphere05_origin"]
+    grids = [oracle.fill_grid_sdf(size, oracle_prog(names[b % 4])) if b % 2 == 0 else noise(size, 100 + b) for b in range(batch)]
+    grids[-1] = np.full_like(grids[0], 1.0)  # an empty chunk at the end
+    stacked = np.ascontiguousarray(np.concatenate([g.reshape(size + 1, size, size) for g in grids]), dtype=np.float32)
+    cap_v = cap_t = 4 * stacked.size
+    xyz = np.full(3 * cap_v, np.nan, np.float32)
+    idx = np.full(3 * cap_t, 0xFFFFFFFF, np.uint32)
+    tot = np.zeros(6, np.uint64)
+    cv, ct = np.zeros(batch + 1, np.uint64), np.zeros(batch + 1, np.uint64)
+    rc = model.list_model_extract_batch(size, batch, stacked.ctypes.data, n_warps, 3, 1 << 14, xyz.ctypes.data, cap_v, idx.ctypes.data,
+                                        cap_t, tot.ctypes.data, cv.ctypes.data, ct.ctypes.data)
+    assert rc == 0
+    for b in range(batch):
+        oxyz, oidx, _ = oracle.extract_grid(size, grids[b])
+        v0, v1, t0, t1 = int(cv[b]), int(cv[b + 1]), int(ct[b]), int(ct[b + 1])
+        assert (v1 - v0, t1 - t0) == (len(oxyz) // 3, len(oidx) // 3), "chunk %d counts" % b
+        assert mesh_diff(xyz[3 * v0:3 * v1], idx[3 * t0:3 * t1], oxyz, oidx) == "", "chunk %d" % b
+    assert int(tot[0]) == int(cv[batch]) and int(tot[2]) == int(ct[batch])
