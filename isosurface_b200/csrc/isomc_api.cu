@@ -63,6 +63,15 @@ struct isomc {
     ListBufs L{};
     uint32_t *list_marks = nullptr; /* [c] = list blocks handed out before z-chunk c; [0] = 0 */
     EmitTab *etab = nullptr;
+    /* stage pipeline of a device-resident extract (pipe_plan): sign words of z-chunk c+2, counting of c+1 and emission of c run
+     * on three streams in CTA-limited grids, so that the HBM-bound stage shares the SMs with the two issue-bound ones */
+    cudaStream_t s_sign = nullptr, s_emit = nullptr;
+    cudaEvent_t ev_pipe0 = nullptr, ev_pipe1 = nullptr, ev_sign[MAX_CHUNKS] = {}, ev_cnt2[MAX_CHUNKS] = {};
+    /* the pipelined sequence (4 launches and 5 event operations per z-chunk) is captured once into a CUDA graph and replayed
+     * while everything a kernel takes by value stays the same (pipe_key: pointers, capacities, plan) */
+    cudaGraphExec_t pipe_exec = nullptr;
+    uint64_t pipe_key[12] = {};
+    uint32_t pipe_launches = 0;
     /* streamed host-to-host extract (isomc_extract_grid_host_to): copy-in / copy-out streams, per-chunk events */
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_cnt[MAX_CHUNKS] = {}, ev_emit[MAX_CHUNKS] = {};
@@ -224,7 +233,7 @@ void tl_mark(isomc *h, const char *name, uint32_t c, cudaStream_t st) {
     h->tl.emplace_back(std::string(name) + "(" + std::to_string(c) + ")", e);
 }
 
-int32_t launch_emit_chunk(isomc *h, uint32_t c, cudaStream_t st) {
+int32_t launch_emit_chunk(isomc *h, uint32_t c, cudaStream_t st, int bps = 0) {
     const Geo &g = h->g;
     const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
     if (h->tile_mode) {
@@ -237,19 +246,34 @@ int32_t launch_emit_chunk(isomc *h, uint32_t c, cudaStream_t st) {
     /* one kernel: edge ids, vertex positions and triangles of the chunk's active cells */
     if (h->kind == SRC_SDF_BATCH)
         CU(h, isomc_launch_emit_list_sdf_batch(g, h->d_progs, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
-                                               h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
+                                               h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st, bps));
     else if (h->kind == SRC_GRID)
         CU(h, isomc_launch_emit_list_grid(g, h->d_grid, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
-                                          h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
+                                          h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st, bps));
     else
         CU(h, isomc_launch_emit_list_sdf(g, h->prog, h->directed, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
-                                         h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st));
+                                         h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st, bps));
+    h->stats.kernel_launches += 1;
+    return ISOMC_OK;
+}
+
+/* CTAs per SM of the three stages while they share the SMs (pipelined extract); 0 = the stage has the GPU to itself */
+struct StageGrids { int sign = 0, count = 0, emit = 0; };
+
+/* sign words of the sample rows z-chunk c adds (list path) */
+int32_t launch_sign_chunk(isomc *h, uint32_t c, cudaStream_t st, int bps = 0) {
+    const Geo &g = h->g;
+    const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
+    const uint32_t row0 = (c == 0 ? 0u : l0 + 1) * g.N, row1 = (l1 + 1) * g.N;
+    if (h->kind == SRC_SDF_BATCH) CU(h, isomc_launch_sign_sdf_batch(g, h->d_progs, h->signs, row0, row1, h->sms, st));
+    else if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, row0, row1, h->sms, bps ? bps : 8, st));
+    else CU(h, isomc_launch_sign_sdf(g, h->prog, h->directed, h->signs, row0, row1, h->sms, bps ? bps : 8, st));
     h->stats.kernel_launches += 1;
     return ISOMC_OK;
 }
 
 /* counting stage of z-chunk c (cell layers [l0, l1)) + the row scan; tile path: one kernel reads the samples once */
-int32_t launch_count_chunk(isomc *h, uint32_t c, cudaStream_t st, uint32_t *chunk_end) {
+int32_t launch_count_chunk(isomc *h, uint32_t c, cudaStream_t st, uint32_t *chunk_end, bool with_sign = true, int bps = 0) {
     const Geo &g = h->g;
     const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
     if (h->tile_mode) {
@@ -263,12 +287,12 @@ int32_t launch_count_chunk(isomc *h, uint32_t c, cudaStream_t st, uint32_t *chun
         h->stats.kernel_launches += 2;
         return ISOMC_OK;
     }
-    const uint32_t row0 = (c == 0 ? 0u : l0 + 1) * g.N, row1 = (l1 + 1) * g.N;
-    if (h->kind == SRC_SDF_BATCH) CU(h, isomc_launch_sign_sdf_batch(g, h->d_progs, h->signs, row0, row1, h->sms, st));
-    else if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, row0, row1, h->sms, 8, st));
-    else CU(h, isomc_launch_sign_sdf(g, h->prog, h->directed, h->signs, row0, row1, h->sms, 8, st));
+    if (with_sign) {
+        int32_t rc = launch_sign_chunk(h, c, st);
+        if (rc) return rc;
+    }
     if (h->profiling) CU(h, cudaEventRecord(h->ev[1], st));
-    CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, h->ticket + c, l0, l1, h->sms, st));
+    CU(h, isomc_launch_count_list(g, h->signs, h->tabs, h->L, h->rowV, h->rowT, h->rowA, h->layerTot, h->ticket + c, l0, l1, h->sms, st, bps));
     if (h->profiling) CU(h, cudaEventRecord(h->ev[2], st));
     CU(h, isomc_launch_scan(g, g.ncx, h->rowV, h->rowT, h->layerTot, h->totals, h->L.ctr, h->list_marks + c + 1, chunk_end, l0, l1, st));
     if (h->batch) { /* per-lattice totals -> output bases, grand totals */
@@ -276,7 +300,122 @@ int32_t launch_count_chunk(isomc *h, uint32_t c, cudaStream_t st, uint32_t *chun
         h->stats.kernel_launches += 1;
     }
     if (h->profiling) CU(h, cudaEventRecord(h->ev[3], st));
-    h->stats.kernel_launches += 3;
+    h->stats.kernel_launches += 2;
+    return ISOMC_OK;
+}
+
+/*
+ * Stage pipeline of a device-resident extract.  The three stages are bound by different things -- k_sign by HBM, k_count_list and
+ * k_emit_list by instruction issue and load latency -- and each of them alone leaves the other resource idle.  The lattice is cut
+ * into z-chunks (the row scan is causal in z, so a chunk can be emitted as soon as it is counted) and the stages run as
+ *
+ *   s_sign : sign(0) sign(1) sign(2) ...
+ *   stream :         count+scan(0) count+scan(1) ...
+ *   s_emit :                       emit(0)       emit(1) ...
+ *
+ * in grids of `sign` / `count` / `emit` CTAs per SM, chosen so that CTAs of all three are resident on every SM at once.
+ * ISOMC_PIPE="chunks,sign,count,emit" overrides the plan ("0" = off).
+ */
+struct PipePlan { uint32_t chunks = 1; StageGrids sg; };
+
+PipePlan pipe_plan(const isomc *h, bool emit_inline) {
+    PipePlan p;
+    const Geo &g = h->g;
+    if (!emit_inline || h->tile_mode || h->batch || h->profiling || h->timeline || g.ncl < 64) return p;
+    /* OFF unless asked for: measured slower than the serial order in every configuration tried (fbm512: serial 0.54 ms; 2 chunks
+     * 0.56-0.75 ms, 4 chunks 0.63, 8 chunks 0.66-0.77 with the CUDA graph, 0.97 without).  Each stage needs all the warps an SM
+     * holds to hide its own load latency, and per-chunk launches of k_count_list / k_emit_list quantise badly (profiles/r02_history.md) */
+    int v[4] = {0, 2, 2, 3};
+    const char *e = getenv("ISOMC_PIPE");
+    if (!e) return p;
+    if (sscanf(e, "%d%*c%d%*c%d%*c%d", &v[0], &v[1], &v[2], &v[3]) < 1 || v[0] < 2) return p; /* "8x2x2x3" (any separator) */
+    p.chunks = (uint32_t)v[0] > (uint32_t)MAX_CHUNKS ? (uint32_t)MAX_CHUNKS : (uint32_t)v[0];
+    if (p.chunks > g.ncl / 8) p.chunks = g.ncl / 8;
+    p.sg.sign = v[1]; p.sg.count = v[2]; p.sg.emit = v[3];
+    return p;
+}
+
+int32_t pipelined_launches(isomc *h, const PipePlan &pp);
+
+int32_t enqueue_pipelined(isomc *h, const PipePlan &pp) {
+    static const bool use_graph = !(getenv("ISOMC_GRAPH") && atoi(getenv("ISOMC_GRAPH")) == 0);
+    if (!use_graph || h->kind != SRC_GRID) return pipelined_launches(h, pp);
+    const uint64_t key[12] = {(uint64_t)(uintptr_t)h->d_grid, (uint64_t)(uintptr_t)h->xyz, (uint64_t)(uintptr_t)h->idx, h->cap_v, h->cap_t,
+                              (uint64_t)(uintptr_t)h->L.ent, h->L.cap_blocks, pp.chunks,
+                              (uint64_t)pp.sg.sign << 32 | (uint64_t)pp.sg.count << 16 | (uint64_t)pp.sg.emit,
+                              (uint64_t)(uintptr_t)h->stream, (uint64_t)(uintptr_t)h->signs, 1};
+    if (h->pipe_exec && memcmp(key, h->pipe_key, sizeof key) == 0) {
+        CU(h, cudaGraphLaunch(h->pipe_exec, h->stream));
+        h->stats.kernel_launches = h->pipe_launches;
+        h->counted = true; h->emitted = true;
+        return ISOMC_OK;
+    }
+    if (h->pipe_exec) { cudaGraphExecDestroy(h->pipe_exec); h->pipe_exec = nullptr; }
+    if (!h->s_sign) { /* (streams and events are created outside the capture) */
+        int32_t rc0 = pipelined_launches(h, pp);
+        return rc0;
+    }
+    CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int32_t rc = pipelined_launches(h, pp);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(h, ISOMC_ERR_CUDA, "stream capture of the pipelined extract failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->pipe_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { h->pipe_exec = nullptr; return fail(h, ISOMC_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    memcpy(h->pipe_key, key, sizeof key);
+    h->pipe_launches = h->stats.kernel_launches;
+    CU(h, cudaGraphLaunch(h->pipe_exec, h->stream));
+    return ISOMC_OK;
+}
+
+int32_t pipelined_launches(isomc *h, const PipePlan &pp) {
+    const Geo &g = h->g;
+    if (!h->s_sign) {
+        CU(h, cudaStreamCreateWithFlags(&h->s_sign, cudaStreamNonBlocking));
+        CU(h, cudaStreamCreateWithFlags(&h->s_emit, cudaStreamNonBlocking));
+        CU(h, cudaEventCreateWithFlags(&h->ev_pipe0, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&h->ev_pipe1, cudaEventDisableTiming));
+        for (int c = 0; c < MAX_CHUNKS; ++c) {
+            CU(h, cudaEventCreateWithFlags(&h->ev_sign[c], cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&h->ev_cnt2[c], cudaEventDisableTiming));
+        }
+    }
+    const uint32_t per = (g.ncl + pp.chunks - 1) / pp.chunks;
+    const uint32_t n = (g.ncl + per - 1) / per;
+    h->n_chunks = n;
+    for (uint32_t c = 0; c <= n; ++c) h->chunk_l[c] = c * per < g.ncl ? c * per : g.ncl;
+    CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t), h->stream));
+    CU(h, cudaEventRecord(h->ev_pipe0, h->stream));
+    CU(h, cudaStreamWaitEvent(h->s_sign, h->ev_pipe0, 0));
+    CU(h, cudaStreamWaitEvent(h->s_emit, h->ev_pipe0, 0));
+    int32_t rc;
+    /* launch order = the order in which the hardware queues may start the kernels: keep the stages interleaved */
+    for (uint32_t step = 0; step < n + 2; ++step) {
+        if (step < n) {
+            rc = launch_sign_chunk(h, step, h->s_sign, pp.sg.sign);
+            if (rc) return rc;
+            CU(h, cudaEventRecord(h->ev_sign[step], h->s_sign));
+        }
+        if (step >= 1 && step - 1 < n) {
+            const uint32_t c = step - 1;
+            CU(h, cudaStreamWaitEvent(h->stream, h->ev_sign[c], 0));
+            rc = launch_count_chunk(h, c, h->stream, nullptr, false, pp.sg.count);
+            if (rc) return rc;
+            CU(h, cudaEventRecord(h->ev_cnt2[c], h->stream));
+        }
+        if (step >= 2) {
+            const uint32_t c = step - 2;
+            CU(h, cudaStreamWaitEvent(h->s_emit, h->ev_cnt2[c], 0));
+            rc = launch_emit_chunk(h, c, h->s_emit, pp.sg.emit);
+            if (rc) return rc;
+        }
+    }
+    CU(h, cudaEventRecord(h->ev_pipe1, h->s_emit));
+    CU(h, cudaStreamWaitEvent(h->stream, h->ev_pipe1, 0));
+    h->counted = true;
+    h->emitted = true;
     return ISOMC_OK;
 }
 
@@ -292,8 +431,9 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
         h->emitted = emit_inline;
         return ISOMC_OK;
     }
-    /* one chunk: the z-chunked forms are the streamed host extract and (measured slower, profiles/r01_history.md) a two-stream
-     * producer / consumer pipeline that round 1 carried; the tile path reads the samples once, so there is nothing to overlap */
+    const PipePlan pp = pipe_plan(h, emit_inline);
+    if (pp.chunks > 1) return enqueue_pipelined(h, pp);
+    /* one chunk, one stream, every stage with the GPU to itself (per-kernel profiling, small lattices, the tile path) */
     h->n_chunks = 1;
     h->chunk_l[0] = 0; h->chunk_l[1] = g.ncl;
     if (h->profiling) CU(h, cudaEventRecord(h->ev[0], h->stream));
@@ -316,7 +456,7 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
 int32_t enqueue_emit(isomc *h) {
     const Geo &g = h->g;
     if (g.ncl == 0 || g.ncx == 0) { h->emitted = true; return ISOMC_OK; }
-    CU(h, cudaMemsetAsync(h->tile_mode ? h->tile_tickets + MAX_CHUNKS : h->ticket, 0, MAX_CHUNKS * sizeof(uint32_t), h->stream));
+    CU(h, cudaMemsetAsync(h->tile_tickets + MAX_CHUNKS, 0, MAX_CHUNKS * sizeof(uint32_t), h->stream)); /* emit tickets */
     for (uint32_t c = 0; c < h->n_chunks; ++c) {
         int32_t rc = launch_emit_chunk(h, c, h->stream);
         if (rc) return rc;
@@ -540,6 +680,13 @@ int32_t isomc_destroy(isomc_t *h) {
     if (!h) return ISOMC_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->pipe_exec) cudaGraphExecDestroy(h->pipe_exec);
+    if (h->s_sign) {
+        cudaStreamSynchronize(h->s_sign); cudaStreamSynchronize(h->s_emit);
+        cudaStreamDestroy(h->s_sign); cudaStreamDestroy(h->s_emit);
+        cudaEventDestroy(h->ev_pipe0); cudaEventDestroy(h->ev_pipe1);
+        for (int c = 0; c < MAX_CHUNKS; ++c) { cudaEventDestroy(h->ev_sign[c]); cudaEventDestroy(h->ev_cnt2[c]); }
+    }
     cudaFree(h->d_progs); cudaFree(h->chunkV); cudaFree(h->chunkT);
     if (h->h_progs) cudaFreeHost(h->h_progs);
     if (h->h_chunk) cudaFreeHost(h->h_chunk);

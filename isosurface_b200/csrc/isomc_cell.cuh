@@ -123,6 +123,9 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
     /* id -> output slot: a slab drops its ghost layer's vertices; batched chunks keep chunk-local ids and add the chunk's base */
     const uint32_t vbase = L.chunkV ? L.chunkV[lz / g.zper] : 0u - A.ghostV;
     const uint32_t tbase = L.chunkT ? L.chunkT[lz / g.zper] : 0u - A.ghostT;
+    /* slot of the cell's first triangle: requested here, with the first wave of loads (the compiler will not move these loads
+     * up across the vertex stores below by itself) */
+    const uint32_t tslot32 = A.rowPT[row] + L.segtpre[(uint64_t)row * g.nsegx + (x >> 5)] + (ea.x >> 16) + tbase;
     uint32_t owned;
 
     if (x >= 2 && y >= 2 && gz >= 2) {
@@ -250,7 +253,7 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
     }
 
     /* triangles in table order (march_cube, marching_cubes_impl.rs:106-116) */
-    const uint64_t tslot = (uint64_t)(A.rowPT[row] + L.segtpre[(uint64_t)row * g.nsegx + (x >> 5)] + (ea.x >> 16) + tbase);
+    const uint64_t tslot = (uint64_t)tslot32;
     uint32_t nt = T.ntri[ci];
     if (tslot >= A.cap_t) nt = 0;
     else if (tslot + nt > A.cap_t) nt = (uint32_t)(A.cap_t - tslot);
@@ -716,8 +719,13 @@ ISOMC_HD void pair_enqueue(const Warp &w, SegQueue &Q, CountState &S, uint32_t m
 #ifndef ISOMC_COUNT_LONG_TASK_AT
 #define ISOMC_COUNT_LONG_TASK_AT (1u << 20) /* (the host model is also built with a small value to cover the long-task branch) */
 #endif
-ISOMC_HD uint32_t count_task_passes(uint32_t n_passes) { /* short tasks balance small lattices, long ones amortise the ticket */
-    return n_passes > ISOMC_COUNT_LONG_TASK_AT ? 64u : 8u;
+/* Passes per ticket.  Long tasks amortise the ticket round trip on very large lattices (and keep neighbouring rows adjacent in
+ * the list); otherwise at most 8, and few enough that every warp draws about five tasks: with 8 passes a 512^3 lattice gave each
+ * warp 1.7 tasks and the last round ran half empty (k_count_list 0.134 -> 0.120 ms with 3) */
+ISOMC_HD uint32_t count_task_passes(uint32_t n_passes, uint32_t n_warps) {
+    if (n_passes > ISOMC_COUNT_LONG_TASK_AT) return 64u;
+    const uint32_t p = n_passes / (5u * (n_warps ? n_warps : 1u));
+    return p < 1u ? 1u : p > 8u ? 8u : p;
 }
 
 ISOMC_HD uint32_t next_task(const Warp &w, uint32_t *ticket) {
@@ -737,7 +745,7 @@ ISOMC_HD uint32_t next_task(const Warp &w, uint32_t *ticket) {
 template <bool WIDE>
 ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs, const uint8_t *s_ntri, const uint8_t *nth8,
                               const ListBufs &L, const CountOut &out, uint32_t gshift, uint32_t row0, uint32_t row1, uint32_t *ticket,
-                              SegQueue &Q) {
+                              SegQueue &Q, uint32_t n_warps, uint32_t task_passes = 0 /* 0: count_task_passes() */) {
     const uint32_t lane = w.lane;
     CountState S;
     S.enq = S.deq = 0;
@@ -746,7 +754,7 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
     if (!WIDE) {
         const uint32_t G = 1u << gshift, rpw = 32u >> gshift, sub = lane >> gshift, j = lane & (G - 1);
         const uint32_t gmask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << (sub << gshift);
-        const uint32_t niter = (row1 - row0 + rpw - 1) / rpw, P = count_task_passes(niter);
+        const uint32_t niter = (row1 - row0 + rpw - 1) / rpw, P = task_passes ? task_passes : count_task_passes(niter, n_warps);
         for (uint32_t task = next_task(w, ticket); task * P < niter; task = next_task(w, ticket))
         for (uint32_t it = task * P; it < niter && it < (task + 1) * P; ++it) {
             const uint32_t row = row0 + it * rpw + sub;
@@ -772,7 +780,7 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
             while (S.enq - S.deq >= 32) count_flush(w, g, s_ntri, nth8, L, out, Q, S, 32);
         }
     } else {
-        const uint32_t nrow = row1 - row0, P = count_task_passes(nrow);
+        const uint32_t nrow = row1 - row0, P = task_passes ? task_passes : count_task_passes(nrow, n_warps);
         for (uint32_t task = next_task(w, ticket); task * P < nrow; task = next_task(w, ticket))
         for (uint32_t row = row0 + task * P; row < row1 && row < row0 + (task + 1) * P; ++row) {
             const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40);

@@ -18,6 +18,7 @@
 
 #include "isomc_device.cuh"
 #include "isomc_kernels.h"
+#include "isomc_launch.cuh"
 #include "isomc_tables.h"
 
 /* ------------------------------------------------------------------------------------------ */
@@ -28,6 +29,7 @@
 template <class Src>
 __global__ void __launch_bounds__(256) k_sign(Src src, Geo g, uint32_t *__restrict__ signs, uint32_t row0, uint32_t row1) {
     constexpr int U = 8;
+    isomc_pdl_trigger();
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
     for (uint32_t row = row0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < row1; row += nwarps) {
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(256) k_sign(Src src, Geo g, uint32_t *__restri
 template <int U>
 __global__ void __launch_bounds__(256) k_sign_vec4(const float4 *__restrict__ grid4, Geo g, uint32_t *__restrict__ signs,
                                                    uint32_t row0, uint32_t row1) {
+    isomc_pdl_trigger();
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
     const uint32_t n4 = g.N >> 2;            /* float4 per sample row */
@@ -130,6 +133,8 @@ __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t ppl, uint32_t
                                                    const uint32_t *__restrict__ list_ctr, uint32_t *__restrict__ list_mark,
                                                    uint32_t *__restrict__ chunk_end, uint32_t lz_first) {
     __shared__ unsigned long long s_w[8];
+    isomc_pdl_trigger();
+    isomc_pdl_wait(); /* row counts, layer totals and the list counter come from the counting kernel */
     if (list_mark && blockIdx.x == 0 && threadIdx.x == 0) *list_mark = *list_ctr; /* list blocks handed out up to this z-chunk */
     __shared__ unsigned long long s_base[2];
     const uint32_t lz = lz_first + blockIdx.x;
@@ -333,8 +338,7 @@ cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, bool dir
 cudaError_t isomc_launch_scan(const Geo &g, uint32_t ppl, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
                               unsigned long long *totals, const uint32_t *list_ctr, uint32_t *list_mark, uint32_t *chunk_end,
                               uint32_t lz0, uint32_t lz1, cudaStream_t st) {
-    k_scan_rows<<<lz1 - lz0, 256, 0, st>>>(g, ppl, rowV, rowT, layerTot, totals, list_ctr, list_mark, chunk_end, lz0);
-    return cudaGetLastError();
+    return isomc_launch(k_scan_rows, lz1 - lz0, 256, st, true, g, ppl, rowV, rowT, layerTot, totals, list_ctr, list_mark, chunk_end, lz0);
 }
 cudaError_t isomc_launch_chunk_bases(uint32_t n, unsigned long long *totals, const uint32_t *list_ctr, uint32_t *chunkV, uint32_t *chunkT,
                                      cudaStream_t st) {

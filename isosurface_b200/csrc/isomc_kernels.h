@@ -46,20 +46,21 @@ cudaError_t isomc_launch_synth(const SynthParams &sp, uint32_t size, uint32_t z_
 uint32_t isomc_count_list_max_warps(int sms);
 cudaError_t isomc_launch_count_list(const Geo &g, const uint32_t *signs, const McTables *tabs, const ListBufs &L, uint32_t *rowV,
                                     uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot, uint32_t *ticket /* zeroed */,
-                                    uint32_t lz0, uint32_t lz1, int sms, cudaStream_t st);
-/* list blocks [*blk_first, *blk_end) (device pointers; blk_first == NULL: from block 0) */
+                                    uint32_t lz0, uint32_t lz1, int sms, cudaStream_t st, int grid_bps = 0);
+/* list blocks [*blk_first, *blk_end) (device pointers; blk_first == NULL: from block 0).
+ * grid_bps: CTAs per SM to launch when the stage shares the SMs with others (0 = as many as fit) */
 cudaError_t isomc_launch_emit_list_grid(const Geo &g, const float *d_grid, const ListBufs &L, const EmitTab *tab,
                                         const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                         const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
-                                        const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st);
+                                        const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st, int grid_bps = 0);
 cudaError_t isomc_launch_emit_list_sdf_batch(const Geo &g, const SdfProgram *d_progs, const ListBufs &L, const EmitTab *tab,
                                              const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                              const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
-                                             const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st);
+                                             const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st, int grid_bps = 0);
 cudaError_t isomc_launch_emit_list_sdf(const Geo &g, const SdfProgram &prog, bool directed, const ListBufs &L, const EmitTab *tab,
                                        const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                        const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
-                                       const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st);
+                                       const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st, int grid_bps = 0);
 
 /* tile path (isomc_tile_kernels.cu): pass 1 = samples -> entries, crossing parameters, per-piece counts over cell layers
  * [lz0, lz1); pass 2 = entries -> mesh.  ticket: a zeroed u32 per launch */

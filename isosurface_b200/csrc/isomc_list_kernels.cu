@@ -22,6 +22,7 @@
 
 #include "isomc_cell.cuh"
 #include "isomc_kernels.h"
+#include "isomc_launch.cuh"
 
 namespace {
 
@@ -29,18 +30,22 @@ namespace {
 template <bool WIDE, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_count_list(Geo g, const uint32_t *__restrict__ signs, const uint8_t *__restrict__ ntri_g,
                                                     ListBufs L, CountOut out, uint32_t gshift, uint32_t row0, uint32_t row1,
-                                                    uint32_t *ticket) {
+                                                    uint32_t *ticket, uint32_t task_passes) {
     __shared__ uint8_t s_ntri[256];
     __shared__ SegQueue s_q[8];
     __shared__ uint8_t s_nth8[256 * 8];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_ntri[i] = ntri_g[i]; nth8_fill(s_nth8, (uint32_t)i); }
+    isomc_pdl_trigger();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_ntri[i] = ntri_g[i]; nth8_fill(s_nth8, (uint32_t)i); } /* (static tables) */
     __syncthreads();
+    isomc_pdl_wait(); /* the sign words come from the kernel before */
     const uint32_t warp = threadIdx.x >> 5;
     const Warp w{threadIdx.x & 31u, nullptr};
-    count_list_warp<WIDE>(w, g, signs, s_ntri, s_nth8, L, out, gshift, row0, row1, ticket, s_q[warp]);
+    count_list_warp<WIDE>(w, g, signs, s_ntri, s_nth8, L, out, gshift, row0, row1, ticket, s_q[warp], gridDim.x * (blockDim.x >> 5), task_passes);
 }
 
-/* list blocks [*blk_first, *blk_end): one CTA per block, one lane per entry */
+/* list blocks [*blk_first, *blk_end): a CTA per block (strided over the CTAs), one lane per entry.  (Warps drawing 32-entry pieces
+ * from a ticket counter instead was measured: emit 0.273 -> 0.325 ms at 512^3, 1.29 -> 2.68 ms at 2048^3 -- the eight warps of a
+ * CTA working on ONE block is what keeps the neighbour look-ups in L1.) */
 template <class Src, int MINB>
 __global__ void __launch_bounds__(LIST_BLOCK, MINB) k_emit_list(Src src, Geo g, ListBufs L, const EmitTab *__restrict__ tab_g,
                                                           const uint32_t *__restrict__ rowPV, const uint32_t *__restrict__ rowPT,
@@ -51,12 +56,14 @@ __global__ void __launch_bounds__(LIST_BLOCK, MINB) k_emit_list(Src src, Geo g, 
                                                           const uint32_t *__restrict__ blk_end) {
     __shared__ EmitTab T;
     __shared__ uint32_t s_eid[12 * LIST_BLOCK];
-    {
+    isomc_pdl_trigger();
+    { /* (the table is written once at create: safe to read before the kernels earlier in the stream are done) */
         const uint32_t *srcw = reinterpret_cast<const uint32_t *>(tab_g);
         uint32_t *dstw = reinterpret_cast<uint32_t *>(&T);
         for (uint32_t i = threadIdx.x; i < sizeof(EmitTab) / 4; i += LIST_BLOCK) dstw[i] = srcw[i];
     }
     __syncthreads();
+    isomc_pdl_wait(); /* list, prefixes, marks: the counting kernel and the row scan */
     if (*L.ctr > L.cap_blocks) return; /* list overflow: entries are incomplete; the host grows the list and re-runs */
     const uint32_t b0 = blk_first ? *blk_first : 0u, b1 = *blk_end;
     EmitArgs A;
@@ -67,12 +74,27 @@ __global__ void __launch_bounds__(LIST_BLOCK, MINB) k_emit_list(Src src, Geo g, 
     A.first_own_layer = g.ghost;
     A.cap_v = cap_v; A.cap_t = cap_t;
     A.xyz = xyz; A.idx = idx;
-    for (uint32_t b = b0 + blockIdx.x; b < b1; b += gridDim.x) {
-        const uint32_t fill = L.blkfill[b];
-        if (threadIdx.x < fill) {
-            const uint64_t k = (uint64_t)b * LIST_BLOCK + threadIdx.x;
-            emit_cell(g, src, T, L, A, k, L.ent[k], L.ent_yz[k], s_eid + threadIdx.x, LIST_BLOCK);
+    /* the entries of the next piece of work are requested before the current one is worked on: the first load of an iteration
+     * (a DRAM miss) was the largest single stall of the kernel */
+    uint32_t b = b0 + blockIdx.x;
+    uint32_t fill = 0, yz = 0;
+    uint2 ea = make_uint2(0u, 0u);
+    if (b < b1) {
+        fill = L.blkfill[b];
+        const uint64_t k = (uint64_t)b * LIST_BLOCK + threadIdx.x;
+        ea = L.ent[k]; yz = L.ent_yz[k]; /* (entries past `fill` are allocated, never used) */
+    }
+    while (b < b1) {
+        const uint32_t bn = b + gridDim.x;
+        uint32_t fill_n = 0, yz_n = 0;
+        uint2 ea_n = make_uint2(0u, 0u);
+        if (bn < b1) {
+            fill_n = L.blkfill[bn];
+            const uint64_t kn = (uint64_t)bn * LIST_BLOCK + threadIdx.x;
+            ea_n = L.ent[kn]; yz_n = L.ent_yz[kn];
         }
+        if (threadIdx.x < fill) emit_cell(g, src, T, L, A, (uint64_t)b * LIST_BLOCK + threadIdx.x, ea, yz, s_eid + threadIdx.x, LIST_BLOCK);
+        b = bn; fill = fill_n; ea = ea_n; yz = yz_n;
     }
 }
 
@@ -98,15 +120,16 @@ template <class Src>
 cudaError_t launch_emit_list(const Src &src, const Geo &g, const ListBufs &L, const EmitTab *tab, const uint32_t *rowPV,
                              const uint32_t *rowPT, const unsigned long long *layerTot, const uint32_t *vofs, float *xyz,
                              uint32_t *idx, uint64_t cap_v, uint64_t cap_t, const uint32_t *blk_first, const uint32_t *blk_end,
-                             int sms, cudaStream_t st) {
+                             int sms, cudaStream_t st, int grid_bps) {
     const int minb = emit_list_minb();
-    const uint32_t grid = (uint32_t)(sms * minb);
+    const uint32_t grid = (uint32_t)(sms * (grid_bps > 0 && grid_bps < minb ? grid_bps : minb));
+#define ISOMC_EMIT_LAUNCH(M) isomc_launch(k_emit_list<Src, M>, grid, LIST_BLOCK, st, true, src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, (unsigned long long)cap_v, (unsigned long long)cap_t, blk_first, blk_end)
     switch (minb) {
-    case 4: k_emit_list<Src, 4><<<grid, LIST_BLOCK, 0, st>>>(src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end); break;
-    case 6: k_emit_list<Src, 6><<<grid, LIST_BLOCK, 0, st>>>(src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end); break;
-    default: k_emit_list<Src, 5><<<grid, LIST_BLOCK, 0, st>>>(src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end); break;
+    case 4: return ISOMC_EMIT_LAUNCH(4);
+    case 6: return ISOMC_EMIT_LAUNCH(6);
+    default: return ISOMC_EMIT_LAUNCH(5);
     }
-    return cudaGetLastError();
+#undef ISOMC_EMIT_LAUNCH
 }
 
 } /* namespace */
@@ -128,23 +151,25 @@ uint32_t isomc_count_list_max_warps(int sms) { return (uint32_t)(sms * 6 * 8); }
 template <bool WIDE>
 static void launch_count_list_v(uint32_t grid, cudaStream_t st, const Geo &g, const uint32_t *signs, const uint8_t *ntri,
                                 const ListBufs &L, const CountOut &out, uint32_t gshift, uint32_t row0, uint32_t row1, uint32_t *ticket) {
+    static int tp = -1; /* ISOMC_COUNT_TASK: passes per ticket (0 = count_task_passes()) */
+    if (tp < 0) { const char *p = getenv("ISOMC_COUNT_TASK"); tp = p ? atoi(p) : 0; if (tp < 0) tp = 0; }
     switch (count_list_minb()) {
-    default: k_count_list<WIDE, 4><<<grid, 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1, ticket); break;
-    case 6: k_count_list<WIDE, 6><<<grid, 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1, ticket); break;
-    case 5: k_count_list<WIDE, 5><<<grid, 256, 0, st>>>(g, signs, ntri, L, out, gshift, row0, row1, ticket); break;
+    default: isomc_launch(k_count_list<WIDE, 4>, grid, 256, st, true, g, signs, ntri, L, out, gshift, row0, row1, ticket, (uint32_t)tp); break;
+    case 6: isomc_launch(k_count_list<WIDE, 6>, grid, 256, st, true, g, signs, ntri, L, out, gshift, row0, row1, ticket, (uint32_t)tp); break;
+    case 5: isomc_launch(k_count_list<WIDE, 5>, grid, 256, st, true, g, signs, ntri, L, out, gshift, row0, row1, ticket, (uint32_t)tp); break;
     }
 }
 
 cudaError_t isomc_launch_count_list(const Geo &g, const uint32_t *signs, const McTables *tabs, const ListBufs &L, uint32_t *rowV,
                                     uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot, uint32_t *ticket, uint32_t lz0,
-                                    uint32_t lz1, int sms, cudaStream_t st) {
+                                    uint32_t lz1, int sms, cudaStream_t st, int grid_bps) {
     const uint32_t npair = (g.nsegx + 1) / 2; /* lanes per row: every lane scans two neighbouring segments */
     uint32_t gshift = 0;
     while ((1u << gshift) < npair && gshift < 5) ++gshift;
     const uint32_t row0 = lz0 * g.ncx, row1 = lz1 * g.ncx;
     const uint8_t *ntri = reinterpret_cast<const uint8_t *>(tabs) + offsetof(McTables, ntri);
     const CountOut out{rowV, rowT, rowA, layerTot};
-    const int per_sm = count_list_minb();
+    const int per_sm = grid_bps > 0 && grid_bps < count_list_minb() ? grid_bps : count_list_minb();
     if (npair <= 32) {
         const uint32_t rpw = 32u >> gshift;
         const uint64_t warps = ((uint64_t)(row1 - row0) + rpw - 1) / rpw;
@@ -158,27 +183,27 @@ cudaError_t isomc_launch_count_list(const Geo &g, const uint32_t *signs, const M
 cudaError_t isomc_launch_emit_list_grid(const Geo &g, const float *d_grid, const ListBufs &L, const EmitTab *tab,
                                         const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                         const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
-                                        const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st) {
+                                        const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st, int grid_bps) {
     return launch_emit_list(GridSrc{d_grid}, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end,
-                            sms, st);
+                            sms, st, grid_bps);
 }
 
 cudaError_t isomc_launch_emit_list_sdf_batch(const Geo &g, const SdfProgram *d_progs, const ListBufs &L, const EmitTab *tab,
                                              const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                              const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
-                                             const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st) {
-    return launch_emit_list(SdfBatchSrc{d_progs}, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end, sms, st);
+                                             const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st, int grid_bps) {
+    return launch_emit_list(SdfBatchSrc{d_progs}, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end, sms, st, grid_bps);
 }
 
 cudaError_t isomc_launch_emit_list_sdf(const Geo &g, const SdfProgram &prog, bool directed, const ListBufs &L, const EmitTab *tab,
                                        const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                        const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
-                                       const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st) {
+                                       const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st, int grid_bps) {
     if (directed)
-        return launch_emit_list(SdfDirSrc{prog}, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end, sms, st);
+        return launch_emit_list(SdfDirSrc{prog}, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end, sms, st, grid_bps);
     SdfChainSrc csrc;
     if (sdf_to_chain(prog, &csrc.chain))
-        return launch_emit_list(csrc, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end, sms, st);
+        return launch_emit_list(csrc, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end, sms, st, grid_bps);
     return launch_emit_list(SdfSrc{prog}, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end, sms,
-                            st);
+                            st, grid_bps);
 }

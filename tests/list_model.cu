@@ -53,7 +53,7 @@ struct WarpJob {
     const uint8_t *ntri, *nth8;
     ListBufs L;
     CountOut out;
-    uint32_t gshift, row0, row1;
+    uint32_t gshift, row0, row1, n_warps;
     uint32_t *ticket;
     SegQueue Q;
 };
@@ -62,8 +62,8 @@ WarpJob *g_job = nullptr;
 void lane_main(int lane) {
     WarpJob &J = *g_job;
     const Warp w{(uint32_t)lane, (void *)g_emu};
-    if (J.wide) count_list_warp<true>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.ticket, J.Q);
-    else count_list_warp<false>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.ticket, J.Q);
+    if (J.wide) count_list_warp<true>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.ticket, J.Q, J.n_warps);
+    else count_list_warp<false>(w, J.g, J.signs, J.ntri, J.nth8, J.L, J.out, J.gshift, J.row0, J.row1, J.ticket, J.Q, J.n_warps);
     g_emu->done[lane] = true;
 }
 
@@ -233,7 +233,7 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
      * to a random emulated warp, and the warps run one after the other in shuffled order */
     uint32_t ticket = 0;
     const uint32_t npass = npair > 32 ? (uint32_t)nrows_c : (uint32_t)((nrows_c + (32u >> gshift) - 1) / (32u >> gshift));
-    const uint32_t ntask = (npass + count_task_passes(npass) - 1) / count_task_passes(npass);
+    const uint32_t ntask = (npass + count_task_passes(npass, n_warps) - 1) / count_task_passes(npass, n_warps);
     std::vector<std::vector<uint32_t>> share(n_warps);
     for (uint32_t t = 0; t < ntask; ++t) {
         st = st * 6364136223846793005ull + 1442695040888963407ull;
@@ -246,7 +246,7 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
         WarpJob J;
         J.wide = npair > 32;
         J.g = g; J.signs = signs.data(); J.ntri = mt.ntri; J.nth8 = nth8.data(); J.L = L; J.out = out;
-        J.gshift = gshift; J.row0 = 0; J.row1 = (uint32_t)nrows_c; J.ticket = &ticket;
+        J.gshift = gshift; J.row0 = 0; J.row1 = (uint32_t)nrows_c; J.ticket = &ticket; J.n_warps = n_warps;
         run_warp(E, J);
     }
 
