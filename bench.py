@@ -243,7 +243,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "Gvoxels/s", "cores": 1, "kind": "port", "sample": last["sample"]},
             "e2e": {"value": v, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -284,6 +284,11 @@ class Runner:
         dev = "cuda:%d" % self.local
         self.mine = torch.as_tensor(CudaArray(d_tot.value, 3, "<i8"), device=dev)
         self.gathered = torch.zeros(3 * self.world, dtype=torch.int64, device=dev)
+        # the totals exchange: peer stores into the ranks' mailboxes over NVLink (default), or an NCCL all-gather per step
+        self.exchange = "nccl" if os.environ.get("ISOMC_EXCHANGE", "peer") == "nccl" else "peer"
+        if self.world > 1 and self.exchange == "peer":
+            from isosurface_b200.sharded import connect_peers_ipc
+            connect_peers_ipc(self.lib, self.h, self.rank, self.world)
 
     def step(self):
         lib, _lib, h = self.lib, self._lib, self.h
@@ -300,8 +305,11 @@ class Runner:
                 _lib.check(lib.isomc_slab_count_grid_device(h, C.c_void_p(self.grid.data_ptr())), h)
             else:
                 _lib.check(lib.isomc_slab_count_sdf(h, self.prog.ctypes.data, len(self.prog)), h)
-            dist.all_gather_into_tensor(self.gathered, self.mine)
-            _lib.check(lib.isomc_slab_emit_gathered(h, C.c_void_p(self.gathered.data_ptr()), self.rank, self.world), h)
+            if self.exchange == "peer":
+                _lib.check(lib.isomc_slab_emit_exchanged(h), h)
+            else:
+                dist.all_gather_into_tensor(self.gathered, self.mine)
+                _lib.check(lib.isomc_slab_emit_gathered(h, C.c_void_p(self.gathered.data_ptr()), self.rank, self.world), h)
 
     def barrier(self):
         self.torch.cuda.synchronize()
@@ -438,6 +446,9 @@ def run_ours(args):
     t_s = ms_step * 1e-3
     value = voxels / t_s / 1e9
     cfg = base_config(wl, world)
+    if world > 1:
+        cfg["exchange"] = ("slab totals as peer stores into the ranks' mailboxes over NVLink (CUDA IPC), offset derived on the device"
+                           if R.exchange == "peer" else "NCCL all-gather of 3 x u64 per rank on the extraction stream")
     cfg.update({"vertices": V, "triangles": T, "active_cells": A, "active_fraction": A / (float(size - 1) ** 2 * size),
                 "timing": "CUDA events on the extraction stream, max over ranks; wall %.3f ms/step" % wall_ms})
     line = {
@@ -583,12 +594,32 @@ def run_ours(args):
                     raise
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: file descriptor 1 is pointed at stderr for the rest of the process, so that what
+    libraries print there (NCCL writes its version banner to stdout at NCCL_DEBUG=VERSION whatever NCCL_DEBUG_FILE says) cannot
+    get in front of it; emit_line() writes to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -198,10 +198,27 @@ int32_t isomc_slab_emit_gathered(isomc_t *h, const uint64_t *d_gathered, uint32_
  * global ids of this slab do not fit u32) */
 int32_t isomc_slab_enqueue_emit_gathered(isomc_t *h, const uint64_t *d_gathered, uint32_t rank, uint32_t n_ranks);
 
+/* ---- the exchange without a collective library: slab totals as peer stores over NVLink / NVSwitch ---------------
+ * Every slab handle owns a small mailbox in device memory.  Once a rank knows the mailboxes of all ranks (same process: device
+ * pointers, peer access is enabled here; one process per GPU: CUDA IPC handles, exchanged once by whatever the host has --
+ * MPI, torch.distributed, a file), isomc_slab_emit_exchanged() replaces "all-gather + isomc_slab_emit_gathered": a one-CTA
+ * kernel writes this rank's three totals into every rank's mailbox, waits for the others' and derives the id offset, the emission
+ * follows on the same stream.  No host synchronisation, no NCCL call, one tiny launch.  A rank that never publishes makes the
+ * others time out (ISOMC_EXCHANGE_TIMEOUT_MS, default 10 s) with ISOMC_ERR_NCCL instead of hanging the device.
+ * All ranks must run the same sequence of slab_count / slab_emit_exchanged steps. */
+#define ISOMC_IPC_HANDLE_BYTES 64
+int32_t isomc_slab_mailbox(isomc_t *h, void **d_mailbox);                     /* this rank's mailbox (device pointer) */
+int32_t isomc_slab_mailbox_ipc(isomc_t *h, void *handle /* ISOMC_IPC_HANDLE_BYTES */);   /* the same as a CUDA IPC handle */
+int32_t isomc_slab_connect(isomc_t *h, uint32_t rank, uint32_t n_ranks, void *const *mailboxes /* [n_ranks], own entry ignored */);
+int32_t isomc_slab_connect_ipc(isomc_t *h, uint32_t rank, uint32_t n_ranks, const void *handles /* n_ranks x ISOMC_IPC_HANDLE_BYTES */);
+int32_t isomc_slab_emit_exchanged(isomc_t *h);
+int32_t isomc_slab_enqueue_emit_exchanged(isomc_t *h);                        /* without the final synchronisation: isomc_finish() */
+
 /* ---- the same sharding driven from ONE process over the GPUs of a box (new) ----------------
  * `MarchingCubes::new(size)` for a host that owns several devices (the Rust shim, include/isosurface.hpp): one slab handle
- * per listed device, cell layers split evenly; each extract = count on every device, ONE ncclAllGather of 3 x u64 per rank
- * on the extraction streams (NCCL over NVLink / NVSwitch; libnccl.so.2 is loaded on first use), emission with global ids.
+ * per listed device, cell layers split evenly; each extract = count on every device, ONE exchange of 3 x u64 per rank on the
+ * extraction streams -- peer stores into the ranks' mailboxes when all devices reach each other as peers (NVLink / NVSwitch), else
+ * one ncclAllGather (libnccl.so.2 is loaded on first use; ISOMC_EXCHANGE=nccl forces it) --, emission with global ids.
  * devices == NULL: devices 0 .. n_gpus-1.  Listing one device several times runs all slabs there (a single-GPU box can
  * exercise the sharded path; the exchange is then a stream-ordered device copy, NCCL refuses duplicate devices).
  * Concatenating the ranks' parts in rank order (isomc_sharded_copy_out does) gives exactly the unsharded mesh. */
@@ -210,6 +227,7 @@ int32_t isomc_sharded_create(uint32_t size, uint32_t n_gpus, const int32_t *devi
 int32_t isomc_sharded_destroy(isomc_sharded_t *s);
 const char *isomc_sharded_last_error(const isomc_sharded_t *s);   /* s may be NULL: last create() error */
 int32_t isomc_sharded_uses_nccl(const isomc_sharded_t *s);        /* 1: the exchange is an NCCL all-gather */
+int32_t isomc_sharded_uses_peer_memory(const isomc_sharded_t *s); /* 1: the exchange is peer stores into mailboxes (the default when every pair of devices has peer access) */
 /* rank's cell layers [z_begin, z_end) and the sample layers it must be given: n_sample_layers starting at first_sample_layer */
 int32_t isomc_sharded_slab(const isomc_sharded_t *s, uint32_t rank, uint32_t *z_begin, uint32_t *z_end, uint32_t *first_sample_layer,
                            uint32_t *n_sample_layers);

@@ -78,10 +78,17 @@ SIGNATURES = {
     "isomc_slab_emit": (_I32, [_P, _U64, _U64]),
     "isomc_slab_emit_gathered": (_I32, [_P, _P, _U32, _U32]),
     "isomc_slab_enqueue_emit_gathered": (_I32, [_P, _P, _U32, _U32]),
+    "isomc_slab_mailbox": (_I32, [_P, C.POINTER(_P)]),
+    "isomc_slab_mailbox_ipc": (_I32, [_P, _P]),
+    "isomc_slab_connect": (_I32, [_P, _U32, _U32, _P]),
+    "isomc_slab_connect_ipc": (_I32, [_P, _U32, _U32, _P]),
+    "isomc_slab_emit_exchanged": (_I32, [_P]),
+    "isomc_slab_enqueue_emit_exchanged": (_I32, [_P]),
     "isomc_sharded_create": (_I32, [_U32, _U32, _P, C.POINTER(_P)]),
     "isomc_sharded_destroy": (_I32, [_P]),
     "isomc_sharded_last_error": (C.c_char_p, [_P]),
     "isomc_sharded_uses_nccl": (_I32, [_P]),
+    "isomc_sharded_uses_peer_memory": (_I32, [_P]),
     "isomc_sharded_slab": (_I32, [_P, _U32, C.POINTER(_U32), C.POINTER(_U32), C.POINTER(_U32), C.POINTER(_U32)]),
     "isomc_sharded_handle": (_I32, [_P, _U32, C.POINTER(_P)]),
     "isomc_sharded_extract_grid": (_I32, [_P, _P]),

@@ -72,6 +72,13 @@ struct isomc {
     cudaGraphExec_t pipe_exec = nullptr;
     uint64_t pipe_key[12] = {};
     uint32_t pipe_launches = 0;
+    /* slab totals exchanged over peer memory (isomc_slab_connect*): own mailbox, the ranks' mailbox addresses, step counter */
+    unsigned long long *mailbox = nullptr;
+    unsigned long long **d_peers = nullptr;
+    std::vector<void *> ipc_opened;
+    uint32_t xchg_rank = 0, xchg_n = 0;
+    unsigned long long xchg_seq = 0;
+    bool step_exchanged = false; /* the id offset of the step in flight came from k_slab_exchange (totals[14] = its time-out flag) */
     /* streamed host-to-host extract (isomc_extract_grid_host_to): copy-in / copy-out streams, per-chunk events */
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_cnt[MAX_CHUNKS] = {}, ev_emit[MAX_CHUNKS] = {};
@@ -496,6 +503,9 @@ int32_t finish_impl(isomc *h) {
     if (h->h_totals[0] >= (1ull << 32) || h->h_totals[1] >= (1ull << 32))
         return fail(h, ISOMC_ERR_INDEX_OVERFLOW, "mesh has %llu vertices / %llu triangles: does not fit u32 indices",
                     (unsigned long long)h->h_totals[0], (unsigned long long)h->h_totals[1]);
+    if (h->vofs_cached < 0 && h->step_exchanged && h->h_totals[14] != 0)
+        return fail(h, ISOMC_ERR_NCCL, "totals exchange over peer memory timed out: rank %llu never published step %llu",
+                    (unsigned long long)h->h_totals[14] - 1, h->xchg_seq);
     if (h->vofs_cached < 0 && h->h_totals[13] + h->h_totals[0] >= (1ull << 32)) /* offset derived on the device (slab_emit_gathered) */
         return fail(h, ISOMC_ERR_INDEX_OVERFLOW, "global vertex ids of this slab reach %llu: do not fit u32 indices",
                     (unsigned long long)(h->h_totals[13] + h->h_totals[0]));
@@ -680,6 +690,8 @@ int32_t isomc_destroy(isomc_t *h) {
     if (!h) return ISOMC_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(h->mailbox); cudaFree(h->d_peers);
     if (h->pipe_exec) cudaGraphExecDestroy(h->pipe_exec);
     if (h->s_sign) {
         cudaStreamSynchronize(h->s_sign); cudaStreamSynchronize(h->s_emit);
@@ -1191,6 +1203,7 @@ int32_t isomc_slab_enqueue_emit_gathered(isomc_t *h, const uint64_t *d_gathered,
     /* id offset on the device; its 64-bit value goes to totals[13] so that finish() can tell an overflow of the global ids */
     CU(h, isomc_launch_slab_bases((const unsigned long long *)d_gathered, rank, h->g.ghost, h->vofs, h->totals + 13, h->stream));
     h->vofs_cached = -1;
+    h->step_exchanged = false;
     h->totals_valid = false; /* (totals[13] is new) */
     h->stats.kernel_launches += 1;
     if (h->cap_v > 0 || h->cap_t > 0) {
@@ -1202,6 +1215,122 @@ int32_t isomc_slab_enqueue_emit_gathered(isomc_t *h, const uint64_t *d_gathered,
 
 int32_t isomc_slab_emit_gathered(isomc_t *h, const uint64_t *d_gathered, uint32_t rank, uint32_t n_ranks) {
     int32_t rc = isomc_slab_enqueue_emit_gathered(h, d_gathered, rank, n_ranks);
+    return rc ? rc : finish_impl(h);
+}
+
+/* ---- totals exchange over peer memory (no collective library) ------------------------------ */
+
+static int32_t ensure_mailbox(isomc_t *h) {
+    if (h->mailbox) return ISOMC_OK;
+    CU(h, cudaMalloc(&h->mailbox, ISOMC_MAILBOX_BYTES));
+    CU(h, cudaMemset(h->mailbox, 0, ISOMC_MAILBOX_BYTES));
+    CU(h, cudaMalloc(&h->d_peers, ISOMC_MAX_RANKS * sizeof(unsigned long long *)));
+    CU(h, cudaMemset(h->d_peers, 0, ISOMC_MAX_RANKS * sizeof(unsigned long long *)));
+    return ISOMC_OK;
+}
+
+int32_t isomc_slab_mailbox(isomc_t *h, void **d_mailbox) {
+    if (!h || !d_mailbox) return ISOMC_ERR_BAD_ARG;
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    rc = ensure_mailbox(h);
+    if (rc) return rc;
+    *d_mailbox = h->mailbox;
+    return ISOMC_OK;
+}
+
+int32_t isomc_slab_mailbox_ipc(isomc_t *h, void *handle64) {
+    if (!h || !handle64) return ISOMC_ERR_BAD_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == ISOMC_IPC_HANDLE_BYTES, "ISOMC_IPC_HANDLE_BYTES");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    rc = ensure_mailbox(h);
+    if (rc) return rc;
+    cudaIpcMemHandle_t hd;
+    CU(h, cudaIpcGetMemHandle(&hd, h->mailbox));
+    memcpy(handle64, &hd, sizeof hd);
+    return ISOMC_OK;
+}
+
+static int32_t connect_impl(isomc_t *h, uint32_t rank, uint32_t n_ranks, std::vector<unsigned long long *> &ptrs) {
+    ptrs[rank] = h->mailbox;
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaMemcpy(h->d_peers, ptrs.data(), n_ranks * sizeof(unsigned long long *), cudaMemcpyHostToDevice));
+    h->xchg_rank = rank; h->xchg_n = n_ranks; h->xchg_seq = 0;
+    CU(h, cudaMemset(h->mailbox, 0, ISOMC_MAILBOX_BYTES));
+    return ISOMC_OK;
+}
+
+int32_t isomc_slab_connect(isomc_t *h, uint32_t rank, uint32_t n_ranks, void *const *mailboxes) {
+    if (!h || !mailboxes || rank >= n_ranks || n_ranks > ISOMC_MAX_RANKS) return h ? fail(h, ISOMC_ERR_BAD_ARG, "bad rank / n_ranks") : ISOMC_ERR_BAD_ARG;
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    rc = ensure_mailbox(h);
+    if (rc) return rc;
+    std::vector<unsigned long long *> ptrs(n_ranks);
+    for (uint32_t r = 0; r < n_ranks; ++r) {
+        if (r != rank && !mailboxes[r]) return fail(h, ISOMC_ERR_BAD_ARG, "mailbox of rank %u is NULL", r);
+        ptrs[r] = (unsigned long long *)mailboxes[r];
+        if (r == rank) continue;
+        cudaPointerAttributes at;
+        CU(h, cudaPointerGetAttributes(&at, mailboxes[r]));
+        if (at.device != h->device) { /* another device of this process: peer stores need peer access */
+            int can = 0;
+            CU(h, cudaDeviceCanAccessPeer(&can, h->device, at.device));
+            if (!can) return fail(h, ISOMC_ERR_CUDA, "device %d cannot access device %d as a peer", h->device, at.device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail(h, ISOMC_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", at.device, cudaGetErrorString(e));
+        }
+    }
+    return connect_impl(h, rank, n_ranks, ptrs);
+}
+
+int32_t isomc_slab_connect_ipc(isomc_t *h, uint32_t rank, uint32_t n_ranks, const void *handles) {
+    if (!h || !handles || rank >= n_ranks || n_ranks > ISOMC_MAX_RANKS) return h ? fail(h, ISOMC_ERR_BAD_ARG, "bad rank / n_ranks") : ISOMC_ERR_BAD_ARG;
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    rc = ensure_mailbox(h);
+    if (rc) return rc;
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    h->ipc_opened.clear();
+    std::vector<unsigned long long *> ptrs(n_ranks);
+    for (uint32_t r = 0; r < n_ranks; ++r) {
+        if (r == rank) continue;
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char *)handles + (size_t)r * ISOMC_IPC_HANDLE_BYTES, sizeof hd);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(h, ISOMC_ERR_CUDA, "cudaIpcOpenMemHandle (mailbox of rank %u): %s", r, cudaGetErrorString(e));
+        h->ipc_opened.push_back(p);
+        ptrs[r] = (unsigned long long *)p;
+    }
+    return connect_impl(h, rank, n_ranks, ptrs);
+}
+
+int32_t isomc_slab_enqueue_emit_exchanged(isomc_t *h) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h->xchg_n) return fail(h, ISOMC_ERR_BAD_ARG, "slab is not connected to its peers (isomc_slab_connect / isomc_slab_connect_ipc)");
+    if (!h->counted) return fail(h, ISOMC_ERR_NO_RESULT, "slab_emit before slab_count");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    static long long timeout = 0;
+    if (!timeout) { const char *p = getenv("ISOMC_EXCHANGE_TIMEOUT_MS"); timeout = (long long)(p ? atof(p) : 10000.0) * 2000000ll; }
+    ++h->xchg_seq;
+    CU(h, isomc_launch_slab_exchange(h->d_peers, h->xchg_rank, h->xchg_n, h->g.ghost, h->xchg_seq, h->totals, h->vofs, timeout, h->stream));
+    h->vofs_cached = -1;
+    h->step_exchanged = true;
+    h->totals_valid = false; /* (totals[13], [14] are new) */
+    h->stats.kernel_launches += 1;
+    if (h->cap_v > 0 || h->cap_t > 0) {
+        rc = enqueue_emit(h);
+        if (rc) return rc;
+    }
+    return ISOMC_OK;
+}
+
+int32_t isomc_slab_emit_exchanged(isomc_t *h) {
+    int32_t rc = isomc_slab_enqueue_emit_exchanged(h);
     return rc ? rc : finish_impl(h);
 }
 

@@ -236,6 +236,56 @@ __global__ void k_slab_bases(const unsigned long long *__restrict__ gathered, ui
     }
 }
 
+/*
+ * The same exchange WITHOUT a collective library: the slab totals travel as peer stores over NVLink / NVSwitch.
+ * Every rank owns a mailbox (2 parities x ISOMC_MAX_RANKS slots of {V, V_before_last, T, seq}) in its device memory and holds the
+ * addresses of all ranks' mailboxes (same process: plain device pointers with peer access enabled; other processes: CUDA IPC
+ * mappings).  Thread r of this one-CTA kernel writes this rank's totals into slot [parity][rank] of rank r's mailbox, fences,
+ * releases the slot's sequence number, then waits for rank r's slot in the rank's OWN mailbox and takes its totals; thread 0
+ * derives the id offset as k_slab_bases does.  Two parities are enough: a rank publishes step s+2 only after it has seen every
+ * rank's step s+1, and a rank publishes s+1 after its own wait of step s (stream order).  A wait that lasts longer than
+ * `timeout_cycles` gives up and flags the step (totals[14] = 1 + the silent rank) instead of hanging the device.
+ */
+__global__ void __launch_bounds__(ISOMC_MAX_RANKS) k_slab_exchange(unsigned long long *const *__restrict__ peers, uint32_t rank,
+                                                                  uint32_t n_ranks, uint32_t ghost, unsigned long long seq,
+                                                                  unsigned long long *__restrict__ totals, uint32_t *__restrict__ vofs,
+                                                                  long long timeout_cycles) {
+    __shared__ unsigned long long s_tot[ISOMC_MAX_RANKS][3];
+    __shared__ uint32_t s_bad;
+    isomc_pdl_trigger();
+    isomc_pdl_wait(); /* totals[8..10] come from the row scan */
+    const uint32_t r = threadIdx.x, par = (uint32_t)(seq & 1ull);
+    if (r == 0) s_bad = 0;
+    __syncthreads();
+    if (r < n_ranks) {
+        volatile unsigned long long *dst = peers[r] + ((size_t)par * ISOMC_MAX_RANKS + rank) * 4;
+        dst[0] = totals[8]; dst[1] = totals[9]; dst[2] = totals[10];
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst + 3), "l"(seq) : "memory");
+        const unsigned long long *src = peers[rank] + ((size_t)par * ISOMC_MAX_RANKS + r) * 4;
+        const long long t0 = clock64();
+        unsigned long long got = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(src + 3) : "memory");
+            if (got == seq) break;
+            if (clock64() - t0 > timeout_cycles) { atomicMax(&s_bad, r + 1); break; }
+            __nanosleep(100);
+        }
+        const volatile unsigned long long *vs = src;
+        s_tot[r][0] = vs[0]; s_tot[r][1] = vs[1]; s_tot[r][2] = vs[2];
+    }
+    __syncthreads();
+    if (r == 0) {
+        unsigned long long vbase = 0;
+        for (uint32_t h = 0; h < rank; ++h) vbase += s_tot[h][0];
+        unsigned long long ofs = vbase;
+        if (ghost && rank > 0) ofs = vbase - s_tot[rank - 1][0] + s_tot[rank - 1][1];
+        *vofs = (uint32_t)ofs;
+        totals[13] = ofs; /* untruncated: the host checks that ofs + local ids fit u32 */
+        totals[14] = s_bad;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* debug / parity kernels                                                                       */
 /* ------------------------------------------------------------------------------------------ */
@@ -354,6 +404,12 @@ cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t
                                     unsigned long long *ofs64, cudaStream_t st) {
     k_slab_bases<<<1, 32, 0, st>>>(gathered, rank, ghost, vofs, ofs64);
     return cudaGetLastError();
+}
+
+cudaError_t isomc_launch_slab_exchange(unsigned long long *const *d_peers, uint32_t rank, uint32_t n_ranks, uint32_t ghost,
+                                       unsigned long long seq, unsigned long long *totals, uint32_t *vofs, long long timeout_cycles,
+                                       cudaStream_t st) {
+    return isomc_launch(k_slab_exchange, 1, ISOMC_MAX_RANKS, st, true, d_peers, rank, n_ranks, ghost, seq, totals, vofs, timeout_cycles);
 }
 
 cudaError_t isomc_launch_cube_indices(const Geo &g, const uint32_t *signs, const McTables *tabs, uint8_t *out, int sms,

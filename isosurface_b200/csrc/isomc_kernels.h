@@ -36,6 +36,12 @@ cudaError_t isomc_launch_chunk_bases(uint32_t n, unsigned long long *totals, con
                                      cudaStream_t st);
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,
                                     unsigned long long *ofs64, cudaStream_t st);
+/* totals exchange over peer memory (k_slab_exchange): d_peers = device array of every rank's mailbox address */
+#define ISOMC_MAX_RANKS 64
+#define ISOMC_MAILBOX_BYTES (2 * ISOMC_MAX_RANKS * 4 * sizeof(unsigned long long))
+cudaError_t isomc_launch_slab_exchange(unsigned long long *const *d_peers, uint32_t rank, uint32_t n_ranks, uint32_t ghost,
+                                       unsigned long long seq, unsigned long long *totals, uint32_t *vofs, long long timeout_cycles,
+                                       cudaStream_t st);
 cudaError_t isomc_launch_cube_indices(const Geo &g, const uint32_t *signs, const McTables *tabs, uint8_t *out, int sms,
                                       cudaStream_t st);
 cudaError_t isomc_launch_sample_sdf(const SdfProgram &prog, const float *xyz, uint64_t n, float *out, int use_chain, cudaStream_t st);

@@ -75,7 +75,7 @@ struct isomc_sharded {
     std::vector<const uint64_t *> totals;       /* per rank: device pointer to its {V, V before last layer, T} */
     std::vector<nccl_comm_t> comm;
     std::vector<cudaEvent_t> ev;                /* single-device mode: count of rank r is enqueued */
-    bool use_nccl = false, have_result = false;
+    bool use_nccl = false, use_mailbox = false, have_result = false;
     std::vector<uint64_t> nv, nt, na;
     std::string err;
 };
@@ -117,7 +117,9 @@ void slab_range(uint32_t size, uint32_t rank, uint32_t world, uint32_t *z0, uint
 
 /* count on every rank, exchange the totals, emit on every rank: everything enqueued, nothing synchronised */
 int32_t exchange_and_emit(isomc_sharded *s) {
-    if (s->use_nccl) {
+    if (s->use_mailbox) { /* totals as peer stores over NVLink: one tiny kernel per rank publishes, waits and derives the offset */
+        for (uint32_t r = 0; r < s->n; ++r) SRC(s, r, isomc_slab_enqueue_emit_exchanged(s->h[r]));
+    } else if (s->use_nccl) {
         SNC(s, g_nccl.GroupStart());
         for (uint32_t r = 0; r < s->n; ++r)
             SNC(s, g_nccl.AllGather(s->totals[r], s->gathered[r], 3, NCCL_UINT64, s->comm[r], s->stream[r]));
@@ -135,7 +137,8 @@ int32_t exchange_and_emit(isomc_sharded *s) {
             }
         }
     }
-    for (uint32_t r = 0; r < s->n; ++r) SRC(s, r, isomc_slab_enqueue_emit_gathered(s->h[r], (const uint64_t *)s->gathered[r], r, s->n));
+    if (!s->use_mailbox)
+        for (uint32_t r = 0; r < s->n; ++r) SRC(s, r, isomc_slab_enqueue_emit_gathered(s->h[r], (const uint64_t *)s->gathered[r], r, s->n));
     /* first extract of a handle, or a larger mesh: finish() grows the buffers and re-runs the emission of that rank */
     for (uint32_t r = 0; r < s->n; ++r) SRC(s, r, isomc_finish(s->h[r]));
     uint64_t vsum = 0;
@@ -181,7 +184,20 @@ int32_t isomc_sharded_create(uint32_t size, uint32_t n_gpus, const int32_t *devi
             SCU(s, cudaMemset(s->gathered[r], 0, 3 * n_gpus * sizeof(unsigned long long)));
             SCU(s, cudaEventCreateWithFlags(&s->ev[r], cudaEventDisableTiming));
         }
-        if (distinct && n_gpus > 1) {
+        /* distinct devices that reach each other as peers exchange through mailboxes in peer memory (ISOMC_EXCHANGE=nccl: NCCL) */
+        const char *xe = getenv("ISOMC_EXCHANGE");
+        bool peers_ok = distinct && n_gpus > 1 && n_gpus <= 64 && !(xe && strcmp(xe, "nccl") == 0);
+        for (uint32_t r = 0; r < n_gpus && peers_ok; ++r)
+            for (uint32_t q = 0; q < n_gpus && peers_ok; ++q) {
+                int can = 1;
+                if (q != r && (cudaDeviceCanAccessPeer(&can, s->dev[r], s->dev[q]) != cudaSuccess || !can)) peers_ok = false;
+            }
+        if (peers_ok) {
+            std::vector<void *> boxes(n_gpus, nullptr);
+            for (uint32_t r = 0; r < n_gpus; ++r) SRC(s, r, isomc_slab_mailbox(s->h[r], &boxes[r]));
+            for (uint32_t r = 0; r < n_gpus; ++r) SRC(s, r, isomc_slab_connect(s->h[r], r, n_gpus, boxes.data()));
+            s->use_mailbox = true;
+        } else if (distinct && n_gpus > 1) {
             if (!g_nccl.load()) return sfail(s, ISOMC_ERR_NCCL, "%s", g_nccl.why.c_str());
             s->comm.assign(n_gpus, nullptr);
             SNC(s, g_nccl.CommInitAll(s->comm.data(), (int)n_gpus, s->dev.data()));
@@ -215,6 +231,7 @@ int32_t isomc_sharded_destroy(isomc_sharded_t *s) {
 const char *isomc_sharded_last_error(const isomc_sharded_t *s) { return s ? s->err.c_str() : g_sharded_create_error.c_str(); }
 
 int32_t isomc_sharded_uses_nccl(const isomc_sharded_t *s) { return s && s->use_nccl ? 1 : 0; }
+int32_t isomc_sharded_uses_peer_memory(const isomc_sharded_t *s) { return s && s->use_mailbox ? 1 : 0; }
 
 int32_t isomc_sharded_slab(const isomc_sharded_t *s, uint32_t rank, uint32_t *z_begin, uint32_t *z_end, uint32_t *first_sample_layer,
                            uint32_t *n_sample_layers) {

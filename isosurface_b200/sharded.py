@@ -109,11 +109,37 @@ class SlabMarchingCubes:
         _lib.check(self._lib.isomc_copy_out(self._h, xyz.ctypes.data, idx.ctypes.data), self._h)
         return xyz, idx
 
+    # ---- the exchange as peer stores over NVLink (no collective call per step) ----------------
+    def connect_peers(self, group=None):
+        """One process per GPU: exchange the CUDA IPC handles of the ranks' mailboxes ONCE (through torch.distributed, any
+        backend) and map them; afterwards `extract_exchanged` needs no collective and no host round trip per step."""
+        connect_peers_ipc(self._lib, self._h, self.rank, self.world, group)
+
+    def extract_exchanged(self, d_slab_ptr):
+        """count -> totals to every rank's mailbox / wait / id offset on the device -> emit"""
+        _lib.check(self._lib.isomc_slab_count_grid_device(self._h, C.c_void_p(d_slab_ptr)), self._h)
+        _lib.check(self._lib.isomc_slab_emit_exchanged(self._h), self._h)
+
+
+def connect_peers_ipc(lib, handle, rank, world, group=None):
+    """all-gather the 64-byte CUDA IPC handles of the slab mailboxes and connect `handle` to its peers"""
+    import torch
+    import torch.distributed as dist
+    mine = (C.c_uint8 * 64)()
+    _lib.check(lib.isomc_slab_mailbox_ipc(handle, mine), handle)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t_mine = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+    t_all = torch.zeros(64 * world, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(t_all, t_mine, group=group)
+    handles = np.ascontiguousarray(t_all.cpu().numpy())
+    _lib.check(lib.isomc_slab_connect_ipc(handle, rank, world, handles.ctypes.data), handle)
+    dist.barrier(group=group)  # every rank has mapped every mailbox before anyone publishes
+
 
 class ShardedMarchingCubes:
     """`MarchingCubes(size)` over several GPUs of one box, driven from THIS process through the in-library
-    `isomc_sharded_*` entry points (include/isomc.h): one slab handle per device, one NCCL all-gather of 3 x u64 per
-    rank per extract.  `devices` may list one device several times (a single-GPU box exercising the sharded path)."""
+    `isomc_sharded_*` entry points (include/isomc.h): one slab handle per device, one exchange of 3 x u64 per rank per
+    extract (peer stores into mailboxes over NVLink when the devices are peers, else an NCCL all-gather).  `devices` may list one device several times (a single-GPU box exercising the sharded path)."""
 
     def __init__(self, size, devices):
         lib = _lib.load()
@@ -143,6 +169,10 @@ class ShardedMarchingCubes:
     @property
     def uses_nccl(self):
         return bool(self._lib.isomc_sharded_uses_nccl(self._h))
+
+    @property
+    def uses_peer_memory(self):
+        return bool(self._lib.isomc_sharded_uses_peer_memory(self._h))
 
     def slab(self, rank):
         """(z_begin, z_end, first sample layer, number of sample layers) of `rank`"""

@@ -2,6 +2,7 @@
 vertex positions bit-exact as well (the north star allows 1e-5 absolute; tolerance used: 0)."""
 import ctypes as C
 import json
+import os
 from pathlib import Path
 
 import numpy as np
@@ -291,6 +292,44 @@ def test_slab_emit_gathered_on_stream(iso, oracle, isolib):
         _lib.check(isolib.isomc_slab_emit_gathered(s._h, C.c_void_p(gathered.data_ptr()), r, world), s._h)
         parts.append(s.copy_out())
     assert mesh_diff(np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), oxyz, oidx) == ""
+
+
+def test_slab_exchange_over_peer_memory_on_one_device(iso, oracle, isolib, monkeypatch):
+    """isomc_slab_connect + isomc_slab_emit_exchanged: the totals travel as stores into the ranks' mailboxes, the id offset is
+    derived by the waiting kernel.  All ranks on one device here (the mailboxes are plain device pointers); several steps, so that
+    both mailbox parities and the step counter are exercised; then a rank that never publishes must time out, not hang."""
+    import torch
+    from isosurface_b200 import _lib
+    from isosurface_b200.sharded import SlabMarchingCubes, slab_sample_layers
+    monkeypatch.setenv("ISOMC_EXCHANGE_TIMEOUT_MS", "1500")
+    size, world = 48, 4
+    slabs = [SlabMarchingCubes(size, r, world) for r in range(world)]
+    boxes = (C.c_void_p * world)()
+    for r, s in enumerate(slabs):
+        b = C.c_void_p()
+        _lib.check(isolib.isomc_slab_mailbox(s._h, C.byref(b)), s._h)
+        boxes[r] = b.value
+    for r, s in enumerate(slabs):
+        _lib.check(isolib.isomc_slab_connect(s._h, r, world, boxes), s._h)
+    for step, seed in enumerate((0, 5, 9)):
+        t = synth(iso, 2 if step == 0 else 1, size, seed)
+        host = t.cpu().numpy().reshape(size + 1, size, size)
+        oxyz, oidx, _ = oracle.extract_grid(size, host)
+        ptrs = [t.data_ptr() + 4 * slab_sample_layers(size, r, world)[0] * size * size for r in range(world)]
+        for _ in range(2 if step == 0 else 1):  # (first extract of a handle: no output buffers yet, finish() runs the emission)
+            for r, s in enumerate(slabs):
+                _lib.check(isolib.isomc_slab_count_grid_device(s._h, C.c_void_p(ptrs[r])), s._h)
+                _lib.check(isolib.isomc_slab_enqueue_emit_exchanged(s._h), s._h)
+            for s in slabs:
+                _lib.check(isolib.isomc_finish(s._h), s._h)
+        parts = [s.copy_out() for s in slabs]
+        assert mesh_diff(np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), oxyz, oidx) == "", step
+    # ranks 1.. stay silent: rank 0 gives up after the timeout with an error naming a silent rank
+    _lib.check(isolib.isomc_slab_count_grid_device(slabs[0]._h, C.c_void_p(ptrs[0])), slabs[0]._h)
+    rc = isolib.isomc_slab_emit_exchanged(slabs[0]._h)
+    assert rc == _lib.ERR_NCCL and b"timed out" in isolib.isomc_last_error(slabs[0]._h)
+    for s in slabs:
+        s.close()
 
 
 def test_full_size_properties_512(iso, oracle):
@@ -738,7 +777,7 @@ def test_sharded_api_on_one_device(iso, oracle, world):
 
 
 def test_sharded_api_nccl_all_devices(iso, oracle):
-    """isomc_sharded_* over every GPU of the box: one NCCL all-gather per extract, each slab's lattice on its own device"""
+    """isomc_sharded_* over every GPU of the box, each slab's lattice on its own device; both forms of the totals exchange"""
     import torch
     from isosurface_b200 import _lib
     from isosurface_b200.sharded import ShardedMarchingCubes
@@ -749,14 +788,20 @@ def test_sharded_api_nccl_all_devices(iso, oracle):
     t = synth(iso, 1, size, 77)
     host = t.cpu().numpy().reshape(size + 1, size, size)
     oxyz, oidx, oact = oracle.extract_grid(size, host)
-    sh = ShardedMarchingCubes(size, list(range(n)))
-    assert sh.uses_nccl
-    parts = []
-    for r in range(n):
-        zb, ze, first, nl = sh.slab(r)
-        parts.append(torch.from_numpy(host[first:first + nl].copy()).to("cuda:%d" % r))
-    for _ in range(2):
-        nv, nt, na = sh.extract_grid([p.data_ptr() for p in parts])
-        xyz, idx = sh.copy_out()
-        assert na == oact and mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
-    sh.close()
+    for mode in ("peer", "nccl"):  # peer stores into mailboxes over NVLink (default), then the NCCL all-gather
+        if mode == "nccl":
+            os.environ["ISOMC_EXCHANGE"] = "nccl"
+        try:
+            sh = ShardedMarchingCubes(size, list(range(n)))
+        finally:
+            os.environ.pop("ISOMC_EXCHANGE", None)
+        assert sh.uses_nccl == (mode == "nccl") and sh.uses_peer_memory == (mode == "peer")
+        parts = []
+        for r in range(n):
+            zb, ze, first, nl = sh.slab(r)
+            parts.append(torch.from_numpy(host[first:first + nl].copy()).to("cuda:%d" % r))
+        for _ in range(3):
+            nv, nt, na = sh.extract_grid([p.data_ptr() for p in parts])
+            xyz, idx = sh.copy_out()
+            assert na == oact and mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == "", mode
+        sh.close()
