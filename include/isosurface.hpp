@@ -231,5 +231,107 @@ class PointCloud : public MarchingCubes {
     }
 };
 
+// ---- many chunks per call (the crate's usage model: one `MarchingCubes::new(size).extract(..)` per chunk,
+// reference src/marching_cubes.rs:44-45, README.md:19).  Up to `n_chunks` implicit trees go through ONE kernel sequence and one
+// size read-back; chunk b of a batch is delivered to extractors[b] exactly as MarchingCubes(size).extract(sources[b], ..) would.
+class BatchedMarchingCubes {
+  public:
+    BatchedMarchingCubes(uint32_t size, uint32_t n_chunks, int32_t device = 0) : n_chunks_(n_chunks) {
+        int32_t rc = isomc_batch_create(size, n_chunks, device, &h_);
+        if (rc) throw Error(rc, isomc_last_error(nullptr));
+    }
+    ~BatchedMarchingCubes() { isomc_destroy(h_); }
+    BatchedMarchingCubes(const BatchedMarchingCubes &) = delete;
+    BatchedMarchingCubes &operator=(const BatchedMarchingCubes &) = delete;
+    uint32_t capacity() const { return n_chunks_; }
+
+    // sources: any container of device sources of ONE type (heterogeneous batches: encode() the programs yourself and call extract_programs)
+    template <class Sources> void extract(const Sources &sources, const std::vector<Extractor *> &extractors) {
+        std::vector<isomc_sdf_node> flat;
+        std::vector<uint32_t> n_nodes;
+        for (const auto &src : sources) {
+            SdfProgram prog;
+            src.encode(prog);
+            flat.insert(flat.end(), prog.begin(), prog.end());
+            n_nodes.push_back((uint32_t)prog.size());
+        }
+        extract_programs(flat, n_nodes, extractors);
+    }
+    void extract_programs(const std::vector<isomc_sdf_node> &flat, const std::vector<uint32_t> &n_nodes, const std::vector<Extractor *> &extractors) {
+        const uint32_t b = (uint32_t)n_nodes.size();
+        if (b < 1 || b > n_chunks_ || extractors.size() != b) throw Error(ISOMC_ERR_BAD_ARG, "batch size / extractor count mismatch");
+        check(isomc_extract_sdf_batch(h_, flat.data(), n_nodes.data(), b));
+        uint64_t nv = 0, nt = 0;
+        check(isomc_counts(h_, &nv, &nt, nullptr));
+        std::vector<float> xyz(3 * nv);
+        std::vector<uint32_t> idx(3 * nt);
+        check(isomc_copy_out(h_, xyz.data(), idx.data()));
+        std::vector<uint64_t> vo(n_chunks_ + 1), to(n_chunks_ + 1);
+        check(isomc_batch_offsets(h_, vo.data(), to.data()));
+        for (uint32_t c = 0; c < b; ++c) {
+            Extractor &ex = *extractors[c];
+            if (auto *iv = dynamic_cast<IndexedVertices *>(&ex)) {
+                iv->vertices.insert(iv->vertices.end(), xyz.begin() + 3 * vo[c], xyz.begin() + 3 * vo[c + 1]);
+                iv->indices.insert(iv->indices.end(), idx.begin() + 3 * to[c], idx.begin() + 3 * to[c + 1]);
+                continue;
+            }
+            for (uint64_t v = vo[c]; v < vo[c + 1]; ++v) ex.extract_vertex(xyz[3 * v], xyz[3 * v + 1], xyz[3 * v + 2]);
+            for (uint64_t i = 3 * to[c]; i < 3 * to[c + 1]; ++i) ex.extract_index(idx[i]);
+        }
+    }
+
+  private:
+    void check(int32_t rc) { if (rc) throw Error(rc, isomc_last_error(h_)); }
+    isomc_t *h_ = nullptr;
+    uint32_t n_chunks_;
+};
+
+// ---- one extract over several GPUs of the box: z-slabs, one exchange of 3 x u64 per rank (peer stores over
+// NVLink, or an NCCL all-gather), global ids written directly; the delivered mesh is the single-GPU (= reference) mesh.
+class ShardedMarchingCubes {
+  public:
+    ShardedMarchingCubes(uint32_t size, const std::vector<int32_t> &devices) : size_(size), n_((uint32_t)devices.size()) {
+        int32_t rc = isomc_sharded_create(size, n_, devices.data(), &s_);
+        if (rc) throw Error(rc, isomc_sharded_last_error(nullptr));
+    }
+    ~ShardedMarchingCubes() { isomc_sharded_destroy(s_); }
+    ShardedMarchingCubes(const ShardedMarchingCubes &) = delete;
+    ShardedMarchingCubes &operator=(const ShardedMarchingCubes &) = delete;
+    bool uses_peer_memory() const { return isomc_sharded_uses_peer_memory(s_) != 0; }
+    bool uses_nccl() const { return isomc_sharded_uses_nccl(s_) != 0; }
+    uint32_t ranks() const { return n_; }
+    // rank r must be given sample layers [first, first + count) of the size x size x (size+1) lattice, on devices[r]
+    void slab(uint32_t rank, uint32_t &first_sample_layer, uint32_t &n_sample_layers) const {
+        if (isomc_sharded_slab(s_, rank, nullptr, nullptr, &first_sample_layer, &n_sample_layers)) throw Error(ISOMC_ERR_BAD_ARG, "bad rank");
+    }
+    template <class S> void extract(const SamplerT<S> &sampler, Extractor &extractor) { extract(sampler.source, extractor); }
+    template <class S> void extract(const S &source, Extractor &extractor) {
+        SdfProgram prog;
+        source.encode(prog);
+        check(isomc_sharded_extract_sdf(s_, prog.data(), (uint32_t)prog.size()));
+        deliver(extractor);
+    }
+    // d_slabs[r]: device pointer on devices[r] to rank r's sample layers
+    void extract(const std::vector<const float *> &d_slabs, Extractor &extractor) {
+        if (d_slabs.size() != n_) throw Error(ISOMC_ERR_BAD_ARG, "one slab pointer per rank");
+        check(isomc_sharded_extract_grid(s_, d_slabs.data()));
+        deliver(extractor);
+    }
+
+  private:
+    void check(int32_t rc) { if (rc) throw Error(rc, isomc_sharded_last_error(s_)); }
+    void deliver(Extractor &ex) {
+        uint64_t nv = 0, nt = 0;
+        check(isomc_sharded_counts(s_, &nv, &nt, nullptr));
+        std::vector<float> xyz(3 * nv);
+        std::vector<uint32_t> idx(3 * nt);
+        check(isomc_sharded_copy_out(s_, xyz.data(), idx.data()));
+        for (uint64_t v = 0; v < nv; ++v) ex.extract_vertex(xyz[3 * v], xyz[3 * v + 1], xyz[3 * v + 2]);
+        for (uint64_t i = 0; i < 3 * nt; ++i) ex.extract_index(idx[i]);
+    }
+    isomc_sharded_t *s_ = nullptr;
+    uint32_t size_, n_;
+};
+
 }  // namespace isosurface
 #endif

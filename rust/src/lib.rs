@@ -31,7 +31,33 @@ extern "C" {
     fn isomc_copy_out(h: *mut isomc_t, xyz: *mut f32, idx: *mut u32) -> i32;
     fn isomc_copy_out_interleaved_normals(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32, epsilon: f32,
                                           xyzn: *mut f32, idx: *mut u32) -> i32;
+    // many chunks per call
+    fn isomc_batch_create(size: u32, n_chunks: u32, device: i32, out: *mut *mut isomc_t) -> i32;
+    fn isomc_extract_sdf_batch(h: *mut isomc_t, progs: *const isomc_sdf_node, n_nodes: *const u32, n_chunks: u32) -> i32;
+    fn isomc_batch_offsets(h: *mut isomc_t, v_offsets: *mut u64, t_offsets: *mut u64) -> i32;
+    // z-slabs: one rank per process (the host brings the exchange) ...
+    pub fn isomc_slab_create(size: u32, z_begin: u32, z_end: u32, device: i32, out: *mut *mut isomc_t) -> i32;
+    pub fn isomc_slab_count_grid_device(h: *mut isomc_t, d_slab: *const f32) -> i32;
+    pub fn isomc_slab_count_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
+    pub fn isomc_slab_totals(h: *mut isomc_t, totals: *mut u64) -> i32;
+    pub fn isomc_slab_emit(h: *mut isomc_t, vertex_base: u64, boundary_base: u64) -> i32;
+    pub fn isomc_slab_emit_gathered(h: *mut isomc_t, d_gathered: *const u64, rank: u32, n_ranks: u32) -> i32;
+    pub fn isomc_slab_mailbox_ipc(h: *mut isomc_t, handle64: *mut u8) -> i32;
+    pub fn isomc_slab_connect_ipc(h: *mut isomc_t, rank: u32, n_ranks: u32, handles: *const u8) -> i32;
+    pub fn isomc_slab_emit_exchanged(h: *mut isomc_t) -> i32;
+    // ... or all ranks of a box driven from this process
+    fn isomc_sharded_create(size: u32, n_gpus: u32, devices: *const i32, out: *mut *mut isomc_sharded_t) -> i32;
+    fn isomc_sharded_destroy(s: *mut isomc_sharded_t) -> i32;
+    fn isomc_sharded_last_error(s: *const isomc_sharded_t) -> *const c_char;
+    fn isomc_sharded_slab(s: *const isomc_sharded_t, rank: u32, z_begin: *mut u32, z_end: *mut u32, first_sample_layer: *mut u32,
+                          n_sample_layers: *mut u32) -> i32;
+    fn isomc_sharded_extract_grid(s: *mut isomc_sharded_t, d_slabs: *const *const f32) -> i32;
+    fn isomc_sharded_extract_sdf(s: *mut isomc_sharded_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
+    fn isomc_sharded_counts(s: *mut isomc_sharded_t, nv: *mut u64, nt: *mut u64, na: *mut u64) -> i32;
+    fn isomc_sharded_copy_out(s: *mut isomc_sharded_t, xyz: *mut f32, idx: *mut u32) -> i32;
 }
+#[repr(C)]
+pub struct isomc_sharded_t { _private: [u8; 0] }
 const ERR_BUFFER_TOO_SMALL: i32 = -8;
 
 const SPHERE: u32 = 1; const TORUS: u32 = 2; const CYLINDER: u32 = 3; const PRISM: u32 = 4;
@@ -107,35 +133,45 @@ impl<'a, S: DeviceNormals> IndexedInterleavedNormals<'a, S> {
     pub fn new(vertices: &'a mut Vec<f32>, indices: &'a mut Vec<u32>, source: &'a S) -> Self { Self { vertices, indices, source } }
 }
 
-pub struct MarchingCubes { h: *mut isomc_t, size: usize }
+/// reference src/distance.rs:39-45: the distance kinds `MarchingCubes` is generic over.  `Signed` = one scalar distance per
+/// sample; `Directed` = a signed distance along each cardinal axis (src/distance.rs:72-104), implicit sources only.
+pub trait Distance {
+    /// the C entry point that samples an implicit tree as this kind of distance
+    #[doc(hidden)] unsafe fn extract_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
+}
+pub struct Signed;
+pub struct Directed;
+impl Distance for Signed {
+    unsafe fn extract_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32 { isomc_extract_sdf(h, prog, n_nodes) }
+}
+impl Distance for Directed {
+    unsafe fn extract_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32 { isomc_extract_sdf_directed(h, prog, n_nodes) }
+}
 
-impl MarchingCubes {
+/// `MarchingCubes<D: Distance>` as in the reference (src/marching_cubes.rs:38-43); `MarchingCubes::<Signed>::new(size)` and
+/// `MarchingCubes::<Directed>::new(size)` are the two instantiations, and `extract` is ONE generic method.
+pub struct MarchingCubes<D: Distance = Signed> { h: *mut isomc_t, size: usize, _d: std::marker::PhantomData<D> }
+
+impl<D: Distance> MarchingCubes<D> {
     /// `MarchingCubes::new(size)`, reference src/marching_cubes.rs:46-50.  Panics without a CUDA device
     /// (the reference's signature has no error channel).
     pub fn new(size: usize) -> Self {
         let mut h = std::ptr::null_mut();
         let rc = unsafe { isomc_create(size as u32, 0, &mut h) };
         assert!(rc == 0, "isomc_create failed ({}): {:?}", rc, unsafe { std::ffi::CStr::from_ptr(isomc_last_error(std::ptr::null())) });
-        Self { h, size }
+        Self { h, size, _d: std::marker::PhantomData }
     }
 
-    /// `extract(&source, &mut extractor)`, reference src/marching_cubes.rs:59-82.
+    /// `extract(&source, &mut extractor)`, reference src/marching_cubes.rs:59-82: the tree is sampled as `D` distances on the
+    /// device (`Directed`: through the `VectorSource` side of the shapes, src/distance.rs:72-104).
     pub fn extract<S: DeviceSource, E: Extractor>(&mut self, source: &S, extractor: &mut E) {
         let mut prog = Vec::new();
         source.encode(&mut prog);
-        self.check(unsafe { isomc_extract_sdf(self.h, prog.as_ptr(), prog.len() as u32) });
+        self.check(unsafe { D::extract_sdf(self.h, prog.as_ptr(), prog.len() as u32) });
         self.deliver(extractor);
     }
 
-    /// `MarchingCubes::<Directed>::extract` (reference src/distance.rs:72-104): in the crate this is the `D = Directed`
-    /// instantiation of the same generic method; the tree is sampled through its `VectorSource` side on the device.
-    pub fn extract_directed<S: DeviceSource, E: Extractor>(&mut self, source: &S, extractor: &mut E) {
-        let mut prog = Vec::new();
-        source.encode(&mut prog);
-        self.check(unsafe { isomc_extract_sdf_directed(self.h, prog.as_ptr(), prog.len() as u32) });
-        self.deliver(extractor);
-    }
-
+    /// (a dense scalar lattice has no Directed distances: the library rejects it on a `MarchingCubes<Directed>` handle)
     pub fn extract_grid<E: Extractor>(&mut self, grid: &DenseGrid, extractor: &mut E) {
         assert_eq!(grid.size, self.size);
         assert_eq!(grid.data.len(), self.size * self.size * (self.size + 1));
@@ -201,12 +237,12 @@ impl MarchingCubes {
     }
 }
 
-impl Drop for MarchingCubes { fn drop(&mut self) { unsafe { isomc_destroy(self.h); } } }
+impl<D: Distance> Drop for MarchingCubes<D> { fn drop(&mut self) { unsafe { isomc_destroy(self.h); } } }
 
 /// reference src/point_cloud.rs:33-63: one vertex per active cell (midpoint of corners 0 and 6), no face data
-pub struct PointCloud { mc: MarchingCubes }
+pub struct PointCloud { mc: MarchingCubes<Signed> }
 impl PointCloud {
-    pub fn new(size: usize) -> Self { Self { mc: MarchingCubes::new(size) } }
+    pub fn new(size: usize) -> Self { Self { mc: MarchingCubes::<Signed>::new(size) } }
     pub fn extract<S: DeviceSource, E: Extractor>(&mut self, source: &S, extractor: &mut E) {
         let mut prog = Vec::new();
         source.encode(&mut prog);
@@ -219,3 +255,83 @@ impl PointCloud {
         self.mc.deliver(extractor);
     }
 }
+
+/// Many chunks per call (the crate's usage model is one `MarchingCubes::new(size).extract(..)` per chunk,
+/// reference src/marching_cubes.rs:44-45, README.md:19): up to `n_chunks` trees through ONE kernel sequence and one size
+/// read-back.  Chunk b is delivered to `extractors[b]` exactly as a single `extract` of `sources[b]` would.
+pub struct BatchedMarchingCubes { h: *mut isomc_t, n_chunks: usize }
+impl BatchedMarchingCubes {
+    pub fn new(size: usize, n_chunks: usize) -> Self {
+        let mut h = std::ptr::null_mut();
+        let rc = unsafe { isomc_batch_create(size as u32, n_chunks as u32, 0, &mut h) };
+        assert!(rc == 0, "isomc_batch_create failed ({}): {:?}", rc, unsafe { std::ffi::CStr::from_ptr(isomc_last_error(std::ptr::null())) });
+        Self { h, n_chunks }
+    }
+    pub fn extract<S: DeviceSource, E: Extractor>(&mut self, sources: &[S], extractors: &mut [E]) {
+        assert!(!sources.is_empty() && sources.len() <= self.n_chunks && sources.len() == extractors.len());
+        let (mut flat, mut n_nodes) = (Vec::new(), Vec::new());
+        for s in sources {
+            let before = flat.len();
+            s.encode(&mut flat);
+            n_nodes.push((flat.len() - before) as u32);
+        }
+        let check = |rc: i32| assert!(rc == 0, "isomc error {}: {:?}", rc, unsafe { std::ffi::CStr::from_ptr(isomc_last_error(self.h)) });
+        check(unsafe { isomc_extract_sdf_batch(self.h, flat.as_ptr(), n_nodes.as_ptr(), n_nodes.len() as u32) });
+        let (mut nv, mut nt) = (0u64, 0u64);
+        check(unsafe { isomc_counts(self.h, &mut nv, &mut nt, std::ptr::null_mut()) });
+        let (mut xyz, mut idx) = (vec![0f32; 3 * nv as usize], vec![0u32; 3 * nt as usize]);
+        check(unsafe { isomc_copy_out(self.h, xyz.as_mut_ptr(), idx.as_mut_ptr()) });
+        let (mut vo, mut to) = (vec![0u64; self.n_chunks + 1], vec![0u64; self.n_chunks + 1]);
+        check(unsafe { isomc_batch_offsets(self.h, vo.as_mut_ptr(), to.as_mut_ptr()) });
+        for (b, ex) in extractors.iter_mut().enumerate() {
+            for v in xyz[3 * vo[b] as usize..3 * vo[b + 1] as usize].chunks_exact(3) { ex.extract_vertex([v[0], v[1], v[2]]) }
+            for &i in &idx[3 * to[b] as usize..3 * to[b + 1] as usize] { ex.extract_index(i as usize) }
+        }
+    }
+}
+impl Drop for BatchedMarchingCubes { fn drop(&mut self) { unsafe { isomc_destroy(self.h); } } }
+
+/// One extract over several GPUs of the box: z-slabs, one exchange of 3 x u64 per rank on the extraction
+/// streams (peer stores over NVLink when the devices are peers, else an NCCL all-gather inside the library), global ids
+/// written directly.  The delivered mesh is the single-GPU (= reference) mesh.  A one-process-per-GPU host uses the
+/// `isomc_slab_*` functions above instead and brings its own exchange (or `isomc_slab_connect_ipc`).
+pub struct ShardedMarchingCubes { s: *mut isomc_sharded_t, n: usize }
+impl ShardedMarchingCubes {
+    pub fn new(size: usize, devices: &[i32]) -> Self {
+        let mut s = std::ptr::null_mut();
+        let rc = unsafe { isomc_sharded_create(size as u32, devices.len() as u32, devices.as_ptr(), &mut s) };
+        assert!(rc == 0, "isomc_sharded_create failed ({}): {:?}", rc, unsafe { std::ffi::CStr::from_ptr(isomc_sharded_last_error(std::ptr::null())) });
+        Self { s, n: devices.len() }
+    }
+    /// (first sample layer, number of sample layers) rank `r` must be given, on its device
+    pub fn slab(&self, r: usize) -> (usize, usize) {
+        let (mut first, mut count) = (0u32, 0u32);
+        let rc = unsafe { isomc_sharded_slab(self.s, r as u32, std::ptr::null_mut(), std::ptr::null_mut(), &mut first, &mut count) };
+        assert!(rc == 0);
+        (first as usize, count as usize)
+    }
+    pub fn extract<S: DeviceSource, E: Extractor>(&mut self, source: &S, extractor: &mut E) {
+        let mut prog = Vec::new();
+        source.encode(&mut prog);
+        self.check(unsafe { isomc_sharded_extract_sdf(self.s, prog.as_ptr(), prog.len() as u32) });
+        self.deliver(extractor);
+    }
+    /// # Safety: `d_slabs[r]` must be a device pointer on rank r's device to the sample layers `slab(r)` names.
+    pub unsafe fn extract_grid_device<E: Extractor>(&mut self, d_slabs: &[*const f32], extractor: &mut E) {
+        assert_eq!(d_slabs.len(), self.n);
+        self.check(isomc_sharded_extract_grid(self.s, d_slabs.as_ptr()));
+        self.deliver(extractor);
+    }
+    fn deliver<E: Extractor>(&mut self, extractor: &mut E) {
+        let (mut nv, mut nt) = (0u64, 0u64);
+        self.check(unsafe { isomc_sharded_counts(self.s, &mut nv, &mut nt, std::ptr::null_mut()) });
+        let (mut xyz, mut idx) = (vec![0f32; 3 * nv as usize], vec![0u32; 3 * nt as usize]);
+        self.check(unsafe { isomc_sharded_copy_out(self.s, xyz.as_mut_ptr(), idx.as_mut_ptr()) });
+        for v in xyz.chunks_exact(3) { extractor.extract_vertex([v[0], v[1], v[2]]) }
+        for i in idx { extractor.extract_index(i as usize) }
+    }
+    fn check(&self, rc: i32) {
+        assert!(rc == 0, "isomc error {}: {:?}", rc, unsafe { std::ffi::CStr::from_ptr(isomc_sharded_last_error(self.s)) });
+    }
+}
+impl Drop for ShardedMarchingCubes { fn drop(&mut self) { unsafe { isomc_sharded_destroy(self.s); } } }

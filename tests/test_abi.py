@@ -64,3 +64,30 @@ def test_product_never_touches_the_oracle():
         if p.is_file() and p.suffix in (".py", ".cu", ".cuh", ".h", ".hpp", ".cpp"):
             text = p.read_text()
             assert "oracle" not in text.lower() or p.name == "isomc.h" and False, "%s mentions the oracle" % p
+
+
+def test_rust_build_script_lists_every_source():
+    """rust/build.rs is never compiled here (no cargo in the image): at least its source list must be the library's"""
+    from isosurface_b200 import _build
+    text = (ROOT / "rust" / "build.rs").read_text()
+    for src in _build.SOURCES:
+        assert '"%s"' % src in text, "rust/build.rs does not compile %s" % src
+    assert set(re.findall(r'"(isomc_[a-z_]+\.cu)"', text)) == set(_build.SOURCES)
+    for flag in ("arch=compute_100a,code=sm_100a", "-fmad=false"):
+        assert flag in text
+
+
+def test_rust_and_cxx_mirrors_bind_only_declared_symbols():
+    """every isomc_* function the Rust shim declares / the C++ mirror calls exists in include/isomc.h; the sharded, slab and
+    batch entry points are bound in both"""
+    syms = set(declared_symbols())
+    rust = (ROOT / "rust" / "src" / "lib.rs").read_text()
+    rust_fns = set(re.findall(r"\bfn (isomc_[a-z_0-9]+)\s*\(", rust))
+    assert rust_fns and rust_fns <= syms, sorted(rust_fns - syms)
+    cxx = (ROOT / "include" / "isosurface.hpp").read_text()
+    cxx_fns = set(re.findall(r"\b(isomc_[a-z_0-9]+)\s*\(", cxx))
+    assert cxx_fns <= syms, sorted(cxx_fns - syms)
+    for need in ("isomc_sharded_create", "isomc_sharded_extract_grid", "isomc_sharded_counts", "isomc_sharded_copy_out",
+                 "isomc_extract_sdf_batch", "isomc_extract_sdf_directed"):
+        assert need in rust_fns and need in cxx_fns, need
+    assert "isomc_slab_emit_exchanged" in rust_fns and "extract_directed" not in rust  # Directed is the D instantiation of extract
