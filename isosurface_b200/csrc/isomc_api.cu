@@ -48,6 +48,7 @@ struct isomc {
     uint32_t *signs = nullptr, *rowV = nullptr, *rowT = nullptr, *rowA = nullptr;
     unsigned long long *layerTot = nullptr, *totals = nullptr; /* totals: 12 u64 */
     uint32_t *vofs = nullptr, *ticket = nullptr;
+    size_t zero_bytes = 0; /* what the memset at the start of an extract clears: layerTot, the auxiliary words, (list path) rowV/rowT/rowA */
     /* active-cell-list kernels (isomc_cell.cuh) by default; ISOMC_PATH=tile selects the TMA-staged tile path (isomc_tile.cuh):
      * parity-green and profiled, but measured slower on every workload (profiles/r02_tile_path.md) */
     bool tile_mode = false;
@@ -393,7 +394,7 @@ int32_t pipelined_launches(isomc *h, const PipePlan &pp) {
     const uint32_t n = (g.ncl + per - 1) / per;
     h->n_chunks = n;
     for (uint32_t c = 0; c <= n; ++c) h->chunk_l[c] = c * per < g.ncl ? c * per : g.ncl;
-    CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t), h->stream));
+    CU(h, cudaMemsetAsync(h->layerTot, 0, h->zero_bytes, h->stream));
     CU(h, cudaEventRecord(h->ev_pipe0, h->stream));
     CU(h, cudaStreamWaitEvent(h->s_sign, h->ev_pipe0, 0));
     CU(h, cudaStreamWaitEvent(h->s_emit, h->ev_pipe0, 0));
@@ -444,7 +445,7 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
     h->n_chunks = 1;
     h->chunk_l[0] = 0; h->chunk_l[1] = g.ncl;
     if (h->profiling) CU(h, cudaEventRecord(h->ev[0], h->stream));
-    CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t), h->stream));
+    CU(h, cudaMemsetAsync(h->layerTot, 0, h->zero_bytes, h->stream));
     tl_mark(h, "start", 0, h->stream);
     int32_t rc = launch_count_chunk(h, 0, h->stream, nullptr);
     if (rc) return rc;
@@ -635,13 +636,21 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
             /* first guess: 1/32 of the cells active, plus the block every counting warp may strand */
             int32_t lrc = ensure_list_capacity(h, nrows_c * g.ncx / 32 / LIST_BLOCK + isomc_count_list_max_warps(h->sms) + 16);
             if (lrc) return lrc;
-            CU(h, cudaMalloc(&h->rowV, (nrows_c + 4) * sizeof(uint32_t)));
-            CU(h, cudaMalloc(&h->rowT, (nrows_c + 4) * sizeof(uint32_t)));
-            CU(h, cudaMalloc(&h->rowA, (nrows_c + 4) * sizeof(uint32_t)));
+            /* (rowV / rowT / rowA live behind the per-layer totals, see below: one memset per extract zeroes all of it) */
         }
         /* per-layer totals followed by the emit tickets: zeroed by a single memset per extract */
-        CU(h, cudaMalloc(&h->layerTot, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t)));
+        /* list path: the per-row counts follow in the same allocation -- the counting kernel only writes the rows that have active
+         * cells, the others keep the zeros of the memset */
+        h->zero_bytes = ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t);
+        const size_t row_words = h->tile_mode ? 0 : (size_t)((nrows_c + 4 + 3) & ~3ull);
+        CU(h, cudaMalloc(&h->layerTot, h->zero_bytes + 3 * row_words * sizeof(uint32_t)));
         h->ticket = reinterpret_cast<uint32_t *>(h->layerTot + ((size_t)g.ncl * 3 + 4));
+        if (!h->tile_mode) {
+            h->rowV = h->ticket + AUX_WORDS;
+            h->rowT = h->rowV + row_words;
+            h->rowA = h->rowT + row_words;
+            h->zero_bytes += 3 * row_words * sizeof(uint32_t);
+        }
         h->L.ctr = h->ticket + MAX_CHUNKS;
         h->list_marks = h->ticket + MAX_CHUNKS + 1;
         h->chunk_ends = h->ticket + 2 * MAX_CHUNKS + 2;
@@ -702,7 +711,8 @@ int32_t isomc_destroy(isomc_t *h) {
     cudaFree(h->d_progs); cudaFree(h->chunkV); cudaFree(h->chunkT);
     if (h->h_progs) cudaFreeHost(h->h_progs);
     if (h->h_chunk) cudaFreeHost(h->h_chunk);
-    cudaFree(h->signs); cudaFree(h->segA); cudaFree(h->rowV); cudaFree(h->rowT); cudaFree(h->rowA);
+    cudaFree(h->signs); cudaFree(h->segA);
+    if (h->tile_mode) { cudaFree(h->rowV); cudaFree(h->rowT); cudaFree(h->rowA); } /* (list path: part of the layerTot allocation) */
     cudaFree(h->TB.pE); cudaFree(h->TB.pTp); cudaFree(h->TB.pA); cudaFree(h->TB.ent); cudaFree(h->TB.tq); cudaFree(h->TB.tbuf);
     cudaFree(h->layerTot); cudaFree(h->totals); cudaFree(h->vofs); cudaFree(h->tabs);
     cudaFree(h->xyz); cudaFree(h->idx); cudaFree(h->stage_grid);
@@ -880,7 +890,7 @@ int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, 
             for (uint32_t c = 0; c <= n; ++c) h->chunk_l[c] = c * per < g.ncl ? c * per : g.ncl;
         }
         const uint64_t cap_v0 = h->cap_v, cap_t0 = h->cap_t;
-        CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t), h->stream));
+        CU(h, cudaMemsetAsync(h->layerTot, 0, h->zero_bytes, h->stream));
         for (uint32_t c = 0; c < h->n_chunks; ++c) {
             const uint64_t row0 = (uint64_t)(c == 0 ? 0u : h->chunk_l[c] + 1) * g.N, row1 = (uint64_t)(h->chunk_l[c + 1] + 1) * g.N;
             CU(h, cudaMemcpyAsync(h->stage_grid + row0 * g.N, h_grid + row0 * g.N, (row1 - row0) * g.N * sizeof(float),
@@ -997,7 +1007,7 @@ static int32_t points_impl(isomc_t *h) {
     rc = ensure_signs(h);
     if (rc) return rc;
     uint32_t *segA = h->segA;
-    CU(h, cudaMemsetAsync(h->layerTot, 0, ((size_t)g.ncl * 3 + 4) * sizeof(unsigned long long) + AUX_WORDS * sizeof(uint32_t), h->stream));
+    CU(h, cudaMemsetAsync(h->layerTot, 0, h->zero_bytes, h->stream));
     if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, 0, g.nsl * g.N, h->sms, 8, h->stream));
     else CU(h, isomc_launch_sign_sdf(g, h->prog, h->directed, h->signs, 0, g.nsl * g.N, h->sms, 8, h->stream));
     CU(h, isomc_launch_points_count(g, h->signs, segA, h->rowV, h->rowT, h->layerTot, h->sms, h->stream));

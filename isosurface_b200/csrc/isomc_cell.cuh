@@ -691,6 +691,37 @@ ISOMC_HD void load_pair(const Geo &g, const uint32_t *signs, uint32_t row, uint3
     }
 }
 
+/* The scan stage's test on the raw loads: px / py / pt = words 2j, 2j + 1, 2j + 2 of the four sample rows.  A segment is uniform
+ * (no active cell) iff its 4 x 33 samples are all outside or all inside.  Same answers as seg_uniform() on the assembled words;
+ * this is the form the hot loop uses (most passes of a sparse field keep nothing and end here). */
+ISOMC_HD void pair_nonuniform(const uint32_t px[4], const uint32_t py[4], const uint32_t pt[4], bool valid_b, bool &ka, bool &kb) {
+    const uint32_t ox = px[0] | px[1] | px[2] | px[3], ax = px[0] & px[1] & px[2] & px[3];
+    const uint32_t oy = py[0] | py[1] | py[2] | py[3], ay = py[0] & py[1] & py[2] & py[3];
+    const uint32_t ot = (pt[0] | pt[1] | pt[2] | pt[3]) & 1u, at = pt[0] & pt[1] & pt[2] & pt[3] & 1u;
+    const bool ua = ((ox | (oy & 1u)) == 0u) || (ax == 0xFFFFFFFFu && (ay & 1u) != 0u);
+    const bool ub = ((oy | ot) == 0u) || (ay == 0xFFFFFFFFu && at != 0u);
+    ka = !ua;
+    kb = valid_b && !ub;
+}
+
+/* the same loads as load_pair(), left as loaded */
+ISOMC_HD void load_pair_raw(const Geo &g, const uint32_t *signs, uint32_t row, uint32_t lz, uint32_t j, bool valid_b, uint32_t px[4],
+                            uint32_t py[4], uint32_t pt[4]) {
+    const uint32_t *r = signs + (uint64_t)(row + lz) * g.nws + 2 * j; /* sample row lz*N + y = row + lz */
+    const uint64_t dz = (uint64_t)g.N * g.nws;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t *q = r + (k & 1 ? g.nws : 0u) + (k & 2 ? dz : 0u);
+#if defined(__CUDA_ARCH__)
+        const uint2 p = __ldg(reinterpret_cast<const uint2 *>(q));
+#else
+        const uint2 p = *reinterpret_cast<const uint2 *>(q);
+#endif
+        px[k] = p.x; py[k] = p.y;
+        pt[k] = valid_b ? hd_ldg(q + 2) : 0u;
+    }
+}
+
 /* queue the segments a pass keeps: lane order, and within a lane segment a before segment b */
 ISOMC_HD void pair_enqueue(const Warp &w, SegQueue &Q, CountState &S, uint32_t mask_a, uint32_t mask_b, bool keep_a, bool keep_b,
                            const uint32_t wa[8], const uint32_t wb[8], uint32_t row, uint32_t meta_a, uint32_t meta_b) {
@@ -720,11 +751,11 @@ ISOMC_HD void pair_enqueue(const Warp &w, SegQueue &Q, CountState &S, uint32_t m
 #define ISOMC_COUNT_LONG_TASK_AT (1u << 20) /* (the host model is also built with a small value to cover the long-task branch) */
 #endif
 /* Passes per ticket.  Long tasks amortise the ticket round trip on very large lattices (and keep neighbouring rows adjacent in
- * the list); otherwise at most 8, and few enough that every warp draws about five tasks: with 8 passes a 512^3 lattice gave each
- * warp 1.7 tasks and the last round ran half empty (k_count_list 0.134 -> 0.120 ms with 3) */
+ * the list); otherwise at most 8, and few enough that every warp draws about four tasks: with 8 passes a 512^3 lattice gave each
+ * warp 1.7 tasks and the last round ran half empty (k_count_list 0.134 -> 0.120 ms with 3; 0.129 with 2, 0.122 with 4) */
 ISOMC_HD uint32_t count_task_passes(uint32_t n_passes, uint32_t n_warps) {
     if (n_passes > ISOMC_COUNT_LONG_TASK_AT) return 64u;
-    const uint32_t p = n_passes / (5u * (n_warps ? n_warps : 1u));
+    const uint32_t nw = n_warps ? n_warps : 1u, p = (n_passes + 2u * nw) / (4u * nw); /* about four tasks per warp */
     return p < 1u ? 1u : p > 8u ? 8u : p;
 }
 
@@ -754,23 +785,26 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
     if (!WIDE) {
         const uint32_t G = 1u << gshift, rpw = 32u >> gshift, sub = lane >> gshift, j = lane & (G - 1);
         const uint32_t gmask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << (sub << gshift);
+        const bool va_lane = 2 * j < g.nsegx, vb_lane = 2 * j + 1 < g.nsegx;
         const uint32_t niter = (row1 - row0 + rpw - 1) / rpw, P = task_passes ? task_passes : count_task_passes(niter, n_warps);
         for (uint32_t task = next_task(w, ticket); task * P < niter; task = next_task(w, ticket))
         for (uint32_t it = task * P; it < niter && it < (task + 1) * P; ++it) {
+            /* (rows without active cells are not written at all: rowV / rowT / rowA are zeroed before the launch) */
             const uint32_t row = row0 + it * rpw + sub;
-            const bool va = row < row1 && 2 * j < g.nsegx, vb = row < row1 && 2 * j + 1 < g.nsegx;
-            uint32_t wa[8], wb[8];
+            uint32_t px[4], py[4], pt[4];
             bool ka = false, kb = false;
-            if (va) {
+            if (row < row1 && va_lane) {
                 const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40);
-                load_pair(g, signs, row, lz, j, vb, wa, wb);
-                const bool dead = geo_dead(g, lz); /* (batched chunks: the layer between two lattices has no cells) */
-                ka = !dead && !seg_uniform(wa);
-                kb = !dead && vb && !seg_uniform(wb);
+                load_pair_raw(g, signs, row, lz, j, vb_lane, px, py, pt);
+                pair_nonuniform(px, py, pt, vb_lane, ka, kb);
+                if (g.zper && geo_dead(g, lz)) ka = kb = false; /* (batched chunks: the layer between two lattices has no cells) */
             }
-            const uint32_t ma = w_ballot(w, ka), mb = w_ballot(w, kb), rany = (ma | mb) & gmask;
-            if (j == 0 && row < row1 && rany == 0) { out.rowV[row] = 0; out.rowT[row] = 0; out.rowA[row] = 0; }
+            const uint32_t ma = w_ballot(w, ka), mb = w_ballot(w, kb);
             if ((ma | mb) == 0) continue;
+            const uint32_t rany = (ma | mb) & gmask;
+            uint32_t wa[8], wb[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { wa[2 * k] = px[k]; wa[2 * k + 1] = py[k]; wb[2 * k] = py[k]; wb[2 * k + 1] = pt[k]; }
             uint32_t meta_a = 2 * j, meta_b = 2 * j + 1;
             if (ka || kb) {
                 if (hd_ffs0(rany) == lane) { if (ka) meta_a |= SEGQ_FIRST; else meta_b |= SEGQ_FIRST; }
@@ -790,15 +824,17 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
             for (uint32_t s0 = 0; s0 < g.nsegx; s0 += 64) {
                 const uint32_t j = (s0 >> 1) + lane;
                 const bool va = 2 * j < g.nsegx, vb = 2 * j + 1 < g.nsegx;
-                uint32_t wa[8], wb[8];
+                uint32_t px[4], py[4], pt[4];
                 bool ka = false, kb = false;
-                if (va) {
-                    load_pair(g, signs, row, lz, j, vb, wa, wb);
-                    ka = !dead && !seg_uniform(wa);
-                    kb = !dead && vb && !seg_uniform(wb);
+                if (va && !dead) {
+                    load_pair_raw(g, signs, row, lz, j, vb, px, py, pt);
+                    pair_nonuniform(px, py, pt, vb, ka, kb);
                 }
                 const uint32_t ma = w_ballot(w, ka), mb = w_ballot(w, kb);
                 if ((ma | mb) == 0) continue;
+                uint32_t wa[8], wb[8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { wa[2 * k] = px[k]; wa[2 * k + 1] = py[k]; wb[2 * k] = py[k]; wb[2 * k + 1] = pt[k]; }
                 uint32_t meta_a = 2 * j, meta_b = 2 * j + 1;
                 if (!row_has && (ka || kb) && hd_ffs0(ma | mb) == lane) { if (ka) meta_a |= SEGQ_FIRST; else meta_b |= SEGQ_FIRST; }
                 pair_enqueue(w, Q, S, ma, mb, ka, kb, wa, wb, row, meta_a, meta_b);
@@ -806,9 +842,8 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
                 last_seq = S.enq - 1;
                 while (S.enq - S.deq >= 32) count_flush(w, g, s_ntri, nth8, L, out, Q, S, 32);
             }
-            /* end of the row: close it */
+            /* end of the row: close it (a row without active cells keeps the zeros it was given before the launch) */
             if (!row_has) {
-                if (lane == 0) { out.rowV[row] = 0; out.rowT[row] = 0; out.rowA[row] = 0; }
             } else if ((int32_t)(last_seq - S.deq) >= 0) { /* its last segment still waits: mark it */
                 if (lane == 0) Q.meta[last_seq & (SEGQ_CAP - 1)] |= SEGQ_LAST;
                 w_sync(w);

@@ -388,7 +388,7 @@ cudaError_t isomc_launch_sign_sdf(const Geo &g, const SdfProgram &prog, bool dir
 cudaError_t isomc_launch_scan(const Geo &g, uint32_t ppl, uint32_t *rowV, uint32_t *rowT, const unsigned long long *layerTot,
                               unsigned long long *totals, const uint32_t *list_ctr, uint32_t *list_mark, uint32_t *chunk_end,
                               uint32_t lz0, uint32_t lz1, cudaStream_t st) {
-    return isomc_launch(k_scan_rows, lz1 - lz0, 256, st, true, g, ppl, rowV, rowT, layerTot, totals, list_ctr, list_mark, chunk_end, lz0);
+    return isomc_launch(k_scan_rows, lz1 - lz0, 256, st, isomc_pdl_for((unsigned long long)g.N * g.N * g.nsl), g, ppl, rowV, rowT, layerTot, totals, list_ctr, list_mark, chunk_end, lz0);
 }
 cudaError_t isomc_launch_chunk_bases(uint32_t n, unsigned long long *totals, const uint32_t *list_ctr, uint32_t *chunkV, uint32_t *chunkT,
                                      cudaStream_t st) {

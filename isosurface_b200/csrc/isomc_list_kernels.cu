@@ -123,7 +123,7 @@ cudaError_t launch_emit_list(const Src &src, const Geo &g, const ListBufs &L, co
                              int sms, cudaStream_t st, int grid_bps) {
     const int minb = emit_list_minb();
     const uint32_t grid = (uint32_t)(sms * (grid_bps > 0 && grid_bps < minb ? grid_bps : minb));
-#define ISOMC_EMIT_LAUNCH(M) isomc_launch(k_emit_list<Src, M>, grid, LIST_BLOCK, st, true, src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, (unsigned long long)cap_v, (unsigned long long)cap_t, blk_first, blk_end)
+#define ISOMC_EMIT_LAUNCH(M) isomc_launch(k_emit_list<Src, M>, grid, LIST_BLOCK, st, isomc_pdl_for((unsigned long long)g.N * g.N * g.nsl), src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, (unsigned long long)cap_v, (unsigned long long)cap_t, blk_first, blk_end)
     switch (minb) {
     case 4: return ISOMC_EMIT_LAUNCH(4);
     case 6: return ISOMC_EMIT_LAUNCH(6);
@@ -154,9 +154,9 @@ static void launch_count_list_v(uint32_t grid, cudaStream_t st, const Geo &g, co
     static int tp = -1; /* ISOMC_COUNT_TASK: passes per ticket (0 = count_task_passes()) */
     if (tp < 0) { const char *p = getenv("ISOMC_COUNT_TASK"); tp = p ? atoi(p) : 0; if (tp < 0) tp = 0; }
     switch (count_list_minb()) {
-    default: isomc_launch(k_count_list<WIDE, 4>, grid, 256, st, true, g, signs, ntri, L, out, gshift, row0, row1, ticket, (uint32_t)tp); break;
-    case 6: isomc_launch(k_count_list<WIDE, 6>, grid, 256, st, true, g, signs, ntri, L, out, gshift, row0, row1, ticket, (uint32_t)tp); break;
-    case 5: isomc_launch(k_count_list<WIDE, 5>, grid, 256, st, true, g, signs, ntri, L, out, gshift, row0, row1, ticket, (uint32_t)tp); break;
+    default: isomc_launch(k_count_list<WIDE, 4>, grid, 256, st, isomc_pdl_for((unsigned long long)g.N * g.N * g.nsl), g, signs, ntri, L, out, gshift, row0, row1, ticket, (uint32_t)tp); break;
+    case 6: isomc_launch(k_count_list<WIDE, 6>, grid, 256, st, isomc_pdl_for((unsigned long long)g.N * g.N * g.nsl), g, signs, ntri, L, out, gshift, row0, row1, ticket, (uint32_t)tp); break;
+    case 5: isomc_launch(k_count_list<WIDE, 5>, grid, 256, st, isomc_pdl_for((unsigned long long)g.N * g.N * g.nsl), g, signs, ntri, L, out, gshift, row0, row1, ticket, (uint32_t)tp); break;
     }
 }
 

@@ -213,7 +213,8 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
     memset(segrec.data(), 0xEE, segrec.size() * sizeof(uint2));
     uint32_t ctr = 0;
     ListBufs L{ent.data(), ent_yz.data(), segrec.data(), segtpre.data(), blkfill.data(), &ctr, cap_blocks, nullptr, nullptr};
-    std::vector<uint32_t> rowV(nrows_c + 4, 0xDEADBEEFu), rowT(nrows_c + 4, 0xDEADBEEFu), rowA(nrows_c + 4, 0xDEADBEEFu);
+    /* zeroed before the count, as the library's memset does: the kernel only writes the rows that have active cells */
+    std::vector<uint32_t> rowV(nrows_c + 4, 0u), rowT(nrows_c + 4, 0u), rowA(nrows_c + 4, 0u);
     std::vector<unsigned long long> layerTot((size_t)g.ncl * 3 + 4, 0ull);
     CountOut out{rowV.data(), rowT.data(), rowA.data(), layerTot.data()};
 
@@ -260,10 +261,6 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
             V = 0; T = 0;
         }
         rowPV[r] = (uint32_t)V; rowPT[r] = (uint32_t)T;
-        if (rowV[r] == 0xDEADBEEFu || rowT[r] == 0xDEADBEEFu || rowA[r] == 0xDEADBEEFu) {
-            fprintf(stderr, "list_model: row %llu totals not written (V %x T %x A %x)\n", (unsigned long long)r, rowV[r], rowT[r], rowA[r]);
-            return -2;
-        }
         V += rowV[r]; T += rowT[r]; Act += rowA[r];
     }
     rowPV[nrows_c] = (uint32_t)V; rowPT[nrows_c] = (uint32_t)T;
