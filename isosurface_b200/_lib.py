@@ -9,7 +9,8 @@ from pathlib import Path
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libisomc_b200.so"
+import os
+LIB_PATH = Path(os.environ["ISOMC_LIB"]) if os.environ.get("ISOMC_LIB") else PKG / "libisomc_b200.so"  # (ISOMC_LIB: experiment builds)
 
 OK = 0
 ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_INDEX_OVERFLOW, ERR_UNSUPPORTED_SOURCE, ERR_NO_RESULT, ERR_NCCL = -1, -2, -3, -4, -5, -6, -7

@@ -585,6 +585,7 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
             return fail(nullptr, ISOMC_ERR_BAD_ARG, "batched chunks need size >= 2");
         }
         g.zper = size + 1;
+        g.zmagic = geo_zmagic(g.zper);
         g.ncl = batch * (size + 1) - 1;
         g.nsl = g.ncl + 1;
         if ((uint64_t)g.ncl * g.ncx >= (1ull << 26) || batch > 65535u) {

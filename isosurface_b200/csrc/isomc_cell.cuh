@@ -121,8 +121,8 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
     const uint32_t vid = A.rowPV[row] + (ea.x & 0xFFFFu);
     const uint32_t gz = geo_z(g, lz);
     /* id -> output slot: a slab drops its ghost layer's vertices; batched chunks keep chunk-local ids and add the chunk's base */
-    const uint32_t vbase = L.chunkV ? L.chunkV[lz / g.zper] : 0u - A.ghostV;
-    const uint32_t tbase = L.chunkT ? L.chunkT[lz / g.zper] : 0u - A.ghostT;
+    uint32_t vbase = 0u - A.ghostV, tbase = 0u - A.ghostT;
+    if (L.chunkV) { const uint32_t b = geo_chunk(g, lz); vbase = L.chunkV[b]; tbase = L.chunkT[b]; }
     /* slot of the cell's first triangle: requested here, with the first wave of loads (the compiler will not move these loads
      * up across the vertex stores below by itself) */
     const uint32_t tslot32 = A.rowPT[row] + L.segtpre[(uint64_t)row * g.nsegx + (x >> 5)] + (ea.x >> 16) + tbase;
@@ -257,12 +257,18 @@ ISOMC_HD void emit_cell(const Geo &g, const Src &src, const EmitTab &T, const Li
     uint32_t nt = T.ntri[ci];
     if (tslot >= A.cap_t) nt = 0;
     else if (tslot + nt > A.cap_t) nt = (uint32_t)(A.cap_t - tslot);
-    uint64_t tri = T.tri[ci];
+    const uint64_t tri = T.tri[ci];
     uint32_t *o = A.idx + 3 * tslot;
-    for (uint32_t t = 0; t < nt; ++t, tri >>= 12, o += 3) {
-        o[0] = eid[((uint32_t)tri & 15u) * eid_stride] + A.vofs;
-        o[1] = eid[((uint32_t)tri >> 4 & 15u) * eid_stride] + A.vofs;
-        o[2] = eid[((uint32_t)tri >> 8 & 15u) * eid_stride] + A.vofs;
+    /* at most five triangles per case: unrolled, so that the shifts and the store offsets are immediates and nothing is carried
+     * from one triangle to the next (the rolled loop cost 31 instructions per triangle, most of them bookkeeping) */
+#pragma unroll
+    for (uint32_t t = 0; t < 5; ++t) {
+        if (t < nt) {
+            const uint32_t c = (uint32_t)(tri >> (12 * t)) & 0xFFFu;
+            o[3 * t + 0] = eid[(c & 15u) * eid_stride] + A.vofs;
+            o[3 * t + 1] = eid[(c >> 4 & 15u) * eid_stride] + A.vofs;
+            o[3 * t + 2] = eid[(c >> 8) * eid_stride] + A.vofs;
+        }
     }
 }
 

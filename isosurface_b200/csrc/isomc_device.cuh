@@ -84,12 +84,22 @@ struct Geo {
     uint64_t row_magic; /* ceil(2^40 / ncx): row / ncx == (row * row_magic) >> 40 for row < 2^26, ncx < 2^13 */
     uint32_t zper;   /* 0, or (batched chunks) sample layers per chunk = N+1: the handle's layers are B lattices stacked in z;
                         layer l belongs to chunk l / zper at z = l % zper, and cell layer z = zper-1 (between two chunks) is dead */
-    uint32_t pad_;
+    uint32_t zmagic; /* 0, or ceil(2^32 / zper): l / zper == (l * zmagic) >> 32 for l * (zper + 1) < 2^32 (no division in the kernels) */
 };
 
 /* z of a (cell or sample) layer within its lattice: what the reference's loop variable is (primal_grid.rs:59-67) */
-ISOMC_HD uint32_t geo_z(const Geo &g, uint32_t lz) { return g.zper ? lz % g.zper : g.gz0 + lz; }
-ISOMC_HD bool geo_dead(const Geo &g, uint32_t lz) { return g.zper != 0 && lz % g.zper == g.zper - 1; }
+/* chunk of a layer of a batch handle (0 otherwise): multiply-high, no division (an integer division per list entry cost the
+ * emission kernel 9 % of its instructions) */
+ISOMC_HD uint32_t geo_chunk(const Geo &g, uint32_t lz) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(lz, g.zmagic);
+#else
+    return (uint32_t)(((uint64_t)lz * g.zmagic) >> 32);
+#endif
+}
+ISOMC_HD uint32_t geo_z(const Geo &g, uint32_t lz) { return g.gz0 + lz - geo_chunk(g, lz) * g.zper; } /* (a batch handle has gz0 == 0) */
+ISOMC_HD bool geo_dead(const Geo &g, uint32_t lz) { return g.zper != 0 && lz - geo_chunk(g, lz) * g.zper == g.zper - 1; }
+static inline uint32_t geo_zmagic(uint32_t zper) { return zper ? (uint32_t)(((1ull << 32) + zper - 1) / zper) : 0u; }
 
 struct SdfProgram {
     isomc_sdf_node nodes[ISOMC_SDF_MAX_NODES];
@@ -385,7 +395,7 @@ struct SdfChainSrc {
 struct SdfBatchSrc {
     const SdfProgram *progs;
     __device__ __forceinline__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
-        const uint32_t b = lz / g.zper;
+        const uint32_t b = geo_chunk(g, lz);
         return sdf_eval(progs[b], __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv), __fmul_rn((float)(lz - b * g.zper), g.inv));
     }
     ISOMC_SCALAR_EDGE_SAMPLES

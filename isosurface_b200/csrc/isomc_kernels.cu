@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t ppl, uint32_t
     __shared__ unsigned long long s_base[2];
     const uint32_t lz = lz_first + blockIdx.x;
     /* base = sum of the totals of the layers below (batched chunks: of the layers below in the same lattice, ids are chunk-local) */
-    const uint32_t l_first = g.zper ? lz - lz % g.zper : 0u;
+    const uint32_t l_first = geo_chunk(g, lz) * g.zper; /* (0 unless the handle is a batch) */
     unsigned long long bv = 0, bt = 0, ba = 0;
     for (uint32_t l = l_first + threadIdx.x; l < lz; l += blockDim.x) {
         bv += layerTot[3 * l];
@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(256) k_scan_rows(Geo g, uint32_t ppl, uint32_t
         chunk_end[0] = (uint32_t)(tv + layerTot[3 * lz]);
         chunk_end[1] = (uint32_t)(tt + layerTot[3 * lz + 1]);
     }
-    if (g.zper && lz % g.zper == g.zper - 2 && threadIdx.x == 0) { /* last cell layer of a lattice of the batch: its totals */
-        unsigned long long *ct = totals + 16 + 3 * (size_t)(lz / g.zper);
+    if (g.zper && lz - geo_chunk(g, lz) * g.zper == g.zper - 2 && threadIdx.x == 0) { /* last cell layer of a lattice of the batch: its totals */
+        unsigned long long *ct = totals + 16 + 3 * (size_t)geo_chunk(g, lz);
         ct[0] = tv + layerTot[3 * lz]; ct[1] = tt + layerTot[3 * lz + 1]; ct[2] = ta + layerTot[3 * lz + 2];
     }
     if (lz == g.ncl - 1 && threadIdx.x == 0 && !g.zper) {

@@ -179,9 +179,10 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
     g.nsl = g.ncl + 1;
     g.inv = 1.0f / (float)(size - 1);
     g.row_magic = g.ncx ? ((1ull << 40) + g.ncx - 1) / g.ncx : 0;
-    g.zper = 0; g.pad_ = 0;
+    g.zper = 0; g.zmagic = 0;
     if (batch) { /* `batch` whole lattices stacked in z (isomc_batch_create): the cell layer between two of them is dead */
         g.zper = size + 1;
+        g.zmagic = geo_zmagic(g.zper);
         g.ncl = batch * (size + 1) - 1;
         g.nsl = g.ncl + 1;
     }

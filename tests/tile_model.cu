@@ -173,7 +173,7 @@ int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const Src &sr
     g.nsl = g.ncl + 1;
     g.inv = 1.0f / (float)(size - 1);
     g.row_magic = g.ncx ? ((1ull << 40) + g.ncx - 1) / g.ncx : 0;
-    g.zper = 0; g.pad_ = 0;
+    g.zper = 0; g.zmagic = 0;
     memset(out_totals, 0, 8 * sizeof(uint64_t));
     if (g.ncl == 0) return 0;
     const TileGeo tg = tile_geo(g);
