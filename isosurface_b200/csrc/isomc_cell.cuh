@@ -756,13 +756,17 @@ ISOMC_HD void pair_enqueue(const Warp &w, SegQueue &Q, CountState &S, uint32_t m
 #ifndef ISOMC_COUNT_LONG_TASK_AT
 #define ISOMC_COUNT_LONG_TASK_AT (1u << 20) /* (the host model is also built with a small value to cover the long-task branch) */
 #endif
-/* Passes per ticket.  Long tasks amortise the ticket round trip on very large lattices (and keep neighbouring rows adjacent in
- * the list); otherwise at most 8, and few enough that every warp draws about four tasks: with 8 passes a 512^3 lattice gave each
- * warp 1.7 tasks and the last round ran half empty (k_count_list 0.134 -> 0.120 ms with 3; 0.129 with 2, 0.122 with 4) */
-ISOMC_HD uint32_t count_task_passes(uint32_t n_passes, uint32_t n_warps) {
+/* Passes per ticket, from what was measured on a B200 (profiles/r02_history.md: count-task sweeps on whole lattices and on the
+ * slabs of an 8-way split): a task should cover about 16 consecutive cell rows while a pass holds several rows (512^3: 0.120 ms
+ * with 3-4 passes of 4 rows, 0.134 with 8; 1024^3: 0.616 ms with 8 passes of 2 rows, 0.643 with 27), and 64 rows once a row fills
+ * the warp (2048^3: 1.37 ms with 64, 1.89 with 27, 2.73 with 4; one rank's eighth of it: 0.246 / 0.307 / 0.427 ms with 64 / 32 / 8)
+ * -- but never so many that the warps in flight get fewer than two tasks each. */
+ISOMC_HD uint32_t count_task_passes(uint32_t n_passes, uint32_t n_warps, uint32_t rows_per_pass) {
     if (n_passes > ISOMC_COUNT_LONG_TASK_AT) return 64u;
-    const uint32_t nw = n_warps ? n_warps : 1u, p = (n_passes + 2u * nw) / (4u * nw); /* about four tasks per warp */
-    return p < 1u ? 1u : p > 8u ? 8u : p;
+    const uint32_t want = rows_per_pass <= 1u ? 64u : (16u + rows_per_pass - 1u) / rows_per_pass;
+    const uint32_t fair = n_passes / (2u * (n_warps ? n_warps : 1u));
+    const uint32_t p = want < fair ? want : fair;
+    return p < 1u ? 1u : p;
 }
 
 ISOMC_HD uint32_t next_task(const Warp &w, uint32_t *ticket) {
@@ -792,7 +796,7 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
         const uint32_t G = 1u << gshift, rpw = 32u >> gshift, sub = lane >> gshift, j = lane & (G - 1);
         const uint32_t gmask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << (sub << gshift);
         const bool va_lane = 2 * j < g.nsegx, vb_lane = 2 * j + 1 < g.nsegx;
-        const uint32_t niter = (row1 - row0 + rpw - 1) / rpw, P = task_passes ? task_passes : count_task_passes(niter, n_warps);
+        const uint32_t niter = (row1 - row0 + rpw - 1) / rpw, P = task_passes ? task_passes : count_task_passes(niter, n_warps, rpw);
         for (uint32_t task = next_task(w, ticket); task * P < niter; task = next_task(w, ticket))
         for (uint32_t it = task * P; it < niter && it < (task + 1) * P; ++it) {
             /* (rows without active cells are not written at all: rowV / rowT / rowA are zeroed before the launch) */
@@ -820,7 +824,7 @@ ISOMC_HD void count_list_warp(const Warp &w, const Geo &g, const uint32_t *signs
             while (S.enq - S.deq >= 32) count_flush(w, g, s_ntri, nth8, L, out, Q, S, 32);
         }
     } else {
-        const uint32_t nrow = row1 - row0, P = task_passes ? task_passes : count_task_passes(nrow, n_warps);
+        const uint32_t nrow = row1 - row0, P = task_passes ? task_passes : count_task_passes(nrow, n_warps, 1u);
         for (uint32_t task = next_task(w, ticket); task * P < nrow; task = next_task(w, ticket))
         for (uint32_t row = row0 + task * P; row < row1 && row < row0 + (task + 1) * P; ++row) {
             const uint32_t lz = (uint32_t)(((uint64_t)row * g.row_magic) >> 40);

@@ -105,15 +105,18 @@ inline uint32_t grid_for(uint64_t warps_needed, int sms, int warps_per_block, in
     return (uint32_t)(blocks < 1 ? 1 : blocks);
 }
 
-/* CTAs per SM of k_emit_list: register budget vs. warps in flight (ISOMC_EMIT_MINB = 4, 5 or 6; default 5) */
-static int emit_list_minb() {
-    static int v = 0;
-    if (v == 0) {
+/* CTAs per SM of k_emit_list, i.e. the register budget vs. the warps in flight (ISOMC_EMIT_MINB = 4, 5 or 6).  Default: 5
+ * (48 registers); 4 (64 registers) on lattices wider than 1024, where the kernel is bound by the sample gathers and more warps
+ * in flight only thrash (2048^3: 1.39 ms with 5, 1.25 ms with 4; 1024^3: 1.27 with 5, 1.30 with 4).  CTAs of 128 threads (twice
+ * as many) were measured too: slower at 512^3 and 1024^3 (profiles/r02_history.md). */
+static int emit_list_minb(const Geo &g) {
+    static int v = -1;
+    if (v < 0) {
         const char *p = getenv("ISOMC_EMIT_MINB");
-        v = p ? atoi(p) : 5;
-        if (v != 4 && v != 5 && v != 6) v = 5;
+        v = p ? atoi(p) : 0;
+        if (v != 4 && v != 5 && v != 6) v = 0;
     }
-    return v;
+    return v ? v : (g.N > 1024 ? 4 : 5);
 }
 
 template <class Src>
@@ -121,7 +124,7 @@ cudaError_t launch_emit_list(const Src &src, const Geo &g, const ListBufs &L, co
                              const uint32_t *rowPT, const unsigned long long *layerTot, const uint32_t *vofs, float *xyz,
                              uint32_t *idx, uint64_t cap_v, uint64_t cap_t, const uint32_t *blk_first, const uint32_t *blk_end,
                              int sms, cudaStream_t st, int grid_bps) {
-    const int minb = emit_list_minb();
+    const int minb = emit_list_minb(g);
     const uint32_t grid = (uint32_t)(sms * (grid_bps > 0 && grid_bps < minb ? grid_bps : minb));
 #define ISOMC_EMIT_LAUNCH(M) isomc_launch(k_emit_list<Src, M>, grid, LIST_BLOCK, st, isomc_pdl_for((unsigned long long)g.N * g.N * g.nsl), src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, (unsigned long long)cap_v, (unsigned long long)cap_t, blk_first, blk_end)
     switch (minb) {

@@ -235,7 +235,8 @@ static int model_extract(uint32_t size, uint32_t z_begin, uint32_t z_end, const 
      * to a random emulated warp, and the warps run one after the other in shuffled order */
     uint32_t ticket = 0;
     const uint32_t npass = npair > 32 ? (uint32_t)nrows_c : (uint32_t)((nrows_c + (32u >> gshift) - 1) / (32u >> gshift));
-    const uint32_t ntask = (npass + count_task_passes(npass, n_warps) - 1) / count_task_passes(npass, n_warps);
+    const uint32_t tp = count_task_passes(npass, n_warps, npair > 32 ? 1u : 32u >> gshift);
+    const uint32_t ntask = (npass + tp - 1) / tp;
     std::vector<std::vector<uint32_t>> share(n_warps);
     for (uint32_t t = 0; t < ntask; ++t) {
         st = st * 6364136223846793005ull + 1442695040888963407ull;
