@@ -141,6 +141,10 @@ int32_t isomc_points_grid_host(isomc_t *h, const float *h_grid);
 
 /* ---- results:  the two Vecs behind extractor::IndexedVertices --------------------------- */
 int32_t isomc_counts(isomc_t *h, uint64_t *n_vertices, uint64_t *n_triangles, uint64_t *n_active_cells);
+/* the same per cell layer of the last extract: counts[3 * l + 0 / 1 / 2] = vertices created / triangles / active cells of layer
+ * z_begin + l, for the handle's own layers (size of them; a slab: z_end - z_begin).  What a host needs to cut z-slabs of equal
+ * WORK instead of equal thickness for the next extracts of a similar field (isosurface_b200/sharded.py: balanced_slabs). */
+int32_t isomc_layer_counts(isomc_t *h, uint64_t *counts);
 int32_t isomc_device_buffers(isomc_t *h, const float **d_xyz, const uint32_t **d_idx);
 int32_t isomc_copy_out(isomc_t *h, float *xyz /* 3*V */, uint32_t *idx /* 3*T */);
 /* extractor::IndexedInterleavedNormals (reference src/extractor.rs:95-127) for a `CentralDifference` source around an

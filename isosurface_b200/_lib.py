@@ -58,6 +58,7 @@ SIGNATURES = {
     "isomc_points_grid_device": (_I32, [_P, _P]),
     "isomc_points_grid_host": (_I32, [_P, _P]),
     "isomc_counts": (_I32, [_P, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
+    "isomc_layer_counts": (_I32, [_P, _P]),
     "isomc_device_buffers": (_I32, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "isomc_copy_out": (_I32, [_P, _P, _P]),
     "isomc_copy_out_interleaved_normals": (_I32, [_P, _P, _U32, C.c_float, _P, _P]),

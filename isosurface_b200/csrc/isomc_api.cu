@@ -1068,6 +1068,20 @@ int32_t isomc_counts(isomc_t *h, uint64_t *n_vertices, uint64_t *n_triangles, ui
     return ISOMC_OK;
 }
 
+/* per cell layer of the last extract: {vertices created, triangles, active cells}; a slab reports its own layers only */
+int32_t isomc_layer_counts(isomc_t *h, uint64_t *counts) {
+    if (!h || !counts) return ISOMC_ERR_BAD_ARG;
+    if (!h->have_result) return fail(h, ISOMC_ERR_NO_RESULT, "no extract has completed on this handle");
+    if (h->tile_mode || h->batch) return fail(h, ISOMC_ERR_BAD_ARG, "per-layer counts are kept by whole-lattice and slab handles of the list path");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    const uint32_t n = h->g.ncl - h->g.ghost;
+    if (n == 0) return ISOMC_OK;
+    CU(h, cudaMemcpyAsync(counts, h->layerTot + 3 * (size_t)h->g.ghost, 3 * (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return ISOMC_OK;
+}
+
 int32_t isomc_device_buffers(isomc_t *h, const float **d_xyz, const uint32_t **d_idx) {
     if (!h) return ISOMC_ERR_BAD_ARG;
     if (!h->have_result) return fail(h, ISOMC_ERR_NO_RESULT, "no extract has completed on this handle");

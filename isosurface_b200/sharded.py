@@ -31,6 +31,33 @@ def slab_sample_layers(size, rank, world):
     return z0 - ghost, (z1 - z0) + ghost + 1
 
 
+# cost of one active cell in units of one lattice sample, measured on a B200 (profiles/r02_history.md: an eighth of the 2048^3
+# sphere field costs 0.85 ms + 0.06 ms per million active cells; 0.85 ms / (256 * 2048^2 samples) = 0.79 ps per sample)
+ACTIVE_CELL_COST = 76.0
+
+
+def balanced_slabs(size, layer_active, world, active_cell_cost=ACTIVE_CELL_COST):
+    """Contiguous cell-layer ranges [(z0, z1)] * world of (nearly) equal WORK instead of equal thickness.
+
+    layer_active[z] = active cells of cell layer z in an earlier extract of a similar field (isomc_layer_counts; all-gathered
+    over the ranks of the earlier split).  Work of a layer = size^2 samples to stream + active_cell_cost per active cell
+    (classification, list entry, look-ups, vertices and triangles).  Every rank gets at least one layer; boundaries are the
+    points where the running work crosses k / world of the total."""
+    a = np.asarray(layer_active, dtype=np.float64)
+    if a.shape != (size,) or world < 1 or world > size:
+        raise ValueError("need one count per cell layer (%d) and 1 <= world <= size" % size)
+    work = float(size) * float(size) + active_cell_cost * a
+    cum = np.concatenate([[0.0], np.cumsum(work)])
+    cuts = [0]
+    for k in range(1, world):
+        z = int(np.searchsorted(cum, cum[-1] * k / world, side="left"))
+        z = max(z, cuts[-1] + 1)            # at least one layer per rank ...
+        z = min(z, size - (world - k))      # ... including the ranks still to come
+        cuts.append(z)
+    cuts.append(size)
+    return [(cuts[k], cuts[k + 1]) for k in range(world)]
+
+
 def bases_from_totals(gathered, rank):
     """gathered: (G, 3) integer array of per-rank {V, V_before_last_layer, T}.
     Returns (vertex_base, boundary_base, triangle_base) of `rank`:
@@ -62,12 +89,13 @@ def allgather_totals(totals, group=None):
 
 
 class SlabMarchingCubes:
-    """One rank's share of a sharded extract.  `extract(d_slab_ptr)` runs count -> all-gather -> emit."""
+    """One rank's share of a sharded extract.  `extract(d_slab_ptr)` runs count -> all-gather -> emit.
+    z_range: the rank's cell layers (default: the equal split `slab_range`; `balanced_slabs` gives a split of equal work)."""
 
-    def __init__(self, size, rank, world, device=0):
+    def __init__(self, size, rank, world, device=0, z_range=None):
         lib = _lib.load()
         self.size, self.rank, self.world, self.device = int(size), int(rank), int(world), int(device)
-        self.z0, self.z1 = slab_range(size, rank, world)
+        self.z0, self.z1 = slab_range(size, rank, world) if z_range is None else (int(z_range[0]), int(z_range[1]))
         self._h = C.c_void_p()
         _lib.check(lib.isomc_slab_create(self.size, self.z0, self.z1, self.device, C.byref(self._h)))
         self._lib = lib
@@ -108,6 +136,13 @@ class SlabMarchingCubes:
         idx = np.empty(t.value * 3, np.uint32)
         _lib.check(self._lib.isomc_copy_out(self._h, xyz.ctypes.data, idx.ctypes.data), self._h)
         return xyz, idx
+
+    def layer_active_cells(self):
+        """active cells of each of this rank's cell layers in the last extract (input of `balanced_slabs`)"""
+        n = self.z1 - self.z0
+        buf = np.zeros(3 * n, np.uint64)
+        _lib.check(self._lib.isomc_layer_counts(self._h, buf.ctypes.data), self._h)
+        return buf.reshape(n, 3)[:, 2].copy()
 
     # ---- the exchange as peer stores over NVLink (no collective call per step) ----------------
     def connect_peers(self, group=None):

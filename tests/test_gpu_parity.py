@@ -294,6 +294,42 @@ def test_slab_emit_gathered_on_stream(iso, oracle, isolib):
     assert mesh_diff(np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), oxyz, oidx) == ""
 
 
+def test_layer_counts_and_slabs_of_equal_work(iso, oracle, isolib):
+    """isomc_layer_counts reports the per-layer totals of the last extract (whole lattice == the slabs' layers put together), and
+    slabs of UNEQUAL thickness cut by sharded.balanced_slabs still concatenate to the reference mesh"""
+    from isosurface_b200 import _lib
+    from isosurface_b200.sharded import SlabMarchingCubes, balanced_slabs, bases_from_totals, slab_range
+    size, world = 48, 4
+    t = synth(iso, 3, size, 11)  # sphere union: the surface is unevenly spread over z
+    host = t.cpu().numpy().reshape(size + 1, size, size)
+    oxyz, oidx, oact = oracle.extract_grid(size, host)
+    mc = iso.MarchingCubes(size)
+    mc.extract_device(iso.DenseGrid(t))
+    whole = np.zeros(3 * size, np.uint64)
+    _lib.check(isolib.isomc_layer_counts(mc._h, whole.ctypes.data), mc._h)
+    whole = whole.reshape(size, 3)
+    assert [int(x) for x in whole.sum(axis=0)] == [len(oxyz) // 3, len(oidx) // 3, oact]
+    ci = oracle.cube_indices(size, host)
+    act_ref = ((ci != 0) & (ci != 255)).reshape(size, -1).sum(axis=1)
+    assert np.array_equal(whole[:, 2].astype(np.int64), act_ref)
+    mc.close()
+    slabs = balanced_slabs(size, whole[:, 2], world, active_cell_cost=400.0)  # (a small lattice: exaggerate the surface cost)
+    assert slabs != [slab_range(size, r, world) for r in range(world)]
+    parts, totals, hs = [], [], []
+    for r in range(world):
+        s = SlabMarchingCubes(size, r, world, z_range=slabs[r])
+        first = slabs[r][0] - (1 if slabs[r][0] > 0 else 0)
+        totals.append(s.count(t.data_ptr() + 4 * first * size * size))
+        hs.append(s)
+    for r, s in enumerate(hs):
+        vbase, bbase, _ = bases_from_totals(np.array(totals), r)
+        s.emit(vbase, bbase)
+        assert np.array_equal(s.layer_active_cells().astype(np.int64), act_ref[slabs[r][0]:slabs[r][1]])
+        parts.append(s.copy_out())
+        s.close()
+    assert mesh_diff(np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), oxyz, oidx) == ""
+
+
 def test_slab_exchange_over_peer_memory_on_one_device(iso, oracle, isolib, monkeypatch):
     """isomc_slab_connect + isomc_slab_emit_exchanged: the totals travel as stores into the ranks' mailboxes, the id offset is
     derived by the waiting kernel.  All ranks on one device here (the mailboxes are plain device pointers); several steps, so that

@@ -109,3 +109,30 @@ def test_new_host_side_argument_checks_need_no_gpu():
     # CentralDifference is transparent as a scalar source: same program as the tree it wraps
     from isosurface_b200.source import encode_program
     assert encode_program(iso.Translate(0.5, cd)).tobytes() == encode_program(iso.Translate(0.5, iso.Sphere(0.3))).tobytes()
+
+
+def test_balanced_slabs_cut_equal_work():
+    """sharded.balanced_slabs: contiguous, covering, at least one layer per rank, and the heaviest rank's work is close to the mean
+    (never worse than the equal-thickness split on a skewed field)"""
+    from isosurface_b200.sharded import balanced_slabs, slab_range
+    size = 256
+    rng = np.random.default_rng(3)
+    z = np.arange(size)
+    active = (40000 * np.exp(-((z - 70) / 25.0) ** 2) + 3000 * rng.random(size)).astype(np.int64)  # the surface sits in one region
+    for world in (1, 2, 3, 8, 31):
+        slabs = balanced_slabs(size, active, world)
+        assert slabs[0][0] == 0 and slabs[-1][1] == size and all(a[1] == b[0] for a, b in zip(slabs, slabs[1:]))
+        assert all(z1 > z0 for z0, z1 in slabs)
+        work = size * size + 76.0 * active
+        heavy = max(work[z0:z1].sum() for z0, z1 in slabs)
+        heavy_equal = max(work[slice(*slab_range(size, r, world))].sum() for r in range(world))
+        assert heavy <= heavy_equal + work.max()
+        if world in (2, 3, 8):
+            assert heavy <= 1.15 * work.sum() / world
+    # a uniform field keeps the equal split; degenerate inputs are rejected
+    assert balanced_slabs(64, np.full(64, 100), 4) == [slab_range(64, r, 4) for r in range(4)]
+    assert balanced_slabs(5, np.zeros(5), 5) == [(i, i + 1) for i in range(5)]
+    with pytest.raises(ValueError):
+        balanced_slabs(8, np.zeros(7), 2)
+    with pytest.raises(ValueError):
+        balanced_slabs(4, np.zeros(4), 5)
