@@ -72,7 +72,7 @@ struct isomc {
      * while everything a kernel takes by value stays the same (pipe_key: pointers, capacities, plan) */
     cudaGraphExec_t pipe_exec = nullptr;
     uint64_t pipe_key[12] = {};
-    uint32_t pipe_launches = 0;
+    uint32_t pipe_launches = 0, pipe_chunks = 1, pipe_chunk_l[MAX_CHUNKS + 1] = {};
     /* slab totals exchanged over peer memory (isomc_slab_connect*): own mailbox, the ranks' mailbox addresses, step counter */
     unsigned long long *mailbox = nullptr;
     unsigned long long **d_peers = nullptr;
@@ -344,36 +344,56 @@ PipePlan pipe_plan(const isomc *h, bool emit_inline) {
 }
 
 int32_t pipelined_launches(isomc *h, const PipePlan &pp);
+int32_t serial_launches(isomc *h, bool emit_inline);
 
-int32_t enqueue_pipelined(isomc *h, const PipePlan &pp) {
+/*
+ * The launch sequence of an extract (memset + 4 kernels; or the stage pipeline) replayed from a CUDA graph: one cudaGraphLaunch
+ * instead of 5 .. 70 API calls, and the dependent launches keep their programmatic edges.  A graph is captured from the very
+ * launch code below and stays valid while everything the kernels take BY VALUE stays the same (the key: source, output buffers
+ * and capacities, list buffers, stream, plan); anything else re-captures.  Off while profiling (events between the kernels) and
+ * for extracts without inline emission (slabs: their sequence is split by the exchange).  ISOMC_GRAPH=0 switches it off.
+ */
+uint64_t program_hash(const isomc *h) {
+    uint64_t x = 1469598103934665603ull; /* FNV-1a over the nodes the kernels receive by value */
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(&h->prog);
+    for (size_t i = 0; i < sizeof(SdfProgram); ++i) { x ^= p[i]; x *= 1099511628211ull; }
+    return x;
+}
+
+int32_t enqueue_graphed(isomc *h, const PipePlan &pp, bool emit_inline) {
     static const bool use_graph = !(getenv("ISOMC_GRAPH") && atoi(getenv("ISOMC_GRAPH")) == 0);
-    if (!use_graph || h->kind != SRC_GRID) return pipelined_launches(h, pp);
+    const bool pipelined = pp.chunks > 1;
+    if (!use_graph || !emit_inline || h->profiling || h->timeline || h->tile_mode)
+        return pipelined ? pipelined_launches(h, pp) : serial_launches(h, emit_inline);
     const uint64_t key[12] = {(uint64_t)(uintptr_t)h->d_grid, (uint64_t)(uintptr_t)h->xyz, (uint64_t)(uintptr_t)h->idx, h->cap_v, h->cap_t,
                               (uint64_t)(uintptr_t)h->L.ent, h->L.cap_blocks, pp.chunks,
                               (uint64_t)pp.sg.sign << 32 | (uint64_t)pp.sg.count << 16 | (uint64_t)pp.sg.emit,
-                              (uint64_t)(uintptr_t)h->stream, (uint64_t)(uintptr_t)h->signs, 1};
+                              (uint64_t)(uintptr_t)h->stream, (uint64_t)h->kind << 8 | (h->directed ? 1u : 0u),
+                              h->kind == SRC_SDF ? program_hash(h) : 0ull};
     if (h->pipe_exec && memcmp(key, h->pipe_key, sizeof key) == 0) {
         CU(h, cudaGraphLaunch(h->pipe_exec, h->stream));
         h->stats.kernel_launches = h->pipe_launches;
+        h->n_chunks = h->pipe_chunks;
+        memcpy(h->chunk_l, h->pipe_chunk_l, sizeof h->chunk_l);
         h->counted = true; h->emitted = true;
         return ISOMC_OK;
     }
     if (h->pipe_exec) { cudaGraphExecDestroy(h->pipe_exec); h->pipe_exec = nullptr; }
-    if (!h->s_sign) { /* (streams and events are created outside the capture) */
-        int32_t rc0 = pipelined_launches(h, pp);
-        return rc0;
-    }
+    if (pipelined && !h->s_sign) return pipelined_launches(h, pp); /* (its streams and events are created outside a capture) */
+    if (h->cap_v == 0 && h->cap_t == 0) return serial_launches(h, emit_inline);
     CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    int32_t rc = pipelined_launches(h, pp);
+    int32_t rc = pipelined ? pipelined_launches(h, pp) : serial_launches(h, emit_inline);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (e != cudaSuccess) return fail(h, ISOMC_ERR_CUDA, "stream capture of the pipelined extract failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(h, ISOMC_ERR_CUDA, "stream capture of the extract failed: %s", cudaGetErrorString(e));
     e = cudaGraphInstantiate(&h->pipe_exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { h->pipe_exec = nullptr; return fail(h, ISOMC_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
     memcpy(h->pipe_key, key, sizeof key);
     h->pipe_launches = h->stats.kernel_launches;
+    h->pipe_chunks = h->n_chunks;
+    memcpy(h->pipe_chunk_l, h->chunk_l, sizeof h->chunk_l);
     CU(h, cudaGraphLaunch(h->pipe_exec, h->stream));
     return ISOMC_OK;
 }
@@ -439,9 +459,12 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
         h->emitted = emit_inline;
         return ISOMC_OK;
     }
-    const PipePlan pp = pipe_plan(h, emit_inline);
-    if (pp.chunks > 1) return enqueue_pipelined(h, pp);
-    /* one chunk, one stream, every stage with the GPU to itself (per-kernel profiling, small lattices, the tile path) */
+    return enqueue_graphed(h, pipe_plan(h, emit_inline), emit_inline);
+}
+
+/* one chunk, one stream, every stage with the GPU to itself */
+int32_t serial_launches(isomc *h, bool emit_inline) {
+    const Geo &g = h->g;
     h->n_chunks = 1;
     h->chunk_l[0] = 0; h->chunk_l[1] = g.ncl;
     if (h->profiling) CU(h, cudaEventRecord(h->ev[0], h->stream));
