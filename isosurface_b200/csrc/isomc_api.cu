@@ -72,6 +72,7 @@ struct isomc {
      * while everything a kernel takes by value stays the same (pipe_key: pointers, capacities, plan) */
     cudaGraphExec_t pipe_exec = nullptr;
     uint64_t pipe_key[12] = {};
+    uint32_t last_blocks = 0; /* list blocks the previous extract used (sizes the emission grid of small lattices) */
     uint32_t pipe_launches = 0, pipe_chunks = 1, pipe_chunk_l[MAX_CHUNKS + 1] = {};
     /* slab totals exchanged over peer memory (isomc_slab_connect*): own mailbox, the ranks' mailbox addresses, step counter */
     unsigned long long *mailbox = nullptr;
@@ -243,6 +244,7 @@ void tl_mark(isomc *h, const char *name, uint32_t c, cudaStream_t st) {
 
 int32_t launch_emit_chunk(isomc *h, uint32_t c, cudaStream_t st, int bps = 0) {
     const Geo &g = h->g;
+    if (bps == 0 && h->last_blocks) bps = -(int)h->last_blocks;
     const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
     if (h->tile_mode) {
         /* pass 2: edge ids, vertex positions and triangles of the chunk's cell layers (warm-up on the layer below) */
@@ -368,7 +370,7 @@ int32_t enqueue_graphed(isomc *h, const PipePlan &pp, bool emit_inline) {
     const uint64_t key[12] = {(uint64_t)(uintptr_t)h->d_grid, (uint64_t)(uintptr_t)h->xyz, (uint64_t)(uintptr_t)h->idx, h->cap_v, h->cap_t,
                               (uint64_t)(uintptr_t)h->L.ent, h->L.cap_blocks, pp.chunks,
                               (uint64_t)pp.sg.sign << 32 | (uint64_t)pp.sg.count << 16 | (uint64_t)pp.sg.emit,
-                              (uint64_t)(uintptr_t)h->stream, (uint64_t)h->kind << 8 | (h->directed ? 1u : 0u),
+                              (uint64_t)(uintptr_t)h->stream, (uint64_t)h->last_blocks << 16 | (uint64_t)h->kind << 8 | (h->directed ? 1u : 0u),
                               h->kind == SRC_SDF ? program_hash(h) : 0ull};
     if (h->pipe_exec && memcmp(key, h->pipe_key, sizeof key) == 0) {
         CU(h, cudaGraphLaunch(h->pipe_exec, h->stream));
@@ -523,6 +525,11 @@ int32_t finish_impl(isomc *h) {
     int32_t rc = fetch_totals(h);
     if (rc) return rc;
     const uint64_t nv = h->h_totals[8], nt = h->h_totals[10];
+    if (!h->tile_mode) { /* rounded up to a power of two: the figure is part of the graph key and must not change with every mesh */
+        uint32_t b = 16;
+        while (b < h->h_totals[7] + 8 && b < 4096) b <<= 1;
+        h->last_blocks = b < 4096 ? b : 0u;
+    }
     /* ids are u32 and the whole numbering (incl. a slab's ghost layer) must fit */
     if (h->h_totals[0] >= (1ull << 32) || h->h_totals[1] >= (1ull << 32))
         return fail(h, ISOMC_ERR_INDEX_OVERFLOW, "mesh has %llu vertices / %llu triangles: does not fit u32 indices",

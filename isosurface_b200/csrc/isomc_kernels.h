@@ -54,7 +54,7 @@ cudaError_t isomc_launch_count_list(const Geo &g, const uint32_t *signs, const M
                                     uint32_t *rowT, uint32_t *rowA, unsigned long long *layerTot, uint32_t *ticket /* zeroed */,
                                     uint32_t lz0, uint32_t lz1, int sms, cudaStream_t st, int grid_bps = 0);
 /* list blocks [*blk_first, *blk_end) (device pointers; blk_first == NULL: from block 0).
- * grid_bps: CTAs per SM to launch when the stage shares the SMs with others (0 = as many as fit) */
+ * grid_bps: > 0 CTAs per SM to launch when the stage shares the SMs with others, 0 = as many as fit, < 0 = -(CTAs in total) */
 cudaError_t isomc_launch_emit_list_grid(const Geo &g, const float *d_grid, const ListBufs &L, const EmitTab *tab,
                                         const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                         const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,

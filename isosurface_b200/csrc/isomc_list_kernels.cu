@@ -125,7 +125,10 @@ cudaError_t launch_emit_list(const Src &src, const Geo &g, const ListBufs &L, co
                              uint32_t *idx, uint64_t cap_v, uint64_t cap_t, const uint32_t *blk_first, const uint32_t *blk_end,
                              int sms, cudaStream_t st, int grid_bps) {
     const int minb = emit_list_minb(g);
-    const uint32_t grid = (uint32_t)(sms * (grid_bps > 0 && grid_bps < minb ? grid_bps : minb));
+    uint32_t grid = (uint32_t)(sms * (grid_bps > 0 && grid_bps < minb ? grid_bps : minb));
+    /* grid_bps < 0: -(list blocks the previous extract of the handle used): a small lattice does not need 740 CTAs that each
+     * copy the tables and find nothing to do (any grid is correct: the CTAs stride over the blocks) */
+    if (grid_bps < 0 && (uint32_t)(-grid_bps) < grid) grid = (uint32_t)(-grid_bps);
 #define ISOMC_EMIT_LAUNCH(M) isomc_launch(k_emit_list<Src, M>, grid, LIST_BLOCK, st, isomc_pdl_for((unsigned long long)g.N * g.N * g.nsl), src, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, (unsigned long long)cap_v, (unsigned long long)cap_t, blk_first, blk_end)
     switch (minb) {
     case 4: return ISOMC_EMIT_LAUNCH(4);
