@@ -76,25 +76,26 @@ __global__ void __launch_bounds__(LIST_BLOCK, MINB) k_emit_list(Src src, Geo g, 
     A.xyz = xyz; A.idx = idx;
     /* the entries of the next piece of work are requested before the current one is worked on: the first load of an iteration
      * (a DRAM miss) was the largest single stall of the kernel */
-    uint32_t b = b0 + blockIdx.x;
-    uint32_t fill = 0, yz = 0;
+    /* (the fill of a block is fetched two blocks ahead, its entries one block ahead and only below the fill: no load ever
+     * touches list space that was not written) */
+    uint32_t b = b0 + blockIdx.x, bn = b + gridDim.x;
+    uint32_t fill = b < b1 ? L.blkfill[b] : 0u, fill_n = bn < b1 ? L.blkfill[bn] : 0u, yz = 0;
     uint2 ea = make_uint2(0u, 0u);
-    if (b < b1) {
-        fill = L.blkfill[b];
+    if (threadIdx.x < fill) {
         const uint64_t k = (uint64_t)b * LIST_BLOCK + threadIdx.x;
-        ea = L.ent[k]; yz = L.ent_yz[k]; /* (entries past `fill` are allocated, never used) */
+        ea = L.ent[k]; yz = L.ent_yz[k];
     }
     while (b < b1) {
-        const uint32_t bn = b + gridDim.x;
-        uint32_t fill_n = 0, yz_n = 0;
+        const uint32_t bnn = bn + gridDim.x;
+        const uint32_t fill_nn = bnn < b1 ? L.blkfill[bnn] : 0u;
+        uint32_t yz_n = 0;
         uint2 ea_n = make_uint2(0u, 0u);
-        if (bn < b1) {
-            fill_n = L.blkfill[bn];
+        if (threadIdx.x < fill_n) {
             const uint64_t kn = (uint64_t)bn * LIST_BLOCK + threadIdx.x;
             ea_n = L.ent[kn]; yz_n = L.ent_yz[kn];
         }
         if (threadIdx.x < fill) emit_cell(g, src, T, L, A, (uint64_t)b * LIST_BLOCK + threadIdx.x, ea, yz, s_eid + threadIdx.x, LIST_BLOCK);
-        b = bn; fill = fill_n; ea = ea_n; yz = yz_n;
+        b = bn; bn = bnn; fill = fill_n; fill_n = fill_nn; ea = ea_n; yz = yz_n;
     }
 }
 

@@ -32,3 +32,34 @@ totals = np.array([s.count(p) for s, p in zip(slabs, ptrs)], dtype=np.uint64)
 for r, s in enumerate(slabs):
     s.extract(ptrs[r], gathered=totals)
     print("slab", r, [len(a) for a in s.copy_out()])
+    s.close()
+
+# round 2: repeated extracts (CUDA-graph replay of the launch sequence), batched chunks, the peer-memory totals exchange
+import ctypes as C  # noqa: E402
+from isosurface_b200 import _lib  # noqa: E402
+mc = iso.MarchingCubes(40)
+for _ in range(3):
+    print("graph replay", mc.extract_device(iso.Sampler(iso_source("torus"))))
+mc.close()
+drv = iso.BatchedMarchingCubes(24, n_chunks=6)
+srcs = [iso.Sampler(iso.Translate((0.3 + 0.08 * i, 0.5, 0.5), iso.Sphere(0.2))) for i in range(9)]
+print("batch", [len(m[1]) // 3 for m in drv.extract_many(srcs)])
+drv.close()
+lib = _lib.load()
+slabs = [SlabMarchingCubes(size, r, world) for r in range(world)]
+boxes = (C.c_void_p * world)()
+for r, s in enumerate(slabs):
+    b = C.c_void_p()
+    _lib.check(lib.isomc_slab_mailbox(s._h, C.byref(b)), s._h)
+    boxes[r] = b.value
+for r, s in enumerate(slabs):
+    _lib.check(lib.isomc_slab_connect(s._h, r, world, boxes), s._h)
+for step in range(3):
+    for r, s in enumerate(slabs):
+        _lib.check(lib.isomc_slab_count_grid_device(s._h, C.c_void_p(ptrs[r])), s._h)
+        _lib.check(lib.isomc_slab_enqueue_emit_exchanged(s._h), s._h)
+    for s in slabs:
+        _lib.check(lib.isomc_finish(s._h), s._h)
+print("exchanged", [[len(a) for a in s.copy_out()] for s in slabs])
+for s in slabs:
+    s.close()
