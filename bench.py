@@ -302,6 +302,9 @@ class Runner:
                 _lib.check(lib.isomc_finish(h), h)
                 return
             import torch.distributed as dist
+            if self.kind == "grid" and self.exchange == "peer":  # count + exchange + emit: one launch sequence, one call
+                _lib.check(lib.isomc_slab_extract_grid_exchanged(h, C.c_void_p(self.grid.data_ptr())), h)
+                return
             if self.kind == "grid":
                 _lib.check(lib.isomc_slab_count_grid_device(h, C.c_void_p(self.grid.data_ptr())), h)
             else:

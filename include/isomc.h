@@ -217,6 +217,10 @@ int32_t isomc_slab_connect(isomc_t *h, uint32_t rank, uint32_t n_ranks, void *co
 int32_t isomc_slab_connect_ipc(isomc_t *h, uint32_t rank, uint32_t n_ranks, const void *handles /* n_ranks x ISOMC_IPC_HANDLE_BYTES */);
 int32_t isomc_slab_emit_exchanged(isomc_t *h);
 int32_t isomc_slab_enqueue_emit_exchanged(isomc_t *h);                        /* without the final synchronisation: isomc_finish() */
+/* slab_count + slab_emit_exchanged in one call: memset, sign, count, scan, exchange and emission form ONE launch sequence,
+ * replayed from a CUDA graph while source pointer and buffers stay the same (one cudaGraphLaunch per step and rank) */
+int32_t isomc_slab_extract_grid_exchanged(isomc_t *h, const float *d_slab);
+int32_t isomc_slab_enqueue_extract_grid_exchanged(isomc_t *h, const float *d_slab);   /* finish with isomc_finish() */
 
 /* ---- the same sharding driven from ONE process over the GPUs of a box (new) ----------------
  * `MarchingCubes::new(size)` for a host that owns several devices (the Rust shim, include/isosurface.hpp): one slab handle

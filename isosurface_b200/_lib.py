@@ -86,6 +86,8 @@ SIGNATURES = {
     "isomc_slab_connect_ipc": (_I32, [_P, _U32, _U32, _P]),
     "isomc_slab_emit_exchanged": (_I32, [_P]),
     "isomc_slab_enqueue_emit_exchanged": (_I32, [_P]),
+    "isomc_slab_extract_grid_exchanged": (_I32, [_P, _P]),
+    "isomc_slab_enqueue_extract_grid_exchanged": (_I32, [_P, _P]),
     "isomc_sharded_create": (_I32, [_U32, _U32, _P, C.POINTER(_P)]),
     "isomc_sharded_destroy": (_I32, [_P]),
     "isomc_sharded_last_error": (C.c_char_p, [_P]),

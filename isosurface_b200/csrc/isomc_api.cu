@@ -79,7 +79,7 @@ struct isomc {
     unsigned long long **d_peers = nullptr;
     std::vector<void *> ipc_opened;
     uint32_t xchg_rank = 0, xchg_n = 0;
-    unsigned long long xchg_seq = 0;
+    bool seq_exchange = false; /* the launch sequence being built / replayed contains the peer exchange (slab extract in one go) */
     bool step_exchanged = false; /* the id offset of the step in flight came from k_slab_exchange (totals[14] = its time-out flag) */
     /* streamed host-to-host extract (isomc_extract_grid_host_to): copy-in / copy-out streams, per-chunk events */
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -331,7 +331,7 @@ struct PipePlan { uint32_t chunks = 1; StageGrids sg; };
 PipePlan pipe_plan(const isomc *h, bool emit_inline) {
     PipePlan p;
     const Geo &g = h->g;
-    if (!emit_inline || h->tile_mode || h->batch || h->profiling || h->timeline || g.ncl < 64) return p;
+    if (!emit_inline || h->tile_mode || h->batch || h->profiling || h->timeline || h->seq_exchange || g.ncl < 64) return p;
     /* OFF unless asked for: measured slower than the serial order in every configuration tried (fbm512: serial 0.54 ms; 2 chunks
      * 0.56-0.75 ms, 4 chunks 0.63, 8 chunks 0.66-0.77 with the CUDA graph, 0.97 without).  Each stage needs all the warps an SM
      * holds to hide its own load latency, and per-chunk launches of k_count_list / k_emit_list quantise badly (profiles/r02_history.md) */
@@ -343,6 +343,18 @@ PipePlan pipe_plan(const isomc *h, bool emit_inline) {
     if (p.chunks > g.ncl / 8) p.chunks = g.ncl / 8;
     p.sg.sign = v[1]; p.sg.count = v[2]; p.sg.emit = v[3];
     return p;
+}
+
+/* totals of this slab to every rank's mailbox, the other ranks' totals from this rank's, id offset -> *vofs (k_slab_exchange) */
+int32_t launch_exchange(isomc *h, cudaStream_t st) {
+    static long long timeout = 0;
+    if (!timeout) { const char *p = getenv("ISOMC_EXCHANGE_TIMEOUT_MS"); timeout = (long long)(p ? atof(p) : 10000.0) * 2000000ll; }
+    CU(h, isomc_launch_slab_exchange(h->d_peers, h->xchg_rank, h->xchg_n, h->g.ghost, h->totals, h->vofs, timeout, st));
+    h->vofs_cached = -1;
+    h->step_exchanged = true;
+    h->totals_valid = false; /* (totals[13..15] are new) */
+    h->stats.kernel_launches += 1;
+    return ISOMC_OK;
 }
 
 int32_t pipelined_launches(isomc *h, const PipePlan &pp);
@@ -370,7 +382,8 @@ int32_t enqueue_graphed(isomc *h, const PipePlan &pp, bool emit_inline) {
     const uint64_t key[12] = {(uint64_t)(uintptr_t)h->d_grid, (uint64_t)(uintptr_t)h->xyz, (uint64_t)(uintptr_t)h->idx, h->cap_v, h->cap_t,
                               (uint64_t)(uintptr_t)h->L.ent, h->L.cap_blocks, pp.chunks,
                               (uint64_t)pp.sg.sign << 32 | (uint64_t)pp.sg.count << 16 | (uint64_t)pp.sg.emit,
-                              (uint64_t)(uintptr_t)h->stream, (uint64_t)h->last_blocks << 16 | (uint64_t)h->kind << 8 | (h->directed ? 1u : 0u),
+                              (uint64_t)(uintptr_t)h->stream,
+                              (uint64_t)h->last_blocks << 16 | (uint64_t)h->kind << 8 | (h->seq_exchange ? 2u : 0u) | (h->directed ? 1u : 0u),
                               h->kind == SRC_SDF ? program_hash(h) : 0ull};
     if (h->pipe_exec && memcmp(key, h->pipe_key, sizeof key) == 0) {
         CU(h, cudaGraphLaunch(h->pipe_exec, h->stream));
@@ -378,6 +391,7 @@ int32_t enqueue_graphed(isomc *h, const PipePlan &pp, bool emit_inline) {
         h->n_chunks = h->pipe_chunks;
         memcpy(h->chunk_l, h->pipe_chunk_l, sizeof h->chunk_l);
         h->counted = true; h->emitted = true;
+        if (h->seq_exchange) { h->vofs_cached = -1; h->step_exchanged = true; h->totals_valid = false; }
         return ISOMC_OK;
     }
     if (h->pipe_exec) { cudaGraphExecDestroy(h->pipe_exec); h->pipe_exec = nullptr; }
@@ -456,7 +470,7 @@ int32_t enqueue_count(isomc *h, bool emit_inline) {
     h->stats.kernel_launches = 0; h->stats.emit_reruns = 0;
     h->emit_inline = emit_inline;
     if (g.ncl == 0 || g.ncx == 0) { /* size == 1: the reference visits no cells */
-        CU(h, cudaMemsetAsync(h->totals, 0, N_TOTALS * sizeof(unsigned long long), h->stream));
+        CU(h, cudaMemsetAsync(h->totals, 0, 15 * sizeof(unsigned long long), h->stream)); /* ([15] is the exchange's step counter) */
         h->counted = true;
         h->emitted = emit_inline;
         return ISOMC_OK;
@@ -475,6 +489,10 @@ int32_t serial_launches(isomc *h, bool emit_inline) {
     int32_t rc = launch_count_chunk(h, 0, h->stream, nullptr);
     if (rc) return rc;
     tl_mark(h, "count+scan", 0, h->stream);
+    if (h->seq_exchange) {
+        rc = launch_exchange(h, h->stream);
+        if (rc) return rc;
+    }
     if (emit_inline) {
         rc = launch_emit_chunk(h, 0, h->stream);
         if (rc) return rc;
@@ -536,7 +554,7 @@ int32_t finish_impl(isomc *h) {
                     (unsigned long long)h->h_totals[0], (unsigned long long)h->h_totals[1]);
     if (h->vofs_cached < 0 && h->step_exchanged && h->h_totals[14] != 0)
         return fail(h, ISOMC_ERR_NCCL, "totals exchange over peer memory timed out: rank %llu never published step %llu",
-                    (unsigned long long)h->h_totals[14] - 1, h->xchg_seq);
+                    (unsigned long long)h->h_totals[14] - 1, (unsigned long long)h->h_totals[15]);
     if (h->vofs_cached < 0 && h->h_totals[13] + h->h_totals[0] >= (1ull << 32)) /* offset derived on the device (slab_emit_gathered) */
         return fail(h, ISOMC_ERR_INDEX_OVERFLOW, "global vertex ids of this slab reach %llu: do not fit u32 indices",
                     (unsigned long long)(h->h_totals[13] + h->h_totals[0]));
@@ -1311,8 +1329,10 @@ static int32_t connect_impl(isomc_t *h, uint32_t rank, uint32_t n_ranks, std::ve
     ptrs[rank] = h->mailbox;
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaMemcpy(h->d_peers, ptrs.data(), n_ranks * sizeof(unsigned long long *), cudaMemcpyHostToDevice));
-    h->xchg_rank = rank; h->xchg_n = n_ranks; h->xchg_seq = 0;
+    h->xchg_rank = rank; h->xchg_n = n_ranks;
     CU(h, cudaMemset(h->mailbox, 0, ISOMC_MAILBOX_BYTES));
+    CU(h, cudaMemset(h->totals + 15, 0, sizeof(unsigned long long))); /* step counter of k_slab_exchange */
+    if (h->pipe_exec) { cudaGraphExecDestroy(h->pipe_exec); h->pipe_exec = nullptr; }
     return ISOMC_OK;
 }
 
@@ -1369,14 +1389,8 @@ int32_t isomc_slab_enqueue_emit_exchanged(isomc_t *h) {
     if (!h->counted) return fail(h, ISOMC_ERR_NO_RESULT, "slab_emit before slab_count");
     int32_t rc = bind_device(h);
     if (rc) return rc;
-    static long long timeout = 0;
-    if (!timeout) { const char *p = getenv("ISOMC_EXCHANGE_TIMEOUT_MS"); timeout = (long long)(p ? atof(p) : 10000.0) * 2000000ll; }
-    ++h->xchg_seq;
-    CU(h, isomc_launch_slab_exchange(h->d_peers, h->xchg_rank, h->xchg_n, h->g.ghost, h->xchg_seq, h->totals, h->vofs, timeout, h->stream));
-    h->vofs_cached = -1;
-    h->step_exchanged = true;
-    h->totals_valid = false; /* (totals[13], [14] are new) */
-    h->stats.kernel_launches += 1;
+    rc = launch_exchange(h, h->stream);
+    if (rc) return rc;
     if (h->cap_v > 0 || h->cap_t > 0) {
         rc = enqueue_emit(h);
         if (rc) return rc;
@@ -1386,6 +1400,25 @@ int32_t isomc_slab_enqueue_emit_exchanged(isomc_t *h) {
 
 int32_t isomc_slab_emit_exchanged(isomc_t *h) {
     int32_t rc = isomc_slab_enqueue_emit_exchanged(h);
+    return rc ? rc : finish_impl(h);
+}
+
+/* count + exchange + emit of a slab as ONE launch sequence (replayed from a CUDA graph in steady state) */
+int32_t isomc_slab_enqueue_extract_grid_exchanged(isomc_t *h, const float *d_slab) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!d_slab) return fail(h, ISOMC_ERR_BAD_ARG, "d_slab == NULL");
+    if (!h->xchg_n) return fail(h, ISOMC_ERR_BAD_ARG, "slab is not connected to its peers (isomc_slab_connect / isomc_slab_connect_ipc)");
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    h->kind = SRC_GRID; h->d_grid = d_slab; h->directed = false;
+    h->seq_exchange = true;
+    rc = enqueue_count(h, h->cap_v > 0 || h->cap_t > 0); /* (first extract: no output buffers yet, finish() sizes them and emits) */
+    h->seq_exchange = false;
+    return rc;
+}
+
+int32_t isomc_slab_extract_grid_exchanged(isomc_t *h, const float *d_slab) {
+    int32_t rc = isomc_slab_enqueue_extract_grid_exchanged(h, d_slab);
     return rc ? rc : finish_impl(h);
 }
 

@@ -243,20 +243,29 @@ __global__ void k_slab_bases(const unsigned long long *__restrict__ gathered, ui
  * mappings).  Thread r of this one-CTA kernel writes this rank's totals into slot [parity][rank] of rank r's mailbox, fences,
  * releases the slot's sequence number, then waits for rank r's slot in the rank's OWN mailbox and takes its totals; thread 0
  * derives the id offset as k_slab_bases does.  Two parities are enough: a rank publishes step s+2 only after it has seen every
- * rank's step s+1, and a rank publishes s+1 after its own wait of step s (stream order).  A wait that lasts longer than
+ * rank's step s+1, and a rank publishes s+1 after its own wait of step s (stream order).  The step number is kept in totals[15]
+ * and advanced here.  A wait that lasts longer than
  * `timeout_cycles` gives up and flags the step (totals[14] = 1 + the silent rank) instead of hanging the device.
  */
 __global__ void __launch_bounds__(ISOMC_MAX_RANKS) k_slab_exchange(unsigned long long *const *__restrict__ peers, uint32_t rank,
-                                                                  uint32_t n_ranks, uint32_t ghost, unsigned long long seq,
+                                                                  uint32_t n_ranks, uint32_t ghost,
                                                                   unsigned long long *__restrict__ totals, uint32_t *__restrict__ vofs,
                                                                   long long timeout_cycles) {
     __shared__ unsigned long long s_tot[ISOMC_MAX_RANKS][3];
+    __shared__ unsigned long long s_seq;
     __shared__ uint32_t s_bad;
     isomc_pdl_trigger();
     isomc_pdl_wait(); /* totals[8..10] come from the row scan */
-    const uint32_t r = threadIdx.x, par = (uint32_t)(seq & 1ull);
-    if (r == 0) s_bad = 0;
+    const uint32_t r = threadIdx.x;
+    if (r == 0) { /* the step number lives on the device (totals[15]): the launch carries nothing that changes from step to step, so
+                     the whole slab extract can be replayed from a CUDA graph */
+        s_bad = 0;
+        s_seq = totals[15] + 1ull;
+        totals[15] = s_seq;
+    }
     __syncthreads();
+    const unsigned long long seq = s_seq;
+    const uint32_t par = (uint32_t)(seq & 1ull);
     if (r < n_ranks) {
         volatile unsigned long long *dst = peers[r] + ((size_t)par * ISOMC_MAX_RANKS + rank) * 4;
         dst[0] = totals[8]; dst[1] = totals[9]; dst[2] = totals[10];
@@ -407,9 +416,8 @@ cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t
 }
 
 cudaError_t isomc_launch_slab_exchange(unsigned long long *const *d_peers, uint32_t rank, uint32_t n_ranks, uint32_t ghost,
-                                       unsigned long long seq, unsigned long long *totals, uint32_t *vofs, long long timeout_cycles,
-                                       cudaStream_t st) {
-    return isomc_launch(k_slab_exchange, 1, ISOMC_MAX_RANKS, st, true, d_peers, rank, n_ranks, ghost, seq, totals, vofs, timeout_cycles);
+                                       unsigned long long *totals, uint32_t *vofs, long long timeout_cycles, cudaStream_t st) {
+    return isomc_launch(k_slab_exchange, 1, ISOMC_MAX_RANKS, st, true, d_peers, rank, n_ranks, ghost, totals, vofs, timeout_cycles);
 }
 
 cudaError_t isomc_launch_cube_indices(const Geo &g, const uint32_t *signs, const McTables *tabs, uint8_t *out, int sms,

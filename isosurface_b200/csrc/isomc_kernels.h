@@ -40,7 +40,7 @@ cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t
 #define ISOMC_MAX_RANKS 64
 #define ISOMC_MAILBOX_BYTES (2 * ISOMC_MAX_RANKS * 4 * sizeof(unsigned long long))
 cudaError_t isomc_launch_slab_exchange(unsigned long long *const *d_peers, uint32_t rank, uint32_t n_ranks, uint32_t ghost,
-                                       unsigned long long seq, unsigned long long *totals, uint32_t *vofs, long long timeout_cycles,
+                                       unsigned long long *totals /* [15] = step counter */, uint32_t *vofs, long long timeout_cycles,
                                        cudaStream_t st);
 cudaError_t isomc_launch_cube_indices(const Geo &g, const uint32_t *signs, const McTables *tabs, uint8_t *out, int sms,
                                       cudaStream_t st);

@@ -116,8 +116,9 @@ void slab_range(uint32_t size, uint32_t rank, uint32_t world, uint32_t *z0, uint
 }
 
 /* count on every rank, exchange the totals, emit on every rank: everything enqueued, nothing synchronised */
-int32_t exchange_and_emit(isomc_sharded *s) {
-    if (s->use_mailbox) { /* totals as peer stores over NVLink: one tiny kernel per rank publishes, waits and derives the offset */
+int32_t exchange_and_emit(isomc_sharded *s, bool already_enqueued = false) {
+    if (already_enqueued) {
+    } else if (s->use_mailbox) { /* totals as peer stores over NVLink: one tiny kernel per rank publishes, waits and derives the offset */
         for (uint32_t r = 0; r < s->n; ++r) SRC(s, r, isomc_slab_enqueue_emit_exchanged(s->h[r]));
     } else if (s->use_nccl) {
         SNC(s, g_nccl.GroupStart());
@@ -256,9 +257,11 @@ int32_t isomc_sharded_extract_grid(isomc_sharded_t *s, const float *const *d_sla
     s->have_result = false;
     for (uint32_t r = 0; r < s->n; ++r) {
         if (!d_slabs[r]) return sfail(s, ISOMC_ERR_BAD_ARG, "d_slabs[%u] == NULL", r);
-        SRC(s, r, isomc_slab_count_grid_device(s->h[r], d_slabs[r]));
+        /* peer-memory exchange: count, exchange and emission of a rank are one launch sequence (one graph launch per rank) */
+        if (s->use_mailbox) SRC(s, r, isomc_slab_enqueue_extract_grid_exchanged(s->h[r], d_slabs[r]));
+        else SRC(s, r, isomc_slab_count_grid_device(s->h[r], d_slabs[r]));
     }
-    return exchange_and_emit(s);
+    return exchange_and_emit(s, s->use_mailbox);
 }
 
 int32_t isomc_sharded_extract_sdf(isomc_sharded_t *s, const isomc_sdf_node *prog, uint32_t n_nodes) {

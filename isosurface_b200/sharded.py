@@ -152,8 +152,7 @@ class SlabMarchingCubes:
 
     def extract_exchanged(self, d_slab_ptr):
         """count -> totals to every rank's mailbox / wait / id offset on the device -> emit"""
-        _lib.check(self._lib.isomc_slab_count_grid_device(self._h, C.c_void_p(d_slab_ptr)), self._h)
-        _lib.check(self._lib.isomc_slab_emit_exchanged(self._h), self._h)
+        _lib.check(self._lib.isomc_slab_extract_grid_exchanged(self._h, C.c_void_p(d_slab_ptr)), self._h)
 
 
 def connect_peers_ipc(lib, handle, rank, world, group=None):

@@ -352,10 +352,13 @@ def test_slab_exchange_over_peer_memory_on_one_device(iso, oracle, isolib, monke
         host = t.cpu().numpy().reshape(size + 1, size, size)
         oxyz, oidx, _ = oracle.extract_grid(size, host)
         ptrs = [t.data_ptr() + 4 * slab_sample_layers(size, r, world)[0] * size * size for r in range(world)]
-        for _ in range(2 if step == 0 else 1):  # (first extract of a handle: no output buffers yet, finish() runs the emission)
+        for rep in range(3 if step == 0 else 2):  # (first extract of a handle: no output buffers yet, finish() runs the emission)
             for r, s in enumerate(slabs):
-                _lib.check(isolib.isomc_slab_count_grid_device(s._h, C.c_void_p(ptrs[r])), s._h)
-                _lib.check(isolib.isomc_slab_enqueue_emit_exchanged(s._h), s._h)
+                if rep == 0:  # the two-call form ...
+                    _lib.check(isolib.isomc_slab_count_grid_device(s._h, C.c_void_p(ptrs[r])), s._h)
+                    _lib.check(isolib.isomc_slab_enqueue_emit_exchanged(s._h), s._h)
+                else:         # ... and the one-call form (one launch sequence per rank, replayed from a graph the second time)
+                    _lib.check(isolib.isomc_slab_enqueue_extract_grid_exchanged(s._h, C.c_void_p(ptrs[r])), s._h)
             for s in slabs:
                 _lib.check(isolib.isomc_finish(s._h), s._h)
         parts = [s.copy_out() for s in slabs]
