@@ -234,6 +234,15 @@ def run_reference(args):
     cfg.update({"host_cores": os.cpu_count(), "path": "CPU oracle (C restatement of the reference), faithful-cost mode",
                 "note": "each step is a bounded sample (first cell layers of the workload); ms_per_step is extrapolated to the full grid",
                 "timing": "time.perf_counter around the oracle call"})
+    # the same keys as our arm's config: mesh size of the FULL workload from the committed oracle record of the benchmark fields
+    try:
+        gold = json.loads((ROOT / "tests" / "golden" / "full_hashes.json").read_text()).get(wl)
+    except Exception:  # noqa: BLE001
+        gold = None
+    if gold and gold.get("z_cells") == size:
+        cfg.update({"vertices": gold["vertices"], "triangles": gold["triangles"], "active_cells": gold["active_cells"],
+                    "active_fraction": gold["active_cells"] / (float(size - 1) ** 2 * size)})
+    cfg["kernel_src_sha"] = None  # (no kernels on this arm)
     line = {"impl": "reference", "metric": "MarchingCubes Gvoxels/s", "value": v, "unit": "Gvoxels/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": vox_per_step / (v * 1e9) * 1e3, "higher_is_better": True,

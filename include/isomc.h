@@ -97,6 +97,7 @@ int32_t isomc_create(uint32_t size, int32_t device, isomc_t **out);
 int32_t isomc_destroy(isomc_t *h);
 const char *isomc_last_error(const isomc_t *h);      /* h may be NULL: last create() error */
 const char *isomc_version(void);
+int32_t isomc_device_count(void);   /* CUDA devices this process sees (0: none, no CPU fallback) */
 
 /* ---- extract(&source, ...) --------------------------------------------------------------- */
 /* source = implicit tree (evaluated on device; no grid is materialised) */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "isomc_destroy": (_I32, [_P]),
     "isomc_last_error": (C.c_char_p, [_P]),
     "isomc_version": (C.c_char_p, []),
+    "isomc_device_count": (_I32, []),
     "isomc_extract_sdf": (_I32, [_P, _P, _U32]),
     "isomc_extract_sdf_directed": (_I32, [_P, _P, _U32]),
     "isomc_extract_grid_device": (_I32, [_P, _P]),

@@ -736,7 +736,12 @@ int32_t create_impl(uint32_t size, uint32_t z_begin, uint32_t z_end, int32_t dev
 
 extern "C" {
 
-const char *isomc_version(void) { return "isomc_b200 0.1.0 (sm_100a)"; }
+const char *isomc_version(void) { return "isomc_b200 0.2.0 (sm_100a)"; }
+
+int32_t isomc_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 
 int32_t isomc_create(uint32_t size, int32_t device, isomc_t **out) { return create_impl(size, 0, size, device, out); }
 

@@ -70,7 +70,10 @@ int main() {
         {
             std::vector<float> sv, ov; std::vector<uint32_t> si, oi;
             IndexedVertices ss(sv, si), os(ov, oi);
-            ShardedMarchingCubes sharded(64, {0, 0, 0});
+            const int nd = isomc_device_count();
+            std::vector<int32_t> devs = {0, nd > 1 ? 1 : 0, nd > 2 ? 2 : 0};   // distinct devices when the box has them
+            ShardedMarchingCubes sharded(64, devs);
+            if (nd > 2 && !sharded.uses_peer_memory() && !sharded.uses_nccl()) { std::printf("no inter-device exchange chosen\n"); return 1; }
             sharded.extract(Sampler(src), ss);
             MarchingCubes one(64);
             one.extract(Sampler(src), os);
