@@ -297,8 +297,17 @@ class Runner:
         # the totals exchange: peer stores into the ranks' mailboxes over NVLink (default), or an NCCL all-gather per step
         self.exchange = "nccl" if os.environ.get("ISOMC_EXCHANGE", "peer") == "nccl" else "peer"
         if self.world > 1 and self.exchange == "peer":
+            import torch.distributed as dist
             from isosurface_b200.sharded import connect_peers_ipc
-            connect_peers_ipc(self.lib, self.h, self.rank, self.world)
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            try:
+                connect_peers_ipc(self.lib, self.h, self.rank, self.world)
+            except _lib.IsomcError as e:  # (CUDA IPC not available between these processes): every rank falls back together
+                print("[bench] rank %d: peer mailboxes unavailable (%s): NCCL all-gather instead" % (self.rank, e), file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                self.exchange = "nccl"
 
     def step(self):
         lib, _lib, h = self.lib, self._lib, self.h

@@ -166,8 +166,10 @@ def connect_peers_ipc(lib, handle, rank, world, group=None):
     t_all = torch.zeros(64 * world, dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(t_all, t_mine, group=group)
     handles = np.ascontiguousarray(t_all.cpu().numpy())
-    _lib.check(lib.isomc_slab_connect_ipc(handle, rank, world, handles.ctypes.data), handle)
-    dist.barrier(group=group)  # every rank has mapped every mailbox before anyone publishes
+    try:
+        _lib.check(lib.isomc_slab_connect_ipc(handle, rank, world, handles.ctypes.data), handle)
+    finally:
+        dist.barrier(group=group)  # every rank has mapped every mailbox (or given up) before anyone publishes
 
 
 class ShardedMarchingCubes:
