@@ -73,11 +73,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+HOST_ONLY_SOURCES = ("isomc_api.cu", "isomc_sharded.cu")  # entry points and plumbing: no device code
+
+
 def kernel_source_sha():
-    """sha256 over the kernel sources: what an ncu capture (profiles/traffic.json) is valid for.  The GPU box has no .git."""
+    """sha256 over the sources that hold device code: what an ncu capture (profiles/traffic.json) is valid for.
+    The GPU box has no .git."""
     h = hashlib.sha256()
     for f in sorted((ROOT / "isosurface_b200" / "csrc").glob("*")):
-        if f.suffix in (".cu", ".cuh", ".h"):
+        if f.suffix in (".cu", ".cuh", ".h") and f.name not in HOST_ONLY_SOURCES:
             h.update(f.name.encode())
             h.update(f.read_bytes())
     return h.hexdigest()[:16]

@@ -137,6 +137,9 @@ int32_t isomc_batch_offsets(isomc_t *h, uint64_t *v_offsets, uint64_t *t_offsets
  * Results through the same calls as a mesh: isomc_counts() reports the points as vertices (0 triangles),
  * isomc_copy_out(h, xyz, NULL) / isomc_device_buffers() deliver them.  Whole-lattice handles only. */
 int32_t isomc_points_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes);
+/* PointCloud::<Directed> (the D = Directed instantiation, src/distance.rs:72-104): the tree is sampled through sample_vector and a
+ * corner is outside iff any component is positive; implicit sources only */
+int32_t isomc_points_sdf_directed(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes);
 int32_t isomc_points_grid_device(isomc_t *h, const float *d_grid);
 int32_t isomc_points_grid_host(isomc_t *h, const float *h_grid);
 

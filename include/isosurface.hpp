@@ -216,16 +216,18 @@ class MarchingCubes {
 // ---- PointCloud (reference src/point_cloud.rs:33-63): one vertex per active cell, no face data ---------------
 class PointCloud : public MarchingCubes {
   public:
-    explicit PointCloud(uint32_t size, int32_t device = 0) : MarchingCubes(size, device) {}
+    explicit PointCloud(uint32_t size, int32_t device = 0, Distance distance = Distance::Signed) : MarchingCubes(size, device, distance) {}
     template <class S> void extract(const SamplerT<S> &sampler, Extractor &extractor) { extract(sampler.source, extractor); }
     template <class S> void extract(const S &source, Extractor &extractor) {
         SdfProgram prog;
         source.encode(prog);
-        check(isomc_points_sdf(h_, prog.data(), (uint32_t)prog.size()));
+        check(distance_ == Distance::Directed ? isomc_points_sdf_directed(h_, prog.data(), (uint32_t)prog.size())
+                                              : isomc_points_sdf(h_, prog.data(), (uint32_t)prog.size()));
         deliver(extractor);
     }
     void extract(const DenseGrid &grid, Extractor &extractor) {
         if (grid.size != size_) throw Error(ISOMC_ERR_BAD_ARG, "grid size does not match");
+        if (distance_ == Distance::Directed) throw Error(ISOMC_ERR_UNSUPPORTED_SOURCE, "a dense scalar lattice has no Directed distances");
         check(grid.on_device ? isomc_points_grid_device(h_, grid.data) : isomc_points_grid_host(h_, grid.data));
         deliver(extractor);
     }

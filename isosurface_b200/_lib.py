@@ -56,6 +56,7 @@ SIGNATURES = {
     "isomc_extract_sdf_batch": (_I32, [_P, _P, _P, _U32]),
     "isomc_batch_offsets": (_I32, [_P, _P, _P]),
     "isomc_points_sdf": (_I32, [_P, _P, _U32]),
+    "isomc_points_sdf_directed": (_I32, [_P, _P, _U32]),
     "isomc_points_grid_device": (_I32, [_P, _P]),
     "isomc_points_grid_host": (_I32, [_P, _P]),
     "isomc_counts": (_I32, [_P, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),

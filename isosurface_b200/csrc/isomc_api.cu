@@ -1099,6 +1099,15 @@ int32_t isomc_points_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_node
     return points_impl(h);
 }
 
+/* PointCloud::<Directed>: the tree sampled as Directed distances (a cell corner is outside iff any component is positive) */
+int32_t isomc_points_sdf_directed(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    int32_t rc = validate_program(h, prog, n_nodes, &h->prog);
+    if (rc) return rc;
+    h->kind = SRC_SDF; h->d_grid = nullptr; h->directed = true;
+    return points_impl(h);
+}
+
 int32_t isomc_points_grid_host(isomc_t *h, const float *h_grid) {
     if (!h) return ISOMC_ERR_BAD_ARG;
     if (!h_grid) return fail(h, ISOMC_ERR_BAD_ARG, "h_grid == NULL");

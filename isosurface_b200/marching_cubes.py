@@ -194,11 +194,14 @@ class PointCloud(MarchingCubes):
         if isinstance(src, DenseGrid):
             if src.size != self.size:
                 raise ValueError("grid is for size %d, PointCloud for %d" % (src.size, self.size))
+            if self.distance == "directed":
+                raise TypeError("a dense scalar lattice has no Directed distances; use an implicit source")
             fn = self._lib.isomc_points_grid_device if src.on_device else self._lib.isomc_points_grid_host
             _lib.check(fn(self._h, src.ptr), self._h)
         else:
             prog = encode_program(src)
-            _lib.check(self._lib.isomc_points_sdf(self._h, prog.ctypes.data, len(prog)), self._h)
+            fn = self._lib.isomc_points_sdf_directed if self.distance == "directed" else self._lib.isomc_points_sdf
+            _lib.check(fn(self._h, prog.ctypes.data, len(prog)), self._h)
         return self.counts()
 
     def extract_host(self, grid, xyz=None, idx=None):

@@ -828,3 +828,47 @@ done:
     if (rc) oracle_mesh_free(out);
     return rc;
 }
+
+/* PointCloud::<Directed>::new(size).extract(&Sampler::new(&implicit_tree), ..): reference src/point_cloud.rs:50-63 with
+ * D = Directed -- the same traversal, classify_corners through Directed::is_positive (src/distance.rs:77-80: outside iff any
+ * component is positive), one point corners[0].lerp(corners[6], 0.5) per cell whose cube index is neither 0 nor 255. */
+int oracle_point_cloud_sdf_directed(uint32_t size, const osdf_node *prog, uint32_t n, oracle_mesh *out) {
+    memset(out, 0, sizeof *out);
+    if (size < 1) return -1;
+    int rc = 0, err = 0;
+    unsigned char *inside[2];
+    inside[0] = (unsigned char *)malloc((size_t)size * size);
+    inside[1] = (unsigned char *)malloc((size_t)size * size);
+    if (!inside[0] || !inside[1]) { rc = -4; goto done; }
+    const uint32_t sm1 = size - 1;
+    const float inv = 1.0f / (float)sm1;
+    for (uint32_t z = 0; z <= size; ++z) { /* sample layer z; cells of layer z - 1 once it is there */
+        for (uint32_t y = 0; y < size; ++y)
+            for (uint32_t x = 0; x < size; ++x) {
+                const v3 c = {(float)x * inv, (float)y * inv, (float)z * inv};
+                const v3 v = sdf_eval_vec(prog, n, c, &err);
+                inside[1][(size_t)y * size + x] = !(v.x > 0.0f || v.y > 0.0f || v.z > 0.0f);
+            }
+        if (err) { rc = -2; goto done; }
+        if (z > 0)
+            for (uint32_t y = 0; y < sm1; ++y)
+                for (uint32_t x = 0; x < sm1; ++x) {
+                    unsigned cube_index = 0;
+                    for (int i = 0; i < 8; ++i)
+                        if (inside[CORNER_OFF[i][2]][(size_t)(y + CORNER_OFF[i][1]) * size + x + CORNER_OFF[i][0]]) cube_index |= 1u << i;
+                    if (cube_index != 0 && cube_index != 255) {
+                        const v3 a = {(float)x * inv, (float)y * inv, (float)(z - 1) * inv};           /* corners[0] */
+                        const v3 b = {(float)(x + 1) * inv, (float)(y + 1) * inv, (float)z * inv};     /* corners[6] */
+                        const float f = 0.5f, of = 1.0f - f;
+                        const v3 p = {of * a.x + f * b.x, of * a.y + f * b.y, of * a.z + f * b.z};
+                        if (push_vertex(out, p)) { rc = -4; goto done; }
+                        out->n_active_cells++;
+                    }
+                }
+        { unsigned char *t = inside[0]; inside[0] = inside[1]; inside[1] = t; }
+    }
+done:
+    free(inside[0]); free(inside[1]);
+    if (rc) oracle_mesh_free(out);
+    return rc;
+}

@@ -51,6 +51,7 @@ def lib():
         _LIB.oracle_sample_sdf_vector.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         _LIB.oracle_extract_sdf_directed.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
         _LIB.oracle_point_cloud_sdf.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
+        _LIB.oracle_point_cloud_sdf_directed.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
         _LIB.oracle_point_cloud_grid.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(_Mesh)]
         _LIB.oracle_synth_field.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
     return _LIB
@@ -136,6 +137,16 @@ def point_cloud_sdf(size, prog):
     rc = lib().oracle_point_cloud_sdf(size, prog.ctypes.data, len(prog), C.byref(m))
     if rc:
         raise RuntimeError("oracle_point_cloud_sdf rc=%d" % rc)
+    return _take(m)[0]
+
+
+def point_cloud_sdf_directed(size, prog):
+    """PointCloud::<Directed>::new(size).extract over an implicit tree (point_cloud.rs:50-63, distance.rs:77-80)"""
+    m = _Mesh()
+    prog = np.ascontiguousarray(prog)
+    rc = lib().oracle_point_cloud_sdf_directed(size, prog.ctypes.data, len(prog), C.byref(m))
+    if rc:
+        raise RuntimeError("oracle_point_cloud_sdf_directed rc=%d" % rc)
     return _take(m)[0]
 
 

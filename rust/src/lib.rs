@@ -26,6 +26,7 @@ extern "C" {
     fn isomc_extract_grid_host_to(h: *mut isomc_t, grid: *const f32, xyz: *mut f32, cap_vertices: u64, idx: *mut u32,
                                   cap_triangles: u64) -> i32;
     fn isomc_points_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
+    fn isomc_points_sdf_directed(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
     fn isomc_points_grid_host(h: *mut isomc_t, grid: *const f32) -> i32;
     fn isomc_counts(h: *mut isomc_t, nv: *mut u64, nt: *mut u64, na: *mut u64) -> i32;
     fn isomc_copy_out(h: *mut isomc_t, xyz: *mut f32, idx: *mut u32) -> i32;
@@ -138,14 +139,18 @@ impl<'a, S: DeviceNormals> IndexedInterleavedNormals<'a, S> {
 pub trait Distance {
     /// the C entry point that samples an implicit tree as this kind of distance
     #[doc(hidden)] unsafe fn extract_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
+    /// ... and the one behind `PointCloud<D>`
+    #[doc(hidden)] unsafe fn points_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
 }
 pub struct Signed;
 pub struct Directed;
 impl Distance for Signed {
     unsafe fn extract_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32 { isomc_extract_sdf(h, prog, n_nodes) }
+    unsafe fn points_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32 { isomc_points_sdf(h, prog, n_nodes) }
 }
 impl Distance for Directed {
     unsafe fn extract_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32 { isomc_extract_sdf_directed(h, prog, n_nodes) }
+    unsafe fn points_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32 { isomc_points_sdf_directed(h, prog, n_nodes) }
 }
 
 /// `MarchingCubes<D: Distance>` as in the reference (src/marching_cubes.rs:38-43); `MarchingCubes::<Signed>::new(size)` and
@@ -239,16 +244,17 @@ impl<D: Distance> MarchingCubes<D> {
 
 impl<D: Distance> Drop for MarchingCubes<D> { fn drop(&mut self) { unsafe { isomc_destroy(self.h); } } }
 
-/// reference src/point_cloud.rs:33-63: one vertex per active cell (midpoint of corners 0 and 6), no face data
-pub struct PointCloud { mc: MarchingCubes<Signed> }
-impl PointCloud {
-    pub fn new(size: usize) -> Self { Self { mc: MarchingCubes::<Signed>::new(size) } }
+/// reference src/point_cloud.rs:28-63: `PointCloud<D: Distance>`, one vertex per active cell (midpoint of corners 0 and 6), no face data
+pub struct PointCloud<D: Distance = Signed> { mc: MarchingCubes<D> }
+impl<D: Distance> PointCloud<D> {
+    pub fn new(size: usize) -> Self { Self { mc: MarchingCubes::<D>::new(size) } }
     pub fn extract<S: DeviceSource, E: Extractor>(&mut self, source: &S, extractor: &mut E) {
         let mut prog = Vec::new();
         source.encode(&mut prog);
-        self.mc.check(unsafe { isomc_points_sdf(self.mc.h, prog.as_ptr(), prog.len() as u32) });
+        self.mc.check(unsafe { D::points_sdf(self.mc.h, prog.as_ptr(), prog.len() as u32) });
         self.mc.deliver(extractor);
     }
+    /// (a dense scalar lattice has no Directed distances: `PointCloud::<Signed>` only in practice)
     pub fn extract_grid<E: Extractor>(&mut self, grid: &DenseGrid, extractor: &mut E) {
         assert_eq!(grid.size, self.mc.size);
         self.mc.check(unsafe { isomc_points_grid_host(self.mc.h, grid.data.as_ptr()) });

@@ -589,6 +589,19 @@ def test_point_cloud_matches_oracle(iso, oracle):
     assert iso.PointCloud(1).extract_device(iso.Sampler(iso_source("sphere03")))[0] == 0
 
 
+def test_directed_point_cloud_matches_oracle(iso, oracle):
+    """PointCloud<Directed> over implicit trees: bit-identical to the restatement; a dense lattice is refused"""
+    for name, size in (("sphere03", 24), ("csgA", 40), ("csgB", 33), ("torus_origin", 32)):
+        want = oracle.point_cloud_sdf_directed(size, oracle_prog(name))
+        pc = iso.PointCloud(size, distance="directed")
+        pts = []
+        pc.extract(iso.Sampler(iso_source(name)), iso.OnlyVertices(pts))
+        assert np.array_equal(np.asarray(pts, np.float32).view(np.uint32), want.view(np.uint32)), (name, size)
+        with pytest.raises(TypeError):
+            pc.extract_device(iso.DenseGrid(np.zeros((size + 1, size, size), np.float32)))
+        pc.close()
+
+
 def test_interleaved_normals_match_oracle(iso, oracle):
     """IndexedInterleavedNormals + CentralDifference (examples/sampler.rs:79-103): positions and central-difference
     normals, evaluated on the device, bit-identical to the restated reference"""

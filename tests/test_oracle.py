@@ -258,3 +258,29 @@ def test_widened_rows_match_committed_golden_hashes(oracle):
         xyz, _, _ = O.extract_sdf(g["size"], oracle_prog(g["shape"]))
         xyzn = O.interleaved_normals_cd(O.program(inner[g["shape"]]), xyz, g["epsilon"], [(.5, .5, .5)])
         assert (len(xyzn), sha(xyzn, "<f4")) == (g["vertices"], g["sha_vn"]), g
+
+
+def test_directed_point_cloud_restatement(oracle):
+    """PointCloud<Directed> (point_cloud.rs:50-63 with distance.rs:77-80): one point per cell whose corners are not all on one side
+    under "outside iff any component of the directed distance is positive"; cross-checked against the vertex-sharing Directed
+    extract (same active-cell count) and against a numpy formulation from sample_vector"""
+    from helpers import oracle_prog
+    for name, size in (("sphere03", 20), ("csgA", 24), ("torus", 22)):
+        prog = oracle_prog(name)
+        pts = oracle.point_cloud_sdf_directed(size, prog)
+        _, _, act = oracle.extract_sdf_directed(size, prog)
+        assert len(pts) // 3 == act and act > 0
+        inv = np.float32(1.0) / np.float32(size - 1)
+        ax = (np.arange(size, dtype=np.float32) * inv).astype(np.float32)
+        zs = (np.arange(size + 1, dtype=np.float32) * inv).astype(np.float32)
+        Z, Y, X = np.meshgrid(zs, ax, ax, indexing="ij")
+        P = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1).astype(np.float32)
+        V = oracle.sample_sdf_vector(prog, P).reshape(size + 1, size, size, 3)
+        inside = ~((V[..., 0] > 0) | (V[..., 1] > 0) | (V[..., 2] > 0))
+        n_in = sum(inside[dz:size + dz, dy:size - 1 + dy, dx:size - 1 + dx].astype(np.int32) for dz in (0, 1) for dy in (0, 1) for dx in (0, 1))
+        active = (n_in != 0) & (n_in != 8)
+        zz, yy, xx = np.nonzero(active)
+        half = np.float32(0.5)
+        want = np.stack([half * ax[xx] + half * ax[xx + 1], half * ax[yy] + half * ax[yy + 1], half * zs[zz] + half * zs[zz + 1]], axis=1)
+        assert np.array_equal(pts.reshape(-1, 3).view(np.uint32), want.astype(np.float32).view(np.uint32)), name
+
