@@ -191,6 +191,7 @@ int32_t isomc_slab_create(uint32_t size, uint32_t z_begin, uint32_t z_end, int32
 /* phase 1: classify + count.  d_slab = first sample layer of the slab, (layers)*N*N f32 */
 int32_t isomc_slab_count_grid_device(isomc_t *h, const float *d_slab);
 int32_t isomc_slab_count_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes);
+int32_t isomc_slab_count_sdf_directed(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes);   /* MarchingCubes<Directed> on a slab */
 /* totals[0] = vertices owned by this slab, [1] = of those, vertices created before the slab's
  * last cell layer, [2] = triangles owned by this slab.  Synchronises the stream. */
 int32_t isomc_slab_totals(isomc_t *h, uint64_t totals[3]);
@@ -247,6 +248,7 @@ int32_t isomc_sharded_handle(isomc_sharded_t *s, uint32_t rank, isomc_t **h);   
 /* d_slabs[r] = rank r's sample layers on ITS device (n_sample_layers * N * N f32, first = first_sample_layer) */
 int32_t isomc_sharded_extract_grid(isomc_sharded_t *s, const float *const *d_slabs);
 int32_t isomc_sharded_extract_sdf(isomc_sharded_t *s, const isomc_sdf_node *prog, uint32_t n_nodes);
+int32_t isomc_sharded_extract_sdf_directed(isomc_sharded_t *s, const isomc_sdf_node *prog, uint32_t n_nodes);   /* <Directed> */
 int32_t isomc_sharded_counts(isomc_sharded_t *s, uint64_t *n_vertices, uint64_t *n_triangles, uint64_t *n_active_cells);   /* whole mesh */
 int32_t isomc_sharded_rank_counts(isomc_sharded_t *s, uint32_t rank, uint64_t *n_vertices, uint64_t *n_triangles, uint64_t *n_active_cells);
 int32_t isomc_sharded_copy_out(isomc_sharded_t *s, float *xyz /* 3*V */, uint32_t *idx /* 3*T */);

@@ -77,6 +77,7 @@ SIGNATURES = {
     "isomc_slab_create": (_I32, [_U32, _U32, _U32, _I32, C.POINTER(_P)]),
     "isomc_slab_count_grid_device": (_I32, [_P, _P]),
     "isomc_slab_count_sdf": (_I32, [_P, _P, _U32]),
+    "isomc_slab_count_sdf_directed": (_I32, [_P, _P, _U32]),
     "isomc_slab_totals": (_I32, [_P, C.POINTER(_U64 * 3)]),
     "isomc_slab_totals_device": (_I32, [_P, C.POINTER(_P)]),
     "isomc_slab_emit": (_I32, [_P, _U64, _U64]),
@@ -99,6 +100,7 @@ SIGNATURES = {
     "isomc_sharded_handle": (_I32, [_P, _U32, C.POINTER(_P)]),
     "isomc_sharded_extract_grid": (_I32, [_P, _P]),
     "isomc_sharded_extract_sdf": (_I32, [_P, _P, _U32]),
+    "isomc_sharded_extract_sdf_directed": (_I32, [_P, _P, _U32]),
     "isomc_sharded_counts": (_I32, [_P, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
     "isomc_sharded_rank_counts": (_I32, [_P, _U32, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
     "isomc_sharded_copy_out": (_I32, [_P, _P, _P]),

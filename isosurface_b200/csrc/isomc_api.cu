@@ -1245,6 +1245,17 @@ int32_t isomc_slab_count_sdf(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_
     return enqueue_count(h, false);
 }
 
+/* the same with the tree sampled as Directed distances (MarchingCubes<Directed> on a slab) */
+int32_t isomc_slab_count_sdf_directed(isomc_t *h, const isomc_sdf_node *prog, uint32_t n_nodes) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    rc = validate_program(h, prog, n_nodes, &h->prog);
+    if (rc) return rc;
+    h->kind = SRC_SDF; h->d_grid = nullptr; h->directed = true;
+    return enqueue_count(h, false);
+}
+
 int32_t isomc_slab_totals(isomc_t *h, uint64_t totals[3]) {
     if (!h || !totals) return ISOMC_ERR_BAD_ARG;
     if (!h->counted) return fail(h, ISOMC_ERR_NO_RESULT, "slab_totals before slab_count");

@@ -271,6 +271,13 @@ int32_t isomc_sharded_extract_sdf(isomc_sharded_t *s, const isomc_sdf_node *prog
     return exchange_and_emit(s);
 }
 
+int32_t isomc_sharded_extract_sdf_directed(isomc_sharded_t *s, const isomc_sdf_node *prog, uint32_t n_nodes) {
+    if (!s) return ISOMC_ERR_BAD_ARG;
+    s->have_result = false;
+    for (uint32_t r = 0; r < s->n; ++r) SRC(s, r, isomc_slab_count_sdf_directed(s->h[r], prog, n_nodes));
+    return exchange_and_emit(s);
+}
+
 int32_t isomc_sharded_counts(isomc_sharded_t *s, uint64_t *n_vertices, uint64_t *n_triangles, uint64_t *n_active_cells) {
     if (!s) return ISOMC_ERR_BAD_ARG;
     if (!s->have_result) return sfail(s, ISOMC_ERR_NO_RESULT, "no sharded extract has completed");

@@ -222,10 +222,12 @@ class ShardedMarchingCubes:
         self._check(self._lib.isomc_sharded_extract_grid(self._h, arr))
         return self.counts()
 
-    def extract_sdf(self, source):
+    def extract_sdf(self, source, distance="signed"):
+        """distance="directed": MarchingCubes<Directed> over the slabs (the tree sampled through sample_vector)"""
         from .source import Sampler, encode_program
         prog = encode_program(source.source if isinstance(source, Sampler) else source)
-        self._check(self._lib.isomc_sharded_extract_sdf(self._h, prog.ctypes.data, len(prog)))
+        fn = self._lib.isomc_sharded_extract_sdf_directed if distance == "directed" else self._lib.isomc_sharded_extract_sdf
+        self._check(fn(self._h, prog.ctypes.data, len(prog)))
         return self.counts()
 
     def counts(self):

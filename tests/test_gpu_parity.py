@@ -828,6 +828,20 @@ def test_sharded_api_on_one_device(iso, oracle, world):
     sh.close()
 
 
+def test_directed_marching_cubes_on_slabs(iso, oracle):
+    """MarchingCubes<Directed> sharded into z-slabs (isomc_sharded_extract_sdf_directed): the concatenation is the unsharded
+    Directed mesh of the restatement"""
+    from isosurface_b200.sharded import ShardedMarchingCubes
+    for name, size, world in (("csgA", 40, 3), ("torus", 33, 4)):
+        oxyz, oidx, oact = oracle.extract_sdf_directed(size, oracle_prog(name))
+        sh = ShardedMarchingCubes(size, [0] * world)
+        for _ in range(2):
+            nv, nt, na = sh.extract_sdf(iso.Sampler(iso_source(name)), distance="directed")
+            xyz, idx = sh.copy_out()
+            assert na == oact and mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == "", (name, world)
+        sh.close()
+
+
 def test_sharded_api_nccl_all_devices(iso, oracle):
     """isomc_sharded_* over every GPU of the box, each slab's lattice on its own device; both forms of the totals exchange"""
     import torch
