@@ -751,6 +751,28 @@ def test_window_matches_committed_oracle_hashes(iso, isolib, name):
     assert sha(idx, "<u4") == g["sha_i"] and sha(xyz, "<f4") == g["sha_v"]
 
 
+@pytest.mark.parametrize("size,z_cells,kind,seed", [(2112, 3, 1, 5), (2600, 2, 3, 9)])
+def test_rows_wider_than_a_warp_pass(iso, isolib, oracle, size, z_cells, kind, seed):
+    """lattices wider than 2049 samples: a cell row has more than 64 segments, so the counting kernel runs its WIDE form (a pass is a
+    64-segment chunk of one row, rows closed across passes).  A few cell layers of such a lattice against the live oracle."""
+    from isosurface_b200 import _lib
+    t = synth(iso, kind, size, seed, 0, z_cells + 1)
+    host = t.cpu().numpy().reshape(z_cells + 1, size, size)
+    oxyz, oidx, oact = oracle.extract_grid(size, host, z_cells=z_cells)
+    assert oact > 1000
+    h = C.c_void_p()
+    _lib.check(isolib.isomc_slab_create(size, 0, z_cells, 0, C.byref(h)))
+    for _ in range(2):  # (second extract: inline emission, graph replay)
+        _lib.check(isolib.isomc_slab_count_grid_device(h, C.c_void_p(t.data_ptr())), h)
+        _lib.check(isolib.isomc_slab_emit(h, 0, 0), h)
+        v, tr, a = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _lib.check(isolib.isomc_counts(h, C.byref(v), C.byref(tr), C.byref(a)), h)
+        xyz, idx = np.empty(3 * v.value, np.float32), np.empty(3 * tr.value, np.uint32)
+        _lib.check(isolib.isomc_copy_out(h, xyz.ctypes.data, idx.ctypes.data), h)
+        assert a.value == oact and mesh_diff(xyz, idx, oxyz, oidx, POS_TOL) == ""
+    isolib.isomc_destroy(h)
+
+
 def test_fbm512_whole_mesh_against_live_oracle(iso, oracle):
     """BASELINE C3: the whole 512^3 fBm mesh (6.9 M vertices, 13.8 M triangles) against a LIVE lean oracle run on the same
     field bytes -- memcmp on both streams (tens of seconds of CPU time)"""
