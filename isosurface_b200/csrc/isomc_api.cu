@@ -72,6 +72,7 @@ struct isomc {
      * while everything a kernel takes by value stays the same (pipe_key: pointers, capacities, plan) */
     cudaGraphExec_t pipe_exec = nullptr;
     uint64_t pipe_key[12] = {};
+    bool graph_broken = false; /* capture / instantiation failed once on this handle: launch directly */
     uint32_t last_blocks = 0; /* list blocks the previous extract used (sizes the emission grid of small lattices) */
     uint32_t pipe_launches = 0, pipe_chunks = 1, pipe_chunk_l[MAX_CHUNKS + 1] = {};
     /* slab totals exchanged over peer memory (isomc_slab_connect*): own mailbox, the ranks' mailbox addresses, step counter */
@@ -397,15 +398,25 @@ int32_t enqueue_graphed(isomc *h, const PipePlan &pp, bool emit_inline) {
     if (h->pipe_exec) { cudaGraphExecDestroy(h->pipe_exec); h->pipe_exec = nullptr; }
     if (pipelined && !h->s_sign) return pipelined_launches(h, pp); /* (its streams and events are created outside a capture) */
     if (h->cap_v == 0 && h->cap_t == 0) return serial_launches(h, emit_inline);
-    CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    /* A driver that cannot capture or instantiate this sequence (programmatic edges in a capture need CUDA 12.3+) must not cost
+     * the extract: the handle then launches directly from now on. */
+    if (h->graph_broken || cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        h->graph_broken = true;
+        return pipelined ? pipelined_launches(h, pp) : serial_launches(h, emit_inline);
+    }
     int32_t rc = pipelined ? pipelined_launches(h, pp) : serial_launches(h, emit_inline);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (e != cudaSuccess) return fail(h, ISOMC_ERR_CUDA, "stream capture of the extract failed: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&h->pipe_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { h->pipe_exec = nullptr; return fail(h, ISOMC_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    if (rc == ISOMC_OK && e == cudaSuccess) e = cudaGraphInstantiate(&h->pipe_exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != ISOMC_OK || e != cudaSuccess) { /* nothing has run yet (the launches were only recorded): run them directly */
+        cudaGetLastError();
+        h->pipe_exec = nullptr;
+        h->graph_broken = true;
+        h->stats.kernel_launches = 0;
+        return pipelined ? pipelined_launches(h, pp) : serial_launches(h, emit_inline);
+    }
     memcpy(h->pipe_key, key, sizeof key);
     h->pipe_launches = h->stats.kernel_launches;
     h->pipe_chunks = h->n_chunks;
