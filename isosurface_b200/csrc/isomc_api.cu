@@ -587,6 +587,9 @@ int32_t finish_impl(isomc *h) {
             }
         for (auto &e : h->tl) cudaEventDestroy(e.second);
         h->tl.clear();
+        fprintf(stderr, "[isomc timeline] %llu list blocks of %u entries for %llu listed cells (%.1f %% of the slots used)\n",
+                (unsigned long long)h->h_totals[7], LIST_BLOCK, (unsigned long long)h->h_totals[2],
+                h->h_totals[7] ? 100.0 * (double)h->h_totals[2] / ((double)h->h_totals[7] * LIST_BLOCK) : 0.0);
     }
     h->n_v = nv; h->n_t = nt; h->n_a = h->h_totals[11];
     h->have_result = true;
