@@ -131,6 +131,11 @@ int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, 
 int32_t isomc_batch_create(uint32_t size, uint32_t n_chunks, int32_t device, isomc_t **out);
 int32_t isomc_extract_sdf_batch(isomc_t *h, const isomc_sdf_node *progs, const uint32_t *n_nodes, uint32_t n_chunks);
 int32_t isomc_batch_offsets(isomc_t *h, uint64_t *v_offsets, uint64_t *t_offsets);
+/* the same for DENSE chunks (voxel worlds cut into size^3 chunks): `n_chunks` lattices of size * size * (size + 1) f32 back to back.
+ * Device-resident lattices are used in place and must fill the handle (n_chunks == the handle's capacity); host lattices are
+ * copied, and a partly filled batch is padded with empty lattices. */
+int32_t isomc_extract_grid_batch_device(isomc_t *h, const float *d_lattices, uint32_t n_chunks);
+int32_t isomc_extract_grid_batch_host(isomc_t *h, const float *h_lattices, uint32_t n_chunks);
 
 /* ---- PointCloud::<Signed>::new(size).extract(&source, &mut extractor)  (reference src/point_cloud.rs:50-63) ----
  * One point per active cell (cube index neither 0 nor 255): corners[0].lerp(corners[6], 0.5), in (z, y, x) cell order.

@@ -263,6 +263,23 @@ class BatchedMarchingCubes {
         const uint32_t b = (uint32_t)n_nodes.size();
         if (b < 1 || b > n_chunks_ || extractors.size() != b) throw Error(ISOMC_ERR_BAD_ARG, "batch size / extractor count mismatch");
         check(isomc_extract_sdf_batch(h_, flat.data(), n_nodes.data(), b));
+        deliver(b, extractors);
+    }
+    // dense chunks: `n` host lattices of size * size * (size + 1) floats back to back (a voxel world cut into chunks)
+    void extract_grids(const float *lattices, uint32_t n, const std::vector<Extractor *> &extractors) {
+        if (n < 1 || n > n_chunks_ || extractors.size() != n) throw Error(ISOMC_ERR_BAD_ARG, "batch size / extractor count mismatch");
+        check(isomc_extract_grid_batch_host(h_, lattices, n));
+        deliver(n, extractors);
+    }
+    // the same with the handle's whole capacity of lattices already in device memory (used in place)
+    void extract_device_grids(const float *d_lattices, const std::vector<Extractor *> &extractors) {
+        if (extractors.size() != n_chunks_) throw Error(ISOMC_ERR_BAD_ARG, "a device batch fills the handle: one extractor per chunk");
+        check(isomc_extract_grid_batch_device(h_, d_lattices, n_chunks_));
+        deliver(n_chunks_, extractors);
+    }
+
+  private:
+    void deliver(uint32_t b, const std::vector<Extractor *> &extractors) {
         uint64_t nv = 0, nt = 0;
         check(isomc_counts(h_, &nv, &nt, nullptr));
         std::vector<float> xyz(3 * nv);
@@ -281,8 +298,6 @@ class BatchedMarchingCubes {
             for (uint64_t i = 3 * to[c]; i < 3 * to[c + 1]; ++i) ex.extract_index(idx[i]);
         }
     }
-
-  private:
     void check(int32_t rc) { if (rc) throw Error(rc, isomc_last_error(h_)); }
     isomc_t *h_ = nullptr;
     uint32_t n_chunks_;

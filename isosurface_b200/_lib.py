@@ -55,6 +55,8 @@ SIGNATURES = {
     "isomc_batch_create": (_I32, [_U32, _U32, _I32, C.POINTER(_P)]),
     "isomc_extract_sdf_batch": (_I32, [_P, _P, _P, _U32]),
     "isomc_batch_offsets": (_I32, [_P, _P, _P]),
+    "isomc_extract_grid_batch_device": (_I32, [_P, _P, _U32]),
+    "isomc_extract_grid_batch_host": (_I32, [_P, _P, _U32]),
     "isomc_points_sdf": (_I32, [_P, _P, _U32]),
     "isomc_points_sdf_directed": (_I32, [_P, _P, _U32]),
     "isomc_points_grid_device": (_I32, [_P, _P]),

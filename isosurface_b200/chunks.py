@@ -103,6 +103,37 @@ class BatchedMarchingCubes:
         _lib.check(self._lib.isomc_batch_offsets(self._h, vo.ctypes.data, to.ctypes.data), self._h)
         return xyz, idx, vo[:len(progs) + 1], to[:len(progs) + 1]
 
+    def _results(self, n):
+        import ctypes as C
+        import numpy as np
+        from . import _lib
+        v, t, a = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _lib.check(self._lib.isomc_counts(self._h, C.byref(v), C.byref(t), C.byref(a)), self._h)
+        xyz, idx = np.empty(3 * v.value, np.float32), np.empty(3 * t.value, np.uint32)
+        _lib.check(self._lib.isomc_copy_out(self._h, xyz.ctypes.data, idx.ctypes.data), self._h)
+        vo, to = np.zeros(self.n_chunks + 1, np.uint64), np.zeros(self.n_chunks + 1, np.uint64)
+        _lib.check(self._lib.isomc_batch_offsets(self._h, vo.ctypes.data, to.ctypes.data), self._h)
+        return xyz, idx, vo[:n + 1], to[:n + 1]
+
+    def extract_grids(self, lattices):
+        """Dense chunks: `lattices` = a float32 array of shape (n, size + 1, size, size) on the host (n <= n_chunks), or a CUDA
+        tensor of exactly n_chunks lattices (used in place).  Returns (xyz, idx, v_offsets, t_offsets) like extract_batch."""
+        import numpy as np
+        from . import _lib
+        per = self.size * self.size * (self.size + 1)
+        if hasattr(lattices, "data_ptr"):
+            if not lattices.is_cuda or lattices.numel() != per * self.n_chunks or str(lattices.dtype) != "torch.float32" or not lattices.is_contiguous():
+                raise ValueError("a device batch is a contiguous float32 CUDA tensor of exactly n_chunks lattices")
+            n = self.n_chunks
+            _lib.check(self._lib.isomc_extract_grid_batch_device(self._h, int(lattices.data_ptr()), n), self._h)
+        else:
+            arr = np.ascontiguousarray(lattices, dtype=np.float32)
+            if arr.size % per or not 1 <= arr.size // per <= self.n_chunks:
+                raise ValueError("host lattices must be (n, size + 1, size, size) with 1 <= n <= n_chunks")
+            n = arr.size // per
+            _lib.check(self._lib.isomc_extract_grid_batch_host(self._h, arr.ctypes.data, n), self._h)
+        return self._results(n)
+
     def extract_many(self, sources, deliver=None):
         """any number of chunks, `n_chunks` per kernel sequence; `deliver(i, xyz, idx)` per chunk in submission order"""
         sources = list(sources)

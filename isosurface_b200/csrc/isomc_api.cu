@@ -58,6 +58,7 @@ struct isomc {
     uint32_t *segA = nullptr;         /* PointCloud: per-segment prefixes (allocated on first use, with `signs`) */
     /* batched chunks (isomc_batch_create): `batch` lattices stacked in z (Geo.zper), one implicit tree each */
     uint32_t batch = 0, batch_used = 0;
+    bool batch_call = false; /* the extract being enqueued comes from a batch entry point */
     SdfProgram *d_progs = nullptr, *h_progs = nullptr; /* h_progs pinned */
     uint32_t *chunkV = nullptr, *chunkT = nullptr;     /* device: [batch + 1] output slots of the chunks' first vertex / triangle */
     uint32_t *h_chunk = nullptr;                       /* pinned: 2 * (batch + 1) */
@@ -834,8 +835,8 @@ int32_t isomc_reserve(isomc_t *h, uint64_t n_vertices, uint64_t n_triangles) {
 /* ---- full extracts ------------------------------------------------------------------------ */
 
 static int32_t enqueue_full(isomc_t *h) {
-    if (h->batch && h->kind != SRC_SDF_BATCH)
-        return fail(h, ISOMC_ERR_BAD_ARG, "this handle is a batch of %u chunks: use isomc_extract_sdf_batch", h->batch);
+    if (h->batch && !h->batch_call)
+        return fail(h, ISOMC_ERR_BAD_ARG, "this handle is a batch of %u chunks: use isomc_extract_sdf_batch / isomc_extract_grid_batch_*", h->batch);
     if (h->z_begin != 0 || h->z_end != h->size)
         return fail(h, ISOMC_ERR_BAD_ARG, "this handle is a slab [%u, %u): use the isomc_slab_* calls", h->z_begin, h->z_end);
     int32_t rc = bind_device(h);
@@ -1035,7 +1036,46 @@ int32_t isomc_extract_sdf_batch(isomc_t *h, const isomc_sdf_node *progs, const u
     CU(h, cudaMemcpyAsync(h->d_progs, h->h_progs, h->batch * sizeof(SdfProgram), cudaMemcpyHostToDevice, h->stream));
     h->kind = SRC_SDF_BATCH; h->d_grid = nullptr; h->directed = false;
     h->batch_used = n_chunks;
+    h->batch_call = true;
     rc = enqueue_full(h);
+    h->batch_call = false;
+    return rc ? rc : isomc_finish(h);
+}
+
+/* the same for dense chunks: the handle's `n_chunks` lattices (size * size * (size + 1) f32 each) back to back in device memory --
+ * which IS the stacked lattice the kernels walk, so nothing is copied */
+int32_t isomc_extract_grid_batch_device(isomc_t *h, const float *d_lattices, uint32_t n_chunks) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h->batch) return fail(h, ISOMC_ERR_BAD_ARG, "not a batch handle (isomc_batch_create)");
+    if (!d_lattices) return fail(h, ISOMC_ERR_BAD_ARG, "d_lattices == NULL");
+    if (n_chunks != h->batch)
+        return fail(h, ISOMC_ERR_BAD_ARG, "a device-resident batch must fill the handle: %u lattices given, the handle holds %u", n_chunks, h->batch);
+    h->kind = SRC_GRID; h->d_grid = d_lattices; h->directed = false;
+    h->batch_used = n_chunks;
+    h->batch_call = true;
+    int32_t rc = enqueue_full(h);
+    h->batch_call = false;
+    return rc ? rc : isomc_finish(h);
+}
+
+/* host lattices: copied into the handle's staging buffer; lattices the call does not fill are padded with a positive value (no surface) */
+int32_t isomc_extract_grid_batch_host(isomc_t *h, const float *h_lattices, uint32_t n_chunks) {
+    if (!h) return ISOMC_ERR_BAD_ARG;
+    if (!h->batch) return fail(h, ISOMC_ERR_BAD_ARG, "not a batch handle (isomc_batch_create)");
+    if (!h_lattices || n_chunks < 1 || n_chunks > h->batch)
+        return fail(h, ISOMC_ERR_BAD_ARG, "bad batch arguments (%u chunks, the handle holds %u)", n_chunks, h->batch);
+    int32_t rc = bind_device(h);
+    if (rc) return rc;
+    const size_t per = (size_t)h->g.N * h->g.N * (h->g.N + 1) * sizeof(float), bytes = per * h->batch;
+    if (!h->stage_grid) CU(h, cudaMalloc(&h->stage_grid, bytes));
+    CU(h, cudaMemcpyAsync(h->stage_grid, h_lattices, per * n_chunks, cudaMemcpyHostToDevice, h->stream));
+    if (n_chunks < h->batch) /* 0x7F7F7F7F = 3.4e38f: outside everywhere */
+        CU(h, cudaMemsetAsync(reinterpret_cast<char *>(h->stage_grid) + per * n_chunks, 0x7F, per * (h->batch - n_chunks), h->stream));
+    h->kind = SRC_GRID; h->d_grid = h->stage_grid; h->directed = false;
+    h->batch_used = n_chunks;
+    h->batch_call = true;
+    rc = enqueue_full(h);
+    h->batch_call = false;
     return rc ? rc : isomc_finish(h);
 }
 

@@ -36,6 +36,7 @@ extern "C" {
     fn isomc_batch_create(size: u32, n_chunks: u32, device: i32, out: *mut *mut isomc_t) -> i32;
     fn isomc_extract_sdf_batch(h: *mut isomc_t, progs: *const isomc_sdf_node, n_nodes: *const u32, n_chunks: u32) -> i32;
     fn isomc_batch_offsets(h: *mut isomc_t, v_offsets: *mut u64, t_offsets: *mut u64) -> i32;
+    fn isomc_extract_grid_batch_host(h: *mut isomc_t, h_lattices: *const f32, n_chunks: u32) -> i32;
     // z-slabs: one rank per process (the host brings the exchange) ...
     pub fn isomc_slab_create(size: u32, z_begin: u32, z_end: u32, device: i32, out: *mut *mut isomc_t) -> i32;
     pub fn isomc_slab_count_grid_device(h: *mut isomc_t, d_slab: *const f32) -> i32;
@@ -281,8 +282,22 @@ impl BatchedMarchingCubes {
             s.encode(&mut flat);
             n_nodes.push((flat.len() - before) as u32);
         }
-        let check = |rc: i32| assert!(rc == 0, "isomc error {}: {:?}", rc, unsafe { std::ffi::CStr::from_ptr(isomc_last_error(self.h)) });
-        check(unsafe { isomc_extract_sdf_batch(self.h, flat.as_ptr(), n_nodes.as_ptr(), n_nodes.len() as u32) });
+        self.check(unsafe { isomc_extract_sdf_batch(self.h, flat.as_ptr(), n_nodes.as_ptr(), n_nodes.len() as u32) });
+        self.deliver(extractors);
+    }
+    /// Dense chunks (a voxel world cut into `size`^3 chunks): `lattices` holds `extractors.len()` lattices of
+    /// `size * size * (size + 1)` samples back to back; chunk b goes to `extractors[b]`.
+    pub fn extract_grids<E: Extractor>(&mut self, lattices: &[f32], extractors: &mut [E]) {
+        let n = extractors.len();
+        assert!(n >= 1 && n <= self.n_chunks && lattices.len() % n == 0);
+        self.check(unsafe { isomc_extract_grid_batch_host(self.h, lattices.as_ptr(), n as u32) });
+        self.deliver(extractors);
+    }
+    fn check(&self, rc: i32) {
+        assert!(rc == 0, "isomc error {}: {:?}", rc, unsafe { std::ffi::CStr::from_ptr(isomc_last_error(self.h)) });
+    }
+    fn deliver<E: Extractor>(&mut self, extractors: &mut [E]) {
+        let check = |rc: i32| self.check(rc);
         let (mut nv, mut nt) = (0u64, 0u64);
         check(unsafe { isomc_counts(self.h, &mut nv, &mut nt, std::ptr::null_mut()) });
         let (mut xyz, mut idx) = (vec![0f32; 3 * nv as usize], vec![0u32; 3 * nt as usize]);

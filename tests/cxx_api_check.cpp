@@ -66,6 +66,28 @@ int main() {
                 if (ov != bv[b] || oi != bi[b]) { std::printf("batched chunk %d differs from the single extract\n", b); return 1; }
             }
         }
+        // dense chunks through the same batch handle: chunk b = the host-grid extract of lattice b
+        {
+            const uint32_t n = 24, B = 3;
+            const size_t per = (size_t)n * n * (n + 1);
+            std::vector<float> lat(per * B);
+            for (size_t i = 0; i < lat.size(); ++i) lat[i] = (float)((i * 2246822519u >> 9) % 1000) - 480.0f;
+            std::vector<std::vector<float>> bv(B);
+            std::vector<std::vector<uint32_t>> bi(B);
+            std::vector<IndexedVertices> sinks;
+            for (uint32_t b = 0; b < B; ++b) sinks.emplace_back(bv[b], bi[b]);
+            std::vector<Extractor *> ptrs;
+            for (auto &sk : sinks) ptrs.push_back(&sk);
+            BatchedMarchingCubes batch(n, B);
+            batch.extract_grids(lat.data(), B, ptrs);
+            MarchingCubes one(n);
+            for (uint32_t b = 0; b < B; ++b) {
+                std::vector<float> ov; std::vector<uint32_t> oi;
+                IndexedVertices os(ov, oi);
+                one.extract(DenseGrid{lat.data() + per * b, n, false}, os);
+                if (ov != bv[b] || oi != bi[b]) { std::printf("batched dense chunk %u differs from the single extract\n", b); return 1; }
+            }
+        }
         // the same extract over z-slabs (all on device 0 here; distinct devices exchange over NVLink): identical mesh
         {
             std::vector<float> sv, ov; std::vector<uint32_t> si, oi;
