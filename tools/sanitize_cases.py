@@ -45,6 +45,12 @@ drv = iso.BatchedMarchingCubes(24, n_chunks=6)
 srcs = [iso.Sampler(iso.Translate((0.3 + 0.08 * i, 0.5, 0.5), iso.Sphere(0.2))) for i in range(9)]
 print("batch", [len(m[1]) // 3 for m in drv.extract_many(srcs)])
 drv.close()
+# dense chunks through the same stacked-lattice handle: a device batch (used in place) and a partly filled host batch
+gdrv = iso.BatchedMarchingCubes(20, n_chunks=4)
+lat = np.random.default_rng(5).standard_normal((4, 21, 20, 20)).astype(np.float32)
+print("batch grids", [int(v) for v in gdrv.extract_grids(torch.from_numpy(lat).cuda())[2]],
+      [int(v) for v in gdrv.extract_grids(lat[:3])[2]])
+gdrv.close()
 lib = _lib.load()
 slabs = [SlabMarchingCubes(size, r, world) for r in range(world)]
 boxes = (C.c_void_p * world)()
