@@ -949,14 +949,21 @@ int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, 
         h->have_result = false; h->counted = false; h->emitted = false; h->totals_valid = false;
         h->stats.kernel_launches = 0; h->stats.emit_reruns = 0;
         h->emit_inline = true;
-        /* chunk plan: up to MAX_CHUNKS chunks of >= 8 cell layers */
+        /* chunk plan: up to MAX_CHUNKS chunks of >= 8 cell layers.  The copy-in of the lattice is what the call waits for, so what
+         * is left to do when its last byte has arrived -- the kernels and the copy-out of the LAST chunk -- is the only part
+         * that is not hidden: the last chunks are made small (8, 16, ... layers), the ones before share the rest evenly. */
         {
             uint32_t n = g.ncl / 8 < (uint32_t)MAX_CHUNKS ? g.ncl / 8 : (uint32_t)MAX_CHUNKS;
             if (n < 1) n = 1;
-            const uint32_t per = (g.ncl + n - 1) / n;
-            n = (g.ncl + per - 1) / per;
-            h->n_chunks = n;
-            for (uint32_t c = 0; c <= n; ++c) h->chunk_l[c] = c * per < g.ncl ? c * per : g.ncl;
+            uint32_t tail[MAX_CHUNKS], n_tail = 0, tail_sum = 0;
+            static const bool graded = !(getenv("ISOMC_HOST_TAIL") && atoi(getenv("ISOMC_HOST_TAIL")) == 0);
+            for (uint32_t t = 8; graded && n_tail + 2 < n && t < g.ncl / n && tail_sum + t < g.ncl / 4; t *= 2) { tail[n_tail++] = t; tail_sum += t; }
+            const uint32_t n_head = n - n_tail, head = g.ncl - tail_sum, per = (head + n_head - 1) / n_head;
+            uint32_t c = 0, l = 0;
+            h->chunk_l[0] = 0;
+            while (l < head) { l = l + per < head ? l + per : head; h->chunk_l[++c] = l; }
+            for (uint32_t i = n_tail; i-- > 0;) { l += tail[i]; h->chunk_l[++c] = l; }
+            h->n_chunks = c;
         }
         const uint64_t cap_v0 = h->cap_v, cap_t0 = h->cap_t;
         CU(h, cudaMemsetAsync(h->layerTot, 0, h->zero_bytes, h->stream));
