@@ -583,6 +583,17 @@ def run_ours(args):
                        "d2h_bytes_per_step": 12 * V + 12 * T, "ms_per_step": dt * 1e3, "steps": n_e2e,
                        "api": "isomc_extract_grid_host_to: host lattice -> host mesh, z-chunk pipelined (pinned host buffers)" if kind == "grid"
                        else "MarchingCubes.extract(Sampler(source), ArrayMesh())"}
+        if kind == "grid":
+            # what the link alone takes for the same pinned lattice (no kernels, no copy-out): the floor of ms_per_step
+            best = None
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                R.grid.view(-1).copy_(hgrid, non_blocking=True)
+                torch.cuda.synchronize()
+                d = time.perf_counter() - t0
+                best = d if best is None or d < best else best
+            line["e2e"]["h2d_only_ms"] = best * 1e3
         mc.close()
     elif kind == "grid":
         # every rank: pinned host slab -> device, count, all-gather, emit, its part of the mesh -> pinned host buffers
