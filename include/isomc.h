@@ -130,6 +130,8 @@ int32_t isomc_extract_grid_host_to(isomc_t *h, const float *h_grid, float *xyz, 
  * is byte for byte what a single isomc_extract_sdf of its program returns. */
 int32_t isomc_batch_create(uint32_t size, uint32_t n_chunks, int32_t device, isomc_t **out);
 int32_t isomc_extract_sdf_batch(isomc_t *h, const isomc_sdf_node *progs, const uint32_t *n_nodes, uint32_t n_chunks);
+/* the D = Directed instantiation per chunk (isomc_extract_sdf_directed; reference src/marching_cubes.rs:38-43, src/distance.rs:72-104) */
+int32_t isomc_extract_sdf_batch_directed(isomc_t *h, const isomc_sdf_node *progs, const uint32_t *n_nodes, uint32_t n_chunks);
 int32_t isomc_batch_offsets(isomc_t *h, uint64_t *v_offsets, uint64_t *t_offsets);
 /* the same for DENSE chunks (voxel worlds cut into size^3 chunks): `n_chunks` lattices of size * size * (size + 1) f32 back to back.
  * Device-resident lattices are used in place and must fill the handle (n_chunks == the handle's capacity); host lattices are

@@ -238,7 +238,8 @@ class PointCloud : public MarchingCubes {
 // size read-back; chunk b of a batch is delivered to extractors[b] exactly as MarchingCubes(size).extract(sources[b], ..) would.
 class BatchedMarchingCubes {
   public:
-    BatchedMarchingCubes(uint32_t size, uint32_t n_chunks, int32_t device = 0) : n_chunks_(n_chunks) {
+    BatchedMarchingCubes(uint32_t size, uint32_t n_chunks, int32_t device = 0, Distance distance = Distance::Signed)
+        : n_chunks_(n_chunks), distance_(distance) {
         int32_t rc = isomc_batch_create(size, n_chunks, device, &h_);
         if (rc) throw Error(rc, isomc_last_error(nullptr));
     }
@@ -262,18 +263,21 @@ class BatchedMarchingCubes {
     void extract_programs(const std::vector<isomc_sdf_node> &flat, const std::vector<uint32_t> &n_nodes, const std::vector<Extractor *> &extractors) {
         const uint32_t b = (uint32_t)n_nodes.size();
         if (b < 1 || b > n_chunks_ || extractors.size() != b) throw Error(ISOMC_ERR_BAD_ARG, "batch size / extractor count mismatch");
-        check(isomc_extract_sdf_batch(h_, flat.data(), n_nodes.data(), b));
+        check(distance_ == Distance::Directed ? isomc_extract_sdf_batch_directed(h_, flat.data(), n_nodes.data(), b)
+                                              : isomc_extract_sdf_batch(h_, flat.data(), n_nodes.data(), b));
         deliver(b, extractors);
     }
     // dense chunks: `n` host lattices of size * size * (size + 1) floats back to back (a voxel world cut into chunks)
     void extract_grids(const float *lattices, uint32_t n, const std::vector<Extractor *> &extractors) {
         if (n < 1 || n > n_chunks_ || extractors.size() != n) throw Error(ISOMC_ERR_BAD_ARG, "batch size / extractor count mismatch");
+        if (distance_ == Distance::Directed) throw Error(ISOMC_ERR_BAD_ARG, "a lattice of scalars has no Directed distances");
         check(isomc_extract_grid_batch_host(h_, lattices, n));
         deliver(n, extractors);
     }
     // the same with the handle's whole capacity of lattices already in device memory (used in place)
     void extract_device_grids(const float *d_lattices, const std::vector<Extractor *> &extractors) {
         if (extractors.size() != n_chunks_) throw Error(ISOMC_ERR_BAD_ARG, "a device batch fills the handle: one extractor per chunk");
+        if (distance_ == Distance::Directed) throw Error(ISOMC_ERR_BAD_ARG, "a lattice of scalars has no Directed distances");
         check(isomc_extract_grid_batch_device(h_, d_lattices, n_chunks_));
         deliver(n_chunks_, extractors);
     }
@@ -301,6 +305,7 @@ class BatchedMarchingCubes {
     void check(int32_t rc) { if (rc) throw Error(rc, isomc_last_error(h_)); }
     isomc_t *h_ = nullptr;
     uint32_t n_chunks_;
+    Distance distance_;
 };
 
 // ---- one extract over several GPUs of the box: z-slabs, one exchange of 3 x u64 per rank (peer stores over

@@ -54,6 +54,7 @@ SIGNATURES = {
     "isomc_extract_grid_host_to": (_I32, [_P, _P, _P, _U64, _P, _U64]),
     "isomc_batch_create": (_I32, [_U32, _U32, _I32, C.POINTER(_P)]),
     "isomc_extract_sdf_batch": (_I32, [_P, _P, _P, _U32]),
+    "isomc_extract_sdf_batch_directed": (_I32, [_P, _P, _P, _U32]),
     "isomc_batch_offsets": (_I32, [_P, _P, _P]),
     "isomc_extract_grid_batch_device": (_I32, [_P, _P, _U32]),
     "isomc_extract_grid_batch_host": (_I32, [_P, _P, _U32]),

@@ -62,11 +62,14 @@ class BatchedMarchingCubes:
     the launch and synchronisation latency of a 32^3-sized extract.  Each chunk's mesh is byte for byte what
     `MarchingCubes(size).extract_device(source)` + `copy_out()` returns (indices relative to the chunk's own first vertex)."""
 
-    def __init__(self, size, n_chunks=64, device=0):
+    def __init__(self, size, n_chunks=64, device=0, distance="signed"):
         import ctypes as C
         from . import _lib
         if n_chunks < 1:
             raise ValueError("n_chunks must be >= 1")
+        if distance not in ("signed", "directed"):
+            raise ValueError("distance must be 'signed' or 'directed'")
+        self.distance = distance  # 'directed' = MarchingCubes<Directed> per chunk (implicit sources; a lattice holds scalars)
         self.size, self.n_chunks = int(size), int(n_chunks)
         self._lib = _lib.load()
         self._h = C.c_void_p()
@@ -94,14 +97,9 @@ class BatchedMarchingCubes:
             raise ValueError("a batch holds 1..%d chunks, got %d" % (self.n_chunks, len(progs)))
         flat = np.concatenate(progs)
         n_nodes = np.asarray([len(p) for p in progs], np.uint32)
-        _lib.check(self._lib.isomc_extract_sdf_batch(self._h, flat.ctypes.data, n_nodes.ctypes.data, len(progs)), self._h)
-        v, t, a = C.c_uint64(), C.c_uint64(), C.c_uint64()
-        _lib.check(self._lib.isomc_counts(self._h, C.byref(v), C.byref(t), C.byref(a)), self._h)
-        xyz, idx = np.empty(3 * v.value, np.float32), np.empty(3 * t.value, np.uint32)
-        _lib.check(self._lib.isomc_copy_out(self._h, xyz.ctypes.data, idx.ctypes.data), self._h)
-        vo, to = np.zeros(self.n_chunks + 1, np.uint64), np.zeros(self.n_chunks + 1, np.uint64)
-        _lib.check(self._lib.isomc_batch_offsets(self._h, vo.ctypes.data, to.ctypes.data), self._h)
-        return xyz, idx, vo[:len(progs) + 1], to[:len(progs) + 1]
+        entry = self._lib.isomc_extract_sdf_batch_directed if self.distance == "directed" else self._lib.isomc_extract_sdf_batch
+        _lib.check(entry(self._h, flat.ctypes.data, n_nodes.ctypes.data, len(progs)), self._h)
+        return self._results(len(progs))
 
     def _results(self, n):
         import ctypes as C
@@ -118,6 +116,8 @@ class BatchedMarchingCubes:
     def extract_grids(self, lattices):
         """Dense chunks: `lattices` = a float32 array of shape (n, size + 1, size, size) on the host (n <= n_chunks), or a CUDA
         tensor of exactly n_chunks lattices (used in place).  Returns (xyz, idx, v_offsets, t_offsets) like extract_batch."""
+        if self.distance == "directed":
+            raise TypeError("a lattice of scalars has no Directed distances")
         import numpy as np
         from . import _lib
         per = self.size * self.size * (self.size + 1)

@@ -257,7 +257,7 @@ int32_t launch_emit_chunk(isomc *h, uint32_t c, cudaStream_t st, int bps = 0) {
     }
     /* one kernel: edge ids, vertex positions and triangles of the chunk's active cells */
     if (h->kind == SRC_SDF_BATCH)
-        CU(h, isomc_launch_emit_list_sdf_batch(g, h->d_progs, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
+        CU(h, isomc_launch_emit_list_sdf_batch(g, h->d_progs, h->directed, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
                                                h->cap_v, h->cap_t, h->list_marks + c, h->list_marks + c + 1, h->sms, st, bps));
     else if (h->kind == SRC_GRID)
         CU(h, isomc_launch_emit_list_grid(g, h->d_grid, h->L, h->etab, h->rowV, h->rowT, h->layerTot, h->vofs, h->xyz, h->idx,
@@ -277,7 +277,7 @@ int32_t launch_sign_chunk(isomc *h, uint32_t c, cudaStream_t st, int bps = 0) {
     const Geo &g = h->g;
     const uint32_t l0 = h->chunk_l[c], l1 = h->chunk_l[c + 1];
     const uint32_t row0 = (c == 0 ? 0u : l0 + 1) * g.N, row1 = (l1 + 1) * g.N;
-    if (h->kind == SRC_SDF_BATCH) CU(h, isomc_launch_sign_sdf_batch(g, h->d_progs, h->signs, row0, row1, h->sms, st));
+    if (h->kind == SRC_SDF_BATCH) CU(h, isomc_launch_sign_sdf_batch(g, h->d_progs, h->directed, h->signs, row0, row1, h->sms, st));
     else if (h->kind == SRC_GRID) CU(h, isomc_launch_sign_grid(g, h->d_grid, h->signs, row0, row1, h->sms, bps ? bps : 8, st));
     else CU(h, isomc_launch_sign_sdf(g, h->prog, h->directed, h->signs, row0, row1, h->sms, bps ? bps : 8, st));
     h->stats.kernel_launches += 1;
@@ -1019,7 +1019,7 @@ int32_t isomc_batch_create(uint32_t size, uint32_t n_chunks, int32_t device, iso
     return create_impl(size, 0, size, device, out, n_chunks);
 }
 
-int32_t isomc_extract_sdf_batch(isomc_t *h, const isomc_sdf_node *progs, const uint32_t *n_nodes, uint32_t n_chunks) {
+static int32_t extract_sdf_batch_impl(isomc_t *h, const isomc_sdf_node *progs, const uint32_t *n_nodes, uint32_t n_chunks, bool directed) {
     if (!h) return ISOMC_ERR_BAD_ARG;
     if (!h->batch) return fail(h, ISOMC_ERR_BAD_ARG, "not a batch handle (isomc_batch_create)");
     if (!progs || !n_nodes || n_chunks < 1 || n_chunks > h->batch)
@@ -1033,20 +1033,28 @@ int32_t isomc_extract_sdf_batch(isomc_t *h, const isomc_sdf_node *progs, const u
             rc = validate_program(h, p, n_nodes[b], &h->h_progs[b]);
             if (rc) return rc;
             p += n_nodes[b];
-        } else { /* unused lattice: a field that is positive everywhere has no surface */
-            memset(&h->h_progs[b], 0, sizeof(SdfProgram));
-            h->h_progs[b].nodes[0].op = ISOMC_SDF_SPHERE;
-            h->h_progs[b].nodes[0].a = -1.0f;
-            h->h_progs[b].n = 1;
+        } else { /* unused lattice: a unit sphere far below the origin -- positive everywhere, in every component too */
+            static const isomc_sdf_node pad[3] = {{ISOMC_SDF_TRANSLATE_PUSH, -10.0f, -10.0f, -10.0f}, {ISOMC_SDF_SPHERE, 1.0f, 0.0f, 0.0f},
+                                                  {ISOMC_SDF_TRANSLATE_POP, 0.0f, 0.0f, 0.0f}};
+            rc = validate_program(h, pad, 3, &h->h_progs[b]);
+            if (rc) return rc;
         }
     }
     CU(h, cudaMemcpyAsync(h->d_progs, h->h_progs, h->batch * sizeof(SdfProgram), cudaMemcpyHostToDevice, h->stream));
-    h->kind = SRC_SDF_BATCH; h->d_grid = nullptr; h->directed = false;
+    h->kind = SRC_SDF_BATCH; h->d_grid = nullptr; h->directed = directed;
     h->batch_used = n_chunks;
     h->batch_call = true;
     rc = enqueue_full(h);
     h->batch_call = false;
     return rc ? rc : isomc_finish(h);
+}
+
+int32_t isomc_extract_sdf_batch(isomc_t *h, const isomc_sdf_node *progs, const uint32_t *n_nodes, uint32_t n_chunks) {
+    return extract_sdf_batch_impl(h, progs, n_nodes, n_chunks, false);
+}
+/* MarchingCubes<Directed> per chunk (isomc_extract_sdf_directed) */
+int32_t isomc_extract_sdf_batch_directed(isomc_t *h, const isomc_sdf_node *progs, const uint32_t *n_nodes, uint32_t n_chunks) {
+    return extract_sdf_batch_impl(h, progs, n_nodes, n_chunks, true);
 }
 
 /* the same for dense chunks: the handle's `n_chunks` lattices (size * size * (size + 1) f32 each) back to back in device memory --

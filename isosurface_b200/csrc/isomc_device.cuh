@@ -402,30 +402,43 @@ struct SdfBatchSrc {
 };
 
 /* MarchingCubes<Directed> over an implicit tree (reference src/distance.rs:72-104): outside iff any component > 0,
- * crossings interpolated from the component along the edge's own axis */
+ * crossings interpolated from the component along the edge's own axis.  The sampling members of a source with a vec() */
+#define ISOMC_VECTOR_EDGE_SAMPLES                                                                                                   \
+    /* value for the sign test: positive iff some component is positive (NaN components never are) */                              \
+    __device__ __forceinline__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {                                  \
+        const Vec3f v = vec(g, x, y, lz);                                                                                           \
+        return (v.x > 0.0f || v.y > 0.0f || v.z > 0.0f) ? 1.0f : -1.0f;                                                            \
+    }                                                                                                                               \
+    static __device__ __forceinline__ float comp(const Vec3f &v, uint32_t axis) { return axis == 0 ? v.x : axis == 1 ? v.y : v.z; } \
+    __device__ __forceinline__ void pair(const Geo &g, uint32_t ux, uint32_t uy, uint32_t uz, uint32_t vx, uint32_t vy, uint32_t vz, \
+                                         uint32_t axis, float &a, float &b) const {                                                 \
+        a = comp(vec(g, ux, uy, uz), axis);                                                                                         \
+        b = comp(vec(g, vx, vy, vz), axis);                                                                                         \
+    }                                                                                                                               \
+    __device__ __forceinline__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n6, bool n10, float &a5, \
+                                            float &b5, float &a6, float &b6, float &a10, float &b10) const {                       \
+        const Vec3f s6 = vec(g, x + 1, y + 1, lz + 1);                                                                              \
+        a5 = n5 ? vec(g, x + 1, y, lz + 1).y : 0.0f; b5 = s6.y;                                                                     \
+        a6 = s6.x; b6 = n6 ? vec(g, x, y + 1, lz + 1).x : 0.0f;                                                                     \
+        a10 = n10 ? vec(g, x + 1, y + 1, lz).z : 0.0f; b10 = s6.z;                                                                  \
+    }
+
 struct SdfDirSrc {
     SdfProgram prog;
     __device__ __forceinline__ Vec3f vec(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
         return sdf_eval_vec(prog, __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv), __fmul_rn((float)geo_z(g, lz), g.inv));
     }
-    /* value for the sign test: positive iff some component is positive (NaN components never are) */
-    __device__ __forceinline__ float at(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
-        const Vec3f v = vec(g, x, y, lz);
-        return (v.x > 0.0f || v.y > 0.0f || v.z > 0.0f) ? 1.0f : -1.0f;
+    ISOMC_VECTOR_EDGE_SAMPLES
+};
+
+/* ... and over the B trees of a batch */
+struct SdfBatchDirSrc {
+    const SdfProgram *progs;
+    __device__ __forceinline__ Vec3f vec(const Geo &g, uint32_t x, uint32_t y, uint32_t lz) const {
+        const uint32_t b = geo_chunk(g, lz);
+        return sdf_eval_vec(progs[b], __fmul_rn((float)x, g.inv), __fmul_rn((float)y, g.inv), __fmul_rn((float)(lz - b * g.zper), g.inv));
     }
-    static __device__ __forceinline__ float comp(const Vec3f &v, uint32_t axis) { return axis == 0 ? v.x : axis == 1 ? v.y : v.z; }
-    __device__ __forceinline__ void pair(const Geo &g, uint32_t ux, uint32_t uy, uint32_t uz, uint32_t vx, uint32_t vy, uint32_t vz,
-                                         uint32_t axis, float &a, float &b) const {
-        a = comp(vec(g, ux, uy, uz), axis);
-        b = comp(vec(g, vx, vy, vz), axis);
-    }
-    __device__ __forceinline__ void corner6(const Geo &g, uint32_t x, uint32_t y, uint32_t lz, bool n5, bool n6, bool n10, float &a5,
-                                            float &b5, float &a6, float &b6, float &a10, float &b10) const {
-        const Vec3f s6 = vec(g, x + 1, y + 1, lz + 1);
-        a5 = n5 ? vec(g, x + 1, y, lz + 1).y : 0.0f; b5 = s6.y;
-        a6 = s6.x; b6 = n6 ? vec(g, x, y + 1, lz + 1).x : 0.0f;
-        a10 = n10 ? vec(g, x + 1, y + 1, lz).z : 0.0f; b10 = s6.z;
-    }
+    ISOMC_VECTOR_EDGE_SAMPLES
 };
 
 #endif

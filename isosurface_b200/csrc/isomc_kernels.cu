@@ -404,9 +404,11 @@ cudaError_t isomc_launch_chunk_bases(uint32_t n, unsigned long long *totals, con
     k_chunk_bases<<<1, 256, 0, st>>>(n, totals, list_ctr, chunkV, chunkT);
     return cudaGetLastError();
 }
-cudaError_t isomc_launch_sign_sdf_batch(const Geo &g, const SdfProgram *d_progs, uint32_t *signs, uint32_t row0, uint32_t row1, int sms,
-                                        cudaStream_t st) {
-    k_sign<SdfBatchSrc><<<grid_for((uint64_t)(row1 - row0), sms, 8, 8), 256, 0, st>>>(SdfBatchSrc{d_progs}, g, signs, row0, row1);
+cudaError_t isomc_launch_sign_sdf_batch(const Geo &g, const SdfProgram *d_progs, bool directed, uint32_t *signs, uint32_t row0,
+                                        uint32_t row1, int sms, cudaStream_t st) {
+    const uint32_t grid = grid_for((uint64_t)(row1 - row0), sms, 8, 8);
+    if (directed) k_sign<SdfBatchDirSrc><<<grid, 256, 0, st>>>(SdfBatchDirSrc{d_progs}, g, signs, row0, row1);
+    else k_sign<SdfBatchSrc><<<grid, 256, 0, st>>>(SdfBatchSrc{d_progs}, g, signs, row0, row1);
     return cudaGetLastError();
 }
 cudaError_t isomc_launch_slab_bases(const unsigned long long *gathered, uint32_t rank, uint32_t ghost, uint32_t *vofs,

@@ -195,10 +195,12 @@ cudaError_t isomc_launch_emit_list_grid(const Geo &g, const float *d_grid, const
                             sms, st, grid_bps);
 }
 
-cudaError_t isomc_launch_emit_list_sdf_batch(const Geo &g, const SdfProgram *d_progs, const ListBufs &L, const EmitTab *tab,
+cudaError_t isomc_launch_emit_list_sdf_batch(const Geo &g, const SdfProgram *d_progs, bool directed, const ListBufs &L, const EmitTab *tab,
                                              const uint32_t *rowPV, const uint32_t *rowPT, const unsigned long long *layerTot,
                                              const uint32_t *vofs, float *xyz, uint32_t *idx, uint64_t cap_v, uint64_t cap_t,
                                              const uint32_t *blk_first, const uint32_t *blk_end, int sms, cudaStream_t st, int grid_bps) {
+    if (directed)
+        return launch_emit_list(SdfBatchDirSrc{d_progs}, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end, sms, st, grid_bps);
     return launch_emit_list(SdfBatchSrc{d_progs}, g, L, tab, rowPV, rowPT, layerTot, vofs, xyz, idx, cap_v, cap_t, blk_first, blk_end, sms, st, grid_bps);
 }
 

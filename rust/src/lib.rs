@@ -35,6 +35,7 @@ extern "C" {
     // many chunks per call
     fn isomc_batch_create(size: u32, n_chunks: u32, device: i32, out: *mut *mut isomc_t) -> i32;
     fn isomc_extract_sdf_batch(h: *mut isomc_t, progs: *const isomc_sdf_node, n_nodes: *const u32, n_chunks: u32) -> i32;
+    fn isomc_extract_sdf_batch_directed(h: *mut isomc_t, progs: *const isomc_sdf_node, n_nodes: *const u32, n_chunks: u32) -> i32;
     fn isomc_batch_offsets(h: *mut isomc_t, v_offsets: *mut u64, t_offsets: *mut u64) -> i32;
     fn isomc_extract_grid_batch_host(h: *mut isomc_t, h_lattices: *const f32, n_chunks: u32) -> i32;
     // z-slabs: one rank per process (the host brings the exchange) ...
@@ -142,16 +143,24 @@ pub trait Distance {
     #[doc(hidden)] unsafe fn extract_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
     /// ... and the one behind `PointCloud<D>`
     #[doc(hidden)] unsafe fn points_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32;
+    /// ... and the one behind `BatchedMarchingCubes<D>`
+    #[doc(hidden)] unsafe fn extract_sdf_batch(h: *mut isomc_t, progs: *const isomc_sdf_node, n_nodes: *const u32, n_chunks: u32) -> i32;
 }
 pub struct Signed;
 pub struct Directed;
 impl Distance for Signed {
     unsafe fn extract_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32 { isomc_extract_sdf(h, prog, n_nodes) }
     unsafe fn points_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32 { isomc_points_sdf(h, prog, n_nodes) }
+    unsafe fn extract_sdf_batch(h: *mut isomc_t, progs: *const isomc_sdf_node, n_nodes: *const u32, n_chunks: u32) -> i32 {
+        isomc_extract_sdf_batch(h, progs, n_nodes, n_chunks)
+    }
 }
 impl Distance for Directed {
     unsafe fn extract_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32 { isomc_extract_sdf_directed(h, prog, n_nodes) }
     unsafe fn points_sdf(h: *mut isomc_t, prog: *const isomc_sdf_node, n_nodes: u32) -> i32 { isomc_points_sdf_directed(h, prog, n_nodes) }
+    unsafe fn extract_sdf_batch(h: *mut isomc_t, progs: *const isomc_sdf_node, n_nodes: *const u32, n_chunks: u32) -> i32 {
+        isomc_extract_sdf_batch_directed(h, progs, n_nodes, n_chunks)
+    }
 }
 
 /// `MarchingCubes<D: Distance>` as in the reference (src/marching_cubes.rs:38-43); `MarchingCubes::<Signed>::new(size)` and
@@ -266,13 +275,13 @@ impl<D: Distance> PointCloud<D> {
 /// Many chunks per call (the crate's usage model is one `MarchingCubes::new(size).extract(..)` per chunk,
 /// reference src/marching_cubes.rs:44-45, README.md:19): up to `n_chunks` trees through ONE kernel sequence and one size
 /// read-back.  Chunk b is delivered to `extractors[b]` exactly as a single `extract` of `sources[b]` would.
-pub struct BatchedMarchingCubes { h: *mut isomc_t, n_chunks: usize }
-impl BatchedMarchingCubes {
+pub struct BatchedMarchingCubes<D: Distance = Signed> { h: *mut isomc_t, n_chunks: usize, _d: std::marker::PhantomData<D> }
+impl<D: Distance> BatchedMarchingCubes<D> {
     pub fn new(size: usize, n_chunks: usize) -> Self {
         let mut h = std::ptr::null_mut();
         let rc = unsafe { isomc_batch_create(size as u32, n_chunks as u32, 0, &mut h) };
         assert!(rc == 0, "isomc_batch_create failed ({}): {:?}", rc, unsafe { std::ffi::CStr::from_ptr(isomc_last_error(std::ptr::null())) });
-        Self { h, n_chunks }
+        Self { h, n_chunks, _d: std::marker::PhantomData }
     }
     pub fn extract<S: DeviceSource, E: Extractor>(&mut self, sources: &[S], extractors: &mut [E]) {
         assert!(!sources.is_empty() && sources.len() <= self.n_chunks && sources.len() == extractors.len());
@@ -282,15 +291,7 @@ impl BatchedMarchingCubes {
             s.encode(&mut flat);
             n_nodes.push((flat.len() - before) as u32);
         }
-        self.check(unsafe { isomc_extract_sdf_batch(self.h, flat.as_ptr(), n_nodes.as_ptr(), n_nodes.len() as u32) });
-        self.deliver(extractors);
-    }
-    /// Dense chunks (a voxel world cut into `size`^3 chunks): `lattices` holds `extractors.len()` lattices of
-    /// `size * size * (size + 1)` samples back to back; chunk b goes to `extractors[b]`.
-    pub fn extract_grids<E: Extractor>(&mut self, lattices: &[f32], extractors: &mut [E]) {
-        let n = extractors.len();
-        assert!(n >= 1 && n <= self.n_chunks && lattices.len() % n == 0);
-        self.check(unsafe { isomc_extract_grid_batch_host(self.h, lattices.as_ptr(), n as u32) });
+        self.check(unsafe { D::extract_sdf_batch(self.h, flat.as_ptr(), n_nodes.as_ptr(), n_nodes.len() as u32) });
         self.deliver(extractors);
     }
     fn check(&self, rc: i32) {
@@ -310,7 +311,18 @@ impl BatchedMarchingCubes {
         }
     }
 }
-impl Drop for BatchedMarchingCubes { fn drop(&mut self) { unsafe { isomc_destroy(self.h); } } }
+/// a lattice holds scalars: dense chunks exist for `Signed` only
+impl BatchedMarchingCubes<Signed> {
+    /// Dense chunks (a voxel world cut into `size`^3 chunks): `lattices` holds `extractors.len()` lattices of
+    /// `size * size * (size + 1)` samples back to back; chunk b goes to `extractors[b]`.
+    pub fn extract_grids<E: Extractor>(&mut self, lattices: &[f32], extractors: &mut [E]) {
+        let n = extractors.len();
+        assert!(n >= 1 && n <= self.n_chunks && lattices.len() % n == 0);
+        self.check(unsafe { isomc_extract_grid_batch_host(self.h, lattices.as_ptr(), n as u32) });
+        self.deliver(extractors);
+    }
+}
+impl<D: Distance> Drop for BatchedMarchingCubes<D> { fn drop(&mut self) { unsafe { isomc_destroy(self.h); } } }
 
 /// One extract over several GPUs of the box: z-slabs, one exchange of 3 x u64 per rank on the extraction
 /// streams (peer stores over NVLink when the devices are peers, else an NCCL all-gather inside the library), global ids

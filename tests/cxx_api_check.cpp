@@ -66,6 +66,26 @@ int main() {
                 if (ov != bv[b] || oi != bi[b]) { std::printf("batched chunk %d differs from the single extract\n", b); return 1; }
             }
         }
+        // MarchingCubes<Directed> per chunk: chunk b = the single Directed extract of tree b
+        {
+            std::vector<TranslateT<Sphere>> chunks;
+            for (int b = 0; b < 3; ++b) chunks.push_back(Translate(0.4f + 0.1f * b, 0.5f, 0.5f, Sphere{0.25f}));
+            std::vector<std::vector<float>> bv(3);
+            std::vector<std::vector<uint32_t>> bi(3);
+            std::vector<IndexedVertices> sinks;
+            for (int b = 0; b < 3; ++b) sinks.emplace_back(bv[b], bi[b]);
+            std::vector<Extractor *> ptrs;
+            for (auto &sk : sinks) ptrs.push_back(&sk);
+            BatchedMarchingCubes batch(32, 4, 0, Distance::Directed);
+            batch.extract(chunks, ptrs);
+            MarchingCubes one(32, 0, Distance::Directed);
+            for (int b = 0; b < 3; ++b) {
+                std::vector<float> ov; std::vector<uint32_t> oi;
+                IndexedVertices os(ov, oi);
+                one.extract(chunks[b], os);
+                if (ov != bv[b] || oi != bi[b]) { std::printf("batched Directed chunk %d differs from the single extract\n", b); return 1; }
+            }
+        }
         // dense chunks through the same batch handle: chunk b = the host-grid extract of lattice b
         {
             const uint32_t n = 24, B = 3;

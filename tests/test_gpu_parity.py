@@ -705,6 +705,26 @@ def test_batched_chunks_match_single_extracts(iso, oracle):
         iso.BatchedMarchingCubes(1, n_chunks=4)
 
 
+def test_batched_directed_chunks_match_oracle(iso, oracle):
+    """isomc_extract_sdf_batch_directed: MarchingCubes<Directed> per chunk through one kernel sequence; every chunk = the oracle's
+    Directed mesh of that tree (incl. a partly filled batch: the padding lattices must stay empty for vector distances too)"""
+    for size, cap in ((24, 5), (33, 3)):
+        names = ["sphere03", "torus", "csgA", "csgB", "sphere05_origin"][:cap]
+        want = [oracle.extract_sdf_directed(size, oracle_prog(n)) for n in names]
+        drv = iso.BatchedMarchingCubes(size, n_chunks=cap + 2, distance="directed")
+        for _ in range(2):
+            xyz, idx, vo, to = drv.extract_batch([iso.Sampler(iso_source(n)) for n in names])
+            assert len(vo) == cap + 1
+            for b in range(cap):
+                oxyz, oidx, _ = want[b]
+                cx, ci = xyz[3 * int(vo[b]):3 * int(vo[b + 1])], idx[3 * int(to[b]):3 * int(to[b + 1])]
+                assert mesh_diff(cx, ci, oxyz, oidx, POS_TOL) == "", (size, names[b])
+            assert len(xyz) == 3 * int(vo[cap]) and len(idx) == 3 * int(to[cap])  # nothing in the padding lattices
+        with pytest.raises(TypeError):
+            drv.extract_grids(np.zeros((1, size + 1, size, size), np.float32))
+        drv.close()
+
+
 def test_batched_dense_chunks_match_single_extracts(iso, oracle):
     """isomc_extract_grid_batch_{host,device}: dense size^3 chunks (a voxel world cut into chunks) through one kernel sequence; every
     chunk's mesh is the oracle's mesh of that lattice alone, incl. empty chunks, a partly filled host batch and handle reuse"""
