@@ -51,6 +51,9 @@ lat = np.random.default_rng(5).standard_normal((4, 21, 20, 20)).astype(np.float3
 print("batch grids", [int(v) for v in gdrv.extract_grids(torch.from_numpy(lat).cuda())[2]],
       [int(v) for v in gdrv.extract_grids(lat[:3])[2]])
 gdrv.close()
+ddrv = iso.BatchedMarchingCubes(24, n_chunks=4, distance="directed")  # MarchingCubes<Directed> per chunk, one padding lattice
+print("batch directed", [int(v) for v in ddrv.extract_batch(srcs[:3])[2]])
+ddrv.close()
 lib = _lib.load()
 slabs = [SlabMarchingCubes(size, r, world) for r in range(world)]
 boxes = (C.c_void_p * world)()
